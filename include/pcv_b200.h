@@ -1,0 +1,156 @@
+/*
+ * pcv_b200.h — C ABI of libpcv_b200.so: the B200 (sm_100a) eval-mode convolution path for pytorchcv models.
+ *
+ * The reference (osmr/pytorchcv) has no FFI: its "operator API" for this path is the nn.Module.forward of the
+ * blocks in pytorchcv/models/common/{conv,att,activ,norm}.py, which issue eager torch ops.  Each entry point below
+ * replaces the torch-op sequence of one such forward; the reference location is cited per function.
+ *
+ * Conventions
+ *  - Every function returns 0 on success, a negative pcv_status otherwise; pcv_last_error() gives the message
+ *    (thread-local).  Nothing throws across the ABI; nothing allocates device memory (callers own all buffers).
+ *  - All pointers are DEVICE pointers unless a name ends in _host.  Activations are NHWC ("pixels x channels")
+ *    with an explicit channel pitch (elements between consecutive pixels; 0 means "= channels"), so a tensor can
+ *    be a channel slice of a wider buffer (torch.cat on dim 1 becomes a write at a channel offset).
+ *  - `dtype` selects the arithmetic tier: PCV_BF16 = bf16 storage, fp32 accumulate/epilogue (tcgen05 tensor cores
+ *    for dense/grouped conv); PCV_F32 = fp32 storage and true fp32 FMA (the <=1e-4 tier).
+ *  - `plan`: when non-NULL the op is RECORDED into the plan (stream ignored) and runs on every pcv_plan_run();
+ *    when NULL it is launched immediately on `stream`.  Kernels never synchronise the host.
+ */
+#ifndef PCV_B200_H
+#define PCV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define PCV_API __attribute__((visibility("default")))
+#else
+#define PCV_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pcv_plan pcv_plan;  /* opaque: a flat list of fused-kernel launches */
+typedef void* pcv_stream;          /* cudaStream_t */
+
+enum pcv_status {
+  PCV_OK = 0,
+  PCV_ERR_INVALID = -1,      /* bad argument / unsupported shape (the AssertionError / ValueError analogue) */
+  PCV_ERR_UNSUPPORTED = -2,  /* valid in the reference but outside this path (NotImplementedError analogue) */
+  PCV_ERR_CUDA = -3,         /* a CUDA runtime / driver call failed */
+  PCV_ERR_NO_DEVICE = -4     /* no sm_100 device: there is no CPU fallback */
+};
+
+enum pcv_dtype { PCV_BF16 = 0, PCV_F32 = 1 };
+
+/* activations of pytorchcv/models/common/activ.py:188-222 (create_activation_layer) */
+enum pcv_act {
+  PCV_ACT_NONE = 0,
+  PCV_ACT_RELU = 1,     /* nn.ReLU     activ.py:50-64   */
+  PCV_ACT_RELU6 = 2,    /* nn.ReLU6    activ.py:67-81   */
+  PCV_ACT_SIGMOID = 3,  /* nn.Sigmoid  activ.py:123-132 */
+  PCV_ACT_SWISH = 4,    /* Swish       activ.py:16-21   */
+  PCV_ACT_HSWISH = 5,   /* HSwish      activ.py:33-47   */
+  PCV_ACT_HSIGMOID = 6  /* HSigmoid    activ.py:24-30   */
+};
+
+enum pcv_conv_flags {
+  PCV_CONV_OUT_F32 = 1,      /* bf16 tier only: store the result as fp32 (classifier logits) */
+  PCV_CONV_FORCE_SIMT = 2,   /* bf16 tier only: use the CUDA-core kernel (cross-check for the tcgen05 path) */
+  PCV_CONV_A_IM2COL = 4,     /* bf16 tier only: use the im2col TMA descriptor even for 1x1 stride-1 */
+  PCV_CONV_RES_F32_NCHW = 8  /* reserved */
+};
+
+/* One ConvBlock (conv.py:204-286): y = act(BN(conv2d(x)) [+ residual]).  Square kernels, symmetric padding. */
+typedef struct pcv_conv_desc {
+  int32_t N, H, W;        /* input batch and spatial size */
+  int32_t Cin, Cout;      /* channels (Cin is the logical count; buffers may be pitched wider) */
+  int32_t kh, kw;         /* kernel size */
+  int32_t stride, pad, dil;
+  int32_t groups;         /* 1 = dense, Cin = depthwise (conv.py:472), else grouped (resnext.py:44-55) */
+  int32_t act;            /* pcv_act applied AFTER the optional residual add (resnet.py:226-228) */
+  int32_t in_pitch;       /* channel pitch of x        (0 -> Cin)  */
+  int32_t out_pitch;      /* channel pitch of y        (0 -> Cout) */
+  int32_t res_pitch;      /* channel pitch of residual (0 -> Cout) */
+  int32_t flags;          /* pcv_conv_flags */
+} pcv_conv_desc;
+
+/* ---- library ---------------------------------------------------------------------------------------------- */
+PCV_API const char* pcv_last_error(void);
+PCV_API int pcv_version(void);
+/* sm major*10+minor of device `dev`, SM count, bytes of HBM; PCV_ERR_NO_DEVICE when there is no GPU. */
+PCV_API int pcv_device_info(int dev, int* sm_arch, int* sm_count, size_t* hbm_bytes);
+/* number of kernels this library has launched (eager or via plans) since load, for bench.py's gpu_launches */
+PCV_API int64_t pcv_launch_count(void);
+
+/* ---- weights: BN fold + repack (norm.py:34-50 folded into conv.py:250-259) ---------------- */
+/* Output sizes in bytes for the packed weight and the fp32 bias of `d` in tier `dtype`. */
+PCV_API int pcv_conv_packed_bytes(const pcv_conv_desc* d, int dtype, size_t* w_bytes, size_t* bias_bytes);
+/* w: fp32 [Cout, Cin/groups, kh, kw] (state_dict layout); conv_bias: fp32 [Cout] or NULL; bn_*: fp32 [Cout] or all
+ * NULL when the block has no BatchNorm.  Computes w' = w*g/sqrt(v+eps), b' = (bias-mean)*g/sqrt(v+eps)+beta. */
+PCV_API int pcv_pack_conv_weights(const pcv_conv_desc* d, int dtype, const float* w, const float* conv_bias,
+                          const float* bn_gamma, const float* bn_beta, const float* bn_mean, const float* bn_var,
+                          float eps, void* w_packed, float* bias_out, pcv_stream stream);
+
+/* ---- the hot path -------------------------------------------------------------------------------------------- */
+/* ConvBlock.forward (conv.py:278-286) + the unit's residual add and final activation (resnet.py:221-229,
+ * mobilenetv2.py:62-71) fused into one kernel.  residual may be NULL. */
+PCV_API int pcv_conv2d_bias_act(pcv_plan* plan, const pcv_conv_desc* d, int dtype, const void* x, const void* w_packed,
+                        const float* bias, const void* residual, void* y, pcv_stream stream);
+
+/* nn.MaxPool2d(k, stride, pad), -inf padding, floor mode (resnet.py:255-258, senet.py:154-157). */
+PCV_API int pcv_maxpool2d(pcv_plan* plan, int dtype, int N, int H, int W, int C, int k, int stride, int pad, const void* x,
+                  int in_pitch, void* y, int out_pitch, pcv_stream stream);
+
+/* nn.AdaptiveAvgPool2d(1) == nn.AvgPool2d(7) on a 7x7 map (resnet.py:316-318, att.py:72, deeplabv3.py:77):
+ * pooled[n, c] = mean over HW; fp32 accumulate.  out_dtype selects the storage of `pooled`. */
+PCV_API int pcv_global_avgpool(pcv_plan* plan, int dtype, int N, int HW, int C, const void* x, int in_pitch, void* pooled,
+                       int out_dtype, pcv_stream stream);
+
+/* SEBlock.forward (att.py:94-105) in three steps: squeeze = pcv_global_avgpool (fp32 out);
+ * excite: gate = out_act(W2 * mid_act(W1 * pooled + b1) + b2), W1 [Cmid, C], W2 [C, Cmid] fp32 (att.py:74-87);
+ *         `gate` must hold N*(C+Cmid) floats: [N, C] gates followed by [N, Cmid] scratch for the hidden layer;
+ * scale:  y = act(x * gate[n, c] + identity)   (seresnext.py:62-65; identity may be NULL, act may be NONE). */
+PCV_API int pcv_se_excite(pcv_plan* plan, int N, int C, int Cmid, const float* pooled, const float* w1, const float* b1,
+                  const float* w2, const float* b2, int mid_act, int out_act, float* gate, pcv_stream stream);
+PCV_API int pcv_se_scale_add_act(pcv_plan* plan, int dtype, int N, int HW, int C, const void* x, const float* gate,
+                         const void* identity, int act, void* y, pcv_stream stream);
+
+/* y = act(a + b), elementwise over N*HW*C (residual adds that could not be fused into a conv epilogue). */
+PCV_API int pcv_add_act(pcv_plan* plan, int dtype, size_t count, const void* a, const void* b, int act, void* y,
+                pcv_stream stream);
+
+/* ---- network edges ------------------------------------------------------------------------------------------- */
+/* Reference tensors are NCHW fp32.  Ingest pads channels with zeros up to c_pitch. */
+PCV_API int pcv_nchw_f32_to_nhwc(pcv_plan* plan, int dtype, int N, int C, int H, int W, const float* x, void* y,
+                         int c_pitch, pcv_stream stream);
+PCV_API int pcv_nhwc_to_nchw_f32(pcv_plan* plan, int dtype, int N, int C, int H, int W, const void* x, int c_pitch,
+                         float* y, pcv_stream stream);
+/* F.interpolate(mode="bilinear", align_corners=True) (deeplabv3.py:53,86).  Output is NHWC `dtype` with
+ * out_pitch, or NCHW fp32 when out_nchw_f32 != 0 (the tensor the reference returns). */
+PCV_API int pcv_bilinear_upsample_ac(pcv_plan* plan, int dtype, int N, int Hin, int Win, int C, const void* x, int in_pitch,
+                             int Hout, int Wout, void* y, int out_pitch, int out_nchw_f32, pcv_stream stream);
+
+/* ---- plans ---------------------------------------------------------------------------------------------------- */
+PCV_API int pcv_plan_create(pcv_plan** plan);
+PCV_API int pcv_plan_destroy(pcv_plan* plan);
+PCV_API int pcv_plan_num_ops(const pcv_plan* plan);
+/* kernels launched per pcv_plan_run */
+PCV_API int pcv_plan_num_launches(const pcv_plan* plan);
+/* Enqueue every recorded op on `stream` in order.  No host synchronisation. */
+PCV_API int pcv_plan_run(pcv_plan* plan, pcv_stream stream);
+/* Capture the plan into a CUDA graph (once) and replay it; falls back to an error, never to eager, on failure. */
+PCV_API int pcv_plan_graph_launch(pcv_plan* plan, pcv_stream stream);
+/* Per-op device time of one eager pass (CUDA events on `stream`, synchronises): fills ms[0..num_ops). */
+PCV_API int pcv_plan_profile(pcv_plan* plan, pcv_stream stream, float* ms_host, int capacity);
+/* Human-readable name of op i ("conv_tc 1x1 s1 256->64 bn=64", ...).  Pointer valid until plan destroy. */
+PCV_API const char* pcv_plan_op_name(const pcv_plan* plan, int i);
+/* Algorithmic FLOPs and HBM bytes of op i (SURVEY 8d formulas), for the roofline. */
+PCV_API int pcv_plan_op_cost(const pcv_plan* plan, int i, double* flops, double* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCV_B200_H */

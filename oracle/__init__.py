@@ -1,0 +1,3 @@
+"""ORACLE package — test infrastructure only (see ref_forward.py).  Never imported by pytorchcv_b200/."""
+from .ref_forward import oracle_forward, OracleUnsupported  # noqa: F401
+from .seeded import seeded_init, seeded_input  # noqa: F401

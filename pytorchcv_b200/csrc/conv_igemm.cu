@@ -1,0 +1,599 @@
+// Dense / grouped convolution as a tcgen05 implicit GEMM (bf16 in, fp32 accumulate in TMEM).
+//
+// Replaces, for one ConvBlock, the reference's  nn.Conv2d -> BatchNorm2d -> activation  sequence
+// (pytorchcv/models/common/conv.py:278-286) plus the unit-level  x + identity ; ReLU  (models/resnet.py:221-229):
+// BatchNorm is folded into the packed weights / bias, residual add and activation run in the epilogue.
+//
+// GEMM view:  D[m, n] = sum_k A[m, k] * B[n, k]
+//   m = output pixel (n_img, ho, wo) linearised, M = N*Ho*Wo        (BLOCK_M = 128 rows = 128 TMEM lanes)
+//   n = output channel                                                (BLOCK_N = 32 / 64 / 128 TMEM columns)
+//   k = (filter tap, input channel), 64 channels per k-block          (BLOCK_K = 64 bf16 = one 128-byte swizzle row)
+// A tiles come straight from the NHWC activation tensor through a TMA *im2col* descriptor (one instruction per
+// k-block: 128 pixels x 64 channels, halo and padding zero-filled by the TMA unit); 1x1 stride-1 convs use a plain
+// 2-D tiled descriptor.  B tiles come from the packed [Cout, taps*Cpad] weight matrix.  Both land in 128B-swizzled
+// shared memory and feed tcgen05.mma (M=128, N=BLOCK_N, K=16) issued by a single thread.
+//
+// Persistent, warp-specialised CTA (one per SM), 8 warps:
+//   warp 0  TMA producer (A+B ring of STAGES)          warp 1  MMA issuer (double-buffered TMEM accumulator)
+//   warp 2  TMEM allocator                              warp 3  residual prefetcher (TMA load into the staging tile)
+//   warps 4-7  epilogue: tcgen05.ld -> +bias (+residual) -> act -> bf16 -> swizzled staging smem -> TMA store
+// so the epilogue of tile i overlaps the main loop of tile i+1.
+#include "ptx.cuh"
+#include "runtime.h"
+
+namespace pcv {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_THREADS = 128;
+
+struct IgemmParams {
+  const float* bias;          // [round_up(Cout,128)] folded BN bias
+  void* out;                  // direct-store modes only
+  const __nv_bfloat16* res;   // direct-store modes only
+  int M, Cout;
+  int out_pitch, res_pitch;
+  int HoWo, Wo;
+  int stride, pad, dil, kw;
+  int cblocks;                // 64-channel blocks per filter tap
+  int num_kblocks;            // taps * cblocks
+  int tiles_m, tiles_n;
+  int act, has_res;
+  int a_mode;                 // 0: 2-D tiled [Cin, M]; 1: im2col 4-D
+  int out_mode;               // 0: TMA bf16 store; 1: direct bf16; 2: direct fp32
+  int grouped;                // 1: A channel window = n_tile*BLOCK_N (block-diagonal weights)
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
+  static constexpr int SUB_COLS = BN >= 64 ? 64 : BN;               // columns per staging sub-tile
+  static constexpr int SUB_BYTES = BLOCK_M * SUB_COLS * 2;          // one [128 x SUB_COLS] bf16 sub-tile
+  static constexpr int NSUB = BN / SUB_COLS;
+  static constexpr int STG_BYTES = BLOCK_M * BN * 2;                // one staging buffer
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_B = OFF_A + STAGES * A_STAGE_BYTES;
+  static constexpr int OFF_STG = OFF_B + STAGES * B_STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_STG + 2 * STG_BYTES;
+  static constexpr int NUM_BARS = 2 * STAGES + 8;
+  static constexpr int TOTAL = OFF_BAR + NUM_BARS * 8 + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;                    // slack for manual 1 KiB alignment
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case PCV_ACT_RELU: return fmaxf(v, 0.f);
+    case PCV_ACT_RELU6: return fminf(fmaxf(v, 0.f), 6.f);
+    case PCV_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+    case PCV_ACT_SWISH: return v / (1.f + __expf(-v));
+    case PCV_ACT_HSWISH: return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    case PCV_ACT_HSIGMOID: return fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    default: return v;
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+             const IgemmParams p) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint8_t* sA = smem + L::OFF_A;
+  uint8_t* sB = smem + L::OFF_B;
+  uint8_t* sStg = smem + L::OFF_STG;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* full = bars;                       // [STAGES]  TMA -> MMA
+  uint64_t* empty = bars + STAGES;             // [STAGES]  MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * STAGES;     // [2]       MMA -> epilogue
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]       epilogue -> MMA
+  uint64_t* stg_empty = tmem_empty + 2;        // [2]       epilogue -> residual prefetcher
+  uint64_t* res_full = stg_empty + 2;          // [2]       residual TMA -> epilogue
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.out_mode == 0) tma_prefetch_desc(&tmOut);
+    if (p.has_res && p.out_mode == 0) tma_prefetch_desc(&tmRes);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&stg_empty[i], 1);
+      mbar_init(&res_full[i], 1);
+    }
+    fence_mbar_init();
+    mbar_arrive(&stg_empty[0]);  // staging buffer 0 starts out free (buffer 1 is released by tile 0's epilogue)
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_tile = t / p.tiles_n;
+        const int n_tile = t - m_tile * p.tiles_n;
+        const int m0 = m_tile * BLOCK_M;
+        const int img = m0 / p.HoWo;
+        const int rem = m0 - img * p.HoWo;
+        const int ho = rem / p.Wo;
+        const int wo = rem - ho * p.Wo;
+        const int w0 = wo * p.stride - p.pad;
+        const int h0 = ho * p.stride - p.pad;
+        const int c_base = p.grouped ? n_tile * BN : 0;
+        int tap = 0, cb = 0, fr = 0, fs = 0;
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], A_STAGE_BYTES + L::B_STAGE_BYTES);
+          uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
+          if (p.a_mode == 1) {
+            tma_load_im2col_4d(&tmA, &full[stage], a_dst, c_base + cb * BLOCK_K, w0, h0, img,
+                               static_cast<uint16_t>(fs * p.dil), static_cast<uint16_t>(fr * p.dil));
+          } else {
+            tma_load_2d(&tmA, &full[stage], a_dst, c_base + cb * BLOCK_K, m0);
+          }
+          tma_load_2d(&tmB, &full[stage], sB + stage * L::B_STAGE_BYTES, kb * BLOCK_K, n_tile * BN);
+          if (++cb == p.cblocks) {
+            cb = 0;
+            ++tap;
+            if (++fs == p.kw) {
+              fs = 0;
+              ++fr;
+            }
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * L::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t a_desc = make_smem_desc(a_addr + k * 32, 128);
+            const uint64_t b_desc = make_smem_desc(b_addr + k * 32, 128);
+            umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // frees this smem stage once the MMAs above have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[buf]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp == 3) {
+    // ===================================== residual prefetcher =====================================
+    if (lane == 0 && p.has_res && p.out_mode == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int m_tile = t / p.tiles_n;
+        const int n_tile = t - m_tile * p.tiles_n;
+        mbar_wait(&stg_empty[buf], (it >> 1) & 1);
+        mbar_arrive_expect_tx(&res_full[buf], L::STG_BYTES);
+#pragma unroll
+        for (int sub = 0; sub < L::NSUB; ++sub)
+          tma_load_2d(&tmRes, &res_full[buf], sStg + buf * L::STG_BYTES + sub * L::SUB_BYTES,
+                      n_tile * BN + sub * L::SUB_COLS, m_tile * BLOCK_M);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue =====================================
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;       // accumulator row == output pixel within the tile
+    const int epi_tid = threadIdx.x - 128;
+    constexpr uint32_t ROW_BYTES = L::SUB_COLS * 2;
+    constexpr uint32_t SWZ_MASK = ROW_BYTES == 128 ? 7u : (ROW_BYTES == 64 ? 3u : 1u);
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m_tile = t / p.tiles_n;
+      const int n_tile = t - m_tile * p.tiles_n;
+      const int m0 = m_tile * BLOCK_M;
+      const int n0 = n_tile * BN;
+      uint8_t* stg = sStg + buf * L::STG_BYTES;
+
+      if (p.has_res && p.out_mode == 0) mbar_wait(&res_full[buf], acc_phase);
+      mbar_wait(&tmem_full[buf], acc_phase);
+      tc_fence_after();
+
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + j * 32, acc);
+        tmem_ld_wait();
+        float v[32];
+        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + j * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = __ldg(bias4 + i);
+          v[4 * i + 0] = __uint_as_float(acc[4 * i + 0]) + b.x;
+          v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b.y;
+          v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b.z;
+          v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b.w;
+        }
+        if (p.out_mode == 0) {
+          // staging sub-tile holding columns [j*32, j*32+32): row pitch ROW_BYTES, 16-byte chunks XOR-swizzled
+          const int col = j * 32;
+          uint8_t* sub = stg + (col / L::SUB_COLS) * L::SUB_BYTES;
+          const uint32_t row_off = row * ROW_BYTES + (col % L::SUB_COLS) * 2;
+          if (p.has_res) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t off = row_off + c * 16;
+              off ^= ((off >> 7) & SWZ_MASK) << 4;
+              const uint4 r = *reinterpret_cast<const uint4*>(sub + off);
+              v[8 * c + 0] += bf16lo(r.x);
+              v[8 * c + 1] += bf16hi(r.x);
+              v[8 * c + 2] += bf16lo(r.y);
+              v[8 * c + 3] += bf16hi(r.y);
+              v[8 * c + 4] += bf16lo(r.z);
+              v[8 * c + 5] += bf16hi(r.z);
+              v[8 * c + 6] += bf16lo(r.w);
+              v[8 * c + 7] += bf16hi(r.w);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t off = row_off + c * 16;
+            off ^= ((off >> 7) & SWZ_MASK) << 4;
+            uint4 o;
+            o.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]);
+            o.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+            o.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
+            o.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+            *reinterpret_cast<uint4*>(sub + off) = o;
+          }
+        } else {
+          // direct global stores: any Cout / pitch, bf16 or fp32 output (classifier logits, 21-class heads)
+          const int m = m0 + row;
+          if (m < p.M) {
+            const int ncol = min(32, p.Cout - (n0 + j * 32));
+            if (p.has_res) {
+              const __nv_bfloat16* rp = p.res + static_cast<size_t>(m) * p.res_pitch + n0 + j * 32;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < ncol) v[i] += __bfloat162float(rp[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+            if (p.out_mode == 2) {
+              float* op = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_pitch + n0 + j * 32;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < ncol) op[i] = v[i];
+            } else {
+              __nv_bfloat16* op =
+                  reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(m) * p.out_pitch + n0 + j * 32;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < ncol) op[i] = __float2bfloat16(v[i]);
+            }
+          }
+        }
+      }
+      // accumulator buffer fully read -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+
+      if (p.out_mode == 0) {
+        fence_proxy_async_smem();           // st.shared above -> visible to the TMA (async proxy)
+        named_bar_sync(1, EPI_THREADS);
+        if (epi_tid == 0) {
+#pragma unroll
+          for (int sub = 0; sub < L::NSUB; ++sub)
+            tma_store_2d(&tmOut, stg + sub * L::SUB_BYTES, n0 + sub * L::SUB_COLS, m0);
+          tma_store_commit();
+          tma_store_wait_read<1>();          // the store issued one tile ago has finished reading buffer buf^1
+          mbar_arrive(&stg_empty[buf ^ 1]);
+        }
+        named_bar_sync(1, EPI_THREADS);     // everyone may now overwrite staging buffer buf^1
+      }
+    }
+    if (p.out_mode == 0 && epi_tid == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// weight packing: fold BN, cast to bf16, lay out as [Cout, taps * cblocks * 64] (K-major, zero padded)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void igemm_pack_kernel(const float* __restrict__ w, const float* __restrict__ conv_bias,
+                                  const float* __restrict__ g, const float* __restrict__ b,
+                                  const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                  int Cout, int Cin, int groups, int taps, int cblocks, int grouped_bn,
+                                  __nv_bfloat16* __restrict__ wp, float* __restrict__ bias_out, int bias_len) {
+  const int kpad = taps * cblocks * BLOCK_K;
+  const size_t total = static_cast<size_t>(Cout) * kpad;
+  const int cin_g = Cin / groups;
+  const int cout_g = Cout / groups;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int o = static_cast<int>(idx / kpad);
+    const int kp = static_cast<int>(idx - static_cast<size_t>(o) * kpad);
+    const int tap = kp / (cblocks * BLOCK_K);
+    const int cc = kp - tap * (cblocks * BLOCK_K);
+    const float scale = g ? g[o] * rsqrtf(var[o] + eps) : 1.f;
+    float val = 0.f;
+    if (groups == 1) {
+      if (cc < Cin) val = w[(static_cast<size_t>(o) * Cin + cc) * taps + tap];
+    } else {
+      // block-diagonal: the A window of this output channel's N tile starts at input channel (o / bn) * bn
+      const int ci_abs = (o / grouped_bn) * grouped_bn + cc;
+      const int grp = o / cout_g;
+      const int ci = ci_abs - grp * cin_g;
+      if (ci >= 0 && ci < cin_g && cc < grouped_bn) val = w[(static_cast<size_t>(o) * cin_g + ci) * taps + tap];
+    }
+    wp[idx] = __float2bfloat16(val * scale);
+  }
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < bias_len; o += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (o < Cout) {
+      const float cb = conv_bias ? conv_bias[o] : 0.f;
+      if (g) {
+        const float scale = g[o] * rsqrtf(var[o] + eps);
+        v = (cb - mean[o]) * scale + b[o];
+      } else {
+        v = cb;
+      }
+    }
+    bias_out[o] = v;
+  }
+}
+
+static int pick_bn(const pcv_conv_desc& d) {
+  if (d.groups > 1) return 64;
+  if (d.Cout <= 32) return 32;
+  if (d.Cout <= 64) return 64;
+  return 128;
+}
+
+int igemm_supported(const pcv_conv_desc& d, std::string* why) {
+  auto no = [&](const char* m) {
+    if (why) *why = m;
+    return 0;
+  };
+  const int in_pitch = pitch_or(d.in_pitch, d.Cin);
+  if (in_pitch % 8 != 0) return no("input channel pitch must be a multiple of 8 (16-byte TMA stride)");
+  if (d.Cin % 8 != 0) return no("Cin must be a multiple of 8");
+  if (d.kh * d.kw > 49 || d.stride > 8) return no("kernel/stride out of range");
+  const int lo = -d.pad, up_w = d.pad - (d.kw - 1) * d.dil, up_h = d.pad - (d.kh - 1) * d.dil;
+  if (lo < -128 || up_w < -128 || up_h < -128 || up_w > 127 || up_h > 127) return no("im2col corner out of range");
+  if (d.groups > 1) {
+    const int cg_in = d.Cin / d.groups, cg_out = d.Cout / d.groups;
+    if (cg_in != cg_out) return no("grouped conv needs Cin/g == Cout/g");
+    if (64 % cg_out != 0 || d.Cout % 64 != 0) return no("grouped conv needs 64 % (C/g) == 0 and Cout % 64 == 0");
+  }
+  return 1;
+}
+
+int igemm_packed_bytes(const pcv_conv_desc& d, size_t* w_bytes, size_t* b_bytes) {
+  const int taps = d.kh * d.kw;
+  const int cblocks = d.groups > 1 ? 1 : ceil_div(d.Cin, BLOCK_K);
+  *w_bytes = static_cast<size_t>(d.Cout) * taps * cblocks * BLOCK_K * 2;
+  *b_bytes = static_cast<size_t>(round_up(d.Cout, 128)) * 4;
+  return PCV_OK;
+}
+
+int igemm_pack(const pcv_conv_desc& d, const float* w, const float* conv_bias, const float* g, const float* b,
+               const float* m, const float* v, float eps, void* w_packed, float* bias_out, cudaStream_t s) {
+  const int taps = d.kh * d.kw;
+  const int cblocks = d.groups > 1 ? 1 : ceil_div(d.Cin, BLOCK_K);
+  const size_t total = static_cast<size_t>(d.Cout) * taps * cblocks * BLOCK_K;
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 4096));
+  igemm_pack_kernel<<<blocks, 256, 0, s>>>(w, conv_bias, g, b, m, v, eps, d.Cout, d.Cin, d.groups, taps, cblocks, 64,
+                                           reinterpret_cast<__nv_bfloat16*>(w_packed), bias_out,
+                                           round_up(d.Cout, 128));
+  g_launches++;
+  PCV_CHECK_CUDA(cudaGetLastError());
+  return PCV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// tensor maps
+// ------------------------------------------------------------------------------------------------------------
+static int make_tiled_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                         uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): inner=%llu rows=%llu stride=%llu box=%ux%u", (int)r,
+                (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)row_stride_bytes, box_inner,
+                box_rows);
+  return PCV_OK;
+}
+
+static int make_im2col_4d(CUtensorMap* tm, const void* base, const pcv_conv_desc& d, int in_pitch) {
+  EncodeIm2colFn fn = encode_im2col_fn();
+  if (!fn) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeIm2col entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.N};
+  cuuint64_t strides[3] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)d.W * in_pitch * 2,
+                           (cuuint64_t)d.H * d.W * in_pitch * 2};
+  int lower[2] = {-d.pad, -d.pad};                                              // {W, H}
+  int upper[2] = {d.pad - (d.kw - 1) * d.dil, d.pad - (d.kh - 1) * d.dil};      // {W, H}
+  cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper,
+                  BLOCK_K, BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(PCV_ERR_CUDA, "cuTensorMapEncodeIm2col failed (%d): C=%d W=%d H=%d N=%d pitch=%d pad=%d k=%d dil=%d s=%d",
+                (int)r, d.Cin, d.W, d.H, d.N, in_pitch, d.pad, d.kw, d.dil, d.stride);
+  return PCV_OK;
+}
+
+struct IgemmOp : Op {
+  CUtensorMap tmA, tmB, tmOut, tmRes;
+  IgemmParams p;
+  int bn, grid;
+  cudaError_t launch(cudaStream_t s) override;
+};
+
+template <int BN, int STAGES>
+static cudaError_t launch_variant(const IgemmOp& op, cudaStream_t s) {
+  using L = SmemLayout<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::DYN_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  igemm_kernel<BN, STAGES><<<op.grid, NUM_THREADS, L::DYN_BYTES, s>>>(op.tmA, op.tmB, op.tmOut, op.tmRes, op.p);
+  return cudaGetLastError();
+}
+
+cudaError_t IgemmOp::launch(cudaStream_t s) {
+  g_launches++;
+  switch (bn) {
+    case 32: return launch_variant<32, 6>(*this, s);
+    case 64: return launch_variant<64, 6>(*this, s);
+    default: return launch_variant<128, 4>(*this, s);
+  }
+}
+
+int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float* bias, const void* res, void* y,
+               Op** out) {
+  std::string why;
+  if (!igemm_supported(d, &why)) return fail(PCV_ERR_UNSUPPORTED, "tcgen05 conv: %s", why.c_str());
+  const int Ho = conv_out(d.H, d.kh, d.stride, d.pad, d.dil);
+  const int Wo = conv_out(d.W, d.kw, d.stride, d.pad, d.dil);
+  PCV_REQUIRE(Ho > 0 && Wo > 0, "conv output is empty (H=%d W=%d k=%d)", d.H, d.W, d.kh);
+  const int in_pitch = pitch_or(d.in_pitch, d.Cin);
+  const int out_pitch = pitch_or(d.out_pitch, d.Cout);
+  const int res_pitch = pitch_or(d.res_pitch, d.Cout);
+  const int taps = d.kh * d.kw;
+  const bool grouped = d.groups > 1;
+
+  auto op = std::make_unique<IgemmOp>();
+  op->bn = pick_bn(d);
+  IgemmParams& p = op->p;
+  p.bias = bias;
+  p.out = y;
+  p.res = reinterpret_cast<const __nv_bfloat16*>(res);
+  p.M = d.N * Ho * Wo;
+  p.Cout = d.Cout;
+  p.out_pitch = out_pitch;
+  p.res_pitch = res_pitch;
+  p.HoWo = Ho * Wo;
+  p.Wo = Wo;
+  p.stride = d.stride;
+  p.pad = d.pad;
+  p.dil = d.dil;
+  p.kw = d.kw;
+  p.cblocks = grouped ? 1 : ceil_div(d.Cin, BLOCK_K);
+  p.num_kblocks = taps * p.cblocks;
+  p.tiles_m = ceil_div(p.M, BLOCK_M);
+  p.tiles_n = ceil_div(d.Cout, op->bn);
+  p.act = d.act;
+  p.has_res = res != nullptr;
+  p.grouped = grouped;
+  const bool pointwise = (taps == 1 && d.stride == 1 && d.pad == 0);
+  p.a_mode = (pointwise && !(d.flags & PCV_CONV_A_IM2COL)) ? 0 : 1;
+  const bool tma_out = !(d.flags & PCV_CONV_OUT_F32) && (out_pitch % 8 == 0) && (!res || res_pitch % 8 == 0) &&
+                       (reinterpret_cast<uintptr_t>(y) % 16 == 0) && (reinterpret_cast<uintptr_t>(res) % 16 == 0);
+  p.out_mode = tma_out ? 0 : ((d.flags & PCV_CONV_OUT_F32) ? 2 : 1);
+  PCV_REQUIRE(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(w) % 16 == 0,
+              "conv operands must be 16-byte aligned");
+
+  int rc;
+  if (p.a_mode == 1) {
+    rc = make_im2col_4d(&op->tmA, x, d, in_pitch);
+  } else {
+    rc = make_tiled_2d(&op->tmA, x, d.Cin, p.M, (uint64_t)in_pitch * 2, BLOCK_K, BLOCK_M, CU_TENSOR_MAP_SWIZZLE_128B);
+  }
+  if (rc) return rc;
+  const uint64_t kpad = (uint64_t)taps * p.cblocks * BLOCK_K;
+  rc = make_tiled_2d(&op->tmB, w, kpad, d.Cout, kpad * 2, BLOCK_K, op->bn, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  const int sub_cols = op->bn >= 64 ? 64 : op->bn;
+  const CUtensorMapSwizzle oswz = sub_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  if (p.out_mode == 0) {
+    rc = make_tiled_2d(&op->tmOut, y, d.Cout, p.M, (uint64_t)out_pitch * 2, sub_cols, BLOCK_M, oswz);
+    if (rc) return rc;
+    if (res) {
+      rc = make_tiled_2d(&op->tmRes, res, d.Cout, p.M, (uint64_t)res_pitch * 2, sub_cols, BLOCK_M, oswz);
+      if (rc) return rc;
+    } else {
+      op->tmRes = op->tmOut;
+    }
+  } else {
+    op->tmOut = op->tmB;
+    op->tmRes = op->tmB;
+  }
+  op->grid = std::min(p.tiles_m * p.tiles_n, sm_count());
+
+  char nm[160];
+  snprintf(nm, sizeof nm, "conv_tc %dx%d s%d d%d g%d %d->%d @%dx%d bn=%d%s%s", d.kh, d.kw, d.stride, d.dil, d.groups,
+           d.Cin, d.Cout, d.H, d.W, op->bn, res ? " +res" : "", p.out_mode ? " direct" : "");
+  op->name = nm;
+  const double e = 2.0;
+  const double pin = (taps == 1 && d.stride > 1) ? (double)Ho * Wo : (double)d.H * d.W;
+  op->flops = 2.0 * p.M * d.Cout * (d.Cin / d.groups) * taps;
+  op->bytes = e * d.N * d.Cin * pin + ((d.flags & PCV_CONV_OUT_F32) ? 4.0 : e) * p.M * d.Cout +
+              (res ? e * p.M * d.Cout : 0.0) + e * d.Cout * (d.Cin / d.groups) * taps + 4.0 * d.Cout;
+  *out = op.release();
+  return PCV_OK;
+}
+
+}  // namespace pcv

@@ -1,0 +1,579 @@
+// Bandwidth-bound helpers of the eval path: pooling, SE squeeze/excite/scale, residual add, layout edges, bilinear.
+// All NHWC with 8-channel (16-byte bf16) vectors per lane; consecutive lanes own consecutive channel vectors.
+#include "ptx.cuh"
+#include "runtime.h"
+
+namespace pcv {
+
+__device__ __forceinline__ float misc_act(float v, int act) {
+  switch (act) {
+    case PCV_ACT_RELU: return fmaxf(v, 0.f);
+    case PCV_ACT_RELU6: return fminf(fmaxf(v, 0.f), 6.f);
+    case PCV_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case PCV_ACT_SWISH: return v / (1.f + expf(-v));
+    case PCV_ACT_HSWISH: return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) / 6.f;
+    case PCV_ACT_HSIGMOID: return fminf(fmaxf(v + 3.f, 0.f), 6.f) / 6.f;
+    default: return v;
+  }
+}
+
+template <typename T>
+struct V8;
+template <>
+struct V8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    f[0] = bf16lo(v.x); f[1] = bf16hi(v.x); f[2] = bf16lo(v.y); f[3] = bf16hi(v.y);
+    f[4] = bf16lo(v.z); f[5] = bf16hi(v.z); f[6] = bf16lo(v.w); f[7] = bf16hi(v.w);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
+    uint4 v;
+    v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+    v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = v;
+  }
+  static __device__ __forceinline__ float ld1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+};
+template <>
+struct V8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&f)[8]) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0];
+    const float4 b = reinterpret_cast<const float4*>(p)[1];
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&f)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+  static __device__ __forceinline__ float ld1(const float* p) { return *p; }
+  static __device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+};
+
+static inline int grid_for(long long items, int block = 256) {
+  return static_cast<int>(std::min<long long>((items + block - 1) / block, static_cast<long long>(sm_count()) * 32));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// max pool (nn.MaxPool2d: -inf padding, floor mode)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_kernel(int N, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad, const T* __restrict__ x,
+               int in_pitch, T* __restrict__ y, int out_pitch) {
+  const int cvecs = C >> 3;
+  const long long total = static_cast<long long>(N) * Ho * Wo * cvecs;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = idx;
+    const int cv = static_cast<int>(r % cvecs); r /= cvecs;
+    const int wo = static_cast<int>(r % Wo); r /= Wo;
+    const int ho = static_cast<int>(r % Ho);
+    const int n = static_cast<int>(r / Ho);
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+    for (int fr = 0; fr < k; ++fr) {
+      const int hi = ho * stride - pad + fr;
+      if (hi < 0 || hi >= H) continue;
+      for (int fs = 0; fs < k; ++fs) {
+        const int wi = wo * stride - pad + fs;
+        if (wi < 0 || wi >= W) continue;
+        float v[8];
+        V8<T>::load(x + ((static_cast<size_t>(n) * H + hi) * W + wi) * in_pitch + (cv << 3), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
+      }
+    }
+    V8<T>::store(y + ((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * out_pitch + (cv << 3), m);
+  }
+}
+
+struct MaxPoolOp : Op {
+  int dtype, N, H, W, C, Ho, Wo, k, stride, pad, in_pitch, out_pitch;
+  const void* x;
+  void* y;
+  cudaError_t launch(cudaStream_t s) override {
+    g_launches++;
+    const int grid = grid_for(static_cast<long long>(N) * Ho * Wo * (C >> 3));
+    if (dtype == PCV_F32)
+      maxpool_kernel<float><<<grid, 256, 0, s>>>(N, H, W, C, Ho, Wo, k, stride, pad, (const float*)x, in_pitch,
+                                                 (float*)y, out_pitch);
+    else
+      maxpool_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(N, H, W, C, Ho, Wo, k, stride, pad, (const __nv_bfloat16*)x,
+                                                         in_pitch, (__nv_bfloat16*)y, out_pitch);
+    return cudaGetLastError();
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// global average pool: one CTA per (image, 64-channel slab); 8 channel vectors x 32 pixel lanes, smem tree reduce.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+gap_kernel(int HW, int C, const T* __restrict__ x, int in_pitch, void* __restrict__ out, int out_f32) {
+  __shared__ float red[32][8][8 + 1];
+  const int n = blockIdx.y;
+  const int c0 = blockIdx.x * 64;
+  const int cv = threadIdx.x & 7;
+  const int pl = threadIdx.x >> 3;  // pixel lane 0..31
+  const int c = c0 + cv * 8;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (c < C) {
+    const T* base = x + static_cast<size_t>(n) * HW * in_pitch + c;
+    for (int p = pl; p < HW; p += 32) {
+      float v[8];
+      V8<T>::load(base + static_cast<size_t>(p) * in_pitch, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += v[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[pl][cv][e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int ch = threadIdx.x;  // channel within the slab
+    float s = 0.f;
+#pragma unroll 8
+    for (int p = 0; p < 32; ++p) s += red[p][ch >> 3][ch & 7];
+    if (c0 + ch < C) {
+      const float mean = s / static_cast<float>(HW);
+      const size_t o = static_cast<size_t>(n) * C + c0 + ch;
+      if (out_f32) reinterpret_cast<float*>(out)[o] = mean;
+      else reinterpret_cast<__nv_bfloat16*>(out)[o] = __float2bfloat16(mean);
+    }
+  }
+}
+
+struct GapOp : Op {
+  int dtype, N, HW, C, in_pitch, out_f32;
+  const void* x;
+  void* out;
+  cudaError_t launch(cudaStream_t s) override {
+    g_launches++;
+    dim3 grid(ceil_div(C, 64), N);
+    if (dtype == PCV_F32) gap_kernel<float><<<grid, 256, 0, s>>>(HW, C, (const float*)x, in_pitch, out, out_f32);
+    else gap_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(HW, C, (const __nv_bfloat16*)x, in_pitch, out, out_f32);
+    return cudaGetLastError();
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// skinny fp32 FC: y[n, j] = act(b[j] + sum_c x[n, c] * W[j, c]).  CTA = 8 images x 8 outputs (one output per warp),
+// lanes stride over c so W rows are read coalesced and reused across the 8 images.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fc_f32_kernel(int N, int C, int J, const float* __restrict__ x, const float* __restrict__ W,
+              const float* __restrict__ b, int act, float* __restrict__ y) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + warp;
+  const int n0 = blockIdx.y * 8;
+  if (j >= J) return;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const float* wr = W + static_cast<size_t>(j) * C;
+  for (int c = lane; c < C; c += 32) {
+    const float wv = __ldg(wr + c);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = n0 + i;
+      if (n < N) acc[i] = fmaf(wv, __ldg(x + static_cast<size_t>(n) * C + c), acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  }
+  if (lane == 0) {
+    const float bj = b ? b[j] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = n0 + i;
+      if (n < N) y[static_cast<size_t>(n) * J + j] = misc_act(acc[i] + bj, act);
+    }
+  }
+}
+
+struct SeExciteOp : Op {
+  int N, C, Cmid, mid_act, out_act;
+  const float *pooled, *w1, *b1, *w2, *b2;
+  float* gate;
+  float* mid;  // scratch lives at gate + N*C (caller sizes gate as N*(C+Cmid))
+  cudaError_t launch(cudaStream_t s) override {
+    g_launches += 2;
+    fc_f32_kernel<<<dim3(ceil_div(Cmid, 8), ceil_div(N, 8)), 256, 0, s>>>(N, C, Cmid, pooled, w1, b1, mid_act, mid);
+    fc_f32_kernel<<<dim3(ceil_div(C, 8), ceil_div(N, 8)), 256, 0, s>>>(N, Cmid, C, mid, w2, b2, out_act, gate);
+    return cudaGetLastError();
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// SE scale (+ identity, + activation);  plain residual add
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+se_scale_kernel(int HW, int C, long long total_vecs, const T* __restrict__ x, const float* __restrict__ gate,
+                const T* __restrict__ idn, int act, T* __restrict__ y) {
+  const int cvecs = C >> 3;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total_vecs;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(idx % cvecs);
+    const long long pix = idx / cvecs;
+    const int n = static_cast<int>(pix / HW);
+    float v[8], g[8];
+    V8<T>::load(x + idx * 8, v);
+    V8<float>::load(gate + static_cast<size_t>(n) * C + cv * 8, g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= g[e];
+    if (idn) {
+      float r[8];
+      V8<T>::load(idn + idx * 8, r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += r[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = misc_act(v[e], act);
+    V8<T>::store(y + idx * 8, v);
+  }
+}
+
+struct SeScaleOp : Op {
+  int dtype, N, HW, C, act;
+  const void *x, *idn;
+  const float* gate;
+  void* y;
+  cudaError_t launch(cudaStream_t s) override {
+    g_launches++;
+    const long long vecs = static_cast<long long>(N) * HW * (C >> 3);
+    const int grid = grid_for(vecs);
+    if (dtype == PCV_F32)
+      se_scale_kernel<float><<<grid, 256, 0, s>>>(HW, C, vecs, (const float*)x, gate, (const float*)idn, act, (float*)y);
+    else
+      se_scale_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(HW, C, vecs, (const __nv_bfloat16*)x, gate,
+                                                          (const __nv_bfloat16*)idn, act, (__nv_bfloat16*)y);
+    return cudaGetLastError();
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+add_act_kernel(long long vecs, const T* __restrict__ a, const T* __restrict__ b, int act, T* __restrict__ y) {
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < vecs;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float u[8], v[8];
+    V8<T>::load(a + idx * 8, u);
+    V8<T>::load(b + idx * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) u[e] = misc_act(u[e] + v[e], act);
+    V8<T>::store(y + idx * 8, u);
+  }
+}
+
+struct AddActOp : Op {
+  int dtype, act;
+  long long vecs;
+  const void *a, *b;
+  void* y;
+  cudaError_t launch(cudaStream_t s) override {
+    g_launches++;
+    const int grid = grid_for(vecs);
+    if (dtype == PCV_F32) add_act_kernel<float><<<grid, 256, 0, s>>>(vecs, (const float*)a, (const float*)b, act, (float*)y);
+    else add_act_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(vecs, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, act,
+                                                             (__nv_bfloat16*)y);
+    return cudaGetLastError();
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// layout edges: NCHW fp32 <-> NHWC T
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(int N, int C, int HW, int c_pitch, const float* __restrict__ x, T* __restrict__ y) {
+  // thread = (pixel, 8-channel vector); pixel-fastest so the NCHW plane reads are coalesced
+  const int cvecs = c_pitch >> 3;
+  const long long total = static_cast<long long>(N) * cvecs * HW;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int p = static_cast<int>(idx % HW);
+    const long long r = idx / HW;
+    const int cv = static_cast<int>(r % cvecs);
+    const int n = static_cast<int>(r / cvecs);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = cv * 8 + e;
+      v[e] = c < C ? x[(static_cast<size_t>(n) * C + c) * HW + p] : 0.f;
+    }
+    V8<T>::store(y + (static_cast<size_t>(n) * HW + p) * c_pitch + cv * 8, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(int N, int C, int HW, int c_pitch, const T* __restrict__ x, float* __restrict__ y) {
+  const long long total = static_cast<long long>(N) * C * HW;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int p = static_cast<int>(idx % HW);
+    const long long r = idx / HW;
+    const int c = static_cast<int>(r % C);
+    const int n = static_cast<int>(r / C);
+    y[idx] = V8<T>::ld1(x + (static_cast<size_t>(n) * HW + p) * c_pitch + c);
+  }
+}
+
+struct LayoutOp : Op {
+  int dtype, N, C, HW, c_pitch, to_nhwc;
+  const void* x;
+  void* y;
+  cudaError_t launch(cudaStream_t s) override {
+    g_launches++;
+    if (to_nhwc) {
+      const int grid = grid_for(static_cast<long long>(N) * (c_pitch >> 3) * HW);
+      if (dtype == PCV_F32) nchw_to_nhwc_kernel<float><<<grid, 256, 0, s>>>(N, C, HW, c_pitch, (const float*)x, (float*)y);
+      else nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(N, C, HW, c_pitch, (const float*)x, (__nv_bfloat16*)y);
+    } else {
+      const int grid = grid_for(static_cast<long long>(N) * C * HW);
+      if (dtype == PCV_F32) nhwc_to_nchw_kernel<float><<<grid, 256, 0, s>>>(N, C, HW, c_pitch, (const float*)x, (float*)y);
+      else nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(N, C, HW, c_pitch, (const __nv_bfloat16*)x, (float*)y);
+    }
+    return cudaGetLastError();
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// bilinear, align_corners=True:  src = dst * (in-1)/(out-1)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+bilinear_nchw_kernel(int N, int Hin, int Win, int C, const T* __restrict__ x, int in_pitch, int Hout, int Wout,
+                     float* __restrict__ y, float sh, float sw) {
+  // thread = (n, c, oh, ow), ow-fastest: coalesced fp32 plane writes; the 4 taps of neighbouring lanes share lines
+  const long long total = static_cast<long long>(N) * C * Hout * Wout;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ow = static_cast<int>(idx % Wout);
+    long long r = idx / Wout;
+    const int oh = static_cast<int>(r % Hout); r /= Hout;
+    const int c = static_cast<int>(r % C);
+    const int n = static_cast<int>(r / C);
+    const float fy = oh * sh, fx = ow * sw;
+    int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+    y0 = min(y0, Hin - 1); x0 = min(x0, Win - 1);
+    const int y1 = min(y0 + 1, Hin - 1), x1 = min(x0 + 1, Win - 1);
+    const float ly = fy - y0, lx = fx - x0;
+    const T* base = x + static_cast<size_t>(n) * Hin * Win * in_pitch + c;
+    const float v00 = V8<T>::ld1(base + (static_cast<size_t>(y0) * Win + x0) * in_pitch);
+    const float v01 = V8<T>::ld1(base + (static_cast<size_t>(y0) * Win + x1) * in_pitch);
+    const float v10 = V8<T>::ld1(base + (static_cast<size_t>(y1) * Win + x0) * in_pitch);
+    const float v11 = V8<T>::ld1(base + (static_cast<size_t>(y1) * Win + x1) * in_pitch);
+    y[idx] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bilinear_nhwc_kernel(int N, int Hin, int Win, int C, const T* __restrict__ x, int in_pitch, int Hout, int Wout,
+                     T* __restrict__ y, int out_pitch, float sh, float sw) {
+  const int cvecs = C >> 3;
+  const long long total = static_cast<long long>(N) * Hout * Wout * cvecs;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(idx % cvecs);
+    long long r = idx / cvecs;
+    const int ow = static_cast<int>(r % Wout); r /= Wout;
+    const int oh = static_cast<int>(r % Hout);
+    const int n = static_cast<int>(r / Hout);
+    const float fy = oh * sh, fx = ow * sw;
+    int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+    y0 = min(y0, Hin - 1); x0 = min(x0, Win - 1);
+    const int y1 = min(y0 + 1, Hin - 1), x1 = min(x0 + 1, Win - 1);
+    const float ly = fy - y0, lx = fx - x0;
+    const T* base = x + static_cast<size_t>(n) * Hin * Win * in_pitch + cv * 8;
+    float a[8], b[8], c2[8], d[8], o[8];
+    V8<T>::load(base + (static_cast<size_t>(y0) * Win + x0) * in_pitch, a);
+    V8<T>::load(base + (static_cast<size_t>(y0) * Win + x1) * in_pitch, b);
+    V8<T>::load(base + (static_cast<size_t>(y1) * Win + x0) * in_pitch, c2);
+    V8<T>::load(base + (static_cast<size_t>(y1) * Win + x1) * in_pitch, d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      o[e] = (1.f - ly) * ((1.f - lx) * a[e] + lx * b[e]) + ly * ((1.f - lx) * c2[e] + lx * d[e]);
+    V8<T>::store(y + ((static_cast<size_t>(n) * Hout + oh) * Wout + ow) * out_pitch + cv * 8, o);
+  }
+}
+
+struct BilinearOp : Op {
+  int dtype, N, Hin, Win, C, in_pitch, Hout, Wout, out_pitch, nchw;
+  const void* x;
+  void* y;
+  cudaError_t launch(cudaStream_t s) override {
+    g_launches++;
+    const float sh = Hout > 1 ? static_cast<float>(Hin - 1) / static_cast<float>(Hout - 1) : 0.f;
+    const float sw = Wout > 1 ? static_cast<float>(Win - 1) / static_cast<float>(Wout - 1) : 0.f;
+    if (nchw) {
+      const int grid = grid_for(static_cast<long long>(N) * C * Hout * Wout);
+      if (dtype == PCV_F32)
+        bilinear_nchw_kernel<float><<<grid, 256, 0, s>>>(N, Hin, Win, C, (const float*)x, in_pitch, Hout, Wout, (float*)y, sh, sw);
+      else
+        bilinear_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(N, Hin, Win, C, (const __nv_bfloat16*)x, in_pitch, Hout,
+                                                                 Wout, (float*)y, sh, sw);
+    } else {
+      const int grid = grid_for(static_cast<long long>(N) * Hout * Wout * (C >> 3));
+      if (dtype == PCV_F32)
+        bilinear_nhwc_kernel<float><<<grid, 256, 0, s>>>(N, Hin, Win, C, (const float*)x, in_pitch, Hout, Wout, (float*)y,
+                                                         out_pitch, sh, sw);
+      else
+        bilinear_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(N, Hin, Win, C, (const __nv_bfloat16*)x, in_pitch, Hout,
+                                                                 Wout, (__nv_bfloat16*)y, out_pitch, sh, sw);
+    }
+    return cudaGetLastError();
+  }
+};
+
+}  // namespace pcv
+
+using namespace pcv;
+
+static const char* dn(int dtype) { return dtype == PCV_F32 ? "f32" : "bf16"; }
+#define PCV_DTYPE_OK(dt) PCV_REQUIRE((dt) == PCV_BF16 || (dt) == PCV_F32, "unknown dtype %d", (dt))
+
+extern "C" {
+
+int pcv_maxpool2d(pcv_plan* plan, int dtype, int N, int H, int W, int C, int k, int stride, int pad, const void* x,
+                  int in_pitch, void* y, int out_pitch, pcv_stream stream) {
+  PCV_DTYPE_OK(dtype);
+  PCV_REQUIRE(x && y, "NULL tensor pointer");
+  PCV_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && k > 0 && stride > 0 && pad >= 0 && 2 * pad <= k, "bad maxpool dims");
+  in_pitch = pitch_or(in_pitch, C);
+  out_pitch = pitch_or(out_pitch, C);
+  PCV_REQUIRE(C % 8 == 0 && in_pitch % 8 == 0 && out_pitch % 8 == 0, "maxpool needs channel counts/pitches % 8 == 0");
+  auto op = std::make_unique<MaxPoolOp>();
+  op->dtype = dtype; op->N = N; op->H = H; op->W = W; op->C = C; op->k = k; op->stride = stride; op->pad = pad;
+  op->Ho = (H + 2 * pad - k) / stride + 1;
+  op->Wo = (W + 2 * pad - k) / stride + 1;
+  PCV_REQUIRE(op->Ho > 0 && op->Wo > 0, "maxpool output is empty");
+  op->in_pitch = in_pitch; op->out_pitch = out_pitch; op->x = x; op->y = y;
+  char nm[96];
+  snprintf(nm, sizeof nm, "maxpool_%s %dx%d s%d C=%d @%dx%d", dn(dtype), k, k, stride, C, H, W);
+  op->name = nm;
+  op->bytes = esize(dtype) * static_cast<double>(N) * C * (static_cast<double>(H) * W + static_cast<double>(op->Ho) * op->Wo);
+  return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
+}
+
+int pcv_global_avgpool(pcv_plan* plan, int dtype, int N, int HW, int C, const void* x, int in_pitch, void* pooled,
+                       int out_dtype, pcv_stream stream) {
+  PCV_DTYPE_OK(dtype);
+  PCV_DTYPE_OK(out_dtype);
+  PCV_REQUIRE(x && pooled, "NULL tensor pointer");
+  PCV_REQUIRE(N > 0 && HW > 0 && C > 0 && N <= 65535, "bad avgpool dims");
+  in_pitch = pitch_or(in_pitch, C);
+  PCV_REQUIRE(C % 8 == 0 && in_pitch % 8 == 0, "avgpool needs channel count/pitch % 8 == 0");
+  auto op = std::make_unique<GapOp>();
+  op->dtype = dtype; op->N = N; op->HW = HW; op->C = C; op->in_pitch = in_pitch; op->out_f32 = out_dtype == PCV_F32;
+  op->x = x; op->out = pooled;
+  char nm[96];
+  snprintf(nm, sizeof nm, "gavgpool_%s C=%d HW=%d", dn(dtype), C, HW);
+  op->name = nm;
+  op->bytes = esize(dtype) * static_cast<double>(N) * C * HW + esize(out_dtype) * static_cast<double>(N) * C;
+  return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
+}
+
+int pcv_se_excite(pcv_plan* plan, int N, int C, int Cmid, const float* pooled, const float* w1, const float* b1,
+                  const float* w2, const float* b2, int mid_act, int out_act, float* gate, pcv_stream stream) {
+  PCV_REQUIRE(pooled && w1 && w2 && gate, "NULL tensor pointer");
+  PCV_REQUIRE(N > 0 && C > 0 && Cmid > 0, "bad SE dims");
+  auto op = std::make_unique<SeExciteOp>();
+  op->N = N; op->C = C; op->Cmid = Cmid; op->mid_act = mid_act; op->out_act = out_act;
+  op->pooled = pooled; op->w1 = w1; op->b1 = b1; op->w2 = w2; op->b2 = b2; op->gate = gate;
+  op->mid = gate + static_cast<size_t>(N) * C;
+  op->launches = 2;
+  char nm[96];
+  snprintf(nm, sizeof nm, "se_excite C=%d mid=%d", C, Cmid);
+  op->name = nm;
+  op->flops = 4.0 * N * C * Cmid;
+  op->bytes = 8.0 * C * Cmid + 8.0 * N * C;
+  return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
+}
+
+int pcv_se_scale_add_act(pcv_plan* plan, int dtype, int N, int HW, int C, const void* x, const float* gate,
+                         const void* identity, int act, void* y, pcv_stream stream) {
+  PCV_DTYPE_OK(dtype);
+  PCV_REQUIRE(x && gate && y, "NULL tensor pointer");
+  PCV_REQUIRE(N > 0 && HW > 0 && C > 0 && C % 8 == 0, "SE scale needs C % 8 == 0");
+  auto op = std::make_unique<SeScaleOp>();
+  op->dtype = dtype; op->N = N; op->HW = HW; op->C = C; op->act = act; op->x = x; op->gate = gate; op->idn = identity;
+  op->y = y;
+  char nm[96];
+  snprintf(nm, sizeof nm, "se_scale_%s C=%d HW=%d%s", dn(dtype), C, HW, identity ? " +id" : "");
+  op->name = nm;
+  op->bytes = esize(dtype) * static_cast<double>(N) * HW * C * (identity ? 3.0 : 2.0);
+  return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
+}
+
+int pcv_add_act(pcv_plan* plan, int dtype, size_t count, const void* a, const void* b, int act, void* y,
+                pcv_stream stream) {
+  PCV_DTYPE_OK(dtype);
+  PCV_REQUIRE(a && b && y, "NULL tensor pointer");
+  PCV_REQUIRE(count > 0 && count % 8 == 0, "add_act needs count % 8 == 0");
+  auto op = std::make_unique<AddActOp>();
+  op->dtype = dtype; op->act = act; op->vecs = static_cast<long long>(count / 8); op->a = a; op->b = b; op->y = y;
+  op->name = std::string("add_act_") + dn(dtype);
+  op->bytes = 3.0 * esize(dtype) * static_cast<double>(count);
+  return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
+}
+
+int pcv_nchw_f32_to_nhwc(pcv_plan* plan, int dtype, int N, int C, int H, int W, const float* x, void* y, int c_pitch,
+                         pcv_stream stream) {
+  PCV_DTYPE_OK(dtype);
+  PCV_REQUIRE(x && y, "NULL tensor pointer");
+  c_pitch = pitch_or(c_pitch, round_up(C, 8));
+  PCV_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && c_pitch >= C && c_pitch % 8 == 0, "bad ingest dims");
+  auto op = std::make_unique<LayoutOp>();
+  op->dtype = dtype; op->N = N; op->C = C; op->HW = H * W; op->c_pitch = c_pitch; op->to_nhwc = 1; op->x = x; op->y = y;
+  char nm[96];
+  snprintf(nm, sizeof nm, "ingest_nchw_f32_to_nhwc_%s C=%d->%d @%dx%d", dn(dtype), C, c_pitch, H, W);
+  op->name = nm;
+  op->bytes = static_cast<double>(N) * H * W * (4.0 * C + esize(dtype) * c_pitch);
+  return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
+}
+
+int pcv_nhwc_to_nchw_f32(pcv_plan* plan, int dtype, int N, int C, int H, int W, const void* x, int c_pitch, float* y,
+                         pcv_stream stream) {
+  PCV_DTYPE_OK(dtype);
+  PCV_REQUIRE(x && y, "NULL tensor pointer");
+  c_pitch = pitch_or(c_pitch, C);
+  PCV_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && c_pitch >= C, "bad egress dims");
+  auto op = std::make_unique<LayoutOp>();
+  op->dtype = dtype; op->N = N; op->C = C; op->HW = H * W; op->c_pitch = c_pitch; op->to_nhwc = 0; op->x = x; op->y = y;
+  char nm[96];
+  snprintf(nm, sizeof nm, "egress_nhwc_%s_to_nchw_f32 C=%d @%dx%d", dn(dtype), C, H, W);
+  op->name = nm;
+  op->bytes = static_cast<double>(N) * H * W * C * (4.0 + esize(dtype));
+  return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
+}
+
+int pcv_bilinear_upsample_ac(pcv_plan* plan, int dtype, int N, int Hin, int Win, int C, const void* x, int in_pitch,
+                             int Hout, int Wout, void* y, int out_pitch, int out_nchw_f32, pcv_stream stream) {
+  PCV_DTYPE_OK(dtype);
+  PCV_REQUIRE(x && y, "NULL tensor pointer");
+  PCV_REQUIRE(N > 0 && Hin > 0 && Win > 0 && C > 0 && Hout > 0 && Wout > 0, "bad bilinear dims");
+  in_pitch = pitch_or(in_pitch, C);
+  out_pitch = pitch_or(out_pitch, C);
+  if (!out_nchw_f32)
+    PCV_REQUIRE(C % 8 == 0 && in_pitch % 8 == 0 && out_pitch % 8 == 0, "NHWC bilinear needs channels/pitches % 8 == 0");
+  auto op = std::make_unique<BilinearOp>();
+  op->dtype = dtype; op->N = N; op->Hin = Hin; op->Win = Win; op->C = C; op->in_pitch = in_pitch; op->Hout = Hout;
+  op->Wout = Wout; op->out_pitch = out_pitch; op->nchw = out_nchw_f32; op->x = x; op->y = y;
+  char nm[96];
+  snprintf(nm, sizeof nm, "bilinear_%s C=%d %dx%d->%dx%d%s", dn(dtype), C, Hin, Win, Hout, Wout, out_nchw_f32 ? " nchw_f32" : "");
+  op->name = nm;
+  op->bytes = static_cast<double>(N) * C * (esize(dtype) * Hin * Win + (out_nchw_f32 ? 4.0 : esize(dtype)) * Hout * Wout);
+  return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// Internal runtime shared by the kernels' host launchers and the C ABI: the Op record, the Plan, error plumbing.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/pcv_b200.h"
+
+namespace pcv {
+
+// ---- errors (thread-local message, integer status across the ABI) -------------------------------------------
+std::string& last_error_ref();
+int fail(int code, const char* fmt, ...);
+
+#define PCV_CHECK_CUDA(expr)                                                                  \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return ::pcv::fail(PCV_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                         __FILE__, __LINE__);                                                 \
+  } while (0)
+
+#define PCV_REQUIRE(cond, ...)                                 \
+  do {                                                         \
+    if (!(cond)) return ::pcv::fail(PCV_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+extern std::atomic<int64_t> g_launches;
+
+// ---- one recorded fused-kernel launch --------------------------------------------------------------------------
+struct Op {
+  std::string name;
+  double flops = 0.0;   // algorithmic FLOPs (2*MACs) of this op
+  double bytes = 0.0;   // algorithmic HBM bytes of this op
+  int launches = 1;     // kernels per launch() call
+  virtual ~Op() {}
+  virtual cudaError_t launch(cudaStream_t s) = 0;
+};
+
+}  // namespace pcv
+
+struct pcv_plan {
+  std::vector<std::unique_ptr<pcv::Op>> ops;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  int launches = 0;
+};
+
+namespace pcv {
+
+// Run the op now (plan == nullptr) or append it to the plan.  Takes ownership of `op`.
+int submit(pcv_plan* plan, Op* op, cudaStream_t stream);
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+inline int conv_out(int H, int k, int stride, int pad, int dil) { return (H + 2 * pad - dil * (k - 1) - 1) / stride + 1; }
+inline int pitch_or(int pitch, int c) { return pitch > 0 ? pitch : c; }
+inline size_t esize(int dtype) { return dtype == PCV_F32 ? 4 : 2; }
+int sm_count();
+
+// ---- driver entry points for tensor maps (resolved at run time so the .so loads without libcuda) ----------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn();
+EncodeIm2colFn encode_im2col_fn();
+
+// ---- launchers implemented in the .cu files --------------------------------------------------------------------
+// conv_igemm.cu : tcgen05 implicit GEMM (dense + block-diagonal grouped), bf16
+int igemm_supported(const pcv_conv_desc& d, std::string* why);
+int igemm_packed_bytes(const pcv_conv_desc& d, size_t* w_bytes, size_t* b_bytes);
+int igemm_pack(const pcv_conv_desc& d, const float* w, const float* conv_bias, const float* g, const float* b,
+               const float* m, const float* v, float eps, void* w_packed, float* bias_out, cudaStream_t s);
+int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float* bias, const void* res, void* y,
+               Op** out);
+// conv_simt.cu : CUDA-core direct convolution (fp32 tier; generic bf16 fallback / cross-check)
+int simt_packed_bytes(const pcv_conv_desc& d, int dtype, size_t* w_bytes, size_t* b_bytes);
+int simt_pack(const pcv_conv_desc& d, int dtype, const float* w, const float* conv_bias, const float* g,
+              const float* b, const float* m, const float* v, float eps, void* w_packed, float* bias_out,
+              cudaStream_t s);
+int simt_make(const pcv_conv_desc& d, int dtype, const void* x, const void* w, const float* bias, const void* res,
+              void* y, Op** out);
+// dwconv.cu : depthwise kxk, bf16 / fp32, NHWC vectorised
+int dw_packed_bytes(const pcv_conv_desc& d, int dtype, size_t* w_bytes, size_t* b_bytes);
+int dw_pack(const pcv_conv_desc& d, int dtype, const float* w, const float* conv_bias, const float* g, const float* b,
+            const float* m, const float* v, float eps, void* w_packed, float* bias_out, cudaStream_t s);
+int dw_make(const pcv_conv_desc& d, int dtype, const void* x, const void* w, const float* bias, const void* res,
+            void* y, Op** out);
+
+enum ConvRoute { ROUTE_IGEMM = 0, ROUTE_DW = 1, ROUTE_SIMT = 2 };
+int conv_route(const pcv_conv_desc& d, int dtype, std::string* why);
+
+}  // namespace pcv

@@ -1,0 +1,561 @@
+"""Host-side mirror of the reference model definitions on the hot path.
+
+ResNet (models/resnet.py), MobileNetV2 (models/mobilenetv2.py), ResNeXt / SE-ResNeXt (models/resnext.py,
+models/seresnext.py), SEInitBlock (models/senet.py:127-164), ResNet(D) (models/resnetd.py), DeepLabv3
+(models/deeplabv3.py) and, as the DwsConvBlock vehicle, MobileNet (models/mobilenet.py).
+
+Class names, attribute names, constructor kwargs, module registration order (hence state_dict keys AND the RNG
+stream consumed by `torch.manual_seed(s); get_model(...)`) follow the reference, so seeds and checkpoints carry over.
+All forwards run through the compiled B200 plan (plan.run_module); nothing here calls a torch op.
+"""
+from __future__ import annotations
+
+import math
+
+import torch.nn as nn
+
+from .blocks import (B200Module, SEBlock, conv1x1, conv1x1_block, conv3x3_block, conv7x7_block, dwconv3x3_block,
+                     dwsconv3x3_block, lambda_batchnorm2d, lambda_relu, lambda_relu6)
+from .plan import run_module
+
+
+def _kaiming_init(net: nn.Module) -> None:
+    """The `_init_params` shared by every net on this path (e.g. resnet.py:326-331)."""
+    for _, mod in net.named_modules():
+        if isinstance(mod, nn.Conv2d):
+            nn.init.kaiming_uniform_(mod.weight)
+            if mod.bias is not None:
+                nn.init.constant_(mod.bias, 0)
+
+
+def _no_pretrained(pretrained: bool, model_name) -> None:
+    if not pretrained:
+        return
+    if not model_name:
+        raise ValueError("Parameter `model_name` should be properly initialized for loading pretrained model.")
+    raise RuntimeError("pretrained=True needs the reference's model_store download path, which is out of scope for "
+                       "the B200 eval path (no network); build with pretrained=False and load_state_dict() a "
+                       "reference checkpoint instead — the state_dict keys are identical")
+
+
+def _stages(features: nn.Sequential, channels, in_channels, make_unit, stride_of=None):
+    """Append stage{i}/unit{j} containers the way every reference net does (resnet.py:303-315)."""
+    for i, per_stage in enumerate(channels):
+        stage = nn.Sequential()
+        for j, out_channels in enumerate(per_stage):
+            stride = stride_of(i, j) if stride_of else (2 if (j == 0 and i != 0) else 1)
+            stage.add_module(f"unit{j + 1}", make_unit(i, j, in_channels, out_channels, stride))
+            in_channels = out_channels
+        features.add_module(f"stage{i + 1}", stage)
+    return in_channels
+
+
+# ===== containers (common/arch.py) ================================================================================
+class Concurrent(nn.Sequential):
+    """Branches on the same input, outputs concatenated on `axis` (arch.py:58-95)."""
+
+    def __init__(self, axis: int = 1, stack: bool = False, merge_type: str | None = None):
+        super().__init__()
+        assert merge_type is None or merge_type in ("cat", "stack", "sum")
+        self.axis = axis
+        self.merge_type = merge_type if merge_type is not None else ("stack" if stack else "cat")
+
+    def forward(self, x):
+        return run_module(self, x)
+
+
+class MultiOutputSequential(nn.Sequential):
+    """Sequential that also returns the outputs of children flagged `do_output` (arch.py:309-347)."""
+
+    def __init__(self, multi_output: bool = True, dual_output: bool = False, return_last: bool = True):
+        super().__init__()
+        self.multi_output, self.dual_output, self.return_last = multi_output, dual_output, return_last
+
+    def forward(self, x):
+        return run_module(self, x)
+
+
+# ===== ResNet (resnet.py) ===========================================================================================
+class ResBlock(B200Module):
+    def __init__(self, in_channels, out_channels, stride, bias=False, normalization=lambda_batchnorm2d(),
+                 activation=lambda_relu(), final_activation=None):
+        super().__init__()
+        self.conv1 = conv3x3_block(in_channels=in_channels, out_channels=out_channels, stride=stride, bias=bias,
+                                   normalization=normalization, activation=activation)
+        self.conv2 = conv3x3_block(in_channels=out_channels, out_channels=out_channels, bias=bias,
+                                   normalization=normalization, activation=final_activation)
+
+
+class ResBottleneck(B200Module):
+    def __init__(self, in_channels, out_channels, stride, padding=1, dilation=1, bias=False,
+                 normalization=lambda_batchnorm2d(), conv1_stride=False, bottleneck_factor=4,
+                 activation=lambda_relu(), final_activation=None):
+        super().__init__()
+        mid = out_channels // bottleneck_factor
+        self.conv1 = conv1x1_block(in_channels=in_channels, out_channels=mid, stride=(stride if conv1_stride else 1),
+                                   bias=bias, normalization=normalization, activation=activation)
+        self.conv2 = conv3x3_block(in_channels=mid, out_channels=mid, stride=(1 if conv1_stride else stride),
+                                   padding=padding, dilation=dilation, bias=bias, normalization=normalization,
+                                   activation=activation)
+        self.conv3 = conv1x1_block(in_channels=mid, out_channels=out_channels, bias=bias,
+                                   normalization=normalization, activation=final_activation)
+
+
+class ResUnit(B200Module):
+    """relu(body(x) + identity): the add and the ReLU run in the last conv's epilogue (resnet.py:221-229)."""
+
+    def __init__(self, in_channels, out_channels, stride=1, padding=1, dilation=1, bias=False,
+                 normalization=lambda_batchnorm2d(), bottleneck=True, conv1_stride=False, activation=lambda_relu(),
+                 final_body_activation=None, final_activation=lambda_relu()):
+        super().__init__()
+        self.resize_identity = (in_channels != out_channels) or (stride != 1)
+        if bottleneck:
+            self.body = ResBottleneck(in_channels=in_channels, out_channels=out_channels, stride=stride,
+                                      padding=padding, dilation=dilation, bias=bias, normalization=normalization,
+                                      conv1_stride=conv1_stride, activation=activation,
+                                      final_activation=final_body_activation)
+        else:
+            self.body = ResBlock(in_channels=in_channels, out_channels=out_channels, stride=stride, bias=bias,
+                                 normalization=normalization, activation=activation,
+                                 final_activation=final_body_activation)
+        if self.resize_identity:
+            self.identity_conv = conv1x1_block(in_channels=in_channels, out_channels=out_channels, stride=stride,
+                                               bias=bias, normalization=normalization, activation=None)
+        self.activ = final_activation()
+
+
+class ResInitBlock(B200Module):
+    def __init__(self, in_channels, out_channels, normalization=lambda_batchnorm2d()):
+        super().__init__()
+        self.conv = conv7x7_block(in_channels=in_channels, out_channels=out_channels, stride=2,
+                                  normalization=normalization)
+        self.pool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+
+
+class _Classifier(B200Module):
+    """features -> flatten -> output; shared shell of the ImageNet classifiers."""
+
+    def _finish(self, in_channels, num_classes, pool=None):
+        self.features.add_module("final_pool", pool if pool is not None else nn.AvgPool2d(kernel_size=7, stride=1))
+        self.output = nn.Linear(in_features=in_channels, out_features=num_classes)
+        _kaiming_init(self)
+
+
+class ResNet(_Classifier):
+    def __init__(self, channels, init_block_channels, bottleneck, conv1_stride, in_channels=3, in_size=(224, 224),
+                 num_classes=1000):
+        super().__init__()
+        self.in_size, self.num_classes = in_size, num_classes
+        self.features = nn.Sequential()
+        self.features.add_module("init_block", ResInitBlock(in_channels=in_channels,
+                                                            out_channels=init_block_channels))
+        last = _stages(self.features, channels, init_block_channels,
+                       lambda i, j, cin, cout, s: ResUnit(in_channels=cin, out_channels=cout, stride=s,
+                                                          bottleneck=bottleneck, conv1_stride=conv1_stride))
+        self._finish(last, num_classes)
+
+
+_RESNET_LAYERS = {10: [1, 1, 1, 1], 12: [2, 1, 1, 1], 16: [2, 2, 2, 1], 18: [2, 2, 2, 2], 34: [3, 4, 6, 3],
+                  50: [3, 4, 6, 3], 101: [3, 4, 23, 3], 152: [3, 8, 36, 3], 200: [3, 24, 36, 3]}
+_RESNET_LAYERS_BY_KIND = {(14, False): [2, 2, 1, 1], (14, True): [1, 1, 1, 1], (26, False): [3, 3, 3, 3],
+                          (26, True): [2, 2, 2, 2], (38, True): [3, 3, 3, 3]}
+
+
+def _scaled(channels, init_channels, width_scale):
+    if width_scale != 1.0:
+        n = len(channels)
+        channels = [[int(c * width_scale) if (i != n - 1 or j != len(ci) - 1) else c for j, c in enumerate(ci)]
+                    for i, ci in enumerate(channels)]
+        init_channels = int(init_channels * width_scale)
+    return channels, init_channels
+
+
+def get_resnet(blocks, bottleneck=None, conv1_stride=True, width_scale=1.0, model_name=None, pretrained=False,
+               root=None, **kwargs):
+    """Same contract as resnet.py:340-442 (ValueError on an unsupported depth)."""
+    if bottleneck is None:
+        bottleneck = blocks >= 50
+    layers = _RESNET_LAYERS_BY_KIND.get((blocks, bool(bottleneck))) or _RESNET_LAYERS.get(blocks)
+    if layers is None:
+        raise ValueError("Unsupported ResNet with number of blocks: {}".format(blocks))
+    assert sum(layers) * (3 if bottleneck else 2) + 2 == blocks
+    widths = [64, 128, 256, 512]
+    if bottleneck:
+        widths = [w * 4 for w in widths]
+    channels, init_channels = _scaled([[w] * n for w, n in zip(widths, layers)], 64, width_scale)
+    net = ResNet(channels=channels, init_block_channels=init_channels, bottleneck=bottleneck,
+                 conv1_stride=conv1_stride, **kwargs)
+    _no_pretrained(pretrained, model_name)
+    return net
+
+
+def _resnet_ctor(name, **fixed):
+    def ctor(**kwargs):
+        return get_resnet(model_name=name, **fixed, **kwargs)
+    ctor.__name__ = name
+    ctor.__doc__ = f"{name}: see models/resnet.py of the reference for the variant definition."
+    return ctor
+
+
+RESNET_VARIANTS = {
+    "resnet10": dict(blocks=10), "resnet12": dict(blocks=12), "resnet14": dict(blocks=14),
+    "resnetbc14b": dict(blocks=14, bottleneck=True, conv1_stride=False), "resnet16": dict(blocks=16),
+    "resnet18_wd4": dict(blocks=18, width_scale=0.25), "resnet18_wd2": dict(blocks=18, width_scale=0.5),
+    "resnet18_w3d4": dict(blocks=18, width_scale=0.75), "resnet18": dict(blocks=18),
+    "resnet26": dict(blocks=26, bottleneck=False), "resnetbc26b": dict(blocks=26, bottleneck=True, conv1_stride=False),
+    "resnet34": dict(blocks=34), "resnetbc38b": dict(blocks=38, bottleneck=True, conv1_stride=False),
+    "resnet50": dict(blocks=50), "resnet50b": dict(blocks=50, conv1_stride=False),
+    "resnet101": dict(blocks=101), "resnet101b": dict(blocks=101, conv1_stride=False),
+    "resnet152": dict(blocks=152), "resnet152b": dict(blocks=152, conv1_stride=False),
+    "resnet200": dict(blocks=200), "resnet200b": dict(blocks=200, conv1_stride=False),
+}
+
+
+# ===== MobileNetV2 (mobilenetv2.py) ==================================================================================
+class LinearBottleneck(B200Module):
+    def __init__(self, in_channels, out_channels, stride, expansion, remove_exp_conv, activation):
+        super().__init__()
+        self.residual = (in_channels == out_channels) and (stride == 1)
+        mid = in_channels * 6 if expansion else in_channels
+        self.use_exp_conv = expansion or (not remove_exp_conv)
+        if self.use_exp_conv:
+            self.conv1 = conv1x1_block(in_channels=in_channels, out_channels=mid, activation=activation)
+        self.conv2 = dwconv3x3_block(in_channels=mid, out_channels=mid, stride=stride, activation=activation)
+        self.conv3 = conv1x1_block(in_channels=mid, out_channels=out_channels, activation=None)
+
+
+class MobileNetV2(B200Module):
+    def __init__(self, channels, init_block_channels, final_block_channels, remove_exp_conv, in_channels=3,
+                 in_size=(224, 224), num_classes=1000):
+        super().__init__()
+        self.in_size, self.num_classes = in_size, num_classes
+        act = lambda_relu6()
+        self.features = nn.Sequential()
+        self.features.add_module("init_block", conv3x3_block(in_channels=in_channels,
+                                                             out_channels=init_block_channels, stride=2,
+                                                             activation=act))
+        last = _stages(self.features, channels, init_block_channels,
+                       lambda i, j, cin, cout, s: LinearBottleneck(in_channels=cin, out_channels=cout, stride=s,
+                                                                   expansion=(i != 0 or j != 0),
+                                                                   remove_exp_conv=remove_exp_conv, activation=act))
+        self.features.add_module("final_block", conv1x1_block(in_channels=last, out_channels=final_block_channels,
+                                                              activation=act))
+        self.features.add_module("final_pool", nn.AvgPool2d(kernel_size=7, stride=1))
+        self.output = conv1x1(in_channels=final_block_channels, out_channels=num_classes, bias=False)
+        _kaiming_init(self)
+
+
+def get_mobilenetv2(width_scale, remove_exp_conv=False, model_name=None, pretrained=False, root=None, **kwargs):
+    """Same contract as mobilenetv2.py:159-220."""
+    init_channels, final_channels = 32, 1280
+    channels: list[list[int]] = [[]]
+    for width, count, down in zip([16, 24, 32, 64, 96, 160, 320], [1, 2, 3, 4, 3, 3, 1], [0, 1, 1, 1, 0, 1, 0]):
+        if down:
+            channels.append([width] * count)
+        else:
+            channels[-1] = channels[-1] + [width] * count
+    if width_scale != 1.0:
+        channels = [[int(c * width_scale) for c in ci] for ci in channels]
+        init_channels = int(init_channels * width_scale)
+        if width_scale > 1.0:
+            final_channels = int(final_channels * width_scale)
+    net = MobileNetV2(channels=channels, init_block_channels=init_channels, final_block_channels=final_channels,
+                      remove_exp_conv=remove_exp_conv, **kwargs)
+    _no_pretrained(pretrained, model_name)
+    return net
+
+
+MOBILENETV2_VARIANTS = {
+    "mobilenetv2_w1": dict(width_scale=1.0), "mobilenetv2_w3d4": dict(width_scale=0.75),
+    "mobilenetv2_wd2": dict(width_scale=0.5), "mobilenetv2_wd4": dict(width_scale=0.25),
+    "mobilenetv2b_w1": dict(width_scale=1.0, remove_exp_conv=True),
+    "mobilenetv2b_w3d4": dict(width_scale=0.75, remove_exp_conv=True),
+    "mobilenetv2b_wd2": dict(width_scale=0.5, remove_exp_conv=True),
+    "mobilenetv2b_wd4": dict(width_scale=0.25, remove_exp_conv=True),
+}
+
+
+# ===== MobileNet v1: the DwsConvBlock vehicle (mobilenet.py) ==========================================================
+class MobileNet(_Classifier):
+    def __init__(self, channels, first_stage_stride, dw_use_bn=True, dw_activation=lambda_relu(), in_channels=3,
+                 in_size=(224, 224), num_classes=1000):
+        super().__init__()
+        self.in_size, self.num_classes = in_size, num_classes
+        dw_norm = lambda_batchnorm2d() if dw_use_bn else None
+        self.features = nn.Sequential()
+        first = channels[0][0]
+        self.features.add_module("init_block", conv3x3_block(in_channels=in_channels, out_channels=first, stride=2))
+        last = _stages(self.features, channels[1:], first,
+                       lambda i, j, cin, cout, s: dwsconv3x3_block(in_channels=cin, out_channels=cout, stride=s,
+                                                                   dw_normalization=dw_norm,
+                                                                   dw_activation=dw_activation),
+                       stride_of=lambda i, j: 2 if (j == 0 and (i != 0 or first_stage_stride)) else 1)
+        self.features.add_module("final_pool", nn.AvgPool2d(kernel_size=7, stride=1))
+        self.output = nn.Linear(in_features=last, out_features=num_classes)
+        self._init_params()
+
+    def _init_params(self):
+        """mobilenet.py:74-86 (name-keyed kaiming_normal_)."""
+        for name, mod in self.named_modules():
+            if "dw_conv.conv" in name:
+                nn.init.kaiming_normal_(mod.weight, mode="fan_in")
+            elif name == "init_block.conv" or "pw_conv.conv" in name:
+                nn.init.kaiming_normal_(mod.weight, mode="fan_out")
+            elif "bn" in name:
+                nn.init.constant_(mod.weight, 1)
+                nn.init.constant_(mod.bias, 0)
+            elif "output" in name:
+                nn.init.kaiming_normal_(mod.weight, mode="fan_out")
+                nn.init.constant_(mod.bias, 0)
+
+
+def get_mobilenet(width_scale, dws_simplified=False, model_name=None, pretrained=False, root=None, **kwargs):
+    channels = [[32], [64], [128, 128], [256, 256], [512] * 6, [1024, 1024]]
+    if width_scale != 1.0:
+        channels = [[int(c * width_scale) for c in ci] for ci in channels]
+    net = MobileNet(channels=channels, first_stage_stride=False, dw_use_bn=not dws_simplified,
+                    dw_activation=None if dws_simplified else lambda_relu(), **kwargs)
+    _no_pretrained(pretrained, model_name)
+    return net
+
+
+MOBILENET_VARIANTS = {"mobilenet_w1": 1.0, "mobilenet_w3d4": 0.75, "mobilenet_wd2": 0.5, "mobilenet_wd4": 0.25}
+
+
+# ===== ResNeXt / SE-ResNeXt (resnext.py, seresnext.py) =================================================================
+class ResNeXtBottleneck(B200Module):
+    def __init__(self, in_channels, out_channels, stride, cardinality, bottleneck_width, bottleneck_factor=4):
+        super().__init__()
+        mid = out_channels // bottleneck_factor
+        group_width = cardinality * int(math.floor(mid * (bottleneck_width / 64.0)))
+        self.conv1 = conv1x1_block(in_channels=in_channels, out_channels=group_width)
+        self.conv2 = conv3x3_block(in_channels=group_width, out_channels=group_width, stride=stride,
+                                   groups=cardinality)
+        self.conv3 = conv1x1_block(in_channels=group_width, out_channels=out_channels, activation=None)
+
+
+class ResNeXtUnit(B200Module):
+    def __init__(self, in_channels, out_channels, stride, cardinality, bottleneck_width):
+        super().__init__()
+        self.resize_identity = (in_channels != out_channels) or (stride != 1)
+        self.body = ResNeXtBottleneck(in_channels=in_channels, out_channels=out_channels, stride=stride,
+                                      cardinality=cardinality, bottleneck_width=bottleneck_width)
+        if self.resize_identity:
+            self.identity_conv = conv1x1_block(in_channels=in_channels, out_channels=out_channels, stride=stride,
+                                               activation=None)
+        self.activ = nn.ReLU(inplace=True)
+
+
+class SEResNeXtUnit(B200Module):
+    """relu(se(body(x)) + identity): squeeze -> excite -> one fused scale+add+ReLU pass (seresnext.py:57-66)."""
+
+    def __init__(self, in_channels, out_channels, stride, cardinality, bottleneck_width):
+        super().__init__()
+        self.resize_identity = (in_channels != out_channels) or (stride != 1)
+        self.body = ResNeXtBottleneck(in_channels=in_channels, out_channels=out_channels, stride=stride,
+                                      cardinality=cardinality, bottleneck_width=bottleneck_width)
+        self.se = SEBlock(channels=out_channels)
+        if self.resize_identity:
+            self.identity_conv = conv1x1_block(in_channels=in_channels, out_channels=out_channels, stride=stride,
+                                               activation=None)
+        self.activ = nn.ReLU(inplace=True)
+
+
+class _ResNeXtLike(_Classifier):
+    unit_cls = None
+
+    def __init__(self, channels, init_block_channels, cardinality, bottleneck_width, in_channels=3,
+                 in_size=(224, 224), num_classes=1000):
+        super().__init__()
+        self.in_size, self.num_classes = in_size, num_classes
+        self.features = nn.Sequential()
+        self.features.add_module("init_block", ResInitBlock(in_channels=in_channels,
+                                                            out_channels=init_block_channels))
+        unit = type(self).unit_cls
+        last = _stages(self.features, channels, init_block_channels,
+                       lambda i, j, cin, cout, s: unit(in_channels=cin, out_channels=cout, stride=s,
+                                                       cardinality=cardinality, bottleneck_width=bottleneck_width))
+        self._finish(last, num_classes)
+
+
+class ResNeXt(_ResNeXtLike):
+    unit_cls = ResNeXtUnit
+
+
+class SEResNeXt(_ResNeXtLike):
+    unit_cls = SEResNeXtUnit
+
+
+def _get_resnext_like(cls, family, layer_table, blocks, cardinality, bottleneck_width, model_name, pretrained, kwargs):
+    if blocks not in layer_table:
+        raise ValueError("Unsupported {} with number of blocks: {}".format(family, blocks))
+    layers = layer_table[blocks]
+    channels = [[w] * n for w, n in zip([256, 512, 1024, 2048], layers)]
+    net = cls(channels=channels, init_block_channels=64, cardinality=cardinality, bottleneck_width=bottleneck_width,
+              **kwargs)
+    _no_pretrained(pretrained, model_name)
+    return net
+
+
+def get_seresnext(blocks, cardinality, bottleneck_width, model_name=None, pretrained=False, root=None, **kwargs):
+    """Same contract as seresnext.py:143-201."""
+    return _get_resnext_like(SEResNeXt, "SE-ResNeXt", {50: [3, 4, 6, 3], 101: [3, 4, 23, 3]}, blocks, cardinality,
+                             bottleneck_width, model_name, pretrained, kwargs)
+
+
+def get_resnext(blocks, cardinality, bottleneck_width, model_name=None, pretrained=False, root=None, **kwargs):
+    """Same contract as resnext.py:193-259."""
+    table = {14: [1, 1, 1, 1], 26: [2, 2, 2, 2], 38: [3, 3, 3, 3], 50: [3, 4, 6, 3], 101: [3, 4, 23, 3]}
+    return _get_resnext_like(ResNeXt, "ResNeXt", table, blocks, cardinality, bottleneck_width, model_name, pretrained,
+                             kwargs)
+
+
+SERESNEXT_VARIANTS = {"seresnext50_32x4d": (50, 32, 4), "seresnext101_32x4d": (101, 32, 4),
+                      "seresnext101_64x4d": (101, 64, 4)}
+RESNEXT_VARIANTS = {"resnext14_16x4d": (14, 16, 4), "resnext14_32x2d": (14, 32, 2), "resnext14_32x4d": (14, 32, 4),
+                    "resnext26_16x4d": (26, 16, 4), "resnext26_32x2d": (26, 32, 2), "resnext26_32x4d": (26, 32, 4),
+                    "resnext38_32x4d": (38, 32, 4), "resnext50_32x4d": (50, 32, 4), "resnext101_32x4d": (101, 32, 4),
+                    "resnext101_64x4d": (101, 64, 4)}
+
+
+# ===== SENet stem + ResNet(D) (senet.py:127-164, resnetd.py) ==========================================================
+class SEInitBlock(B200Module):
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        mid = out_channels // 2
+        self.conv1 = conv3x3_block(in_channels=in_channels, out_channels=mid, stride=2)
+        self.conv2 = conv3x3_block(in_channels=mid, out_channels=mid)
+        self.conv3 = conv3x3_block(in_channels=mid, out_channels=out_channels)
+        self.pool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+
+
+class ResNetD(B200Module):
+    """Dilated ResNet: stride only in stages 1-2, dilation 2/4 in stages 3-4 (resnetd.py:59-81)."""
+
+    def __init__(self, channels, init_block_channels, bottleneck, conv1_stride, ordinary_init=False, bends=None,
+                 in_channels=3, in_size=(224, 224), num_classes=1000):
+        super().__init__()
+        self.in_size, self.num_classes = in_size, num_classes
+        self.multi_output = bends is not None
+        self.features = MultiOutputSequential()
+        if ordinary_init:
+            self.features.add_module("init_block", ResInitBlock(in_channels=in_channels,
+                                                                out_channels=init_block_channels))
+        else:
+            init_block_channels = 2 * init_block_channels
+            self.features.add_module("init_block", SEInitBlock(in_channels=in_channels,
+                                                               out_channels=init_block_channels))
+        in_channels = init_block_channels
+        for i, per_stage in enumerate(channels):
+            stage = nn.Sequential()
+            for j, out_channels in enumerate(per_stage):
+                stride = 2 if (j == 0 and i != 0 and i < 2) else 1
+                dilation = 2 ** max(0, i - 1 - int(j == 0))
+                stage.add_module(f"unit{j + 1}", ResUnit(in_channels=in_channels, out_channels=out_channels,
+                                                         stride=stride, padding=dilation, dilation=dilation,
+                                                         bottleneck=bottleneck, conv1_stride=conv1_stride))
+                in_channels = out_channels
+            if self.multi_output and (i + 1) in bends:
+                stage.do_output = True
+            self.features.add_module(f"stage{i + 1}", stage)
+        self.features.add_module("final_pool", nn.AdaptiveAvgPool2d(output_size=1))
+        self.output = nn.Linear(in_features=in_channels, out_features=num_classes)
+        _kaiming_init(self)
+
+
+def get_resnetd(blocks, conv1_stride=True, width_scale=1.0, model_name=None, pretrained=False, root=None, **kwargs):
+    """Same contract as resnetd.py:109-194."""
+    table = {10: [1, 1, 1, 1], 12: [2, 1, 1, 1], 14: [2, 2, 1, 1], 16: [2, 2, 2, 1], 18: [2, 2, 2, 2],
+             34: [3, 4, 6, 3], 50: [3, 4, 6, 3], 101: [3, 4, 23, 3], 152: [3, 8, 36, 3], 200: [3, 24, 36, 3]}
+    if blocks not in table:
+        raise ValueError("Unsupported ResNet(D) with number of blocks: {}".format(blocks))
+    bottleneck = blocks >= 50
+    widths = [256, 512, 1024, 2048] if bottleneck else [64, 128, 256, 512]
+    channels, init_channels = _scaled([[w] * n for w, n in zip(widths, table[blocks])], 64, width_scale)
+    net = ResNetD(channels=channels, init_block_channels=init_channels, bottleneck=bottleneck,
+                  conv1_stride=conv1_stride, **kwargs)
+    _no_pretrained(pretrained, model_name)
+    return net
+
+
+RESNETD_VARIANTS = {"resnetd50b": 50, "resnetd101b": 101, "resnetd152b": 152}
+
+
+# ===== DeepLabv3 (deeplabv3.py) ========================================================================================
+class DeepLabv3FinalBlock(B200Module):
+    def __init__(self, in_channels, out_channels, bottleneck_factor=4):
+        super().__init__()
+        assert in_channels % bottleneck_factor == 0
+        mid = in_channels // bottleneck_factor
+        self.conv1 = conv3x3_block(in_channels=in_channels, out_channels=mid)
+        self.dropout = nn.Dropout(p=0.1, inplace=False)
+        self.conv2 = conv1x1(in_channels=mid, out_channels=out_channels, bias=True)
+
+    def forward(self, x, out_size):
+        return run_module(self, x, out_size=tuple(out_size))
+
+
+class ASPPAvgBranch(B200Module):
+    def __init__(self, in_channels, out_channels, upscale_out_size):
+        super().__init__()
+        self.upscale_out_size = upscale_out_size
+        self.pool = nn.AdaptiveAvgPool2d(1)
+        self.conv = conv1x1_block(in_channels=in_channels, out_channels=out_channels)
+
+
+class AtrousSpatialPyramidPooling(B200Module):
+    def __init__(self, in_channels, upscale_out_size):
+        super().__init__()
+        assert in_channels % 8 == 0
+        mid = in_channels // 8
+        self.branches = Concurrent()
+        self.branches.add_module("branch1", conv1x1_block(in_channels=in_channels, out_channels=mid))
+        for i, rate in enumerate([12, 24, 36]):
+            self.branches.add_module(f"branch{i + 2}", conv3x3_block(in_channels=in_channels, out_channels=mid,
+                                                                     padding=rate, dilation=rate))
+        self.branches.add_module("branch5", ASPPAvgBranch(in_channels=in_channels, out_channels=mid,
+                                                          upscale_out_size=upscale_out_size))
+        self.conv = conv1x1_block(in_channels=5 * mid, out_channels=mid)
+        self.dropout = nn.Dropout(p=0.5, inplace=False)
+
+
+class DeepLabv3(B200Module):
+    def __init__(self, backbone, backbone_out_channels=2048, aux=False, fixed_size=True, in_channels=3,
+                 in_size=(480, 480), num_classes=21):
+        super().__init__()
+        assert in_channels > 0
+        self.in_size, self.num_classes, self.aux, self.fixed_size = in_size, num_classes, aux, fixed_size
+        self.backbone = backbone
+        pool_out_size = (in_size[0] // 8, in_size[1] // 8) if fixed_size else None
+        self.pool = AtrousSpatialPyramidPooling(in_channels=backbone_out_channels, upscale_out_size=pool_out_size)
+        self.final_block = DeepLabv3FinalBlock(in_channels=backbone_out_channels // 8, out_channels=num_classes,
+                                               bottleneck_factor=1)
+        if aux:
+            self.aux_block = DeepLabv3FinalBlock(in_channels=backbone_out_channels // 2, out_channels=num_classes,
+                                                 bottleneck_factor=4)
+        _kaiming_init(self)
+
+
+def get_deeplabv3(backbone, num_classes, aux=False, model_name=None, pretrained=False, root=None, **kwargs):
+    net = DeepLabv3(backbone=backbone, num_classes=num_classes, aux=aux, **kwargs)
+    _no_pretrained(pretrained, model_name)
+    return net
+
+
+DEEPLABV3_VARIANTS = {  # name -> (ResNet(D) depth, default num_classes)   (deeplabv3.py:259-645)
+    "deeplabv3_resnetd50b_voc": (50, 21), "deeplabv3_resnetd101b_voc": (101, 21),
+    "deeplabv3_resnetd152b_voc": (152, 21), "deeplabv3_resnetd50b_coco": (50, 21),
+    "deeplabv3_resnetd101b_coco": (101, 21), "deeplabv3_resnetd152b_coco": (152, 21),
+    "deeplabv3_resnetd50b_ade20k": (50, 150), "deeplabv3_resnetd101b_ade20k": (101, 150),
+    "deeplabv3_resnetd50b_cityscapes": (50, 19), "deeplabv3_resnetd101b_cityscapes": (101, 19),
+}
+
+
+def _deeplab_ctor(name, depth, default_classes):
+    def ctor(pretrained_backbone=False, num_classes=default_classes, aux=True, **kwargs):
+        backbone = get_resnetd(blocks=depth, conv1_stride=False, model_name=f"resnetd{depth}b",
+                               pretrained=pretrained_backbone, ordinary_init=False, bends=(3,)).features
+        del backbone[-1]
+        return get_deeplabv3(backbone=backbone, num_classes=num_classes, aux=aux, model_name=name, **kwargs)
+    ctor.__name__ = name
+    return ctor

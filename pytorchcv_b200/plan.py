@@ -1,0 +1,825 @@
+"""Compile a pytorchcv module tree into a flat plan of fused sm_100a kernels and run it.
+
+The reference executes ~4 eager torch ops per block from Python (ConvBlock.forward, pytorchcv/models/common/conv.py:
+278-286).  Here `compile_module` walks the module tree ONCE, pattern-matching on the reference's class names and
+attributes (so it accepts both this package's mirror modules and real `pytorchcv` modules), folds BatchNorm into
+packed weights, lays activations out as NHWC in one arena with liveness-based reuse, and records one fused C-ABI op
+per block into a `pcv_plan`.  A forward is then: one ingest kernel (NCHW fp32 -> NHWC) + `pcv_plan_run`.
+
+Nothing here computes on the CPU or through torch ops: every op goes through libpcv_b200.so, and unsupported module
+patterns raise (NotImplementedError / ValueError) at compile time.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Any, Callable
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SIGMOID, ACT_SWISH, ACT_HSWISH, ACT_HSIGMOID, BF16, F32, ConvDesc
+
+_ALIGN = 1024  # arena / weight blob alignment (TMA needs 16 B; 1 KiB keeps every tensor sector- and line-aligned)
+
+
+def _esize(dtype: int) -> int:
+    return 4 if dtype == F32 else 2
+
+
+def _rup(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+def dtype_code(dtype) -> int:
+    if dtype in (BF16, "bf16", torch.bfloat16):
+        return BF16
+    if dtype in (F32, "fp32", "f32", torch.float32):
+        return F32
+    raise ValueError(f"unsupported dtype {dtype!r}: the path has a bf16 tier and an fp32 tier")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# symbolic tensors
+# ---------------------------------------------------------------------------------------------------------------
+@dataclass
+class Buf:
+    nbytes: int
+    first: int            # op index that defines it (-1: network input)
+    last: int = -1        # last op index that reads it
+    pinned: bool = False  # network input / output: never reused
+    offset: int = -1
+
+
+@dataclass
+class TRef:
+    """A logical NHWC activation: N x H x W pixels, C channels at `pitch` elements per pixel, inside `buf`."""
+    N: int
+    H: int
+    W: int
+    C: int
+    pitch: int
+    dtype: int
+    buf: Buf
+    ch_off: int = 0
+    layout: str = "nhwc"   # "nhwc" | "nchw" (fp32 network outputs written by the bilinear kernel)
+    flat: bool = False     # return as [N, C] (the reference's x.view(N, -1))
+
+    @property
+    def byte_off(self) -> int:
+        return self.ch_off * _esize(self.dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# activation / norm classification (activ.py:188-222, norm.py:95-115)
+# ---------------------------------------------------------------------------------------------------------------
+def act_code(m: nn.Module | None) -> int:
+    if m is None or isinstance(m, nn.Identity):
+        return ACT_NONE
+    if isinstance(m, nn.ReLU6):
+        return ACT_RELU6
+    if isinstance(m, nn.ReLU):
+        return ACT_RELU
+    if isinstance(m, nn.Sigmoid):
+        return ACT_SIGMOID
+    name = type(m).__name__
+    if name == "Swish" or isinstance(m, nn.SiLU):
+        return ACT_SWISH
+    if name == "HSwish" or isinstance(m, nn.Hardswish):
+        return ACT_HSWISH
+    if name == "HSigmoid" or isinstance(m, nn.Hardsigmoid):
+        return ACT_HSIGMOID
+    raise NotImplementedError(f"activation {name} is outside the B200 eval path (SURVEY 8a8)")
+
+
+def _check_bn(bn: nn.Module) -> None:
+    if not isinstance(bn, nn.BatchNorm2d):
+        raise NotImplementedError(f"normalization {type(bn).__name__} cannot be folded (needs per-sample statistics)")
+    if bn.training:
+        raise RuntimeError("pytorchcv_b200 is an eval-mode path: call net.eval() first (BatchNorm uses running stats)")
+    if bn.running_mean is None or bn.running_var is None:
+        raise NotImplementedError("BatchNorm2d without running statistics cannot be folded")
+
+
+def _one(v) -> int:
+    if isinstance(v, (tuple, list)):
+        if len(v) != 2 or v[0] != v[1]:
+            raise NotImplementedError(f"only square kernels / symmetric stride, padding, dilation are supported, got {v}")
+        return int(v[0])
+    return int(v)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# builder: records symbolic ops, then materialises them
+# ---------------------------------------------------------------------------------------------------------------
+class Builder:
+    def __init__(self, dtype: int, device: torch.device):
+        self.dtype = dtype
+        self.device = device
+        self.ops: list[Callable[[Any, Callable[[TRef], int]], None]] = []
+        self.bufs: list[Buf] = []
+        self.weight_jobs: list[tuple] = []   # (kind, payload) resolved in materialise()
+        self.weight_bytes = 0
+
+    # -- buffers ------------------------------------------------------------------------------------------------
+    def new(self, N, H, W, C, dtype=None, pitch=None, layout="nhwc", extra_bytes=0) -> TRef:
+        dtype = self.dtype if dtype is None else dtype
+        pitch = C if pitch is None else pitch
+        buf = Buf(nbytes=N * H * W * pitch * _esize(dtype) + extra_bytes, first=len(self.ops))
+        self.bufs.append(buf)
+        return TRef(N, H, W, C, pitch, dtype, buf, 0, layout)
+
+    @staticmethod
+    def view(t: TRef, ch_off: int, C: int) -> TRef:
+        return TRef(t.N, t.H, t.W, C, t.pitch, t.dtype, t.buf, t.ch_off + ch_off, t.layout)
+
+    def _use(self, *trefs: TRef | None) -> int:
+        idx = len(self.ops)
+        for t in trefs:
+            if t is not None:
+                t.buf.last = max(t.buf.last, idx)
+        return idx
+
+    def _wblob(self, nbytes: int) -> int:
+        off = self.weight_bytes
+        self.weight_bytes += _rup(max(nbytes, 16), 256)
+        return off
+
+    # -- ops ----------------------------------------------------------------------------------------------------
+    def conv(self, x: TRef, conv: nn.Conv2d, bn: nn.Module | None = None, act: int = ACT_NONE,
+             residual: TRef | None = None, out: TRef | None = None, out_f32: bool = False, flags: int = 0) -> TRef:
+        """One fused ConvBlock: conv + folded BN + optional residual + activation."""
+        if conv.padding_mode != "zeros" or isinstance(conv.padding, str):
+            raise NotImplementedError("only zero padding with integer sizes is supported")
+        kh, kw = conv.kernel_size
+        k_stride, k_pad, k_dil = _one(conv.stride), _one(conv.padding), _one(conv.dilation)
+        cin, cout, groups = conv.in_channels, conv.out_channels, conv.groups
+        pad_cin = 0
+        if cin != x.C:
+            # the ingest pads the image's channels with zeros up to a multiple of 8 (TMA needs 16-byte strides):
+            # widen the weights with zero input channels to match
+            if groups != 1 or x.C < cin:
+                raise ValueError(f"conv expects {cin} input channels, tensor has {x.C}")
+            pad_cin = x.C - cin
+        if bn is not None:
+            _check_bn(bn)
+        Ho = (x.H + 2 * k_pad - k_dil * (kh - 1) - 1) // k_stride + 1
+        Wo = (x.W + 2 * k_pad - k_dil * (kw - 1) - 1) // k_stride + 1
+        if Ho <= 0 or Wo <= 0:
+            raise ValueError(f"convolution output is empty for input {x.H}x{x.W}")
+        odt = F32 if out_f32 else self.dtype
+        if out is None:
+            out = self.new(x.N, Ho, Wo, cout, dtype=odt)
+        if (out.N, out.H, out.W, out.C, out.dtype) != (x.N, Ho, Wo, cout, odt):
+            raise ValueError("conv output view has the wrong shape")
+        if residual is not None and (residual.N, residual.H, residual.W, residual.C) != (x.N, Ho, Wo, cout):
+            raise ValueError("residual shape does not match the conv output")
+        d = ConvDesc(N=x.N, H=x.H, W=x.W, Cin=x.C, Cout=cout, kh=kh, kw=kw, stride=k_stride, pad=k_pad, dil=k_dil,
+                     groups=groups, act=act, in_pitch=x.pitch, out_pitch=out.pitch,
+                     res_pitch=residual.pitch if residual is not None else 0,
+                     flags=flags | (_lib.CONV_OUT_F32 if (out_f32 and self.dtype == BF16) else 0))
+        wb, bb = C.c_size_t(), C.c_size_t()
+        _lib.call("pcv_conv_packed_bytes", C.byref(d), self.dtype, C.byref(wb), C.byref(bb))
+        w_off, b_off = self._wblob(wb.value), self._wblob(bb.value)
+        self.weight_jobs.append(("conv", (d, conv, bn, pad_cin, w_off, b_off)))
+        self._use(x, residual, out)
+        dtype = self.dtype
+
+        def emit(plan, ptr, wptr):
+            _lib.call("pcv_conv2d_bias_act", plan, C.byref(d), dtype, ptr(x), wptr(w_off), wptr(b_off),
+                      ptr(residual) if residual is not None else None, ptr(out), None)
+        self.ops.append(emit)
+        return out
+
+    def linear(self, x: TRef, fc: nn.Linear, out_f32: bool = True) -> TRef:
+        """nn.Linear on pooled features == 1x1 conv on a 1x1 map (resnet.py:320-322,335-336)."""
+        if (x.H, x.W) != (1, 1):
+            raise ValueError("Linear expects a 1x1 feature map (the reference flattens [N,C,1,1])")
+        shim = _ConvShim(fc.weight.view(fc.out_features, fc.in_features, 1, 1), fc.bias)
+        return self.conv(x, shim, None, ACT_NONE, out_f32=out_f32)
+
+    def maxpool(self, x: TRef, k: int, stride: int, pad: int) -> TRef:
+        Ho = (x.H + 2 * pad - k) // stride + 1
+        Wo = (x.W + 2 * pad - k) // stride + 1
+        out = self.new(x.N, Ho, Wo, x.C, dtype=x.dtype)
+        self._use(x, out)
+        self.ops.append(lambda plan, ptr, wptr: _lib.call(
+            "pcv_maxpool2d", plan, x.dtype, x.N, x.H, x.W, x.C, k, stride, pad, ptr(x), x.pitch, ptr(out), out.pitch,
+            None))
+        return out
+
+    def gap(self, x: TRef, out_dtype: int | None = None) -> TRef:
+        out_dtype = x.dtype if out_dtype is None else out_dtype
+        out = self.new(x.N, 1, 1, x.C, dtype=out_dtype)
+        self._use(x, out)
+        self.ops.append(lambda plan, ptr, wptr: _lib.call(
+            "pcv_global_avgpool", plan, x.dtype, x.N, x.H * x.W, x.C, ptr(x), x.pitch, ptr(out), out_dtype, None))
+        return out
+
+    def se_gate(self, pooled: TRef, w1: torch.Tensor, b1, w2: torch.Tensor, b2, mid_act: int, out_act: int) -> TRef:
+        """SEBlock excite (att.py:99-102): gate = out_act(W2 @ mid_act(W1 @ pooled + b1) + b2), all fp32."""
+        N, Cc = pooled.N, pooled.C
+        cmid = w1.shape[0]
+        gate = self.new(N, 1, 1, Cc, dtype=F32, extra_bytes=N * cmid * 4)
+        offs = []
+        for t in (w1, b1, w2, b2):
+            offs.append(None if t is None else self._wblob(t.numel() * 4))
+            if t is not None:
+                self.weight_jobs.append(("raw", (t, offs[-1])))
+        self._use(pooled, gate)
+
+        def emit(plan, ptr, wptr):
+            _lib.call("pcv_se_excite", plan, N, Cc, cmid, ptr(pooled), wptr(offs[0]),
+                      wptr(offs[1]) if offs[1] is not None else None, wptr(offs[2]),
+                      wptr(offs[3]) if offs[3] is not None else None, mid_act, out_act, ptr(gate), None)
+        self.ops.append(emit)
+        return gate
+
+    def se_scale(self, x: TRef, gate: TRef, identity: TRef | None, act: int) -> TRef:
+        for t in (x, identity):
+            if t is not None and t.pitch != t.C:
+                raise NotImplementedError("SE scale needs dense tensors")
+        out = self.new(x.N, x.H, x.W, x.C, dtype=x.dtype)
+        self._use(x, gate, identity, out)
+        self.ops.append(lambda plan, ptr, wptr: _lib.call(
+            "pcv_se_scale_add_act", plan, x.dtype, x.N, x.H * x.W, x.C, ptr(x), ptr(gate),
+            ptr(identity) if identity is not None else None, act, ptr(out), None))
+        return out
+
+    def add_act(self, a: TRef, b: TRef, act: int) -> TRef:
+        if (a.N, a.H, a.W, a.C) != (b.N, b.H, b.W, b.C) or a.pitch != a.C or b.pitch != b.C:
+            raise ValueError("add needs two dense tensors of the same shape")
+        out = self.new(a.N, a.H, a.W, a.C, dtype=a.dtype)
+        self._use(a, b, out)
+        self.ops.append(lambda plan, ptr, wptr: _lib.call(
+            "pcv_add_act", plan, a.dtype, a.N * a.H * a.W * a.C, ptr(a), ptr(b), act, ptr(out), None))
+        return out
+
+    def bilinear(self, x: TRef, Hout: int, Wout: int, out: TRef | None = None, nchw_f32: bool = False) -> TRef:
+        if nchw_f32:
+            out = self.new(x.N, Hout, Wout, x.C, dtype=F32, layout="nchw")
+        elif out is None:
+            out = self.new(x.N, Hout, Wout, x.C, dtype=x.dtype)
+        self._use(x, out)
+        self.ops.append(lambda plan, ptr, wptr: _lib.call(
+            "pcv_bilinear_upsample_ac", plan, x.dtype, x.N, x.H, x.W, x.C, ptr(x), x.pitch, Hout, Wout, ptr(out),
+            out.pitch, 1 if nchw_f32 else 0, None))
+        return out
+
+    def egress(self, x: TRef) -> TRef:
+        out = self.new(x.N, x.H, x.W, x.C, dtype=F32, layout="nchw")
+        self._use(x, out)
+        self.ops.append(lambda plan, ptr, wptr: _lib.call(
+            "pcv_nhwc_to_nchw_f32", plan, x.dtype, x.N, x.C, x.H, x.W, ptr(x), x.pitch, ptr(out), None))
+        return out
+
+
+class _ConvShim:
+    """Presents an nn.Linear (or SE fc) as the nn.Conv2d attribute set Builder.conv reads."""
+
+    def __init__(self, weight4d: torch.Tensor, bias):
+        self.weight, self.bias = weight4d, bias
+        self.out_channels, self.in_channels = weight4d.shape[0], weight4d.shape[1]
+        self.kernel_size, self.stride, self.padding, self.dilation = (1, 1), (1, 1), (0, 0), (1, 1)
+        self.groups, self.padding_mode = 1, "zeros"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# lowering rules, keyed by the reference's class names
+# ---------------------------------------------------------------------------------------------------------------
+LOWER: dict[str, Callable] = {}
+
+
+def lowers(*names):
+    def deco(fn):
+        for n in names:
+            LOWER[n] = fn
+        return fn
+    return deco
+
+
+def lower(b: Builder, m: nn.Module, x, **kw):
+    fn = LOWER.get(type(m).__name__)
+    if fn is None and type(m) is nn.Sequential:
+        fn = _lower_sequential
+    if fn is None:
+        raise NotImplementedError(
+            f"module {type(m).__name__} is outside the B200 eval path (no CPU fallback; see SURVEY.md section 8)")
+    return fn(b, m, x, **kw)
+
+
+def _lower_sequential(b, m, x, **kw):
+    mods = list(m.children())
+    for i, child in enumerate(mods):
+        x = lower(b, child, x, **(kw if i == len(mods) - 1 else {}))
+    return x
+
+
+@lowers("Dropout", "Identity")
+def _lower_identity(b, m, x, **kw):
+    if isinstance(m, nn.Dropout) and m.training:
+        raise RuntimeError("pytorchcv_b200 is an eval-mode path: call net.eval() first")
+    return x
+
+
+@lowers("Conv2d")
+def _lower_conv2d(b, m, x, out=None, out_f32=False, **kw):
+    """bare conv1x1 / conv3x3 (conv.py:89-164): no BN, no activation."""
+    return b.conv(x, m, None, ACT_NONE, out=out, out_f32=out_f32)
+
+
+@lowers("Linear")
+def _lower_linear(b, m, x, **kw):
+    return b.linear(x, m)
+
+
+@lowers("ConvBlock")
+def _lower_convblock(b, m, x, residual=None, post_act=None, out=None, **kw):
+    """ConvBlock.forward (conv.py:278-286); `residual`/`post_act` carry the enclosing unit's add + activation."""
+    if getattr(m, "use_pad", False):
+        raise NotImplementedError("ConvBlock with asymmetric ZeroPad2d padding is outside the B200 eval path")
+    bn = m.bn if m.normalize else None
+    act = act_code(m.activ) if m.activate else ACT_NONE
+    if residual is None and post_act is None:
+        return b.conv(x, m.conv, bn, act, out=out)
+    post = ACT_NONE if post_act is None else post_act
+    if act == ACT_NONE:
+        return b.conv(x, m.conv, bn, post, residual=residual, out=out)     # fused: act(conv + residual)
+    y = b.conv(x, m.conv, bn, act)                                         # block has its own activation
+    return b.add_act(y, residual, post) if residual is not None else y
+
+
+@lowers("DwsConvBlock")
+def _lower_dws(b, m, x, **kw):
+    """DwsConvBlock.forward (conv.py:605-608): depthwise ConvBlock then pointwise ConvBlock."""
+    return lower(b, m.pw_conv, lower(b, m.dw_conv, x), **kw)
+
+
+@lowers("MaxPool2d")
+def _lower_maxpool(b, m, x, **kw):
+    if m.ceil_mode or _one(m.dilation) != 1:
+        raise NotImplementedError("MaxPool2d with ceil_mode / dilation is outside the B200 eval path")
+    return b.maxpool(x, _one(m.kernel_size), _one(m.stride if m.stride is not None else m.kernel_size),
+                     _one(m.padding))
+
+
+@lowers("AvgPool2d")
+def _lower_avgpool(b, m, x, **kw):
+    """The reference only uses AvgPool2d(7, stride=1) on a 7x7 map, i.e. a global mean (resnet.py:316-318)."""
+    k = _one(m.kernel_size)
+    if k != x.H or k != x.W or _one(m.padding) != 0:
+        raise NotImplementedError(f"AvgPool2d({k}) on a {x.H}x{x.W} map is not a global pool (SURVEY appendix B)")
+    return b.gap(x)
+
+
+@lowers("AdaptiveAvgPool2d")
+def _lower_adaptive(b, m, x, **kw):
+    if m.output_size not in (1, (1, 1)):
+        raise NotImplementedError("only AdaptiveAvgPool2d(1) is supported")
+    return b.gap(x)
+
+
+def _se_parts(b, m):
+    if m.use_conv:
+        c1, c2 = m.conv1, m.conv2
+        w1, w2 = c1.weight.view(c1.out_channels, -1), c2.weight.view(c2.out_channels, -1)
+    else:
+        c1, c2 = m.fc1, m.fc2
+        w1, w2 = c1.weight, c2.weight
+    return w1, c1.bias, w2, c2.bias, act_code(m.activ), act_code(m.sigmoid)
+
+
+@lowers("SEBlock")
+def _lower_se(b, m, x, identity=None, post_act=ACT_NONE, **kw):
+    """SEBlock.forward (att.py:94-105): x * sigmoid(W2 relu(W1 mean(x) + b1) + b2) [+ identity, act]."""
+    w1, b1, w2, b2, mid_act, out_act = _se_parts(b, m)
+    pooled = b.gap(x, out_dtype=F32)
+    gate = b.se_gate(pooled, w1, b1, w2, b2, mid_act, out_act)
+    return b.se_scale(x, gate, identity, post_act)
+
+
+@lowers("ResBlock", "ResBottleneck", "ResNeXtBottleneck")
+def _lower_resbody(b, m, x, residual=None, post_act=None, **kw):
+    """conv1 -> conv2 [-> conv3] (resnet.py:63-66,136-140; resnext.py:56-59); the last conv takes the fusion."""
+    convs = [m.conv1, m.conv2] + ([m.conv3] if hasattr(m, "conv3") else [])
+    for c in convs[:-1]:
+        x = lower(b, c, x)
+    return lower(b, convs[-1], x, residual=residual, post_act=post_act)
+
+
+@lowers("ResUnit", "ResNeXtUnit")
+def _lower_resunit(b, m, x, **kw):
+    """ResUnit.forward (resnet.py:221-229): act(body(x) + (identity_conv(x) | x))."""
+    identity = lower(b, m.identity_conv, x) if m.resize_identity else x
+    return lower(b, m.body, x, residual=identity, post_act=act_code(m.activ))
+
+
+@lowers("SEResNeXtUnit", "SEResUnit")
+def _lower_seresnext_unit(b, m, x, **kw):
+    """SEResNeXtUnit.forward (seresnext.py:57-66): relu(se(body(x)) + identity)."""
+    identity = lower(b, m.identity_conv, x) if m.resize_identity else x
+    y = lower(b, m.body, x)
+    return lower(b, m.se, y, identity=identity, post_act=act_code(m.activ))
+
+
+@lowers("ResInitBlock")
+def _lower_resinit(b, m, x, **kw):
+    return lower(b, m.pool, lower(b, m.conv, x))
+
+
+@lowers("SEInitBlock")
+def _lower_seinit(b, m, x, **kw):
+    for c in (m.conv1, m.conv2, m.conv3):
+        x = lower(b, c, x)
+    return lower(b, m.pool, x)
+
+
+@lowers("LinearBottleneck")
+def _lower_linear_bottleneck(b, m, x, **kw):
+    """LinearBottleneck.forward (mobilenetv2.py:62-71): [1x1 expand] -> dw3x3 -> 1x1 linear (+x), no final act."""
+    y = lower(b, m.conv1, x) if m.use_exp_conv else x
+    y = lower(b, m.conv2, y)
+    return lower(b, m.conv3, y, residual=x if m.residual else None, post_act=None)
+
+
+@lowers("MultiOutputSequential")
+def _lower_multi_output(b, m, x, **kw):
+    """MultiOutputSequential.forward (arch.py:332-347)."""
+    outs = []
+    for child in m.children():
+        x = lower(b, child, x)
+        if getattr(child, "do_output", False):
+            outs.append(x)
+        elif getattr(child, "do_output2", False):
+            raise NotImplementedError("do_output2 children are outside the B200 eval path")
+    if m.multi_output:
+        return [x] + outs if m.return_last else outs
+    if m.dual_output:
+        return x, outs
+    return x
+
+
+@lowers("Concurrent")
+def _lower_concurrent(b, m, x, **kw):
+    """Concurrent.forward (arch.py:84-95), merge_type "cat": branches write straight into channel slices."""
+    if m.merge_type != "cat" or m.axis != 1:
+        raise NotImplementedError("only Concurrent(cat, axis=1) is supported")
+    branches = list(m.children())
+    widths = [_branch_width(br) for br in branches]
+    Ho, Wo = x.H, x.W
+    cat = b.new(x.N, Ho, Wo, sum(widths))
+    off = 0
+    for br, wd in zip(branches, widths):
+        y = lower(b, br, x, out=Builder.view(cat, off, wd))
+        if y.buf is not cat.buf:
+            raise NotImplementedError(f"branch {type(br).__name__} cannot write into a concat slice")
+        off += wd
+    return cat
+
+
+def _branch_width(br: nn.Module) -> int:
+    convs = [mod for mod in br.modules() if isinstance(mod, nn.Conv2d)]
+    if not convs:
+        raise NotImplementedError(f"cannot infer the width of branch {type(br).__name__}")
+    return convs[-1].out_channels
+
+
+@lowers("ASPPAvgBranch")
+def _lower_aspp_avg(b, m, x, out=None, **kw):
+    """ASPPAvgBranch.forward (deeplabv3.py:80-87): global mean -> 1x1 ConvBlock -> bilinear broadcast."""
+    size = m.upscale_out_size if m.upscale_out_size is not None else (x.H, x.W)
+    y = lower(b, m.conv, b.gap(x))
+    return b.bilinear(y, size[0], size[1], out=out)
+
+
+@lowers("AtrousSpatialPyramidPooling")
+def _lower_aspp(b, m, x, **kw):
+    return lower(b, m.dropout, lower(b, m.conv, lower(b, m.branches, x)))
+
+
+@lowers("DeepLabv3FinalBlock")
+def _lower_deeplab_final(b, m, x, out_size=None, **kw):
+    """DeepLabv3FinalBlock.forward (deeplabv3.py:49-54); the result is the fp32 NCHW tensor the reference returns."""
+    y = lower(b, m.conv2, lower(b, m.dropout, lower(b, m.conv1, x)))
+    return b.bilinear(y, out_size[0], out_size[1], nchw_f32=True)
+
+
+@lowers("DeepLabv3")
+def _lower_deeplab(b, m, x, **kw):
+    """DeepLabv3.forward (deeplabv3.py:199-208)."""
+    in_size = m.in_size if m.fixed_size else (x.H, x.W)
+    feats = lower(b, m.backbone, x)
+    x4, x3 = feats[0], feats[1]
+    y = lower(b, m.final_block, lower(b, m.pool, x4), out_size=in_size)
+    if m.aux:
+        return y, lower(b, m.aux_block, x3, out_size=in_size)
+    return y
+
+
+def _flat(t: TRef) -> TRef:
+    t.flat = True
+    return t
+
+
+@lowers("ResNet", "SEResNeXt", "SEResNet", "ResNeXt", "MobileNet")
+def _lower_classifier(b, m, x, **kw):
+    """features -> view(N,-1) -> Linear (resnet.py:333-337, seresnext.py:136-140)."""
+    return _flat(lower(b, m.output, lower(b, m.features, x)))
+
+
+@lowers("MobileNetV2")
+def _lower_mobilenetv2(b, m, x, **kw):
+    """features -> bare conv1x1 classifier on the 1x1 map -> view (mobilenetv2.py:152-156)."""
+    return _flat(lower(b, m.output, lower(b, m.features, x), out_f32=True))
+
+
+@lowers("ResNetD")
+def _lower_resnetd(b, m, x, **kw):
+    """ResNetD.forward (resnetd.py:98-106)."""
+    outs = lower(b, m.features, x)
+    if not isinstance(outs, list):
+        outs = [outs]
+    logits = _flat(lower(b, m.output, outs[0]))
+    return [logits] + outs[1:] if m.multi_output else logits
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# compiled module
+# ---------------------------------------------------------------------------------------------------------------
+def _assign_offsets(bufs: list[Buf]) -> int:
+    """Greedy lowest-offset placement with lifetime-overlap checks; returns the arena size."""
+    placed: list[Buf] = []
+    top = 0
+    for buf in sorted(bufs, key=lambda z: (z.first, -z.nbytes)):
+        size = _rup(buf.nbytes, _ALIGN)
+        lo, hi = buf.first, (1 << 60) if buf.pinned else max(buf.last, buf.first)
+        conflicts = sorted(
+            ((p.offset, p.offset + _rup(p.nbytes, _ALIGN)) for p in placed
+             if not (((1 << 60) if p.pinned else max(p.last, p.first)) < lo or p.first > hi)),
+            key=lambda iv: iv[0])
+        off = 0
+        for s, e in conflicts:
+            if off + size <= s:
+                break
+            off = max(off, e)
+        buf.offset = off
+        placed.append(buf)
+        top = max(top, off + size)
+    return top
+
+
+def weights_signature(module: nn.Module) -> tuple:
+    return tuple((id(t), t._version) for t in list(module.parameters()) + list(module.buffers()))
+
+
+class CompiledModule:
+    """A module tree compiled for one input shape / tier / device."""
+
+    def __init__(self, module: nn.Module, in_shape: tuple[int, int, int, int], dtype="bf16",
+                 device: torch.device | str | None = None, graph: bool = False, lower_kwargs: dict | None = None):
+        lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("pytorchcv_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.dtype = dtype_code(dtype)
+        self.in_shape = tuple(int(v) for v in in_shape)
+        self.use_graph = graph
+        self.signature = weights_signature(module)
+        N, Cin, H, W = self.in_shape
+
+        b = Builder(self.dtype, self.device)
+        x = b.new(N, H, W, _rup(Cin, 8))
+        x.buf.first = -1
+        x.buf.pinned = True
+        self._in = x
+        self._in_channels = Cin
+        result = lower(b, module, x, **(lower_kwargs or {}))
+        self._structure, trefs = _flatten(result)
+        outs = []
+        for t in trefs:
+            if t.layout == "nhwc" and not (t.flat and t.dtype == F32):
+                flat = t.flat
+                t = b.egress(t)
+                t.flat = flat
+            t.buf.pinned = True
+            outs.append(t)
+        self._outs = outs
+
+        arena_bytes = _assign_offsets(b.bufs)
+        with torch.cuda.device(self.device):
+            self.arena = torch.zeros(arena_bytes + _ALIGN, dtype=torch.uint8, device=self.device)
+            self.weights = torch.zeros(b.weight_bytes + _ALIGN, dtype=torch.uint8, device=self.device)
+            abase = _rup(self.arena.data_ptr(), _ALIGN)
+            wbase = _rup(self.weights.data_ptr(), _ALIGN)
+            self._abase = abase
+
+            def ptr(t: TRef) -> int:
+                return abase + t.buf.offset + t.byte_off
+
+            def wptr(off: int) -> int:
+                return wbase + off
+
+            self._pack_weights(b, wptr)
+            handle = C.c_void_p()
+            _lib.call("pcv_plan_create", C.byref(handle))
+            self._plan = handle
+            for emit in b.ops:
+                emit(self._plan, ptr, wptr)
+            torch.cuda.synchronize(self.device)
+        self._in_ptr = ptr(self._in)
+        self.arena_bytes = arena_bytes
+        self.weight_bytes = b.weight_bytes
+        self.num_ops = lib.pcv_plan_num_ops(self._plan)
+        self.num_launches = lib.pcv_plan_num_launches(self._plan) + 1  # + ingest
+        self._out_tensors = [self._tensor_of(t) for t in outs]
+        self._graph_stream = torch.cuda.Stream(device=self.device) if graph else None
+
+    # -- weights ------------------------------------------------------------------------------------------------
+    def _dev_f32(self, t: torch.Tensor | None):
+        if t is None:
+            return None
+        return t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+
+    def _pack_weights(self, b: Builder, wptr) -> None:
+        keep = []
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        for kind, payload in b.weight_jobs:
+            if kind == "raw":
+                t, off = payload
+                src = self._dev_f32(t)
+                keep.append(src)
+                rel = wptr(off) - self.weights.data_ptr()
+                self.weights[rel:rel + src.numel() * 4].copy_(src.view(-1).view(torch.uint8))
+                continue
+            d, conv, bn, pad_cin, w_off, b_off = payload
+            w = self._dev_f32(conv.weight)
+            if pad_cin:
+                w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, pad_cin)).contiguous()
+            cb = self._dev_f32(conv.bias)
+            if bn is not None:
+                g = self._dev_f32(bn.weight) if bn.weight is not None else torch.ones_like(self._dev_f32(bn.running_var))
+                be = self._dev_f32(bn.bias) if bn.bias is not None else torch.zeros_like(g)
+                mu, var, eps = self._dev_f32(bn.running_mean), self._dev_f32(bn.running_var), float(bn.eps)
+            else:
+                g = be = mu = var = None
+                eps = 0.0
+            keep += [w, cb, g, be, mu, var]
+            _lib.call("pcv_pack_conv_weights", C.byref(d), self.dtype, w.data_ptr(),
+                      cb.data_ptr() if cb is not None else None,
+                      g.data_ptr() if g is not None else None, be.data_ptr() if be is not None else None,
+                      mu.data_ptr() if mu is not None else None, var.data_ptr() if var is not None else None,
+                      eps, wptr(w_off), wptr(b_off), stream)
+        torch.cuda.synchronize(self.device)
+        del keep
+
+    # -- outputs ------------------------------------------------------------------------------------------------
+    def _tensor_of(self, t: TRef) -> torch.Tensor:
+        if t.dtype != F32:
+            raise AssertionError("network outputs are fp32")
+        start = (self._abase - self.arena.data_ptr()) + t.buf.offset
+        if t.layout == "nchw":
+            n = t.N * t.C * t.H * t.W
+            out = self.arena[start:start + 4 * n].view(torch.float32).view(t.N, t.C, t.H, t.W)
+        else:  # flat fp32 logits written NHWC with H = W = 1
+            n = t.N * t.pitch
+            out = self.arena[start:start + 4 * n].view(torch.float32).view(t.N, t.pitch)[:, :t.C]
+        if t.flat:
+            out = out.reshape(t.N, -1)
+        return out
+
+    # -- run ----------------------------------------------------------------------------------------------------
+    def __call__(self, x: torch.Tensor):
+        if tuple(x.shape) != self.in_shape:
+            raise ValueError(f"compiled for input {self.in_shape}, got {tuple(x.shape)}")
+        if x.device != self.device:
+            raise ValueError(f"compiled for {self.device}, input is on {x.device}: there is no CPU fallback")
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        N, Cin, H, W = self.in_shape
+        cur = torch.cuda.current_stream(self.device)
+        if self.use_graph:
+            gs = self._graph_stream
+            gs.wait_stream(cur)
+            _lib.call("pcv_nchw_f32_to_nhwc", None, self.dtype, N, Cin, H, W, x.data_ptr(), self._in_ptr,
+                      self._in.pitch, gs.cuda_stream)
+            _lib.call("pcv_plan_graph_launch", self._plan, gs.cuda_stream)
+            cur.wait_stream(gs)
+            x.record_stream(gs)
+        else:
+            _lib.call("pcv_nchw_f32_to_nhwc", None, self.dtype, N, Cin, H, W, x.data_ptr(), self._in_ptr,
+                      self._in.pitch, cur.cuda_stream)
+            _lib.call("pcv_plan_run", self._plan, cur.cuda_stream)
+        return _unflatten(self._structure, list(self._out_tensors))
+
+    def profile(self) -> list[tuple[str, float, float, float]]:
+        """[(op name, ms, algorithmic FLOPs, algorithmic bytes)] for one eager pass (synchronises)."""
+        lib = _lib.load()
+        n = self.num_ops
+        ms = (C.c_float * n)()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.call("pcv_plan_profile", self._plan, stream, ms, n)
+        rows = []
+        for i in range(n):
+            fl, by = C.c_double(), C.c_double()
+            _lib.call("pcv_plan_op_cost", self._plan, i, C.byref(fl), C.byref(by))
+            rows.append((lib.pcv_plan_op_name(self._plan, i).decode(), float(ms[i]), fl.value, by.value))
+        return rows
+
+    def __del__(self):
+        plan = getattr(self, "_plan", None)
+        if plan is not None and _lib._lib is not None:
+            try:
+                _lib._lib.pcv_plan_destroy(plan)
+            except Exception:
+                pass
+            self._plan = None
+
+
+def _flatten(obj):
+    if isinstance(obj, TRef):
+        return None, [obj]
+    if isinstance(obj, (list, tuple)):
+        specs, flat = [], []
+        for o in obj:
+            s, f = _flatten(o)
+            specs.append((s, len(f)))
+            flat += f
+        return (type(obj), specs), flat
+    raise TypeError(f"unexpected lowering result {type(obj)}")
+
+
+def _unflatten(spec, flat):
+    if spec is None:
+        return flat.pop(0)
+    typ, specs = spec
+    return typ(_unflatten(s, flat) for s, _ in specs)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# per-module cache used by the mirror modules' forward() and by accelerate()
+# ---------------------------------------------------------------------------------------------------------------
+_DEFAULT = {"dtype": "bf16", "graph": False}
+
+
+def set_default_precision(dtype: str) -> None:
+    """Tier used by modules that were not explicitly accelerate()d: "bf16" (default) or "fp32"."""
+    dtype_code(dtype)
+    _DEFAULT["dtype"] = dtype
+
+
+def run_module(module: nn.Module, x: torch.Tensor, dtype=None, graph=None, check_weights: bool = True, **lower_kwargs):
+    """forward() of every mirror block/net: compile on first use (per input shape & tier), then run the plan."""
+    if not isinstance(x, torch.Tensor) or x.dim() != 4:
+        raise ValueError("expected an NCHW tensor")
+    if not x.is_cuda:
+        raise RuntimeError("pytorchcv_b200 runs on CUDA (sm_100a) only; there is no CPU fallback — move the input "
+                           "to the GPU or use the reference package on CPU")
+    dtype = _DEFAULT["dtype"] if dtype is None else dtype
+    graph = _DEFAULT["graph"] if graph is None else graph
+    cache = module.__dict__.setdefault("_pcv_cache", {})
+    key = (tuple(x.shape), dtype_code(dtype), x.device.index, bool(graph), tuple(sorted(lower_kwargs.items())))
+    cm = cache.get(key)
+    if cm is not None and check_weights and cm.signature != weights_signature(module):
+        cm = None  # parameters were replaced or modified in place (load_state_dict, .to(), optimizer step)
+    if cm is None:
+        cm = CompiledModule(module, tuple(x.shape), dtype=dtype, device=x.device, graph=graph,
+                            lower_kwargs=lower_kwargs)
+        cache[key] = cm
+    return cm(x)
+
+
+def invalidate(module: nn.Module) -> None:
+    """Drop every compiled plan cached on `module` (and its sub-modules)."""
+    for mod in module.modules():
+        mod.__dict__.pop("_pcv_cache", None)
+
+
+class Accelerated(nn.Module):
+    """Drop-in wrapper returned by accelerate(): same call signature as the wrapped reference module."""
+
+    def __init__(self, net: nn.Module, dtype="bf16", graph: bool = False, check_weights: bool = True):
+        super().__init__()
+        self.net = net
+        self._dtype, self._graph, self._check = dtype, graph, check_weights
+
+    def forward(self, x):
+        return run_module(self.net, x, dtype=self._dtype, graph=self._graph, check_weights=self._check)
+
+    def compiled(self, x: torch.Tensor) -> CompiledModule:
+        self.forward(x)
+        key = (tuple(x.shape), dtype_code(self._dtype), x.device.index, bool(self._graph), ())
+        return self.net.__dict__["_pcv_cache"][key]
+
+
+def accelerate(net: nn.Module, dtype="bf16", graph: bool = False, check_weights: bool = True) -> Accelerated:
+    """Compile an eval-mode pytorchcv network (reference or mirror modules) for the B200 path.
+
+    Opt-in per model instance (the reference's own _test()s call .backward() on eval nets, so a
+    global monkey-patch of ConvBlock.forward would break them)."""
+    if net.training:
+        raise RuntimeError("pytorchcv_b200 is an eval-mode path: call net.eval() first")
+    dtype_code(dtype)
+    return Accelerated(net, dtype=dtype, graph=graph, check_weights=check_weights)

@@ -1,0 +1,187 @@
+"""First-light diagnostics for the CUDA kernels on a real B200 (run under gpurun).
+
+Each case runs in its own subprocess with a timeout, so a hung mbarrier pipeline cannot take the box down, and
+prints one line: name, status, max relative error vs a torch-CPU fp32 evaluation of the same fused block, plus a
+short mismatch pattern (which rows / channels are wrong) to make descriptor bugs identifiable from the log alone.
+
+    python scripts/gpu_diag.py            # all cases
+    python scripts/gpu_diag.py --case N   # one case in-process (what the parent spawns)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+# name, N, H, W, Cin, Cout, k, stride, pad, dil, groups, act, residual, flags, dtype
+CASES = [
+    ("gemm_1x1_64_64_tiled",      2, 16, 16,  64,  64, 1, 1, 0, 1, 1, 0, 0, 0, "bf16"),
+    ("gemm_1x1_128_128",          2, 16, 16, 128, 128, 1, 1, 0, 1, 1, 0, 0, 0, "bf16"),
+    ("gemm_1x1_res_relu",         2, 16, 16, 128, 128, 1, 1, 0, 1, 1, 1, 1, 0, "bf16"),
+    ("gemm_1x1_im2col_mode",      2, 16, 16,  64,  64, 1, 1, 0, 1, 1, 0, 0, 4, "bf16"),
+    ("gemm_1x1_mtail",            3, 14, 14,  64,  64, 1, 1, 0, 1, 1, 1, 0, 0, "bf16"),
+    ("gemm_1x1_bn32",             2, 16, 16,  32,  32, 1, 1, 0, 1, 1, 2, 0, 0, "bf16"),
+    ("gemm_1x1_odd_16_24",        2, 16, 16,  16,  24, 1, 1, 0, 1, 1, 0, 0, 0, "bf16"),
+    ("gemm_1x1_odd_144_32_res",   2, 28, 28, 144,  32, 1, 1, 0, 1, 1, 0, 1, 0, "bf16"),
+    ("gemm_1x1_960_160",          2,  7,  7, 960, 160, 1, 1, 0, 1, 1, 0, 0, 0, "bf16"),
+    ("conv3x3_64_64",             4, 14, 14,  64,  64, 3, 1, 1, 1, 1, 1, 0, 0, "bf16"),
+    ("conv3x3_128_256_res",       2, 28, 28, 128, 256, 3, 1, 1, 1, 1, 1, 1, 0, "bf16"),
+    ("conv3x3_s2",                2, 28, 28,  64, 128, 3, 2, 1, 1, 1, 1, 0, 0, "bf16"),
+    ("conv1x1_s2",                2, 28, 28, 256, 512, 1, 2, 0, 1, 1, 0, 0, 0, "bf16"),
+    ("conv3x3_d2",                2, 30, 30,  64,  64, 3, 1, 2, 2, 1, 1, 0, 0, "bf16"),
+    ("conv3x3_d12",               1, 60, 60, 128,  64, 3, 1, 12, 12, 1, 1, 0, 0, "bf16"),
+    ("conv3x3_d36",               1, 60, 60, 128,  64, 3, 1, 36, 36, 1, 1, 0, 0, "bf16"),
+    ("conv7x7_s2_c8",             2, 64, 64,   8,  64, 7, 2, 3, 1, 1, 1, 0, 0, "bf16"),
+    ("conv3x3_s2_c8",             2, 64, 64,   8,  32, 3, 2, 1, 1, 1, 2, 0, 0, "bf16"),
+    ("grouped_g32_c128",          2, 28, 28, 128, 128, 3, 1, 1, 1, 32, 1, 0, 0, "bf16"),
+    ("grouped_g32_c256_s2",       2, 28, 28, 256, 256, 3, 2, 1, 1, 32, 1, 0, 0, "bf16"),
+    ("grouped_g32_c1024",         2,  7,  7, 1024, 1024, 3, 1, 1, 1, 32, 1, 0, 0, "bf16"),
+    ("fc_2048_1000_f32out",       8,  1,  1, 2048, 1000, 1, 1, 0, 1, 1, 0, 0, 1, "bf16"),
+    ("head_256_21_direct",        2, 30, 30, 256,  21, 1, 1, 0, 1, 1, 0, 0, 0, "bf16"),
+    ("persistent_many_tiles",     8, 56, 56,  64, 256, 1, 1, 0, 1, 1, 1, 1, 0, "bf16"),
+    ("persistent_3x3_many",       8, 56, 56,  64,  64, 3, 1, 1, 1, 1, 1, 0, 0, "bf16"),
+    ("simt_bf16_3x3",             2, 14, 14,  64,  64, 3, 1, 1, 1, 1, 1, 1, 2, "bf16"),
+    ("simt_f32_3x3",              2, 14, 14,  64,  64, 3, 1, 1, 1, 1, 1, 1, 0, "fp32"),
+    ("simt_f32_7x7_c3",           2, 64, 64,   3,  64, 7, 2, 3, 1, 1, 1, 0, 0, "fp32"),
+    ("simt_f32_grouped",          2, 14, 14, 128, 128, 3, 1, 1, 1, 32, 1, 0, 0, "fp32"),
+    ("dw3x3_s1_bf16",             2, 28, 28, 144, 144, 3, 1, 1, 1, 144, 2, 0, 0, "bf16"),
+    ("dw3x3_s2_bf16",             2, 28, 28,  96,  96, 3, 2, 1, 1, 96, 2, 0, 0, "bf16"),
+    ("dw5x5_s1_bf16",             2, 14, 14,  96,  96, 5, 1, 2, 1, 96, 2, 0, 0, "bf16"),
+    ("dw3x3_s1_f32",              2, 28, 28,  32,  32, 3, 1, 1, 1, 32, 2, 1, 0, "fp32"),
+    ("dw3x3_d2_generic",          2, 28, 28,  32,  32, 3, 1, 2, 2, 32, 1, 0, 0, "bf16"),
+]
+
+
+def run_case(idx: int) -> dict:
+    import torch
+    import torch.nn.functional as F
+    from pytorchcv_b200 import functional as P, _lib
+
+    name, N, H, W, Cin, Cout, k, stride, pad, dil, groups, act, has_res, flags, dt = CASES[idx]
+    tdt = torch.bfloat16 if dt == "bf16" else torch.float32
+    code = _lib.BF16 if dt == "bf16" else _lib.F32
+    g = torch.Generator().manual_seed(1000 + idx)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin // groups, k, k, generator=g) * (2.0 / (Cin // groups * k * k)) ** 0.5
+    gamma = torch.rand(Cout, generator=g) + 0.5
+    beta = torch.rand(Cout, generator=g) - 0.5
+    mean = torch.rand(Cout, generator=g) - 0.5
+    var = torch.rand(Cout, generator=g) + 0.5
+    Ho = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    res = torch.randn(N, Cout, Ho, Wo, generator=g) if has_res else None
+
+    # reference: same operand rounding as the tier (bf16 activations / BN-folded bf16 weights), fp32 math
+    rnd = (lambda t: t.to(torch.bfloat16).float()) if dt == "bf16" else (lambda t: t)
+    scale = gamma / torch.sqrt(var + 1e-5)
+    wf = rnd(w * scale.view(-1, 1, 1, 1)) if groups != Cin or dt == "fp32" or True else w
+    bf = beta - mean * scale
+    ref = F.conv2d(rnd(x), wf, bf, stride=stride, padding=pad, dilation=dil, groups=groups)
+    if has_res:
+        ref = ref + rnd(res)
+    ref = {0: lambda t: t, 1: torch.relu, 2: lambda t: t.clamp(0, 6)}[act](ref)
+
+    dev = torch.device("cuda")
+    xg = x.to(dev).permute(0, 2, 3, 1).contiguous().to(tdt)
+    rg = res.to(dev).permute(0, 2, 3, 1).contiguous().to(tdt) if has_res else None
+    desc = P.make_desc(N, H, W, Cin, Cout, k, stride, pad, dil, groups, act, flags=flags)
+    packed = P.pack_conv(desc, code, w.to(dev), None, (gamma.to(dev), beta.to(dev), mean.to(dev), var.to(dev)))
+    t0 = time.time()
+    y = P.conv2d(xg, packed, rg)
+    torch.cuda.synchronize()
+    dt_ms = (time.time() - t0) * 1e3
+    got = y.float().cpu().permute(0, 3, 1, 2)[:, :Cout]
+    err = (got - ref).abs()
+    denom = ref.abs().max().item() + 1e-12
+    rel = err.max().item() / denom
+    tol = 1.2e-2 if dt == "bf16" and not (flags & 1) else (2e-3 if dt == "bf16" else 1e-4)
+    out = {"case": name, "rel": rel, "ok": bool(rel <= tol and torch.isfinite(got).all()), "ms": round(dt_ms, 2)}
+    if not out["ok"]:
+        bad = err > tol * denom
+        out["bad_frac"] = round(bad.float().mean().item(), 4)
+        out["bad_by_channel"] = [round(v, 2) for v in bad.float().mean(dim=(0, 2, 3))[:16].tolist()]
+        flat_rows = bad.permute(0, 2, 3, 1).reshape(-1, Cout).float().mean(dim=1)  # per output pixel (GEMM row)
+        out["bad_rows_first32"] = [round(v, 2) for v in flat_rows[:32].tolist()]
+        out["bad_rows_128_160"] = [round(v, 2) for v in flat_rows[128:160].tolist()]
+        out["got_sample"] = [round(v, 3) for v in got.permute(0, 2, 3, 1).reshape(-1, Cout)[0, :8].tolist()]
+        out["ref_sample"] = [round(v, 3) for v in ref.permute(0, 2, 3, 1).reshape(-1, Cout)[0, :8].tolist()]
+        out["nan"] = int((~torch.isfinite(got)).sum().item())
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--from-case", type=int, default=None, help="child mode: run cases [i, end) in-process")
+    ap.add_argument("--only", type=str, default=None, help="substring filter")
+    ap.add_argument("--timeout", type=int, default=120, help="seconds allowed per case before the child is killed")
+    ap.add_argument("--out", type=str, default="gpurun_out/diag.jsonl")
+    a = ap.parse_args()
+    if a.from_case is not None:
+        for i in range(a.from_case, len(CASES)):
+            if a.only and a.only not in CASES[i][0]:
+                continue
+            try:
+                r = run_case(i)
+            except Exception as e:  # noqa: BLE001
+                r = {"case": CASES[i][0], "ok": False, "error": repr(e)[-600:]}
+            r["idx"] = i
+            print("DIAG " + json.dumps(r), flush=True)
+            if "CUDA" in r.get("error", "") or "cuda" in r.get("error", ""):
+                return  # sticky CUDA error: let the parent restart a fresh process at the next case
+        print("DIAG_DONE", flush=True)
+        return
+
+    import selectors
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    results, start = [], 0
+    while start < len(CASES):
+        cmd = [sys.executable, "-u", __file__, "--from-case", str(start)] + (["--only", a.only] if a.only else [])
+        child = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        sel = selectors.DefaultSelector()
+        sel.register(child.stdout, selectors.EVENT_READ)
+        last, done, tail = start - 1, False, []
+        deadline = time.time() + a.timeout + 120  # first case also pays the torch import
+        while True:
+            if not sel.select(timeout=max(0.0, deadline - time.time())):
+                child.kill()
+                r = {"case": CASES[min(last + 1, len(CASES) - 1)][0], "idx": last + 1, "ok": False,
+                     "error": "TIMEOUT (hang)"}
+                results.append(r)
+                print(json.dumps(r), flush=True)
+                last += 1
+                break
+            line = child.stdout.readline()
+            if not line:
+                if not done and child.wait() != 0:
+                    r = {"case": CASES[min(last + 1, len(CASES) - 1)][0], "idx": last + 1, "ok": False,
+                         "error": "child died: " + " | ".join(tail[-6:])[-700:]}
+                    results.append(r)
+                    print(json.dumps(r), flush=True)
+                    last += 1
+                break
+            line = line.rstrip()
+            if line.startswith("DIAG_DONE"):
+                done = True
+                last = len(CASES)
+            elif line.startswith("DIAG "):
+                r = json.loads(line[5:])
+                results.append(r)
+                last = r["idx"]
+                print(json.dumps(r), flush=True)
+                deadline = time.time() + a.timeout
+            else:
+                tail.append(line)
+        child.wait()
+        start = last + 1
+    with open(a.out, "a") as f:
+        for r in results:
+            f.write(json.dumps(r) + "\n")
+    n_ok = sum(1 for r in results if r.get("ok"))
+    print(f"SUMMARY {n_ok}/{len(results)} ok", flush=True)
+
+
+if __name__ == "__main__":
+    main()

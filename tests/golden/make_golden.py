@@ -1,0 +1,86 @@
+"""Generates tests/golden/*.npz by running the REFERENCE ITSELF (osmr/pytorchcv at /root/reference) on CPU.
+
+Run in the build container only (the GPU box has no /root/reference):
+    PYTHONPATH=/root/reference:. python tests/golden/make_golden.py
+The vectors pin `oracle/` (tests/test_oracle.py) and, through it, the CUDA path (tests/test_gpu_*.py).
+Weights/inputs are not stored: they are regenerated from seeds by oracle/seeded.py (name-keyed, order-independent).
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+sys.path.insert(0, REF)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+
+from pytorchcv.model_provider import get_model as ref_get_model  # noqa: E402
+from pytorchcv.models.common.conv import ConvBlock, DwsConvBlock, conv3x3_block, dwconv5x5_block  # noqa: E402
+from pytorchcv.models.common.att import SEBlock  # noqa: E402
+from pytorchcv.models.resnet import ResUnit  # noqa: E402
+from pytorchcv.models.mobilenetv2 import LinearBottleneck  # noqa: E402
+from pytorchcv.models.seresnext import SEResNeXtUnit  # noqa: E402
+from pytorchcv.models.common.activ import lambda_relu6  # noqa: E402
+
+from oracle.seeded import seeded_init, seeded_input  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+# (file stem, model name, kwargs, input shape, seed, output subsample stride for dense maps)
+NETS = [
+    ("resnet18_bs2", "resnet18", {}, (2, 3, 224, 224), 0, 1),
+    ("resnet50_bs2", "resnet50", {}, (2, 3, 224, 224), 0, 1),
+    ("mobilenetv2_w1_bs2", "mobilenetv2_w1", {}, (2, 3, 224, 224), 0, 1),
+    ("seresnext50_32x4d_bs2", "seresnext50_32x4d", {}, (2, 3, 224, 224), 0, 1),
+    ("mobilenet_w1_bs2", "mobilenet_w1", {}, (2, 3, 224, 224), 0, 1),
+    ("deeplabv3_resnetd50b_voc_bs1", "deeplabv3_resnetd50b_voc", {}, (1, 3, 480, 480), 0, 16),
+]
+
+# block-level cases: (stem, ctor, input shape)
+BLOCKS = [
+    ("convblock_3x3_s2", lambda: conv3x3_block(in_channels=16, out_channels=24, stride=2), (2, 16, 15, 15)),
+    ("convblock_1x1_noact", lambda: ConvBlock(32, 64, kernel_size=1, activation=None), (2, 32, 9, 9)),
+    ("convblock_3x3_d2_bias", lambda: ConvBlock(16, 16, kernel_size=3, padding=2, dilation=2, bias=True), (1, 16, 12, 12)),
+    ("dws_3x3", lambda: DwsConvBlock(16, 32, kernel_size=3, stride=1, padding=1), (2, 16, 10, 10)),
+    ("dwconv5x5_relu6", lambda: dwconv5x5_block(in_channels=24, out_channels=24, activation=lambda_relu6()), (1, 24, 11, 11)),
+    ("seblock_64", lambda: SEBlock(channels=64), (2, 64, 7, 7)),
+    ("resunit_bottleneck_s2", lambda: ResUnit(64, 128, stride=2, bottleneck=True, conv1_stride=True), (2, 64, 14, 14)),
+    ("resunit_basic", lambda: ResUnit(32, 32, stride=1, bottleneck=False), (2, 32, 8, 8)),
+    ("linear_bottleneck_res", lambda: LinearBottleneck(24, 24, stride=1, expansion=True, remove_exp_conv=False,
+                                                       activation=lambda_relu6()), (2, 24, 14, 14)),
+    ("seresnext_unit", lambda: SEResNeXtUnit(256, 256, stride=1, cardinality=32, bottleneck_width=4), (1, 256, 8, 8)),
+]
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@torch.no_grad()
+def main():
+    torch.set_num_threads(1)  # thread count perturbs fp32 sums; fix it for reproducible fixtures
+    for stem, name, kw, shape, seed, sub in NETS:
+        net = seeded_init(ref_get_model(name, pretrained=False, **kw).eval(), seed=seed, randomize_bn=True)
+        x = seeded_input(shape, seed=1234)
+        y = net(x)
+        ys = y if isinstance(y, (tuple, list)) else (y,)
+        arrs = {}
+        for i, t in enumerate(ys):
+            a = t.numpy()
+            arrs[f"out{i}_sha1"] = np.frombuffer(sha(a).encode(), dtype=np.uint8)
+            arrs[f"out{i}"] = a[..., ::sub, ::sub] if (a.ndim == 4 and sub > 1) else a
+        arrs["n_params"] = np.array(sum(p.numel() for p in net.parameters()))
+        np.savez_compressed(os.path.join(OUT, stem + ".npz"), **arrs)
+        print(stem, [tuple(t.shape) for t in ys], int(arrs["n_params"]))
+    for stem, ctor, shape in BLOCKS:
+        blk = seeded_init(ctor().eval(), seed=7, randomize_bn=True)
+        x = seeded_input(shape, seed=99)
+        y = blk(x)
+        np.savez_compressed(os.path.join(OUT, "block_" + stem + ".npz"), out0=y.numpy())
+        print("block", stem, tuple(y.shape))
+
+
+if __name__ == "__main__":
+    main()
