@@ -61,6 +61,7 @@ def sha(a: np.ndarray) -> str:
 @torch.no_grad()
 def main():
     torch.set_num_threads(1)  # thread count perturbs fp32 sums; fix it for reproducible fixtures
+    keys = {}
     for stem, name, kw, shape, seed, sub in NETS:
         net = seeded_init(ref_get_model(name, pretrained=False, **kw).eval(), seed=seed, randomize_bn=True)
         x = seeded_input(shape, seed=1234)
@@ -72,8 +73,14 @@ def main():
             arrs[f"out{i}_sha1"] = np.frombuffer(sha(a).encode(), dtype=np.uint8)
             arrs[f"out{i}"] = a[..., ::sub, ::sub] if (a.ndim == 4 and sub > 1) else a
         arrs["n_params"] = np.array(sum(p.numel() for p in net.parameters()))
+        keys[name] = {"n": len(net.state_dict()),
+                      "sha1": hashlib.sha1("\n".join(f"{k}:{tuple(v.shape)}" for k, v in net.state_dict().items())
+                                           .encode()).hexdigest()}
         np.savez_compressed(os.path.join(OUT, stem + ".npz"), **arrs)
         print(stem, [tuple(t.shape) for t in ys], int(arrs["n_params"]))
+    import json
+    with open(os.path.join(OUT, "state_dict_keys.json"), "w") as f:
+        json.dump(keys, f, indent=1, sort_keys=True)
     for stem, ctor, shape in BLOCKS:
         blk = seeded_init(ctor().eval(), seed=7, randomize_bn=True)
         x = seeded_input(shape, seed=99)

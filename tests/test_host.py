@@ -1,0 +1,166 @@
+"""CPU-side contract tests: the C-ABI library loads and exports what include/pcv_b200.h declares, get_model keeps
+the reference's contract, the plan compiler lowers every config and places buffers without overlap."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+import torch.nn as nn
+
+import pytorchcv_b200 as P
+from pytorchcv_b200 import _lib, blocks as B, nets as M, plan as PL
+from pytorchcv_b200._lib import BF16, F32
+from conftest import ROOT
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "pcv_b200.h")).read()
+    return sorted(set(re.findall(r"PCV_API[^;(]*?\b(pcv_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_loads_and_exports_every_header_symbol():
+    lib = _lib.load()
+    names = _header_symbols()
+    assert len(names) >= 24
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/pcv_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes SIGNATURES out of sync with the header"
+    assert lib.pcv_version() >= 100
+
+
+def test_no_device_is_an_error_not_a_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    arch = ctypes.c_int()
+    rc = _lib.load().pcv_device_info(0, ctypes.byref(arch), None, None)
+    assert rc == _lib.ERR_NO_DEVICE
+    assert b"no CPU fallback" in _lib.load().pcv_last_error()
+    net = P.get_model("resnet18").eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(1, 3, 224, 224))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        B.conv3x3_block(in_channels=8, out_channels=8).eval()(torch.zeros(1, 8, 4, 4))
+
+
+def test_abi_validates_arguments():
+    d = _lib.ConvDesc(N=1, H=8, W=8, Cin=6, Cout=8, kh=3, kw=3, stride=1, pad=1, dil=1, groups=4, act=0)
+    wb, bb = ctypes.c_size_t(), ctypes.c_size_t()
+    rc = _lib.load().pcv_conv_packed_bytes(ctypes.byref(d), BF16, ctypes.byref(wb), ctypes.byref(bb))
+    assert rc == _lib.ERR_INVALID and b"groups" in _lib.load().pcv_last_error()
+    d.groups, d.act = 1, 99
+    assert _lib.load().pcv_conv_packed_bytes(ctypes.byref(d), BF16, ctypes.byref(wb), ctypes.byref(bb)) == _lib.ERR_INVALID
+    with pytest.raises(_lib.PcvError):
+        _lib.call("pcv_plan_run", None, None)
+
+
+def test_packed_sizes_follow_route():
+    wb, bb = ctypes.c_size_t(), ctypes.c_size_t()
+    d = _lib.ConvDesc(N=1, H=14, W=14, Cin=256, Cout=256, kh=3, kw=3, stride=1, pad=1, dil=1, groups=1, act=1)
+    _lib.call("pcv_conv_packed_bytes", ctypes.byref(d), BF16, ctypes.byref(wb), ctypes.byref(bb))
+    assert wb.value == 256 * 9 * 256 * 2 and bb.value == 256 * 4          # tcgen05 route: bf16 [Cout, taps*Cpad]
+    _lib.call("pcv_conv_packed_bytes", ctypes.byref(d), F32, ctypes.byref(wb), ctypes.byref(bb))
+    assert wb.value == 256 * 9 * 256 * 4                                    # fp32 tier: CUDA-core route
+    d.groups = 256
+    _lib.call("pcv_conv_packed_bytes", ctypes.byref(d), BF16, ctypes.byref(wb), ctypes.byref(bb))
+    assert wb.value == 256 * 9 * 4                                          # depthwise: fp32 [tap][C]
+
+
+def test_get_model_contract():
+    assert isinstance(P.get_model("ResNet18"), nn.Module)                   # case-insensitive (model_provider.py:1378)
+    with pytest.raises(ValueError, match="Unsupported model"):
+        P.get_model("resnet19")
+    with pytest.raises(ValueError, match="Unsupported ResNet"):
+        M.get_resnet(blocks=19)
+    with pytest.raises(ValueError, match="model_name"):
+        M.get_resnet(blocks=18, pretrained=True)
+    with pytest.raises(NotImplementedError):
+        B.create_activation_layer("gelu")                                   # activ.py:219
+    for n in ("resnet18", "resnet50", "mobilenetv2_w1", "seresnext50_32x4d", "deeplabv3_resnetd50b_voc"):
+        assert n in P.supported_models()
+
+
+@pytest.mark.parametrize("name,count", [("resnet18", 11689512), ("resnet50", 25557032), ("resnet50b", 25557032),
+                                        ("mobilenetv2_w1", 3504960), ("seresnext50_32x4d", 27559896),
+                                        ("resnext50_32x4d", 25028904), ("mobilenet_w1", 4231976),
+                                        ("deeplabv3_resnetd50b_voc", 42127850)])
+def test_parameter_counts_pinned_by_reference_tests(name, count):
+    """resnet.py:975-995, mobilenetv2.py:436, seresnext.py:296, resnext.py, mobilenet.py, deeplabv3.py:678."""
+    net = P.get_model(name, pretrained=False)
+    assert sum(p.numel() for p in net.parameters() if p.requires_grad) == count
+
+
+def test_kwargs_flow_to_constructor():
+    net = P.get_model("resnet18", in_channels=1, num_classes=10, in_size=(64, 64))
+    assert net.features.init_block.conv.conv.in_channels == 1 and net.output.out_features == 10
+    dl = P.get_model("deeplabv3_resnetd50b_voc", aux=False, num_classes=5)
+    assert not hasattr(dl, "aux_block") and dl.final_block.conv2.out_channels == 5
+
+
+CONFIGS = [("resnet18", (8, 3, 224, 224), 23), ("resnet50", (4, 3, 224, 224), 56), ("mobilenetv2_w1", (4, 3, 224, 224), 55),
+           ("seresnext50_32x4d", (4, 3, 224, 224), 104), ("deeplabv3_resnetd50b_voc", (1, 3, 480, 480), 70)]
+
+
+@pytest.mark.parametrize("tier", [BF16, F32])
+@pytest.mark.parametrize("name,shape,n_ops", CONFIGS, ids=[c[0] for c in CONFIGS])
+def test_lowering_and_arena(name, shape, n_ops, tier):
+    """Dry-run the compiler on CPU: op counts, output shapes, and no two live buffers share arena bytes."""
+    net = P.get_model(name).eval()
+    b = PL.Builder(tier, torch.device("cpu"))
+    N, _, H, W = shape
+    x = b.new(N, H, W, 8)
+    x.buf.first, x.buf.pinned = -1, True
+    out = PL.lower(b, net, x)
+    _, trefs = PL._flatten(out)
+    assert len(b.ops) == n_ops
+    for t in trefs:
+        t.buf.pinned = True
+    if name.startswith("deeplab"):
+        assert [(t.N, t.C, t.H, t.W, t.layout) for t in trefs] == [(N, 21, 480, 480, "nchw")] * 2
+    else:
+        assert [(t.N, t.C, t.flat) for t in trefs] == [(N, 1000, True)]
+    top = PL._assign_offsets(b.bufs)
+    assert top < sum(z.nbytes for z in b.bufs)  # liveness reuse actually happens
+    life = lambda z: (z.first, 1 << 60 if z.pinned else max(z.last, z.first))
+    bufs = b.bufs
+    for i in range(len(bufs)):
+        for j in range(i + 1, len(bufs)):
+            a, c = bufs[i], bufs[j]
+            (a0, a1), (c0, c1) = life(a), life(c)
+            if a1 < c0 or c1 < a0:
+                continue
+            assert a.offset + a.nbytes <= c.offset or c.offset + c.nbytes <= a.offset, "live buffers overlap"
+
+
+def test_identity_buffer_outlives_the_unit():
+    """SURVEY hard part 8: the unit's input must stay intact until the last conv's epilogue has read it."""
+    unit = M.ResUnit(64, 64, stride=1, bottleneck=True).eval()
+    b = PL.Builder(BF16, torch.device("cpu"))
+    x = b.new(2, 14, 14, 64)
+    PL.lower(b, unit, x)
+    assert x.buf.last == len(b.ops) - 1 == 2  # read by conv1 (op 0) and again as the residual of conv3 (op 2)
+
+
+def test_unsupported_patterns_raise_at_compile_time():
+    b = PL.Builder(BF16, torch.device("cpu"))
+    x = b.new(1, 8, 8, 16)
+    with pytest.raises(NotImplementedError, match="outside the B200 eval path"):
+        PL.lower(b, nn.GELU(), x)
+    with pytest.raises(RuntimeError, match="eval-mode"):
+        PL.lower(b, B.conv1x1_block(in_channels=16, out_channels=16), x)            # still in training mode
+    with pytest.raises(NotImplementedError, match="cannot be folded"):
+        PL.lower(b, B.ConvBlock(16, 16, 1, normalization=lambda num_features: nn.InstanceNorm2d(num_features)).eval(), x)
+    with pytest.raises(NotImplementedError, match="ZeroPad2d"):
+        PL.lower(b, B.ConvBlock(16, 16, 3, padding=(1, 0, 1, 0)).eval(), x)
+    with pytest.raises(RuntimeError, match="eval-mode"):
+        P.accelerate(P.get_model("resnet18"))
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "pytorchcv_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f"{f} imports the oracle"
+                assert "/root/reference" not in text, f"{f} reads the reference at run time"

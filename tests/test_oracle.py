@@ -1,0 +1,140 @@
+"""Pins the oracle (oracle/ref_forward.py) against outputs of the reference itself.
+
+ - golden replay: fixtures in tests/golden/*.npz were produced by /root/reference on CPU (make_golden.py);
+ - live: when /root/reference is importable, the oracle is compared with the reference module's own forward.
+Runs on CPU in well under a minute.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pytorchcv_b200 as P
+from pytorchcv_b200 import blocks as B, nets as M
+from oracle import oracle_forward, seeded_init, seeded_input
+from conftest import GOLDEN
+
+NETS = [
+    ("resnet18_bs2", "resnet18", (2, 3, 224, 224), 1),
+    ("resnet50_bs2", "resnet50", (2, 3, 224, 224), 1),
+    ("mobilenetv2_w1_bs2", "mobilenetv2_w1", (2, 3, 224, 224), 1),
+    ("seresnext50_32x4d_bs2", "seresnext50_32x4d", (2, 3, 224, 224), 1),
+    ("mobilenet_w1_bs2", "mobilenet_w1", (2, 3, 224, 224), 1),
+    ("deeplabv3_resnetd50b_voc_bs1", "deeplabv3_resnetd50b_voc", (1, 3, 480, 480), 16),
+]
+
+BLOCKS = {
+    "convblock_3x3_s2": (lambda: B.conv3x3_block(in_channels=16, out_channels=24, stride=2), (2, 16, 15, 15)),
+    "convblock_1x1_noact": (lambda: B.ConvBlock(32, 64, kernel_size=1, activation=None), (2, 32, 9, 9)),
+    "convblock_3x3_d2_bias": (lambda: B.ConvBlock(16, 16, kernel_size=3, padding=2, dilation=2, bias=True),
+                              (1, 16, 12, 12)),
+    "dws_3x3": (lambda: B.DwsConvBlock(16, 32, kernel_size=3, stride=1, padding=1), (2, 16, 10, 10)),
+    "dwconv5x5_relu6": (lambda: B.dwconv5x5_block(in_channels=24, out_channels=24, activation=B.lambda_relu6()),
+                        (1, 24, 11, 11)),
+    "seblock_64": (lambda: B.SEBlock(channels=64), (2, 64, 7, 7)),
+    "resunit_bottleneck_s2": (lambda: M.ResUnit(64, 128, stride=2, bottleneck=True, conv1_stride=True),
+                              (2, 64, 14, 14)),
+    "resunit_basic": (lambda: M.ResUnit(32, 32, stride=1, bottleneck=False), (2, 32, 8, 8)),
+    "linear_bottleneck_res": (lambda: M.LinearBottleneck(24, 24, stride=1, expansion=True, remove_exp_conv=False,
+                                                         activation=B.lambda_relu6()), (2, 24, 14, 14)),
+    "seresnext_unit": (lambda: M.SEResNeXtUnit(256, 256, stride=1, cardinality=32, bottleneck_width=4),
+                       (1, 256, 8, 8)),
+}
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+@pytest.fixture(autouse=True)
+def _one_thread():
+    n = torch.get_num_threads()
+    torch.set_num_threads(1)  # the fixtures were generated single-threaded (thread count perturbs fp32 sums)
+    yield
+    torch.set_num_threads(n)
+
+
+@pytest.mark.parametrize("stem,name,shape,sub", NETS, ids=[n[1] for n in NETS])
+def test_oracle_matches_reference_golden_nets(stem, name, shape, sub):
+    gold = np.load(os.path.join(GOLDEN, stem + ".npz"))
+    net = seeded_init(P.get_model(name, pretrained=False).eval(), seed=0, randomize_bn=True)
+    assert sum(p.numel() for p in net.parameters()) == int(gold["n_params"])
+    y = oracle_forward(net, seeded_input(shape, seed=1234))
+    ys = y if isinstance(y, (tuple, list)) else (y,)
+    for i, t in enumerate(ys):
+        g = torch.from_numpy(gold[f"out{i}"])
+        t = t[..., ::sub, ::sub] if (t.dim() == 4 and sub > 1) else t
+        assert t.shape == g.shape
+        assert _rel(t, g) <= 1e-4, f"{name} out{i}: oracle deviates from the reference golden vector"
+        if t.dim() == 2:
+            assert torch.equal(t.argmax(1), g.argmax(1))
+
+
+@pytest.mark.parametrize("stem", sorted(BLOCKS))
+def test_oracle_matches_reference_golden_blocks(stem):
+    ctor, shape = BLOCKS[stem]
+    gold = torch.from_numpy(np.load(os.path.join(GOLDEN, "block_" + stem + ".npz"))["out0"])
+    blk = seeded_init(ctor().eval(), seed=7, randomize_bn=True)
+    y = oracle_forward(blk, seeded_input(shape, seed=99))
+    assert y.shape == gold.shape
+    assert _rel(y, gold) <= 1e-5
+
+
+def test_state_dict_keys_match_reference():
+    """Checkpoint compatibility: same keys and shapes, in the same order, as the reference's modules."""
+    import hashlib
+    with open(os.path.join(GOLDEN, "state_dict_keys.json")) as f:
+        want = json.load(f)
+    for name, rec in want.items():
+        sd = P.get_model(name, pretrained=False).state_dict()
+        digest = hashlib.sha1("\n".join(f"{k}:{tuple(v.shape)}" for k, v in sd.items()).encode()).hexdigest()
+        assert len(sd) == rec["n"], name
+        assert digest == rec["sha1"], f"{name}: state_dict keys/shapes differ from the reference"
+
+
+# ---- live comparisons against the reference package (build container only) ---------------------------------------
+@pytest.mark.reference
+@pytest.mark.parametrize("name,shape", [("resnet18", (8, 3, 224, 224)), ("mobilenetv2_w1", (2, 3, 224, 224)),
+                                        ("seresnext50_32x4d", (1, 3, 224, 224))])
+def test_oracle_equals_reference_live(reference_pkg, name, shape):
+    from pytorchcv.model_provider import get_model as ref_get_model
+    ref = seeded_init(ref_get_model(name, pretrained=False).eval(), seed=3, randomize_bn=True)
+    x = seeded_input(shape, seed=5)
+    with torch.no_grad():
+        want = ref(x)
+    got = oracle_forward(ref, x)           # the oracle walks the REFERENCE's own module tree ...
+    assert _rel(got, want) <= 1e-6
+    mine = seeded_init(P.get_model(name, pretrained=False).eval(), seed=3, randomize_bn=True)
+    got2 = oracle_forward(mine, x)         # ... and the mirror tree with the same name-keyed weights
+    assert _rel(got2, want) <= 1e-6
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("name", ["resnet18", "resnet50", "mobilenetv2_w1", "seresnext50_32x4d",
+                                  "deeplabv3_resnetd50b_voc", "mobilenet_w1"])
+def test_same_seed_same_random_init_as_reference(reference_pkg, name):
+    """torch.manual_seed(0); get_model(name) consumes the RNG in the reference's order -> bit-identical weights."""
+    from pytorchcv.model_provider import get_model as ref_get_model
+    torch.manual_seed(0)
+    a = ref_get_model(name, pretrained=False).state_dict()
+    torch.manual_seed(0)
+    b = P.get_model(name, pretrained=False).state_dict()
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.reference
+def test_reference_modules_lower_without_mirror(reference_pkg):
+    """accelerate() pattern-matches on class names, so the real reference tree compiles too (dry run, no GPU)."""
+    from pytorchcv.model_provider import get_model as ref_get_model
+    from pytorchcv_b200 import plan as PL
+    from pytorchcv_b200._lib import BF16
+    net = ref_get_model("resnet50", pretrained=False).eval()
+    b = PL.Builder(BF16, torch.device("cpu"))
+    x = b.new(2, 224, 224, 8)
+    out = PL.lower(b, net, x)
+    assert (out.N, out.C, out.flat) == (2, 1000, True)
+    assert len(b.ops) == 56  # 53 convs + maxpool + global pool + fc
