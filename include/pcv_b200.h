@@ -60,7 +60,7 @@ enum pcv_conv_flags {
   PCV_CONV_OUT_F32 = 1,      /* bf16 tier only: store the result as fp32 (classifier logits) */
   PCV_CONV_FORCE_SIMT = 2,   /* bf16 tier only: use the CUDA-core kernel (cross-check for the tcgen05 path) */
   PCV_CONV_A_IM2COL = 4,     /* bf16 tier only: use the im2col TMA descriptor even for 1x1 stride-1 */
-  PCV_CONV_RES_F32_NCHW = 8  /* reserved */
+  PCV_CONV_IN_OVERLAP = 8    /* x is an overlapping-window VIEW: in_pitch < Cin is allowed (space-to-depth stem) */
 };
 
 /* One ConvBlock (conv.py:204-286): y = act(BN(conv2d(x)) [+ residual]).  Square kernels, symmetric padding. */
@@ -75,6 +75,7 @@ typedef struct pcv_conv_desc {
   int32_t out_pitch;      /* channel pitch of y        (0 -> Cout) */
   int32_t res_pitch;      /* channel pitch of residual (0 -> Cout) */
   int32_t flags;          /* pcv_conv_flags */
+  int32_t in_row_pitch;   /* elements between consecutive input rows (0 -> W * in_pitch); image pitch = H * that */
 } pcv_conv_desc;
 
 /* ---- library ---------------------------------------------------------------------------------------------- */
@@ -128,6 +129,20 @@ PCV_API int pcv_nchw_f32_to_nhwc(pcv_plan* plan, int dtype, int N, int C, int H,
                          int c_pitch, pcv_stream stream);
 PCV_API int pcv_nhwc_to_nchw_f32(pcv_plan* plan, int dtype, int N, int C, int H, int W, const void* x, int c_pitch,
                          float* y, pcv_stream stream);
+/* Space-to-depth stem.  A k x k stride-2 pad-(k/2) convolution on a <=4-channel image (ResInitBlock's 7x7,
+ * resnet.py:250-254; the 3x3 stems of mobilenetv2.py:108-112 and senet.py:139-142) is re-expressed as a
+ * (p+1) x 1 stride-1 convolution, p = k/2, over a zero-bordered space-to-depth tensor
+ *     s2d[n, hb + ceil(p/2), wb + ceil(p/2), (dy*2+dx)*C + c] = x[n, c, 2*hb+dy, 2*wb+dx]      (16 channels/pixel)
+ * read through an overlapping window view of (p+1) consecutive pixels = (p+1)*16 "channels" at a pixel pitch of 16,
+ * so the implicit GEMM sees a dense K = (p+1)^2 * 16 instead of k*k zero-padded 64-channel taps.
+ * pcv_stem_s2d_dims: rows/cols of the s2d tensor (incl. borders) and the equivalent conv's Cin / taps.
+ * pcv_stem_s2d_ingest: NCHW fp32 image -> interior of the (pre-zeroed) s2d tensor, bf16.
+ * pcv_stem_s2d_weights: fp32 [Cout, C, k, k] -> fp32 [Cout, (p+1)*16, p+1, 1] (then pcv_pack_conv_weights). */
+PCV_API int pcv_stem_s2d_dims(int C, int H, int W, int k, int* rows, int* cols, int* cin_eq, int* taps_eq);
+PCV_API int pcv_stem_s2d_ingest(pcv_plan* plan, int N, int C, int H, int W, int k, const float* x, void* s2d,
+                                pcv_stream stream);
+PCV_API int pcv_stem_s2d_weights(int Cout, int C, int k, const float* w, float* w_eq, pcv_stream stream);
+
 /* F.interpolate(mode="bilinear", align_corners=True) (deeplabv3.py:53,86).  Output is NHWC `dtype` with
  * out_pitch, or NCHW fp32 when out_nchw_f32 != 0 (the tensor the reference returns). */
 PCV_API int pcv_bilinear_upsample_ac(pcv_plan* plan, int dtype, int N, int Hin, int Win, int C, const void* x, int in_pitch,

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libpcv_b200.so")
 
 BF16, F32 = 0, 1
 ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SIGMOID, ACT_SWISH, ACT_HSWISH, ACT_HSIGMOID = range(7)
-CONV_OUT_F32, CONV_FORCE_SIMT, CONV_A_IM2COL = 1, 2, 4
+CONV_OUT_F32, CONV_FORCE_SIMT, CONV_A_IM2COL, CONV_IN_OVERLAP = 1, 2, 4, 8
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 
@@ -29,7 +29,7 @@ class PcvError(RuntimeError):
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "N", "H", "W", "Cin", "Cout", "kh", "kw", "stride", "pad", "dil", "groups", "act",
-        "in_pitch", "out_pitch", "res_pitch", "flags")]
+        "in_pitch", "out_pitch", "res_pitch", "flags", "in_row_pitch")]
 
 
 _P = C.c_void_p
@@ -53,6 +53,9 @@ SIGNATURES = {
     "pcv_nchw_f32_to_nhwc": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "pcv_nhwc_to_nchw_f32": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _P]),
     "pcv_bilinear_upsample_ac": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _P]),
+    "pcv_stem_s2d_dims": (_I, [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "pcv_stem_s2d_ingest": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "pcv_stem_s2d_weights": (_I, [_I, _I, _I, _P, _P, _P]),
     "pcv_plan_create": (_I, [C.POINTER(_P)]),
     "pcv_plan_destroy": (_I, [_P]),
     "pcv_plan_num_ops": (_I, [_P]),

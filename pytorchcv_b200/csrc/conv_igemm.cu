@@ -41,6 +41,7 @@ struct IgemmParams {
   int num_kblocks;            // taps * cblocks
   int tiles_m, tiles_n;
   int act, has_res;
+  float act_lo, act_hi;        // ReLU / ReLU6 / none as a clamp; other activations take the slow path
   int a_mode;                 // 0: 2-D tiled [Cin, M]; 1: im2col 4-D
   int out_mode;               // 0: TMA bf16 store; 1: direct bf16; 2: direct fp32
   int grouped;                // 1: A channel window = n_tile*BLOCK_N (block-diagonal weights)
@@ -56,13 +57,16 @@ struct SmemLayout {
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + STAGES * A_STAGE_BYTES;
   static constexpr int OFF_STG = OFF_B + STAGES * B_STAGE_BYTES;
-  static constexpr int OFF_BAR = OFF_STG + 2 * STG_BYTES;
-  static constexpr int NUM_BARS = 2 * STAGES + 8;
+  static constexpr int NSTG = 3;                                    // staging ring: residual in -> result out
+  static constexpr int OFF_BAR = OFF_STG + NSTG * STG_BYTES;
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * NSTG;
   static constexpr int TOTAL = OFF_BAR + NUM_BARS * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;                    // slack for manual 1 KiB alignment
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
+// Rare activations (sigmoid / swish / h-swish / h-sigmoid): kept out of line so the hot epilogue stays compact —
+// an inlined 7-way switch per element blew the epilogue up to ~100 KB of SASS and made it instruction-fetch bound.
+__device__ __noinline__ float apply_act(float v, int act) {
   switch (act) {
     case PCV_ACT_RELU: return fmaxf(v, 0.f);
     case PCV_ACT_RELU6: return fminf(fmaxf(v, 0.f), 6.f);
@@ -74,7 +78,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int OUT_MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
@@ -91,8 +95,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* empty = bars + STAGES;             // [STAGES]  MMA -> TMA
   uint64_t* tmem_full = bars + 2 * STAGES;     // [2]       MMA -> epilogue
   uint64_t* tmem_empty = tmem_full + 2;        // [2]       epilogue -> MMA
-  uint64_t* stg_empty = tmem_empty + 2;        // [2]       epilogue -> residual prefetcher
-  uint64_t* res_full = stg_empty + 2;          // [2]       residual TMA -> epilogue
+  uint64_t* stg_empty = tmem_empty + 2;        // [NSTG]    epilogue -> residual prefetcher
+  uint64_t* res_full = stg_empty + L::NSTG;    // [NSTG]    residual TMA -> epilogue
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
 
   const int warp = threadIdx.x >> 5;
@@ -103,8 +107,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (p.out_mode == 0) tma_prefetch_desc(&tmOut);
-    if (p.has_res && p.out_mode == 0) tma_prefetch_desc(&tmRes);
+    if (OUT_MODE == 0) tma_prefetch_desc(&tmOut);
+    if (p.has_res && OUT_MODE == 0) tma_prefetch_desc(&tmRes);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -114,11 +118,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);
+    }
+    for (int i = 0; i < L::NSTG; ++i) {
       mbar_init(&stg_empty[i], 1);
       mbar_init(&res_full[i], 1);
     }
     fence_mbar_init();
-    mbar_arrive(&stg_empty[0]);  // staging buffer 0 starts out free (buffer 1 is released by tile 0's epilogue)
+    // staging buffers 0..NSTG-2 start out free; buffer NSTG-1 is released by tile 0's epilogue (see below)
+    for (int i = 0; i < L::NSTG - 1; ++i) mbar_arrive(&stg_empty[i]);
   }
   if (warp == 2) {
     tmem_alloc(tmem_ptr, TMEM_COLS);
@@ -207,18 +214,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 3) {
     // ===================================== residual prefetcher =====================================
-    if (lane == 0 && p.has_res && p.out_mode == 0) {
-      int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int buf = it & 1;
+    if (lane == 0 && p.has_res && OUT_MODE == 0) {
+      int sbuf = 0;
+      uint32_t sphase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m_tile = t / p.tiles_n;
         const int n_tile = t - m_tile * p.tiles_n;
-        mbar_wait(&stg_empty[buf], (it >> 1) & 1);
-        mbar_arrive_expect_tx(&res_full[buf], L::STG_BYTES);
+        mbar_wait(&stg_empty[sbuf], sphase);
+        mbar_arrive_expect_tx(&res_full[sbuf], L::STG_BYTES);
 #pragma unroll
         for (int sub = 0; sub < L::NSUB; ++sub)
-          tma_load_2d(&tmRes, &res_full[buf], sStg + buf * L::STG_BYTES + sub * L::SUB_BYTES,
+          tma_load_2d(&tmRes, &res_full[sbuf], sStg + sbuf * L::STG_BYTES + sub * L::SUB_BYTES,
                       n_tile * BN + sub * L::SUB_COLS, m_tile * BLOCK_M);
+        if (++sbuf == L::NSTG) {
+          sbuf = 0;
+          sphase ^= 1;
+        }
       }
     }
   } else if (warp >= 4) {
@@ -228,7 +239,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int epi_tid = threadIdx.x - 128;
     constexpr uint32_t ROW_BYTES = L::SUB_COLS * 2;
     constexpr uint32_t SWZ_MASK = ROW_BYTES == 128 ? 7u : (ROW_BYTES == 64 ? 3u : 1u);
+    const float act_lo = p.act_lo, act_hi = p.act_hi;
+    const bool fancy_act = p.act > PCV_ACT_RELU6;
     int it = 0;
+    int sbuf = 0;           // staging ring position of this tile
+    uint32_t sphase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -236,9 +251,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int n_tile = t - m_tile * p.tiles_n;
       const int m0 = m_tile * BLOCK_M;
       const int n0 = n_tile * BN;
-      uint8_t* stg = sStg + buf * L::STG_BYTES;
+      uint8_t* stg = sStg + sbuf * L::STG_BYTES;
 
-      if (p.has_res && p.out_mode == 0) mbar_wait(&res_full[buf], acc_phase);
+      if (p.has_res && OUT_MODE == 0) mbar_wait(&res_full[sbuf], sphase);
       mbar_wait(&tmem_full[buf], acc_phase);
       tc_fence_after();
 
@@ -257,7 +272,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b.z;
           v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b.w;
         }
-        if (p.out_mode == 0) {
+        if (OUT_MODE == 0) {
           // staging sub-tile holding columns [j*32, j*32+32): row pitch ROW_BYTES, 16-byte chunks XOR-swizzled
           const int col = j * 32;
           uint8_t* sub = stg + (col / L::SUB_COLS) * L::SUB_BYTES;
@@ -278,8 +293,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               v[8 * c + 7] += bf16hi(r.w);
             }
           }
+          if (fancy_act) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+            for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], act_lo), act_hi);
+          }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint32_t off = row_off + c * 16;
@@ -302,9 +322,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               for (int i = 0; i < 32; ++i)
                 if (i < ncol) v[i] += __bfloat162float(rp[i]);
             }
+            if (fancy_act) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
-            if (p.out_mode == 2) {
+              for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], act_lo), act_hi);
+            }
+            if (OUT_MODE == 2) {
               float* op = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.out_pitch + n0 + j * 32;
 #pragma unroll
               for (int i = 0; i < 32; ++i)
@@ -324,7 +349,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
 
-      if (p.out_mode == 0) {
+      if (OUT_MODE == 0) {
         fence_proxy_async_smem();           // st.shared above -> visible to the TMA (async proxy)
         named_bar_sync(1, EPI_THREADS);
         if (epi_tid == 0) {
@@ -332,13 +357,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int sub = 0; sub < L::NSUB; ++sub)
             tma_store_2d(&tmOut, stg + sub * L::SUB_BYTES, n0 + sub * L::SUB_COLS, m0);
           tma_store_commit();
-          tma_store_wait_read<1>();          // the store issued one tile ago has finished reading buffer buf^1
-          mbar_arrive(&stg_empty[buf ^ 1]);
+          // the store issued one tile ago has finished reading its buffer: hand that buffer (ring position
+          // sbuf-1, i.e. the one tile it+NSTG-1 will use) back to the residual prefetcher
+          tma_store_wait_read<1>();
+          mbar_arrive(&stg_empty[sbuf == 0 ? L::NSTG - 1 : sbuf - 1]);
         }
-        named_bar_sync(1, EPI_THREADS);     // everyone may now overwrite staging buffer buf^1
+        named_bar_sync(1, EPI_THREADS);     // ... and every epilogue thread may overwrite it from now on
+      }
+      if (++sbuf == L::NSTG) {
+        sbuf = 0;
+        sphase ^= 1;
       }
     }
-    if (p.out_mode == 0 && epi_tid == 0) tma_store_wait_all<0>();
+    if (OUT_MODE == 0 && epi_tid == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -408,7 +439,8 @@ int igemm_supported(const pcv_conv_desc& d, std::string* why) {
     return 0;
   };
   const int in_pitch = pitch_or(d.in_pitch, d.Cin);
-  if (in_pitch % 8 != 0) return no("input channel pitch must be a multiple of 8 (16-byte TMA stride)");
+  if (in_pitch % 8 != 0 || d.in_row_pitch % 8 != 0)
+    return no("input channel / row pitch must be a multiple of 8 (16-byte TMA stride)");
   if (d.Cin % 8 != 0) return no("Cin must be a multiple of 8");
   if (d.kh * d.kw > 49 || d.stride > 8) return no("kernel/stride out of range");
   const int lo = -d.pad, up_w = d.pad - (d.kw - 1) * d.dil, up_h = d.pad - (d.kh - 1) * d.dil;
@@ -468,8 +500,8 @@ static int make_im2col_4d(CUtensorMap* tm, const void* base, const pcv_conv_desc
   EncodeIm2colFn fn = encode_im2col_fn();
   if (!fn) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeIm2col entry point not available");
   cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.N};
-  cuuint64_t strides[3] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)d.W * in_pitch * 2,
-                           (cuuint64_t)d.H * d.W * in_pitch * 2};
+  const cuuint64_t row_pitch = d.in_row_pitch > 0 ? (cuuint64_t)d.in_row_pitch : (cuuint64_t)d.W * in_pitch;
+  cuuint64_t strides[3] = {(cuuint64_t)in_pitch * 2, row_pitch * 2, (cuuint64_t)d.H * row_pitch * 2};
   int lower[2] = {-d.pad, -d.pad};                                              // {W, H}
   int upper[2] = {d.pad - (d.kw - 1) * d.dil, d.pad - (d.kh - 1) * d.dil};      // {W, H}
   cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
@@ -489,26 +521,36 @@ struct IgemmOp : Op {
   cudaError_t launch(cudaStream_t s) override;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int OUT_MODE>
 static cudaError_t launch_variant(const IgemmOp& op, cudaStream_t s) {
   using L = SmemLayout<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::DYN_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, STAGES, OUT_MODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  igemm_kernel<BN, STAGES><<<op.grid, NUM_THREADS, L::DYN_BYTES, s>>>(op.tmA, op.tmB, op.tmOut, op.tmRes, op.p);
+  igemm_kernel<BN, STAGES, OUT_MODE><<<op.grid, NUM_THREADS, L::DYN_BYTES, s>>>(op.tmA, op.tmB, op.tmOut, op.tmRes,
+                                                                                 op.p);
   return cudaGetLastError();
+}
+
+template <int BN, int STAGES>
+static cudaError_t launch_bn(const IgemmOp& op, cudaStream_t s) {
+  switch (op.p.out_mode) {
+    case 0: return launch_variant<BN, STAGES, 0>(op, s);
+    case 1: return launch_variant<BN, STAGES, 1>(op, s);
+    default: return launch_variant<BN, STAGES, 2>(op, s);
+  }
 }
 
 cudaError_t IgemmOp::launch(cudaStream_t s) {
   g_launches++;
   switch (bn) {
-    case 32: return launch_variant<32, 6>(*this, s);
-    case 64: return launch_variant<64, 6>(*this, s);
-    default: return launch_variant<128, 4>(*this, s);
+    case 32: return launch_bn<32, 6>(*this, s);
+    case 64: return launch_bn<64, 6>(*this, s);
+    default: return launch_bn<128, 4>(*this, s);
   }
 }
 
@@ -546,9 +588,12 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   p.tiles_m = ceil_div(p.M, BLOCK_M);
   p.tiles_n = ceil_div(d.Cout, op->bn);
   p.act = d.act;
+  p.act_lo = (d.act == PCV_ACT_RELU || d.act == PCV_ACT_RELU6) ? 0.f : -INFINITY;
+  p.act_hi = d.act == PCV_ACT_RELU6 ? 6.f : INFINITY;
   p.has_res = res != nullptr;
   p.grouped = grouped;
-  const bool pointwise = (taps == 1 && d.stride == 1 && d.pad == 0);
+  const bool pointwise = (taps == 1 && d.stride == 1 && d.pad == 0 && d.in_row_pitch == 0 &&
+                          !(d.flags & PCV_CONV_IN_OVERLAP));
   p.a_mode = (pointwise && !(d.flags & PCV_CONV_A_IM2COL)) ? 0 : 1;
   const bool tma_out = !(d.flags & PCV_CONV_OUT_F32) && (out_pitch % 8 == 0) && (!res || res_pitch % 8 == 0) &&
                        (reinterpret_cast<uintptr_t>(y) % 16 == 0) && (reinterpret_cast<uintptr_t>(res) % 16 == 0);

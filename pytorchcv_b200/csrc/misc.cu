@@ -577,3 +577,132 @@ int pcv_bilinear_upsample_ac(pcv_plan* plan, int dtype, int N, int Hin, int Win,
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// space-to-depth stem (see include/pcv_b200.h): ingest + weight re-expression
+// ---------------------------------------------------------------------------------------------------------------
+namespace pcv {
+
+struct S2dGeom {
+  int p, kb, pad_lo, delta, rows, cols;
+};
+static inline S2dGeom s2d_geom(int H, int W, int k) {
+  S2dGeom g;
+  g.p = k / 2;
+  g.kb = g.p + 1;                       // s2d blocks touched per output pixel and axis
+  g.pad_lo = (g.p + 1) / 2;             // zero border before the interior (ceil(p/2)); after: floor(p/2)
+  g.delta = 2 * g.pad_lo - g.p;         // filter index = 2*block + parity - delta
+  g.rows = H / 2 + g.kb - 1;
+  g.cols = W / 2 + g.kb - 1;
+  return g;
+}
+
+__global__ void __launch_bounds__(256)
+s2d_ingest_kernel(int N, int C, int H, int W, int pad_lo, int rows, int cols, const float* __restrict__ x,
+                  __nv_bfloat16* __restrict__ y) {
+  const int Hb = H >> 1, Wb = W >> 1;
+  const long long total = static_cast<long long>(N) * Hb * Wb;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int wb = static_cast<int>(idx % Wb);
+    const long long r = idx / Wb;
+    const int hb = static_cast<int>(r % Hb);
+    const int n = static_cast<int>(r / Hb);
+    float v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float* px = x + ((static_cast<size_t>(n) * C + c) * H + 2 * hb) * W + 2 * wb;
+      const float2 top = *reinterpret_cast<const float2*>(px);
+      const float2 bot = *reinterpret_cast<const float2*>(px + W);
+      // channel = (dy*2+dx)*C + c ; C <= 4 so the index is < 16 (static indexing keeps v[] in registers)
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        if (e == 0 * C + c) v[e] = top.x;
+        if (e == 1 * C + c) v[e] = top.y;
+        if (e == 2 * C + c) v[e] = bot.x;
+        if (e == 3 * C + c) v[e] = bot.y;
+      }
+    }
+    uint4 lo, hi;
+    lo.x = pack_bf16x2(v[0], v[1]); lo.y = pack_bf16x2(v[2], v[3]); lo.z = pack_bf16x2(v[4], v[5]); lo.w = pack_bf16x2(v[6], v[7]);
+    hi.x = pack_bf16x2(v[8], v[9]); hi.y = pack_bf16x2(v[10], v[11]); hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
+    uint4* dst = reinterpret_cast<uint4*>(y + ((static_cast<size_t>(n) * rows + hb + pad_lo) * cols + wb + pad_lo) * 16);
+    dst[0] = lo;
+    dst[1] = hi;
+  }
+}
+
+__global__ void s2d_weight_kernel(int Cout, int C, int k, int kb, int delta, const float* __restrict__ w,
+                                  float* __restrict__ weq) {
+  const int cin_eq = kb * 16;
+  const int total = Cout * cin_eq * kb;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int r = idx % kb;                 // equivalent filter row (kh = kb, kw = 1)
+    const int cc = (idx / kb) % cin_eq;     // equivalent input channel = window pixel j, s2d channel ch
+    const int o = idx / (kb * cin_eq);
+    const int j = cc / 16, ch = cc % 16;
+    float v = 0.f;
+    if (ch < 4 * C) {
+      const int q = ch / C, c = ch % C;
+      const int fr = 2 * r + (q >> 1) - delta, fs = 2 * j + (q & 1) - delta;
+      if (fr >= 0 && fr < k && fs >= 0 && fs < k) v = w[((static_cast<size_t>(o) * C + c) * k + fr) * k + fs];
+    }
+    weq[idx] = v;
+  }
+}
+
+struct S2dIngestOp : Op {
+  int N, C, H, W;
+  S2dGeom g;
+  const float* x;
+  __nv_bfloat16* y;
+  cudaError_t launch(cudaStream_t s) override {
+    g_launches++;
+    const int grid = grid_for(static_cast<long long>(N) * (H / 2) * (W / 2));
+    s2d_ingest_kernel<<<grid, 256, 0, s>>>(N, C, H, W, g.pad_lo, g.rows, g.cols, x, y);
+    return cudaGetLastError();
+  }
+};
+
+}  // namespace pcv
+
+extern "C" {
+
+int pcv_stem_s2d_dims(int C, int H, int W, int k, int* rows, int* cols, int* cin_eq, int* taps_eq) {
+  PCV_REQUIRE(C >= 1 && C <= 4 && (k == 3 || k == 5 || k == 7) && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0,
+              "space-to-depth stem needs C <= 4, k in {3,5,7}, even H and W (got C=%d k=%d %dx%d)", C, k, H, W);
+  const S2dGeom g = s2d_geom(H, W, k);
+  if (rows) *rows = g.rows;
+  if (cols) *cols = g.cols;
+  if (cin_eq) *cin_eq = g.kb * 16;
+  if (taps_eq) *taps_eq = g.kb;
+  return PCV_OK;
+}
+
+int pcv_stem_s2d_ingest(pcv_plan* plan, int N, int C, int H, int W, int k, const float* x, void* s2d,
+                        pcv_stream stream) {
+  if (int rc = pcv_stem_s2d_dims(C, H, W, k, nullptr, nullptr, nullptr, nullptr)) return rc;
+  PCV_REQUIRE(x && s2d && N > 0, "NULL tensor pointer");
+  PCV_REQUIRE(reinterpret_cast<uintptr_t>(x) % 8 == 0 && reinterpret_cast<uintptr_t>(s2d) % 16 == 0, "misaligned stem tensors");
+  auto op = std::make_unique<S2dIngestOp>();
+  op->N = N; op->C = C; op->H = H; op->W = W; op->g = s2d_geom(H, W, k); op->x = x;
+  op->y = reinterpret_cast<__nv_bfloat16*>(s2d);
+  char nm[96];
+  snprintf(nm, sizeof nm, "ingest_s2d_bf16 C=%d k=%d @%dx%d", C, k, H, W);
+  op->name = nm;
+  op->bytes = static_cast<double>(N) * (4.0 * C * H * W + 32.0 * (H / 2) * (W / 2));
+  return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
+}
+
+int pcv_stem_s2d_weights(int Cout, int C, int k, const float* w, float* w_eq, pcv_stream stream) {
+  PCV_REQUIRE(w && w_eq && Cout > 0 && C >= 1 && C <= 4 && (k == 3 || k == 5 || k == 7), "bad stem weight arguments");
+  const S2dGeom g = s2d_geom(2, 2, k);
+  const int total = Cout * g.kb * 16 * g.kb;
+  s2d_weight_kernel<<<ceil_div(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(Cout, C, k, g.kb, g.delta, w, w_eq);
+  g_launches++;
+  PCV_CHECK_CUDA(cudaGetLastError());
+  return PCV_OK;
+}
+
+}  // extern "C"

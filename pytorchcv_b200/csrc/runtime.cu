@@ -70,7 +70,7 @@ int conv_route(const pcv_conv_desc& d, int dtype, std::string* why) {
   if (depthwise && pitch_or(d.in_pitch, d.Cin) % 8 == 0 && pitch_or(d.out_pitch, d.Cout) % 8 == 0 && d.Cin % 8 == 0)
     return ROUTE_DW;
   if (dtype == PCV_BF16 && !(d.flags & PCV_CONV_FORCE_SIMT) && igemm_supported(d, why)) return ROUTE_IGEMM;
-  return ROUTE_SIMT;
+  return ROUTE_SIMT;  // (validate_conv rejects overlapped / row-pitched views that reach this route)
 }
 
 static int validate_conv(const pcv_conv_desc* d, int dtype) {
@@ -81,9 +81,20 @@ static int validate_conv(const pcv_conv_desc* d, int dtype) {
   PCV_REQUIRE(d->groups > 0 && d->Cin % d->groups == 0 && d->Cout % d->groups == 0,
               "channels (%d -> %d) not divisible by groups=%d", d->Cin, d->Cout, d->groups);
   PCV_REQUIRE(d->act >= PCV_ACT_NONE && d->act <= PCV_ACT_HSIGMOID, "unknown activation %d", d->act);
-  PCV_REQUIRE(pitch_or(d->in_pitch, d->Cin) >= d->Cin && pitch_or(d->out_pitch, d->Cout) >= d->Cout,
+  PCV_REQUIRE((pitch_or(d->in_pitch, d->Cin) >= d->Cin || (d->flags & PCV_CONV_IN_OVERLAP)) &&
+                  pitch_or(d->out_pitch, d->Cout) >= d->Cout,
               "channel pitch smaller than channel count");
+  PCV_REQUIRE(!(d->flags & PCV_CONV_IN_OVERLAP) || (dtype == PCV_BF16 && d->groups == 1),
+              "overlapping input views are only supported by the bf16 tensor-core path");
+  PCV_REQUIRE(d->in_row_pitch == 0 || d->in_row_pitch >= (d->W - 1) * pitch_or(d->in_pitch, d->Cin) + d->Cin ||
+                  (d->flags & PCV_CONV_IN_OVERLAP),
+              "in_row_pitch smaller than a row");
   PCV_REQUIRE(!(d->flags & PCV_CONV_OUT_F32) || dtype == PCV_BF16, "OUT_F32 only applies to the bf16 tier");
+  if ((d->flags & PCV_CONV_IN_OVERLAP) || d->in_row_pitch != 0) {
+    std::string why;
+    PCV_REQUIRE(conv_route(*d, dtype, &why) == ROUTE_IGEMM, "row-pitched input views need the tcgen05 route: %s",
+                why.c_str());
+  }
   return PCV_OK;
 }
 

@@ -113,10 +113,18 @@ def _one(v) -> int:
 # ---------------------------------------------------------------------------------------------------------------
 # builder: records symbolic ops, then materialises them
 # ---------------------------------------------------------------------------------------------------------------
+class _NoS2dStem(Exception):
+    """The network input feeds more than the stem convolution: recompile with the generic NHWC ingest."""
+
+
 class Builder:
-    def __init__(self, dtype: int, device: torch.device):
+    def __init__(self, dtype: int, device: torch.device, allow_s2d_stem: bool = True):
         self.dtype = dtype
         self.device = device
+        self.allow_s2d_stem = allow_s2d_stem
+        self.input_tref: TRef | None = None   # NHWC (channel-padded) image, set by CompiledModule
+        self.image_channels = 0
+        self.stem: dict | None = None         # {"k": kernel, "tref": s2d tensor} once the s2d stem is chosen
         self.ops: list[Callable[[Any, Callable[[TRef], int]], None]] = []
         self.bufs: list[Buf] = []
         self.weight_jobs: list[tuple] = []   # (kind, payload) resolved in materialise()
@@ -138,8 +146,44 @@ class Builder:
         idx = len(self.ops)
         for t in trefs:
             if t is not None:
+                if self.stem is not None and self.input_tref is not None and t.buf is self.input_tref.buf:
+                    raise _NoS2dStem()
                 t.buf.last = max(t.buf.last, idx)
         return idx
+
+    def _s2d_stem(self, x: TRef, conv, k: int, stride: int, pad: int, dil: int) -> bool:
+        """k x k stride-2 conv on the <=4-channel network input -> space-to-depth stem (include/pcv_b200.h)."""
+        return (self.allow_s2d_stem and self.dtype == BF16 and x is self.input_tref and self.stem is None
+                and x.buf.last < 0 and conv.groups == 1 and conv.in_channels == self.image_channels <= 4
+                and k in (3, 5, 7) and conv.kernel_size[0] == conv.kernel_size[1] and stride == 2 and pad == k // 2
+                and dil == 1 and x.H % 2 == 0 and x.W % 2 == 0)
+
+    def _conv_s2d(self, x: TRef, conv, bn, act: int, k: int) -> TRef:
+        rows, cols, cin_eq, taps = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _lib.call("pcv_stem_s2d_dims", conv.in_channels, x.H, x.W, k, C.byref(rows), C.byref(cols), C.byref(cin_eq),
+                  C.byref(taps))
+        xs = self.new(x.N, rows.value, cols.value, 16)
+        xs.buf.first, xs.buf.pinned = -1, True
+        x.buf.nbytes = 0                      # the NHWC copy of the image is never materialised
+        self.stem = {"k": k, "tref": xs}
+        Ho, Wo, cout = x.H // 2, x.W // 2, conv.out_channels
+        out = self.new(x.N, Ho, Wo, cout)
+        d = ConvDesc(N=x.N, H=rows.value, W=Wo, Cin=cin_eq.value, Cout=cout, kh=taps.value, kw=1, stride=1, pad=0,
+                     dil=1, groups=1, act=act, in_pitch=16, out_pitch=out.pitch, res_pitch=0,
+                     flags=_lib.CONV_IN_OVERLAP, in_row_pitch=cols.value * 16)
+        wb, bb = C.c_size_t(), C.c_size_t()
+        _lib.call("pcv_conv_packed_bytes", C.byref(d), self.dtype, C.byref(wb), C.byref(bb))
+        w_off, b_off = self._wblob(wb.value), self._wblob(bb.value)
+        self.weight_jobs.append(("conv_s2d", (d, conv, bn, k, w_off, b_off)))
+        idx = len(self.ops)
+        xs.buf.last = out.buf.last = idx
+        dtype = self.dtype
+
+        def emit(plan, ptr, wptr):
+            _lib.call("pcv_conv2d_bias_act", plan, C.byref(d), dtype, ptr(xs), wptr(w_off), wptr(b_off), None,
+                      ptr(out), None)
+        self.ops.append(emit)
+        return out
 
     def _wblob(self, nbytes: int) -> int:
         off = self.weight_bytes
@@ -155,6 +199,10 @@ class Builder:
         kh, kw = conv.kernel_size
         k_stride, k_pad, k_dil = _one(conv.stride), _one(conv.padding), _one(conv.dilation)
         cin, cout, groups = conv.in_channels, conv.out_channels, conv.groups
+        if residual is None and out is None and not out_f32 and self._s2d_stem(x, conv, kh, k_stride, k_pad, k_dil):
+            if bn is not None:
+                _check_bn(bn)
+            return self._conv_s2d(x, conv, bn, act, kh)
         pad_cin = 0
         if cin != x.C:
             # the ingest pads the image's channels with zeros up to a multiple of 8 (TMA needs 16-byte strides):
@@ -590,13 +638,20 @@ class CompiledModule:
         self.signature = weights_signature(module)
         N, Cin, H, W = self.in_shape
 
-        b = Builder(self.dtype, self.device)
-        x = b.new(N, H, W, _rup(Cin, 8))
-        x.buf.first = -1
-        x.buf.pinned = True
-        self._in = x
+        for allow_s2d in (True, False):
+            b = Builder(self.dtype, self.device, allow_s2d_stem=allow_s2d)
+            x = b.new(N, H, W, _rup(Cin, 8))
+            x.buf.first = -1
+            x.buf.pinned = True
+            b.input_tref, b.image_channels = x, Cin
+            try:
+                result = lower(b, module, x, **(lower_kwargs or {}))
+                break
+            except _NoS2dStem:
+                continue
+        self._stem_k = b.stem["k"] if b.stem else 0
+        self._in = b.stem["tref"] if b.stem else x
         self._in_channels = Cin
-        result = lower(b, module, x, **(lower_kwargs or {}))
         self._structure, trefs = _flatten(result)
         outs = []
         for t in trefs:
@@ -654,8 +709,17 @@ class CompiledModule:
                 rel = wptr(off) - self.weights.data_ptr()
                 self.weights[rel:rel + src.numel() * 4].copy_(src.view(-1).view(torch.uint8))
                 continue
-            d, conv, bn, pad_cin, w_off, b_off = payload
-            w = self._dev_f32(conv.weight)
+            if kind == "conv_s2d":
+                d, conv, bn, k, w_off, b_off = payload
+                w0 = self._dev_f32(conv.weight)
+                w = torch.empty((conv.out_channels, d.Cin, d.kh, 1), dtype=torch.float32, device=self.device)
+                _lib.call("pcv_stem_s2d_weights", conv.out_channels, conv.in_channels, k, w0.data_ptr(), w.data_ptr(),
+                          stream)
+                keep.append(w0)
+                pad_cin = 0
+            else:
+                d, conv, bn, pad_cin, w_off, b_off = payload
+                w = self._dev_f32(conv.weight)
             if pad_cin:
                 w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, pad_cin)).contiguous()
             cb = self._dev_f32(conv.bias)
@@ -703,16 +767,23 @@ class CompiledModule:
         if self.use_graph:
             gs = self._graph_stream
             gs.wait_stream(cur)
-            _lib.call("pcv_nchw_f32_to_nhwc", None, self.dtype, N, Cin, H, W, x.data_ptr(), self._in_ptr,
-                      self._in.pitch, gs.cuda_stream)
+            self._ingest(x, gs.cuda_stream)
             _lib.call("pcv_plan_graph_launch", self._plan, gs.cuda_stream)
             cur.wait_stream(gs)
             x.record_stream(gs)
         else:
-            _lib.call("pcv_nchw_f32_to_nhwc", None, self.dtype, N, Cin, H, W, x.data_ptr(), self._in_ptr,
-                      self._in.pitch, cur.cuda_stream)
+            self._ingest(x, cur.cuda_stream)
             _lib.call("pcv_plan_run", self._plan, cur.cuda_stream)
         return _unflatten(self._structure, list(self._out_tensors))
+
+    def _ingest(self, x: torch.Tensor, stream: int) -> None:
+        """The network edge: NCHW fp32 image -> NHWC (channel-padded) or, for a strided stem, space-to-depth."""
+        N, Cin, H, W = self.in_shape
+        if self._stem_k:
+            _lib.call("pcv_stem_s2d_ingest", None, N, Cin, H, W, self._stem_k, x.data_ptr(), self._in_ptr, stream)
+        else:
+            _lib.call("pcv_nchw_f32_to_nhwc", None, self.dtype, N, Cin, H, W, x.data_ptr(), self._in_ptr,
+                      self._in.pitch, stream)
 
     def profile(self) -> list[tuple[str, float, float, float]]:
         """[(op name, ms, algorithmic FLOPs, algorithmic bytes)] for one eager pass (synchronises)."""
