@@ -12,6 +12,7 @@ patterns raise (NotImplementedError / ValueError) at compile time.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass, field
 from typing import Any, Callable
 
@@ -833,6 +834,12 @@ def _unflatten(spec, flat):
 # per-module cache used by the mirror modules' forward() and by accelerate()
 # ---------------------------------------------------------------------------------------------------------------
 _DEFAULT = {"dtype": "bf16", "graph": False}
+# compiled plans per module instance; kept OUT of module.__dict__ so deepcopy / pickle / state_dict never see them
+_CACHES: "weakref.WeakKeyDictionary[nn.Module, dict]" = weakref.WeakKeyDictionary()
+
+
+def plan_cache(module: nn.Module) -> dict:
+    return _CACHES.setdefault(module, {})
 
 
 def set_default_precision(dtype: str) -> None:
@@ -850,7 +857,7 @@ def run_module(module: nn.Module, x: torch.Tensor, dtype=None, graph=None, check
                            "to the GPU or use the reference package on CPU")
     dtype = _DEFAULT["dtype"] if dtype is None else dtype
     graph = _DEFAULT["graph"] if graph is None else graph
-    cache = module.__dict__.setdefault("_pcv_cache", {})
+    cache = plan_cache(module)
     key = (tuple(x.shape), dtype_code(dtype), x.device.index, bool(graph), tuple(sorted(lower_kwargs.items())))
     cm = cache.get(key)
     if cm is not None and check_weights and cm.signature != weights_signature(module):
@@ -865,7 +872,7 @@ def run_module(module: nn.Module, x: torch.Tensor, dtype=None, graph=None, check
 def invalidate(module: nn.Module) -> None:
     """Drop every compiled plan cached on `module` (and its sub-modules)."""
     for mod in module.modules():
-        mod.__dict__.pop("_pcv_cache", None)
+        _CACHES.pop(mod, None)
 
 
 class Accelerated(nn.Module):
@@ -882,7 +889,7 @@ class Accelerated(nn.Module):
     def compiled(self, x: torch.Tensor) -> CompiledModule:
         self.forward(x)
         key = (tuple(x.shape), dtype_code(self._dtype), x.device.index, bool(self._graph), ())
-        return self.net.__dict__["_pcv_cache"][key]
+        return plan_cache(self.net)[key]
 
 
 def accelerate(net: nn.Module, dtype="bf16", graph: bool = False, check_weights: bool = True) -> Accelerated:

@@ -113,11 +113,12 @@ def test_recompiles_when_weights_change_and_caches_per_shape():
     net = seeded_init(P.get_model("resnet18", pretrained=False).eval(), seed=0).cuda()
     x = seeded_input((2, 3, 224, 224)).cuda()
     y0 = net(x).clone()
-    assert len(net.__dict__["_pcv_cache"]) == 1
+    from pytorchcv_b200.plan import plan_cache
+    assert len(plan_cache(net)) == 1
     y1 = net(x).clone()
     assert torch.equal(y0, y1)                       # deterministic replay
     net(seeded_input((1, 3, 224, 224)).cuda())
-    assert len(net.__dict__["_pcv_cache"]) == 2      # one plan per input shape
+    assert len(plan_cache(net)) == 2                 # one plan per input shape
     with torch.no_grad():
         net.output.bias.add_(1.0)                    # in-place update bumps the tensor version -> recompile
     y2 = net(x)
