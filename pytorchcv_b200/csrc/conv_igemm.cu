@@ -18,34 +18,9 @@
 //   warp 2  TMEM allocator                              warp 3  residual prefetcher (TMA load into the staging tile)
 //   warps 4-7  epilogue: tcgen05.ld -> +bias (+residual) -> act -> bf16 -> swizzled staging smem -> TMA store
 // so the epilogue of tile i overlaps the main loop of tile i+1.
-#include "ptx.cuh"
-#include "runtime.h"
+#include "igemm_common.cuh"
 
 namespace pcv {
-
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
-constexpr int NUM_THREADS = 256;
-constexpr int EPI_THREADS = 128;
-
-struct IgemmParams {
-  const float* bias;          // [round_up(Cout,128)] folded BN bias
-  void* out;                  // direct-store modes only
-  const __nv_bfloat16* res;   // direct-store modes only
-  int M, Cout;
-  int out_pitch, res_pitch;
-  int HoWo, Wo;
-  int stride, pad, dil, kw;
-  int cblocks;                // 64-channel blocks per filter tap
-  int num_kblocks;            // taps * cblocks
-  int tiles_m, tiles_n;
-  int act, has_res;
-  float act_lo, act_hi;        // ReLU / ReLU6 / none as a clamp; other activations take the slow path
-  int a_mode;                 // 0: 2-D tiled [Cin, M]; 1: im2col 4-D
-  int out_mode;               // 0: TMA bf16 store; 1: direct bf16; 2: direct fp32
-  int grouped;                // 1: A channel window = n_tile*BLOCK_N (block-diagonal weights)
-};
 
 template <int BN, int STAGES>
 struct SmemLayout {
@@ -63,20 +38,6 @@ struct SmemLayout {
   static constexpr int TOTAL = OFF_BAR + NUM_BARS * 8 + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;                    // slack for manual 1 KiB alignment
 };
-
-// Rare activations (sigmoid / swish / h-swish / h-sigmoid): kept out of line so the hot epilogue stays compact —
-// an inlined 7-way switch per element blew the epilogue up to ~100 KB of SASS and made it instruction-fetch bound.
-__device__ __noinline__ float apply_act(float v, int act) {
-  switch (act) {
-    case PCV_ACT_RELU: return fmaxf(v, 0.f);
-    case PCV_ACT_RELU6: return fminf(fmaxf(v, 0.f), 6.f);
-    case PCV_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
-    case PCV_ACT_SWISH: return v / (1.f + __expf(-v));
-    case PCV_ACT_HSWISH: return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
-    case PCV_ACT_HSIGMOID: return fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
-    default: return v;
-  }
-}
 
 template <int BN, int STAGES, int OUT_MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -155,6 +116,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         int tap = 0, cb = 0, fr = 0, fs = 0;
         for (int kb = 0; kb < p.num_kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
+          if (p.dbg & 1) {
+            mbar_arrive(&full[stage]);
+          } else {
           mbar_arrive_expect_tx(&full[stage], A_STAGE_BYTES + L::B_STAGE_BYTES);
           uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
           if (p.a_mode == 1) {
@@ -164,6 +128,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tma_load_2d(&tmA, &full[stage], a_dst, c_base + cb * BLOCK_K, m0);
           }
           tma_load_2d(&tmB, &full[stage], sB + stage * L::B_STAGE_BYTES, kb * BLOCK_K, n_tile * BN);
+          }
           if (++cb == p.cblocks) {
             cb = 0;
             ++tap;
@@ -183,6 +148,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ===================================== MMA issuer =====================================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN);
+      const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA)), b_lo0 = smem_desc_lo(smem_u32(sB));
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -195,13 +161,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kb = 0; kb < p.num_kblocks; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * L::B_STAGE_BYTES);
+          const uint32_t a_lo = a_lo0 + stage * (A_STAGE_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + stage * (L::B_STAGE_BYTES >> 4);
+          if (!(p.dbg & 2)) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t a_desc = make_smem_desc(a_addr + k * 32, 128);
-            const uint64_t b_desc = make_smem_desc(b_addr + k * 32, 128);
-            umma_bf16(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / 16; ++k)
+              umma_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty[stage]);  // frees this smem stage once the MMAs above have read it
           if (++stage == STAGES) {
@@ -457,7 +422,7 @@ int igemm_packed_bytes(const pcv_conv_desc& d, size_t* w_bytes, size_t* b_bytes)
   const int taps = d.kh * d.kw;
   const int cblocks = d.groups > 1 ? 1 : ceil_div(d.Cin, BLOCK_K);
   *w_bytes = static_cast<size_t>(d.Cout) * taps * cblocks * BLOCK_K * 2;
-  *b_bytes = static_cast<size_t>(round_up(d.Cout, 128)) * 4;
+  *b_bytes = static_cast<size_t>(round_up(d.Cout, 256)) * 4;
   return PCV_OK;
 }
 
@@ -469,7 +434,7 @@ int igemm_pack(const pcv_conv_desc& d, const float* w, const float* conv_bias, c
   const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 4096));
   igemm_pack_kernel<<<blocks, 256, 0, s>>>(w, conv_bias, g, b, m, v, eps, d.Cout, d.Cin, d.groups, taps, cblocks, 64,
                                            reinterpret_cast<__nv_bfloat16*>(w_packed), bias_out,
-                                           round_up(d.Cout, 128));
+                                           round_up(d.Cout, 256));
   g_launches++;
   PCV_CHECK_CUDA(cudaGetLastError());
   return PCV_OK;
@@ -518,6 +483,7 @@ struct IgemmOp : Op {
   CUtensorMap tmA, tmB, tmOut, tmRes;
   IgemmParams p;
   int bn, grid;
+  bool pair = false;  // cta_group::2 kernel (conv_igemm2.cu)
   cudaError_t launch(cudaStream_t s) override;
 };
 
@@ -547,6 +513,7 @@ static cudaError_t launch_bn(const IgemmOp& op, cudaStream_t s) {
 
 cudaError_t IgemmOp::launch(cudaStream_t s) {
   g_launches++;
+  if (pair) return launch_igemm2(bn, grid, tmA, tmB, tmOut, tmRes, p, s);
   switch (bn) {
     case 32: return launch_bn<32, 6>(*this, s);
     case 64: return launch_bn<64, 6>(*this, s);
@@ -586,12 +553,16 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   p.cblocks = grouped ? 1 : ceil_div(d.Cin, BLOCK_K);
   p.num_kblocks = taps * p.cblocks;
   p.tiles_m = ceil_div(p.M, BLOCK_M);
-  p.tiles_n = ceil_div(d.Cout, op->bn);
   p.act = d.act;
   p.act_lo = (d.act == PCV_ACT_RELU || d.act == PCV_ACT_RELU6) ? 0.f : -INFINITY;
   p.act_hi = d.act == PCV_ACT_RELU6 ? 6.f : INFINITY;
   p.has_res = res != nullptr;
   p.grouped = grouped;
+  p.stages = p.nstg = 0;
+  {
+    const char* e = getenv("PCV_IGEMM_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   const bool pointwise = (taps == 1 && d.stride == 1 && d.pad == 0 && d.in_row_pitch == 0 &&
                           !(d.flags & PCV_CONV_IN_OVERLAP));
   p.a_mode = (pointwise && !(d.flags & PCV_CONV_A_IM2COL)) ? 0 : 1;
@@ -600,6 +571,17 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   p.out_mode = tma_out ? 0 : ((d.flags & PCV_CONV_OUT_F32) ? 2 : 1);
   PCV_REQUIRE(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(w) % 16 == 0,
               "conv operands must be 16-byte aligned");
+  // CTA-pair kernel for wide dense layers: halves the L2->SMEM operand traffic per MMA (see conv_igemm2.cu)
+  static const bool pair_enabled = [] {
+    const char* e = getenv("PCV_IGEMM_2CTA");
+    return !(e && e[0] == '0');
+  }();
+  op->pair = pair_enabled && p.out_mode == 0 && d.Cout >= 64 && p.tiles_m >= 2;
+  if (op->pair) {
+    op->bn = grouped ? 64 : (d.Cout > 128 ? 256 : (d.Cout > 64 ? 128 : 64));
+    igemm2_pick_smem(op->bn, p.num_kblocks, res != nullptr, &p.stages, &p.nstg);
+  }
+  p.tiles_n = ceil_div(d.Cout, op->bn);
 
   int rc;
   if (p.a_mode == 1) {
@@ -609,7 +591,8 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   }
   if (rc) return rc;
   const uint64_t kpad = (uint64_t)taps * p.cblocks * BLOCK_K;
-  rc = make_tiled_2d(&op->tmB, w, kpad, d.Cout, kpad * 2, BLOCK_K, op->bn, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = make_tiled_2d(&op->tmB, w, kpad, d.Cout, kpad * 2, BLOCK_K, op->pair ? op->bn / 2 : op->bn,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   const int sub_cols = op->bn >= 64 ? 64 : op->bn;
   const CUtensorMapSwizzle oswz = sub_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -626,11 +609,12 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
     op->tmOut = op->tmB;
     op->tmRes = op->tmB;
   }
-  op->grid = std::min(p.tiles_m * p.tiles_n, sm_count());
+  if (op->pair) op->grid = 2 * std::min(((p.tiles_m + 1) / 2) * p.tiles_n, sm_count() / 2);
+  else op->grid = std::min(p.tiles_m * p.tiles_n, sm_count());
 
   char nm[160];
-  snprintf(nm, sizeof nm, "conv_tc %dx%d s%d d%d g%d %d->%d @%dx%d bn=%d%s%s", d.kh, d.kw, d.stride, d.dil, d.groups,
-           d.Cin, d.Cout, d.H, d.W, op->bn, res ? " +res" : "", p.out_mode ? " direct" : "");
+  snprintf(nm, sizeof nm, "conv_tc%s %dx%d s%d d%d g%d %d->%d @%dx%d bn=%d%s%s", op->pair ? "2" : "", d.kh, d.kw,
+           d.stride, d.dil, d.groups, d.Cin, d.Cout, d.H, d.W, op->bn, res ? " +res" : "", p.out_mode ? " direct" : "");
   op->name = nm;
   const double e = 2.0;
   const double pin = (taps == 1 && d.stride > 1) ? (double)Ho * Wo : (double)d.H * d.W;

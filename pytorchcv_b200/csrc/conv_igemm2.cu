@@ -1,0 +1,366 @@
+// CTA-pair variant of the implicit-GEMM convolution: tcgen05.mma.cta_group::2, 256 x BN output tile per cluster.
+//
+// Why: with 128 x 128 single-CTA tiles every SM has to pull 32 KB of operands from L2 per 256 MMA cycles, and the
+// L2 -> SMEM fabric (measured ~11.7 TB/s on B200, round-1 profiles) saturates long before the tensor pipe or HBM.
+// Pairing the two SMs of a TPC halves that traffic: each CTA loads its own 128 pixel rows of A and only HALF of the
+// B (weight) tile; one tcgen05.mma (M = 256, N = BN <= 256) issued by the leader CTA consumes A/B from both CTAs'
+// shared memory and writes 128 x BN accumulators into EACH CTA's TMEM.  BN = 256 also halves how often an A tile is
+// re-read for wide layers.
+//
+// Roles per CTA (8 warps) are those of conv_igemm.cu; differences:
+//   * cluster of 2 (rank 0 = leader).  Both producers issue `cp.async.bulk.tensor...cta_group::2` loads that
+//     complete on the LEADER's full barrier (count 1: the leader's arrive.expect_tx covers both CTAs' bytes).  Only the leader's warp 1 issues MMAs; `tcgen05.commit...multicast::cluster` (mask 0b11)
+//     releases the smem stage / publishes the accumulator in both CTAs.
+//   * the accumulator-free barrier lives in the leader and counts the 4 epilogue warps of BOTH CTAs (peer arrives
+//     through mapa + mbarrier.arrive.shared::cluster).
+//   * the epilogue's staging ring works on 64-column sub-tiles (16 KB): residual TMA load -> math -> TMA store per
+//     sub-tile, NSTG slots, up to PENDING stores in flight, so the residual of sub-tile u+NSTG-PENDING is prefetched
+//     while sub-tile u is computed and no per-tile bubble remains.
+#include "igemm_common.cuh"
+
+namespace pcv {
+
+template <int BN>
+struct Pair {
+  static constexpr int HALF_N = BN / 2;
+  static constexpr int B_STAGE_BYTES = HALF_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int SUB_COLS = 64;
+  static constexpr int SUB_BYTES = BLOCK_M * SUB_COLS * 2;  // 16 KiB
+  static constexpr int NSUB = BN / SUB_COLS;                // sub-tiles per output tile
+  static constexpr int PENDING = 1;                         // TMA stores allowed in flight
+  static constexpr int MAX_STAGES = 8, MAX_NSTG = 8;
+  static constexpr int NUM_BARS = 2 * MAX_STAGES + 4 + 2 * MAX_NSTG;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;             // double-buffered accumulator (256 or 512 columns)
+  // shared memory: [stages x A][stages x B][nstg x staging][barriers]; the split is chosen per layer at run time
+  // (long-K tensor-bound layers want a deep operand ring, short-K bandwidth-bound layers a deep staging ring)
+  static constexpr int SMEM_LIMIT = 232448;
+  __host__ __device__ static constexpr int bytes(int stages, int nstg) {
+    return stages * STAGE_BYTES + nstg * SUB_BYTES + NUM_BARS * 8 + 16 + 1024;
+  }
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+              const IgemmParams p) {
+  using L = Pair<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int STAGES = p.stages, NSTG = p.nstg;
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + STAGES * A_STAGE_BYTES;
+  uint8_t* sStg = sB + STAGES * L::B_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + NSTG * L::SUB_BYTES);
+  uint64_t* full = bars;                            // [STAGES]  (leader's copy is the live one)
+  uint64_t* empty = bars + L::MAX_STAGES;           // [STAGES]  per CTA, released by the multicast commit
+  uint64_t* tmem_full = bars + 2 * L::MAX_STAGES;   // [2]       per CTA, multicast commit
+  uint64_t* tmem_empty = tmem_full + 2;             // [2]       leader's copy, 8 arrivals
+  uint64_t* stg_empty = tmem_empty + 2;             // [NSTG]
+  uint64_t* res_full = stg_empty + L::MAX_NSTG;     // [NSTG]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();        // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+  const int pair_tiles_m = (p.tiles_m + 1) >> 1;
+  const int num_tiles = pair_tiles_m * p.tiles_n;  // pair tiles: 256 rows x BN columns
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+    if (p.has_res) tma_prefetch_desc(&tmRes);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);   // leader's arrive.expect_tx covers both CTAs' bytes
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    for (int i = 0; i < NSTG; ++i) {
+      mbar_init(&stg_empty[i], 1);
+      mbar_init(&res_full[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc2(tmem_ptr, L::TMEM_COLS);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // peer barriers initialised, both TMEM allocations done
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================== TMA producer (both CTAs) =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < num_tiles; t += npairs) {
+        const int pm = t / p.tiles_n;
+        const int n_tile = t - pm * p.tiles_n;
+        int m0 = (2 * pm + static_cast<int>(rank)) * BLOCK_M;
+        if (m0 >= p.M) m0 = 0;  // phantom second tile of an odd tail pair: load anything valid, its store is clipped
+        const int img = m0 / p.HoWo;
+        const int rem = m0 - img * p.HoWo;
+        const int ho = rem / p.Wo;
+        const int wo = rem - ho * p.Wo;
+        const int w0 = wo * p.stride - p.pad;
+        const int h0 = ho * p.stride - p.pad;
+        const int b_row = n_tile * BN + static_cast<int>(rank) * L::HALF_N;
+        const int c_base = p.grouped ? n_tile * BN : 0;
+        int cb = 0, fr = 0, fs = 0;
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
+          if (p.dbg & 1) {
+            if (rank == 0) mbar_arrive(&full[stage]);
+          } else {
+          // only the leader arrives; the peer's bytes may land first (tx-count goes negative, the phase cannot
+          // complete before the leader's arrival), exactly the CUTLASS 2-SM pipeline protocol
+          if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * L::STAGE_BYTES);
+          uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
+          if (p.a_mode == 1) {
+            tma2_load_im2col_4d(&tmA, full_leader, a_dst, c_base + cb * BLOCK_K, w0, h0, img,
+                                static_cast<uint16_t>(fs * p.dil), static_cast<uint16_t>(fr * p.dil));
+          } else {
+            tma2_load_2d(&tmA, full_leader, a_dst, c_base + cb * BLOCK_K, m0);
+          }
+          tma2_load_2d(&tmB, full_leader, sB + stage * L::B_STAGE_BYTES, kb * BLOCK_K, b_row);
+          }
+          if (++cb == p.cblocks) {
+            cb = 0;
+            if (++fs == p.kw) {
+              fs = 0;
+              ++fr;
+            }
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader CTA only) =====================================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BN);
+      const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA)), b_lo0 = smem_desc_lo(smem_u32(sB));
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = pair; t < num_tiles; t += npairs, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + stage * (A_STAGE_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + stage * (L::B_STAGE_BYTES >> 4);
+          if (!(p.dbg & 2)) {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k)
+              umma2_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma2_commit(&empty[stage], 0x3);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma2_commit(&tmem_full[buf], 0x3);
+      }
+    }
+  } else if (warp == 3) {
+    // ===================================== residual prefetcher (both CTAs) =====================================
+    if (lane == 0 && p.has_res) {
+      int slot = 0;
+      uint32_t sphase = 0;
+      for (int t = pair; t < num_tiles; t += npairs) {
+        const int pm = t / p.tiles_n;
+        const int n_tile = t - pm * p.tiles_n;
+        const int m0 = (2 * pm + static_cast<int>(rank)) * BLOCK_M;
+        for (int sub = 0; sub < L::NSUB; ++sub) {
+          mbar_wait(&stg_empty[slot], sphase ^ 1);
+          mbar_arrive_expect_tx(&res_full[slot], L::SUB_BYTES);
+          tma_load_2d(&tmRes, &res_full[slot], sStg + slot * L::SUB_BYTES, n_tile * BN + sub * L::SUB_COLS, m0);
+          if (++slot == NSTG) {
+            slot = 0;
+            sphase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue (both CTAs) =====================================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int epi_tid = threadIdx.x - 128;
+    const float act_lo = p.act_lo, act_hi = p.act_hi;
+    const bool fancy_act = p.act > PCV_ACT_RELU6;
+    const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+    const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
+    int it = 0;
+    int slot = 0;
+    int subs_done = 0;
+    uint32_t sphase = 0;
+    for (int t = pair; t < num_tiles; t += npairs, ++it) {
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int pm = t / p.tiles_n;
+      const int n_tile = t - pm * p.tiles_n;
+      const int m0 = (2 * pm + static_cast<int>(rank)) * BLOCK_M;
+      const int n0 = n_tile * BN;
+
+      mbar_wait(&tmem_full[buf], acc_phase);
+      tc_fence_after();
+
+#pragma unroll 1
+      for (int sub = 0; sub < L::NSUB; ++sub) {
+        uint8_t* stg = sStg + slot * L::SUB_BYTES;
+        if (p.has_res) mbar_wait(&res_full[slot], sphase);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int col = sub * L::SUB_COLS + h * 32;
+          uint32_t acc[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + col, acc);
+          tmem_ld_wait();
+          float v[32];
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(bias4 + i);
+            v[4 * i + 0] = __uint_as_float(acc[4 * i + 0]) + b.x;
+            v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b.y;
+            v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b.z;
+            v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b.w;
+          }
+          const uint32_t row_off = row * 128 + h * 64;
+          if (p.has_res) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t off = row_off + c * 16;
+              off ^= ((off >> 7) & 7u) << 4;
+              const uint4 r = *reinterpret_cast<const uint4*>(stg + off);
+              v[8 * c + 0] += bf16lo(r.x);
+              v[8 * c + 1] += bf16hi(r.x);
+              v[8 * c + 2] += bf16lo(r.y);
+              v[8 * c + 3] += bf16hi(r.y);
+              v[8 * c + 4] += bf16lo(r.z);
+              v[8 * c + 5] += bf16hi(r.z);
+              v[8 * c + 6] += bf16lo(r.w);
+              v[8 * c + 7] += bf16hi(r.w);
+            }
+          }
+          if (fancy_act) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], act_lo), act_hi);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t off = row_off + c * 16;
+            off ^= ((off >> 7) & 7u) << 4;
+            uint4 o;
+            o.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]);
+            o.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+            o.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
+            o.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+            *reinterpret_cast<uint4*>(stg + off) = o;
+          }
+        }
+        if (sub == L::NSUB - 1) {
+          // all accumulator columns of this tile are in registers / smem: release the TMEM buffer to the leader's MMA
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (rank == 0) mbar_arrive(&tmem_empty[buf]);
+            else mbar_arrive_cluster(buf ? tmem_empty_leader1 : tmem_empty_leader0);
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, EPI_THREADS);
+        if (epi_tid == 0) {
+          tma_store_2d(&tmOut, stg, n0 + sub * L::SUB_COLS, m0);
+          tma_store_commit();
+          // at most PENDING stores in flight: the slot used PENDING sub-tiles ago is readable again by TMA loads
+          tma_store_wait_read<L::PENDING>();
+          if (subs_done >= L::PENDING) {
+            const int freed = slot >= L::PENDING ? slot - L::PENDING : slot - L::PENDING + NSTG;
+            mbar_arrive(&stg_empty[freed]);
+          }
+        }
+        ++subs_done;
+        if (++slot == NSTG) {
+          slot = 0;
+          sphase ^= 1;
+        }
+      }
+    }
+    if (epi_tid == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // no CTA may exit (or free TMEM) while its peer can still multicast into it
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, L::TMEM_COLS);
+  }
+}
+
+template <int BN>
+static cudaError_t launch_pair(int grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                               const CUtensorMap& tmRes, const IgemmParams& p, cudaStream_t s) {
+  using L = Pair<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_LIMIT);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  igemm2_kernel<BN><<<grid, NUM_THREADS, L::bytes(p.stages, p.nstg), s>>>(tmA, tmB, tmOut, tmRes, p);
+  return cudaGetLastError();
+}
+
+// Operand-ring depth / staging slots for a layer: everything that fits in 227 KB, biased by the K extent.
+void igemm2_pick_smem(int bn, int num_kblocks, bool has_res, int* stages, int* nstg) {
+  const int stage_bytes = A_STAGE_BYTES + (bn / 2) * BLOCK_K * 2;
+  const int sub_bytes = BLOCK_M * 64 * 2;
+  const int fixed = (2 * 8 + 4 + 2 * 8) * 8 + 16 + 1024;
+  // >= PENDING + 2 slots, so that (without a residual wait) the barrier before the NEXT store orders every epilogue
+  // thread's writes into a slot after thread 0 has seen that slot's previous store finish reading
+  int ns = num_kblocks >= 8 ? 3 : (has_res ? 6 : 4);        // long-K: the epilogue is hidden anyway
+  int st = (232448 - fixed - ns * sub_bytes) / stage_bytes;
+  st = std::min(st, 8);
+  if (num_kblocks < 8) st = std::min(st, 4);
+  ns = std::max(3, std::min(8, (232448 - fixed - st * stage_bytes) / sub_bytes));
+  if (const char* e = getenv("PCV_IGEMM2_STAGES")) st = atoi(e);
+  if (const char* e = getenv("PCV_IGEMM2_NSTG")) ns = atoi(e);
+  *stages = st;
+  *nstg = ns;
+}
+
+cudaError_t launch_igemm2(int bn, int grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                          const CUtensorMap& tmRes, const IgemmParams& p, cudaStream_t s) {
+  switch (bn) {
+    case 256: return launch_pair<256>(grid, tmA, tmB, tmOut, tmRes, p, s);
+    case 128: return launch_pair<128>(grid, tmA, tmB, tmOut, tmRes, p, s);
+    default: return launch_pair<64>(grid, tmA, tmB, tmOut, tmRes, p, s);
+  }
+}
+
+}  // namespace pcv

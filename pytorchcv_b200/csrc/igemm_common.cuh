@@ -1,0 +1,55 @@
+// Definitions shared by the 1-CTA (conv_igemm.cu) and CTA-pair (conv_igemm2.cu) implicit-GEMM kernels.
+#pragma once
+#include "ptx.cuh"
+#include "runtime.h"
+
+namespace pcv {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_THREADS = 128;
+
+struct IgemmParams {
+  const float* bias;          // [round_up(Cout,128)] folded BN bias
+  void* out;                  // direct-store modes only
+  const __nv_bfloat16* res;   // direct-store modes only
+  int M, Cout;
+  int out_pitch, res_pitch;
+  int HoWo, Wo;
+  int stride, pad, dil, kw;
+  int cblocks;                // 64-channel blocks per filter tap
+  int num_kblocks;            // taps * cblocks
+  int tiles_m, tiles_n;
+  int act, has_res;
+  float act_lo, act_hi;        // ReLU / ReLU6 / none as a clamp; other activations take the slow path
+  int a_mode;                 // 0: 2-D tiled [Cin, M]; 1: im2col 4-D
+  int out_mode;               // 0: TMA bf16 store; 1: direct bf16; 2: direct fp32
+  int grouped;                // 1: A channel window = n_tile*BLOCK_N (block-diagonal weights)
+  int dbg;                    // PCV_IGEMM_DBG: bit0 skip operand TMA, bit1 skip MMA issue (throughput experiments)
+  int stages, nstg;           // CTA-pair kernel: operand ring depth / staging slots (smem split chosen per layer)
+};
+
+// Rare activations (sigmoid / swish / h-swish / h-sigmoid): kept out of line so the hot epilogue stays compact —
+// an inlined 7-way switch per element blew the epilogue up to ~100 KB of SASS and made it instruction-fetch bound.
+static __device__ __noinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case PCV_ACT_RELU: return fmaxf(v, 0.f);
+    case PCV_ACT_RELU6: return fminf(fmaxf(v, 0.f), 6.f);
+    case PCV_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+    case PCV_ACT_SWISH: return v / (1.f + __expf(-v));
+    case PCV_ACT_HSWISH: return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    case PCV_ACT_HSIGMOID: return fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    default: return v;
+  }
+}
+
+
+// conv_igemm2.cu: launch the cta_group::2 kernel (BN = 128 or 256) on `grid` CTAs (a multiple of 2)
+cudaError_t launch_igemm2(int bn, int grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                          const CUtensorMap& tmRes, const IgemmParams& p, cudaStream_t s);
+
+void igemm2_pick_smem(int bn, int num_kblocks, bool has_res, int* stages, int* nstg);
+
+}  // namespace pcv
