@@ -559,6 +559,7 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   p.has_res = res != nullptr;
   p.grouped = grouped;
   p.stages = p.nstg = 0;
+  p.ksub = 1;
   {
     const char* e = getenv("PCV_IGEMM_DBG");
     p.dbg = e ? atoi(e) : 0;
@@ -579,7 +580,7 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   op->pair = pair_enabled && p.out_mode == 0 && d.Cout >= 64 && p.tiles_m >= 2;
   if (op->pair) {
     op->bn = grouped ? 64 : (d.Cout > 128 ? 256 : (d.Cout > 64 ? 128 : 64));
-    igemm2_pick_smem(op->bn, p.num_kblocks, res != nullptr, &p.stages, &p.nstg);
+    igemm2_pick_smem(op->bn, p.num_kblocks, res != nullptr, &p.stages, &p.ksub, &p.nstg);
   }
   p.tiles_n = ceil_div(d.Cout, op->bn);
 
@@ -613,8 +614,11 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   else op->grid = std::min(p.tiles_m * p.tiles_n, sm_count());
 
   char nm[160];
-  snprintf(nm, sizeof nm, "conv_tc%s %dx%d s%d d%d g%d %d->%d @%dx%d bn=%d%s%s", op->pair ? "2" : "", d.kh, d.kw,
-           d.stride, d.dil, d.groups, d.Cin, d.Cout, d.H, d.W, op->bn, res ? " +res" : "", p.out_mode ? " direct" : "");
+  char cfg[48] = "";
+  if (op->pair) snprintf(cfg, sizeof cfg, " st%dx%d/%d", p.stages, p.ksub, p.nstg);
+  snprintf(nm, sizeof nm, "conv_tc%s %dx%d s%d d%d g%d %d->%d @%dx%d bn=%d%s%s%s", op->pair ? "2" : "", d.kh, d.kw,
+           d.stride, d.dil, d.groups, d.Cin, d.Cout, d.H, d.W, op->bn, cfg, res ? " +res" : "",
+           p.out_mode ? " direct" : "");
   op->name = nm;
   const double e = 2.0;
   const double pin = (taps == 1 && d.stride > 1) ? (double)Ho * Wo : (double)d.H * d.W;

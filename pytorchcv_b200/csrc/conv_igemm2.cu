@@ -28,15 +28,14 @@ struct Pair {
   static constexpr int SUB_COLS = 64;
   static constexpr int SUB_BYTES = BLOCK_M * SUB_COLS * 2;  // 16 KiB
   static constexpr int NSUB = BN / SUB_COLS;                // sub-tiles per output tile
-  static constexpr int PENDING = 1;                         // TMA stores allowed in flight
   static constexpr int MAX_STAGES = 8, MAX_NSTG = 8;
   static constexpr int NUM_BARS = 2 * MAX_STAGES + 4 + 2 * MAX_NSTG;
   static constexpr uint32_t TMEM_COLS = 2 * BN;             // double-buffered accumulator (256 or 512 columns)
   // shared memory: [stages x A][stages x B][nstg x staging][barriers]; the split is chosen per layer at run time
   // (long-K tensor-bound layers want a deep operand ring, short-K bandwidth-bound layers a deep staging ring)
   static constexpr int SMEM_LIMIT = 232448;
-  __host__ __device__ static constexpr int bytes(int stages, int nstg) {
-    return stages * STAGE_BYTES + nstg * SUB_BYTES + NUM_BARS * 8 + 16 + 1024;
+  __host__ __device__ static constexpr int bytes(int stages, int ksub, int nstg) {
+    return stages * ksub * STAGE_BYTES + nstg * SUB_BYTES + NUM_BARS * 8 + 16 + 1024;
   }
 };
 
@@ -48,10 +47,10 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   using L = Pair<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int STAGES = p.stages, NSTG = p.nstg;
+  const int STAGES = p.stages, NSTG = p.nstg, KSUB = p.ksub;
   uint8_t* sA = smem;
-  uint8_t* sB = sA + STAGES * A_STAGE_BYTES;
-  uint8_t* sStg = sB + STAGES * L::B_STAGE_BYTES;
+  uint8_t* sB = sA + STAGES * KSUB * A_STAGE_BYTES;
+  uint8_t* sStg = sB + STAGES * KSUB * L::B_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + NSTG * L::SUB_BYTES);
   uint64_t* full = bars;                            // [STAGES]  (leader's copy is the live one)
   uint64_t* empty = bars + L::MAX_STAGES;           // [STAGES]  per CTA, released by the multicast commit
@@ -101,6 +100,8 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
   if (warp == 0) {
     // ===================================== TMA producer (both CTAs) =====================================
+    // One full/empty handshake per STAGE; a stage holds KSUB 64-channel sub-blocks (KSUB chosen per layer so that
+    // a stage carries >= ~512 tensor-pipe cycles of work: the single-thread handshake costs ~400-600 cycles).
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -118,29 +119,31 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const int b_row = n_tile * BN + static_cast<int>(rank) * L::HALF_N;
         const int c_base = p.grouped ? n_tile * BN : 0;
         int cb = 0, fr = 0, fs = 0;
-        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+        for (int kb = 0; kb < p.num_kblocks; kb += KSUB) {
+          const int nsub = min(KSUB, p.num_kblocks - kb);
           mbar_wait(&empty[stage], phase ^ 1);
           const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
-          if (p.dbg & 1) {
-            if (rank == 0) mbar_arrive(&full[stage]);
-          } else {
           // only the leader arrives; the peer's bytes may land first (tx-count goes negative, the phase cannot
           // complete before the leader's arrival), exactly the CUTLASS 2-SM pipeline protocol
-          if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * L::STAGE_BYTES);
-          uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
-          if (p.a_mode == 1) {
-            tma2_load_im2col_4d(&tmA, full_leader, a_dst, c_base + cb * BLOCK_K, w0, h0, img,
-                                static_cast<uint16_t>(fs * p.dil), static_cast<uint16_t>(fr * p.dil));
-          } else {
-            tma2_load_2d(&tmA, full_leader, a_dst, c_base + cb * BLOCK_K, m0);
-          }
-          tma2_load_2d(&tmB, full_leader, sB + stage * L::B_STAGE_BYTES, kb * BLOCK_K, b_row);
-          }
-          if (++cb == p.cblocks) {
-            cb = 0;
-            if (++fs == p.kw) {
-              fs = 0;
-              ++fr;
+          if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * nsub * L::STAGE_BYTES);
+          uint8_t* a_dst = sA + stage * KSUB * A_STAGE_BYTES;
+          uint8_t* b_dst = sB + stage * KSUB * L::B_STAGE_BYTES;
+          for (int j = 0; j < nsub; ++j) {
+            if (p.a_mode == 1) {
+              tma2_load_im2col_4d(&tmA, full_leader, a_dst, c_base + cb * BLOCK_K, w0, h0, img,
+                                  static_cast<uint16_t>(fs * p.dil), static_cast<uint16_t>(fr * p.dil));
+            } else {
+              tma2_load_2d(&tmA, full_leader, a_dst, c_base + cb * BLOCK_K, m0);
+            }
+            tma2_load_2d(&tmB, full_leader, b_dst, (kb + j) * BLOCK_K, b_row);
+            a_dst += A_STAGE_BYTES;
+            b_dst += L::B_STAGE_BYTES;
+            if (++cb == p.cblocks) {
+              cb = 0;
+              if (++fs == p.kw) {
+                fs = 0;
+                ++fr;
+              }
             }
           }
           if (++stage == STAGES) {
@@ -164,15 +167,21 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BN;
-        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+        uint32_t accum = 0;
+        for (int kb = 0; kb < p.num_kblocks; kb += KSUB) {
+          const int nsub = min(KSUB, p.num_kblocks - kb);
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_lo = a_lo0 + stage * (A_STAGE_BYTES >> 4);
-          const uint32_t b_lo = b_lo0 + stage * (L::B_STAGE_BYTES >> 4);
-          if (!(p.dbg & 2)) {
+          uint32_t a_lo = a_lo0 + stage * KSUB * (A_STAGE_BYTES >> 4);
+          uint32_t b_lo = b_lo0 + stage * KSUB * (L::B_STAGE_BYTES >> 4);
+          for (int j = 0; j < nsub; ++j) {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / 16; ++k)
-              umma2_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              umma2_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, accum);
+              accum = 1;
+            }
+            a_lo += A_STAGE_BYTES >> 4;
+            b_lo += L::B_STAGE_BYTES >> 4;
           }
           umma2_commit(&empty[stage], 0x3);
           if (++stage == STAGES) {
@@ -297,13 +306,16 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         if (epi_tid == 0) {
           tma_store_2d(&tmOut, stg, n0 + sub * L::SUB_COLS, m0);
           tma_store_commit();
-          // at most PENDING stores in flight: the slot used PENDING sub-tiles ago is readable again by TMA loads
-          tma_store_wait_read<L::PENDING>();
-          if (subs_done >= L::PENDING) {
-            const int freed = slot >= L::PENDING ? slot - L::PENDING : slot - L::PENDING + NSTG;
-            mbar_arrive(&stg_empty[freed]);
+          if (NSTG >= 3) {
+            // one store stays in flight: the slot used one sub-tile ago is readable again by the residual TMA loads
+            tma_store_wait_read<1>();
+            if (subs_done >= 1) mbar_arrive(&stg_empty[slot >= 1 ? slot - 1 : NSTG - 1]);
+          } else {
+            tma_store_wait_read<0>();      // 2-slot ring (long-K layers): recycle this slot as soon as it is read
+            mbar_arrive(&stg_empty[slot]);
           }
         }
+        if (NSTG < 3) named_bar_sync(1, EPI_THREADS);  // without look-ahead every thread must see the slot free
         ++subs_done;
         if (++slot == NSTG) {
           slot = 0;
@@ -332,25 +344,33 @@ static cudaError_t launch_pair(int grid, const CUtensorMap& tmA, const CUtensorM
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  igemm2_kernel<BN><<<grid, NUM_THREADS, L::bytes(p.stages, p.nstg), s>>>(tmA, tmB, tmOut, tmRes, p);
+  igemm2_kernel<BN><<<grid, NUM_THREADS, L::bytes(p.stages, p.ksub, p.nstg), s>>>(tmA, tmB, tmOut, tmRes, p);
   return cudaGetLastError();
 }
 
-// Operand-ring depth / staging slots for a layer: everything that fits in 227 KB, biased by the K extent.
-void igemm2_pick_smem(int bn, int num_kblocks, bool has_res, int* stages, int* nstg) {
+// Per-layer shared-memory split: K sub-blocks per stage (amortises the per-stage handshake over >= ~512 MMA cycles),
+// operand-ring depth, staging slots.  Long-K (tensor-bound) layers get a deep operand ring and a 2-slot staging ring;
+// short-K (bandwidth-bound) layers a shallow operand ring and a deep staging ring for residual prefetch.
+void igemm2_pick_smem(int bn, int num_kblocks, bool has_res, int* stages, int* ksub, int* nstg) {
   const int stage_bytes = A_STAGE_BYTES + (bn / 2) * BLOCK_K * 2;
   const int sub_bytes = BLOCK_M * 64 * 2;
   const int fixed = (2 * 8 + 4 + 2 * 8) * 8 + 16 + 1024;
-  // >= PENDING + 2 slots, so that (without a residual wait) the barrier before the NEXT store orders every epilogue
-  // thread's writes into a slot after thread 0 has seen that slot's previous store finish reading
-  int ns = num_kblocks >= 8 ? 3 : (has_res ? 6 : 4);        // long-K: the epilogue is hidden anyway
-  int st = (232448 - fixed - ns * sub_bytes) / stage_bytes;
-  st = std::min(st, 8);
-  if (num_kblocks < 8) st = std::min(st, 4);
-  ns = std::max(3, std::min(8, (232448 - fixed - st * stage_bytes) / sub_bytes));
+  const int budget = 232448 - fixed;
+  int ks = bn >= 256 ? 2 : 4;                       // MMA cycles per 64-K sub-block: 512 (bn 256), 256, 128
+  ks = std::max(1, std::min(ks, num_kblocks));
+  int ns = num_kblocks >= 8 ? 2 : (has_res ? 6 : 4);
+  int st = std::min(8, (budget - ns * sub_bytes) / (ks * stage_bytes));
+  while (st < 2 && ks > 1) {
+    ks /= 2;
+    st = std::min(8, (budget - ns * sub_bytes) / (ks * stage_bytes));
+  }
+  if (num_kblocks < 8) st = std::min(st, std::max(2, 4 / ks + 1));
+  ns = std::max(2, std::min(8, (budget - st * ks * stage_bytes) / sub_bytes));
   if (const char* e = getenv("PCV_IGEMM2_STAGES")) st = atoi(e);
+  if (const char* e = getenv("PCV_IGEMM2_KSUB")) ks = atoi(e);
   if (const char* e = getenv("PCV_IGEMM2_NSTG")) ns = atoi(e);
   *stages = st;
+  *ksub = ks;
   *nstg = ns;
 }
 

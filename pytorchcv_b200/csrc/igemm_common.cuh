@@ -28,7 +28,7 @@ struct IgemmParams {
   int out_mode;               // 0: TMA bf16 store; 1: direct bf16; 2: direct fp32
   int grouped;                // 1: A channel window = n_tile*BLOCK_N (block-diagonal weights)
   int dbg;                    // PCV_IGEMM_DBG: bit0 skip operand TMA, bit1 skip MMA issue (throughput experiments)
-  int stages, nstg;           // CTA-pair kernel: operand ring depth / staging slots (smem split chosen per layer)
+  int stages, ksub, nstg;     // CTA-pair kernel: ring depth / 64-K sub-blocks per stage / staging slots (per layer)
 };
 
 // Rare activations (sigmoid / swish / h-swish / h-sigmoid): kept out of line so the hot epilogue stays compact —
@@ -50,6 +50,6 @@ static __device__ __noinline__ float apply_act(float v, int act) {
 cudaError_t launch_igemm2(int bn, int grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                           const CUtensorMap& tmRes, const IgemmParams& p, cudaStream_t s);
 
-void igemm2_pick_smem(int bn, int num_kblocks, bool has_res, int* stages, int* nstg);
+void igemm2_pick_smem(int bn, int num_kblocks, bool has_res, int* stages, int* ksub, int* nstg);
 
 }  // namespace pcv
