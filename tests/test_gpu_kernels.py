@@ -136,5 +136,5 @@ def test_plan_records_and_replays():
         s.synchronize()
         assert torch.equal(out, eager)
     name = _lib.load().pcv_plan_op_name(plan, 0).decode()
-    assert name.startswith("conv_tc 3x3")
+    assert name.startswith("conv_tc") and " 3x3 " in name
     _lib.call("pcv_plan_destroy", plan)
