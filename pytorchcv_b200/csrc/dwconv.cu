@@ -253,6 +253,27 @@ struct DwOp : Op {
 int dw_make(const pcv_conv_desc& d, int dtype, const void* x, const void* w, const float* bias, const void* res,
             void* y, Op** out) {
   PCV_REQUIRE(d.kh == d.kw, "depthwise conv needs a square kernel");
+  char nm[128];
+  const double e = esize(dtype);
+  const int Ho_ = conv_out(d.H, d.kh, d.stride, d.pad, d.dil), Wo_ = conv_out(d.W, d.kw, d.stride, d.pad, d.dil);
+  const double M = static_cast<double>(d.N) * Ho_ * Wo_;
+  const double flops = 2.0 * M * d.Cout * d.kh * d.kw;
+  const double bytes = e * d.N * d.Cin * d.H * d.W + e * M * d.Cout * (res ? 2.0 : 1.0) + 4.0 * d.Cout * d.kh * d.kw + 4.0 * d.Cout;
+  if (dtype == PCV_BF16 && d.dil == 1) {
+    // TMA halo-staged kernel (window_tma.cu) for the 3x3 stride-1/2 layers of the MobileNet family
+    Op* wop = nullptr;
+    const int rc = win_make(0, d.N, d.H, d.W, d.Cout, d.kh, d.stride, d.pad, d.act, x, pitch_or(d.in_pitch, d.Cin),
+                            reinterpret_cast<const float*>(w), bias, res, pitch_or(d.res_pitch, d.Cout), y,
+                            pitch_or(d.out_pitch, d.Cout), &wop);
+    if (rc == PCV_OK) {
+      snprintf(nm, sizeof nm, "dwconv_tma_bf16 %dx%d s%d d%d C=%d @%dx%d%s", d.kh, d.kw, d.stride, d.dil, d.Cout, d.H,
+               d.W, res ? " +res" : "");
+      wop->name = nm; wop->flops = flops; wop->bytes = bytes;
+      *out = wop;
+      return PCV_OK;
+    }
+    if (rc != PCV_ERR_UNSUPPORTED) return rc;
+  }
   auto op = std::make_unique<DwOp>();
   DwParams& p = op->p;
   p.N = d.N; p.H = d.H; p.W = d.W; p.C = d.Cout;
@@ -268,14 +289,11 @@ int dw_make(const pcv_conv_desc& d, int dtype, const void* x, const void* w, con
   p.act = d.act;
   p.strips = 0;
   op->dtype = dtype; op->x = x; op->w = reinterpret_cast<const float*>(w); op->bias = bias; op->res = res; op->y = y;
-  char nm[128];
   snprintf(nm, sizeof nm, "dwconv_%s %dx%d s%d d%d C=%d @%dx%d%s", dtype == PCV_F32 ? "f32" : "bf16", d.kh, d.kw,
            d.stride, d.dil, d.Cout, d.H, d.W, res ? " +res" : "");
   op->name = nm;
-  const double e = esize(dtype);
-  const double M = static_cast<double>(d.N) * p.Ho * p.Wo;
-  op->flops = 2.0 * M * d.Cout * d.kh * d.kw;
-  op->bytes = e * d.N * d.Cin * d.H * d.W + e * M * d.Cout * (res ? 2.0 : 1.0) + 4.0 * d.Cout * d.kh * d.kw + 4.0 * d.Cout;
+  op->flops = flops;
+  op->bytes = bytes;
   *out = op.release();
   return PCV_OK;
 }

@@ -54,8 +54,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Spin on a phase parity.  try_wait suspends in hardware, so this is not a hot poll.
+// A wait that outlives ~2 s of SM clocks is a protocol bug (lost TMA, wrong tx count): trap so the launch fails with
+// an error instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
 

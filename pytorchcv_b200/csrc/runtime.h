@@ -97,6 +97,11 @@ int dw_pack(const pcv_conv_desc& d, int dtype, const float* w, const float* conv
 int dw_make(const pcv_conv_desc& d, int dtype, const void* x, const void* w, const float* bias, const void* res,
             void* y, Op** out);
 
+// window_tma.cu : TMA halo-staged 3x3 window ops, bf16 (op_kind 0 = depthwise conv, 1 = max pool).  Returns
+// PCV_ERR_UNSUPPORTED (without touching the error message) for shapes the caller must serve with its generic kernel.
+int win_make(int op_kind, int N, int H, int W, int C, int k, int stride, int pad, int act, const void* x, int in_pitch,
+             const float* w, const float* bias, const void* res, int res_pitch, void* y, int out_pitch, Op** out);
+
 enum ConvRoute { ROUTE_IGEMM = 0, ROUTE_DW = 1, ROUTE_SIMT = 2 };
 int conv_route(const pcv_conv_desc& d, int dtype, std::string* why);
 

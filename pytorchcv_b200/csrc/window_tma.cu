@@ -1,0 +1,352 @@
+// Bandwidth-bound 3x3 window ops on NHWC bf16 with TMA halo staging: depthwise convolution (+ folded BN bias,
+// clamp activation, optional residual) and max pooling.
+//
+// Reference: dwconv3x3_block (pytorchcv/models/common/conv.py:476-508) inside LinearBottleneck
+// (models/mobilenetv2.py:52-56) / DwsConvBlock (conv.py:546-608); nn.MaxPool2d(3, 2, 1) of ResInitBlock
+// (models/resnet.py:255-258) and SEInitBlock (models/senet.py:154-157).
+//
+// Both ops move ~(1 + 1/S^2) tensors through HBM for a handful of FLOPs per byte, so the kernel is organised around
+// the memory system, not the math:
+//   * persistent CTAs; each tile = TH x TW output pixels x CB channels.  One elected thread fetches the tile's input
+//     halo box ((TH-1)*S+KS rows x (TW-1)*S+KS columns x CB channels) with ONE 4-D TMA load into a ring of smem
+//     stages (mbarrier complete_tx); image borders are zero-filled by the TMA unit, so the hot loop has no bounds
+//     checks for the convolution and only predicate masks for the max.
+//   * a thread owns 4 consecutive channels (8 bytes) of one output column and walks down the tile's rows: every
+//     input row is read from smem once per thread (KS 8-byte LDS, conflict-free: consecutive lanes read consecutive
+//     addresses) and contributes to the ceil(KS/S) output rows that are live in registers; weights stay in registers
+//     as fp32 pairs and the multiply-accumulate is the packed fma.rn.f32x2 (two channels per instruction).
+//   * results leave with coalesced 8-byte-per-lane global stores (CB*2 contiguous bytes per pixel).
+#include <algorithm>
+#include <cmath>
+
+#include "ptx.cuh"
+#include "runtime.h"
+
+namespace pcv {
+
+struct WinParams {
+  int N, H, W, C, Ho, Wo;
+  int pad;
+  int out_pitch, res_pitch;
+  int CB, TW, IW;
+  int tiles_x, tiles_y, cblocks;
+  long long num_tiles;
+  int items;          // active threads per tile: TW * CB / 4
+  int stages, stage_bytes, tx_bytes;   // smem stride of a stage (128 B multiple) / exact bytes of one TMA box
+  float act_lo, act_hi;
+};
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// d = a * b + d on two packed fp32 lanes (Blackwell FFMA2); each lane rounds exactly like fmaf.
+__device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
+  uint64_t dd = (static_cast<uint64_t>(__float_as_uint(d.y)) << 32) | __float_as_uint(d.x);
+  const uint64_t aa = (static_cast<uint64_t>(__float_as_uint(a.y)) << 32) | __float_as_uint(a.x);
+  const uint64_t bb = (static_cast<uint64_t>(__float_as_uint(b.y)) << 32) | __float_as_uint(b.x);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+  d.x = __uint_as_float(static_cast<uint32_t>(dd));
+  d.y = __uint_as_float(static_cast<uint32_t>(dd >> 32));
+}
+
+__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+struct TileCoord {
+  int n, ho0, wo0, c0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const WinParams& p, long long t, int TH) {
+  TileCoord tc;
+  const int cb = static_cast<int>(t % p.cblocks); t /= p.cblocks;
+  const int tx = static_cast<int>(t % p.tiles_x); t /= p.tiles_x;
+  const int ty = static_cast<int>(t % p.tiles_y);
+  tc.n = static_cast<int>(t / p.tiles_y);
+  tc.ho0 = ty * TH;
+  tc.wo0 = tx * p.TW;
+  tc.c0 = cb * p.CB;
+  return tc;
+}
+
+template <int OP, int KS, int S, int TH>   // OP 0: depthwise conv, 1: max pool
+__global__ void __launch_bounds__(256, 2)
+win_kernel(const __grid_constant__ CUtensorMap tmIn, const WinParams p, const float* __restrict__ w,
+           const float* __restrict__ bias, const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y) {
+  constexpr int IH = (TH - 1) * S + KS;
+  constexpr int NACC = (KS + S - 1) / S;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
+  const int tid = threadIdx.x;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmIn);
+    for (int i = 0; i < p.stages; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    long long t = blockIdx.x;
+    for (int i = 0; i < p.stages && t < p.num_tiles; ++i, t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t, TH);
+      mbar_arrive_expect_tx(&full[i], p.tx_bytes);
+      tma_load_4d(&tmIn, &full[i], smem + i * p.stage_bytes, tc.c0, tc.wo0 * S - p.pad, tc.ho0 * S - p.pad, tc.n);
+    }
+  }
+
+  const int nv = p.CB >> 2;
+  const bool active = tid < p.items;
+  const int col = active ? tid / nv : 0;
+  const int v = active ? tid - col * nv : 0;
+  const int row_bytes = p.IW * p.CB * 2;
+  const int px_bytes = p.CB * 2;
+  const uint32_t thread_off = (col * S * p.CB + v * 4) * 2;
+
+  int stage = 0;
+  uint32_t phase = 0;
+  for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    const TileCoord tc = decode_tile(p, t, TH);
+    const int c = tc.c0 + v * 4;
+    float2 wr[OP == 0 ? KS * KS : 1][2];
+    float2 b2[2];
+    if (OP == 0) {
+#pragma unroll
+      for (int k = 0; k < KS * KS; ++k) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(k) * p.C + c));
+        wr[k][0] = make_float2(q.x, q.y);
+        wr[k][1] = make_float2(q.z, q.w);
+      }
+      const float4 q = __ldg(reinterpret_cast<const float4*>(bias + c));
+      b2[0] = make_float2(q.x, q.y);
+      b2[1] = make_float2(q.z, q.w);
+    }
+    const int wo = tc.wo0 + col;
+    const bool col_ok = active && wo < p.Wo;
+    // max pool: which taps of this thread's window fall inside the image
+    bool fs_ok[KS];
+#pragma unroll
+    for (int fs = 0; fs < KS; ++fs) {
+      const int wi = wo * S - p.pad + fs;
+      fs_ok[fs] = wi >= 0 && wi < p.W;
+    }
+    const int hi0 = tc.ho0 * S - p.pad;
+
+    mbar_wait(&full[stage], phase);
+    const uint8_t* sbase = smem + stage * p.stage_bytes + thread_off;
+
+    float2 acc[NACC][2];
+    uint2 mx[NACC];
+#pragma unroll
+    for (int ir = 0; ir < IH; ++ir) {
+      uint2 raw[KS];
+#pragma unroll
+      for (int fs = 0; fs < KS; ++fs) raw[fs] = *reinterpret_cast<const uint2*>(sbase + ir * row_bytes + fs * px_bytes);
+      float2 xv[KS][2];
+      if (OP == 0) {
+#pragma unroll
+        for (int fs = 0; fs < KS; ++fs) {
+          xv[fs][0] = make_float2(bf16lo(raw[fs].x), bf16hi(raw[fs].x));
+          xv[fs][1] = make_float2(bf16lo(raw[fs].y), bf16hi(raw[fs].y));
+        }
+      }
+      const bool row_ok = (hi0 + ir) >= 0 && (hi0 + ir) < p.H;
+#pragma unroll
+      for (int fr = 0; fr < KS; ++fr) {
+        if ((ir - fr) < 0 || (ir - fr) % S != 0 || (ir - fr) / S >= TH) continue;   // compile-time after unrolling
+        const int ho = (ir - fr) / S;
+        const int a = ho % NACC;
+        if (OP == 0) {
+          if (fr == 0) {
+            acc[a][0] = b2[0];
+            acc[a][1] = b2[1];
+          }
+#pragma unroll
+          for (int fs = 0; fs < KS; ++fs) {
+            ffma2(acc[a][0], xv[fs][0], wr[fr * KS + fs][0]);
+            ffma2(acc[a][1], xv[fs][1], wr[fr * KS + fs][1]);
+          }
+        } else {
+          if (fr == 0) mx[a] = make_uint2(0xFF80FF80u, 0xFF80FF80u);   // -inf, -inf
+          if (row_ok) {
+#pragma unroll
+            for (int fs = 0; fs < KS; ++fs) {
+              if (fs_ok[fs]) {
+                mx[a].x = hmax2_u32(mx[a].x, raw[fs].x);
+                mx[a].y = hmax2_u32(mx[a].y, raw[fs].y);
+              }
+            }
+          }
+        }
+        if (fr == KS - 1) {
+          const int hog = tc.ho0 + ho;
+          if (col_ok && hog < p.Ho) {
+            const size_t pix = (static_cast<size_t>(tc.n) * p.Ho + hog) * p.Wo + wo;
+            uint2 o;
+            if (OP == 0) {
+              float2 r0 = acc[a][0], r1 = acc[a][1];
+              if (res) {
+                const uint2 rr = __ldg(reinterpret_cast<const uint2*>(res + pix * p.res_pitch + c));
+                r0.x += bf16lo(rr.x); r0.y += bf16hi(rr.x); r1.x += bf16lo(rr.y); r1.y += bf16hi(rr.y);
+              }
+              r0.x = fminf(fmaxf(r0.x, p.act_lo), p.act_hi); r0.y = fminf(fmaxf(r0.y, p.act_lo), p.act_hi);
+              r1.x = fminf(fmaxf(r1.x, p.act_lo), p.act_hi); r1.y = fminf(fmaxf(r1.y, p.act_lo), p.act_hi);
+              o.x = pack_bf16x2(r0.x, r0.y);
+              o.y = pack_bf16x2(r1.x, r1.y);
+            } else {
+              o = mx[a];
+            }
+            *reinterpret_cast<uint2*>(y + pix * p.out_pitch + c) = o;
+          }
+        }
+      }
+    }
+
+    __syncthreads();   // every thread is done reading this stage
+    if (tid == 0) {
+      const long long tn = t + static_cast<long long>(p.stages) * gridDim.x;
+      if (tn < p.num_tiles) {
+        const TileCoord nc = decode_tile(p, tn, TH);
+        mbar_arrive_expect_tx(&full[stage], p.tx_bytes);
+        tma_load_4d(&tmIn, &full[stage], smem + stage * p.stage_bytes, nc.c0, nc.wo0 * S - p.pad, nc.ho0 * S - p.pad,
+                    nc.n);
+      }
+    }
+    if (++stage == p.stages) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side: tile geometry, tensor map, launch
+// ---------------------------------------------------------------------------------------------------------------
+struct WinCfg {
+  int TH, threads, ctas_per_sm, smem_bytes;
+};
+
+static bool pick_cfg(int C, int Ho, int Wo, int KS, int S, WinParams* p, WinCfg* cfg) {
+  double best = -1.0;
+  for (int CB = 8; CB <= std::min(C, 256); CB += 8) {
+    if (C % CB != 0) continue;
+    const int nv = CB / 4;
+    for (int TW = 1; TW <= Wo && TW * nv <= 256; ++TW) {
+      const int IW = (TW - 1) * S + KS;
+      if (IW > 256) break;
+      for (int TH = 7; TH <= 8; ++TH) {
+        const int IH = (TH - 1) * S + KS;
+        const int stage = (IH * IW * CB * 2 + 127) & ~127;
+        if (stage > 56 * 1024) continue;
+        const int items = TW * nv, threads = round_up(items, 32);
+        const double e_w = static_cast<double>(Wo) / (ceil_div(Wo, TW) * TW);
+        const double e_h = static_cast<double>(Ho) / (ceil_div(Ho, TH) * TH);
+        const double e_t = static_cast<double>(items) / threads;
+        const double halo = static_cast<double>(TH * S * TW * S) / (IH * IW);
+        const double wide = std::min(1.0, CB * 2 / 64.0);          // >= 64 contiguous bytes per pixel and DRAM burst
+        const double big = std::min(1.0, items / 128.0);            // enough threads to cover latency
+        const double score = e_w * e_h * e_t * std::sqrt(std::min(1.0, halo)) * wide * big + 1e-6 * stage;
+        if (score > best) {
+          best = score;
+          p->CB = CB; p->TW = TW; p->IW = IW; p->items = items; p->stage_bytes = stage; p->tx_bytes = IH * IW * CB * 2;
+          cfg->TH = TH; cfg->threads = threads;
+        }
+      }
+    }
+  }
+  if (best < 0) return false;
+  const int budget = 100 * 1024;   // per CTA; two CTAs per SM
+  p->stages = std::max(2, std::min(4, budget / p->stage_bytes));
+  cfg->smem_bytes = p->stages * p->stage_bytes + 8 * 8 + 128;
+  cfg->ctas_per_sm = std::max(1, std::min(2, (220 * 1024) / cfg->smem_bytes));
+  p->tiles_x = ceil_div(Wo, p->TW);
+  p->tiles_y = ceil_div(Ho, cfg->TH);
+  p->cblocks = C / p->CB;
+  return true;
+}
+
+static int make_win_map(CUtensorMap* tm, const void* x, int N, int H, int W, int C, int in_pitch, int CB, int IW,
+                        int IH) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)W * in_pitch * 2, (cuuint64_t)H * W * in_pitch * 2};
+  cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)IW, (cuuint32_t)IH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled (window op) failed (%d): C=%d W=%d H=%d N=%d box=%dx%dx%d", (int)r, C,
+                W, H, N, CB, IW, IH);
+  return PCV_OK;
+}
+
+struct WinOp : Op {
+  CUtensorMap tm;
+  WinParams p;
+  WinCfg cfg;
+  int op_kind, S;
+  const float *w, *bias;
+  const __nv_bfloat16* res;
+  __nv_bfloat16* y;
+
+  template <int OP, int S_, int TH>
+  cudaError_t go(cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(win_kernel<OP, 3, S_, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    const long long cap = static_cast<long long>(sm_count()) * cfg.ctas_per_sm;
+    const int grid = static_cast<int>(std::min<long long>(p.num_tiles, cap));
+    win_kernel<OP, 3, S_, TH><<<grid, cfg.threads, cfg.smem_bytes, s>>>(tm, p, w, bias, res, y);
+    return cudaGetLastError();
+  }
+  template <int OP>
+  cudaError_t go_op(cudaStream_t s) {
+    if (S == 1) return cfg.TH == 7 ? go<OP, 1, 7>(s) : go<OP, 1, 8>(s);
+    return cfg.TH == 7 ? go<OP, 2, 7>(s) : go<OP, 2, 8>(s);
+  }
+  cudaError_t launch(cudaStream_t s) override {
+    g_launches++;
+    return op_kind == 0 ? go_op<0>(s) : go_op<1>(s);
+  }
+};
+
+// Returns PCV_OK and sets *out, or PCV_ERR_UNSUPPORTED (no message) when the shape is outside this kernel's domain
+// and the caller should use its generic kernel.
+int win_make(int op_kind, int N, int H, int W, int C, int k, int stride, int pad, int act, const void* x, int in_pitch,
+             const float* w, const float* bias, const void* res, int res_pitch, void* y, int out_pitch, Op** out) {
+  if (k != 3 || (stride != 1 && stride != 2) || pad > 1 || C % 8 != 0 || in_pitch % 8 != 0 || out_pitch % 4 != 0 ||
+      (res && res_pitch % 4 != 0) || act > PCV_ACT_RELU6 || reinterpret_cast<uintptr_t>(x) % 16 != 0 ||
+      reinterpret_cast<uintptr_t>(y) % 8 != 0 || reinterpret_cast<uintptr_t>(res) % 8 != 0)
+    return PCV_ERR_UNSUPPORTED;
+  if (getenv("PCV_WIN_TMA") && getenv("PCV_WIN_TMA")[0] == '0') return PCV_ERR_UNSUPPORTED;
+  auto op = std::make_unique<WinOp>();
+  WinParams& p = op->p;
+  p.N = N; p.H = H; p.W = W; p.C = C;
+  p.Ho = (H + 2 * pad - k) / stride + 1;
+  p.Wo = (W + 2 * pad - k) / stride + 1;
+  if (p.Ho <= 0 || p.Wo <= 0) return PCV_ERR_UNSUPPORTED;
+  p.pad = pad; p.out_pitch = out_pitch; p.res_pitch = res_pitch;
+  p.act_lo = (act == PCV_ACT_RELU || act == PCV_ACT_RELU6) ? 0.f : -INFINITY;
+  p.act_hi = act == PCV_ACT_RELU6 ? 6.f : INFINITY;
+  if (!pick_cfg(C, p.Ho, p.Wo, k, stride, &p, &op->cfg)) return PCV_ERR_UNSUPPORTED;
+  p.num_tiles = static_cast<long long>(N) * p.tiles_y * p.tiles_x * p.cblocks;
+  const int IH = (op->cfg.TH - 1) * stride + k;
+  if (int rc = make_win_map(&op->tm, x, N, H, W, C, in_pitch, p.CB, p.IW, IH)) return rc;
+  op->op_kind = op_kind; op->S = stride; op->w = w; op->bias = bias;
+  op->res = reinterpret_cast<const __nv_bfloat16*>(res);
+  op->y = reinterpret_cast<__nv_bfloat16*>(y);
+  *out = op.release();
+  return PCV_OK;
+}
+
+}  // namespace pcv

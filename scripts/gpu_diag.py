@@ -51,6 +51,11 @@ CASES = [
     ("dw3x3_s2_bf16",             2, 28, 28,  96,  96, 3, 2, 1, 1, 96, 2, 0, 0, "bf16"),
     ("dw5x5_s1_bf16",             2, 14, 14,  96,  96, 5, 1, 2, 1, 96, 2, 0, 0, "bf16"),
     ("dw3x3_s1_f32",              2, 28, 28,  32,  32, 3, 1, 1, 1, 32, 2, 1, 0, "fp32"),
+    ("dw3x3_s1_c32_112",          2, 112, 112, 32,  32, 3, 1, 1, 1, 32, 2, 0, 0, "bf16"),
+    ("dw3x3_s1_c960_7",           3,  7,  7, 960, 960, 3, 1, 1, 1, 960, 2, 0, 0, "bf16"),
+    ("dw3x3_s2_c576_14",          2, 14, 14, 576, 576, 3, 2, 1, 1, 576, 2, 0, 0, "bf16"),
+    ("dw3x3_s1_ragged_res",       2, 20, 18,  48,  48, 3, 1, 1, 1, 48, 1, 1, 0, "bf16"),
+    ("dw3x3_s2_ragged_none",      3, 19, 23,  40,  40, 3, 2, 1, 1, 40, 0, 0, 0, "bf16"),
     ("dw3x3_d2_generic",          2, 28, 28,  32,  32, 3, 1, 2, 2, 32, 1, 0, 0, "bf16"),
 ]
 
