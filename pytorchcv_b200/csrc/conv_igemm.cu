@@ -96,10 +96,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (tmem_base != 0) __trap();   // one CTA per SM => the allocation starts at column 0; the MMA warp relies on it
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    // whole warp with warp-uniform values; TMA / mbarrier instructions under elect.sync so ptxas keeps addresses in
+    // uniform registers (inside `if (lane == 0)` every UTMALDG / UTCHMMA got a ~13-instruction uniformisation loop)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -116,18 +119,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         int tap = 0, cb = 0, fr = 0, fs = 0;
         for (int kb = 0; kb < p.num_kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          if (p.dbg & 1) {
-            mbar_arrive(&full[stage]);
-          } else {
-          mbar_arrive_expect_tx(&full[stage], A_STAGE_BYTES + L::B_STAGE_BYTES);
-          uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
-          if (p.a_mode == 1) {
-            tma_load_im2col_4d(&tmA, &full[stage], a_dst, c_base + cb * BLOCK_K, w0, h0, img,
-                               static_cast<uint16_t>(fs * p.dil), static_cast<uint16_t>(fr * p.dil));
-          } else {
-            tma_load_2d(&tmA, &full[stage], a_dst, c_base + cb * BLOCK_K, m0);
-          }
-          tma_load_2d(&tmB, &full[stage], sB + stage * L::B_STAGE_BYTES, kb * BLOCK_K, n_tile * BN);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full[stage], A_STAGE_BYTES + L::B_STAGE_BYTES);
+            uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
+            if (p.a_mode == 1) {
+              tma_load_im2col_4d(&tmA, &full[stage], a_dst, c_base + cb * BLOCK_K, w0, h0, img,
+                                 static_cast<uint16_t>(fs * p.dil), static_cast<uint16_t>(fr * p.dil));
+            } else {
+              tma_load_2d(&tmA, &full[stage], a_dst, c_base + cb * BLOCK_K, m0);
+            }
+            tma_load_2d(&tmB, &full[stage], sB + stage * L::B_STAGE_BYTES, kb * BLOCK_K, n_tile * BN);
           }
           if (++cb == p.cblocks) {
             cb = 0;
@@ -146,7 +147,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
+    {   // whole warp; tcgen05 instructions under elect.sync
       constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN);
       const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA)), b_lo0 = smem_desc_lo(smem_u32(sB));
       int stage = 0;
@@ -157,40 +158,42 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * BN;
+        const uint32_t d_tmem = buf * BN;   // TMEM base is 0 (one CTA per SM, checked after the allocation)
         for (int kb = 0; kb < p.num_kblocks; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + stage * (A_STAGE_BYTES >> 4);
           const uint32_t b_lo = b_lo0 + stage * (L::B_STAGE_BYTES >> 4);
-          if (!(p.dbg & 2)) {
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k)
               umma_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty[stage]);  // frees this smem stage once the MMAs above have read it
           }
-          umma_commit(&empty[stage]);  // frees this smem stage once the MMAs above have read it
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[buf]);  // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(&tmem_full[buf]);  // accumulator complete -> epilogue
       }
     }
   } else if (warp == 3) {
     // ===================================== residual prefetcher =====================================
-    if (lane == 0 && p.has_res && OUT_MODE == 0) {
+    if (p.has_res && OUT_MODE == 0) {   // whole warp, TMA under elect.sync
       int sbuf = 0;
       uint32_t sphase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m_tile = t / p.tiles_n;
         const int n_tile = t - m_tile * p.tiles_n;
         mbar_wait(&stg_empty[sbuf], sphase);
-        mbar_arrive_expect_tx(&res_full[sbuf], L::STG_BYTES);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&res_full[sbuf], L::STG_BYTES);
 #pragma unroll
-        for (int sub = 0; sub < L::NSUB; ++sub)
-          tma_load_2d(&tmRes, &res_full[sbuf], sStg + sbuf * L::STG_BYTES + sub * L::SUB_BYTES,
-                      n_tile * BN + sub * L::SUB_COLS, m_tile * BLOCK_M);
+          for (int sub = 0; sub < L::NSUB; ++sub)
+            tma_load_2d(&tmRes, &res_full[sbuf], sStg + sbuf * L::STG_BYTES + sub * L::SUB_BYTES,
+                        n_tile * BN + sub * L::SUB_COLS, m_tile * BLOCK_M);
+        }
         if (++sbuf == L::NSTG) {
           sbuf = 0;
           sphase ^= 1;
@@ -317,7 +320,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (OUT_MODE == 0) {
         fence_proxy_async_smem();           // st.shared above -> visible to the TMA (async proxy)
         named_bar_sync(1, EPI_THREADS);
-        if (epi_tid == 0) {
+        if (warp == 4 && elect_one()) {   // elect.sync is deterministic: one lane owns every bulk group
 #pragma unroll
           for (int sub = 0; sub < L::NSUB; ++sub)
             tma_store_2d(&tmOut, stg + sub * L::SUB_BYTES, n0 + sub * L::SUB_COLS, m0);
@@ -334,7 +337,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         sphase ^= 1;
       }
     }
-    if (OUT_MODE == 0 && epi_tid == 0) tma_store_wait_all<0>();
+    if (OUT_MODE == 0 && warp == 4 && elect_one()) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -525,6 +528,10 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
                Op** out) {
   std::string why;
   if (!igemm_supported(d, &why)) return fail(PCV_ERR_UNSUPPORTED, "tcgen05 conv: %s", why.c_str());
+  {
+    const int rc3 = igemm3_try_make(d, x, w, bias, res, y, out);   // 3x3 stride-1 layers with a smem halo tile
+    if (rc3 != PCV_ERR_UNSUPPORTED) return rc3;
+  }
   const int Ho = conv_out(d.H, d.kh, d.stride, d.pad, d.dil);
   const int Wo = conv_out(d.W, d.kw, d.stride, d.pad, d.dil);
   PCV_REQUIRE(Ho > 0 && Wo > 0, "conv output is empty (H=%d W=%d k=%d)", d.H, d.W, d.kh);

@@ -97,12 +97,16 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   cluster_sync_all();   // peer barriers initialised, both TMEM allocations done
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (tmem_base != 0) __trap();   // one CTA per SM => the allocation starts at column 0; the MMA warp relies on it
 
   if (warp == 0) {
     // ===================================== TMA producer (both CTAs) =====================================
     // One full/empty handshake per STAGE; a stage holds KSUB 64-channel sub-blocks (KSUB chosen per layer so that
     // a stage carries >= ~512 tensor-pipe cycles of work: the single-thread handshake costs ~400-600 cycles).
-    if (lane == 0) {
+    // whole warp, warp-uniform values; only the TMA / mbarrier instructions are predicated on elect.sync so that ptxas
+    // keeps addresses and coordinates in uniform registers (an `if (lane == 0)` region wraps every UTMALDG / UTCHMMA
+    // in a ~13-instruction ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = pair; t < num_tiles; t += npairs) {
@@ -125,17 +129,19 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
           // only the leader arrives; the peer's bytes may land first (tx-count goes negative, the phase cannot
           // complete before the leader's arrival), exactly the CUTLASS 2-SM pipeline protocol
-          if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * nsub * L::STAGE_BYTES);
+          if (rank == 0 && elect_one()) mbar_arrive_expect_tx(&full[stage], 2 * nsub * L::STAGE_BYTES);
           uint8_t* a_dst = sA + stage * KSUB * A_STAGE_BYTES;
           uint8_t* b_dst = sB + stage * KSUB * L::B_STAGE_BYTES;
           for (int j = 0; j < nsub; ++j) {
-            if (p.a_mode == 1) {
-              tma2_load_im2col_4d(&tmA, full_leader, a_dst, c_base + cb * BLOCK_K, w0, h0, img,
-                                  static_cast<uint16_t>(fs * p.dil), static_cast<uint16_t>(fr * p.dil));
-            } else {
-              tma2_load_2d(&tmA, full_leader, a_dst, c_base + cb * BLOCK_K, m0);
+            if (elect_one()) {
+              if (p.a_mode == 1) {
+                tma2_load_im2col_4d(&tmA, full_leader, a_dst, c_base + cb * BLOCK_K, w0, h0, img,
+                                    static_cast<uint16_t>(fs * p.dil), static_cast<uint16_t>(fr * p.dil));
+              } else {
+                tma2_load_2d(&tmA, full_leader, a_dst, c_base + cb * BLOCK_K, m0);
+              }
+              tma2_load_2d(&tmB, full_leader, b_dst, (kb + j) * BLOCK_K, b_row);
             }
-            tma2_load_2d(&tmB, full_leader, b_dst, (kb + j) * BLOCK_K, b_row);
             a_dst += A_STAGE_BYTES;
             b_dst += L::B_STAGE_BYTES;
             if (++cb == p.cblocks) {
@@ -155,7 +161,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer (leader CTA only) =====================================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {   // whole warp (see the producer's note); tcgen05 instructions under elect.sync
       constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BN);
       const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA)), b_lo0 = smem_desc_lo(smem_u32(sB));
       int stage = 0;
@@ -166,7 +172,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * BN;
+        const uint32_t d_tmem = buf * BN;   // TMEM base is 0 (one CTA per SM, checked after the allocation)
         uint32_t accum = 0;
         for (int kb = 0; kb < p.num_kblocks; kb += KSUB) {
           const int nsub = min(KSUB, p.num_kblocks - kb);
@@ -175,26 +181,26 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           uint32_t a_lo = a_lo0 + stage * KSUB * (A_STAGE_BYTES >> 4);
           uint32_t b_lo = b_lo0 + stage * KSUB * (L::B_STAGE_BYTES >> 4);
           for (int j = 0; j < nsub; ++j) {
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / 16; ++k) {
-              umma2_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, accum);
-              accum = 1;
+              for (int k = 0; k < BLOCK_K / 16; ++k) umma2_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, k ? 1u : accum);
             }
+            accum = 1;
             a_lo += A_STAGE_BYTES >> 4;
             b_lo += L::B_STAGE_BYTES >> 4;
           }
-          umma2_commit(&empty[stage], 0x3);
+          if (elect_one()) umma2_commit(&empty[stage], 0x3);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma2_commit(&tmem_full[buf], 0x3);
+        if (elect_one()) umma2_commit(&tmem_full[buf], 0x3);
       }
     }
   } else if (warp == 3) {
     // ===================================== residual prefetcher (both CTAs) =====================================
-    if (lane == 0 && p.has_res) {
+    if (p.has_res) {   // whole warp, TMA under elect.sync (see the producer's note)
       int slot = 0;
       uint32_t sphase = 0;
       for (int t = pair; t < num_tiles; t += npairs) {
@@ -203,8 +209,10 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const int m0 = (2 * pm + static_cast<int>(rank)) * BLOCK_M;
         for (int sub = 0; sub < L::NSUB; ++sub) {
           mbar_wait(&stg_empty[slot], sphase ^ 1);
-          mbar_arrive_expect_tx(&res_full[slot], L::SUB_BYTES);
-          tma_load_2d(&tmRes, &res_full[slot], sStg + slot * L::SUB_BYTES, n_tile * BN + sub * L::SUB_COLS, m0);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&res_full[slot], L::SUB_BYTES);
+            tma_load_2d(&tmRes, &res_full[slot], sStg + slot * L::SUB_BYTES, n_tile * BN + sub * L::SUB_COLS, m0);
+          }
           if (++slot == NSTG) {
             slot = 0;
             sphase ^= 1;
@@ -303,7 +311,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
         fence_proxy_async_smem();
         named_bar_sync(1, EPI_THREADS);
-        if (epi_tid == 0) {
+        if (warp == 4 && elect_one()) {   // elect.sync is deterministic: the same lane owns every bulk group
           tma_store_2d(&tmOut, stg, n0 + sub * L::SUB_COLS, m0);
           tma_store_commit();
           if (NSTG >= 3) {
@@ -323,7 +331,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
       }
     }
-    if (epi_tid == 0) tma_store_wait_all<0>();
+    if (warp == 4 && elect_one()) tma_store_wait_all<0>();
   }
 
   tc_fence_before();

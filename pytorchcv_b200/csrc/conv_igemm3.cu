@@ -1,0 +1,371 @@
+// 3x3 stride-1 pad-1 dense convolution with a shared-memory HALO tile: the input is staged ONCE per tile and the nine
+// filter taps are nine shifted views of the same shared-memory rows.
+//
+// Why (round-1 ncu + per-layer model, profiles/): with TMA-im2col every 128-pixel A tile is re-fetched once per tap,
+// so a 3x3 layer pulls 9x its input through the L2 -> SMEM fabric; all 3x3 layers of ResNet-50 sat at 9-10 TB/s of
+// smem fill (the measured ~6300 B/clk LTS cap), 2-4x above their tensor / HBM bounds.  Here the fill traffic is
+// (R+2)/R x the input, the weights never move, and the layer becomes tensor / HBM bound.
+//
+// Layout trick: a tile is R full output rows of one image.  Its input box - (R+2) rows x (W+2) pixels x 64 channels,
+// fetched by ONE 4-D tiled TMA load starting at (w = -1, h = h0-1) so the zero padding is materialised by the TMA
+// unit's out-of-bounds fill - lands in shared memory as a dense list of 128-byte pixel rows (SWIZZLE_128B), i.e.
+// exactly the canonical K-major operand layout with "row" = padded pixel index.  Output pixel q = r*(W+2) + c of the
+// tile needs, for tap (fr, fs), input row q + fr*(W+2) + fs: the tap is a constant row offset, so the A operand of
+// tap (fr, fs) and M-block j is the SAME buffer with the descriptor start address advanced by
+// (j*128 + fr*(W+2) + fs) * 128 bytes (the 128B swizzle is a function of the absolute smem address, which is what
+// makes the K-advance of +32 B work as well).  Columns c >= W of each row are computed and dropped (2/(W+2) waste).
+//
+// CTA pair (cta_group::2, one 256 x BN MMA per K=16 step): each CTA owns its own tile (128 A rows per M-block from
+// each CTA) and HALF of the output channels' weights, which stay RESIDENT in shared memory for the whole kernel
+// (9 * Cin/64 blocks of [BN/2 x 64]).  Roles per CTA: warp 0 producer (weights once, then one A box per 64-channel
+// block into a ring), warp 1 MMA issuer (leader CTA only), warp 2 TMEM allocator, warps 4-7 epilogue
+// (tcgen05.ld -> +bias -> clamp -> bf16 -> direct 64-byte-per-thread global stores; garbage columns masked).
+#include "igemm_common.cuh"
+
+namespace pcv {
+
+struct Igemm3Params {
+  const float* bias;
+  __nv_bfloat16* out;
+  int out_pitch;
+  int N, H, W, Cout;
+  int R, PW, NMB;            // output rows per tile, padded width W+2, 128-row M-blocks per tile
+  int cblocks;               // Cin / 64
+  int tiles_per_img, num_tiles;
+  int NA;                    // A ring depth
+  int a_buf_bytes;           // smem stride of one A buffer (multiple of 1024, includes the over-read slack)
+  int a_tx_bytes;            // bytes of one A box: (R+2) * PW * 128
+  int b_block_bytes;         // BN/2 * 128
+  float act_lo, act_hi;
+};
+
+__device__ __forceinline__ void tma2_load_4d(const CUtensorMap* m, uint32_t mbar_cluster_addr, void* dst, int c0,
+                                             int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+constexpr int I3_MAX_NA = 6;
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Igemm3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nb_blocks = 9 * p.cblocks;
+  uint8_t* sB = smem;                                         // resident weights: nb_blocks x [BN/2 x 128 B]
+  uint8_t* sA = sB + ((nb_blocks * p.b_block_bytes + 1023) & ~1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + p.NA * p.a_buf_bytes);
+  uint64_t* full = bars;                         // [NA]  leader's copy is live
+  uint64_t* empty = bars + I3_MAX_NA;            // [NA]  per CTA, multicast commit
+  uint64_t* b_full = bars + 2 * I3_MAX_NA;       // [1]   leader's copy
+  uint64_t* tmem_full = b_full + 1;              // [2]   per CTA, multicast commit
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]   leader's copy, 8 arrivals
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+  const int pair_tiles = (p.num_tiles + 1) >> 1;
+  const int acc_cols = p.NMB * BN;               // TMEM columns of one accumulator buffer
+  const uint32_t tmem_cols = 2 * acc_cols <= 256 ? 256u : 512u;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.NA; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(b_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc2(tmem_ptr, tmem_cols);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (tmem_base != 0) __trap();   // one CTA per SM (227 KB smem) => the allocation starts at column 0; the MMA warp relies on it
+
+  if (warp == 0) {
+    // ===================================== producer (both CTAs) =====================================
+    {   // whole warp; TMA / mbarrier instructions under elect.sync (uniform-register operands)
+      const uint32_t bfull_leader = mapa_u32(smem_u32(b_full), 0);
+      if (rank == 0 && elect_one()) mbar_arrive_expect_tx(b_full, 2 * nb_blocks * p.b_block_bytes);
+      for (int b = 0; b < nb_blocks; ++b)
+        if (elect_one())
+          tma2_load_2d(&tmB, bfull_leader, sB + b * p.b_block_bytes, b * BLOCK_K, static_cast<int>(rank) * (BN / 2));
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < pair_tiles; t += npairs) {
+        int tile = 2 * t + static_cast<int>(rank);
+        if (tile >= p.num_tiles) tile = p.num_tiles - 1;   // phantom tile of an odd tail: recompute the last one, stores masked
+        const int img = tile / p.tiles_per_img;
+        const int h0 = (tile - img * p.tiles_per_img) * p.R;
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          mbar_wait(&empty[slot], phase ^ 1);
+          const uint32_t full_leader = mapa_u32(smem_u32(&full[slot]), 0);
+          if (elect_one()) {
+            if (rank == 0) mbar_arrive_expect_tx(&full[slot], 2 * p.a_tx_bytes);
+            tma2_load_4d(&tmA, full_leader, sA + slot * p.a_buf_bytes, cb * BLOCK_K, -1, h0 - 1, img);
+          }
+          if (++slot == p.NA) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader CTA only) =====================================
+    // The WHOLE warp runs this loop with warp-uniform values and only the tcgen05 instructions are predicated on
+    // elect.sync: ptxas then keeps descriptors in uniform registers.  (Inside an `if (lane == 0)` region every
+    // UTCHMMA was wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY "waterfall" of ~13 dependent instructions, which
+    // capped the issue rate at one MMA per ~120 cycles whatever its N.)
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BN);
+      const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA)), b_lo0 = smem_desc_lo(smem_u32(sB));
+      const uint32_t b_step = p.b_block_bytes >> 4;
+      mbar_wait(b_full, 0);
+      tc_fence_after();
+      int slot = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = pair; t < pair_tiles; t += npairs, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = buf * acc_cols;     // TMEM base is 0: this CTA owns the SM's whole TMEM (checked above)
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          mbar_wait(&full[slot], phase);
+          tc_fence_after();
+          const uint32_t a_buf = a_lo0 + slot * (p.a_buf_bytes >> 4);
+          int tap = 0;
+          for (int fr = 0; fr < 3; ++fr) {
+            for (int fs = 0; fs < 3; ++fs, ++tap) {
+              const uint32_t b_lo = b_lo0 + (tap * p.cblocks + cb) * b_step;
+              const uint32_t a_tap = a_buf + (fr * p.PW + fs) * (128 >> 4);
+              const uint32_t acc = (cb | tap) != 0 ? 1u : 0u;
+              for (int mb = 0; mb < p.NMB; ++mb) {
+                const uint32_t a_lo = a_tap + mb * (BLOCK_M * 128 >> 4);
+                if (elect_one()) {
+#pragma unroll
+                  for (int k = 0; k < BLOCK_K / 16; ++k)
+                    umma2_bf16_lohi(d_tmem + mb * BN, a_lo + 2 * k, b_lo + 2 * k, idesc, (k != 0) ? 1u : acc);
+                }
+              }
+            }
+          }
+          if (elect_one()) umma2_commit(&empty[slot], 0x3);
+          if (++slot == p.NA) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+        if (elect_one()) umma2_commit(&tmem_full[buf], 0x3);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue (both CTAs) =====================================
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const float act_lo = p.act_lo, act_hi = p.act_hi;
+    const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+    const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
+    int it = 0;
+    for (int t = pair; t < pair_tiles; t += npairs, ++it) {
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int tile = 2 * t + static_cast<int>(rank);
+      const bool tile_ok = tile < p.num_tiles;
+      const int img = tile / p.tiles_per_img;
+      const int h0 = (tile - img * p.tiles_per_img) * p.R;
+
+      mbar_wait(&tmem_full[buf], acc_phase);
+      tc_fence_after();
+
+      for (int mb = 0; mb < p.NMB; ++mb) {
+        const int q = mb * BLOCK_M + row;
+        const int r = q / p.PW;
+        const int c = q - r * p.PW;
+        const bool ok = tile_ok && c < p.W && r < p.R && (h0 + r) < p.H;
+        __nv_bfloat16* dst = p.out + (static_cast<size_t>(img * p.H + h0 + r) * p.W + c) * p.out_pitch;
+#pragma unroll 1
+        for (int j = 0; j < BN / 32; ++j) {
+          uint32_t acc[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * acc_cols + mb * BN + j * 32, acc);
+          tmem_ld_wait();
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + j * 32);
+          uint32_t o[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(bias4 + i);
+            const float v0 = fminf(fmaxf(__uint_as_float(acc[4 * i + 0]) + b.x, act_lo), act_hi);
+            const float v1 = fminf(fmaxf(__uint_as_float(acc[4 * i + 1]) + b.y, act_lo), act_hi);
+            const float v2 = fminf(fmaxf(__uint_as_float(acc[4 * i + 2]) + b.z, act_lo), act_hi);
+            const float v3 = fminf(fmaxf(__uint_as_float(acc[4 * i + 3]) + b.w, act_lo), act_hi);
+            o[2 * i + 0] = pack_bf16x2(v0, v1);
+            o[2 * i + 1] = pack_bf16x2(v2, v3);
+          }
+          if (ok) {
+            uint4* d4 = reinterpret_cast<uint4*>(dst + j * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d4[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&tmem_empty[buf]);
+        else mbar_arrive_cluster(buf ? tmem_empty_leader1 : tmem_empty_leader0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+struct Igemm3Op : Op {
+  CUtensorMap tmA, tmB;
+  Igemm3Params p;
+  int bn, grid, smem_bytes;
+  cudaError_t launch(cudaStream_t s) override;
+};
+
+template <int BN>
+static cudaError_t launch_i3(const Igemm3Op& op, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  igemm3_kernel<BN><<<op.grid, NUM_THREADS, op.smem_bytes, s>>>(op.tmA, op.tmB, op.p);
+  return cudaGetLastError();
+}
+
+cudaError_t Igemm3Op::launch(cudaStream_t s) {
+  g_launches++;
+  return bn == 64 ? launch_i3<64>(*this, s) : launch_i3<128>(*this, s);
+}
+
+// Returns PCV_ERR_UNSUPPORTED (message untouched) when the layer is outside this kernel's domain.
+int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const float* bias, const void* res, void* y,
+                    Op** out) {
+  static const bool enabled = [] {
+    const char* e = getenv("PCV_IGEMM_HALO");
+    return !(e && e[0] == '0');
+  }();
+  const int in_pitch = pitch_or(d.in_pitch, d.Cin), out_pitch = pitch_or(d.out_pitch, d.Cout);
+  if (!enabled || res || d.kh != 3 || d.kw != 3 || d.stride != 1 || d.dil != 1 || d.pad != 1 || d.groups != 1 ||
+      d.flags != 0 || d.in_row_pitch != 0 || d.Cin % 64 != 0 || (d.Cout != 64 && d.Cout != 128) || in_pitch % 8 != 0 ||
+      out_pitch % 8 != 0 || d.W + 2 > 256 || d.W < 24 || d.act > PCV_ACT_RELU6 ||
+      reinterpret_cast<uintptr_t>(x) % 16 != 0 || reinterpret_cast<uintptr_t>(y) % 16 != 0 ||
+      reinterpret_cast<uintptr_t>(w) % 16 != 0)
+    return PCV_ERR_UNSUPPORTED;
+  const int BN = d.Cout, PW = d.W + 2, cblocks = d.Cin / 64;
+  const int b_block = BN / 2 * 128;
+  const int b_bytes = round_up(9 * cblocks * b_block, 1024);
+  const int budget = 232448 - 1024 - 256 - b_bytes;
+  if (budget <= 0) return PCV_ERR_UNSUPPORTED;
+  // rows per tile: maximise (useful MMA rows) x (wave efficiency) among the tiles that fit
+  const int pairs = sm_count() / 2;
+  double best = 0.0;
+  int bestR = 0, bestNA = 0, bestNMB = 0, best_buf = 0;
+  for (int R = 1; R <= std::min(d.H, 32); ++R) {
+    const int Q = R * PW, NMB = ceil_div(Q, BLOCK_M);
+    if (2 * NMB * BN > 512 || R + 2 > 256) continue;
+    const int buf = round_up((NMB * BLOCK_M + 2 * PW + 2) * 128, 1024);
+    const int NA = std::min(I3_MAX_NA, budget / buf);
+    if (NA < 2) continue;
+    const int tiles = d.N * ceil_div(d.H, R);
+    const int pair_tiles = (tiles + 1) / 2;
+    const double wave = static_cast<double>(pair_tiles) / (ceil_div(pair_tiles, pairs) * pairs);
+    const double rows = static_cast<double>(d.H) * d.W / (static_cast<double>(ceil_div(d.H, R)) * NMB * BLOCK_M);
+    const double halo = static_cast<double>(R) / (R + 2);
+    const double work = static_cast<double>(NMB) * cblocks * 36 * (BN / 2);   // tensor-pipe cycles per tile
+    const double score = wave * rows * (0.9 + 0.1 * halo) * work / (work + 500.0);  // ~500-cycle handshake per tile
+    if (score > best) {
+      best = score; bestR = R; bestNA = NA; bestNMB = NMB; best_buf = buf;
+    }
+  }
+  if (bestR == 0) return PCV_ERR_UNSUPPORTED;
+
+  auto op = std::make_unique<Igemm3Op>();
+  Igemm3Params& p = op->p;
+  p.bias = bias;
+  p.out = reinterpret_cast<__nv_bfloat16*>(y);
+  p.out_pitch = out_pitch;
+  p.N = d.N; p.H = d.H; p.W = d.W; p.Cout = d.Cout;
+  p.R = bestR; p.PW = PW; p.NMB = bestNMB; p.cblocks = cblocks;
+  p.tiles_per_img = ceil_div(d.H, bestR);
+  p.num_tiles = d.N * p.tiles_per_img;
+  p.NA = bestNA;
+  p.a_buf_bytes = best_buf;
+  p.a_tx_bytes = (bestR + 2) * PW * 128;
+  p.b_block_bytes = b_block;
+  p.act_lo = (d.act == PCV_ACT_RELU || d.act == PCV_ACT_RELU6) ? 0.f : -INFINITY;
+  p.act_hi = d.act == PCV_ACT_RELU6 ? 6.f : INFINITY;
+  op->bn = BN;
+  op->smem_bytes = 1024 + b_bytes + bestNA * best_buf + 256;
+  op->grid = 2 * std::min((p.num_tiles + 1) / 2, pairs);
+
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.N};
+    cuuint64_t strides[3] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)d.W * in_pitch * 2, (cuuint64_t)d.H * d.W * in_pitch * 2};
+    cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)PW, (cuuint32_t)(bestR + 2), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(&op->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled (halo A) failed (%d)", (int)r);
+  }
+  {
+    const uint64_t kpad = 9ull * cblocks * BLOCK_K;
+    cuuint64_t dims[2] = {kpad, (cuuint64_t)d.Cout};
+    cuuint64_t strides[1] = {kpad * 2};
+    cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)(BN / 2)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&op->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled (halo B) failed (%d)", (int)r);
+  }
+  char nm[160];
+  snprintf(nm, sizeof nm, "conv_tc3 3x3 s1 d1 g1 %d->%d @%dx%d bn=%d halo R=%d mb=%d na=%d", d.Cin, d.Cout, d.H, d.W, BN,
+           bestR, bestNMB, bestNA);
+  op->name = nm;
+  const double M = static_cast<double>(d.N) * d.H * d.W;
+  op->flops = 2.0 * M * d.Cout * d.Cin * 9;
+  op->bytes = 2.0 * d.N * d.Cin * d.H * d.W + 2.0 * M * d.Cout + 2.0 * d.Cout * d.Cin * 9 + 4.0 * d.Cout;
+  *out = op.release();
+  return PCV_OK;
+}
+
+}  // namespace pcv

@@ -50,6 +50,10 @@ static __device__ __noinline__ float apply_act(float v, int act) {
 cudaError_t launch_igemm2(int bn, int grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                           const CUtensorMap& tmRes, const IgemmParams& p, cudaStream_t s);
 
+// conv_igemm3.cu: 3x3 stride-1 halo kernel; PCV_ERR_UNSUPPORTED (no message) when the layer is outside its domain
+int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const float* bias, const void* res, void* y,
+                    Op** out);
+
 void igemm2_pick_smem(int bn, int num_kblocks, bool has_res, int* stages, int* ksub, int* nstg);
 
 }  // namespace pcv

@@ -107,37 +107,51 @@ struct MaxPoolOp : Op {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// global average pool: one CTA per (image, 64-channel slab); 8 channel vectors x 32 pixel lanes, smem tree reduce.
+// global average pool / SE squeeze: one CTA per (image, channel slab).  The slab width is chosen on the host so that
+// the grid has >= ~4 CTAs per SM; inside the CTA `cv` lanes own consecutive 8-channel vectors (16-byte coalesced
+// loads, slab*2 contiguous bytes per pixel) and 256/cv pixel lanes stride over the pixels with 4 loads in flight per
+// thread; fp32 accumulation, fixed-order smem tree reduce (deterministic).
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
-gap_kernel(int HW, int C, const T* __restrict__ x, int in_pitch, void* __restrict__ out, int out_f32) {
-  __shared__ float red[32][8][8 + 1];
+gap_kernel(int HW, int C, int slab, const T* __restrict__ x, int in_pitch, void* __restrict__ out, int out_f32) {
+  __shared__ float red[256 * 8];
   const int n = blockIdx.y;
-  const int c0 = blockIdx.x * 64;
-  const int cv = threadIdx.x & 7;
-  const int pl = threadIdx.x >> 3;  // pixel lane 0..31
-  const int c = c0 + cv * 8;
+  const int c0 = blockIdx.x * slab;
+  const int cv = slab >> 3;           // channel-vector lanes (power of two, <= 64)
+  const int PL = 256 / cv;            // pixel lanes
+  const int cvi = threadIdx.x & (cv - 1);
+  const int pl = threadIdx.x / cv;
+  const int c = c0 + cvi * 8;
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   if (c < C) {
     const T* base = x + static_cast<size_t>(n) * HW * in_pitch + c;
-    for (int p = pl; p < HW; p += 32) {
+    int p = pl;
+    for (; p + 3 * PL < HW; p += 4 * PL) {
+      float v0[8], v1[8], v2[8], v3[8];
+      V8<T>::load(base + static_cast<size_t>(p) * in_pitch, v0);
+      V8<T>::load(base + static_cast<size_t>(p + PL) * in_pitch, v1);
+      V8<T>::load(base + static_cast<size_t>(p + 2 * PL) * in_pitch, v2);
+      V8<T>::load(base + static_cast<size_t>(p + 3 * PL) * in_pitch, v3);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += (v0[e] + v1[e]) + (v2[e] + v3[e]);
+    }
+    for (; p < HW; p += PL) {
       float v[8];
       V8<T>::load(base + static_cast<size_t>(p) * in_pitch, v);
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] += v[e];
     }
   }
+  // red[pl][cvi][e], padded by one float per 8 to dodge bank conflicts on the column sums below
 #pragma unroll
-  for (int e = 0; e < 8; ++e) red[pl][cv][e] = acc[e];
+  for (int e = 0; e < 8; ++e) red[(pl * cv + cvi) * 8 + e] = acc[e];
   __syncthreads();
-  if (threadIdx.x < 64) {
-    const int ch = threadIdx.x;  // channel within the slab
+  for (int ch = threadIdx.x; ch < slab; ch += 256) {
     float s = 0.f;
-#pragma unroll 8
-    for (int p = 0; p < 32; ++p) s += red[p][ch >> 3][ch & 7];
+    for (int q = 0; q < PL; ++q) s += red[q * slab + ch];
     if (c0 + ch < C) {
       const float mean = s / static_cast<float>(HW);
       const size_t o = static_cast<size_t>(n) * C + c0 + ch;
@@ -153,9 +167,11 @@ struct GapOp : Op {
   void* out;
   cudaError_t launch(cudaStream_t s) override {
     g_launches++;
-    dim3 grid(ceil_div(C, 64), N);
-    if (dtype == PCV_F32) gap_kernel<float><<<grid, 256, 0, s>>>(HW, C, (const float*)x, in_pitch, out, out_f32);
-    else gap_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(HW, C, (const __nv_bfloat16*)x, in_pitch, out, out_f32);
+    int slab = 512;
+    while (slab > 64 && (slab > C || static_cast<long long>(N) * ceil_div(C, slab) < 4ll * sm_count())) slab >>= 1;
+    dim3 grid(ceil_div(C, slab), N);
+    if (dtype == PCV_F32) gap_kernel<float><<<grid, 256, 0, s>>>(HW, C, slab, (const float*)x, in_pitch, out, out_f32);
+    else gap_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(HW, C, slab, (const __nv_bfloat16*)x, in_pitch, out, out_f32);
     return cudaGetLastError();
   }
 };
@@ -198,75 +214,99 @@ fc_f32_kernel(int N, int C, int J, const float* __restrict__ x, const float* __r
   }
 }
 
-// Fused SE excite: one CTA per IMGS images does both skinny FCs with the pooled vectors and the hidden layer in
-// shared memory (the two-kernel version above was latency-bound: 160 us for 0.27 GFLOP at C = 2048).
-//   FC1: warp-per-hidden-unit, lanes stride over C with float4 loads of W1 (coalesced) and of the smem pooled rows;
-//   FC2: thread-per-output-channel, W2 rows read as float4 (each 128-byte line is consumed by the same thread over
-//        consecutive iterations, so L1 serves 7 of 8 accesses), hidden vector broadcast from smem; gate stores are
-//        coalesced across threads.
-template <int IMGS>
+// SE excite as two well-parallelised skinny-FC kernels (the per-image-group single-CTA version was latency-bound:
+// 160 us at C = 2048 with only 64 CTAs in flight).  Both kernels tile (IMGS images) x (a slice of the outputs) per CTA
+// so that ~500 CTAs are resident at C = 2048, keep the IMGS input rows in shared memory and read each weight row
+// exactly once per CTA with float4 loads.
+//   FC1: warp-per-hidden-unit (2 units per warp in flight), lanes stride over C, shuffle reduction.
+//   FC2: thread-per-output-channel, the hidden vectors broadcast from smem, coalesced gate stores.
+template <int IMGS, int JPW>
 __global__ void __launch_bounds__(256)
-se_excite_kernel(int N, int C, int Cmid, const float* __restrict__ pooled, const float* __restrict__ w1,
-                 const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2, int mid_act,
-                 int out_act, float* __restrict__ gate) {
-  extern __shared__ float se_smem[];
-  float* xs = se_smem;                 // [IMGS][C]
-  float* mids = se_smem + IMGS * C;    // [IMGS][Cmid]
+se_fc1_kernel(int N, int C, int Cmid, const float* __restrict__ pooled, const float* __restrict__ w1,
+              const float* __restrict__ b1, int mid_act, float* __restrict__ mid) {
+  extern __shared__ float se_smem[];   // [IMGS][C]
   const int n0 = blockIdx.x * IMGS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c4n = C >> 2;
   for (int i = threadIdx.x; i < IMGS * c4n; i += 256) {
     const int img = i / c4n, c4 = i - img * c4n;
     const int n = min(n0 + img, N - 1);
-    reinterpret_cast<float4*>(xs)[i] = __ldg(reinterpret_cast<const float4*>(pooled + static_cast<size_t>(n) * C) + c4);
+    reinterpret_cast<float4*>(se_smem)[i] = __ldg(reinterpret_cast<const float4*>(pooled + static_cast<size_t>(n) * C) + c4);
   }
   __syncthreads();
-  for (int j = warp; j < Cmid; j += 8) {
-    float acc[IMGS];
+  const int j0 = (blockIdx.y * 8 + warp) * JPW;
+  float acc[JPW][IMGS];
 #pragma unroll
-    for (int i = 0; i < IMGS; ++i) acc[i] = 0.f;
-    const float4* wr = reinterpret_cast<const float4*>(w1 + static_cast<size_t>(j) * C);
-#pragma unroll 4
-    for (int c4 = lane; c4 < c4n; c4 += 32) {
-      const float4 wv = __ldg(wr + c4);
+  for (int u = 0; u < JPW; ++u)
 #pragma unroll
-      for (int i = 0; i < IMGS; ++i) {
-        const float4 xv = reinterpret_cast<const float4*>(xs + i * C)[c4];
-        acc[i] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[i]))));
-      }
+    for (int i = 0; i < IMGS; ++i) acc[u][i] = 0.f;
+#pragma unroll 2
+  for (int c4 = lane; c4 < c4n; c4 += 32) {
+    float4 wv[JPW];
+#pragma unroll
+    for (int u = 0; u < JPW; ++u)
+      wv[u] = __ldg(reinterpret_cast<const float4*>(w1 + static_cast<size_t>(min(j0 + u, Cmid - 1)) * C) + c4);
+#pragma unroll
+    for (int i = 0; i < IMGS; ++i) {
+      const float4 xv = reinterpret_cast<const float4*>(se_smem + i * C)[c4];
+#pragma unroll
+      for (int u = 0; u < JPW; ++u)
+        acc[u][i] = fmaf(wv[u].x, xv.x, fmaf(wv[u].y, xv.y, fmaf(wv[u].z, xv.z, fmaf(wv[u].w, xv.w, acc[u][i]))));
     }
+  }
+#pragma unroll
+  for (int u = 0; u < JPW; ++u)
 #pragma unroll
     for (int i = 0; i < IMGS; ++i) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+      for (int o = 16; o > 0; o >>= 1) acc[u][i] += __shfl_xor_sync(0xffffffffu, acc[u][i], o);
     }
-    if (lane == 0) {
-      const float bj = b1 ? b1[j] : 0.f;
+  if (lane == 0) {
 #pragma unroll
-      for (int i = 0; i < IMGS; ++i) mids[i * Cmid + j] = misc_act(acc[i] + bj, mid_act);
-    }
-  }
-  __syncthreads();
-  const int m4n = Cmid >> 2;
-  for (int o = threadIdx.x; o < C; o += 256) {
-    float acc[IMGS];
-    const float bo = b2 ? b2[o] : 0.f;
+    for (int u = 0; u < JPW; ++u) {
+      const int j = j0 + u;
+      if (j < Cmid) {
+        const float bj = b1 ? b1[j] : 0.f;
 #pragma unroll
-    for (int i = 0; i < IMGS; ++i) acc[i] = bo;
-    const float4* wr = reinterpret_cast<const float4*>(w2 + static_cast<size_t>(o) * Cmid);
-#pragma unroll 4
-    for (int m4 = 0; m4 < m4n; ++m4) {
-      const float4 wv = __ldg(wr + m4);
-#pragma unroll
-      for (int i = 0; i < IMGS; ++i) {
-        const float4 mv = reinterpret_cast<const float4*>(mids + i * Cmid)[m4];
-        acc[i] = fmaf(wv.x, mv.x, fmaf(wv.y, mv.y, fmaf(wv.z, mv.z, fmaf(wv.w, mv.w, acc[i]))));
+        for (int i = 0; i < IMGS; ++i)
+          if (n0 + i < N) mid[static_cast<size_t>(n0 + i) * Cmid + j] = misc_act(acc[u][i] + bj, mid_act);
       }
     }
-#pragma unroll
-    for (int i = 0; i < IMGS; ++i)
-      if (n0 + i < N) gate[static_cast<size_t>(n0 + i) * C + o] = misc_act(acc[i], out_act);
   }
+}
+
+template <int IMGS>
+__global__ void __launch_bounds__(256)
+se_fc2_kernel(int N, int C, int Cmid, const float* __restrict__ mid, const float* __restrict__ w2,
+              const float* __restrict__ b2, int out_act, float* __restrict__ gate) {
+  extern __shared__ float se_smem[];   // [IMGS][Cmid]
+  const int n0 = blockIdx.x * IMGS;
+  const int m4n = Cmid >> 2;
+  for (int i = threadIdx.x; i < IMGS * m4n; i += 256) {
+    const int img = i / m4n, m4 = i - img * m4n;
+    const int n = min(n0 + img, N - 1);
+    reinterpret_cast<float4*>(se_smem)[i] = __ldg(reinterpret_cast<const float4*>(mid + static_cast<size_t>(n) * Cmid) + m4);
+  }
+  __syncthreads();
+  const int o = blockIdx.y * 256 + threadIdx.x;
+  if (o >= C) return;
+  float acc[IMGS];
+  const float bo = b2 ? b2[o] : 0.f;
+#pragma unroll
+  for (int i = 0; i < IMGS; ++i) acc[i] = bo;
+  const float4* wr = reinterpret_cast<const float4*>(w2 + static_cast<size_t>(o) * Cmid);
+#pragma unroll 8
+  for (int m4 = 0; m4 < m4n; ++m4) {
+    const float4 wv = __ldg(wr + m4);
+#pragma unroll
+    for (int i = 0; i < IMGS; ++i) {
+      const float4 mv = reinterpret_cast<const float4*>(se_smem + i * Cmid)[m4];
+      acc[i] = fmaf(wv.x, mv.x, fmaf(wv.y, mv.y, fmaf(wv.z, mv.z, fmaf(wv.w, mv.w, acc[i]))));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < IMGS; ++i)
+    if (n0 + i < N) gate[static_cast<size_t>(n0 + i) * C + o] = misc_act(acc[i], out_act);
 }
 
 struct SeExciteOp : Op {
@@ -275,22 +315,22 @@ struct SeExciteOp : Op {
   float* gate;
   float* mid;  // scratch lives at gate + N*C (caller sizes gate as N*(C+Cmid))
   cudaError_t launch(cudaStream_t s) override {
-    constexpr int IMGS = 4;
-    const size_t smem = static_cast<size_t>(IMGS) * (C + Cmid) * sizeof(float);
+    constexpr int IMGS = 4, JPW = 2;
+    g_launches += 2;
+    const size_t smem1 = static_cast<size_t>(IMGS) * C * sizeof(float), smem2 = static_cast<size_t>(IMGS) * Cmid * sizeof(float);
     const bool aligned = ((reinterpret_cast<uintptr_t>(pooled) | reinterpret_cast<uintptr_t>(w1) |
-                           reinterpret_cast<uintptr_t>(w2)) & 15) == 0;
-    if (C % 4 == 0 && Cmid % 4 == 0 && smem <= 200 * 1024 && aligned) {
-      g_launches += 1;
+                           reinterpret_cast<uintptr_t>(w2) | reinterpret_cast<uintptr_t>(mid)) & 15) == 0;
+    if (C % 4 == 0 && Cmid % 4 == 0 && smem1 <= 200 * 1024 && aligned && N <= 65535 * IMGS) {
       static size_t attr = 48 * 1024;
-      if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(se_excite_kernel<IMGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (smem1 > attr) {
+        cudaError_t e = cudaFuncSetAttribute(se_fc1_kernel<IMGS, JPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr = 200 * 1024;
       }
-      se_excite_kernel<IMGS><<<ceil_div(N, IMGS), 256, smem, s>>>(N, C, Cmid, pooled, w1, b1, w2, b2, mid_act, out_act, gate);
+      se_fc1_kernel<IMGS, JPW><<<dim3(ceil_div(N, IMGS), ceil_div(Cmid, 8 * JPW)), 256, smem1, s>>>(N, C, Cmid, pooled, w1, b1, mid_act, mid);
+      se_fc2_kernel<IMGS><<<dim3(ceil_div(N, IMGS), ceil_div(C, 256)), 256, smem2, s>>>(N, C, Cmid, mid, w2, b2, out_act, gate);
       return cudaGetLastError();
     }
-    g_launches += 2;
     fc_f32_kernel<<<dim3(ceil_div(Cmid, 8), ceil_div(N, 8)), 256, 0, s>>>(N, C, Cmid, pooled, w1, b1, mid_act, mid);
     fc_f32_kernel<<<dim3(ceil_div(C, 8), ceil_div(N, 8)), 256, 0, s>>>(N, Cmid, C, mid, w2, b2, out_act, gate);
     return cudaGetLastError();
@@ -638,7 +678,7 @@ int pcv_se_excite(pcv_plan* plan, int N, int C, int Cmid, const float* pooled, c
   op->N = N; op->C = C; op->Cmid = Cmid; op->mid_act = mid_act; op->out_act = out_act;
   op->pooled = pooled; op->w1 = w1; op->b1 = b1; op->w2 = w2; op->b2 = b2; op->gate = gate;
   op->mid = gate + static_cast<size_t>(N) * C;
-  op->launches = (C % 4 == 0 && Cmid % 4 == 0 && static_cast<size_t>(4) * (C + Cmid) * 4 <= 200 * 1024) ? 1 : 2;
+  op->launches = 2;
   char nm[96];
   snprintf(nm, sizeof nm, "se_excite C=%d mid=%d", C, Cmid);
   op->name = nm;

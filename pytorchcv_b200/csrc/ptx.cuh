@@ -176,6 +176,21 @@ __device__ __forceinline__ void umma2_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, 
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(SMEM_DESC_HI_SW128)
       : "memory");
 }
+// cta_group::2 MMA with an explicit high descriptor word for A (experiments with the matrix base-offset field)
+__device__ __forceinline__ void umma2_bf16_lohi_a(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %6};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(SMEM_DESC_HI_SW128), "r"(a_hi)
+      : "memory");
+}
 // mbarrier arrive once every previously issued tcgen05.mma of this thread has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

@@ -59,19 +59,33 @@ __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
   return *reinterpret_cast<const uint32_t*>(&r);
 }
 
+// Tile coordinates as a mixed-radix counter (channel block fastest, then tile column, tile row, image) that is
+// advanced by the CTA's stride with carries: no integer division in the persistent loop.
 struct TileCoord {
-  int n, ho0, wo0, c0;
+  int cb, tx, ty, n;
 };
-__device__ __forceinline__ TileCoord decode_tile(const WinParams& p, long long t, int TH) {
+__device__ __forceinline__ TileCoord tile_decode(const WinParams& p, uint32_t t) {
   TileCoord tc;
-  const int cb = static_cast<int>(t % p.cblocks); t /= p.cblocks;
-  const int tx = static_cast<int>(t % p.tiles_x); t /= p.tiles_x;
-  const int ty = static_cast<int>(t % p.tiles_y);
-  tc.n = static_cast<int>(t / p.tiles_y);
-  tc.ho0 = ty * TH;
-  tc.wo0 = tx * p.TW;
-  tc.c0 = cb * p.CB;
+  tc.cb = t % p.cblocks; t /= p.cblocks;
+  tc.tx = t % p.tiles_x; t /= p.tiles_x;
+  tc.ty = t % p.tiles_y;
+  tc.n = t / p.tiles_y;
   return tc;
+}
+__device__ __forceinline__ void tile_advance(const WinParams& p, TileCoord& tc, const TileCoord& step) {
+  tc.cb += step.cb;
+  if (tc.cb >= p.cblocks) { tc.cb -= p.cblocks; ++tc.tx; }
+  tc.tx += step.tx;
+  if (tc.tx >= p.tiles_x) { tc.tx -= p.tiles_x; ++tc.ty; }
+  tc.ty += step.ty;
+  if (tc.ty >= p.tiles_y) { tc.ty -= p.tiles_y; ++tc.n; }
+  tc.n += step.n;
+}
+
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
 }
 
 template <int OP, int KS, int S, int TH>   // OP 0: depthwise conv, 1: max pool
@@ -84,6 +98,12 @@ win_kernel(const __grid_constant__ CUtensorMap tmIn, const WinParams p, const fl
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
   const int tid = threadIdx.x;
+  const uint32_t num_tiles = static_cast<uint32_t>(p.num_tiles);
+
+  const TileCoord step = tile_decode(p, gridDim.x);          // this CTA's stride as mixed-radix digits
+  TileCoord tc = tile_decode(p, blockIdx.x);                 // tile being computed
+  TileCoord lc = tc;                                         // tile being loaded (thread 0), `stages` tiles ahead
+  uint32_t lt = blockIdx.x;
 
   if (tid == 0) {
     tma_prefetch_desc(&tmIn);
@@ -92,11 +112,12 @@ win_kernel(const __grid_constant__ CUtensorMap tmIn, const WinParams p, const fl
   }
   __syncthreads();
   if (tid == 0) {
-    long long t = blockIdx.x;
-    for (int i = 0; i < p.stages && t < p.num_tiles; ++i, t += gridDim.x) {
-      const TileCoord tc = decode_tile(p, t, TH);
+    for (int i = 0; i < p.stages && lt < num_tiles; ++i) {
       mbar_arrive_expect_tx(&full[i], p.tx_bytes);
-      tma_load_4d(&tmIn, &full[i], smem + i * p.stage_bytes, tc.c0, tc.wo0 * S - p.pad, tc.ho0 * S - p.pad, tc.n);
+      tma_load_4d(&tmIn, &full[i], smem + i * p.stage_bytes, lc.cb * p.CB, lc.tx * p.TW * S - p.pad,
+                  lc.ty * TH * S - p.pad, lc.n);
+      lt += gridDim.x;
+      tile_advance(p, lc, step);
     }
   }
 
@@ -106,15 +127,11 @@ win_kernel(const __grid_constant__ CUtensorMap tmIn, const WinParams p, const fl
   const int v = active ? tid - col * nv : 0;
   const int row_bytes = p.IW * p.CB * 2;
   const int px_bytes = p.CB * 2;
-  const uint32_t thread_off = (col * S * p.CB + v * 4) * 2;
+  const uint32_t thread_off = smem_u32(smem) + (col * S * p.CB + v * 4) * 2;
 
-  int stage = 0;
-  uint32_t phase = 0;
-  for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-    const TileCoord tc = decode_tile(p, t, TH);
-    const int c = tc.c0 + v * 4;
-    float2 wr[OP == 0 ? KS * KS : 1][2];
-    float2 b2[2];
+  float2 wr[OP == 0 ? KS * KS : 1][2];
+  float2 b2[2];
+  auto load_weights = [&](int c) {
     if (OP == 0) {
 #pragma unroll
       for (int k = 0; k < KS * KS; ++k) {
@@ -126,7 +143,16 @@ win_kernel(const __grid_constant__ CUtensorMap tmIn, const WinParams p, const fl
       b2[0] = make_float2(q.x, q.y);
       b2[1] = make_float2(q.z, q.w);
     }
-    const int wo = tc.wo0 + col;
+  };
+  if (p.cblocks == 1) load_weights(v * 4);                   // one channel block: weights are loop-invariant
+
+  int stage = 0;
+  uint32_t phase = 0;
+  for (uint32_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const int c = tc.cb * p.CB + v * 4;
+    if (p.cblocks != 1) load_weights(c);
+    const int ho0 = tc.ty * TH;
+    const int wo = tc.tx * p.TW + col;
     const bool col_ok = active && wo < p.Wo;
     // max pool: which taps of this thread's window fall inside the image
     bool fs_ok[KS];
@@ -135,10 +161,14 @@ win_kernel(const __grid_constant__ CUtensorMap tmIn, const WinParams p, const fl
       const int wi = wo * S - p.pad + fs;
       fs_ok[fs] = wi >= 0 && wi < p.W;
     }
-    const int hi0 = tc.ho0 * S - p.pad;
+    const int hi0 = ho0 * S - p.pad;
+    const size_t pix0 = (static_cast<size_t>(tc.n) * p.Ho + ho0) * p.Wo + wo;
+    __nv_bfloat16* yp = y + pix0 * p.out_pitch + c;
+    const __nv_bfloat16* rp = res ? res + pix0 * p.res_pitch + c : nullptr;
+    const size_t y_row = static_cast<size_t>(p.Wo) * p.out_pitch, r_row = static_cast<size_t>(p.Wo) * p.res_pitch;
 
     mbar_wait(&full[stage], phase);
-    const uint8_t* sbase = smem + stage * p.stage_bytes + thread_off;
+    const uint32_t sbase = thread_off + stage * p.stage_bytes;
 
     float2 acc[NACC][2];
     uint2 mx[NACC];
@@ -146,7 +176,7 @@ win_kernel(const __grid_constant__ CUtensorMap tmIn, const WinParams p, const fl
     for (int ir = 0; ir < IH; ++ir) {
       uint2 raw[KS];
 #pragma unroll
-      for (int fs = 0; fs < KS; ++fs) raw[fs] = *reinterpret_cast<const uint2*>(sbase + ir * row_bytes + fs * px_bytes);
+      for (int fs = 0; fs < KS; ++fs) raw[fs] = lds64(sbase + ir * row_bytes + fs * px_bytes);
       float2 xv[KS][2];
       if (OP == 0) {
 #pragma unroll
@@ -184,14 +214,12 @@ win_kernel(const __grid_constant__ CUtensorMap tmIn, const WinParams p, const fl
           }
         }
         if (fr == KS - 1) {
-          const int hog = tc.ho0 + ho;
-          if (col_ok && hog < p.Ho) {
-            const size_t pix = (static_cast<size_t>(tc.n) * p.Ho + hog) * p.Wo + wo;
+          if (col_ok && ho0 + ho < p.Ho) {
             uint2 o;
             if (OP == 0) {
               float2 r0 = acc[a][0], r1 = acc[a][1];
-              if (res) {
-                const uint2 rr = __ldg(reinterpret_cast<const uint2*>(res + pix * p.res_pitch + c));
+              if (rp) {
+                const uint2 rr = __ldg(reinterpret_cast<const uint2*>(rp + ho * r_row));
                 r0.x += bf16lo(rr.x); r0.y += bf16hi(rr.x); r1.x += bf16lo(rr.y); r1.y += bf16hi(rr.y);
               }
               r0.x = fminf(fmaxf(r0.x, p.act_lo), p.act_hi); r0.y = fminf(fmaxf(r0.y, p.act_lo), p.act_hi);
@@ -201,22 +229,21 @@ win_kernel(const __grid_constant__ CUtensorMap tmIn, const WinParams p, const fl
             } else {
               o = mx[a];
             }
-            *reinterpret_cast<uint2*>(y + pix * p.out_pitch + c) = o;
+            *reinterpret_cast<uint2*>(yp + ho * y_row) = o;
           }
         }
       }
     }
 
     __syncthreads();   // every thread is done reading this stage
-    if (tid == 0) {
-      const long long tn = t + static_cast<long long>(p.stages) * gridDim.x;
-      if (tn < p.num_tiles) {
-        const TileCoord nc = decode_tile(p, tn, TH);
-        mbar_arrive_expect_tx(&full[stage], p.tx_bytes);
-        tma_load_4d(&tmIn, &full[stage], smem + stage * p.stage_bytes, nc.c0, nc.wo0 * S - p.pad, nc.ho0 * S - p.pad,
-                    nc.n);
-      }
+    if (tid == 0 && lt < num_tiles) {
+      mbar_arrive_expect_tx(&full[stage], p.tx_bytes);
+      tma_load_4d(&tmIn, &full[stage], smem + stage * p.stage_bytes, lc.cb * p.CB, lc.tx * p.TW * S - p.pad,
+                  lc.ty * TH * S - p.pad, lc.n);
+      lt += gridDim.x;
+      tile_advance(p, lc, step);
     }
+    tile_advance(p, tc, step);
     if (++stage == p.stages) {
       stage = 0;
       phase ^= 1;
@@ -340,6 +367,7 @@ int win_make(int op_kind, int N, int H, int W, int C, int k, int stride, int pad
   p.act_hi = act == PCV_ACT_RELU6 ? 6.f : INFINITY;
   if (!pick_cfg(C, p.Ho, p.Wo, k, stride, &p, &op->cfg)) return PCV_ERR_UNSUPPORTED;
   p.num_tiles = static_cast<long long>(N) * p.tiles_y * p.tiles_x * p.cblocks;
+  if (p.num_tiles >= (1ll << 31)) return PCV_ERR_UNSUPPORTED;
   const int IH = (op->cfg.TH - 1) * stride + k;
   if (int rc = make_win_map(&op->tm, x, N, H, W, C, in_pitch, p.CB, p.IW, IH)) return rc;
   op->op_kind = op_kind; op->S = stride; op->w = w; op->bias = bias;

@@ -43,6 +43,11 @@ CASES = [
     ("head_256_21_direct",        2, 30, 30, 256,  21, 1, 1, 0, 1, 1, 0, 0, 0, "bf16"),
     ("persistent_many_tiles",     8, 56, 56,  64, 256, 1, 1, 0, 1, 1, 1, 1, 0, "bf16"),
     ("persistent_3x3_many",       8, 56, 56,  64,  64, 3, 1, 1, 1, 1, 1, 0, 0, "bf16"),
+    ("halo3x3_64_64_56",          4, 56, 56,  64,  64, 3, 1, 1, 1, 1, 1, 0, 0, "bf16"),
+    ("halo3x3_128_128_28",        5, 28, 28, 128, 128, 3, 1, 1, 1, 1, 1, 0, 0, "bf16"),
+    ("halo3x3_64_128_ragged",     3, 30, 26,  64, 128, 3, 1, 1, 1, 1, 0, 0, 0, "bf16"),
+    ("halo3x3_128_64_relu6",      2, 41, 33, 128,  64, 3, 1, 1, 1, 1, 2, 0, 0, "bf16"),
+    ("halo3x3_256_64_wide",       1, 24, 120, 256, 64, 3, 1, 1, 1, 1, 1, 0, 0, "bf16"),
     ("simt_bf16_3x3",             2, 14, 14,  64,  64, 3, 1, 1, 1, 1, 1, 1, 2, "bf16"),
     ("simt_f32_3x3",              2, 14, 14,  64,  64, 3, 1, 1, 1, 1, 1, 1, 0, "fp32"),
     ("simt_f32_7x7_c3",           2, 64, 64,   3,  64, 7, 2, 3, 1, 1, 1, 0, 0, "fp32"),
