@@ -141,7 +141,7 @@ def main() -> None:
     ap.add_argument("--model", type=str, default="resnet50", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=None, help="images per GPU (weak scaling)")
     ap.add_argument("--dtype", type=str, default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--graph", type=int, default=0, help="replay the plan from a CUDA graph")
+    ap.add_argument("--graph", type=int, default=1, help="replay the plan from a CUDA graph")
     ap.add_argument("--ref-batch", type=int, default=32, help="images per step of the CPU reference arm")
     ap.add_argument("--ref-max-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -49,9 +49,10 @@ __device__ __forceinline__ void tma2_load_4d(const CUtensorMap* m, uint32_t mbar
 }
 
 constexpr int I3_MAX_NA = 6;
+constexpr int I3_THREADS = 384;   // 4 control warps + 8 epilogue warps
 
 template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I3_THREADS, 1)
 igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Igemm3Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -87,7 +88,7 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     mbar_init(b_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
+      mbar_init(&tmem_empty[i], 16);   // 8 epilogue warps x 2 CTAs
     }
     fence_mbar_init();
   }
@@ -182,9 +183,12 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
   } else if (warp >= 4) {
     // ===================================== epilogue (both CTAs) =====================================
+    // eight warps: warp w owns TMEM lane quarter (w & 3) and every second 32-column chunk starting at (w - 4) >> 2
     const int q4 = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int row = q4 * 32 + lane;
-    const float act_lo = p.act_lo, act_hi = p.act_hi;
+    const uint32_t lo2 = pack_bf16x2(p.act_lo, p.act_lo), hi2 = pack_bf16x2(p.act_hi, p.act_hi);
+    const bool clamp_lo = p.act_lo > -INFINITY, clamp_hi = p.act_hi < INFINITY;
     const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
     int it = 0;
@@ -206,7 +210,7 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const bool ok = tile_ok && c < p.W && r < p.R && (h0 + r) < p.H;
         __nv_bfloat16* dst = p.out + (static_cast<size_t>(img * p.H + h0 + r) * p.W + c) * p.out_pitch;
 #pragma unroll 1
-        for (int j = 0; j < BN / 32; ++j) {
+        for (int j = half; j < BN / 32; j += 2) {
           uint32_t acc[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * acc_cols + mb * BN + j * 32, acc);
           tmem_ld_wait();
@@ -215,12 +219,13 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 b = __ldg(bias4 + i);
-            const float v0 = fminf(fmaxf(__uint_as_float(acc[4 * i + 0]) + b.x, act_lo), act_hi);
-            const float v1 = fminf(fmaxf(__uint_as_float(acc[4 * i + 1]) + b.y, act_lo), act_hi);
-            const float v2 = fminf(fmaxf(__uint_as_float(acc[4 * i + 2]) + b.z, act_lo), act_hi);
-            const float v3 = fminf(fmaxf(__uint_as_float(acc[4 * i + 3]) + b.w, act_lo), act_hi);
-            o[2 * i + 0] = pack_bf16x2(v0, v1);
-            o[2 * i + 1] = pack_bf16x2(v2, v3);
+            const float2 v0 = add2(make_float2(__uint_as_float(acc[4 * i + 0]), __uint_as_float(acc[4 * i + 1])), make_float2(b.x, b.y));
+            const float2 v1 = add2(make_float2(__uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3])), make_float2(b.z, b.w));
+            uint32_t w0 = pack_bf16x2(v0.x, v0.y), w1 = pack_bf16x2(v1.x, v1.y);
+            if (clamp_lo) { w0 = hmax2_bf16(w0, lo2); w1 = hmax2_bf16(w1, lo2); }
+            if (clamp_hi) { w0 = hmin2_bf16(w0, hi2); w1 = hmin2_bf16(w1, hi2); }
+            o[2 * i + 0] = w0;
+            o[2 * i + 1] = w1;
           }
           if (ok) {
             uint4* d4 = reinterpret_cast<uint4*>(dst + j * 32);
@@ -264,7 +269,7 @@ static cudaError_t launch_i3(const Igemm3Op& op, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  igemm3_kernel<BN><<<op.grid, NUM_THREADS, op.smem_bytes, s>>>(op.tmA, op.tmB, op.p);
+  igemm3_kernel<BN><<<op.grid, I3_THREADS, op.smem_bytes, s>>>(op.tmA, op.tmB, op.p);
   return cudaGetLastError();
 }
 

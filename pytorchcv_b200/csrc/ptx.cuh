@@ -237,6 +237,21 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// packed fp32x2 add (Blackwell FADD2); each lane rounds like a scalar add
+__device__ __forceinline__ float2 add2(const float2 a, const float2 b) {
+  uint64_t aa = (static_cast<uint64_t>(__float_as_uint(a.y)) << 32) | __float_as_uint(a.x);
+  const uint64_t bb = (static_cast<uint64_t>(__float_as_uint(b.y)) << 32) | __float_as_uint(b.x);
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(aa) : "l"(bb));
+  return make_float2(__uint_as_float(static_cast<uint32_t>(aa)), __uint_as_float(static_cast<uint32_t>(aa >> 32)));
+}
+__device__ __forceinline__ uint32_t hmax2_bf16(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t hmin2_bf16(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r = __hmin2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
