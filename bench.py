@@ -271,7 +271,16 @@ def main() -> None:
         ach = top["mb"] / top["ms"]     # MB/ms == GB/s
         roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": round(BW / 1e9, 1), "unit": "GB/s",
                 "frac": round(ach / (BW / 1e9), 3)}
-    roof.update({"traffic": None, "kernel": top["op"], "kernel_ms": top["ms"], "peak_source": pk["source"],
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        for key, rec in tj.items():
+            if not key.startswith("_") and top["op"].startswith(key) and N == CONFIGS[a.model][0]:
+                traffic = {"bytes": rec["dram_read_bytes"] + rec["dram_write_bytes"], "algorithmic_bytes": top["mb"] * 1e6,
+                           "source": rec["source"]}
+    except (OSError, ValueError, KeyError):
+        pass
+    roof.update({"traffic": traffic, "kernel": top["op"], "kernel_ms": top["ms"], "peak_source": pk["source"],
                  "share_of_step": round(top["ms"] / sum_meas, 3)})
     tc = [r for r in table if r["op"].startswith("conv_tc") and r["bound"] == "tensor"]
     hb = [r for r in table if r["bound"] == "hbm"]

@@ -97,6 +97,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   if (tmem_base != 0) __trap();   // one CTA per SM => the allocation starts at column 0; the MMA warp relies on it
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -500,9 +502,8 @@ static cudaError_t launch_variant(const IgemmOp& op, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  igemm_kernel<BN, STAGES, OUT_MODE><<<op.grid, NUM_THREADS, L::DYN_BYTES, s>>>(op.tmA, op.tmB, op.tmOut, op.tmRes,
-                                                                                 op.p);
-  return cudaGetLastError();
+  return launch_pdl(igemm_kernel<BN, STAGES, OUT_MODE>, dim3(op.grid), dim3(NUM_THREADS), L::DYN_BYTES, s, op.tmA, op.tmB,
+                    op.tmOut, op.tmRes, op.p);
 }
 
 template <int BN, int STAGES>

@@ -98,6 +98,8 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   if (tmem_base != 0) __trap();   // one CTA per SM => the allocation starts at column 0; the MMA warp relies on it
+  pdl_launch_dependents();        // the next kernel may start its prologue as SMs drain ...
+  pdl_wait();                     // ... and this one touches activations only after its predecessor completed
 
   if (warp == 0) {
     // ===================================== TMA producer (both CTAs) =====================================
@@ -352,8 +354,8 @@ static cudaError_t launch_pair(int grid, const CUtensorMap& tmA, const CUtensorM
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  igemm2_kernel<BN><<<grid, NUM_THREADS, L::bytes(p.stages, p.ksub, p.nstg), s>>>(tmA, tmB, tmOut, tmRes, p);
-  return cudaGetLastError();
+  return launch_pdl(igemm2_kernel<BN>, dim3(grid), dim3(NUM_THREADS), L::bytes(p.stages, p.ksub, p.nstg), s, tmA, tmB, tmOut,
+                    tmRes, p);
 }
 
 // Per-layer shared-memory split: K sub-blocks per stage (amortises the per-stage handshake over >= ~512 MMA cycles),

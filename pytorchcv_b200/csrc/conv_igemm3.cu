@@ -101,6 +101,7 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   if (tmem_base != 0) __trap();   // one CTA per SM (227 KB smem) => the allocation starts at column 0; the MMA warp relies on it
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================================== producer (both CTAs) =====================================
@@ -110,6 +111,7 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       for (int b = 0; b < nb_blocks; ++b)
         if (elect_one())
           tma2_load_2d(&tmB, bfull_leader, sB + b * p.b_block_bytes, b * BLOCK_K, static_cast<int>(rank) * (BN / 2));
+      pdl_wait();   // weights above do not depend on the previous kernel; the activations below do
       int slot = 0;
       uint32_t phase = 0;
       for (int t = pair; t < pair_tiles; t += npairs) {
@@ -184,6 +186,7 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else if (warp >= 4) {
     // ===================================== epilogue (both CTAs) =====================================
     // eight warps: warp w owns TMEM lane quarter (w & 3) and every second 32-column chunk starting at (w - 4) >> 2
+    pdl_wait();   // the output buffer may alias a tensor the previous kernel is still reading
     const int q4 = warp & 3;
     const int half = (warp - 4) >> 2;
     const int row = q4 * 32 + lane;
@@ -269,8 +272,7 @@ static cudaError_t launch_i3(const Igemm3Op& op, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  igemm3_kernel<BN><<<op.grid, I3_THREADS, op.smem_bytes, s>>>(op.tmA, op.tmB, op.p);
-  return cudaGetLastError();
+  return launch_pdl(igemm3_kernel<BN>, dim3(op.grid), dim3(I3_THREADS), op.smem_bytes, s, op.tmA, op.tmB, op.p);
 }
 
 cudaError_t Igemm3Op::launch(cudaStream_t s) {

@@ -24,6 +24,14 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("PCV_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {

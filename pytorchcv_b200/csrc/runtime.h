@@ -64,6 +64,26 @@ inline int pitch_or(int pitch, int c) { return pitch > 0 ? pitch : c; }
 inline size_t esize(int dtype) { return dtype == PCV_F32 ? 4 : 2; }
 int sm_count();
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// The hot kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization so that the next kernel's
+// prologue (barrier init, TMEM allocation, descriptor prefetch, resident-weight loads) overlaps the tail of the
+// previous one; every such kernel executes griddepcontrol.wait before touching activation memory.  PCV_PDL=0 disables.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- driver entry points for tensor maps (resolved at run time so the .so loads without libcuda) ----------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -120,6 +120,8 @@ win_kernel(const __grid_constant__ CUtensorMap tmIn, const WinParams p, const fl
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();   // nothing of the previous kernel's output is read, and nothing it may still read is overwritten, before this
   if (tid == 0) {
     for (int i = 0; i < p.stages && lt < num_tiles; ++i) {
       mbar_arrive_expect_tx(&full[i], p.tx_bytes);
@@ -364,8 +366,7 @@ struct WinOp : Op {
     }
     const long long cap = static_cast<long long>(sm_count()) * cfg.ctas_per_sm;
     const int grid = static_cast<int>(std::min<long long>(p.num_tiles, cap));
-    win_kernel<OP, 3, S_, TH, COLS, RES><<<grid, cfg.threads, cfg.smem_bytes, s>>>(tm, p, w, bias, res, y);
-    return cudaGetLastError();
+    return launch_pdl(win_kernel<OP, 3, S_, TH, COLS, RES>, dim3(grid), dim3(cfg.threads), cfg.smem_bytes, s, tm, p, w, bias, res, y);
   }
   template <int OP, int S_, int COLS, bool RES>
   cudaError_t go_th(cudaStream_t s) {
