@@ -588,7 +588,7 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   op->pair = pair_enabled && p.out_mode == 0 && d.Cout >= 64 && p.tiles_m >= 2;
   if (op->pair) {
     op->bn = grouped ? 64 : (d.Cout > 128 ? 256 : (d.Cout > 64 ? 128 : 64));
-    igemm2_pick_smem(op->bn, p.num_kblocks, res != nullptr, &p.stages, &p.ksub, &p.nstg);
+    igemm2_pick_smem(op->bn, p.num_kblocks, res != nullptr, taps, &p.stages, &p.ksub, &p.nstg);
   }
   p.tiles_n = ceil_div(d.Cout, op->bn);
 

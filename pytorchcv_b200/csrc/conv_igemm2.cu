@@ -29,7 +29,7 @@ struct Pair {
   static constexpr int SUB_BYTES = BLOCK_M * SUB_COLS * 2;  // 16 KiB
   static constexpr int NSUB = BN / SUB_COLS;                // sub-tiles per output tile
   static constexpr int MAX_STAGES = 8, MAX_NSTG = 8;
-  static constexpr int NUM_BARS = 2 * MAX_STAGES + 4 + 2 * MAX_NSTG;
+  static constexpr int NUM_BARS = 2 * MAX_STAGES + 4 + 3 * MAX_NSTG;
   static constexpr uint32_t TMEM_COLS = 2 * BN;             // double-buffered accumulator (256 or 512 columns)
   // shared memory: [stages x A][stages x B][nstg x staging][barriers]; the split is chosen per layer at run time
   // (long-K tensor-bound layers want a deep operand ring, short-K bandwidth-bound layers a deep staging ring)
@@ -56,8 +56,9 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint64_t* empty = bars + L::MAX_STAGES;           // [STAGES]  per CTA, released by the multicast commit
   uint64_t* tmem_full = bars + 2 * L::MAX_STAGES;   // [2]       per CTA, multicast commit
   uint64_t* tmem_empty = tmem_full + 2;             // [2]       leader's copy, 8 arrivals
-  uint64_t* stg_empty = tmem_empty + 2;             // [NSTG]
-  uint64_t* res_full = stg_empty + L::MAX_NSTG;     // [NSTG]
+  uint64_t* stg_free = tmem_empty + 2;              // [NSTG]  staging manager -> epilogue: slot may be overwritten
+  uint64_t* res_full = stg_free + L::MAX_NSTG;      // [NSTG]  residual TMA -> epilogue: residual sub-tile landed
+  uint64_t* stg_full = res_full + L::MAX_NSTG;      // [NSTG]  epilogue (4 warps) -> staging manager: result written
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
 
   const int warp = threadIdx.x >> 5;
@@ -84,8 +85,9 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       mbar_init(&tmem_empty[i], 8);
     }
     for (int i = 0; i < NSTG; ++i) {
-      mbar_init(&stg_empty[i], 1);
+      mbar_init(&stg_free[i], 1);
       mbar_init(&res_full[i], 1);
+      mbar_init(&stg_full[i], 4);
     }
     fence_mbar_init();
   }
@@ -201,46 +203,67 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
   } else if (warp == 3) {
-    // ===================================== residual prefetcher (both CTAs) =====================================
-    if (p.has_res) {   // whole warp, TMA under elect.sync (see the producer's note)
-      int slot = 0;
-      uint32_t sphase = 0;
-      for (int t = pair; t < num_tiles; t += npairs) {
-        const int pm = t / p.tiles_n;
-        const int n_tile = t - pm * p.tiles_n;
-        const int m0 = (2 * pm + static_cast<int>(rank)) * BLOCK_M;
-        for (int sub = 0; sub < L::NSUB; ++sub) {
-          mbar_wait(&stg_empty[slot], sphase ^ 1);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&res_full[slot], L::SUB_BYTES);
-            tma_load_2d(&tmRes, &res_full[slot], sStg + slot * L::SUB_BYTES, n_tile * BN + sub * L::SUB_COLS, m0);
-          }
-          if (++slot == NSTG) {
-            slot = 0;
-            sphase ^= 1;
-          }
+    // ===================================== staging manager (both CTAs) =====================================
+    // Owns every TMA operation on the staging ring: stores the finished 64-column sub-tiles and refills freed slots
+    // with the residual of the sub-tile that will use them NSTG rounds later.  The epilogue warps never wait for a
+    // store to drain or for each other - they only wait for data (res_full) or a free slot (stg_free) - so the
+    // per-round latency chain (bar.sync + store issue + read-out wait) that paced every short-K layer is gone.
+    const int my_tiles = pair < num_tiles ? (num_tiles - pair + npairs - 1) / npairs : 0;
+    const int total_rounds = my_tiles * L::NSUB;
+    auto round_coords = [&](int r, int& col0, int& row0) {
+      const int t = pair + (r / L::NSUB) * npairs;
+      const int pm = t / p.tiles_n;
+      const int n_tile = t - pm * p.tiles_n;
+      col0 = n_tile * BN + (r % L::NSUB) * L::SUB_COLS;
+      row0 = (2 * pm + static_cast<int>(rank)) * BLOCK_M;
+    };
+    auto refill = [&](int r) {   // slot of round r is free: fetch its residual, or tell the epilogue it may write
+      if (r >= total_rounds) return;
+      const int s = r % NSTG;
+      if (elect_one()) {
+        if (p.has_res) {
+          int col0, row0;
+          round_coords(r, col0, row0);
+          mbar_arrive_expect_tx(&res_full[s], L::SUB_BYTES);
+          tma_load_2d(&tmRes, &res_full[s], sStg + s * L::SUB_BYTES, col0, row0);
+        } else {
+          mbar_arrive(&stg_free[s]);
         }
       }
+    };
+    for (int r = 0; r < NSTG; ++r) refill(r);
+    for (int r = 0; r < total_rounds; ++r) {
+      const int s = r % NSTG;
+      mbar_wait(&stg_full[s], (r / NSTG) & 1);
+      if (elect_one()) {   // elect.sync is deterministic: one lane owns every bulk group
+        int col0, row0;
+        round_coords(r, col0, row0);
+        tma_store_2d(&tmOut, sStg + s * L::SUB_BYTES, col0, row0);
+        tma_store_commit();
+        tma_store_wait_read<1>();   // the store of round r-1 has left its slot
+      }
+      __syncwarp();
+      if (r >= 1) refill(r - 1 + NSTG);
     }
+    if (elect_one()) tma_store_wait_read<0>();
+    __syncwarp();
+    if (elect_one()) tma_store_wait_all<0>();
   } else if (warp >= 4) {
     // ===================================== epilogue (both CTAs) =====================================
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int epi_tid = threadIdx.x - 128;
     const float act_lo = p.act_lo, act_hi = p.act_hi;
     const bool fancy_act = p.act > PCV_ACT_RELU6;
     const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
     int it = 0;
     int slot = 0;
-    int subs_done = 0;
     uint32_t sphase = 0;
     for (int t = pair; t < num_tiles; t += npairs, ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int pm = t / p.tiles_n;
       const int n_tile = t - pm * p.tiles_n;
-      const int m0 = (2 * pm + static_cast<int>(rank)) * BLOCK_M;
       const int n0 = n_tile * BN;
 
       mbar_wait(&tmem_full[buf], acc_phase);
@@ -249,7 +272,9 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll 1
       for (int sub = 0; sub < L::NSUB; ++sub) {
         uint8_t* stg = sStg + slot * L::SUB_BYTES;
-        if (p.has_res) mbar_wait(&res_full[slot], sphase);
+        // the slot is ready when its residual has landed (which implies the previous store has left it) or, without
+        // a residual, when the staging manager has released it
+        mbar_wait(p.has_res ? &res_full[slot] : &stg_free[slot], sphase);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int col = sub * L::SUB_COLS + h * 32;
@@ -311,29 +336,15 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             else mbar_arrive_cluster(buf ? tmem_empty_leader1 : tmem_empty_leader0);
           }
         }
-        fence_proxy_async_smem();
-        named_bar_sync(1, EPI_THREADS);
-        if (warp == 4 && elect_one()) {   // elect.sync is deterministic: the same lane owns every bulk group
-          tma_store_2d(&tmOut, stg, n0 + sub * L::SUB_COLS, m0);
-          tma_store_commit();
-          if (NSTG >= 3) {
-            // one store stays in flight: the slot used one sub-tile ago is readable again by the residual TMA loads
-            tma_store_wait_read<1>();
-            if (subs_done >= 1) mbar_arrive(&stg_empty[slot >= 1 ? slot - 1 : NSTG - 1]);
-          } else {
-            tma_store_wait_read<0>();      // 2-slot ring (long-K layers): recycle this slot as soon as it is read
-            mbar_arrive(&stg_empty[slot]);
-          }
-        }
-        if (NSTG < 3) named_bar_sync(1, EPI_THREADS);  // without look-ahead every thread must see the slot free
-        ++subs_done;
+        fence_proxy_async_smem();   // this thread's st.shared -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stg_full[slot]);   // 4 arrivals (one per epilogue warp) hand the slot to the manager
         if (++slot == NSTG) {
           slot = 0;
           sphase ^= 1;
         }
       }
     }
-    if (warp == 4 && elect_one()) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -361,7 +372,7 @@ static cudaError_t launch_pair(int grid, const CUtensorMap& tmA, const CUtensorM
 // Per-layer shared-memory split: K sub-blocks per stage (amortises the per-stage handshake over >= ~512 MMA cycles),
 // operand-ring depth, staging slots.  Long-K (tensor-bound) layers get a deep operand ring and a 2-slot staging ring;
 // short-K (bandwidth-bound) layers a shallow operand ring and a deep staging ring for residual prefetch.
-void igemm2_pick_smem(int bn, int num_kblocks, bool has_res, int* stages, int* ksub, int* nstg) {
+void igemm2_pick_smem(int bn, int num_kblocks, bool has_res, int taps, int* stages, int* ksub, int* nstg) {
   const int stage_bytes = A_STAGE_BYTES + (bn / 2) * BLOCK_K * 2;
   const int sub_bytes = BLOCK_M * 64 * 2;
   const int fixed = (2 * 8 + 4 + 2 * 8) * 8 + 16 + 1024;
@@ -376,6 +387,13 @@ void igemm2_pick_smem(int bn, int num_kblocks, bool has_res, int* stages, int* k
   }
   if (num_kblocks < 8) st = std::min(st, std::max(2, 4 / ks + 1));
   ns = std::max(2, std::min(8, (budget - st * ks * stage_bytes) / sub_bytes));
+  if (taps == 1 && num_kblocks >= 8 && bn == 256) {
+    // long-K pointwise layers are paced by the epilogue round trip (store read-out + barrier), not by operand
+    // latency: measured sweep (profiles/README.md) prefers one k-block per stage and >= 4 staging slots
+    ks = 1;
+    ns = has_res ? 6 : 4;
+    st = std::min(8, (budget - ns * sub_bytes) / stage_bytes);
+  }
   if (const char* e = getenv("PCV_IGEMM2_STAGES")) st = atoi(e);
   if (const char* e = getenv("PCV_IGEMM2_KSUB")) ks = atoi(e);
   if (const char* e = getenv("PCV_IGEMM2_NSTG")) ns = atoi(e);
