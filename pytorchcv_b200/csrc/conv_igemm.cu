@@ -60,7 +60,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* res_full = stg_empty + L::NSTG;    // [NSTG]    residual TMA -> epilogue
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
 
-  const int warp = threadIdx.x >> 5;
+  // role index (see conv_igemm2.cu): control roles live in the high physical warp ids, which the scheduler prefers
+  const int warp = ((threadIdx.x >> 5) + 4) & 7;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.tiles_m * p.tiles_n;
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;

@@ -67,7 +67,10 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint64_t* tmem_empty = tmem_full + 2;          // [2]   leader's copy, 8 arrivals
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // role index: physical warps 8-11 are the control roles 0-3 (the scheduler prefers high warp ids), physical warps
+  // 0-7 the epilogue roles 4-11 (TMEM lane quarter = role & 3 = physical warp & 3)
+  const int pw = threadIdx.x >> 5;
+  const int warp = pw >= 8 ? pw - 8 : pw + 4;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1;
