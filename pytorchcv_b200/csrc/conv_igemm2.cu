@@ -20,6 +20,8 @@
 
 namespace pcv {
 
+constexpr int NUM_THREADS2 = 384;   // 4 control warps (physical warps 8-11) + 8 epilogue warps
+
 template <int BN>
 struct Pair {
   static constexpr int HALF_N = BN / 2;
@@ -40,7 +42,7 @@ struct Pair {
 };
 
 template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
               const IgemmParams p) {
@@ -65,7 +67,8 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   // producer, MMA issuer, staging manager) take the HIGH warp ids 4-7 and the four epilogue warps the low ids 0-3
   // (TMEM lane quarter = physical warp id & 3 either way).  `warp` below is the ROLE index: 0 producer, 1 MMA,
   // 2 TMEM allocator, 3 staging manager, 4-7 epilogue.
-  const int warp = ((threadIdx.x >> 5) + 4) & 7;
+  const int pw = threadIdx.x >> 5;
+  const int warp = pw >= 8 ? pw - 8 : pw + 4;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();        // 0 = leader
   const int pair = blockIdx.x >> 1;
@@ -86,12 +89,12 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
+      mbar_init(&tmem_empty[i], 16);   // 8 epilogue warps x 2 CTAs
     }
     for (int i = 0; i < NSTG; ++i) {
       mbar_init(&stg_free[i], 1);
       mbar_init(&res_full[i], 1);
-      mbar_init(&stg_full[i], 4);
+      mbar_init(&stg_full[i], 8);
     }
     fence_mbar_init();
   }
@@ -255,6 +258,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else if (warp >= 4) {
     // ===================================== epilogue (both CTAs) =====================================
     const int q = warp & 3;
+    const int half = (warp - 4) >> 2;   // eight epilogue warps: (lane quarter, 32-column half)
     const int row = q * 32 + lane;
     const float act_lo = p.act_lo, act_hi = p.act_hi;
     const bool fancy_act = p.act > PCV_ACT_RELU6;
@@ -279,8 +283,8 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         // the slot is ready when its residual has landed (which implies the previous store has left it) or, without
         // a residual, when the staging manager has released it
         mbar_wait(p.has_res ? &res_full[slot] : &stg_free[slot], sphase);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        {
+          const int h = half;
           const int col = sub * L::SUB_COLS + h * 32;
           uint32_t acc[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + col, acc);
@@ -369,7 +373,7 @@ static cudaError_t launch_pair(int grid, const CUtensorMap& tmA, const CUtensorM
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  return launch_pdl(igemm2_kernel<BN>, dim3(grid), dim3(NUM_THREADS), L::bytes(p.stages, p.ksub, p.nstg), s, tmA, tmB, tmOut,
+  return launch_pdl(igemm2_kernel<BN>, dim3(grid), dim3(NUM_THREADS2), L::bytes(p.stages, p.ksub, p.nstg), s, tmA, tmB, tmOut,
                     tmRes, p);
 }
 
