@@ -193,8 +193,7 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int q4 = warp & 3;
     const int half = (warp - 4) >> 2;
     const int row = q4 * 32 + lane;
-    const uint32_t lo2 = pack_bf16x2(p.act_lo, p.act_lo), hi2 = pack_bf16x2(p.act_hi, p.act_hi);
-    const bool clamp_lo = p.act_lo > -INFINITY, clamp_hi = p.act_hi < INFINITY;
+    const float act_lo = p.act_lo, act_hi = p.act_hi;
     const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
     int it = 0;
@@ -222,16 +221,17 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           tmem_ld_wait();
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + j * 32);
           uint32_t o[16];
+          // scalar fp32 math on purpose: packing the tcgen05.ld registers into 64-bit operands for add.f32x2 cost more
+          // instructions than it saved (measured on the igemm2 epilogue)
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 b = __ldg(bias4 + i);
-            const float2 v0 = add2(make_float2(__uint_as_float(acc[4 * i + 0]), __uint_as_float(acc[4 * i + 1])), make_float2(b.x, b.y));
-            const float2 v1 = add2(make_float2(__uint_as_float(acc[4 * i + 2]), __uint_as_float(acc[4 * i + 3])), make_float2(b.z, b.w));
-            uint32_t w0 = pack_bf16x2(v0.x, v0.y), w1 = pack_bf16x2(v1.x, v1.y);
-            if (clamp_lo) { w0 = hmax2_bf16(w0, lo2); w1 = hmax2_bf16(w1, lo2); }
-            if (clamp_hi) { w0 = hmin2_bf16(w0, hi2); w1 = hmin2_bf16(w1, hi2); }
-            o[2 * i + 0] = w0;
-            o[2 * i + 1] = w1;
+            const float v0 = fminf(fmaxf(__uint_as_float(acc[4 * i + 0]) + b.x, act_lo), act_hi);
+            const float v1 = fminf(fmaxf(__uint_as_float(acc[4 * i + 1]) + b.y, act_lo), act_hi);
+            const float v2 = fminf(fmaxf(__uint_as_float(acc[4 * i + 2]) + b.z, act_lo), act_hi);
+            const float v3 = fminf(fmaxf(__uint_as_float(acc[4 * i + 3]) + b.w, act_lo), act_hi);
+            o[2 * i + 0] = pack_bf16x2(v0, v1);
+            o[2 * i + 1] = pack_bf16x2(v2, v3);
           }
           if (ok) {
             uint4* d4 = reinterpret_cast<uint4*>(dst + j * 32);
