@@ -30,7 +30,8 @@ struct Igemm3Params {
   int out_pitch;
   int N, H, W, Cout;
   int R, PW, NMB;            // output rows per tile, padded width W+2, 128-row M-blocks per tile
-  int cblocks;               // Cin / 64
+  int cblocks;               // Cin / 64 (dense) or 1 (grouped: every 64-channel block is its own 64 -> 64 conv)
+  int G;                     // 64-channel group blocks (1 for dense); pair tiles iterate (spatial pair, g), g fastest
   int tiles_per_img, num_tiles;
   int NA;                    // A ring depth
   int a_buf_bytes;           // smem stride of one A buffer (multiple of 1024, includes the over-read slack)
@@ -56,7 +57,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I3_THREADS, 1)
 igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Igemm3Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int nb_blocks = 9 * p.cblocks;
+  const int nb_blocks = 9 * p.cblocks * p.G;
   uint8_t* sB = smem;                                         // resident weights: nb_blocks x [BN/2 x 128 B]
   uint8_t* sA = sB + ((nb_blocks * p.b_block_bytes + 1023) & ~1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sA + p.NA * p.a_buf_bytes);
@@ -75,7 +76,7 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1;
   const int npairs = gridDim.x >> 1;
-  const int pair_tiles = (p.num_tiles + 1) >> 1;
+  const int pair_tiles = ((p.num_tiles + 1) >> 1) * p.G;
   const int acc_cols = p.NMB * BN;               // TMEM columns of one accumulator buffer
   const uint32_t tmem_cols = 2 * acc_cols <= 256 ? 256u : 512u;
 
@@ -111,14 +112,17 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     {   // whole warp; TMA / mbarrier instructions under elect.sync (uniform-register operands)
       const uint32_t bfull_leader = mapa_u32(smem_u32(b_full), 0);
       if (rank == 0 && elect_one()) mbar_arrive_expect_tx(b_full, 2 * nb_blocks * p.b_block_bytes);
-      for (int b = 0; b < nb_blocks; ++b)
+      for (int b = 0; b < nb_blocks; ++b) {
+        const int g = b / (9 * p.cblocks), kb = b - g * 9 * p.cblocks;
         if (elect_one())
-          tma2_load_2d(&tmB, bfull_leader, sB + b * p.b_block_bytes, b * BLOCK_K, static_cast<int>(rank) * (BN / 2));
+          tma2_load_2d(&tmB, bfull_leader, sB + b * p.b_block_bytes, kb * BLOCK_K, g * BN + static_cast<int>(rank) * (BN / 2));
+      }
       pdl_wait();   // weights above do not depend on the previous kernel; the activations below do
       int slot = 0;
       uint32_t phase = 0;
       for (int t = pair; t < pair_tiles; t += npairs) {
-        int tile = 2 * t + static_cast<int>(rank);
+        const int sp = t / p.G, g = t - sp * p.G;
+        int tile = 2 * sp + static_cast<int>(rank);
         if (tile >= p.num_tiles) tile = p.num_tiles - 1;   // phantom tile of an odd tail: recompute the last one, stores masked
         const int img = tile / p.tiles_per_img;
         const int h0 = (tile - img * p.tiles_per_img) * p.R;
@@ -127,7 +131,7 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           const uint32_t full_leader = mapa_u32(smem_u32(&full[slot]), 0);
           if (elect_one()) {
             if (rank == 0) mbar_arrive_expect_tx(&full[slot], 2 * p.a_tx_bytes);
-            tma2_load_4d(&tmA, full_leader, sA + slot * p.a_buf_bytes, cb * BLOCK_K, -1, h0 - 1, img);
+            tma2_load_4d(&tmA, full_leader, sA + slot * p.a_buf_bytes, (g + cb) * BLOCK_K, -1, h0 - 1, img);
           }
           if (++slot == p.NA) {
             slot = 0;
@@ -157,6 +161,7 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = buf * acc_cols;     // TMEM base is 0: this CTA owns the SM's whole TMEM (checked above)
+        const int g = t % p.G;
         for (int cb = 0; cb < p.cblocks; ++cb) {
           mbar_wait(&full[slot], phase);
           tc_fence_after();
@@ -164,7 +169,7 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           int tap = 0;
           for (int fr = 0; fr < 3; ++fr) {
             for (int fs = 0; fs < 3; ++fs, ++tap) {
-              const uint32_t b_lo = b_lo0 + (tap * p.cblocks + cb) * b_step;
+              const uint32_t b_lo = b_lo0 + (g * 9 * p.cblocks + tap * p.cblocks + cb) * b_step;
               const uint32_t a_tap = a_buf + (fr * p.PW + fs) * (128 >> 4);
               const uint32_t acc = (cb | tap) != 0 ? 1u : 0u;
               for (int mb = 0; mb < p.NMB; ++mb) {
@@ -200,7 +205,8 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     for (int t = pair; t < pair_tiles; t += npairs, ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int tile = 2 * t + static_cast<int>(rank);
+      const int sp = t / p.G, g = t - sp * p.G;
+      const int tile = 2 * sp + static_cast<int>(rank);
       const bool tile_ok = tile < p.num_tiles;
       const int img = tile / p.tiles_per_img;
       const int h0 = (tile - img * p.tiles_per_img) * p.R;
@@ -213,13 +219,13 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const int r = q / p.PW;
         const int c = q - r * p.PW;
         const bool ok = tile_ok && c < p.W && r < p.R && (h0 + r) < p.H;
-        __nv_bfloat16* dst = p.out + (static_cast<size_t>(img * p.H + h0 + r) * p.W + c) * p.out_pitch;
+        __nv_bfloat16* dst = p.out + (static_cast<size_t>(img * p.H + h0 + r) * p.W + c) * p.out_pitch + g * BN;
 #pragma unroll 1
         for (int j = half; j < BN / 32; j += 2) {
           uint32_t acc[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * acc_cols + mb * BN + j * 32, acc);
           tmem_ld_wait();
-          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + j * 32);
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + g * BN + j * 32);
           uint32_t o[16];
           // scalar fp32 math on purpose: packing the tcgen05.ld registers into 64-bit operands for add.f32x2 cost more
           // instructions than it saved (measured on the igemm2 epilogue)
@@ -291,15 +297,20 @@ int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const 
     return !(e && e[0] == '0');
   }();
   const int in_pitch = pitch_or(d.in_pitch, d.Cin), out_pitch = pitch_or(d.out_pitch, d.Cout);
-  if (!enabled || res || d.kh != 3 || d.kw != 3 || d.stride != 1 || d.dil != 1 || d.pad != 1 || d.groups != 1 ||
-      d.flags != 0 || d.in_row_pitch != 0 || d.Cin % 64 != 0 || (d.Cout != 64 && d.Cout != 128) || in_pitch % 8 != 0 ||
-      out_pitch % 8 != 0 || d.W + 2 > 256 || d.W < 24 || d.act > PCV_ACT_RELU6 ||
+  const bool grouped = d.groups > 1;
+  if (grouped && (d.Cin != d.Cout || d.Cin % 64 != 0 || 64 % (d.Cin / d.groups) != 0)) return PCV_ERR_UNSUPPORTED;
+  if (!enabled || res || d.kh != 3 || d.kw != 3 || d.stride != 1 || d.dil != 1 || d.pad != 1 ||
+      d.flags != 0 || d.in_row_pitch != 0 || d.Cin % 64 != 0 || (!grouped && d.Cout != 64 && d.Cout != 128) ||
+      in_pitch % 8 != 0 || out_pitch % 8 != 0 || d.W + 2 > 256 || d.W < (grouped ? 14 : 24) || d.act > PCV_ACT_RELU6 ||
       reinterpret_cast<uintptr_t>(x) % 16 != 0 || reinterpret_cast<uintptr_t>(y) % 16 != 0 ||
       reinterpret_cast<uintptr_t>(w) % 16 != 0)
     return PCV_ERR_UNSUPPORTED;
-  const int BN = d.Cout, PW = d.W + 2, cblocks = d.Cin / 64;
+  // grouped (ResNeXt, resnext.py:44-55): every 64-channel block is an independent 64 -> 64 convolution with
+  // block-diagonal weights; all G blocks' weights stay resident
+  const int G = grouped ? d.Cin / 64 : 1;
+  const int BN = grouped ? 64 : d.Cout, PW = d.W + 2, cblocks = grouped ? 1 : d.Cin / 64;
   const int b_block = BN / 2 * 128;
-  const int b_bytes = round_up(9 * cblocks * b_block, 1024);
+  const int b_bytes = round_up(9 * cblocks * G * b_block, 1024);
   const int budget = 232448 - 1024 - 256 - b_bytes;
   if (budget <= 0) return PCV_ERR_UNSUPPORTED;
   // rows per tile: maximise (useful MMA rows) x (wave efficiency) among the tiles that fit
@@ -313,7 +324,7 @@ int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const 
     const int NA = std::min(I3_MAX_NA, budget / buf);
     if (NA < 2) continue;
     const int tiles = d.N * ceil_div(d.H, R);
-    const int pair_tiles = (tiles + 1) / 2;
+    const int pair_tiles = (tiles + 1) / 2 * G;
     const double wave = static_cast<double>(pair_tiles) / (ceil_div(pair_tiles, pairs) * pairs);
     const double rows = static_cast<double>(d.H) * d.W / (static_cast<double>(ceil_div(d.H, R)) * NMB * BLOCK_M);
     const double halo = static_cast<double>(R) / (R + 2);
@@ -331,7 +342,7 @@ int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const 
   p.out = reinterpret_cast<__nv_bfloat16*>(y);
   p.out_pitch = out_pitch;
   p.N = d.N; p.H = d.H; p.W = d.W; p.Cout = d.Cout;
-  p.R = bestR; p.PW = PW; p.NMB = bestNMB; p.cblocks = cblocks;
+  p.R = bestR; p.PW = PW; p.NMB = bestNMB; p.cblocks = cblocks; p.G = G;
   p.tiles_per_img = ceil_div(d.H, bestR);
   p.num_tiles = d.N * p.tiles_per_img;
   p.NA = bestNA;
@@ -342,7 +353,7 @@ int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const 
   p.act_hi = d.act == PCV_ACT_RELU6 ? 6.f : INFINITY;
   op->bn = BN;
   op->smem_bytes = 1024 + b_bytes + bestNA * best_buf + 256;
-  op->grid = 2 * std::min((p.num_tiles + 1) / 2, pairs);
+  op->grid = 2 * std::min((p.num_tiles + 1) / 2 * G, pairs);
 
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -357,7 +368,7 @@ int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const 
     if (r != CUDA_SUCCESS) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled (halo A) failed (%d)", (int)r);
   }
   {
-    const uint64_t kpad = 9ull * cblocks * BLOCK_K;
+    const uint64_t kpad = 9ull * cblocks * BLOCK_K;   // grouped: [Cout, 9 * 64] block-diagonal rows
     cuuint64_t dims[2] = {kpad, (cuuint64_t)d.Cout};
     cuuint64_t strides[1] = {kpad * 2};
     cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)(BN / 2)};
@@ -368,12 +379,12 @@ int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const 
     if (r != CUDA_SUCCESS) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled (halo B) failed (%d)", (int)r);
   }
   char nm[160];
-  snprintf(nm, sizeof nm, "conv_tc3 3x3 s1 d1 g1 %d->%d @%dx%d bn=%d halo R=%d mb=%d na=%d", d.Cin, d.Cout, d.H, d.W, BN,
-           bestR, bestNMB, bestNA);
+  snprintf(nm, sizeof nm, "conv_tc3 3x3 s1 d1 g%d %d->%d @%dx%d bn=%d halo R=%d mb=%d na=%d", d.groups, d.Cin, d.Cout, d.H,
+           d.W, BN, bestR, bestNMB, bestNA);
   op->name = nm;
   const double M = static_cast<double>(d.N) * d.H * d.W;
-  op->flops = 2.0 * M * d.Cout * d.Cin * 9;
-  op->bytes = 2.0 * d.N * d.Cin * d.H * d.W + 2.0 * M * d.Cout + 2.0 * d.Cout * d.Cin * 9 + 4.0 * d.Cout;
+  op->flops = 2.0 * M * d.Cout * (d.Cin / d.groups) * 9;
+  op->bytes = 2.0 * d.N * d.Cin * d.H * d.W + 2.0 * M * d.Cout + 2.0 * d.Cout * (d.Cin / d.groups) * 9 + 4.0 * d.Cout;
   *out = op.release();
   return PCV_OK;
 }

@@ -48,6 +48,9 @@ CASES = [
     ("halo3x3_64_128_ragged",     3, 30, 26,  64, 128, 3, 1, 1, 1, 1, 0, 0, 0, "bf16"),
     ("halo3x3_128_64_relu6",      2, 41, 33, 128,  64, 3, 1, 1, 1, 1, 2, 0, 0, "bf16"),
     ("halo3x3_256_64_wide",       1, 24, 120, 256, 64, 3, 1, 1, 1, 1, 1, 0, 0, "bf16"),
+    ("halo_grouped_g32_c128_56",  2, 56, 56, 128, 128, 3, 1, 1, 1, 32, 1, 0, 0, "bf16"),
+    ("halo_grouped_g32_c256_28",  3, 28, 28, 256, 256, 3, 1, 1, 1, 32, 1, 0, 0, "bf16"),
+    ("halo_grouped_g4_c128_ragged", 3, 16, 14, 128, 128, 3, 1, 1, 1, 4, 2, 0, 0, "bf16"),
     ("simt_bf16_3x3",             2, 14, 14,  64,  64, 3, 1, 1, 1, 1, 1, 1, 2, "bf16"),
     ("simt_f32_3x3",              2, 14, 14,  64,  64, 3, 1, 1, 1, 1, 1, 1, 0, "fp32"),
     ("simt_f32_7x7_c3",           2, 64, 64,   3,  64, 7, 2, 3, 1, 1, 1, 0, 0, "fp32"),
