@@ -531,6 +531,10 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   std::string why;
   if (!igemm_supported(d, &why)) return fail(PCV_ERR_UNSUPPORTED, "tcgen05 conv: %s", why.c_str());
   {
+    const int rcs = stem_halo_try_make(d, x, w, bias, res, y, out);   // s2d stem with a 32-byte-row halo tile
+    if (rcs != PCV_ERR_UNSUPPORTED) return rcs;
+  }
+  {
     const int rc3 = igemm3_try_make(d, x, w, bias, res, y, out);   // 3x3 stride-1 layers with a smem halo tile
     if (rc3 != PCV_ERR_UNSUPPORTED) return rc3;
   }

@@ -54,6 +54,10 @@ cudaError_t launch_igemm2(int bn, int grid, const CUtensorMap& tmA, const CUtens
 int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const float* bias, const void* res, void* y,
                     Op** out);
 
+// conv_igemm3s.cu: space-to-depth stem (PCV_CONV_IN_OVERLAP view of 16-channel s2d pixels) with a 32-byte-row halo tile
+int stem_halo_try_make(const pcv_conv_desc& d, const void* x, const void* w, const float* bias, const void* res,
+                       void* y, Op** out);
+
 void igemm2_pick_smem(int bn, int num_kblocks, bool has_res, int taps, int* stages, int* ksub, int* nstg);
 
 }  // namespace pcv

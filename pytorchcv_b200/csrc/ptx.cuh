@@ -110,6 +110,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                "r"(smem_u32(src)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
@@ -196,6 +202,22 @@ __device__ __forceinline__ void umma2_bf16_lohi_a(uint32_t d_tmem, uint32_t a_lo
       "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
       "}\n" ::"r"(d_tmem),
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(SMEM_DESC_HI_SW128), "r"(a_hi)
+      : "memory");
+}
+// cta_group::2 MMA with one explicit high descriptor word shared by A and B (layouts other than SWIZZLE_128B)
+constexpr uint32_t SMEM_DESC_HI_SW32 = (256u >> 4) | (1u << 14) | (6u << 29);   // SBO=256 B, version 1, SWIZZLE_32B
+__device__ __forceinline__ void umma2_bf16_lohi_h(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                  uint32_t accumulate, uint32_t hi) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(hi)
       : "memory");
 }
 // mbarrier arrive once every previously issued tcgen05.mma of this thread has completed.

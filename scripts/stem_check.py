@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Isolated parity + op-name check of the space-to-depth stem kernel (conv_igemm3s.cu) through the mirror blocks.
+Each case runs in a child process with a timeout so a hung mbarrier pipeline cannot take the box down."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+CASES = [  # name, k, Cout, act, N, H, W
+    ("stem7_64_small", 7, 64, "relu", 3, 64, 64),
+    ("stem7_64_224", 7, 64, "relu", 2, 224, 224),
+    ("stem3_32_relu6_224", 3, 32, "relu6", 2, 224, 224),
+    ("stem3_64_480", 3, 64, "relu", 1, 480, 480),
+    ("stem3_32_ragged", 3, 32, "relu", 3, 50, 38),
+    ("stem7_64_ragged", 7, 64, "relu", 5, 38, 50),
+    ("stem5_64", 5, 64, "relu", 2, 96, 96),
+]
+
+
+def run(idx):
+    import torch
+    import torch.nn.functional as F
+    import pytorchcv_b200 as P
+    from pytorchcv_b200 import blocks
+    from oracle import seeded_init, seeded_input
+    name, k, cout, act, N, H, W = CASES[idx]
+    blk = blocks.ConvBlock(in_channels=3, out_channels=cout, kernel_size=k, stride=2, padding=k // 2,
+                           activation=(lambda: torch.nn.ReLU6(inplace=True)) if act == "relu6" else (lambda: torch.nn.ReLU(inplace=True)))
+    blk = seeded_init(blk.eval(), seed=3, randomize_bn=True)
+    x = seeded_input((N, 3, H, W), seed=5)
+    bn = blk.bn
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    rnd = lambda t: t.to(torch.bfloat16).float()
+    wf = rnd(blk.conv.weight * scale.view(-1, 1, 1, 1))
+    bf = bn.bias - bn.running_mean * scale
+    with torch.no_grad():
+        ref = F.conv2d(rnd(x), wf, bf, stride=2, padding=k // 2)
+        ref = ref.clamp(0, 6) if act == "relu6" else torch.relu(ref)
+    fast = P.accelerate(blk.cuda(), dtype="bf16", graph=False)
+    y = fast(x.cuda()).float().cpu()
+    torch.cuda.synchronize()
+    cm = fast.compiled(x.cuda())
+    names = [r[0] for r in cm.profile()]
+    rel = float((y - ref).abs().max() / ref.abs().max())
+    out = {"case": name, "rel": rel, "ok": bool(rel <= 1.2e-2 and torch.isfinite(y).all()), "ops": names}
+    if not out["ok"]:
+        err = (y - ref).abs() > 1.2e-2 * ref.abs().max()
+        out["bad_frac"] = float(err.float().mean())
+        out["bad_by_channel"] = [round(v, 2) for v in err.float().mean(dim=(0, 2, 3))[:16].tolist()]
+        out["bad_by_row"] = [round(v, 2) for v in err.float().mean(dim=(0, 1, 3))[:16].tolist()]
+        out["bad_by_col"] = [round(v, 2) for v in err.float().mean(dim=(0, 1, 2))[:16].tolist()]
+        out["got"] = [round(v, 3) for v in y[0, :6, 0, 0].tolist()]
+        out["ref"] = [round(v, 3) for v in ref[0, :6, 0, 0].tolist()]
+    return out
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        print(json.dumps(run(int(sys.argv[1]))), flush=True)
+        sys.exit(0)
+    fails = 0
+    for i, c in enumerate(CASES):
+        try:
+            r = subprocess.run([sys.executable, "-u", __file__, str(i)], capture_output=True, text=True, timeout=150)
+            line = (r.stdout.strip().splitlines() or ["{}"])[-1]
+            print(c[0], "rc", r.returncode, line[:900], flush=True)
+            if r.returncode != 0:
+                print(r.stderr[-800:], flush=True)
+                fails += 1
+            elif not json.loads(line).get("ok"):
+                fails += 1
+        except subprocess.TimeoutExpired:
+            print(c[0], "TIMEOUT", flush=True)
+            fails += 1
+    print("stem_check fails:", fails)
