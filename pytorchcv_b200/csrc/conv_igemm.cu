@@ -596,6 +596,27 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
     igemm2_pick_smem(op->bn, p.num_kblocks, res != nullptr, taps, &p.stages, &p.ksub, &p.nstg);
   }
   p.tiles_n = ceil_div(d.Cout, op->bn);
+  p.nsubs = 1;
+  int b_box_rows = op->bn;
+  if (op->pair) {
+    // tile width = nsubs * 64 <= BN: the candidate that pads ceil(Cout/64) the least (ties -> the widest)
+    const int units = ceil_div(d.Cout, 64), maxns = op->bn / 64;
+    int best = maxns, bestpad = 1 << 30;
+    for (int ns = maxns; ns >= std::max(1, maxns / 2); --ns) {
+      const int pad = ceil_div(units, ns) * ns;
+      if (pad < bestpad) {
+        best = ns;
+        bestpad = pad;
+      }
+    }
+    static const bool narrow = [] {
+      const char* e = getenv("PCV_IGEMM2_NARROW");
+      return !(e && e[0] == '0');
+    }();
+    p.nsubs = (narrow && !grouped) ? best : maxns;
+    p.tiles_n = ceil_div(d.Cout, p.nsubs * 64);
+    b_box_rows = p.nsubs * 32;   // each CTA of the pair loads half of the tile's weight rows
+  }
 
   int rc;
   if (p.a_mode == 1) {
@@ -605,8 +626,7 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   }
   if (rc) return rc;
   const uint64_t kpad = (uint64_t)taps * p.cblocks * BLOCK_K;
-  rc = make_tiled_2d(&op->tmB, w, kpad, d.Cout, kpad * 2, BLOCK_K, op->pair ? op->bn / 2 : op->bn,
-                     CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = make_tiled_2d(&op->tmB, w, kpad, d.Cout, kpad * 2, BLOCK_K, b_box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   const int sub_cols = op->bn >= 64 ? 64 : op->bn;
   const CUtensorMapSwizzle oswz = sub_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -628,7 +648,10 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
 
   char nm[160];
   char cfg[48] = "";
-  if (op->pair) snprintf(cfg, sizeof cfg, " st%dx%d/%d", p.stages, p.ksub, p.nstg);
+  if (op->pair) {
+    if (p.nsubs * 64 != op->bn) snprintf(cfg, sizeof cfg, " tw=%d st%dx%d/%d", p.nsubs * 64, p.stages, p.ksub, p.nstg);
+    else snprintf(cfg, sizeof cfg, " st%dx%d/%d", p.stages, p.ksub, p.nstg);
+  }
   snprintf(nm, sizeof nm, "conv_tc%s %dx%d s%d d%d g%d %d->%d @%dx%d bn=%d%s%s%s", op->pair ? "2" : "", d.kh, d.kw,
            d.stride, d.dil, d.groups, d.Cin, d.Cout, d.H, d.W, op->bn, cfg, res ? " +res" : "",
            p.out_mode ? " direct" : "");

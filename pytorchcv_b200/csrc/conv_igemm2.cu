@@ -16,20 +16,26 @@
 //   * the epilogue's staging ring works on 64-column sub-tiles (16 KB): residual TMA load -> math -> TMA store per
 //     sub-tile, NSTG slots, up to PENDING stores in flight, so the residual of sub-tile u+NSTG-PENDING is prefetched
 //     while sub-tile u is computed and no per-tile bubble remains.
+//   * the tile width is NS*64 <= BN output columns (template parameter, chosen per layer on the host so that
+//     ceil(Cout/64) splits into equal tiles): Cout = 144 runs as ONE 192-wide tile (N = 192 MMAs, 3 epilogue rounds), not
+//     as a 256-wide tile with a quarter of the epilogue work spent on padding columns; 576 = 3 x 192, 960 = 5 x 192.
+//     BN only sizes the shared-memory stages and the TMEM double buffer.
 #include "igemm_common.cuh"
 
 namespace pcv {
 
 constexpr int NUM_THREADS2 = 384;   // 4 control warps (physical warps 8-11) + 8 epilogue warps
 
-template <int BN>
+template <int BN, int NS = BN / 64>
 struct Pair {
-  static constexpr int HALF_N = BN / 2;
-  static constexpr int B_STAGE_BYTES = HALF_N * BLOCK_K * 2;
+  static constexpr int TW = NS * 64;                        // tile width in output columns (<= BN)
+  static constexpr int HALF_N = TW / 2;                     // weight rows each CTA of the pair loads per K block
+  static constexpr int B_STAGE_BYTES = (BN / 2) * BLOCK_K * 2;   // stage stride (sized for the full width)
+  static constexpr int B_TX_BYTES = HALF_N * BLOCK_K * 2;        // bytes one weight box really delivers
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int SUB_COLS = 64;
   static constexpr int SUB_BYTES = BLOCK_M * SUB_COLS * 2;  // 16 KiB
-  static constexpr int NSUB = BN / SUB_COLS;                // sub-tiles per output tile
+  static constexpr int NSUB = NS;                           // sub-tiles per output tile
   static constexpr int MAX_STAGES = 8, MAX_NSTG = 8;
   static constexpr int NUM_BARS = 2 * MAX_STAGES + 4 + 3 * MAX_NSTG;
   static constexpr uint32_t TMEM_COLS = 2 * BN;             // double-buffered accumulator (256 or 512 columns)
@@ -41,12 +47,13 @@ struct Pair {
   }
 };
 
-template <int BN>
+template <int BN, int NS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
               const IgemmParams p) {
-  using L = Pair<BN>;
+  using L = Pair<BN, NS>;
+  constexpr int TW = L::TW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int STAGES = p.stages, NSTG = p.nstg, KSUB = p.ksub;
@@ -131,8 +138,8 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const int wo = rem - ho * p.Wo;
         const int w0 = wo * p.stride - p.pad;
         const int h0 = ho * p.stride - p.pad;
-        const int b_row = n_tile * BN + static_cast<int>(rank) * L::HALF_N;
-        const int c_base = p.grouped ? n_tile * BN : 0;
+        const int b_row = n_tile * TW + static_cast<int>(rank) * L::HALF_N;
+        const int c_base = p.grouped ? n_tile * TW : 0;
         int cb = 0, fr = 0, fs = 0;
         for (int kb = 0; kb < p.num_kblocks; kb += KSUB) {
           const int nsub = min(KSUB, p.num_kblocks - kb);
@@ -140,7 +147,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
           // only the leader arrives; the peer's bytes may land first (tx-count goes negative, the phase cannot
           // complete before the leader's arrival), exactly the CUTLASS 2-SM pipeline protocol
-          if (rank == 0 && elect_one()) mbar_arrive_expect_tx(&full[stage], 2 * nsub * L::STAGE_BYTES);
+          if (rank == 0 && elect_one()) mbar_arrive_expect_tx(&full[stage], 2 * nsub * (A_STAGE_BYTES + L::B_TX_BYTES));
           uint8_t* a_dst = sA + stage * KSUB * A_STAGE_BYTES;
           uint8_t* b_dst = sB + stage * KSUB * L::B_STAGE_BYTES;
           for (int j = 0; j < nsub; ++j) {
@@ -173,7 +180,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else if (warp == 1) {
     // ===================================== MMA issuer (leader CTA only) =====================================
     if (rank == 0) {   // whole warp (see the producer's note); tcgen05 instructions under elect.sync
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BN);
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, TW);
       const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA)), b_lo0 = smem_desc_lo(smem_u32(sB));
       int stage = 0;
       uint32_t phase = 0;
@@ -221,7 +228,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const int t = pair + (r / L::NSUB) * npairs;
       const int pm = t / p.tiles_n;
       const int n_tile = t - pm * p.tiles_n;
-      col0 = n_tile * BN + (r % L::NSUB) * L::SUB_COLS;
+      col0 = n_tile * TW + (r % L::NSUB) * L::SUB_COLS;
       row0 = (2 * pm + static_cast<int>(rank)) * BLOCK_M;
     };
     auto refill = [&](int r) {   // slot of round r is free: fetch its residual, or tell the epilogue it may write
@@ -272,7 +279,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const uint32_t acc_phase = (it >> 1) & 1;
       const int pm = t / p.tiles_n;
       const int n_tile = t - pm * p.tiles_n;
-      const int n0 = n_tile * BN;
+      const int n0 = n_tile * TW;
 
       mbar_wait(&tmem_full[buf], acc_phase);
       tc_fence_after();
@@ -363,17 +370,17 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   }
 }
 
-template <int BN>
+template <int BN, int NS>
 static cudaError_t launch_pair(int grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                                const CUtensorMap& tmRes, const IgemmParams& p, cudaStream_t s) {
-  using L = Pair<BN>;
+  using L = Pair<BN, NS>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_LIMIT);
+    cudaError_t e = cudaFuncSetAttribute(igemm2_kernel<BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_LIMIT);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  return launch_pdl(igemm2_kernel<BN>, dim3(grid), dim3(NUM_THREADS2), L::bytes(p.stages, p.ksub, p.nstg), s, tmA, tmB, tmOut,
+  return launch_pdl(igemm2_kernel<BN, NS>, dim3(grid), dim3(NUM_THREADS2), L::bytes(p.stages, p.ksub, p.nstg), s, tmA, tmB, tmOut,
                     tmRes, p);
 }
 
@@ -413,9 +420,12 @@ void igemm2_pick_smem(int bn, int num_kblocks, bool has_res, int taps, int* stag
 cudaError_t launch_igemm2(int bn, int grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                           const CUtensorMap& tmRes, const IgemmParams& p, cudaStream_t s) {
   switch (bn) {
-    case 256: return launch_pair<256>(grid, tmA, tmB, tmOut, tmRes, p, s);
-    case 128: return launch_pair<128>(grid, tmA, tmB, tmOut, tmRes, p, s);
-    default: return launch_pair<64>(grid, tmA, tmB, tmOut, tmRes, p, s);
+    case 256:
+      if (p.nsubs == 3) return launch_pair<256, 3>(grid, tmA, tmB, tmOut, tmRes, p, s);
+      if (p.nsubs == 2) return launch_pair<256, 2>(grid, tmA, tmB, tmOut, tmRes, p, s);
+      return launch_pair<256, 4>(grid, tmA, tmB, tmOut, tmRes, p, s);
+    case 128: return launch_pair<128, 2>(grid, tmA, tmB, tmOut, tmRes, p, s);
+    default: return launch_pair<64, 1>(grid, tmA, tmB, tmOut, tmRes, p, s);
   }
 }
 

@@ -29,6 +29,7 @@ struct IgemmParams {
   int grouped;                // 1: A channel window = n_tile*BLOCK_N (block-diagonal weights)
   int dbg;                    // PCV_IGEMM_DBG: bit0 skip operand TMA, bit1 skip MMA issue (throughput experiments)
   int stages, ksub, nstg;     // CTA-pair kernel: ring depth / 64-K sub-blocks per stage / staging slots (per layer)
+  int nsubs;                  // CTA-pair kernel: 64-column sub-tiles per tile (tile width = nsubs*64 <= BN), per layer
 };
 
 // Rare activations (sigmoid / swish / h-swish / h-sigmoid): kept out of line so the hot epilogue stays compact —

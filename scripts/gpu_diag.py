@@ -57,6 +57,15 @@ CASES = [
     ("simt_f32_grouped",          2, 14, 14, 128, 128, 3, 1, 1, 1, 32, 1, 0, 0, "fp32"),
     ("dw3x3_s1_bf16",             2, 28, 28, 144, 144, 3, 1, 1, 1, 144, 2, 0, 0, "bf16"),
     ("dw3x3_s2_bf16",             2, 28, 28,  96,  96, 3, 2, 1, 1, 96, 2, 0, 0, "bf16"),
+    # segment schedule of the CTA-pair kernel (conv_igemm2.cu::decode_seg): sub-tiles beyond Cout skipped, tail split along N
+    ("seg_cout144_bn256",         4, 56, 56,  24, 144, 1, 1, 0, 1, 1, 2, 0, 0, "bf16"),
+    ("seg_cout96_half_skip",      3, 56, 56,  16,  96, 1, 1, 0, 1, 1, 2, 0, 0, "bf16"),
+    ("seg_cout320_tail_empty",    5, 14, 14, 960, 320, 1, 1, 0, 1, 1, 0, 0, 0, "bf16"),
+    ("seg_tail2_98tiles",       128, 14, 14, 256, 256, 3, 1, 1, 1, 1, 1, 0, 0, "bf16"),
+    ("seg_tail4_res",            41, 14, 14, 128, 256, 1, 1, 0, 1, 1, 1, 1, 0, "bf16"),
+    ("seg_tail2_res_multi_n",    25, 14, 14, 256, 1024, 1, 1, 0, 1, 1, 1, 1, 0, "bf16"),
+    ("seg_cout576_tail",         37, 14, 14,  96, 576, 1, 1, 0, 1, 1, 2, 0, 0, "bf16"),
+    ("seg_bn128_tail",           30, 28, 28, 512, 128, 1, 1, 0, 1, 1, 1, 0, 0, "bf16"),
     ("dw5x5_s1_bf16",             2, 14, 14,  96,  96, 5, 1, 2, 1, 96, 2, 0, 0, "bf16"),
     ("dw3x3_s1_f32",              2, 28, 28,  32,  32, 3, 1, 1, 1, 32, 2, 1, 0, "fp32"),
     ("dw3x3_s1_c32_112",          2, 112, 112, 32,  32, 3, 1, 1, 1, 32, 2, 0, 0, "bf16"),
