@@ -20,6 +20,13 @@
 // (9 * Cin/64 blocks of [BN/2 x 64]).  Roles per CTA: warp 0 producer (weights once, then one A box per 64-channel
 // block into a ring), warp 1 MMA issuer (leader CTA only), warp 2 TMEM allocator, warps 4-7 epilogue
 // (tcgen05.ld -> +bias -> clamp -> bf16 -> direct 64-byte-per-thread global stores; garbage columns masked).
+//
+// Output path (measured with the PCV_IGEMM3_DBG knobs, profiles/README.md): with BN = 64 the MMA is bound by the
+// shared-memory operand read rate (A 4 KB + B 1 KB per 32-cycle MMA), and a direct epilogue - one pixel per thread, so
+// every STG.128 touches 32 different 128-byte lines - costs the same L1/shared-memory port ~128 cycles per warp
+// instruction: MMA-only 0.063 ms, epilogue-only 0.060 ms, together 0.089 ms.  STAGED = true stages the tile in shared
+// memory as R image rows of round_up(W, 8) swizzled pixel rows and writes each image row with one 4-D TMA store
+// (garbage columns never staged), double-buffered; used for BN = 64 whenever the staging buffers fit.
 #include "igemm_common.cuh"
 
 namespace pcv {
@@ -37,7 +44,9 @@ struct Igemm3Params {
   int a_buf_bytes;           // smem stride of one A buffer (multiple of 1024, includes the over-read slack)
   int a_tx_bytes;            // bytes of one A box: (R+2) * PW * 128
   int b_block_bytes;         // BN/2 * 128
+  int WP8, stg_bytes;        // STAGED: pixels per staged image row (W rounded up to 8), bytes of one staging buffer
   float act_lo, act_hi;
+  int dbg;                   // PCV_IGEMM3_DBG throughput experiments: 1 skip MMA issue, 2 skip epilogue math+stores, 4 skip A loads
 };
 
 __device__ __forceinline__ void tma2_load_4d(const CUtensorMap* m, uint32_t mbar_cluster_addr, void* dst, int c0,
@@ -52,15 +61,17 @@ __device__ __forceinline__ void tma2_load_4d(const CUtensorMap* m, uint32_t mbar
 constexpr int I3_MAX_NA = 6;
 constexpr int I3_THREADS = 384;   // 4 control warps + 8 epilogue warps
 
-template <int BN>
+template <int BN, bool STAGED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I3_THREADS, 1)
-igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Igemm3Params p) {
+igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const __grid_constant__ CUtensorMap tmOut, const Igemm3Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nb_blocks = 9 * p.cblocks * p.G;
   uint8_t* sB = smem;                                         // resident weights: nb_blocks x [BN/2 x 128 B]
   uint8_t* sA = sB + ((nb_blocks * p.b_block_bytes + 1023) & ~1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + p.NA * p.a_buf_bytes);
+  uint8_t* sStg = sA + p.NA * p.a_buf_bytes;                  // STAGED: 2 output staging buffers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + (STAGED ? 2 * p.stg_bytes : 0));
   uint64_t* full = bars;                         // [NA]  leader's copy is live
   uint64_t* empty = bars + I3_MAX_NA;            // [NA]  per CTA, multicast commit
   uint64_t* b_full = bars + 2 * I3_MAX_NA;       // [1]   leader's copy
@@ -83,6 +94,7 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (STAGED) tma_prefetch_desc(&tmOut);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.NA; ++i) {
@@ -130,8 +142,12 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           mbar_wait(&empty[slot], phase ^ 1);
           const uint32_t full_leader = mapa_u32(smem_u32(&full[slot]), 0);
           if (elect_one()) {
-            if (rank == 0) mbar_arrive_expect_tx(&full[slot], 2 * p.a_tx_bytes);
-            tma2_load_4d(&tmA, full_leader, sA + slot * p.a_buf_bytes, (g + cb) * BLOCK_K, -1, h0 - 1, img);
+            if (p.dbg & 4) {
+              if (rank == 0) mbar_arrive(&full[slot]);
+            } else {
+              if (rank == 0) mbar_arrive_expect_tx(&full[slot], 2 * p.a_tx_bytes);
+              tma2_load_4d(&tmA, full_leader, sA + slot * p.a_buf_bytes, (g + cb) * BLOCK_K, -1, h0 - 1, img);
+            }
           }
           if (++slot == p.NA) {
             slot = 0;
@@ -167,7 +183,7 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           tc_fence_after();
           const uint32_t a_buf = a_lo0 + slot * (p.a_buf_bytes >> 4);
           int tap = 0;
-          for (int fr = 0; fr < 3; ++fr) {
+          for (int fr = 0; fr < ((p.dbg & 1) ? 0 : 3); ++fr) {
             for (int fs = 0; fs < 3; ++fs, ++tap) {
               const uint32_t b_lo = b_lo0 + (g * 9 * p.cblocks + tap * p.cblocks + cb) * b_step;
               const uint32_t a_tap = a_buf + (fr * p.PW + fs) * (128 >> 4);
@@ -201,10 +217,12 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const float act_lo = p.act_lo, act_hi = p.act_hi;
     const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
+    const bool storer = STAGED && warp == 4 && lane == 0;   // owns every bulk store group of this CTA
     int it = 0;
     for (int t = pair; t < pair_tiles; t += npairs, ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      uint8_t* stg = sStg + (STAGED ? buf * p.stg_bytes : 0);   // free: see the wait before named barrier 1 below
       const int sp = t / p.G, g = t - sp * p.G;
       const int tile = 2 * sp + static_cast<int>(rank);
       const bool tile_ok = tile < p.num_tiles;
@@ -214,7 +232,7 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       mbar_wait(&tmem_full[buf], acc_phase);
       tc_fence_after();
 
-      for (int mb = 0; mb < p.NMB; ++mb) {
+      for (int mb = 0; mb < ((p.dbg & 2) ? 0 : p.NMB); ++mb) {
         const int q = mb * BLOCK_M + row;
         const int r = q / p.PW;
         const int c = q - r * p.PW;
@@ -240,9 +258,18 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             o[2 * i + 1] = pack_bf16x2(v2, v3);
           }
           if (ok) {
-            uint4* d4 = reinterpret_cast<uint4*>(dst + j * 32);
+            if (STAGED) {
+              const uint32_t srow = r * p.WP8 + c;   // staged pixel index; staged image rows start on 1024-byte boundaries
+              uint8_t* dstp = stg + srow * (BN * 2);
+              const uint32_t sw = srow & 7u;         // SWIZZLE_128B chunk XOR (BN = 64: one 128-byte row per pixel)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) d4[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+              for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<uint4*>(dstp + (((j * 4 + i) ^ sw) << 4)) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            } else {
+              uint4* d4 = reinterpret_cast<uint4*>(dst + j * 32);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) d4[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            }
           }
         }
       }
@@ -252,7 +279,18 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         if (rank == 0) mbar_arrive(&tmem_empty[buf]);
         else mbar_arrive_cluster(buf ? tmem_empty_leader1 : tmem_empty_leader0);
       }
+      if (STAGED) {
+        fence_proxy_async_smem();                   // this thread's st.shared -> visible to the TMA (async proxy)
+        if (storer) tma_store_wait_read<0>();       // the previous tile's stores have left the OTHER buffer (next tile's)
+        named_bar_sync(1, 256);                     // all 8 epilogue warps: tile staged, other buffer free
+        if (storer && tile_ok) {
+          for (int r = 0; r < p.R; ++r)
+            if (h0 + r < p.H) tma_store_4d(&tmOut, stg + r * p.WP8 * (BN * 2), g * BN, 0, h0 + r, img);
+          tma_store_commit();
+        }
+      }
     }
+    if (storer) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -267,26 +305,29 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 // host side
 // ------------------------------------------------------------------------------------------------------------
 struct Igemm3Op : Op {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmOut;
   Igemm3Params p;
   int bn, grid, smem_bytes;
+  bool staged = false;
   cudaError_t launch(cudaStream_t s) override;
 };
 
-template <int BN>
+template <int BN, bool STAGED>
 static cudaError_t launch_i3(const Igemm3Op& op, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(igemm3_kernel<BN, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  return launch_pdl(igemm3_kernel<BN>, dim3(op.grid), dim3(I3_THREADS), op.smem_bytes, s, op.tmA, op.tmB, op.p);
+  return launch_pdl(igemm3_kernel<BN, STAGED>, dim3(op.grid), dim3(I3_THREADS), op.smem_bytes, s, op.tmA, op.tmB,
+                    op.tmOut, op.p);
 }
 
 cudaError_t Igemm3Op::launch(cudaStream_t s) {
   g_launches++;
-  return bn == 64 ? launch_i3<64>(*this, s) : launch_i3<128>(*this, s);
+  if (bn == 64) return staged ? launch_i3<64, true>(*this, s) : launch_i3<64, false>(*this, s);
+  return launch_i3<128, false>(*this, s);
 }
 
 // Returns PCV_ERR_UNSUPPORTED (message untouched) when the layer is outside this kernel's domain.
@@ -313,25 +354,36 @@ int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const 
   const int b_bytes = round_up(9 * cblocks * G * b_block, 1024);
   const int budget = 232448 - 1024 - 256 - b_bytes;
   if (budget <= 0) return PCV_ERR_UNSUPPORTED;
-  // rows per tile: maximise (useful MMA rows) x (wave efficiency) among the tiles that fit
+  // rows per tile: maximise (useful MMA rows) x (wave efficiency) among the tiles that fit; BN = 64 first tries to fit
+  // two output staging buffers as well (STAGED, see the header) and falls back to direct stores when no tile fits
+  static const bool stage_enabled = [] {
+    const char* e = getenv("PCV_IGEMM3_STAGED");
+    return !(e && e[0] == '0');
+  }();
   const int pairs = sm_count() / 2;
+  const int WP8 = round_up(d.W, 8);
   double best = 0.0;
-  int bestR = 0, bestNA = 0, bestNMB = 0, best_buf = 0;
-  for (int R = 1; R <= std::min(d.H, 32); ++R) {
-    const int Q = R * PW, NMB = ceil_div(Q, BLOCK_M);
-    if (2 * NMB * BN > 512 || R + 2 > 256) continue;
-    const int buf = round_up((NMB * BLOCK_M + 2 * PW + 2) * 128, 1024);
-    const int NA = std::min(I3_MAX_NA, budget / buf);
-    if (NA < 2) continue;
-    const int tiles = d.N * ceil_div(d.H, R);
-    const int pair_tiles = (tiles + 1) / 2 * G;
-    const double wave = static_cast<double>(pair_tiles) / (ceil_div(pair_tiles, pairs) * pairs);
-    const double rows = static_cast<double>(d.H) * d.W / (static_cast<double>(ceil_div(d.H, R)) * NMB * BLOCK_M);
-    const double halo = static_cast<double>(R) / (R + 2);
-    const double work = static_cast<double>(NMB) * cblocks * 36 * (BN / 2);   // tensor-pipe cycles per tile
-    const double score = wave * rows * (0.9 + 0.1 * halo) * work / (work + 500.0);  // ~500-cycle handshake per tile
-    if (score > best) {
-      best = score; bestR = R; bestNA = NA; bestNMB = NMB; best_buf = buf;
+  int bestR = 0, bestNA = 0, bestNMB = 0, best_buf = 0, best_stg = 0;
+  bool staged = false;
+  for (int pass = (BN == 64 && stage_enabled) ? 0 : 1; pass < 2 && bestR == 0; ++pass) {
+    staged = pass == 0;
+    for (int R = 1; R <= std::min(d.H, 32); ++R) {
+      const int Q = R * PW, NMB = ceil_div(Q, BLOCK_M);
+      if (2 * NMB * BN > 512 || R + 2 > 256) continue;
+      const int buf = round_up((NMB * BLOCK_M + 2 * PW + 2) * 128, 1024);
+      const int stg = staged ? round_up(R * WP8 * BN * 2, 1024) : 0;
+      const int NA = std::min(I3_MAX_NA, (budget - 2 * stg) / buf);
+      if (NA < 2) continue;
+      const int tiles = d.N * ceil_div(d.H, R);
+      const int pair_tiles = (tiles + 1) / 2 * G;
+      const double wave = static_cast<double>(pair_tiles) / (ceil_div(pair_tiles, pairs) * pairs);
+      const double rows = static_cast<double>(d.H) * d.W / (static_cast<double>(ceil_div(d.H, R)) * NMB * BLOCK_M);
+      const double halo = static_cast<double>(R) / (R + 2);
+      const double work = static_cast<double>(NMB) * cblocks * 36 * (BN / 2);   // tensor-pipe cycles per tile
+      const double score = wave * rows * (0.9 + 0.1 * halo) * work / (work + 500.0);  // ~500-cycle handshake per tile
+      if (score > best) {
+        best = score; bestR = R; bestNA = NA; bestNMB = NMB; best_buf = buf; best_stg = stg;
+      }
     }
   }
   if (bestR == 0) return PCV_ERR_UNSUPPORTED;
@@ -349,10 +401,17 @@ int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const 
   p.a_buf_bytes = best_buf;
   p.a_tx_bytes = (bestR + 2) * PW * 128;
   p.b_block_bytes = b_block;
+  p.WP8 = WP8;
+  p.stg_bytes = best_stg;
   p.act_lo = (d.act == PCV_ACT_RELU || d.act == PCV_ACT_RELU6) ? 0.f : -INFINITY;
   p.act_hi = d.act == PCV_ACT_RELU6 ? 6.f : INFINITY;
+  {
+    const char* e = getenv("PCV_IGEMM3_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   op->bn = BN;
-  op->smem_bytes = 1024 + b_bytes + bestNA * best_buf + 256;
+  op->staged = staged;
+  op->smem_bytes = 1024 + b_bytes + bestNA * best_buf + 2 * best_stg + 256;
   op->grid = 2 * std::min((p.num_tiles + 1) / 2 * G, pairs);
 
   EncodeTiledFn fn = encode_tiled_fn();
@@ -378,9 +437,20 @@ int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const 
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled (halo B) failed (%d)", (int)r);
   }
+  op->tmOut = op->tmB;
+  if (staged) {   // output rows leave through 4-D TMA stores: box = one image row (W pixels x 64 channels)
+    cuuint64_t dims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.N};
+    cuuint64_t strides[3] = {(cuuint64_t)out_pitch * 2, (cuuint64_t)d.W * out_pitch * 2, (cuuint64_t)d.H * d.W * out_pitch * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BN, (cuuint32_t)d.W, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(&op->tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled (halo out) failed (%d)", (int)r);
+  }
   char nm[160];
-  snprintf(nm, sizeof nm, "conv_tc3 3x3 s1 d1 g%d %d->%d @%dx%d bn=%d halo R=%d mb=%d na=%d", d.groups, d.Cin, d.Cout, d.H,
-           d.W, BN, bestR, bestNMB, bestNA);
+  snprintf(nm, sizeof nm, "conv_tc3 3x3 s1 d1 g%d %d->%d @%dx%d bn=%d halo R=%d mb=%d na=%d%s", d.groups, d.Cin, d.Cout, d.H,
+           d.W, BN, bestR, bestNMB, bestNA, staged ? " staged" : "");
   op->name = nm;
   const double M = static_cast<double>(d.N) * d.H * d.W;
   op->flops = 2.0 * M * d.Cout * (d.Cin / d.groups) * 9;
