@@ -60,7 +60,9 @@ enum pcv_conv_flags {
   PCV_CONV_OUT_F32 = 1,      /* bf16 tier only: store the result as fp32 (classifier logits) */
   PCV_CONV_FORCE_SIMT = 2,   /* bf16 tier only: use the CUDA-core kernel (cross-check for the tcgen05 path) */
   PCV_CONV_A_IM2COL = 4,     /* bf16 tier only: use the im2col TMA descriptor even for 1x1 stride-1 */
-  PCV_CONV_IN_OVERLAP = 8    /* x is an overlapping-window VIEW: in_pitch < Cin is allowed (space-to-depth stem) */
+  PCV_CONV_IN_OVERLAP = 8,   /* x is an overlapping-window VIEW: in_pitch < Cin is allowed (space-to-depth stem) */
+  PCV_CONV_POOL3S2 = 16      /* space-to-depth stem only: fuse the following MaxPool2d(3, stride 2, pad 1) (ResInitBlock,
+                                resnet.py:255-263); y is the POOLED map [N, Ho/2, Wo/2, Cout].  Ask pcv_stem_s2d_pool_ok first */
 };
 
 /* One ConvBlock (conv.py:204-286): y = act(BN(conv2d(x)) [+ residual]).  Square kernels, symmetric padding. */
@@ -141,6 +143,8 @@ PCV_API int pcv_nhwc_to_nchw_f32(pcv_plan* plan, int dtype, int N, int C, int H,
 PCV_API int pcv_stem_s2d_dims(int C, int H, int W, int k, int* rows, int* cols, int* cin_eq, int* taps_eq);
 PCV_API int pcv_stem_s2d_ingest(pcv_plan* plan, int N, int C, int H, int W, int k, const float* x, void* s2d,
                                 pcv_stream stream);
+/* 1 when the stem conv (C-channel HxW image, k x k stride 2 pad k/2, Cout channels) can run with PCV_CONV_POOL3S2. */
+PCV_API int pcv_stem_s2d_pool_ok(int C, int H, int W, int k, int Cout);
 PCV_API int pcv_stem_s2d_weights(int Cout, int C, int k, const float* w, float* w_eq, pcv_stream stream);
 
 /* F.interpolate(mode="bilinear", align_corners=True) (deeplabv3.py:53,86).  Output is NHWC `dtype` with

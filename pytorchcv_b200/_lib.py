@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("PCV_B200_LIB") or os.path.join(_HERE, "libpcv_b200.so
 
 BF16, F32 = 0, 1
 ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SIGMOID, ACT_SWISH, ACT_HSWISH, ACT_HSIGMOID = range(7)
-CONV_OUT_F32, CONV_FORCE_SIMT, CONV_A_IM2COL, CONV_IN_OVERLAP = 1, 2, 4, 8
+CONV_OUT_F32, CONV_FORCE_SIMT, CONV_A_IM2COL, CONV_IN_OVERLAP, CONV_POOL3S2 = 1, 2, 4, 8, 16
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 
@@ -56,6 +56,7 @@ SIGNATURES = {
     "pcv_stem_s2d_dims": (_I, [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "pcv_stem_s2d_ingest": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "pcv_stem_s2d_weights": (_I, [_I, _I, _I, _P, _P, _P]),
+    "pcv_stem_s2d_pool_ok": (_I, [_I, _I, _I, _I, _I]),
     "pcv_plan_create": (_I, [C.POINTER(_P)]),
     "pcv_plan_destroy": (_I, [_P]),
     "pcv_plan_num_ops": (_I, [_P]),

@@ -397,10 +397,14 @@ __global__ void igemm_pack_kernel(const float* __restrict__ w, const float* __re
   }
 }
 
-static int pick_bn(const pcv_conv_desc& d) {
+static int pick_bn(const pcv_conv_desc& d, int tiles_m) {
   if (d.groups > 1) return 64;
   if (d.Cout <= 32) return 32;
   if (d.Cout <= 64) return 64;
+  // few output rows (the classifier on pooled features: M = batch): narrower tiles put more CTAs on the weight stream -
+  // 2048 -> 1000 at batch 256 was 16 CTAs walking K = 2048 alone (0.030 ms against a 0.001 ms bound)
+  const int sms = sm_count();
+  if (tiles_m * ceil_div(d.Cout, 128) * 2 <= sms) return tiles_m * ceil_div(d.Cout, 64) * 2 <= sms ? 32 : 64;
   return 128;
 }
 
@@ -533,6 +537,8 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   {
     const int rcs = stem_halo_try_make(d, x, w, bias, res, y, out);   // s2d stem with a 32-byte-row halo tile
     if (rcs != PCV_ERR_UNSUPPORTED) return rcs;
+    if (d.flags & PCV_CONV_POOL3S2)
+      return fail(PCV_ERR_UNSUPPORTED, "PCV_CONV_POOL3S2: this stem cannot take the fused max pool (ask pcv_stem_s2d_pool_ok)");
   }
   {
     const int rc3 = igemm3_try_make(d, x, w, bias, res, y, out);   // 3x3 stride-1 layers with a smem halo tile
@@ -548,7 +554,7 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   const bool grouped = d.groups > 1;
 
   auto op = std::make_unique<IgemmOp>();
-  op->bn = pick_bn(d);
+  op->bn = pick_bn(d, ceil_div(d.N * Ho * Wo, BLOCK_M));
   IgemmParams& p = op->p;
   p.bias = bias;
   p.out = y;

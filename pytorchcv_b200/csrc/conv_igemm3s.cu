@@ -19,6 +19,13 @@
 // 0.246 ms).  Instead the tile is staged in shared memory as R image rows of round_up(Wo, 8) swizzled pixel rows and
 // leaves through one 4-D TMA store per image row (garbage columns c >= Wo are never written), double-buffered so the
 // stores of tile i drain while tile i+1 is computed.
+//
+// POOL = true fuses the 3x3 stride-2 pad-1 max pool that follows the stem in every ResNet-style init block
+// (resnet.py:255-258): the conv tile (R even rows) is only STAGED, the R/2 pooled rows are reduced from the staged rows
+// plus the last row of the previous tile (still intact in the other staging buffer), and only the pooled rows are
+// written (4x fewer output bytes; the 64 x 112 x 112 stem output - 0.4 GB per 256 images, written once and read once -
+// never exists).  For the carry row to be there, every CTA walks a CONTIGUOUS range of tiles, preceded by one warm-up
+// tile (computed and staged, nothing stored).
 #include "igemm_common.cuh"
 
 namespace pcv {
@@ -34,6 +41,8 @@ struct StemParams {
   int a_buf_bytes;           // smem stride of one A buffer (multiple of 1024, includes the over-read slack)
   int a_tx_bytes;            // bytes of one A box: (R+T-1) * PW * 32
   int WP8, stg_bytes;        // staging: pixels per staged image row (Wo rounded up to 8), bytes of one staging buffer
+  int tpc;                   // POOL: tiles per CTA (contiguous range), excluding the warm-up tile
+  int Hp, Wp, WPP8;          // POOL: pooled map size, pooled pixels per staged pooled row (Wp rounded up to 8)
   float act_lo, act_hi;
   int dbg;                   // PCV_STEM_DBG throughput experiments: 1 skip MMA issue, 2 skip epilogue math+stores, 4 skip A loads, 8 skip only the TMA stores
 };
@@ -51,7 +60,7 @@ constexpr int ST_MAX_NA = 6;
 constexpr int ST_THREADS = 384;   // 4 control warps + 8 epilogue warps
 constexpr int ST_ROW = 32;        // bytes per s2d pixel (16 bf16 channels)
 
-template <int BN, int T>
+template <int BN, int T, bool POOL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ST_THREADS, 1)
 stem_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const StemParams p) {
@@ -62,7 +71,8 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sB = smem;                                         // resident weights: ntaps x [BN/2 x 32 B]
   uint8_t* sA = sB + ((ntaps * B_BLOCK + 1023) & ~1023);
   uint8_t* sStg = sA + p.NA * p.a_buf_bytes;                  // 2 output staging buffers
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStg + 2 * p.stg_bytes);
+  uint8_t* sPool = sStg + 2 * p.stg_bytes;                    // POOL: one staging buffer of R/2 pooled rows
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPool + (POOL ? (p.R / 2) * p.WPP8 * BN * 2 : 0));
   uint64_t* full = bars;                         // [NA]  leader's copy is live
   uint64_t* empty = bars + ST_MAX_NA;            // [NA]  per CTA, multicast commit
   uint64_t* b_full = bars + 2 * ST_MAX_NA;       // [1]   leader's copy
@@ -77,6 +87,21 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int pair = blockIdx.x >> 1;
   const int npairs = gridDim.x >> 1;
   const int pair_tiles = (p.num_tiles + 1) >> 1;
+  // Tile schedule, identical in every role.  Default: pair-interleaved (iteration i of this CTA = tile
+  // 2*(pair + i*npairs) + rank).  POOL: CTA c owns tiles [c*tpc, (c+1)*tpc) and runs tpc + 1 iterations, the first one
+  // being the warm-up tile c*tpc - 1; both CTAs of a pair run the same number of iterations (one MMA serves both).
+  const int n_iter = POOL ? p.tpc + 1 : (pair < pair_tiles ? (pair_tiles - pair + npairs - 1) / npairs : 0);
+  auto sched = [&](int it, int& tile, bool& live) {
+    if (POOL) {
+      tile = (2 * pair + static_cast<int>(rank)) * p.tpc - 1 + it;
+      live = it >= 1 && tile < p.num_tiles;
+      tile = max(0, min(tile, p.num_tiles - 1));
+    } else {
+      tile = 2 * (pair + it * npairs) + static_cast<int>(rank);
+      live = tile < p.num_tiles;
+      if (!live) tile = p.num_tiles - 1;   // phantom tile of an odd tail: recompute the last one, stores masked
+    }
+  };
   const int acc_cols = p.NMB * BN;               // TMEM columns of one accumulator buffer
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2u * acc_cols) tmem_cols <<= 1;
@@ -121,9 +146,10 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     pdl_wait();   // the weights do not depend on the previous kernel; the s2d image does
     int slot = 0;
     uint32_t phase = 0;
-    for (int t = pair; t < pair_tiles; t += npairs) {
-      int tile = 2 * t + static_cast<int>(rank);
-      if (tile >= p.num_tiles) tile = p.num_tiles - 1;   // phantom tile of an odd tail: recompute the last one, stores masked
+    for (int it = 0; it < n_iter; ++it) {
+      int tile;
+      bool live;
+      sched(it, tile, live);
       const int img = tile / p.tiles_per_img;
       const int h0 = (tile - img * p.tiles_per_img) * p.R;
       mbar_wait(&empty[slot], phase ^ 1);
@@ -150,8 +176,7 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       int slot = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int t = pair; t < pair_tiles; t += npairs, ++it) {
+      for (int it = 0; it < n_iter; ++it) {
         const int buf = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
@@ -201,12 +226,13 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int CH = BN / 32;     // 32-column chunks per M-block
     constexpr int ROWB = BN * 2;    // bytes of one staged pixel
     const bool storer = warp == 4 && lane == 0;   // owns every bulk store group of this CTA
-    int it = 0;
-    for (int t = pair; t < pair_tiles; t += npairs, ++it) {
+    for (int it = 0; it < n_iter; ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int tile = 2 * t + static_cast<int>(rank);
-      const bool tile_ok = tile < p.num_tiles;
+      int tile;
+      bool live;
+      sched(it, tile, live);
+      const bool tile_ok = POOL ? true : live;   // POOL stages every tile (the warm-up tile supplies the carry row)
       const int img = tile / p.tiles_per_img;
       const int h0 = (tile - img * p.tiles_per_img) * p.R;
       uint8_t* stg = sStg + buf * p.stg_bytes;   // free: the storer waited for tile it-2's stores before barrier 1 of tile it-1
@@ -251,13 +277,60 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (rank == 0) mbar_arrive(&tmem_empty[buf]);
         else mbar_arrive_cluster(buf ? tmem_empty_leader1 : tmem_empty_leader0);
       }
-      fence_proxy_async_smem();                   // this thread's st.shared -> visible to the TMA (async proxy)
-      if (storer) tma_store_wait_read<0>();       // tile it-1's stores have left the OTHER buffer (next tile's)
-      named_bar_sync(1, 256);                     // all 8 epilogue warps: tile staged, other buffer free
-      if (storer && tile_ok && !(p.dbg & 10)) {
-        for (int r = 0; r < p.R; ++r)
-          if (h0 + r < p.Ho) tma_store_4d(&tmOut, stg + r * p.WP8 * ROWB, 0, 0, h0 + r, img);
-        tma_store_commit();
+      if (!POOL) {
+        fence_proxy_async_smem();                   // this thread's st.shared -> visible to the TMA (async proxy)
+        if (storer) tma_store_wait_read<0>();       // tile it-1's stores have left the OTHER buffer (next tile's)
+        named_bar_sync(1, 256);                     // all 8 epilogue warps: tile staged, other buffer free
+        if (storer && tile_ok && !(p.dbg & 10)) {
+          for (int r = 0; r < p.R; ++r)
+            if (h0 + r < p.Ho) tma_store_4d(&tmOut, stg + r * p.WP8 * ROWB, 0, 0, h0 + r, img);
+          tma_store_commit();
+        }
+      } else {
+        if (storer) tma_store_wait_read<0>();       // the previous tile's pooled rows have left sPool
+        named_bar_sync(1, 256);                     // conv tile staged by all 8 warps; sPool free
+        if (live) {
+          // 3x3 / stride 2 / pad 1 max over the staged conv rows; local row -1 = last row of the previous tile, which
+          // this CTA staged one iteration ago in the other buffer (contiguous schedule); padding taps are skipped
+          const uint8_t* prev = sStg + (buf ^ 1) * p.stg_bytes;
+          constexpr int CG = BN / 8;                // 16-byte channel groups per pixel
+          const int items = (p.R / 2) * p.Wp * CG;
+          for (int idx = threadIdx.x; idx < items; idx += 256) {
+            const int cg = idx % CG;
+            const int pxy = idx / CG;
+            const int pr = pxy / p.Wp, px = pxy - pr * p.Wp;
+            uint4 m = make_uint4(0, 0, 0, 0);
+            bool have = false;
+#pragma unroll
+            for (int dr = -1; dr <= 1; ++dr) {
+              const int lr = 2 * pr + dr;
+              if (lr < 0 && h0 == 0) continue;      // above the image
+              const uint8_t* base = lr < 0 ? prev : stg;
+              const int rr = lr < 0 ? p.R - 1 : lr;
+#pragma unroll
+              for (int dc = -1; dc <= 1; ++dc) {
+                const int cc = 2 * px + dc;
+                if (cc < 0) continue;               // left of the image (2*px + 1 <= Wo - 1: Wo is even)
+                const uint32_t srow = rr * p.WP8 + cc;
+                const uint4 v = *reinterpret_cast<const uint4*>(base + srow * ROWB + ((cg ^ (srow & 7u)) << 4));
+                if (have) {
+                  m.x = hmax2_bf16(m.x, v.x); m.y = hmax2_bf16(m.y, v.y); m.z = hmax2_bf16(m.z, v.z); m.w = hmax2_bf16(m.w, v.w);
+                } else {
+                  m = v;
+                  have = true;
+                }
+              }
+            }
+            const uint32_t prow = pr * p.WPP8 + px;
+            *reinterpret_cast<uint4*>(sPool + prow * ROWB + ((cg ^ (prow & 7u)) << 4)) = m;
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 256);                     // pooled rows staged (and every read of the carry row done)
+        if (storer && live) {
+          for (int pr = 0; pr < p.R / 2; ++pr) tma_store_4d(&tmOut, sPool + pr * p.WPP8 * ROWB, 0, 0, (h0 >> 1) + pr, img);
+          tma_store_commit();
+        }
       }
     }
     if (storer) tma_store_wait_all<0>();
@@ -278,28 +351,57 @@ struct StemOp : Op {
   CUtensorMap tmA, tmB, tmOut;
   StemParams p;
   int bn, grid, smem_bytes;
+  bool pool = false;
   cudaError_t launch(cudaStream_t s) override;
 };
 
-template <int BN, int T>
+template <int BN, int T, bool POOL>
 static cudaError_t launch_stem(const StemOp& op, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(stem_halo_kernel<BN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(stem_halo_kernel<BN, T, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  return launch_pdl(stem_halo_kernel<BN, T>, dim3(op.grid), dim3(ST_THREADS), op.smem_bytes, s, op.tmA, op.tmB, op.tmOut,
+  return launch_pdl(stem_halo_kernel<BN, T, POOL>, dim3(op.grid), dim3(ST_THREADS), op.smem_bytes, s, op.tmA, op.tmB, op.tmOut,
                     op.p);
 }
 
 cudaError_t StemOp::launch(cudaStream_t s) {
   g_launches++;
-  switch (p.T) {
-    case 2: return bn == 32 ? launch_stem<32, 2>(*this, s) : launch_stem<64, 2>(*this, s);
-    case 3: return bn == 32 ? launch_stem<32, 3>(*this, s) : launch_stem<64, 3>(*this, s);
-    default: return bn == 32 ? launch_stem<32, 4>(*this, s) : launch_stem<64, 4>(*this, s);
+  if (pool) {   // BN = 64 only (stem_pool_geometry)
+    switch (p.T) {
+      case 2: return launch_stem<64, 2, true>(*this, s);
+      case 3: return launch_stem<64, 3, true>(*this, s);
+      default: return launch_stem<64, 4, true>(*this, s);
+    }
   }
+  switch (p.T) {
+    case 2: return bn == 32 ? launch_stem<32, 2, false>(*this, s) : launch_stem<64, 2, false>(*this, s);
+    case 3: return bn == 32 ? launch_stem<32, 3, false>(*this, s) : launch_stem<64, 3, false>(*this, s);
+    default: return bn == 32 ? launch_stem<32, 4, false>(*this, s) : launch_stem<64, 4, false>(*this, s);
+  }
+}
+
+// Fused max pool (PCV_CONV_POOL3S2): rows per tile R (even, divides Ho) for a Ho x Wo conv map with T x T taps, or 0.
+static int stem_pool_rows(int Ho, int Wo, int T, int Cout) {
+  if (Cout != 64 || Ho % 2 != 0 || Wo % 2 != 0 || Wo + T - 1 > 256) return 0;
+  const int PW = Wo + T - 1;
+  for (int R = 8; R >= 2; R -= 2) {
+    if (Ho % R != 0) continue;
+    const int NMB = ceil_div(R * PW, BLOCK_M);
+    if (2 * NMB * 64 > 512) continue;
+    const int buf = round_up((NMB * BLOCK_M + (T - 1) * PW + T) * ST_ROW, 1024);
+    const int stg = round_up(R * round_up(Wo, 8) * 128, 1024);
+    const int pool = round_up((R / 2) * round_up(Wo / 2, 8) * 128, 1024);
+    const int b_bytes = round_up(T * T * 32 * ST_ROW, 1024);
+    if (1024 + 256 + b_bytes + 2 * buf + 2 * stg + pool <= 232448) return R;
+  }
+  return 0;
+}
+int stem_pool_ok(int C, int H, int W, int k, int Cout) {
+  if (C < 1 || C > 4 || (k != 3 && k != 5 && k != 7) || H % 2 != 0 || W % 2 != 0) return 0;
+  return stem_pool_rows(H / 2, W / 2, k / 2 + 1, Cout) > 0;
 }
 
 // The s2d stem as recorded by the plan compiler (plan.py::_conv_s2d): kh = T, kw = 1, Cin = T*16 through an
@@ -314,7 +416,8 @@ int stem_halo_try_make(const pcv_conv_desc& d, const void* x, const void* w, con
   }();
   const int T = d.kh;
   const int out_pitch = pitch_or(d.out_pitch, d.Cout);
-  if (!enabled || res || !(d.flags & PCV_CONV_IN_OVERLAP) || (d.flags & ~PCV_CONV_IN_OVERLAP) || d.kw != 1 || T < 2 ||
+  const bool pool = (d.flags & PCV_CONV_POOL3S2) != 0;
+  if (!enabled || res || !(d.flags & PCV_CONV_IN_OVERLAP) || (d.flags & ~(PCV_CONV_IN_OVERLAP | PCV_CONV_POOL3S2)) || d.kw != 1 || T < 2 ||
       T > 4 || d.Cin != T * 16 || d.in_pitch != 16 || d.stride != 1 || d.pad != 0 || d.dil != 1 || d.groups != 1 ||
       (d.Cout != 32 && d.Cout != 64) || d.in_row_pitch != (d.W + T - 1) * 16 || out_pitch % 8 != 0 ||
       d.W + T - 1 > 256 || d.act > PCV_ACT_RELU6 || reinterpret_cast<uintptr_t>(x) % 16 != 0 ||
@@ -328,12 +431,15 @@ int stem_halo_try_make(const pcv_conv_desc& d, const void* x, const void* w, con
   const int WP8 = round_up(Wo, 8);
   double best = 0.0;
   int bestR = 0, bestNA = 0, bestNMB = 0, best_buf = 0, best_stg = 0;
-  for (int R = 1; R <= std::min(Ho, 64); ++R) {
+  const int poolR = pool ? stem_pool_rows(Ho, Wo, T, d.Cout) : 0;
+  if (pool && poolR == 0) return PCV_ERR_UNSUPPORTED;
+  const int pool_bytes = pool ? round_up((poolR / 2) * round_up(Wo / 2, 8) * 128, 1024) : 0;
+  for (int R = pool ? poolR : 1; R <= (pool ? poolR : std::min(Ho, 64)); ++R) {
     const int Q = R * PW, NMB = ceil_div(Q, BLOCK_M);
     if (2 * NMB * BN > 512 || R + T - 1 > 256) continue;
     const int buf = round_up((NMB * BLOCK_M + (T - 1) * PW + T) * ST_ROW, 1024);
     const int stg = round_up(R * WP8 * BN * 2, 1024);
-    const int NA = std::min(ST_MAX_NA, (budget - 2 * stg) / buf);
+    const int NA = std::min(ST_MAX_NA, (budget - 2 * stg - pool_bytes) / buf);
     if (NA < 2) continue;
     const int tiles = d.N * ceil_div(Ho, R);
     const int pair_tiles = (tiles + 1) / 2;
@@ -368,8 +474,11 @@ int stem_halo_try_make(const pcv_conv_desc& d, const void* x, const void* w, con
     p.dbg = e ? atoi(e) : 0;
   }
   op->bn = BN;
-  op->smem_bytes = 1024 + b_bytes + bestNA * best_buf + 2 * best_stg + 256;
+  op->pool = pool;
+  op->smem_bytes = 1024 + b_bytes + bestNA * best_buf + 2 * best_stg + pool_bytes + 256;
   op->grid = 2 * std::min((p.num_tiles + 1) / 2, pairs);
+  p.tpc = ceil_div(p.num_tiles, op->grid);
+  p.Hp = Ho / 2; p.Wp = Wo / 2; p.WPP8 = round_up(Wo / 2, 8);
 
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -395,9 +504,10 @@ int stem_halo_try_make(const pcv_conv_desc& d, const void* x, const void* w, con
     if (r != CUDA_SUCCESS) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled (stem B) failed (%d)", (int)r);
   }
   {   // output rows leave through 4-D TMA stores: box = one image row (Wo pixels x BN channels)
-    cuuint64_t dims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)d.N};
-    cuuint64_t strides[3] = {(cuuint64_t)out_pitch * 2, (cuuint64_t)Wo * out_pitch * 2, (cuuint64_t)Ho * Wo * out_pitch * 2};
-    cuuint32_t box[4] = {(cuuint32_t)BN, (cuuint32_t)Wo, 1, 1};
+    const int Hy = pool ? Ho / 2 : Ho, Wy = pool ? Wo / 2 : Wo;   // y is the pooled map when the max pool is fused
+    cuuint64_t dims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)Wy, (cuuint64_t)Hy, (cuuint64_t)d.N};
+    cuuint64_t strides[3] = {(cuuint64_t)out_pitch * 2, (cuuint64_t)Wy * out_pitch * 2, (cuuint64_t)Hy * Wy * out_pitch * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BN, (cuuint32_t)Wy, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(&op->tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, BN == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -405,13 +515,14 @@ int stem_halo_try_make(const pcv_conv_desc& d, const void* x, const void* w, con
     if (r != CUDA_SUCCESS) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled (stem out) failed (%d)", (int)r);
   }
   char nm[160];
-  snprintf(nm, sizeof nm, "conv_stem s2d %dx%d taps x16ch ->%d @%dx%d bn=%d halo R=%d mb=%d na=%d", T, T, d.Cout, Ho, Wo, BN,
-           bestR, bestNMB, bestNA);
+  snprintf(nm, sizeof nm, "conv_stem%s s2d %dx%d taps x16ch ->%d @%dx%d bn=%d halo R=%d mb=%d na=%d", pool ? "+maxpool3s2" : "",
+           T, T, d.Cout, Ho, Wo, BN, bestR, bestNMB, bestNA);
   op->name = nm;
   const double M = static_cast<double>(d.N) * Ho * Wo;
   op->flops = 2.0 * M * d.Cout * ntaps * 16;
   // algorithmic bytes: the s2d tensor once (what this kernel's input really is) + the output + weights + bias
-  op->bytes = 2.0 * d.N * rows * PW * 16 + 2.0 * M * d.Cout + 2.0 * d.Cout * ntaps * 16 + 4.0 * d.Cout;
+  // (fused max pool: the conv map never reaches HBM, only the pooled map does)
+  op->bytes = 2.0 * d.N * rows * PW * 16 + 2.0 * (pool ? M / 4 : M) * d.Cout + 2.0 * d.Cout * ntaps * 16 + 4.0 * d.Cout;
   *out = op.release();
   return PCV_OK;
 }

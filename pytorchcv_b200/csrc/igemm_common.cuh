@@ -59,6 +59,8 @@ int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const 
 int stem_halo_try_make(const pcv_conv_desc& d, const void* x, const void* w, const float* bias, const void* res,
                        void* y, Op** out);
 
+int stem_pool_ok(int C, int H, int W, int k, int Cout);
+
 void igemm2_pick_smem(int bn, int num_kblocks, bool has_res, int taps, int* stages, int* ksub, int* nstg);
 
 }  // namespace pcv

@@ -2,6 +2,7 @@
 // All NHWC with 8-channel (16-byte bf16) vectors per lane; consecutive lanes own consecutive channel vectors.
 #include "ptx.cuh"
 #include "runtime.h"
+#include "igemm_common.cuh"
 
 namespace pcv {
 
@@ -881,6 +882,8 @@ int pcv_stem_s2d_ingest(pcv_plan* plan, int N, int C, int H, int W, int k, const
   op->bytes = static_cast<double>(N) * (4.0 * C * H * W + 32.0 * (H / 2) * (W / 2));
   return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
 }
+
+int pcv_stem_s2d_pool_ok(int C, int H, int W, int k, int Cout) { return pcv::stem_pool_ok(C, H, W, k, Cout); }
 
 int pcv_stem_s2d_weights(int Cout, int C, int k, const float* w, float* w_eq, pcv_stream stream) {
   PCV_REQUIRE(w && w_eq && Cout > 0 && C >= 1 && C <= 4 && (k == 3 || k == 5 || k == 7), "bad stem weight arguments");

@@ -98,6 +98,8 @@ static int validate_conv(const pcv_conv_desc* d, int dtype) {
                   (d->flags & PCV_CONV_IN_OVERLAP),
               "in_row_pitch smaller than a row");
   PCV_REQUIRE(!(d->flags & PCV_CONV_OUT_F32) || dtype == PCV_BF16, "OUT_F32 only applies to the bf16 tier");
+  PCV_REQUIRE(!(d->flags & PCV_CONV_POOL3S2) || ((d->flags & PCV_CONV_IN_OVERLAP) && dtype == PCV_BF16),
+              "POOL3S2 only applies to the bf16 space-to-depth stem");
   if ((d->flags & PCV_CONV_IN_OVERLAP) || d->in_row_pitch != 0) {
     std::string why;
     PCV_REQUIRE(conv_route(*d, dtype, &why) == ROUTE_IGEMM, "row-pitched input views need the tcgen05 route: %s",

@@ -118,11 +118,16 @@ class _NoS2dStem(Exception):
     """The network input feeds more than the stem convolution: recompile with the generic NHWC ingest."""
 
 
+class _NoStemPool(Exception):
+    """The stem's conv map is read by something besides the fused max pool: recompile without that fusion."""
+
+
 class Builder:
-    def __init__(self, dtype: int, device: torch.device, allow_s2d_stem: bool = True):
+    def __init__(self, dtype: int, device: torch.device, allow_s2d_stem: bool = True, allow_stem_pool: bool = True):
         self.dtype = dtype
         self.device = device
         self.allow_s2d_stem = allow_s2d_stem
+        self.allow_stem_pool = allow_stem_pool
         self.input_tref: TRef | None = None   # NHWC (channel-padded) image, set by CompiledModule
         self.image_channels = 0
         self.stem: dict | None = None         # {"k": kernel, "tref": s2d tensor} once the s2d stem is chosen
@@ -149,6 +154,8 @@ class Builder:
             if t is not None:
                 if self.stem is not None and self.input_tref is not None and t.buf is self.input_tref.buf:
                     raise _NoS2dStem()
+                if self.stem is not None and t.buf is self.stem.get("fused_conv_buf"):
+                    raise _NoStemPool()
                 t.buf.last = max(t.buf.last, idx)
         return idx
 
@@ -179,10 +186,13 @@ class Builder:
         idx = len(self.ops)
         xs.buf.last = out.buf.last = idx
         dtype = self.dtype
+        target = [out]   # maxpool() may retarget the op at the pooled map (PCV_CONV_POOL3S2)
+        self.stem.update(out=out, idx=idx, desc=d, target=target,
+                         pool_ok=bool(_lib.load().pcv_stem_s2d_pool_ok(conv.in_channels, x.H, x.W, k, cout)))
 
         def emit(plan, ptr, wptr):
             _lib.call("pcv_conv2d_bias_act", plan, C.byref(d), dtype, ptr(xs), wptr(w_off), wptr(b_off), None,
-                      ptr(out), None)
+                      ptr(target[0]), None)
         self.ops.append(emit)
         return out
 
@@ -251,6 +261,19 @@ class Builder:
     def maxpool(self, x: TRef, k: int, stride: int, pad: int) -> TRef:
         Ho = (x.H + 2 * pad - k) // stride + 1
         Wo = (x.W + 2 * pad - k) // stride + 1
+        st = self.stem
+        if (self.allow_stem_pool and st is not None and x is st.get("out") and st.get("pool_ok")
+                and st["idx"] == len(self.ops) - 1 and x.buf.last == st["idx"] and (k, stride, pad) == (3, 2, 1)):
+            # ResInitBlock (resnet.py:255-263): conv7x7_block -> MaxPool2d(3, 2, 1).  The stem kernel reduces the pooled
+            # rows from its staged conv tile, so the conv map is never written (include/pcv_b200.h PCV_CONV_POOL3S2).
+            pooled = self.new(x.N, Ho, Wo, x.C, dtype=x.dtype)
+            pooled.buf.first = pooled.buf.last = st["idx"]
+            st["desc"].flags |= _lib.CONV_POOL3S2
+            st["desc"].out_pitch = pooled.pitch
+            st["target"][0] = pooled
+            st["fused_conv_buf"] = x.buf
+            x.buf.nbytes = 0
+            return pooled
         out = self.new(x.N, Ho, Wo, x.C, dtype=x.dtype)
         self._use(x, out)
         self.ops.append(lambda plan, ptr, wptr: _lib.call(
@@ -639,8 +662,8 @@ class CompiledModule:
         self.signature = weights_signature(module)
         N, Cin, H, W = self.in_shape
 
-        for allow_s2d in (True, False):
-            b = Builder(self.dtype, self.device, allow_s2d_stem=allow_s2d)
+        for allow_s2d, allow_pool in ((True, True), (True, False), (False, False)):
+            b = Builder(self.dtype, self.device, allow_s2d_stem=allow_s2d, allow_stem_pool=allow_pool)
             x = b.new(N, H, W, _rup(Cin, 8))
             x.buf.first = -1
             x.buf.pinned = True
@@ -648,8 +671,8 @@ class CompiledModule:
             try:
                 result = lower(b, module, x, **(lower_kwargs or {}))
                 break
-            except _NoS2dStem:
-                continue
+            except (_NoStemPool, _NoS2dStem):
+                continue   # retry order: drop the pool fusion first, then the s2d stem
         self._stem_k = b.stem["k"] if b.stem else 0
         self._in = b.stem["tref"] if b.stem else x
         self._in_channels = Cin

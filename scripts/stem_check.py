@@ -17,6 +17,12 @@ CASES = [  # name, k, Cout, act, N, H, W
     ("stem3_32_ragged", 3, 32, "relu", 3, 50, 38),
     ("stem7_64_ragged", 7, 64, "relu", 5, 38, 50),
     ("stem5_64", 5, 64, "relu", 2, 96, 96),
+    # conv -> MaxPool2d(3, 2, 1) fused into the stem kernel (PCV_CONV_POOL3S2)
+    ("pool_stem7_64_224", 7, 64, "relu", 3, 224, 224),
+    ("pool_stem7_64_bs40", 7, 64, "relu", 40, 224, 224),
+    ("pool_stem7_64_small", 7, 64, "relu", 5, 64, 64),
+    ("pool_stem3_64_160", 3, 64, "relu", 2, 160, 96),
+    ("pool_stem7_64_448", 7, 64, "relu", 1, 448, 448),
 ]
 
 
@@ -29,16 +35,22 @@ def run(idx):
     name, k, cout, act, N, H, W = CASES[idx]
     blk = blocks.ConvBlock(in_channels=3, out_channels=cout, kernel_size=k, stride=2, padding=k // 2,
                            activation=(lambda: torch.nn.ReLU6(inplace=True)) if act == "relu6" else (lambda: torch.nn.ReLU(inplace=True)))
+    pool = name.startswith("pool_")
+    if pool:
+        blk = torch.nn.Sequential(blk, torch.nn.MaxPool2d(kernel_size=3, stride=2, padding=1))
     blk = seeded_init(blk.eval(), seed=3, randomize_bn=True)
     x = seeded_input((N, 3, H, W), seed=5)
-    bn = blk.bn
+    cb = blk[0] if pool else blk
+    bn = cb.bn
     scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
     rnd = lambda t: t.to(torch.bfloat16).float()
-    wf = rnd(blk.conv.weight * scale.view(-1, 1, 1, 1))
+    wf = rnd(cb.conv.weight * scale.view(-1, 1, 1, 1))
     bf = bn.bias - bn.running_mean * scale
     with torch.no_grad():
         ref = F.conv2d(rnd(x), wf, bf, stride=2, padding=k // 2)
         ref = ref.clamp(0, 6) if act == "relu6" else torch.relu(ref)
+        if pool:
+            ref = F.max_pool2d(ref, 3, 2, 1)
     fast = P.accelerate(blk.cuda(), dtype="bf16", graph=False)
     y = fast(x.cuda()).float().cpu()
     torch.cuda.synchronize()
