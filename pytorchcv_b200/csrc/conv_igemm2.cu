@@ -267,8 +267,10 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;   // eight epilogue warps: (lane quarter, 32-column half)
     const int row = q * 32 + lane;
-    const float act_lo = p.act_lo, act_hi = p.act_hi;
     const bool fancy_act = p.act > PCV_ACT_RELU6;
+    const bool relu = p.act_lo == 0.f, capped = p.act_hi != INFINITY;   // the clamp family: none / ReLU / ReLU6
+    const uint32_t cap2 = pack_bf16x2(p.act_hi, p.act_hi);
+    const uint32_t sStg_u32 = smem_u32(sStg);
     const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
     int it = 0;
@@ -286,7 +288,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
 #pragma unroll 1
       for (int sub = 0; sub < L::NSUB; ++sub) {
-        uint8_t* stg = sStg + slot * L::SUB_BYTES;
+        const uint32_t stg_u32 = sStg_u32 + slot * L::SUB_BYTES;
         // the slot is ready when its residual has landed (which implies the previous store has left it) or, without
         // a residual, when the staging manager has released it
         mbar_wait(p.has_res ? &res_full[slot] : &stg_free[slot], sphase);
@@ -295,52 +297,51 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           const int col = sub * L::SUB_COLS + h * 32;
           uint32_t acc[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + col, acc);
-          tmem_ld_wait();
-          float v[32];
+          // bias and residual loads issued under the TMEM load (the wait below is a compiler barrier for memory operations)
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + col);
+          float4 b4[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) b4[i] = __ldg(bias4 + i);
+          const uint32_t row_off = row * 128 + h * 64;
+          const uint32_t sw = (row & 7u) << 4;   // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
+          uint4 r4[4];
+          if (p.has_res) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) r4[c] = lds128(stg_u32 + ((row_off + c * 16) ^ sw));
+          }
+          tmem_ld_wait_regs(acc);
+          float v[32];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 b = __ldg(bias4 + i);
-            v[4 * i + 0] = __uint_as_float(acc[4 * i + 0]) + b.x;
-            v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b.y;
-            v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b.z;
-            v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b.w;
+            v[4 * i + 0] = __uint_as_float(acc[4 * i + 0]) + b4[i].x;
+            v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b4[i].y;
+            v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b4[i].z;
+            v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b4[i].w;
           }
-          const uint32_t row_off = row * 128 + h * 64;
           if (p.has_res) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              uint32_t off = row_off + c * 16;
-              off ^= ((off >> 7) & 7u) << 4;
-              const uint4 r = *reinterpret_cast<const uint4*>(stg + off);
-              v[8 * c + 0] += bf16lo(r.x);
-              v[8 * c + 1] += bf16hi(r.x);
-              v[8 * c + 2] += bf16lo(r.y);
-              v[8 * c + 3] += bf16hi(r.y);
-              v[8 * c + 4] += bf16lo(r.z);
-              v[8 * c + 5] += bf16hi(r.z);
-              v[8 * c + 6] += bf16lo(r.w);
-              v[8 * c + 7] += bf16hi(r.w);
+              v[8 * c + 0] += bf16lo(r4[c].x);
+              v[8 * c + 1] += bf16hi(r4[c].x);
+              v[8 * c + 2] += bf16lo(r4[c].y);
+              v[8 * c + 3] += bf16hi(r4[c].y);
+              v[8 * c + 4] += bf16lo(r4[c].z);
+              v[8 * c + 5] += bf16hi(r4[c].z);
+              v[8 * c + 6] += bf16lo(r4[c].w);
+              v[8 * c + 7] += bf16hi(r4[c].w);
             }
           }
+          uint32_t o[16];
           if (fancy_act) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+            clamp_pack32(v, o, false, false, 0u);
           } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], act_lo), act_hi);
+            clamp_pack32(v, o, relu, capped, cap2);
           }
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t off = row_off + c * 16;
-            off ^= ((off >> 7) & 7u) << 4;
-            uint4 o;
-            o.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]);
-            o.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
-            o.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
-            o.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
-            *reinterpret_cast<uint4*>(stg + off) = o;
-          }
+          for (int c = 0; c < 4; ++c)
+            sts128(stg_u32 + ((row_off + c * 16) ^ sw), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
         }
         if (sub == L::NSUB - 1) {
           // all accumulator columns of this tile are in registers / smem: release the TMEM buffer to the leader's MMA

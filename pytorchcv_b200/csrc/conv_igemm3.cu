@@ -214,7 +214,8 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int q4 = warp & 3;
     const int half = (warp - 4) >> 2;
     const int row = q4 * 32 + lane;
-    const float act_lo = p.act_lo, act_hi = p.act_hi;
+    const bool relu = p.act_lo == 0.f, capped = p.act_hi != INFINITY;   // clamp family only (igemm3_try_make)
+    const uint32_t cap2 = pack_bf16x2(p.act_hi, p.act_hi);
     const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
     const bool storer = STAGED && warp == 4 && lane == 0;   // owns every bulk store group of this CTA
@@ -242,29 +243,32 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         for (int j = half; j < BN / 32; j += 2) {
           uint32_t acc[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * acc_cols + mb * BN + j * 32, acc);
-          tmem_ld_wait();
+          // bias loads issued under the TMEM load (the wait below is a compiler barrier for memory operations)
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + g * BN + j * 32);
-          uint32_t o[16];
-          // scalar fp32 math on purpose: packing the tcgen05.ld registers into 64-bit operands for add.f32x2 cost more
+          float4 b4[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) b4[i] = __ldg(bias4 + i);
+          tmem_ld_wait_regs(acc);
+          // scalar fp32 adds on purpose: packing the tcgen05.ld registers into 64-bit operands for add.f32x2 cost more
           // instructions than it saved (measured on the igemm2 epilogue)
+          float v[32];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 b = __ldg(bias4 + i);
-            const float v0 = fminf(fmaxf(__uint_as_float(acc[4 * i + 0]) + b.x, act_lo), act_hi);
-            const float v1 = fminf(fmaxf(__uint_as_float(acc[4 * i + 1]) + b.y, act_lo), act_hi);
-            const float v2 = fminf(fmaxf(__uint_as_float(acc[4 * i + 2]) + b.z, act_lo), act_hi);
-            const float v3 = fminf(fmaxf(__uint_as_float(acc[4 * i + 3]) + b.w, act_lo), act_hi);
-            o[2 * i + 0] = pack_bf16x2(v0, v1);
-            o[2 * i + 1] = pack_bf16x2(v2, v3);
+            v[4 * i + 0] = __uint_as_float(acc[4 * i + 0]) + b4[i].x;
+            v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b4[i].y;
+            v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b4[i].z;
+            v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b4[i].w;
           }
+          uint32_t o[16];
+          clamp_pack32(v, o, relu, capped, cap2);
           if (ok) {
             if (STAGED) {
               const uint32_t srow = r * p.WP8 + c;   // staged pixel index; staged image rows start on 1024-byte boundaries
-              uint8_t* dstp = stg + srow * (BN * 2);
+              const uint32_t dstp = smem_u32(stg) + srow * (BN * 2);
               const uint32_t sw = srow & 7u;         // SWIZZLE_128B chunk XOR (BN = 64: one 128-byte row per pixel)
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                *reinterpret_cast<uint4*>(dstp + (((j * 4 + i) ^ sw) << 4)) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                sts128(dstp + (((j * 4 + i) ^ sw) << 4), o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
             } else {
               uint4* d4 = reinterpret_cast<uint4*>(dst + j * 32);
 #pragma unroll

@@ -44,7 +44,7 @@ struct StemParams {
   int tpc;                   // POOL: tiles per CTA (contiguous range), excluding the warm-up tile
   int Hp, Wp, WPP8;          // POOL: pooled map size, pooled pixels per staged pooled row (Wp rounded up to 8)
   float act_lo, act_hi;
-  int dbg;                   // PCV_STEM_DBG throughput experiments: 1 skip MMA issue, 2 skip epilogue math+stores, 4 skip A loads, 8 skip only the TMA stores
+  int dbg;                   // PCV_STEM_DBG throughput experiments: 1 skip MMA issue, 2 skip epilogue loads+math+staging, 4 skip A loads, 8 skip the TMA stores, 16 skip the pool pass
 };
 
 __device__ __forceinline__ void tma2_load_4d_s(const CUtensorMap* m, uint32_t mbar_cluster_addr, void* dst, int c0,
@@ -216,16 +216,44 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp >= 4) {
     // ===================================== epilogue (both CTAs) =====================================
     // eight warps: warp w owns TMEM lane quarter (w & 3) and every second (M-block, 32-column chunk) work item
+    // w = half + 2k.  With CH = BN/32 chunks per M-block that is always the SAME chunk j (CH = 2: j = half, mb = k;
+    // CH = 1: j = 0, mb = half + 2k), so its 32 bias values live in registers for the whole kernel, and a thread's
+    // pixel (TMEM lane) -> staged-row mapping is tile-invariant and precomputed per k (no divisions in the tile loop).
     pdl_wait();   // the output buffer may alias a tensor the previous kernel is still reading
     const int q4 = warp & 3;
     const int half = (warp - 4) >> 2;
     const int row = q4 * 32 + lane;
     const float act_lo = p.act_lo, act_hi = p.act_hi;
+    const bool relu_only = act_lo == 0.f && act_hi == INFINITY;
     const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
     constexpr int CH = BN / 32;     // 32-column chunks per M-block
     constexpr int ROWB = BN * 2;    // bytes of one staged pixel
+    constexpr int MAXK = 4;         // work items per warp and tile: ceil(NMB * CH / 2) <= 4 (2 * NMB * BN <= 512 columns)
+    const int j = half % CH;
+    const int nk = (p.NMB * CH - half + 1) >> 1;
+    float bias_r[32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + j * 32) + i);
+      bias_r[4 * i + 0] = b.x; bias_r[4 * i + 1] = b.y; bias_r[4 * i + 2] = b.z; bias_r[4 * i + 3] = b.w;
+    }
+    int st_off[MAXK], st_r[MAXK];   // byte offset of this thread's staged pixel (-1: padding column / beyond R), its local row
+    const uint32_t t_off0 = (static_cast<uint32_t>(q4 * 32) << 16) + (CH == 2 ? 0 : half) * BN + j * 32;
+    constexpr uint32_t T_STEP = CH == 2 ? BN : 2 * BN;   // TMEM columns between this warp's consecutive work items
+#pragma unroll
+    for (int k = 0; k < MAXK; ++k) {
+      const int mb = CH == 2 ? k : half + 2 * k;
+      const int q = mb * BLOCK_M + row;
+      const int r = q / p.PW;
+      const int c = q - r * p.PW;
+      const uint32_t srow = r * p.WP8 + c;   // staged pixel index; staged image rows start on swizzle-atom boundaries
+      st_off[k] = (k < nk && c < p.Wo && r < p.R) ? static_cast<int>(srow * ROWB) : -1;
+      st_r[k] = r;
+    }
     const bool storer = warp == 4 && lane == 0;   // owns every bulk store group of this CTA
+    const uint32_t sStg_u32 = smem_u32(sStg), sPool_u32 = smem_u32(sPool);
+    const int tid = (warp - 4) * 32 + lane;       // 0..255 among the epilogue threads
     for (int it = 0; it < n_iter; ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -236,39 +264,41 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int img = tile / p.tiles_per_img;
       const int h0 = (tile - img * p.tiles_per_img) * p.R;
       uint8_t* stg = sStg + buf * p.stg_bytes;   // free: the storer waited for tile it-2's stores before barrier 1 of tile it-1
+      const uint32_t stg_u32 = sStg_u32 + buf * p.stg_bytes;
 
       mbar_wait(&tmem_full[buf], acc_phase);
       tc_fence_after();
 
-#pragma unroll 1
-      for (int w = half; w < ((p.dbg & 2) ? 0 : p.NMB * CH); w += 2) {
-        const int mb = w / CH, j = w - mb * CH;
-        const int q = mb * BLOCK_M + row;
-        const int r = q / p.PW;
-        const int c = q - r * p.PW;
-        const bool ok = tile_ok && c < p.Wo && r < p.R && (h0 + r) < p.Ho;
-        uint32_t acc[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * acc_cols + mb * BN + j * 32, acc);
-        tmem_ld_wait();
-        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + j * 32);
-        uint32_t o[16];
+      // TMEM -> registers -> (+bias, activation, bf16) -> swizzled staging; the tcgen05.ld of item k+1 is in flight while
+      // item k is converted
+      const uint32_t tbase = tmem_base + buf * acc_cols;
+      uint32_t acc[2][32];
+      if (nk > 0 && !(p.dbg & 2)) tmem_ld_32x32(tbase + t_off0, acc[0]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b = __ldg(bias4 + i);
-          const float v0 = fminf(fmaxf(__uint_as_float(acc[4 * i + 0]) + b.x, act_lo), act_hi);
-          const float v1 = fminf(fmaxf(__uint_as_float(acc[4 * i + 1]) + b.y, act_lo), act_hi);
-          const float v2 = fminf(fmaxf(__uint_as_float(acc[4 * i + 2]) + b.z, act_lo), act_hi);
-          const float v3 = fminf(fmaxf(__uint_as_float(acc[4 * i + 3]) + b.w, act_lo), act_hi);
-          o[2 * i + 0] = pack_bf16x2(v0, v1);
-          o[2 * i + 1] = pack_bf16x2(v2, v3);
-        }
-        if (ok) {
-          const uint32_t srow = r * p.WP8 + c;   // staged pixel index; staged image rows start on swizzle-atom boundaries
-          uint8_t* dstp = stg + srow * ROWB;
-          const uint32_t sw = BN == 64 ? (srow & 7u) : ((srow >> 1) & 3u);   // SWIZZLE_128B / SWIZZLE_64B chunk XOR
+      for (int k = 0; k < MAXK; ++k) {
+        if (k < nk && !(p.dbg & 2)) {
+          tmem_ld_wait_regs(acc[k & 1]);
+          if (k + 1 < MAXK && k + 1 < nk) tmem_ld_32x32(tbase + t_off0 + (k + 1) * T_STEP, acc[(k + 1) & 1]);
+          const uint32_t* a = acc[k & 1];
+          uint32_t o[16];
+          if (relu_only) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<uint4*>(dstp + (((j * 4 + i) ^ sw) << 4)) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            for (int i = 0; i < 16; ++i)
+              o[i] = pack_relu_bf16x2(__uint_as_float(a[2 * i]) + bias_r[2 * i], __uint_as_float(a[2 * i + 1]) + bias_r[2 * i + 1]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              o[i] = pack_bf16x2(fminf(fmaxf(__uint_as_float(a[2 * i]) + bias_r[2 * i], act_lo), act_hi),
+                                 fminf(fmaxf(__uint_as_float(a[2 * i + 1]) + bias_r[2 * i + 1], act_lo), act_hi));
+          }
+          if (st_off[k] >= 0 && tile_ok && (POOL || h0 + st_r[k] < p.Ho)) {
+            const uint32_t dstp = stg_u32 + st_off[k];
+            // SWIZZLE_128B (128-byte pixels) / SWIZZLE_64B (64-byte pixels) chunk XOR from the staged pixel index
+            const uint32_t sw = BN == 64 ? ((st_off[k] >> 7) & 7u) : ((st_off[k] >> 7) & 3u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              sts128(dstp + (((j * 4 + i) ^ sw) << 4), o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          }
         }
       }
       tc_fence_before();
@@ -289,45 +319,46 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       } else {
         if (storer) tma_store_wait_read<0>();       // the previous tile's pooled rows have left sPool
         named_bar_sync(1, 256);                     // conv tile staged by all 8 warps; sPool free
-        if (live) {
-          // 3x3 / stride 2 / pad 1 max over the staged conv rows; local row -1 = last row of the previous tile, which
-          // this CTA staged one iteration ago in the other buffer (contiguous schedule); padding taps are skipped
-          const uint8_t* prev = sStg + (buf ^ 1) * p.stg_bytes;
+        if (live && !(p.dbg & 16)) {
+          // 3x3 / stride 2 / pad 1 max over the staged conv rows, separable and branch-free: a thread owns one 16-byte
+          // channel group of one pooled column and walks down the tile's rows keeping the horizontal 3-max of the last
+          // row (row 2pr+1 of pooled row pr is row 2(pr+1)-1 of the next).  Local row -1 = the last row of the previous
+          // tile, which this CTA staged one iteration ago in the other buffer (contiguous schedule).  Padding taps are
+          // replaced by a duplicate of an in-range tap (max is idempotent): column -1 -> column 0, row -1 of the
+          // image -> row 0.
+          const uint32_t prev = sStg_u32 + (buf ^ 1) * p.stg_bytes;
           constexpr int CG = BN / 8;                // 16-byte channel groups per pixel
-          const int items = (p.R / 2) * p.Wp * CG;
-          for (int idx = threadIdx.x; idx < items; idx += 256) {
-            const int cg = idx % CG;
-            const int pxy = idx / CG;
-            const int pr = pxy / p.Wp, px = pxy - pr * p.Wp;
-            uint4 m = make_uint4(0, 0, 0, 0);
-            bool have = false;
-#pragma unroll
-            for (int dr = -1; dr <= 1; ++dr) {
-              const int lr = 2 * pr + dr;
-              if (lr < 0 && h0 == 0) continue;      // above the image
-              const uint8_t* base = lr < 0 ? prev : stg;
-              const int rr = lr < 0 ? p.R - 1 : lr;
-#pragma unroll
-              for (int dc = -1; dc <= 1; ++dc) {
-                const int cc = 2 * px + dc;
-                if (cc < 0) continue;               // left of the image (2*px + 1 <= Wo - 1: Wo is even)
-                const uint32_t srow = rr * p.WP8 + cc;
-                const uint4 v = *reinterpret_cast<const uint4*>(base + srow * ROWB + ((cg ^ (srow & 7u)) << 4));
-                if (have) {
-                  m.x = hmax2_bf16(m.x, v.x); m.y = hmax2_bf16(m.y, v.y); m.z = hmax2_bf16(m.z, v.z); m.w = hmax2_bf16(m.w, v.w);
-                } else {
-                  m = v;
-                  have = true;
-                }
-              }
+          const uint32_t rowb = p.WP8 * ROWB, prowb = p.WPP8 * ROWB;
+          for (int idx = tid; idx < p.Wp * CG; idx += 256) {
+            const uint32_t cg = idx & (CG - 1);
+            const uint32_t px = idx >> 3;
+            const uint32_t c1 = 2 * px, c0 = c1 == 0 ? 0 : c1 - 1, c2 = c1 + 1;   // c2 <= Wo - 1: Wo is even
+            const uint32_t o0 = c0 * ROWB + ((cg ^ (c0 & 7u)) << 4);             // WP8 % 8 == 0: the swizzle phase is the column's
+            const uint32_t o1 = c1 * ROWB + ((cg ^ (c1 & 7u)) << 4);
+            const uint32_t o2 = c2 * ROWB + ((cg ^ (c2 & 7u)) << 4);
+            auto hrow = [&](uint32_t rowp) {
+              const uint4 a = lds128(rowp + o0), b = lds128(rowp + o1), c = lds128(rowp + o2);
+              return make_uint4(hmax3_bf16(a.x, b.x, c.x), hmax3_bf16(a.y, b.y, c.y), hmax3_bf16(a.z, b.z, c.z),
+                                hmax3_bf16(a.w, b.w, c.w));
+            };
+            uint4 up = hrow(h0 == 0 ? stg_u32 : prev + (p.R - 1) * rowb);
+            uint32_t src = stg_u32;
+            uint32_t pdst = sPool_u32 + px * ROWB + ((cg ^ (px & 7u)) << 4);   // WPP8 % 8 == 0
+#pragma unroll 2
+            for (int pr = 0; pr < p.R / 2; ++pr) {
+              const uint4 m0 = hrow(src);
+              const uint4 m1 = hrow(src + rowb);
+              sts128(pdst, hmax3_bf16(up.x, m0.x, m1.x), hmax3_bf16(up.y, m0.y, m1.y), hmax3_bf16(up.z, m0.z, m1.z),
+                     hmax3_bf16(up.w, m0.w, m1.w));
+              up = m1;
+              src += 2 * rowb;
+              pdst += prowb;
             }
-            const uint32_t prow = pr * p.WPP8 + px;
-            *reinterpret_cast<uint4*>(sPool + prow * ROWB + ((cg ^ (prow & 7u)) << 4)) = m;
           }
         }
         fence_proxy_async_smem();
         named_bar_sync(2, 256);                     // pooled rows staged (and every read of the carry row done)
-        if (storer && live) {
+        if (storer && live && !(p.dbg & 8)) {
           for (int pr = 0; pr < p.R / 2; ++pr) tma_store_4d(&tmOut, sPool + pr * p.WPP8 * ROWB, 0, 0, (h0 >> 1) + pr, img);
           tma_store_commit();
         }

@@ -227,6 +227,19 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// tcgen05.wait::ld that also "touches" the destination registers of an earlier tcgen05.ld, so that neither the
+// compiler nor ptxas can schedule a use of them above the wait when other loads are issued in between
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+        "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+        "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+        "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :
+      : "memory");
+}
+
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane_base + i), columns [col, col+32).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -266,6 +279,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// max(x, 0) and the bf16 rounding in one instruction (F2FP.RELU): the ReLU epilogue's clamp for free
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 // packed fp32x2 add (Blackwell FADD2); each lane rounds like a scalar add
 __device__ __forceinline__ float2 add2(const float2 a, const float2 b) {
   uint64_t aa = (static_cast<uint64_t>(__float_as_uint(a.y)) << 32) | __float_as_uint(a.x);
@@ -280,6 +299,35 @@ __device__ __forceinline__ uint32_t hmax2_bf16(uint32_t a, uint32_t b) {
 __device__ __forceinline__ uint32_t hmin2_bf16(uint32_t a, uint32_t b) {
   const __nv_bfloat162 r = __hmin2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
   return *reinterpret_cast<const uint32_t*>(&r);
+}
+// Explicit shared-window accesses with 32-bit addresses.  Pointers derived from the aligned dynamic-smem base lose their
+// address space (the compiler emits generic LD.E/ST.E with 64-bit address arithmetic); these keep LDS/STS.
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t hmax3_bf16(uint32_t a, uint32_t b, uint32_t c) {   // one VHMNMX
+  return hmax2_bf16(hmax2_bf16(a, b), c);
+}
+// The clamp-family activations (none / ReLU / ReLU6: lo in {-inf, 0}, hi in {+inf, 6}) on 16 packed pairs: the lower
+// bound rides on the conversion (F2FP.RELU), the upper bound is a packed bf16 min AFTER rounding (6.0 is exact in bf16
+// and rounding is monotonic, so min-then-round == round-then-min).  16 or 32 instructions instead of 64 FMNMX + 16 F2FP.
+__device__ __forceinline__ void clamp_pack32(const float (&v)[32], uint32_t (&o)[16], bool relu, bool capped, uint32_t cap2) {
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = pack_relu_bf16x2(v[2 * i], v[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+  }
+  if (capped) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = hmin2_bf16(o[i], cap2);
+  }
 }
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
