@@ -596,7 +596,14 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
     const char* e = getenv("PCV_IGEMM_2CTA");
     return !(e && e[0] == '0');
   }();
-  op->pair = pair_enabled && p.out_mode == 0 && d.Cout >= 64 && p.tiles_m >= 2;
+  // PCV_IGEMM2_MIN_COUT=16 sends narrow layers (MobileNetV2's 16/24/32-channel projections) to the pair kernel as a 64-wide
+  // tile with zero-weight padding columns and clipped stores.  Measured slower than the single-CTA kernel's 32-wide tiles
+  // (32->32 @112: 0.134 vs 0.116 ms: twice the TMEM reads and staging traffic for the padding), so the default stays 64.
+  static const int pair_min_cout = [] {
+    const char* e = getenv("PCV_IGEMM2_MIN_COUT");
+    return e ? atoi(e) : 64;
+  }();
+  op->pair = pair_enabled && p.out_mode == 0 && d.Cout >= pair_min_cout && d.Cout % 8 == 0 && p.tiles_m >= 2;
   if (op->pair) {
     op->bn = grouped ? 64 : (d.Cout > 128 ? 256 : (d.Cout > 64 ? 128 : 64));
     igemm2_pick_smem(op->bn, p.num_kblocks, res != nullptr, taps, &p.stages, &p.ksub, &p.nstg);

@@ -301,7 +301,8 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + col);
           float4 b4[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) b4[i] = __ldg(bias4 + i);
+          for (int i = 0; i < 8; ++i)   // columns past Cout (tile wider than the layer) are clipped by the store: no read there
+            b4[i] = (n0 + col + 4 * i < p.Cout) ? __ldg(bias4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
           const uint32_t row_off = row * 128 + h * 64;
           const uint32_t sw = (row & 7u) << 4;   // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
           uint4 r4[4];

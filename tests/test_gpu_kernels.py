@@ -12,6 +12,7 @@ from conftest import ROOT
 
 sys.path.insert(0, os.path.join(ROOT, "scripts"))
 import gpu_diag  # noqa: E402  (shares the conv case table with the first-light diagnostics)
+import stem_check  # noqa: E402  (space-to-depth stem cases, incl. the fused MaxPool2d(3, 2, 1))
 
 pytestmark = pytest.mark.gpu
 
@@ -24,6 +25,22 @@ def _rel(a, b):
 def test_conv_block_kernels(idx):
     r = gpu_diag.run_case(idx)
     assert r["ok"], r
+
+
+@pytest.mark.parametrize("idx", range(len(stem_check.CASES)), ids=[c[0] for c in stem_check.CASES])
+def test_s2d_stem_kernels(idx):
+    """ConvBlock(k x k, stride 2) on a 3-channel image [-> MaxPool2d(3, 2, 1)] (resnet.py:232-263, mobilenetv2.py:101,
+    senet.py:127-164) through the space-to-depth halo kernel; pooled cases must report the fused op."""
+    r = stem_check.run(idx)
+    assert r["ok"], r
+    assert r["ops"][0].startswith("conv_stem"), r["ops"]
+    name, k, cout, _, _, H, W = stem_check.CASES[idx]
+    if name.startswith("pool_"):
+        from pytorchcv_b200 import _lib
+        fused = bool(_lib.load().pcv_stem_s2d_pool_ok(3, H, W, k, cout))   # shared-memory fit decides (448x448 does not)
+        assert ("+maxpool3s2" in r["ops"][0]) == fused, r["ops"]
+        assert len(r["ops"]) == (2 if fused else 3), r["ops"]
+        assert fused or W > 256
 
 
 def _nhwc(x, dtype):
