@@ -212,6 +212,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     constexpr uint32_t SWZ_MASK = ROW_BYTES == 128 ? 7u : (ROW_BYTES == 64 ? 3u : 1u);
     const float act_lo = p.act_lo, act_hi = p.act_hi;
     const bool fancy_act = p.act > PCV_ACT_RELU6;
+    const bool relu = p.act_lo == 0.f, capped = p.act_hi != INFINITY;   // the clamp family: none / ReLU / ReLU6
+    const uint32_t cap2 = pack_bf16x2(p.act_hi, p.act_hi);
+    const uint32_t sStg_u32 = smem_u32(sStg);
     int it = 0;
     int sbuf = 0;           // staging ring position of this tile
     uint32_t sphase = 0;
@@ -223,6 +226,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int m0 = m_tile * BLOCK_M;
       const int n0 = n_tile * BN;
       uint8_t* stg = sStg + sbuf * L::STG_BYTES;
+      const uint32_t stg_u32 = sStg_u32 + sbuf * L::STG_BYTES;
 
       if (p.has_res && OUT_MODE == 0) mbar_wait(&res_full[sbuf], sphase);
       mbar_wait(&tmem_full[buf], acc_phase);
@@ -232,55 +236,61 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int j = 0; j < BN / 32; ++j) {
         uint32_t acc[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + j * 32, acc);
-        tmem_ld_wait();
-        float v[32];
+        // bias (and, staged mode, residual) loads issued under the TMEM load: the wait is a compiler barrier for memory ops
         const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + j * 32);
+        float4 b4[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)   // columns past Cout are clipped by the store: no read there
+          b4[i] = (n0 + j * 32 + 4 * i < p.Cout) ? __ldg(bias4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int col = j * 32;
+        const uint32_t sub_u32 = stg_u32 + (col / L::SUB_COLS) * L::SUB_BYTES;
+        const uint32_t row_off = row * ROW_BYTES + (col % L::SUB_COLS) * 2;
+        uint4 r4[4];
+        if (OUT_MODE == 0 && p.has_res) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t off = row_off + c * 16;
+            off ^= ((off >> 7) & SWZ_MASK) << 4;
+            r4[c] = lds128(sub_u32 + off);
+          }
+        }
+        tmem_ld_wait_regs(acc);
+        float v[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 b = __ldg(bias4 + i);
-          v[4 * i + 0] = __uint_as_float(acc[4 * i + 0]) + b.x;
-          v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b.y;
-          v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b.z;
-          v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b.w;
+          v[4 * i + 0] = __uint_as_float(acc[4 * i + 0]) + b4[i].x;
+          v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b4[i].y;
+          v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b4[i].z;
+          v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b4[i].w;
         }
         if (OUT_MODE == 0) {
           // staging sub-tile holding columns [j*32, j*32+32): row pitch ROW_BYTES, 16-byte chunks XOR-swizzled
-          const int col = j * 32;
-          uint8_t* sub = stg + (col / L::SUB_COLS) * L::SUB_BYTES;
-          const uint32_t row_off = row * ROW_BYTES + (col % L::SUB_COLS) * 2;
           if (p.has_res) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              uint32_t off = row_off + c * 16;
-              off ^= ((off >> 7) & SWZ_MASK) << 4;
-              const uint4 r = *reinterpret_cast<const uint4*>(sub + off);
-              v[8 * c + 0] += bf16lo(r.x);
-              v[8 * c + 1] += bf16hi(r.x);
-              v[8 * c + 2] += bf16lo(r.y);
-              v[8 * c + 3] += bf16hi(r.y);
-              v[8 * c + 4] += bf16lo(r.z);
-              v[8 * c + 5] += bf16hi(r.z);
-              v[8 * c + 6] += bf16lo(r.w);
-              v[8 * c + 7] += bf16hi(r.w);
+              v[8 * c + 0] += bf16lo(r4[c].x);
+              v[8 * c + 1] += bf16hi(r4[c].x);
+              v[8 * c + 2] += bf16lo(r4[c].y);
+              v[8 * c + 3] += bf16hi(r4[c].y);
+              v[8 * c + 4] += bf16lo(r4[c].z);
+              v[8 * c + 5] += bf16hi(r4[c].z);
+              v[8 * c + 6] += bf16lo(r4[c].w);
+              v[8 * c + 7] += bf16hi(r4[c].w);
             }
           }
+          uint32_t o[16];
           if (fancy_act) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+            clamp_pack32(v, o, false, false, 0u);
           } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], act_lo), act_hi);
+            clamp_pack32(v, o, relu, capped, cap2);
           }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint32_t off = row_off + c * 16;
             off ^= ((off >> 7) & SWZ_MASK) << 4;
-            uint4 o;
-            o.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]);
-            o.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
-            o.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
-            o.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
-            *reinterpret_cast<uint4*>(sub + off) = o;
+            sts128(sub_u32 + off, o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
           }
         } else {
           // direct global stores: any Cout / pitch, bf16 or fp32 output (classifier logits, 21-class heads)

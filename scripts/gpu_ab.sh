@@ -2,7 +2,7 @@
 # Same-box A/B of two library builds: pytorchcv_b200/libpcv_b200_prev.so (PCV_B200_LIB) against the in-tree build.
 mkdir -p gpurun_out
 MODELS=${MODELS:-"resnet50 mobilenetv2_w1 seresnext50_32x4d deeplabv3_resnetd50b_voc"}
-for rep in 1 2; do
+for rep in $(seq 1 ${REPS:-2}); do
 for m in $MODELS; do
   for which in prev new; do
     if [ $which = prev ]; then export PCV_B200_LIB=$PWD/pytorchcv_b200/libpcv_b200_prev.so; else unset PCV_B200_LIB; fi

@@ -74,7 +74,7 @@ def test_global_avgpool(shape, dtype, tol):
     assert _rel(got, want) <= tol
 
 
-@pytest.mark.parametrize("N,C,mid", [(4, 256, 16), (3, 2048, 128), (1, 64, 4)])
+@pytest.mark.parametrize("N,C,mid", [(4, 256, 16), (3, 2048, 128), (1, 64, 4), (70, 512, 32), (256, 1000, 60)])
 def test_se_excite_and_scale(N, C, mid):
     from pytorchcv_b200 import functional as P, _lib
     g = torch.Generator().manual_seed(3)
@@ -120,6 +120,10 @@ def test_bilinear_align_corners(dtype, tol):
     xin[..., :21] = _nhwc(x, dtype)
     got = P.bilinear_upsample_ac(xin, 120, 120, channels=21, nchw_f32=True).cpu()
     assert _rel(got, want) <= 1e-5 if dtype == torch.float32 else _rel(got, want) <= 1e-5 + 0
+    for size in ((24, 24), (44, 32)):                                 # ratios < 2 and 2..3: the per-element / 3-pixel paths
+        want_s = F.interpolate(x.to(dtype).float(), size=size, mode="bilinear", align_corners=True)
+        got_s = P.bilinear_upsample_ac(xin, size[0], size[1], channels=21, nchw_f32=True).cpu()
+        assert _rel(got_s, want_s) <= 1e-5
     x2 = torch.randn(2, 16, 1, 1, generator=g)                        # 1x1 source == pure broadcast (ASPP avg branch)
     got2 = _nchw(P.bilinear_upsample_ac(_nhwc(x2, dtype), 9, 9))
     assert _rel(got2, x2.to(dtype).float().expand(2, 16, 9, 9)) <= tol
