@@ -70,9 +70,9 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int ntaps = T * T;
   uint8_t* sB = smem;                                         // resident weights: ntaps x [BN/2 x 32 B]
   uint8_t* sA = sB + ((ntaps * B_BLOCK + 1023) & ~1023);
-  uint8_t* sStg = sA + p.NA * p.a_buf_bytes;                  // 2 output staging buffers
-  uint8_t* sPool = sStg + 2 * p.stg_bytes;                    // POOL: one staging buffer of R/2 pooled rows
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sPool + (POOL ? (p.R / 2) * p.WPP8 * BN * 2 : 0));
+  uint8_t* sStg = sA + p.NA * p.a_buf_bytes;                  // 2 output staging buffers (POOL: 1 buffer of R/2 vertically pooled rows)
+  uint8_t* sPool = sStg + (POOL ? 1 : 2) * p.stg_bytes;       // POOL: 2 staging buffers of R/2 pooled rows
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPool + (POOL ? 2 * (p.R / 2) * p.WPP8 * BN * 2 : 0));
   uint64_t* full = bars;                         // [NA]  leader's copy is live
   uint64_t* empty = bars + ST_MAX_NA;            // [NA]  per CTA, multicast commit
   uint64_t* b_full = bars + 2 * ST_MAX_NA;       // [1]   leader's copy
@@ -213,7 +213,133 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (POOL && warp >= 4) {
+    // ============================ epilogue with the max pool fused (both CTAs) ============================
+    // The pooled kernel runs with PW = 128 = BLOCK_M (the TMA box is 128 pixels wide whatever the s2d row width; the
+    // extra columns are out-of-bounds zero fill), so M-block mb IS conv row mb of the tile and TMEM lane c IS conv
+    // column c: a thread sees the same column of all R rows.  The vertical half of the separable 3x3 / stride-2 max
+    // therefore happens in REGISTERS on the packed bf16 values (max commutes with the monotonic ReLU + rounding),
+    // the row above the tile being carried in registers from the previous tile (contiguous tile schedule; warm-up
+    // tile), and only the R/2 vertically pooled rows are staged.  Pass 2 takes the horizontal 3-max at even columns
+    // from that buffer and hands the pooled rows to the TMA.  Shared-memory traffic of the pooling: 71 KB per tile
+    // instead of 164 KB - this kernel is bound by the shared-memory port (MMA operand reads included).
+    // Padding: row -1 of the image is skipped, column -1 is replaced by column 0 (max is idempotent).
+    pdl_wait();   // the output buffer may alias a tensor the previous kernel is still reading
+    const int q4 = warp & 3;
+    const int j = (warp - 4) >> 2;                 // this warp's 32-channel chunk, the same for every row
+    const int col = q4 * 32 + lane;                // conv column of this thread
+    const bool col_ok = col < p.Wo;
+    const float act_lo = p.act_lo, act_hi = p.act_hi;
+    const bool relu_only = act_lo == 0.f && act_hi == INFINITY;
+    const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+    const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
+    constexpr int ROWB = BN * 2;                   // 128 bytes per staged pixel (BN = 64)
+    float bias_r[32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + j * 32) + i);
+      bias_r[4 * i + 0] = b.x; bias_r[4 * i + 1] = b.y; bias_r[4 * i + 2] = b.z; bias_r[4 * i + 3] = b.w;
+    }
+    const uint32_t t_off0 = (static_cast<uint32_t>(q4 * 32) << 16) + j * 32;
+    const bool storer = warp == 4 && lane == 0;    // owns every bulk store group of this CTA
+    const uint32_t sV_u32 = smem_u32(sStg);        // [R/2][WP8] vertically pooled pixels
+    const uint32_t sPool_u32 = smem_u32(sPool);    // 2 x [R/2][WPP8] pooled pixels
+    const int tid = (warp - 4) * 32 + lane;        // 0..255 among the epilogue threads
+    const uint32_t v_rowb = p.WP8 * ROWB, p_rowb = p.WPP8 * ROWB;
+    const uint32_t pool_buf_bytes = (p.R / 2) * p_rowb;
+    // this thread's staged pixel: column `col`, chunks j*4 .. j*4+3, SWIZZLE_128B phase = col & 7 (WP8 % 8 == 0)
+    const uint32_t v_dst = sV_u32 + col * ROWB;
+    const uint32_t v_sw = col & 7u;
+    uint32_t prev[16];                             // packed row above the next row (carried across tiles)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) prev[i] = 0u;
+    for (int it = 0; it < n_iter; ++it) {
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      int tile;
+      bool live;
+      sched(it, tile, live);
+      const int img = tile / p.tiles_per_img;
+      const int h0 = (tile - img * p.tiles_per_img) * p.R;
+
+      mbar_wait(&tmem_full[buf], acc_phase);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + buf * acc_cols + t_off0;
+      uint32_t acc[2][32];
+      uint32_t v[16];
+      if (!(p.dbg & 2)) {
+        tmem_ld_32x32(tbase, acc[0]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {              // R <= 4 rows = M-blocks
+          if (r < p.R) {
+            tmem_ld_wait_regs(acc[r & 1]);
+            if (r + 1 < 4 && r + 1 < p.R) tmem_ld_32x32(tbase + (r + 1) * BN, acc[(r + 1) & 1]);
+            const uint32_t* a = acc[r & 1];
+            uint32_t o[16];
+            if (relu_only) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                o[i] = pack_relu_bf16x2(__uint_as_float(a[2 * i]) + bias_r[2 * i], __uint_as_float(a[2 * i + 1]) + bias_r[2 * i + 1]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                o[i] = pack_bf16x2(fminf(fmaxf(__uint_as_float(a[2 * i]) + bias_r[2 * i], act_lo), act_hi),
+                                   fminf(fmaxf(__uint_as_float(a[2 * i + 1]) + bias_r[2 * i + 1], act_lo), act_hi));
+            }
+            if ((r & 1) == 0) {                    // row 2pr: start pooled row pr with the row above (if inside the image)
+              const bool top = r == 0 && h0 == 0;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = top ? o[i] : hmax2_bf16(prev[i], o[i]);
+            } else {                               // row 2pr+1 completes it
+              if (col_ok) {
+                const uint32_t dstp = v_dst + (r >> 1) * v_rowb;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  sts128(dstp + (((j * 4 + i) ^ v_sw) << 4), hmax2_bf16(v[4 * i], o[4 * i]), hmax2_bf16(v[4 * i + 1], o[4 * i + 1]),
+                         hmax2_bf16(v[4 * i + 2], o[4 * i + 2]), hmax2_bf16(v[4 * i + 3], o[4 * i + 3]));
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) prev[i] = o[i];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&tmem_empty[buf]);
+        else mbar_arrive_cluster(buf ? tmem_empty_leader1 : tmem_empty_leader0);
+      }
+      if (storer) tma_store_wait_read<1>();         // the pooled rows of tile it-2 have left this sPool buffer
+      named_bar_sync(1, 256);                       // vertically pooled rows staged by all 8 warps; sPool[buf] free
+      const uint32_t pool_u32 = sPool_u32 + buf * pool_buf_bytes;
+      if (live && !(p.dbg & 16)) {
+        constexpr int CG = BN / 8;                  // 16-byte channel groups per pixel
+        const int per_row = p.Wp * CG;
+        for (int idx = tid; idx < (p.R / 2) * per_row; idx += 256) {
+          const int pr = idx >= per_row ? 1 : 0;    // R / 2 <= 2 pooled rows
+          const int rem = idx - pr * per_row;
+          const uint32_t cg = rem & (CG - 1);
+          const uint32_t px = rem >> 3;
+          const uint32_t c1 = 2 * px, c0 = c1 == 0 ? 0 : c1 - 1, c2 = c1 + 1;   // c2 <= Wo - 1: Wo is even
+          const uint32_t rowp = sV_u32 + pr * v_rowb;
+          const uint4 a = lds128(rowp + c0 * ROWB + ((cg ^ (c0 & 7u)) << 4));
+          const uint4 b = lds128(rowp + c1 * ROWB + ((cg ^ (c1 & 7u)) << 4));
+          const uint4 c = lds128(rowp + c2 * ROWB + ((cg ^ (c2 & 7u)) << 4));
+          sts128(pool_u32 + pr * p_rowb + px * ROWB + ((cg ^ (px & 7u)) << 4), hmax3_bf16(a.x, b.x, c.x),
+                 hmax3_bf16(a.y, b.y, c.y), hmax3_bf16(a.z, b.z, c.z), hmax3_bf16(a.w, b.w, c.w));
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(2, 256);                       // pooled rows staged; the vertical buffer may be overwritten
+      if (storer && live && !(p.dbg & 8)) {
+        for (int pr = 0; pr < p.R / 2; ++pr)
+          tma_store_4d(&tmOut, sPool + buf * pool_buf_bytes + pr * p_rowb, 0, 0, (h0 >> 1) + pr, img);
+        tma_store_commit();
+      }
+    }
+    if (storer) tma_store_wait_all<0>();
+  } else if (!POOL && warp >= 4) {
     // ===================================== epilogue (both CTAs) =====================================
     // eight warps: warp w owns TMEM lane quarter (w & 3) and every second (M-block, 32-column chunk) work item
     // w = half + 2k.  With CH = BN/32 chunks per M-block that is always the SAME chunk j (CH = 2: j = half, mb = k;
@@ -252,15 +378,14 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       st_r[k] = r;
     }
     const bool storer = warp == 4 && lane == 0;   // owns every bulk store group of this CTA
-    const uint32_t sStg_u32 = smem_u32(sStg), sPool_u32 = smem_u32(sPool);
-    const int tid = (warp - 4) * 32 + lane;       // 0..255 among the epilogue threads
+    const uint32_t sStg_u32 = smem_u32(sStg);
     for (int it = 0; it < n_iter; ++it) {
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       int tile;
       bool live;
       sched(it, tile, live);
-      const bool tile_ok = POOL ? true : live;   // POOL stages every tile (the warm-up tile supplies the carry row)
+      const bool tile_ok = live;
       const int img = tile / p.tiles_per_img;
       const int h0 = (tile - img * p.tiles_per_img) * p.R;
       uint8_t* stg = sStg + buf * p.stg_bytes;   // free: the storer waited for tile it-2's stores before barrier 1 of tile it-1
@@ -291,7 +416,7 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               o[i] = pack_bf16x2(fminf(fmaxf(__uint_as_float(a[2 * i]) + bias_r[2 * i], act_lo), act_hi),
                                  fminf(fmaxf(__uint_as_float(a[2 * i + 1]) + bias_r[2 * i + 1], act_lo), act_hi));
           }
-          if (st_off[k] >= 0 && tile_ok && (POOL || h0 + st_r[k] < p.Ho)) {
+          if (st_off[k] >= 0 && tile_ok && h0 + st_r[k] < p.Ho) {
             const uint32_t dstp = stg_u32 + st_off[k];
             // SWIZZLE_128B (128-byte pixels) / SWIZZLE_64B (64-byte pixels) chunk XOR from the staged pixel index
             const uint32_t sw = BN == 64 ? ((st_off[k] >> 7) & 7u) : ((st_off[k] >> 7) & 3u);
@@ -307,61 +432,13 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (rank == 0) mbar_arrive(&tmem_empty[buf]);
         else mbar_arrive_cluster(buf ? tmem_empty_leader1 : tmem_empty_leader0);
       }
-      if (!POOL) {
-        fence_proxy_async_smem();                   // this thread's st.shared -> visible to the TMA (async proxy)
-        if (storer) tma_store_wait_read<0>();       // tile it-1's stores have left the OTHER buffer (next tile's)
-        named_bar_sync(1, 256);                     // all 8 epilogue warps: tile staged, other buffer free
-        if (storer && tile_ok && !(p.dbg & 10)) {
-          for (int r = 0; r < p.R; ++r)
-            if (h0 + r < p.Ho) tma_store_4d(&tmOut, stg + r * p.WP8 * ROWB, 0, 0, h0 + r, img);
-          tma_store_commit();
-        }
-      } else {
-        if (storer) tma_store_wait_read<0>();       // the previous tile's pooled rows have left sPool
-        named_bar_sync(1, 256);                     // conv tile staged by all 8 warps; sPool free
-        if (live && !(p.dbg & 16)) {
-          // 3x3 / stride 2 / pad 1 max over the staged conv rows, separable and branch-free: a thread owns one 16-byte
-          // channel group of one pooled column and walks down the tile's rows keeping the horizontal 3-max of the last
-          // row (row 2pr+1 of pooled row pr is row 2(pr+1)-1 of the next).  Local row -1 = the last row of the previous
-          // tile, which this CTA staged one iteration ago in the other buffer (contiguous schedule).  Padding taps are
-          // replaced by a duplicate of an in-range tap (max is idempotent): column -1 -> column 0, row -1 of the
-          // image -> row 0.
-          const uint32_t prev = sStg_u32 + (buf ^ 1) * p.stg_bytes;
-          constexpr int CG = BN / 8;                // 16-byte channel groups per pixel
-          const uint32_t rowb = p.WP8 * ROWB, prowb = p.WPP8 * ROWB;
-          for (int idx = tid; idx < p.Wp * CG; idx += 256) {
-            const uint32_t cg = idx & (CG - 1);
-            const uint32_t px = idx >> 3;
-            const uint32_t c1 = 2 * px, c0 = c1 == 0 ? 0 : c1 - 1, c2 = c1 + 1;   // c2 <= Wo - 1: Wo is even
-            const uint32_t o0 = c0 * ROWB + ((cg ^ (c0 & 7u)) << 4);             // WP8 % 8 == 0: the swizzle phase is the column's
-            const uint32_t o1 = c1 * ROWB + ((cg ^ (c1 & 7u)) << 4);
-            const uint32_t o2 = c2 * ROWB + ((cg ^ (c2 & 7u)) << 4);
-            auto hrow = [&](uint32_t rowp) {
-              const uint4 a = lds128(rowp + o0), b = lds128(rowp + o1), c = lds128(rowp + o2);
-              return make_uint4(hmax3_bf16(a.x, b.x, c.x), hmax3_bf16(a.y, b.y, c.y), hmax3_bf16(a.z, b.z, c.z),
-                                hmax3_bf16(a.w, b.w, c.w));
-            };
-            uint4 up = hrow(h0 == 0 ? stg_u32 : prev + (p.R - 1) * rowb);
-            uint32_t src = stg_u32;
-            uint32_t pdst = sPool_u32 + px * ROWB + ((cg ^ (px & 7u)) << 4);   // WPP8 % 8 == 0
-#pragma unroll 2
-            for (int pr = 0; pr < p.R / 2; ++pr) {
-              const uint4 m0 = hrow(src);
-              const uint4 m1 = hrow(src + rowb);
-              sts128(pdst, hmax3_bf16(up.x, m0.x, m1.x), hmax3_bf16(up.y, m0.y, m1.y), hmax3_bf16(up.z, m0.z, m1.z),
-                     hmax3_bf16(up.w, m0.w, m1.w));
-              up = m1;
-              src += 2 * rowb;
-              pdst += prowb;
-            }
-          }
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(2, 256);                     // pooled rows staged (and every read of the carry row done)
-        if (storer && live && !(p.dbg & 8)) {
-          for (int pr = 0; pr < p.R / 2; ++pr) tma_store_4d(&tmOut, sPool + pr * p.WPP8 * ROWB, 0, 0, (h0 >> 1) + pr, img);
-          tma_store_commit();
-        }
+      fence_proxy_async_smem();                   // this thread's st.shared -> visible to the TMA (async proxy)
+      if (storer) tma_store_wait_read<0>();       // tile it-1's stores have left the OTHER buffer (next tile's)
+      named_bar_sync(1, 256);                     // all 8 epilogue warps: tile staged, other buffer free
+      if (storer && tile_ok && !(p.dbg & 10)) {
+        for (int r = 0; r < p.R; ++r)
+          if (h0 + r < p.Ho) tma_store_4d(&tmOut, stg + r * p.WP8 * ROWB, 0, 0, h0 + r, img);
+        tma_store_commit();
       }
     }
     if (storer) tma_store_wait_all<0>();
@@ -414,21 +491,13 @@ cudaError_t StemOp::launch(cudaStream_t s) {
   }
 }
 
-// Fused max pool (PCV_CONV_POOL3S2): rows per tile R (even, divides Ho) for a Ho x Wo conv map with T x T taps, or 0.
+// Fused max pool (PCV_CONV_POOL3S2): rows per tile R for a Ho x Wo conv map with T x T taps, or 0.  The pooled kernel
+// needs one conv row per 128-row M-block (PW = 128 >= Wo + T - 1: TMEM lane == column), an even R = NMB <= 4 that
+// divides Ho, and maps wide enough that padding every row to 128 pixels beats the separate pool kernel's extra pass.
+constexpr int ST_POOL_PW = BLOCK_M;
 static int stem_pool_rows(int Ho, int Wo, int T, int Cout) {
-  if (Cout != 64 || Ho % 2 != 0 || Wo % 2 != 0 || Wo + T - 1 > 256) return 0;
-  const int PW = Wo + T - 1;
-  for (int R = 8; R >= 2; R -= 2) {
-    if (Ho % R != 0) continue;
-    const int NMB = ceil_div(R * PW, BLOCK_M);
-    if (2 * NMB * 64 > 512) continue;
-    const int buf = round_up((NMB * BLOCK_M + (T - 1) * PW + T) * ST_ROW, 1024);
-    const int stg = round_up(R * round_up(Wo, 8) * 128, 1024);
-    const int pool = round_up((R / 2) * round_up(Wo / 2, 8) * 128, 1024);
-    const int b_bytes = round_up(T * T * 32 * ST_ROW, 1024);
-    if (1024 + 256 + b_bytes + 2 * buf + 2 * stg + pool <= 232448) return R;
-  }
-  return 0;
+  if (Cout != 64 || Ho % 2 != 0 || Wo % 2 != 0 || Wo + T - 1 > ST_POOL_PW || Wo < 64) return 0;
+  return Ho % 4 == 0 ? 4 : 2;
 }
 int stem_pool_ok(int C, int H, int W, int k, int Cout) {
   if (C < 1 || C > 4 || (k != 3 && k != 5 && k != 7) || H % 2 != 0 || W % 2 != 0) return 0;
@@ -464,13 +533,23 @@ int stem_halo_try_make(const pcv_conv_desc& d, const void* x, const void* w, con
   int bestR = 0, bestNA = 0, bestNMB = 0, best_buf = 0, best_stg = 0;
   const int poolR = pool ? stem_pool_rows(Ho, Wo, T, d.Cout) : 0;
   if (pool && poolR == 0) return PCV_ERR_UNSUPPORTED;
-  const int pool_bytes = pool ? round_up((poolR / 2) * round_up(Wo / 2, 8) * 128, 1024) : 0;
-  for (int R = pool ? poolR : 1; R <= (pool ? poolR : std::min(Ho, 64)); ++R) {
+  if (pool) {
+    // one conv row per M-block: the A box is ST_POOL_PW pixels wide (columns past the s2d row are zero-filled by the TMA)
+    const int R = poolR, NMB = R;
+    const int buf = round_up((NMB * BLOCK_M + (T - 1) * ST_POOL_PW + T) * ST_ROW, 1024);
+    const int stg = round_up((R / 2) * WP8 * BN * 2, 1024);                                // vertically pooled rows
+    const int pooled = 2 * (R / 2) * round_up(Wo / 2, 8) * BN * 2;                         // 2 buffers of pooled rows
+    const int NA = std::min(ST_MAX_NA, (budget - stg - round_up(pooled, 1024)) / buf);
+    if (NA < 2) return PCV_ERR_UNSUPPORTED;
+    bestR = R; bestNA = NA; bestNMB = NMB; best_buf = buf; best_stg = stg;
+  }
+  const int pool_bytes = pool ? round_up(2 * (poolR / 2) * round_up(Wo / 2, 8) * BN * 2, 1024) : 0;
+  for (int R = 1; !pool && R <= std::min(Ho, 64); ++R) {
     const int Q = R * PW, NMB = ceil_div(Q, BLOCK_M);
     if (2 * NMB * BN > 512 || R + T - 1 > 256) continue;
     const int buf = round_up((NMB * BLOCK_M + (T - 1) * PW + T) * ST_ROW, 1024);
     const int stg = round_up(R * WP8 * BN * 2, 1024);
-    const int NA = std::min(ST_MAX_NA, (budget - 2 * stg - pool_bytes) / buf);
+    const int NA = std::min(ST_MAX_NA, (budget - 2 * stg) / buf);
     if (NA < 2) continue;
     const int tiles = d.N * ceil_div(Ho, R);
     const int pair_tiles = (tiles + 1) / 2;
@@ -490,12 +569,13 @@ int stem_halo_try_make(const pcv_conv_desc& d, const void* x, const void* w, con
   p.out = reinterpret_cast<__nv_bfloat16*>(y);
   p.out_pitch = out_pitch;
   p.N = d.N; p.Ho = Ho; p.Wo = Wo; p.Cout = d.Cout;
-  p.R = bestR; p.PW = PW; p.NMB = bestNMB; p.T = T;
+  const int PWK = pool ? ST_POOL_PW : PW;   // pixels per staged A row (the kernel's row pitch)
+  p.R = bestR; p.PW = PWK; p.NMB = bestNMB; p.T = T;
   p.tiles_per_img = ceil_div(Ho, bestR);
   p.num_tiles = d.N * p.tiles_per_img;
   p.NA = bestNA;
   p.a_buf_bytes = best_buf;
-  p.a_tx_bytes = (bestR + T - 1) * PW * ST_ROW;
+  p.a_tx_bytes = (bestR + T - 1) * PWK * ST_ROW;
   p.WP8 = WP8;
   p.stg_bytes = best_stg;
   p.act_lo = (d.act == PCV_ACT_RELU || d.act == PCV_ACT_RELU6) ? 0.f : -INFINITY;
@@ -506,7 +586,7 @@ int stem_halo_try_make(const pcv_conv_desc& d, const void* x, const void* w, con
   }
   op->bn = BN;
   op->pool = pool;
-  op->smem_bytes = 1024 + b_bytes + bestNA * best_buf + 2 * best_stg + pool_bytes + 256;
+  op->smem_bytes = 1024 + b_bytes + bestNA * best_buf + (pool ? 1 : 2) * best_stg + pool_bytes + 256;
   op->grid = 2 * std::min((p.num_tiles + 1) / 2, pairs);
   p.tpc = ceil_div(p.num_tiles, op->grid);
   p.Hp = Ho / 2; p.Wp = Wo / 2; p.WPP8 = round_up(Wo / 2, 8);
@@ -516,7 +596,7 @@ int stem_halo_try_make(const pcv_conv_desc& d, const void* x, const void* w, con
   {
     cuuint64_t dims[4] = {16, (cuuint64_t)PW, (cuuint64_t)rows, (cuuint64_t)d.N};
     cuuint64_t strides[3] = {ST_ROW, (cuuint64_t)PW * ST_ROW, (cuuint64_t)rows * PW * ST_ROW};
-    cuuint32_t box[4] = {16, (cuuint32_t)PW, (cuuint32_t)(bestR + T - 1), 1};
+    cuuint32_t box[4] = {16, (cuuint32_t)PWK, (cuuint32_t)(bestR + T - 1), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(&op->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

@@ -131,6 +131,7 @@ class Builder:
         self.input_tref: TRef | None = None   # NHWC (channel-padded) image, set by CompiledModule
         self.image_channels = 0
         self.stem: dict | None = None         # {"k": kernel, "tref": s2d tensor} once the s2d stem is chosen
+        self.flops_override: dict[int, float] = {}   # op index -> algorithmic FLOPs where the kernel's GEMM view pads K
         self.ops: list[Callable[[Any, Callable[[TRef], int]], None]] = []
         self.bufs: list[Buf] = []
         self.weight_jobs: list[tuple] = []   # (kind, payload) resolved in materialise()
@@ -185,6 +186,9 @@ class Builder:
         self.weight_jobs.append(("conv_s2d", (d, conv, bn, k, w_off, b_off)))
         idx = len(self.ops)
         xs.buf.last = out.buf.last = idx
+        # FLOPs = 2 * MACs of the reference's k x k conv on C channels (the s2d GEMM computes (k+1)^2 * 4C
+        # products per output, zero weights included - that padding is not algorithmic work)
+        self.flops_override[idx] = 2.0 * x.N * Ho * Wo * cout * conv.in_channels * k * k
         dtype = self.dtype
         target = [out]   # maxpool() may retarget the op at the pooled map (PCV_CONV_POOL3S2)
         self.stem.update(out=out, idx=idx, desc=d, target=target,
@@ -674,6 +678,7 @@ class CompiledModule:
             except (_NoStemPool, _NoS2dStem):
                 continue   # retry order: drop the pool fusion first, then the s2d stem
         self._stem_k = b.stem["k"] if b.stem else 0
+        self._flops_override = dict(b.flops_override)
         self._in = b.stem["tref"] if b.stem else x
         self._in_channels = Cin
         self._structure, trefs = _flatten(result)
@@ -820,7 +825,8 @@ class CompiledModule:
         for i in range(n):
             fl, by = C.c_double(), C.c_double()
             _lib.call("pcv_plan_op_cost", self._plan, i, C.byref(fl), C.byref(by))
-            rows.append((lib.pcv_plan_op_name(self._plan, i).decode(), float(ms[i]), fl.value, by.value))
+            rows.append((lib.pcv_plan_op_name(self._plan, i).decode(), float(ms[i]),
+                         self._flops_override.get(i, fl.value), by.value))
         return rows
 
     def __del__(self):

@@ -23,6 +23,12 @@ CASES = [  # name, k, Cout, act, N, H, W
     ("pool_stem7_64_small", 7, 64, "relu", 5, 64, 64),
     ("pool_stem3_64_160", 3, 64, "relu", 2, 160, 96),
     ("pool_stem7_64_448", 7, 64, "relu", 1, 448, 448),
+    # fused-pool geometry edges: 124-column map (127-pixel s2d rows), R = 2 (Ho % 4 != 0), 80 columns, 3x3 stem, ReLU6
+    ("pool_stem7_64_w248", 7, 64, "relu", 2, 200, 248),
+    ("pool_stem7_64_h228", 7, 64, "relu", 3, 228, 224),
+    ("pool_stem7_64_w160", 7, 64, "relu", 5, 256, 160),
+    ("pool_stem3_64_224", 3, 64, "relu6", 2, 224, 224),
+    ("pool_stem5_64_192", 5, 64, "relu", 2, 192, 192),
 ]
 
 
