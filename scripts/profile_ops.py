@@ -1,6 +1,6 @@
 """Run a fixed list of hot-path ops in isolation, one process, for `ncu` captures and quick CUDA-event timing.
 
-    python scripts/profile_ops.py [--set resnet50|mobilenet|se|all] [--reps 3] [--only SUBSTR]
+    python scripts/profile_ops.py [--set resnet50|mobilenet|se|all] [--reps 3] [--only SUBSTR[,SUBSTR...]]
 
 Each op is launched `--warm` times untimed and `--reps` times timed; L2 is flushed (a 256 MB memset) before every
 timed launch so the number is the cold-L2 figure the roofline (HBM) is quoted against.  Prints one line per op:
@@ -82,7 +82,7 @@ def main():
     sets = list(CONVS) if a.set == "all" else a.set.split(",")
     for s in sets:
         for (name, N, H, Cin, Cout, k, stride, dil, groups, res, act) in CONVS.get(s, []):
-            if a.only and a.only not in name:
+            if a.only and not any(o in name for o in a.only.split(",")):
                 continue
             pad = dil * (k // 2)
             x = torch.randn(N, H, H, Cin, generator=g).to(dev).to(torch.bfloat16)
