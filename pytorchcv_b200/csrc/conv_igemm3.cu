@@ -182,18 +182,27 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           mbar_wait(&full[slot], phase);
           tc_fence_after();
           const uint32_t a_buf = a_lo0 + slot * (p.a_buf_bytes >> 4);
-          int tap = 0;
-          for (int fr = 0; fr < ((p.dbg & 1) ? 0 : 3); ++fr) {
-            for (int fs = 0; fs < 3; ++fs, ++tap) {
-              const uint32_t b_lo = b_lo0 + (g * 9 * p.cblocks + tap * p.cblocks + cb) * b_step;
-              const uint32_t a_tap = a_buf + (fr * p.PW + fs) * (128 >> 4);
-              const uint32_t acc = (cb | tap) != 0 ? 1u : 0u;
-              for (int mb = 0; mb < p.NMB; ++mb) {
-                const uint32_t a_lo = a_tap + mb * (BLOCK_M * 128 >> 4);
-                if (elect_one()) {
+          // All 9 taps x 4 K-steps of one M-block inside ONE elect.sync region with compile-time tap indices: descriptors
+          // are formed with uniform adds and the 36 UTCHMMAs issue back to back.  (One region per (tap, M-block) - 4 MMAs
+          // behind ~30 R2UR / UMOV instructions - left the N = 64 / N = 128 MMAs issue-bound at 78 / 123 cycles each,
+          // against 60 for the stem kernel's shared-memory-bound stream.)
+          const uint32_t row_step = p.PW * (128 >> 4);
+          const uint32_t tap_step = p.cblocks * b_step;
+          const uint32_t b_cb = b_lo0 + (g * 9 * p.cblocks + cb) * b_step;
+          for (int mb = 0; mb < ((p.dbg & 1) ? 0 : p.NMB); ++mb) {
+            const uint32_t a_mb = a_buf + mb * (BLOCK_M * 128 >> 4);
+            const uint32_t d_mb = d_tmem + mb * BN;
+            if (elect_one()) {
+#pragma unroll
+              for (int fr = 0; fr < 3; ++fr) {
+                const uint32_t a_row = a_mb + fr * row_step;
+#pragma unroll
+                for (int fs = 0; fs < 3; ++fs) {
+                  const uint32_t a_lo = a_row + fs * (128 >> 4);
+                  const uint32_t b_lo = b_cb + (fr * 3 + fs) * tap_step;
 #pragma unroll
                   for (int k = 0; k < BLOCK_K / 16; ++k)
-                    umma2_bf16_lohi(d_tmem + mb * BN, a_lo + 2 * k, b_lo + 2 * k, idesc, (k != 0) ? 1u : acc);
+                    umma2_bf16_lohi(d_mb, a_lo + 2 * k, b_lo + 2 * k, idesc, (fr | fs | k) != 0 ? 1u : (cb != 0 ? 1u : 0u));
                 }
               }
             }
