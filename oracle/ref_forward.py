@@ -236,6 +236,53 @@ def deeplabv3(m, x):
     return x
 
 
+# ---- EfficientNet -----------------------------------------------------------------------------------
+def _tf_pad(x, kernel_size, stride=1, dilation=1):
+    """calc_tf_padding (efficientnet.py:27-55) applied with F.pad, as the tf_mode forwards do."""
+    import math
+    h, w = x.shape[2:]
+    oh, ow = math.ceil(h / stride), math.ceil(w / stride)
+    ph = max((oh - 1) * stride + (kernel_size - 1) * dilation + 1 - h, 0)
+    pw = max((ow - 1) * stride + (kernel_size - 1) * dilation + 1 - w, 0)
+    return F.pad(x, (ph // 2, ph - ph // 2, pw // 2, pw - pw // 2))
+
+
+def effi_init_block(m, x):
+    """EffiInitBlock.forward (efficientnet.py:235-239)."""
+    if m.tf_mode:
+        x = _tf_pad(x, 3, 2)
+    return conv_block(m.conv, x)
+
+
+def effi_dws_conv_unit(m, x):
+    """EffiDwsConvUnit.forward (efficientnet.py:105-115)."""
+    identity = x
+    if m.tf_mode:
+        x = _tf_pad(x, 3)
+    x = conv_block(m.pw_conv, se_block(m.se, conv_block(m.dw_conv, x)))
+    return x + identity if m.residual else x
+
+
+def effi_inv_res_unit(m, x):
+    """EffiInvResUnit.forward (efficientnet.py:185-197)."""
+    identity = x
+    x = conv_block(m.conv1, x)
+    if m.tf_mode:
+        x = _tf_pad(x, m.kernel_size, m.stride)
+    x = conv_block(m.conv2, x)
+    if m.use_se:
+        x = se_block(m.se, x)
+    x = conv_block(m.conv3, x)
+    return x + identity if m.residual else x
+
+
+def efficientnet(m, x):
+    """EfficientNet.forward (efficientnet.py:354-358): features -> view -> output (Dropout is the identity in eval)."""
+    x = oracle_forward(m.features, x)
+    x = x.view(x.size(0), -1)
+    return sequential(m.output, x)
+
+
 # ---- dispatch --------------------------------------------------------------------------------------------------------
 def _leaf(m, x):
     if isinstance(m, nn.Conv2d):
@@ -262,6 +309,8 @@ _BY_NAME = {
     "ResInitBlock": res_init_block, "SEInitBlock": se_init_block, "LinearBottleneck": linear_bottleneck,
     "ResNet": classifier, "SEResNeXt": classifier, "ResNeXt": classifier, "MobileNet": classifier,
     "MobileNetV2": mobilenetv2, "ResNetD": resnetd,
+    "EffiInitBlock": effi_init_block, "EffiDwsConvUnit": effi_dws_conv_unit, "EffiInvResUnit": effi_inv_res_unit,
+    "EfficientNet": efficientnet,
     "Concurrent": concurrent, "MultiOutputSequential": multi_output_sequential,
     "ASPPAvgBranch": aspp_avg_branch, "AtrousSpatialPyramidPooling": aspp, "DeepLabv3": deeplabv3,
 }

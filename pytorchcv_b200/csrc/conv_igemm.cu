@@ -280,8 +280,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           uint32_t o[16];
           if (fancy_act) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+            fast_act_n(v, p.act);
             clamp_pack32(v, o, false, false, 0u);
           } else {
             clamp_pack32(v, o, relu, capped, cap2);
@@ -304,8 +303,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (i < ncol) v[i] += __bfloat162float(rp[i]);
             }
             if (fancy_act) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+              fast_act_n(v, p.act);
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], act_lo), act_hi);

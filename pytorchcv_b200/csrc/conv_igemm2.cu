@@ -334,8 +334,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           }
           uint32_t o[16];
           if (fancy_act) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+            fast_act_n(v, p.act);
             clamp_pack32(v, o, false, false, 0u);
           } else {
             clamp_pack32(v, o, relu, capped, cap2);

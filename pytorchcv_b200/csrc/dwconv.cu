@@ -125,8 +125,12 @@ dwconv_strip_kernel(const DwParams p, const T* __restrict__ x, const float* __re
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[t][e] += rv[e];
       }
+      if (sizeof(T) == 2) {
+        fast_act_n(acc[t], p.act);          // bf16 tier: MUFU.TANH based swish / sigmoid (ptx.cuh)
+      } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[t][e] = dw_act(acc[t][e], p.act);
+        for (int e = 0; e < 8; ++e) acc[t][e] = dw_act(acc[t][e], p.act);
+      }
       Vec8<T>::store(y + pix * p.out_pitch + c, acc[t]);
     }
   }
@@ -169,8 +173,12 @@ dwconv_generic_kernel(const DwParams p, const T* __restrict__ x, const float* __
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] += rv[e];
     }
+    if (sizeof(T) == 2) {
+      fast_act_n(acc, p.act);
+    } else {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = dw_act(acc[e], p.act);
+      for (int e = 0; e < 8; ++e) acc[e] = dw_act(acc[e], p.act);
+    }
     Vec8<T>::store(y + pix * p.out_pitch + c, acc);
   }
 }

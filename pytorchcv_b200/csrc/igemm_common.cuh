@@ -32,21 +32,6 @@ struct IgemmParams {
   int nsubs;                  // CTA-pair kernel: 64-column sub-tiles per tile (tile width = nsubs*64 <= BN), per layer
 };
 
-// Rare activations (sigmoid / swish / h-swish / h-sigmoid): kept out of line so the hot epilogue stays compact —
-// an inlined 7-way switch per element blew the epilogue up to ~100 KB of SASS and made it instruction-fetch bound.
-static __device__ __noinline__ float apply_act(float v, int act) {
-  switch (act) {
-    case PCV_ACT_RELU: return fmaxf(v, 0.f);
-    case PCV_ACT_RELU6: return fminf(fmaxf(v, 0.f), 6.f);
-    case PCV_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
-    case PCV_ACT_SWISH: return v / (1.f + __expf(-v));
-    case PCV_ACT_HSWISH: return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
-    case PCV_ACT_HSIGMOID: return fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
-    default: return v;
-  }
-}
-
-
 // conv_igemm2.cu: launch the cta_group::2 kernel (BN = 128 or 256) on `grid` CTAs (a multiple of 2)
 cudaError_t launch_igemm2(int bn, int grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                           const CUtensorMap& tmRes, const IgemmParams& p, cudaStream_t s);

@@ -329,6 +329,46 @@ __device__ __forceinline__ void clamp_pack32(const float (&v)[32], uint32_t (&o)
     for (int i = 0; i < 16; ++i) o[i] = hmin2_bf16(o[i], cap2);
   }
 }
+// bf16-tier versions of the smooth activations (activ.py:16-47): one MUFU.TANH instead of ex2 + a full-precision
+// division.  sigmoid(x) = 0.5 + 0.5 tanh(x/2); tanh.approx.f32 has ~2^-11 relative error, below the bf16 the result is
+// rounded to.  The fp32 tier (conv_simt.cu, misc.cu) keeps expf.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
+__device__ __forceinline__ float fast_swish(float x) {
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(h), h);
+}
+__device__ __forceinline__ float fast_hsigmoid(float x) { return fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f); }
+__device__ __forceinline__ float fast_hswish(float x) { return x * fast_hsigmoid(x); }
+// One activation over N register values with the switch OUTSIDE the element loop (an inlined per-element switch is what
+// once blew the epilogue up to 100 KB of SASS).  Codes are pcv_act (include/pcv_b200.h): 3 sigmoid, 4 swish, 5 h-swish,
+// 6 h-sigmoid; the clamp family (0..2) is handled by the callers' packed paths.
+template <int N>
+__device__ __forceinline__ void fast_act_n(float (&v)[N], int act) {
+  if (act == 4) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = fast_swish(v[i]);
+  } else if (act == 5) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = fast_hswish(v[i]);
+  } else if (act == 3) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = fast_sigmoid(v[i]);
+  } else if (act == 6) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = fast_hsigmoid(v[i]);
+  } else if (act == 1) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (act == 2) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = fminf(fmaxf(v[i], 0.f), 6.f);
+  }
+}
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 

@@ -34,6 +34,7 @@ struct WinParams {
   int items;          // active threads per tile: TW * CB / 4
   int stages, stage_bytes, tx_bytes;   // smem stride of a stage (128 B multiple) / exact bytes of one TMA box
   float act_lo, act_hi;
+  int act;                             // pcv_act; > ReLU6 (swish family) takes the fp32 path before packing
 };
 
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,
@@ -97,7 +98,7 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 // OP 0: depthwise conv, 1: max pool.  COLS = adjacent output columns per thread (their windows overlap, so the shared
 // input columns are loaded and converted once).  RES = residual add in the epilogue.
 template <int OP, int KS, int S, int TH, int COLS, bool RES>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, KS == 5 ? 1 : 2)   // 5x5: 25 taps x 4 channels of fp32 weights live in registers
 win_kernel(const __grid_constant__ CUtensorMap tmIn, const WinParams p, const float* __restrict__ w,
            const float* __restrict__ bias, const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y) {
   constexpr int IH = (TH - 1) * S + KS;
@@ -252,6 +253,12 @@ win_kernel(const __grid_constant__ CUtensorMap tmIn, const WinParams p, const fl
                   if (live) rr = __ldg(reinterpret_cast<const uint2*>(res + (ro + ho * r_row + cc * res_pitch)));
                   r0.x += bf16lo(rr.x); r0.y += bf16hi(rr.x); r1.x += bf16lo(rr.y); r1.y += bf16hi(rr.y);
                 }
+                if (p.act > PCV_ACT_RELU6) {   // swish / h-swish / (h-)sigmoid (EfficientNet, MobileNetV3): warp-uniform
+                  float f[4] = {r0.x, r0.y, r1.x, r1.y};
+                  fast_act_n(f, p.act);
+                  r0 = make_float2(f[0], f[1]);
+                  r1 = make_float2(f[2], f[3]);
+                }
                 // clamp AFTER rounding to bf16: the bounds (0, 6, +-inf) are bf16-exact and rounding is monotone,
                 // so this equals round(clamp(x)) at half the instruction count (packed bf16x2 min / max)
                 o.x = hclamp2_u32(pack_bf16x2(r0.x, r0.y), act_lo2, act_hi2);
@@ -350,33 +357,37 @@ struct WinOp : Op {
   CUtensorMap tm;
   WinParams p;
   WinCfg cfg;
-  int op_kind, S;
+  int op_kind, S, K = 3;
   const float *w, *bias;
   const __nv_bfloat16* res;
   __nv_bfloat16* y;
 
-  template <int OP, int S_, int TH, int COLS, bool RES>
+  template <int OP, int K_, int S_, int TH, int COLS, bool RES>
   cudaError_t go(cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(win_kernel<OP, 3, S_, TH, COLS, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaError_t e = cudaFuncSetAttribute(win_kernel<OP, K_, S_, TH, COLS, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            112 * 1024);
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
     const long long cap = static_cast<long long>(sm_count()) * cfg.ctas_per_sm;
     const int grid = static_cast<int>(std::min<long long>(p.num_tiles, cap));
-    return launch_pdl(win_kernel<OP, 3, S_, TH, COLS, RES>, dim3(grid), dim3(cfg.threads), cfg.smem_bytes, s, tm, p, w, bias, res, y);
+    return launch_pdl(win_kernel<OP, K_, S_, TH, COLS, RES>, dim3(grid), dim3(cfg.threads), cfg.smem_bytes, s, tm, p, w, bias, res, y);
   }
-  template <int OP, int S_, int COLS, bool RES>
+  template <int OP, int K_, int S_, int COLS, bool RES>
   cudaError_t go_th(cudaStream_t s) {
-    return cfg.TH == 7 ? go<OP, S_, 7, COLS, RES>(s) : go<OP, S_, 8, COLS, RES>(s);
+    return cfg.TH == 7 ? go<OP, K_, S_, 7, COLS, RES>(s) : go<OP, K_, S_, 8, COLS, RES>(s);
   }
   cudaError_t launch(cudaStream_t s) override {
     g_launches++;
-    if (op_kind == 1) return S == 1 ? go_th<1, 1, 1, false>(s) : go_th<1, 2, 1, false>(s);
-    if (S == 1) return res ? go_th<0, 1, 2, true>(s) : go_th<0, 1, 2, false>(s);
-    return res ? go_th<0, 2, 1, true>(s) : go_th<0, 2, 1, false>(s);
+    if (op_kind == 1) return S == 1 ? go_th<1, 3, 1, 1, false>(s) : go_th<1, 3, 2, 1, false>(s);
+    if (K == 5) {   // dwconv5x5_block (conv.py:511-543): one output column per thread
+      if (S == 1) return res ? go_th<0, 5, 1, 1, true>(s) : go_th<0, 5, 1, 1, false>(s);
+      return res ? go_th<0, 5, 2, 1, true>(s) : go_th<0, 5, 2, 1, false>(s);
+    }
+    if (S == 1) return res ? go_th<0, 3, 1, 2, true>(s) : go_th<0, 3, 1, 2, false>(s);
+    return res ? go_th<0, 3, 2, 1, true>(s) : go_th<0, 3, 2, 1, false>(s);
   }
 };
 
@@ -384,8 +395,8 @@ struct WinOp : Op {
 // and the caller should use its generic kernel.
 int win_make(int op_kind, int N, int H, int W, int C, int k, int stride, int pad, int act, const void* x, int in_pitch,
              const float* w, const float* bias, const void* res, int res_pitch, void* y, int out_pitch, Op** out) {
-  if (k != 3 || (stride != 1 && stride != 2) || pad > 1 || C % 8 != 0 || in_pitch % 8 != 0 || out_pitch % 4 != 0 ||
-      (res && res_pitch % 4 != 0) || act > PCV_ACT_RELU6 || reinterpret_cast<uintptr_t>(x) % 16 != 0 ||
+  if ((k != 3 && !(k == 5 && op_kind == 0)) || (stride != 1 && stride != 2) || pad > k / 2 || C % 8 != 0 || in_pitch % 8 != 0 || out_pitch % 4 != 0 ||
+      (res && res_pitch % 4 != 0) || act > PCV_ACT_HSIGMOID || reinterpret_cast<uintptr_t>(x) % 16 != 0 ||
       reinterpret_cast<uintptr_t>(y) % 8 != 0 || reinterpret_cast<uintptr_t>(res) % 8 != 0)
     return PCV_ERR_UNSUPPORTED;
   if (getenv("PCV_WIN_TMA") && getenv("PCV_WIN_TMA")[0] == '0') return PCV_ERR_UNSUPPORTED;
@@ -398,14 +409,16 @@ int win_make(int op_kind, int N, int H, int W, int C, int k, int stride, int pad
   p.pad = pad; p.out_pitch = out_pitch; p.res_pitch = res_pitch;
   p.act_lo = (act == PCV_ACT_RELU || act == PCV_ACT_RELU6) ? 0.f : -INFINITY;
   p.act_hi = act == PCV_ACT_RELU6 ? 6.f : INFINITY;
-  const int cols = (op_kind == 0 && stride == 1) ? 2 : 1;   // must match the COLS template argument picked in launch()
+  p.act = act;
+  const int cols = (op_kind == 0 && stride == 1 && k == 3) ? 2 : 1;   // must match the COLS template argument picked in launch()
   if (!pick_cfg(C, p.Ho, p.Wo, k, stride, cols, &p, &op->cfg)) return PCV_ERR_UNSUPPORTED;
   p.num_tiles = static_cast<long long>(N) * p.tiles_y * p.tiles_x * p.cblocks;
   if (p.num_tiles >= (1ll << 31)) return PCV_ERR_UNSUPPORTED;
   if (static_cast<long long>(N) * p.Ho * p.Wo * std::max(out_pitch, res_pitch) >= (1ll << 31)) return PCV_ERR_UNSUPPORTED;
   const int IH = (op->cfg.TH - 1) * stride + k;
   if (int rc = make_win_map(&op->tm, x, N, H, W, C, in_pitch, p.CB, p.IW, IH)) return rc;
-  op->op_kind = op_kind; op->S = stride; op->w = w; op->bias = bias;
+  op->op_kind = op_kind; op->S = stride; op->K = k; op->w = w; op->bias = bias;
+  if (k == 5) op->cfg.ctas_per_sm = 1;   // __launch_bounds__(256, 1)
   op->res = reinterpret_cast<const __nv_bfloat16*>(res);
   op->y = reinterpret_cast<__nv_bfloat16*>(y);
   *out = op.release();

@@ -32,6 +32,9 @@ for _name, (_b, _c, _w) in nets.RESNEXT_VARIANTS.items():
 for _name, _b in nets.RESNETD_VARIANTS.items():
     _register(_name, (lambda n, b: lambda **kw: nets.get_resnetd(
         blocks=b, conv1_stride=False, model_name=n, **kw))(_name, _b))
+for _name, (_v, _sz) in nets.EFFICIENTNET_VARIANTS.items():
+    _register(_name, (lambda n, v, sz: lambda in_size=None, **kw: nets.get_efficientnet(
+        version=v, in_size=in_size if in_size is not None else (sz, sz), model_name=n, **kw))(_name, _v, _sz))
 for _name, (_b, _k) in nets.DEEPLABV3_VARIANTS.items():
     _register(_name, nets._deeplab_ctor(_name, _b, _k))
 

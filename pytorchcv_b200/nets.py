@@ -2,7 +2,8 @@
 
 ResNet (models/resnet.py), MobileNetV2 (models/mobilenetv2.py), ResNeXt / SE-ResNeXt (models/resnext.py,
 models/seresnext.py), SEInitBlock (models/senet.py:127-164), ResNet(D) (models/resnetd.py), DeepLabv3
-(models/deeplabv3.py) and, as the DwsConvBlock vehicle, MobileNet (models/mobilenet.py).
+(models/deeplabv3.py), as the DwsConvBlock vehicle MobileNet (models/mobilenet.py), and - first row of SURVEY 8(f):
+swish epilogues, SE with a swish bottleneck inside the unit, 5x5 depthwise - EfficientNet (models/efficientnet.py).
 
 Class names, attribute names, constructor kwargs, module registration order (hence state_dict keys AND the RNG
 stream consumed by `torch.manual_seed(s); get_model(...)`) follow the reference, so seeds and checkpoints carry over.
@@ -15,7 +16,8 @@ import math
 import torch.nn as nn
 
 from .blocks import (B200Module, SEBlock, conv1x1, conv1x1_block, conv3x3_block, conv7x7_block, dwconv3x3_block,
-                     dwsconv3x3_block, lambda_batchnorm2d, lambda_relu, lambda_relu6)
+                     dwconv5x5_block, dwsconv3x3_block, lambda_batchnorm2d, lambda_relu, lambda_relu6, lambda_swish,
+                     round_channels)
 from .plan import run_module
 
 
@@ -273,6 +275,134 @@ MOBILENETV2_VARIANTS = {
     "mobilenetv2b_wd2": dict(width_scale=0.5, remove_exp_conv=True),
     "mobilenetv2b_wd4": dict(width_scale=0.25, remove_exp_conv=True),
 }
+
+
+# ===== EfficientNet (efficientnet.py), SURVEY 8(f) rank 1 ===========================================================
+def _no_tf_mode(tf_mode: bool) -> None:
+    if tf_mode:
+        raise NotImplementedError("EfficientNet tf_mode=True pads asymmetrically per input size (efficientnet.py:27-55); "
+                                  "only the symmetric-padding variants (efficientnet_b0..b8) are on the B200 eval path")
+
+
+class EffiDwsConvUnit(B200Module):
+    """dw3x3 -> SE(reduction 4, swish bottleneck) -> 1x1 linear (+x) (efficientnet.py:58-115)."""
+
+    def __init__(self, in_channels, out_channels, stride, normalization, activation, tf_mode):
+        super().__init__()
+        _no_tf_mode(tf_mode)
+        self.tf_mode = tf_mode
+        self.residual = (in_channels == out_channels) and (stride == 1)
+        self.dw_conv = dwconv3x3_block(in_channels=in_channels, out_channels=in_channels, padding=1,
+                                       normalization=normalization, activation=activation)
+        self.se = SEBlock(channels=in_channels, reduction=4, mid_activation=activation)
+        self.pw_conv = conv1x1_block(in_channels=in_channels, out_channels=out_channels, normalization=normalization,
+                                     activation=None)
+
+
+class EffiInvResUnit(B200Module):
+    """1x1 expand -> dw kxk (k in {3, 5}) -> [SE] -> 1x1 linear (+x) (efficientnet.py:118-197)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, exp_factor, se_factor, normalization, activation,
+                 tf_mode):
+        super().__init__()
+        _no_tf_mode(tf_mode)
+        self.kernel_size, self.stride, self.tf_mode = kernel_size, stride, tf_mode
+        self.residual = (in_channels == out_channels) and (stride == 1)
+        self.use_se = se_factor > 0
+        mid = in_channels * exp_factor
+        dw = dwconv3x3_block if kernel_size == 3 else (dwconv5x5_block if kernel_size == 5 else None)
+        self.conv1 = conv1x1_block(in_channels=in_channels, out_channels=mid, normalization=normalization,
+                                   activation=activation)
+        self.conv2 = dw(in_channels=mid, out_channels=mid, stride=stride, padding=kernel_size // 2,
+                        normalization=normalization, activation=activation)
+        if self.use_se:
+            self.se = SEBlock(channels=mid, reduction=exp_factor * se_factor, mid_activation=activation)
+        self.conv3 = conv1x1_block(in_channels=mid, out_channels=out_channels, normalization=normalization,
+                                   activation=None)
+
+
+class EffiInitBlock(B200Module):
+    """conv3x3 stride 2 with swish (efficientnet.py:200-239)."""
+
+    def __init__(self, in_channels, out_channels, normalization, activation, tf_mode):
+        super().__init__()
+        _no_tf_mode(tf_mode)
+        self.tf_mode = tf_mode
+        self.conv = conv3x3_block(in_channels=in_channels, out_channels=out_channels, stride=2, padding=1,
+                                  normalization=normalization, activation=activation)
+
+
+class EfficientNet(B200Module):
+    """efficientnet.py:242-360: init block, one EffiDwsConvUnit stage, six EffiInvResUnit stages, 1x1 final block,
+    global pool, [dropout,] Linear."""
+
+    def __init__(self, channels, init_block_channels, final_block_channels, kernel_sizes, strides_per_stage,
+                 expansion_factors, dropout_rate=0.2, tf_mode=False, bn_eps=1e-5, in_channels=3, in_size=(224, 224),
+                 num_classes=1000):
+        super().__init__()
+        self.in_size, self.num_classes = in_size, num_classes
+        norm, act = lambda_batchnorm2d(eps=bn_eps), lambda_swish()
+        self.features = nn.Sequential()
+        self.features.add_module("init_block", EffiInitBlock(in_channels=in_channels, out_channels=init_block_channels,
+                                                             normalization=norm, activation=act, tf_mode=tf_mode))
+
+        def unit(i, j, cin, cout, stride):
+            if i == 0:
+                return EffiDwsConvUnit(in_channels=cin, out_channels=cout, stride=stride, normalization=norm,
+                                       activation=act, tf_mode=tf_mode)
+            return EffiInvResUnit(in_channels=cin, out_channels=cout, kernel_size=kernel_sizes[i][j], stride=stride,
+                                  exp_factor=expansion_factors[i][j], se_factor=4, normalization=norm, activation=act,
+                                  tf_mode=tf_mode)
+
+        last = _stages(self.features, channels, init_block_channels, unit,
+                       stride_of=lambda i, j: strides_per_stage[i] if j == 0 else 1)
+        self.features.add_module("final_block", conv1x1_block(in_channels=last, out_channels=final_block_channels,
+                                                              normalization=norm, activation=act))
+        self.features.add_module("final_pool", nn.AdaptiveAvgPool2d(output_size=1))
+        self.output = nn.Sequential()
+        if dropout_rate > 0.0:
+            self.output.add_module("dropout", nn.Dropout(p=dropout_rate))
+        self.output.add_module("fc", nn.Linear(in_features=final_block_channels, out_features=num_classes))
+        _kaiming_init(self)
+
+
+# version -> (input size, depth factor, width factor, dropout) (efficientnet.py:392-438)
+_EFFICIENTNET_SCALING = {
+    "b0": (224, 1.0, 1.0, 0.2), "b1": (240, 1.1, 1.0, 0.2), "b2": (260, 1.2, 1.1, 0.3), "b3": (300, 1.4, 1.2, 0.3),
+    "b4": (380, 1.8, 1.4, 0.4), "b5": (456, 2.2, 1.6, 0.4), "b6": (528, 2.6, 1.8, 0.5), "b7": (600, 3.1, 2.0, 0.5),
+    "b8": (672, 3.6, 2.2, 0.5),
+}
+
+
+def get_efficientnet(version, in_size, tf_mode=False, bn_eps=1e-5, model_name=None, pretrained=False, root=None,
+                     **kwargs):
+    """Same contract as efficientnet.py:360-490 (compound scaling of depth / width per version)."""
+    if version not in _EFFICIENTNET_SCALING:
+        raise ValueError("Unsupported EfficientNet version {}".format(version))
+    size, depth, width, dropout = _EFFICIENTNET_SCALING[version]
+    assert in_size == (size, size)
+    per_group = zip([16, 24, 40, 80, 112, 192, 320], [1, 2, 2, 3, 3, 4, 1], [1, 1, 1, 1, 0, 1, 0],
+                    [1, 6, 6, 6, 6, 6, 6], [3, 3, 5, 3, 5, 5, 3], [1, 2, 2, 2, 1, 2, 1])
+    channels, kernels, expansions, strides = [], [], [], []
+    for ch, count, new_stage, exp, k, stride in per_group:
+        count, ch = int(math.ceil(count * depth)), round_channels(ch * width)
+        if new_stage:
+            channels.append([]); kernels.append([]); expansions.append([]); strides.append(stride)
+        channels[-1] += [ch] * count
+        kernels[-1] += [k] * count
+        expansions[-1] += [exp] * count
+    final_channels = 1280
+    if width > 1.0:
+        assert int(final_channels * width) == round_channels(final_channels * width)
+        final_channels = round_channels(final_channels * width)
+    net = EfficientNet(channels=channels, init_block_channels=round_channels(32 * width),
+                       final_block_channels=final_channels, kernel_sizes=kernels, strides_per_stage=strides,
+                       expansion_factors=expansions, dropout_rate=dropout, tf_mode=tf_mode, bn_eps=bn_eps, **kwargs)
+    _no_pretrained(pretrained, model_name)
+    return net
+
+
+EFFICIENTNET_VARIANTS = {f"efficientnet_{v}": (v, sz) for v, (sz, _, _, _) in _EFFICIENTNET_SCALING.items()}
 
 
 # ===== MobileNet v1: the DwsConvBlock vehicle (mobilenet.py) ==========================================================

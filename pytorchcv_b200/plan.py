@@ -519,6 +519,36 @@ def _lower_linear_bottleneck(b, m, x, **kw):
     return lower(b, m.conv3, y, residual=x if m.residual else None, post_act=None)
 
 
+def _no_tf_mode(m):
+    if getattr(m, "tf_mode", False):
+        raise NotImplementedError("EfficientNet tf_mode (asymmetric, input-size dependent padding) is outside the B200 eval path")
+
+
+@lowers("EffiInitBlock")
+def _lower_effi_init(b, m, x, **kw):
+    """EffiInitBlock.forward (efficientnet.py:235-239)."""
+    _no_tf_mode(m)
+    return lower(b, m.conv, x)
+
+
+@lowers("EffiDwsConvUnit")
+def _lower_effi_dws(b, m, x, **kw):
+    """EffiDwsConvUnit.forward (efficientnet.py:105-115): dw3x3 -> SE -> 1x1 linear (+x); the add rides on the 1x1."""
+    _no_tf_mode(m)
+    y = lower(b, m.se, lower(b, m.dw_conv, x))
+    return lower(b, m.pw_conv, y, residual=x if m.residual else None, post_act=None)
+
+
+@lowers("EffiInvResUnit")
+def _lower_effi_invres(b, m, x, **kw):
+    """EffiInvResUnit.forward (efficientnet.py:185-197): 1x1 expand -> dw kxk -> [SE] -> 1x1 linear (+x)."""
+    _no_tf_mode(m)
+    y = lower(b, m.conv2, lower(b, m.conv1, x))
+    if m.use_se:
+        y = lower(b, m.se, y)
+    return lower(b, m.conv3, y, residual=x if m.residual else None, post_act=None)
+
+
 @lowers("MultiOutputSequential")
 def _lower_multi_output(b, m, x, **kw):
     """MultiOutputSequential.forward (arch.py:332-347)."""
@@ -598,9 +628,9 @@ def _flat(t: TRef) -> TRef:
     return t
 
 
-@lowers("ResNet", "SEResNeXt", "SEResNet", "ResNeXt", "MobileNet")
+@lowers("ResNet", "SEResNeXt", "SEResNet", "ResNeXt", "MobileNet", "EfficientNet")
 def _lower_classifier(b, m, x, **kw):
-    """features -> view(N,-1) -> Linear (resnet.py:333-337, seresnext.py:136-140)."""
+    """features -> view(N,-1) -> [Dropout ->] Linear (resnet.py:333-337, seresnext.py:136-140, efficientnet.py:354-358)."""
     return _flat(lower(b, m.output, lower(b, m.features, x)))
 
 

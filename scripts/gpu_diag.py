@@ -74,6 +74,18 @@ CASES = [
     ("dw3x3_s1_ragged_res",       2, 20, 18,  48,  48, 3, 1, 1, 1, 48, 1, 1, 0, "bf16"),
     ("dw3x3_s2_ragged_none",      3, 19, 23,  40,  40, 3, 2, 1, 1, 40, 0, 0, 0, "bf16"),
     ("dw3x3_d2_generic",          2, 28, 28,  32,  32, 3, 1, 2, 2, 32, 1, 0, 0, "bf16"),
+    # swish / h-swish epilogues (act 4 / 5) and 5x5 depthwise through the TMA window kernel
+    ("dw5x5_s1_swish_c240_28",    2, 28, 28, 240, 240, 5, 1, 2, 1, 240, 4, 0, 0, "bf16"),
+    ("dw5x5_s2_swish_ragged",     3, 29, 23, 144, 144, 5, 2, 2, 1, 144, 4, 0, 0, "bf16"),
+    ("dw5x5_s1_res_relu6_c672",   2, 14, 14, 672, 672, 5, 1, 2, 1, 672, 2, 1, 0, "bf16"),
+    ("dw5x5_s2_hswish_c1152_7",   2,  7,  7, 1152, 1152, 5, 2, 2, 1, 1152, 5, 0, 0, "bf16"),
+    ("dw3x3_s1_swish_c96_56",     2, 56, 56,  96,  96, 3, 1, 1, 1, 96, 4, 0, 0, "bf16"),
+    ("dw3x3_s2_hswish_c64",       2, 28, 28,  64,  64, 3, 2, 1, 1, 64, 5, 0, 0, "bf16"),
+    ("gemm_1x1_swish_16_96",      2, 56, 56,  16,  96, 1, 1, 0, 1, 1, 4, 0, 0, "bf16"),
+    ("gemm_1x1_swish_32_32",      2, 28, 28,  32,  32, 1, 1, 0, 1, 1, 4, 0, 0, "bf16"),
+    ("gemm_1x1_hswish_res_256",   2, 14, 14, 128, 256, 1, 1, 0, 1, 1, 5, 1, 0, "bf16"),
+    ("conv3x3_s2_swish_stem8",    2, 64, 64,   8,  32, 3, 2, 1, 1, 1, 4, 0, 0, "bf16"),
+    ("gemm_1x1_sigmoid_64",       2, 14, 14,  64,  64, 1, 1, 0, 1, 1, 3, 0, 0, "bf16"),
 ]
 
 
@@ -104,7 +116,8 @@ def run_case(idx: int) -> dict:
     ref = F.conv2d(rnd(x), wf, bf, stride=stride, padding=pad, dilation=dil, groups=groups)
     if has_res:
         ref = ref + rnd(res)
-    ref = {0: lambda t: t, 1: torch.relu, 2: lambda t: t.clamp(0, 6)}[act](ref)
+    ref = {0: lambda t: t, 1: torch.relu, 2: lambda t: t.clamp(0, 6), 3: torch.sigmoid, 4: lambda t: t * torch.sigmoid(t),
+           5: lambda t: t * (t + 3).clamp(0, 6) / 6, 6: lambda t: (t + 3).clamp(0, 6) / 6}[act](ref)
 
     dev = torch.device("cuda")
     xg = x.to(dev).permute(0, 2, 3, 1).contiguous().to(tdt)

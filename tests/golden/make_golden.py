@@ -22,7 +22,9 @@ from pytorchcv.models.common.att import SEBlock  # noqa: E402
 from pytorchcv.models.resnet import ResUnit  # noqa: E402
 from pytorchcv.models.mobilenetv2 import LinearBottleneck  # noqa: E402
 from pytorchcv.models.seresnext import SEResNeXtUnit  # noqa: E402
-from pytorchcv.models.common.activ import lambda_relu6  # noqa: E402
+from pytorchcv.models.common.activ import lambda_relu6, lambda_swish  # noqa: E402
+from pytorchcv.models.common.norm import lambda_batchnorm2d  # noqa: E402
+from pytorchcv.models.efficientnet import EffiDwsConvUnit, EffiInvResUnit  # noqa: E402
 
 from oracle.seeded import seeded_init, seeded_input  # noqa: E402
 
@@ -36,6 +38,7 @@ NETS = [
     ("seresnext50_32x4d_bs2", "seresnext50_32x4d", {}, (2, 3, 224, 224), 0, 1),
     ("mobilenet_w1_bs2", "mobilenet_w1", {}, (2, 3, 224, 224), 0, 1),
     ("deeplabv3_resnetd50b_voc_bs1", "deeplabv3_resnetd50b_voc", {}, (1, 3, 480, 480), 0, 16),
+    ("efficientnet_b0_bs2", "efficientnet_b0", {}, (2, 3, 224, 224), 0, 1),
 ]
 
 # block-level cases: (stem, ctor, input shape)
@@ -51,6 +54,14 @@ BLOCKS = [
     ("linear_bottleneck_res", lambda: LinearBottleneck(24, 24, stride=1, expansion=True, remove_exp_conv=False,
                                                        activation=lambda_relu6()), (2, 24, 14, 14)),
     ("seresnext_unit", lambda: SEResNeXtUnit(256, 256, stride=1, cardinality=32, bottleneck_width=4), (1, 256, 8, 8)),
+    ("effi_dws_unit", lambda: EffiDwsConvUnit(32, 16, stride=1, normalization=lambda_batchnorm2d(),
+                                              activation=lambda_swish(), tf_mode=False), (2, 32, 16, 16)),
+    ("effi_invres_k5_se", lambda: EffiInvResUnit(40, 40, kernel_size=5, stride=1, exp_factor=6, se_factor=4,
+                                                 normalization=lambda_batchnorm2d(), activation=lambda_swish(),
+                                                 tf_mode=False), (2, 40, 14, 14)),
+    ("effi_invres_k3_s2", lambda: EffiInvResUnit(24, 40, kernel_size=3, stride=2, exp_factor=6, se_factor=4,
+                                                 normalization=lambda_batchnorm2d(), activation=lambda_swish(),
+                                                 tf_mode=False), (1, 24, 15, 15)),
 ]
 
 
@@ -61,8 +72,15 @@ def sha(a: np.ndarray) -> str:
 @torch.no_grad()
 def main():
     torch.set_num_threads(1)  # thread count perturbs fp32 sums; fix it for reproducible fixtures
+    only = sys.argv[1] if len(sys.argv) > 1 else ""   # optional substring: (re)generate only the matching fixtures
     keys = {}
+    keys_path = os.path.join(OUT, "state_dict_keys.json")
+    if only and os.path.exists(keys_path):
+        import json
+        keys = json.load(open(keys_path))
     for stem, name, kw, shape, seed, sub in NETS:
+        if only not in stem:
+            continue
         net = seeded_init(ref_get_model(name, pretrained=False, **kw).eval(), seed=seed, randomize_bn=True)
         x = seeded_input(shape, seed=1234)
         y = net(x)
@@ -82,6 +100,8 @@ def main():
     with open(os.path.join(OUT, "state_dict_keys.json"), "w") as f:
         json.dump(keys, f, indent=1, sort_keys=True)
     for stem, ctor, shape in BLOCKS:
+        if only not in stem:
+            continue
         blk = seeded_init(ctor().eval(), seed=7, randomize_bn=True)
         x = seeded_input(shape, seed=99)
         y = blk(x)

@@ -23,6 +23,7 @@ NETS = [
     ("seresnext50_32x4d_bs2", "seresnext50_32x4d", (2, 3, 224, 224), 1),
     ("mobilenet_w1_bs2", "mobilenet_w1", (2, 3, 224, 224), 1),
     ("deeplabv3_resnetd50b_voc_bs1", "deeplabv3_resnetd50b_voc", (1, 3, 480, 480), 16),
+    ("efficientnet_b0_bs2", "efficientnet_b0", (2, 3, 224, 224), 1),
 ]
 
 BLOCKS = {
@@ -41,6 +42,14 @@ BLOCKS = {
                                                          activation=B.lambda_relu6()), (2, 24, 14, 14)),
     "seresnext_unit": (lambda: M.SEResNeXtUnit(256, 256, stride=1, cardinality=32, bottleneck_width=4),
                        (1, 256, 8, 8)),
+    "effi_dws_unit": (lambda: M.EffiDwsConvUnit(32, 16, stride=1, normalization=B.lambda_batchnorm2d(),
+                                                activation=B.lambda_swish(), tf_mode=False), (2, 32, 16, 16)),
+    "effi_invres_k5_se": (lambda: M.EffiInvResUnit(40, 40, kernel_size=5, stride=1, exp_factor=6, se_factor=4,
+                                                   normalization=B.lambda_batchnorm2d(), activation=B.lambda_swish(),
+                                                   tf_mode=False), (2, 40, 14, 14)),
+    "effi_invres_k3_s2": (lambda: M.EffiInvResUnit(24, 40, kernel_size=3, stride=2, exp_factor=6, se_factor=4,
+                                                   normalization=B.lambda_batchnorm2d(), activation=B.lambda_swish(),
+                                                   tf_mode=False), (1, 24, 15, 15)),
 }
 
 
@@ -97,7 +106,8 @@ def test_state_dict_keys_match_reference():
 # ---- live comparisons against the reference package (build container only) ---------------------------------------
 @pytest.mark.reference
 @pytest.mark.parametrize("name,shape", [("resnet18", (8, 3, 224, 224)), ("mobilenetv2_w1", (2, 3, 224, 224)),
-                                        ("seresnext50_32x4d", (1, 3, 224, 224))])
+                                        ("seresnext50_32x4d", (1, 3, 224, 224)), ("efficientnet_b0", (2, 3, 224, 224)),
+                                        ("efficientnet_b1", (1, 3, 240, 240))])
 def test_oracle_equals_reference_live(reference_pkg, name, shape):
     from pytorchcv.model_provider import get_model as ref_get_model
     ref = seeded_init(ref_get_model(name, pretrained=False).eval(), seed=3, randomize_bn=True)
@@ -113,7 +123,7 @@ def test_oracle_equals_reference_live(reference_pkg, name, shape):
 
 @pytest.mark.reference
 @pytest.mark.parametrize("name", ["resnet18", "resnet50", "mobilenetv2_w1", "seresnext50_32x4d",
-                                  "deeplabv3_resnetd50b_voc", "mobilenet_w1"])
+                                  "deeplabv3_resnetd50b_voc", "mobilenet_w1", "efficientnet_b0", "efficientnet_b3"])
 def test_same_seed_same_random_init_as_reference(reference_pkg, name):
     """torch.manual_seed(0); get_model(name) consumes the RNG in the reference's order -> bit-identical weights."""
     from pytorchcv.model_provider import get_model as ref_get_model
