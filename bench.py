@@ -27,7 +27,8 @@ sys.path.insert(0, ROOT)
 CONFIGS = {  # model -> (default batch, H, W)
     "resnet50": (256, 224, 224), "resnet18": (8, 224, 224), "mobilenetv2_w1": (256, 224, 224),
     "seresnext50_32x4d": (256, 224, 224), "deeplabv3_resnetd50b_voc": (16, 480, 480),
-    "efficientnet_b0": (256, 224, 224),   # SURVEY 8(f) rank 1 (not a BASELINE config: measured to the same bar)
+    "efficientnet_b0": (256, 224, 224),   # SURVEY 8(f) rank 1 (not BASELINE configs: measured to the same bar)
+    "mobilenetv3_large_w1": (256, 224, 224),
 }
 
 

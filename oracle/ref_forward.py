@@ -276,6 +276,35 @@ def effi_inv_res_unit(m, x):
     return x + identity if m.residual else x
 
 
+def mobilenetv3_unit(m, x):
+    """MobileNetV3Unit.forward (mobilenetv3.py:82-93)."""
+    identity = x
+    if m.use_exp_conv:
+        x = conv_block(m.exp_conv, x)
+    x = conv_block(m.conv1, x)
+    if m.use_se:
+        x = se_block(m.se, x)
+    x = conv_block(m.conv2, x)
+    return x + identity if m.residual else x
+
+
+def mobilenetv3_final_block(m, x):
+    """MobileNetV3FinalBlock.forward (mobilenetv3.py:127-131)."""
+    x = conv_block(m.conv, x)
+    return se_block(m.se, x) if m.use_se else x
+
+
+def mobilenetv3_classifier(m, x):
+    """MobileNetV3Classifier.forward (mobilenetv3.py:168-174); Dropout is the identity in eval."""
+    return _conv2d(m.conv2, _activation(m.activ, _conv2d(m.conv1, x)))
+
+
+def mobilenetv3(m, x):
+    """MobileNetV3.forward (mobilenetv3.py:277-281)."""
+    x = mobilenetv3_classifier(m.output, oracle_forward(m.features, x))
+    return x.view(x.size(0), -1)
+
+
 def efficientnet(m, x):
     """EfficientNet.forward (efficientnet.py:354-358): features -> view -> output (Dropout is the identity in eval)."""
     x = oracle_forward(m.features, x)
@@ -311,6 +340,8 @@ _BY_NAME = {
     "MobileNetV2": mobilenetv2, "ResNetD": resnetd,
     "EffiInitBlock": effi_init_block, "EffiDwsConvUnit": effi_dws_conv_unit, "EffiInvResUnit": effi_inv_res_unit,
     "EfficientNet": efficientnet,
+    "MobileNetV3Unit": mobilenetv3_unit, "MobileNetV3FinalBlock": mobilenetv3_final_block,
+    "MobileNetV3Classifier": mobilenetv3_classifier, "MobileNetV3": mobilenetv3,
     "Concurrent": concurrent, "MultiOutputSequential": multi_output_sequential,
     "ASPPAvgBranch": aspp_avg_branch, "AtrousSpatialPyramidPooling": aspp, "DeepLabv3": deeplabv3,
 }

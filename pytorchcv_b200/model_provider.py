@@ -35,6 +35,9 @@ for _name, _b in nets.RESNETD_VARIANTS.items():
 for _name, (_v, _sz) in nets.EFFICIENTNET_VARIANTS.items():
     _register(_name, (lambda n, v, sz: lambda in_size=None, **kw: nets.get_efficientnet(
         version=v, in_size=in_size if in_size is not None else (sz, sz), model_name=n, **kw))(_name, _v, _sz))
+for _name, (_ver, _ws) in nets.MOBILENETV3_VARIANTS.items():
+    _register(_name, (lambda n, v, w: lambda **kw: nets.get_mobilenetv3(version=v, width_scale=w, model_name=n, **kw))(
+        _name, _ver, _ws))
 for _name, (_b, _k) in nets.DEEPLABV3_VARIANTS.items():
     _register(_name, nets._deeplab_ctor(_name, _b, _k))
 

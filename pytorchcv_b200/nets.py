@@ -16,8 +16,8 @@ import math
 import torch.nn as nn
 
 from .blocks import (B200Module, SEBlock, conv1x1, conv1x1_block, conv3x3_block, conv7x7_block, dwconv3x3_block,
-                     dwconv5x5_block, dwsconv3x3_block, lambda_batchnorm2d, lambda_relu, lambda_relu6, lambda_swish,
-                     round_channels)
+                     dwconv5x5_block, dwsconv3x3_block, HSwish, lambda_batchnorm2d, lambda_hsigmoid, lambda_hswish,
+                     lambda_relu, lambda_relu6, lambda_swish, round_channels)
 from .plan import run_module
 
 
@@ -403,6 +403,116 @@ def get_efficientnet(version, in_size, tf_mode=False, bn_eps=1e-5, model_name=No
 
 
 EFFICIENTNET_VARIANTS = {f"efficientnet_{v}": (v, sz) for v, (sz, _, _, _) in _EFFICIENTNET_SCALING.items()}
+
+
+# ===== MobileNetV3 (mobilenetv3.py), SURVEY 8(f) rank 1 ==============================================================
+class MobileNetV3Unit(B200Module):
+    """[1x1 expand] -> dw 3x3 | 5x5 -> [SE(reduction 4, rounded, h-sigmoid gate)] -> 1x1 linear (+x)
+    (mobilenetv3.py:18-93)."""
+
+    def __init__(self, in_channels, out_channels, exp_channels, stride, use_kernel3, activation, use_se):
+        super().__init__()
+        assert exp_channels >= out_channels
+        self.residual = (in_channels == out_channels) and (stride == 1)
+        self.use_se = use_se
+        self.use_exp_conv = exp_channels != out_channels
+        if self.use_exp_conv:
+            self.exp_conv = conv1x1_block(in_channels=in_channels, out_channels=exp_channels, activation=activation)
+        dw = dwconv3x3_block if use_kernel3 else dwconv5x5_block
+        self.conv1 = dw(in_channels=exp_channels, out_channels=exp_channels, stride=stride, activation=activation)
+        if self.use_se:
+            self.se = SEBlock(channels=exp_channels, reduction=4, round_mid=True, out_activation=lambda_hsigmoid())
+        self.conv2 = conv1x1_block(in_channels=exp_channels, out_channels=out_channels, activation=None)
+
+
+class MobileNetV3FinalBlock(B200Module):
+    """1x1 h-swish ConvBlock [-> SE] (mobilenetv3.py:96-131)."""
+
+    def __init__(self, in_channels, out_channels, use_se):
+        super().__init__()
+        self.use_se = use_se
+        self.conv = conv1x1_block(in_channels=in_channels, out_channels=out_channels, activation=lambda_hswish())
+        if self.use_se:
+            self.se = SEBlock(channels=out_channels, reduction=4, round_mid=True, out_activation=lambda_hsigmoid())
+
+
+class MobileNetV3Classifier(B200Module):
+    """conv1x1 -> HSwish -> [Dropout] -> conv1x1 with bias, on the pooled 1x1 map (mobilenetv3.py:134-174)."""
+
+    def __init__(self, in_channels, out_channels, mid_channels, dropout_rate):
+        super().__init__()
+        self.use_dropout = dropout_rate != 0.0
+        self.conv1 = conv1x1(in_channels=in_channels, out_channels=mid_channels)
+        self.activ = HSwish(inplace=True)
+        if self.use_dropout:
+            self.dropout = nn.Dropout(p=dropout_rate)
+        self.conv2 = conv1x1(in_channels=mid_channels, out_channels=out_channels, bias=True)
+
+
+class MobileNetV3(B200Module):
+    """mobilenetv3.py:177-281."""
+
+    def __init__(self, channels, exp_channels, init_block_channels, final_block_channels, classifier_mid_channels,
+                 kernels3, use_relu, use_se, first_stride, final_use_se, in_channels=3, in_size=(224, 224),
+                 num_classes=1000):
+        super().__init__()
+        self.in_size, self.num_classes = in_size, num_classes
+        self.features = nn.Sequential()
+        self.features.add_module("init_block", conv3x3_block(in_channels=in_channels, out_channels=init_block_channels,
+                                                             stride=2, activation=lambda_hswish()))
+        last = _stages(
+            self.features, channels, init_block_channels,
+            lambda i, j, cin, cout, s: MobileNetV3Unit(
+                in_channels=cin, out_channels=cout, exp_channels=exp_channels[i][j], use_kernel3=kernels3[i][j] == 1,
+                stride=s, activation=lambda_relu() if use_relu[i][j] == 1 else lambda_hswish(),
+                use_se=use_se[i][j] == 1),
+            stride_of=lambda i, j: 2 if (j == 0) and ((i != 0) or first_stride) else 1)
+        self.features.add_module("final_block", MobileNetV3FinalBlock(in_channels=last,
+                                                                      out_channels=final_block_channels,
+                                                                      use_se=final_use_se))
+        self.features.add_module("final_pool", nn.AvgPool2d(kernel_size=7, stride=1))
+        self.output = MobileNetV3Classifier(in_channels=final_block_channels, out_channels=num_classes,
+                                            mid_channels=classifier_mid_channels, dropout_rate=0.2)
+        _kaiming_init(self)
+
+
+_MOBILENETV3_TABLES = {   # version -> per-unit tables (mobilenetv3.py:308-331)
+    "small": dict(channels=[[16], [24, 24], [40, 40, 40, 48, 48], [96, 96, 96]],
+                  exp_channels=[[16], [72, 88], [96, 240, 240, 120, 144], [288, 576, 576]],
+                  kernels3=[[1], [1, 1], [0, 0, 0, 0, 0], [0, 0, 0]],
+                  use_relu=[[1], [1, 1], [0, 0, 0, 0, 0], [0, 0, 0]],
+                  use_se=[[1], [0, 0], [1, 1, 1, 1, 1], [1, 1, 1]], first_stride=True, final_block_channels=576),
+    "large": dict(channels=[[16], [24, 24], [40, 40, 40], [80, 80, 80, 80, 112, 112], [160, 160, 160]],
+                  exp_channels=[[16], [64, 72], [72, 120, 120], [240, 200, 184, 184, 480, 672], [672, 960, 960]],
+                  kernels3=[[1], [1, 1], [0, 0, 0], [1, 1, 1, 1, 1, 1], [0, 0, 0]],
+                  use_relu=[[1], [1, 1], [1, 1, 1], [0, 0, 0, 0, 0, 0], [0, 0, 0]],
+                  use_se=[[0], [0, 0], [1, 1, 1], [0, 0, 0, 0, 1, 1], [1, 1, 1]], first_stride=False,
+                  final_block_channels=960),
+}
+
+
+def get_mobilenetv3(version, width_scale, model_name=None, pretrained=False, root=None, **kwargs):
+    """Same contract as mobilenetv3.py:284-364."""
+    if version not in _MOBILENETV3_TABLES:
+        raise ValueError("Unsupported MobileNetV3 version {}".format(version))
+    t = {k: (v if not isinstance(v, list) else [list(r) for r in v]) for k, v in _MOBILENETV3_TABLES[version].items()}
+    init_channels = 16
+    if width_scale != 1.0:
+        t["channels"] = [[round_channels(c * width_scale) for c in ci] for ci in t["channels"]]
+        t["exp_channels"] = [[round_channels(c * width_scale) for c in ci] for ci in t["exp_channels"]]
+        init_channels = round_channels(init_channels * width_scale)
+        if width_scale > 1.0:
+            t["final_block_channels"] = round_channels(t["final_block_channels"] * width_scale)
+    net = MobileNetV3(init_block_channels=init_channels, classifier_mid_channels=1280, final_use_se=False, **t,
+                      **kwargs)
+    _no_pretrained(pretrained, model_name)
+    return net
+
+
+MOBILENETV3_VARIANTS = {
+    f"mobilenetv3_{ver}_{tag}": (ver, ws)
+    for ver in ("small", "large") for tag, ws in (("w7d20", 0.35), ("wd2", 0.5), ("w3d4", 0.75), ("w1", 1.0), ("w5d4", 1.25))
+}
 
 
 # ===== MobileNet v1: the DwsConvBlock vehicle (mobilenet.py) ==========================================================

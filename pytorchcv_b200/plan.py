@@ -549,6 +549,36 @@ def _lower_effi_invres(b, m, x, **kw):
     return lower(b, m.conv3, y, residual=x if m.residual else None, post_act=None)
 
 
+@lowers("MobileNetV3Unit")
+def _lower_mnv3_unit(b, m, x, **kw):
+    """MobileNetV3Unit.forward (mobilenetv3.py:82-93): [1x1 expand] -> dw -> [SE] -> 1x1 linear (+x)."""
+    y = lower(b, m.exp_conv, x) if m.use_exp_conv else x
+    y = lower(b, m.conv1, y)
+    if m.use_se:
+        y = lower(b, m.se, y)
+    return lower(b, m.conv2, y, residual=x if m.residual else None, post_act=None)
+
+
+@lowers("MobileNetV3FinalBlock")
+def _lower_mnv3_final(b, m, x, **kw):
+    """MobileNetV3FinalBlock.forward (mobilenetv3.py:127-131)."""
+    y = lower(b, m.conv, x)
+    return lower(b, m.se, y) if m.use_se else y
+
+
+@lowers("MobileNetV3Classifier")
+def _lower_mnv3_classifier(b, m, x, **kw):
+    """MobileNetV3Classifier.forward (mobilenetv3.py:168-174): the h-swish rides on conv1's epilogue, fp32 logits."""
+    y = b.conv(x, m.conv1, None, act_code(m.activ))
+    return b.conv(y, m.conv2, None, ACT_NONE, out_f32=True)
+
+
+@lowers("MobileNetV3")
+def _lower_mobilenetv3(b, m, x, **kw):
+    """MobileNetV3.forward (mobilenetv3.py:277-281): features -> classifier convs on the 1x1 map -> view."""
+    return _flat(lower(b, m.output, lower(b, m.features, x)))
+
+
 @lowers("MultiOutputSequential")
 def _lower_multi_output(b, m, x, **kw):
     """MultiOutputSequential.forward (arch.py:332-347)."""

@@ -22,7 +22,8 @@ from pytorchcv.models.common.att import SEBlock  # noqa: E402
 from pytorchcv.models.resnet import ResUnit  # noqa: E402
 from pytorchcv.models.mobilenetv2 import LinearBottleneck  # noqa: E402
 from pytorchcv.models.seresnext import SEResNeXtUnit  # noqa: E402
-from pytorchcv.models.common.activ import lambda_relu6, lambda_swish  # noqa: E402
+from pytorchcv.models.common.activ import lambda_relu6, lambda_swish, lambda_hswish  # noqa: E402
+from pytorchcv.models.mobilenetv3 import MobileNetV3Unit  # noqa: E402
 from pytorchcv.models.common.norm import lambda_batchnorm2d  # noqa: E402
 from pytorchcv.models.efficientnet import EffiDwsConvUnit, EffiInvResUnit  # noqa: E402
 
@@ -39,6 +40,8 @@ NETS = [
     ("mobilenet_w1_bs2", "mobilenet_w1", {}, (2, 3, 224, 224), 0, 1),
     ("deeplabv3_resnetd50b_voc_bs1", "deeplabv3_resnetd50b_voc", {}, (1, 3, 480, 480), 0, 16),
     ("efficientnet_b0_bs2", "efficientnet_b0", {}, (2, 3, 224, 224), 0, 1),
+    ("mobilenetv3_large_w1_bs2", "mobilenetv3_large_w1", {}, (2, 3, 224, 224), 0, 1),
+    ("mobilenetv3_small_w1_bs2", "mobilenetv3_small_w1", {}, (2, 3, 224, 224), 0, 1),
 ]
 
 # block-level cases: (stem, ctor, input shape)
@@ -62,6 +65,10 @@ BLOCKS = [
     ("effi_invres_k3_s2", lambda: EffiInvResUnit(24, 40, kernel_size=3, stride=2, exp_factor=6, se_factor=4,
                                                  normalization=lambda_batchnorm2d(), activation=lambda_swish(),
                                                  tf_mode=False), (1, 24, 15, 15)),
+    ("mnv3_unit_k5_se_hswish", lambda: MobileNetV3Unit(40, 40, exp_channels=120, stride=1, use_kernel3=False,
+                                                       activation=lambda_hswish(), use_se=True), (2, 40, 14, 14)),
+    ("mnv3_unit_k5_s2_se", lambda: MobileNetV3Unit(24, 40, exp_channels=96, stride=2, use_kernel3=False,
+                                                   activation=lambda_hswish(), use_se=True), (1, 24, 17, 15)),
 ]
 
 

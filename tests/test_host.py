@@ -99,7 +99,7 @@ def test_kwargs_flow_to_constructor():
 
 CONFIGS = [("resnet18", (8, 3, 224, 224), 23), ("resnet50", (4, 3, 224, 224), 56), ("mobilenetv2_w1", (4, 3, 224, 224), 55),
            ("seresnext50_32x4d", (4, 3, 224, 224), 104), ("deeplabv3_resnetd50b_voc", (1, 3, 480, 480), 70),
-           ("efficientnet_b0", (4, 3, 224, 224), 99)]
+           ("efficientnet_b0", (4, 3, 224, 224), 99), ("mobilenetv3_large_w1", (4, 3, 224, 224), 73)]
 
 
 @pytest.mark.parametrize("tier", [BF16, F32])

@@ -24,6 +24,8 @@ NETS = [
     ("mobilenet_w1_bs2", "mobilenet_w1", (2, 3, 224, 224), 1),
     ("deeplabv3_resnetd50b_voc_bs1", "deeplabv3_resnetd50b_voc", (1, 3, 480, 480), 16),
     ("efficientnet_b0_bs2", "efficientnet_b0", (2, 3, 224, 224), 1),
+    ("mobilenetv3_large_w1_bs2", "mobilenetv3_large_w1", (2, 3, 224, 224), 1),
+    ("mobilenetv3_small_w1_bs2", "mobilenetv3_small_w1", (2, 3, 224, 224), 1),
 ]
 
 BLOCKS = {
@@ -50,6 +52,10 @@ BLOCKS = {
     "effi_invres_k3_s2": (lambda: M.EffiInvResUnit(24, 40, kernel_size=3, stride=2, exp_factor=6, se_factor=4,
                                                    normalization=B.lambda_batchnorm2d(), activation=B.lambda_swish(),
                                                    tf_mode=False), (1, 24, 15, 15)),
+    "mnv3_unit_k5_se_hswish": (lambda: M.MobileNetV3Unit(40, 40, exp_channels=120, stride=1, use_kernel3=False,
+                                                         activation=B.lambda_hswish(), use_se=True), (2, 40, 14, 14)),
+    "mnv3_unit_k5_s2_se": (lambda: M.MobileNetV3Unit(24, 40, exp_channels=96, stride=2, use_kernel3=False,
+                                                     activation=B.lambda_hswish(), use_se=True), (1, 24, 17, 15)),
 }
 
 
@@ -107,7 +113,8 @@ def test_state_dict_keys_match_reference():
 @pytest.mark.reference
 @pytest.mark.parametrize("name,shape", [("resnet18", (8, 3, 224, 224)), ("mobilenetv2_w1", (2, 3, 224, 224)),
                                         ("seresnext50_32x4d", (1, 3, 224, 224)), ("efficientnet_b0", (2, 3, 224, 224)),
-                                        ("efficientnet_b1", (1, 3, 240, 240))])
+                                        ("efficientnet_b1", (1, 3, 240, 240)), ("mobilenetv3_large_w1", (2, 3, 224, 224)),
+                                        ("mobilenetv3_small_wd2", (1, 3, 224, 224))])
 def test_oracle_equals_reference_live(reference_pkg, name, shape):
     from pytorchcv.model_provider import get_model as ref_get_model
     ref = seeded_init(ref_get_model(name, pretrained=False).eval(), seed=3, randomize_bn=True)
@@ -123,7 +130,8 @@ def test_oracle_equals_reference_live(reference_pkg, name, shape):
 
 @pytest.mark.reference
 @pytest.mark.parametrize("name", ["resnet18", "resnet50", "mobilenetv2_w1", "seresnext50_32x4d",
-                                  "deeplabv3_resnetd50b_voc", "mobilenet_w1", "efficientnet_b0", "efficientnet_b3"])
+                                  "deeplabv3_resnetd50b_voc", "mobilenet_w1", "efficientnet_b0", "efficientnet_b3",
+                                  "mobilenetv3_large_w1", "mobilenetv3_small_w3d4"])
 def test_same_seed_same_random_init_as_reference(reference_pkg, name):
     """torch.manual_seed(0); get_model(name) consumes the RNG in the reference's order -> bit-identical weights."""
     from pytorchcv.model_provider import get_model as ref_get_model
