@@ -98,7 +98,8 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 // OP 0: depthwise conv, 1: max pool.  COLS = adjacent output columns per thread (their windows overlap, so the shared
 // input columns are loaded and converted once).  RES = residual add in the epilogue.
 template <int OP, int KS, int S, int TH, int COLS, bool RES>
-__global__ void __launch_bounds__(256, KS == 5 ? 1 : 2)   // 5x5: 25 taps x 4 channels of fp32 weights live in registers
+__global__ void __launch_bounds__(KS == 5 ? 384 : 256, KS == 5 ? 1 : 2)   // 5x5: 25 taps x 4 channels of fp32 weights live in
+                                                                         // registers (~165): one 384-thread CTA per SM
 win_kernel(const __grid_constant__ CUtensorMap tmIn, const WinParams p, const float* __restrict__ w,
            const float* __restrict__ bias, const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y) {
   constexpr int IH = (TH - 1) * S + KS;
@@ -302,7 +303,8 @@ static bool pick_cfg(int C, int Ho, int Wo, int KS, int S, int cols, WinParams* 
   for (int CB = 8; CB <= std::min(C, 256); CB += 8) {
     if (C % CB != 0) continue;
     const int nv = CB / 4;
-    for (int TW = cols; TW <= round_up(Wo, cols) && TW / cols * nv <= 256; TW += cols) {
+    const int max_threads = KS == 5 ? 384 : 256;   // __launch_bounds__ of win_kernel
+    for (int TW = cols; TW <= round_up(Wo, cols) && TW / cols * nv <= max_threads; TW += cols) {
       const int IW = (TW - 1) * S + KS;
       if (IW > 256) break;
       for (int TH = 7; TH <= 8; ++TH) {
@@ -418,7 +420,7 @@ int win_make(int op_kind, int N, int H, int W, int C, int k, int stride, int pad
   const int IH = (op->cfg.TH - 1) * stride + k;
   if (int rc = make_win_map(&op->tm, x, N, H, W, C, in_pitch, p.CB, p.IW, IH)) return rc;
   op->op_kind = op_kind; op->S = stride; op->K = k; op->w = w; op->bias = bias;
-  if (k == 5) op->cfg.ctas_per_sm = 1;   // __launch_bounds__(256, 1)
+  if (k == 5) op->cfg.ctas_per_sm = 1;   // __launch_bounds__(384, 1)
   op->res = reinterpret_cast<const __nv_bfloat16*>(res);
   op->y = reinterpret_cast<__nv_bfloat16*>(y);
   *out = op.release();
