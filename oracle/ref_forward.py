@@ -114,7 +114,7 @@ def res_unit(m, x):
 
 
 def se_resnext_unit(m, x):
-    """SEResNeXtUnit.forward (seresnext.py:57-66)."""
+    """SEResNeXtUnit.forward (seresnext.py:57-66) == SEResUnit.forward (seresnet.py:63-72)."""
     identity = conv_block(m.identity_conv, x) if m.resize_identity else x
     x = res_body(m.body, x)
     x = se_block(m.se, x)
@@ -312,6 +312,16 @@ def efficientnet(m, x):
     return sequential(m.output, x)
 
 
+def fcn8sd(m, x):
+    """FCN8sd.forward (fcn8sd.py:112-120); FCNFinalBlock.forward (fcn8sd.py:47-52) has DeepLabv3FinalBlock's body."""
+    in_size = m.in_size if m.fixed_size else x.shape[2:]
+    x, y = multi_output_sequential(m.backbone, x)
+    x = deeplab_final_block(m.final_block, x, in_size)
+    if m.aux:
+        return x, deeplab_final_block(m.aux_block, y, in_size)
+    return x
+
+
 # ---- dispatch --------------------------------------------------------------------------------------------------------
 def _leaf(m, x):
     if isinstance(m, nn.Conv2d):
@@ -334,7 +344,8 @@ def _leaf(m, x):
 _BY_NAME = {
     "ConvBlock": conv_block, "DwsConvBlock": dws_conv_block, "SEBlock": se_block,
     "ResBlock": res_body, "ResBottleneck": res_body, "ResNeXtBottleneck": res_body,
-    "ResUnit": res_unit, "ResNeXtUnit": res_unit, "SEResNeXtUnit": se_resnext_unit,
+    "ResUnit": res_unit, "ResNeXtUnit": res_unit, "SEResNeXtUnit": se_resnext_unit, "SEResUnit": se_resnext_unit,
+    "SEResNet": classifier, "FCN8sd": fcn8sd,
     "ResInitBlock": res_init_block, "SEInitBlock": se_init_block, "LinearBottleneck": linear_bottleneck,
     "ResNet": classifier, "SEResNeXt": classifier, "ResNeXt": classifier, "MobileNet": classifier,
     "MobileNetV2": mobilenetv2, "ResNetD": resnetd,
@@ -353,7 +364,7 @@ def oracle_forward(m: nn.Module, x: torch.Tensor, **kw):
     if x.is_cuda:
         raise ValueError("the oracle is a CPU restatement; pass CPU tensors")
     name = type(m).__name__
-    if name == "DeepLabv3FinalBlock":
+    if name in ("DeepLabv3FinalBlock", "FCNFinalBlock"):
         return deeplab_final_block(m, x, kw["out_size"])
     fn = _BY_NAME.get(name)
     if fn is not None:

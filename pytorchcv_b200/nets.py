@@ -658,6 +658,70 @@ RESNEXT_VARIANTS = {"resnext14_16x4d": (14, 16, 4), "resnext14_32x2d": (14, 32, 
                     "resnext101_64x4d": (101, 64, 4)}
 
 
+# ===== SE-ResNet (seresnet.py), SURVEY 8(f) rank 3 ===================================================================
+class SEResUnit(B200Module):
+    """relu(se(body(x)) + identity) with a ResBlock / ResBottleneck body (seresnet.py:17-72)."""
+
+    def __init__(self, in_channels, out_channels, stride, bottleneck, conv1_stride):
+        super().__init__()
+        self.resize_identity = (in_channels != out_channels) or (stride != 1)
+        if bottleneck:
+            self.body = ResBottleneck(in_channels=in_channels, out_channels=out_channels, stride=stride,
+                                      conv1_stride=conv1_stride)
+        else:
+            self.body = ResBlock(in_channels=in_channels, out_channels=out_channels, stride=stride)
+        self.se = SEBlock(channels=out_channels)
+        if self.resize_identity:
+            self.identity_conv = conv1x1_block(in_channels=in_channels, out_channels=out_channels, stride=stride,
+                                               activation=None)
+        self.activ = nn.ReLU(inplace=True)
+
+
+class SEResNet(_Classifier):
+    """seresnet.py:75-150."""
+
+    def __init__(self, channels, init_block_channels, bottleneck, conv1_stride, in_channels=3, in_size=(224, 224),
+                 num_classes=1000):
+        super().__init__()
+        self.in_size, self.num_classes = in_size, num_classes
+        self.features = nn.Sequential()
+        self.features.add_module("init_block", ResInitBlock(in_channels=in_channels,
+                                                            out_channels=init_block_channels))
+        last = _stages(self.features, channels, init_block_channels,
+                       lambda i, j, cin, cout, s: SEResUnit(in_channels=cin, out_channels=cout, stride=s,
+                                                            bottleneck=bottleneck, conv1_stride=conv1_stride))
+        self._finish(last, num_classes)
+
+
+def get_seresnet(blocks, bottleneck=None, conv1_stride=True, model_name=None, pretrained=False, root=None, **kwargs):
+    """Same contract as seresnet.py:153-243 (the depth table of ResNet)."""
+    if bottleneck is None:
+        bottleneck = blocks >= 50
+    layers = _RESNET_LAYERS_BY_KIND.get((blocks, bool(bottleneck))) or _RESNET_LAYERS.get(blocks)
+    if layers is None:
+        raise ValueError("Unsupported SE-ResNet with number of blocks: {}".format(blocks))
+    assert sum(layers) * (3 if bottleneck else 2) + 2 == blocks
+    widths = [64, 128, 256, 512]
+    if bottleneck:
+        widths = [w * 4 for w in widths]
+    net = SEResNet(channels=[[w] * n for w, n in zip(widths, layers)], init_block_channels=64, bottleneck=bottleneck,
+                   conv1_stride=conv1_stride, **kwargs)
+    _no_pretrained(pretrained, model_name)
+    return net
+
+
+SERESNET_VARIANTS = {
+    "seresnet10": dict(blocks=10), "seresnet12": dict(blocks=12), "seresnet14": dict(blocks=14),
+    "seresnet16": dict(blocks=16), "seresnet18": dict(blocks=18), "seresnet26": dict(blocks=26, bottleneck=False),
+    "seresnetbc26b": dict(blocks=26, bottleneck=True, conv1_stride=False), "seresnet34": dict(blocks=34),
+    "seresnetbc38b": dict(blocks=38, bottleneck=True, conv1_stride=False), "seresnet50": dict(blocks=50),
+    "seresnet50b": dict(blocks=50, conv1_stride=False), "seresnet101": dict(blocks=101),
+    "seresnet101b": dict(blocks=101, conv1_stride=False), "seresnet152": dict(blocks=152),
+    "seresnet152b": dict(blocks=152, conv1_stride=False), "seresnet200": dict(blocks=200),
+    "seresnet200b": dict(blocks=200, conv1_stride=False),
+}
+
+
 # ===== SENet stem + ResNet(D) (senet.py:127-164, resnetd.py) ==========================================================
 class SEInitBlock(B200Module):
     def __init__(self, in_channels, out_channels):
@@ -797,5 +861,60 @@ def _deeplab_ctor(name, depth, default_classes):
                                pretrained=pretrained_backbone, ordinary_init=False, bends=(3,)).features
         del backbone[-1]
         return get_deeplabv3(backbone=backbone, num_classes=num_classes, aux=aux, model_name=name, **kwargs)
+    ctor.__name__ = name
+    return ctor
+
+
+# ===== FCN-8s(d) on the ResNet(D) backbone (fcn8sd.py), SURVEY 8(f) rank 3 ============================================
+class FCNFinalBlock(B200Module):
+    """conv3x3 block -> Dropout -> conv1x1 + bias -> bilinear to `out_size` (fcn8sd.py:17-52)."""
+
+    def __init__(self, in_channels, out_channels, bottleneck_factor=4):
+        super().__init__()
+        assert in_channels % bottleneck_factor == 0
+        mid = in_channels // bottleneck_factor
+        self.conv1 = conv3x3_block(in_channels=in_channels, out_channels=mid)
+        self.dropout = nn.Dropout(p=0.1, inplace=False)
+        self.conv2 = conv1x1(in_channels=mid, out_channels=out_channels, bias=True)
+
+    def forward(self, x, out_size):
+        return run_module(self, x, out_size=tuple(out_size))
+
+
+class FCN8sd(B200Module):
+    """fcn8sd.py:55-120: dual-output dilated backbone, one head on stage 4, an auxiliary head on stage 3."""
+
+    def __init__(self, backbone, backbone_out_channels=2048, aux=False, fixed_size=True, in_channels=3,
+                 in_size=(480, 480), num_classes=21):
+        super().__init__()
+        assert in_channels > 0
+        self.in_size, self.num_classes, self.aux, self.fixed_size = in_size, num_classes, aux, fixed_size
+        self.backbone = backbone
+        self.final_block = FCNFinalBlock(in_channels=backbone_out_channels, out_channels=num_classes)
+        if aux:
+            self.aux_block = FCNFinalBlock(in_channels=backbone_out_channels // 2, out_channels=num_classes)
+        _kaiming_init(self)
+
+
+def get_fcn8sd(backbone, num_classes, aux=False, model_name=None, pretrained=False, root=None, **kwargs):
+    net = FCN8sd(backbone=backbone, num_classes=num_classes, aux=aux, **kwargs)
+    _no_pretrained(pretrained, model_name)
+    return net
+
+
+FCN8SD_VARIANTS = {  # name -> (ResNet(D) depth, default num_classes)   (fcn8sd.py:171-480)
+    "fcn8sd_resnetd50b_voc": (50, 21), "fcn8sd_resnetd101b_voc": (101, 21), "fcn8sd_resnetd50b_coco": (50, 21),
+    "fcn8sd_resnetd101b_coco": (101, 21), "fcn8sd_resnetd50b_ade20k": (50, 150),
+    "fcn8sd_resnetd101b_ade20k": (101, 150), "fcn8sd_resnetd50b_cityscapes": (50, 19),
+    "fcn8sd_resnetd101b_cityscapes": (101, 19),
+}
+
+
+def _fcn8sd_ctor(name, depth, default_classes):
+    def ctor(pretrained_backbone=False, num_classes=default_classes, aux=True, **kwargs):
+        backbone = get_resnetd(blocks=depth, conv1_stride=False, model_name=f"resnetd{depth}b",
+                               pretrained=pretrained_backbone, ordinary_init=False, bends=(3,)).features
+        del backbone[-1]
+        return get_fcn8sd(backbone=backbone, num_classes=num_classes, aux=aux, model_name=name, **kwargs)
     ctor.__name__ = name
     return ctor

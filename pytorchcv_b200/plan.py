@@ -634,9 +634,10 @@ def _lower_aspp(b, m, x, **kw):
     return lower(b, m.dropout, lower(b, m.conv, lower(b, m.branches, x)))
 
 
-@lowers("DeepLabv3FinalBlock")
+@lowers("DeepLabv3FinalBlock", "FCNFinalBlock")
 def _lower_deeplab_final(b, m, x, out_size=None, **kw):
-    """DeepLabv3FinalBlock.forward (deeplabv3.py:49-54); the result is the fp32 NCHW tensor the reference returns."""
+    """DeepLabv3FinalBlock.forward (deeplabv3.py:49-54) == FCNFinalBlock.forward (fcn8sd.py:47-52); the result is the
+    fp32 NCHW tensor the reference returns."""
     y = lower(b, m.conv2, lower(b, m.dropout, lower(b, m.conv1, x)))
     return b.bilinear(y, out_size[0], out_size[1], nchw_f32=True)
 
@@ -648,6 +649,18 @@ def _lower_deeplab(b, m, x, **kw):
     feats = lower(b, m.backbone, x)
     x4, x3 = feats[0], feats[1]
     y = lower(b, m.final_block, lower(b, m.pool, x4), out_size=in_size)
+    if m.aux:
+        return y, lower(b, m.aux_block, x3, out_size=in_size)
+    return y
+
+
+@lowers("FCN8sd")
+def _lower_fcn8sd(b, m, x, **kw):
+    """FCN8sd.forward (fcn8sd.py:112-120)."""
+    in_size = m.in_size if m.fixed_size else (x.H, x.W)
+    feats = lower(b, m.backbone, x)
+    x4, x3 = feats[0], feats[1]
+    y = lower(b, m.final_block, x4, out_size=in_size)
     if m.aux:
         return y, lower(b, m.aux_block, x3, out_size=in_size)
     return y

@@ -42,6 +42,9 @@ NETS = [
     ("efficientnet_b0_bs2", "efficientnet_b0", {}, (2, 3, 224, 224), 0, 1),
     ("mobilenetv3_large_w1_bs2", "mobilenetv3_large_w1", {}, (2, 3, 224, 224), 0, 1),
     ("mobilenetv3_small_w1_bs2", "mobilenetv3_small_w1", {}, (2, 3, 224, 224), 0, 1),
+    ("seresnet18_bs2", "seresnet18", {}, (2, 3, 224, 224), 0, 1),
+    ("seresnet50_bs2", "seresnet50", {}, (2, 3, 224, 224), 0, 1),
+    ("fcn8sd_resnetd50b_voc_bs1", "fcn8sd_resnetd50b_voc", {}, (1, 3, 480, 480), 0, 16),
 ]
 
 # block-level cases: (stem, ctor, input shape)
