@@ -318,7 +318,10 @@ static bool pick_cfg(int C, int Ho, int Wo, int KS, int S, int cols, WinParams* 
         const double halo = static_cast<double>(TH * S * TW * S) / (IH * IW);
         const double wide = std::min(1.0, CB * 2 / 64.0);          // >= 64 contiguous bytes per pixel and DRAM burst
         const double big = std::min(1.0, items * cols / 128.0);     // enough work per CTA to cover latency
-        const double score = e_w * e_h * e_t * std::sqrt(std::min(1.0, halo)) * wide * big + 1e-6 * stage;
+        // 5x5: ~160 registers per thread cap an SM at ~400 resident threads, as k CTAs of <= 400/k threads each
+        // (ncu: a single 128-thread CTA per SM left 6 % of the warp slots occupied)
+        const double occ = KS == 5 ? std::min(1.0, std::min(3, 400 / threads) * threads / 384.0) : 1.0;
+        const double score = e_w * e_h * e_t * std::sqrt(std::min(1.0, halo)) * wide * big * occ + 1e-6 * stage;
         if (score > best) {
           best = score;
           p->CB = CB; p->TW = TW; p->IW = IW; p->items = items; p->stage_bytes = stage; p->tx_bytes = IH * IW * CB * 2;
@@ -328,10 +331,17 @@ static bool pick_cfg(int C, int Ho, int Wo, int KS, int S, int cols, WinParams* 
     }
   }
   if (best < 0) return false;
-  const int budget = 100 * 1024;   // per CTA; two CTAs per SM
-  p->stages = std::max(2, std::min(4, budget / p->stage_bytes));
-  cfg->smem_bytes = p->stages * p->stage_bytes + 8 * 8 + 128;
-  cfg->ctas_per_sm = std::max(1, std::min(2, (220 * 1024) / cfg->smem_bytes));
+  if (KS == 5) {
+    const int fit = std::max(1, std::min(3, 400 / cfg->threads));        // CTAs per SM the register file allows
+    p->stages = std::max(2, std::min(4, (216 * 1024 / fit) / p->stage_bytes));
+    cfg->smem_bytes = p->stages * p->stage_bytes + 8 * 8 + 128;
+    cfg->ctas_per_sm = std::max(1, std::min(fit, (220 * 1024) / cfg->smem_bytes));
+  } else {
+    const int budget = 100 * 1024;   // per CTA; two CTAs per SM
+    p->stages = std::max(2, std::min(4, budget / p->stage_bytes));
+    cfg->smem_bytes = p->stages * p->stage_bytes + 8 * 8 + 128;
+    cfg->ctas_per_sm = std::max(1, std::min(2, (220 * 1024) / cfg->smem_bytes));
+  }
   p->tiles_x = ceil_div(Wo, p->TW);
   p->tiles_y = ceil_div(Ho, cfg->TH);
   p->cblocks = C / p->CB;
@@ -369,7 +379,7 @@ struct WinOp : Op {
     static bool attr_set = false;
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(win_kernel<OP, K_, S_, TH, COLS, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           112 * 1024);
+                                           (K_ == 5 ? 224 : 112) * 1024);
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
@@ -420,7 +430,6 @@ int win_make(int op_kind, int N, int H, int W, int C, int k, int stride, int pad
   const int IH = (op->cfg.TH - 1) * stride + k;
   if (int rc = make_win_map(&op->tm, x, N, H, W, C, in_pitch, p.CB, p.IW, IH)) return rc;
   op->op_kind = op_kind; op->S = stride; op->K = k; op->w = w; op->bias = bias;
-  if (k == 5) op->cfg.ctas_per_sm = 1;   // __launch_bounds__(384, 1)
   op->res = reinterpret_cast<const __nv_bfloat16*>(res);
   op->y = reinterpret_cast<__nv_bfloat16*>(y);
   *out = op.release();

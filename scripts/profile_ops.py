@@ -46,6 +46,12 @@ CONVS = {
         ("c1_16_96_112", 256, 112, 16, 96, 1, 1, 1, 1, 0, 2),
         ("c1_144_24_56_res", 256, 56, 144, 24, 1, 1, 1, 1, 1, 0),
     ],
+    "effi": [   # EfficientNet-b0 / MobileNetV3: 5x5 depthwise, swish epilogues (act 4)
+        ("dw5_240_28_swish", 256, 28, 240, 240, 5, 1, 1, 240, 0, 4),
+        ("dw5s2_144_56_swish", 256, 56, 144, 144, 5, 2, 1, 144, 0, 4),
+        ("dw5_672_14_swish", 256, 14, 672, 672, 5, 1, 1, 672, 0, 4),
+        ("c1_16_96_112_swish", 256, 112, 16, 96, 1, 1, 1, 1, 0, 4),
+    ],
 }
 
 
