@@ -5,7 +5,8 @@ nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv,noheader; lsc
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 600 python bench.py > gpurun_out/final_resnet50.json 2> gpurun_out/final_resnet50.err; tail -c 2500 gpurun_out/final_resnet50.json; tail -3 gpurun_out/final_resnet50.err
 cp gpurun_out/bench_ops.json gpurun_out/final_ops_resnet50.json
-for m in resnet18 mobilenetv2_w1 seresnext50_32x4d deeplabv3_resnetd50b_voc; do
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log | cut -c1-600
+for m in resnet18 mobilenetv2_w1 seresnext50_32x4d deeplabv3_resnetd50b_voc efficientnet_b0 mobilenetv3_large_w1; do
   extra=""; [ $m = resnet18 ] && extra="--dtype fp32 --batch 8"
   timeout 600 python bench.py --model $m $extra --steps 50 --ops-out gpurun_out/final_ops_$m.json > gpurun_out/final_$m.json 2> gpurun_out/final_$m.err
   python - <<PY
