@@ -112,6 +112,11 @@ PCV_API int pcv_maxpool2d(pcv_plan* plan, int dtype, int N, int H, int W, int C,
 PCV_API int pcv_global_avgpool(pcv_plan* plan, int dtype, int N, int HW, int C, const void* x, int in_pitch, void* pooled,
                        int out_dtype, pcv_stream stream);
 
+/* nn.AdaptiveAvgPool2d(k) with k > 1 (PyramidPoolingBranch, pspnet.py:55-79): y[n, by, bx, c] = mean of x over rows
+ * [floor(by*H/out_h), ceil((by+1)*H/out_h)) and the same rule in W; NHWC `dtype` in and out, y dense [N, out_h, out_w, C]. */
+PCV_API int pcv_adaptive_avgpool(pcv_plan* plan, int dtype, int N, int H, int W, int C, const void* x, int in_pitch,
+                         int out_h, int out_w, void* y, pcv_stream stream);
+
 /* SEBlock.forward (att.py:94-105) in three steps: squeeze = pcv_global_avgpool (fp32 out);
  * excite: gate = out_act(W2 * mid_act(W1 * pooled + b1) + b2), W1 [Cmid, C], W2 [C, Cmid] fp32 (att.py:74-87);
  *         `gate` must hold N*(C+Cmid) floats: [N, C] gates followed by [N, Cmid] scratch for the hidden layer;

@@ -312,10 +312,25 @@ def efficientnet(m, x):
     return sequential(m.output, x)
 
 
+def pyramid_pooling_branch(m, x):
+    """PyramidPoolingBranch.forward (pspnet.py:71-75)."""
+    in_size = m.upscale_out_size if m.upscale_out_size is not None else x.shape[2:]
+    x = conv_block(m.conv, F.adaptive_avg_pool2d(x, m.pool.output_size))
+    return F.interpolate(x, size=in_size, mode="bilinear", align_corners=True)
+
+
+def pyramid_pooling(m, x):
+    """PyramidPooling.forward (pspnet.py:116-118): Concurrent(Identity, 4 pooled branches), concatenated on channels."""
+    return concurrent(m.branches, x)
+
+
 def fcn8sd(m, x):
-    """FCN8sd.forward (fcn8sd.py:112-120); FCNFinalBlock.forward (fcn8sd.py:47-52) has DeepLabv3FinalBlock's body."""
+    """FCN8sd.forward (fcn8sd.py:112-120); FCNFinalBlock.forward (fcn8sd.py:47-52) has DeepLabv3FinalBlock's body.
+    PSPNet.forward (pspnet.py:196-205) is the same with the pyramid pooling module before the head."""
     in_size = m.in_size if m.fixed_size else x.shape[2:]
     x, y = multi_output_sequential(m.backbone, x)
+    if hasattr(m, "pool"):
+        x = pyramid_pooling(m.pool, x)
     x = deeplab_final_block(m.final_block, x, in_size)
     if m.aux:
         return x, deeplab_final_block(m.aux_block, y, in_size)
@@ -345,7 +360,8 @@ _BY_NAME = {
     "ConvBlock": conv_block, "DwsConvBlock": dws_conv_block, "SEBlock": se_block,
     "ResBlock": res_body, "ResBottleneck": res_body, "ResNeXtBottleneck": res_body,
     "ResUnit": res_unit, "ResNeXtUnit": res_unit, "SEResNeXtUnit": se_resnext_unit, "SEResUnit": se_resnext_unit,
-    "SEResNet": classifier, "FCN8sd": fcn8sd,
+    "SEResNet": classifier, "FCN8sd": fcn8sd, "PSPNet": fcn8sd, "PyramidPoolingBranch": pyramid_pooling_branch,
+    "PyramidPooling": pyramid_pooling, "Identity": lambda m, x: x,
     "ResInitBlock": res_init_block, "SEInitBlock": se_init_block, "LinearBottleneck": linear_bottleneck,
     "ResNet": classifier, "SEResNeXt": classifier, "ResNeXt": classifier, "MobileNet": classifier,
     "MobileNetV2": mobilenetv2, "ResNetD": resnetd,
@@ -364,7 +380,7 @@ def oracle_forward(m: nn.Module, x: torch.Tensor, **kw):
     if x.is_cuda:
         raise ValueError("the oracle is a CPU restatement; pass CPU tensors")
     name = type(m).__name__
-    if name in ("DeepLabv3FinalBlock", "FCNFinalBlock"):
+    if name in ("DeepLabv3FinalBlock", "FCNFinalBlock", "PSPFinalBlock"):
         return deeplab_final_block(m, x, kw["out_size"])
     fn = _BY_NAME.get(name)
     if fn is not None:

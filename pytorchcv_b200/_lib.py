@@ -47,6 +47,7 @@ SIGNATURES = {
     "pcv_conv2d_bias_act": (_I, [_P, C.POINTER(ConvDesc), _I, _P, _P, _P, _P, _P, _P]),
     "pcv_maxpool2d": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P]),
     "pcv_global_avgpool": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _I, _P]),
+    "pcv_adaptive_avgpool": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P]),
     "pcv_se_excite": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "pcv_se_scale_add_act": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P]),
     "pcv_add_act": (_I, [_P, _I, _Z, _P, _P, _I, _P, _P]),

@@ -178,6 +178,64 @@ struct GapOp : Op {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// nn.AdaptiveAvgPool2d(k) (PyramidPoolingBranch, pspnet.py:71-75): bin (by, bx) averages rows
+// [floor(by*H/k), ceil((by+1)*H/k)) x the same in W (torch's adaptive pooling rule); fp32 accumulate.
+// CTA = one bin of one image x a slab of 256 channels: 32 lanes of 8-channel vectors x 8 pixel lanes, 4 loads in flight.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+adaptive_avgpool_kernel(int H, int W, int C, int OH, int OW, const T* __restrict__ x, int in_pitch, T* __restrict__ y) {
+  __shared__ float red[8][256];
+  const int bin = blockIdx.x, n = blockIdx.z;
+  const int by = bin / OW, bx = bin - by * OW;
+  const int h0 = (by * H) / OH, h1 = ((by + 1) * H + OH - 1) / OH;
+  const int w0 = (bx * W) / OW, w1 = ((bx + 1) * W + OW - 1) / OW;
+  const int cvi = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int c = blockIdx.y * 256 + cvi * 8;
+  const int bw = w1 - w0, npx = (h1 - h0) * bw;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (c < C) {
+    const T* base = x + (static_cast<size_t>(n) * H * W) * in_pitch + c;
+    for (int p = pl; p < npx; p += 8) {
+      const int r = p / bw, q = p - r * bw;
+      float v[8];
+      V8<T>::load(base + (static_cast<size_t>(h0 + r) * W + w0 + q) * in_pitch, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += v[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[pl][cvi * 8 + e] = acc[e];
+  __syncthreads();
+  const int ch = threadIdx.x;
+  if (blockIdx.y * 256 + ch < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += red[q][ch];
+    const float mean = s / static_cast<float>(npx);
+    const size_t o = ((static_cast<size_t>(n) * OH + by) * OW + bx) * C + blockIdx.y * 256 + ch;
+    V8<T>::st1(y + o, mean);
+  }
+}
+
+struct AdaptivePoolOp : Op {
+  int dtype, N, H, W, C, OH, OW, in_pitch;
+  const void* x;
+  void* y;
+  cudaError_t launch(cudaStream_t s) override {
+    g_launches++;
+    dim3 grid(OH * OW, ceil_div(C, 256), N);
+    if (dtype == PCV_F32)
+      adaptive_avgpool_kernel<float><<<grid, 256, 0, s>>>(H, W, C, OH, OW, (const float*)x, in_pitch, (float*)y);
+    else
+      adaptive_avgpool_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(H, W, C, OH, OW, (const __nv_bfloat16*)x, in_pitch, (__nv_bfloat16*)y);
+    return cudaGetLastError();
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
 // skinny fp32 FC: y[n, j] = act(b[j] + sum_c x[n, c] * W[j, c]).  CTA = 8 images x 8 outputs (one output per warp),
 // lanes stride over c so W rows are read coalesced and reused across the 8 images.
 // ---------------------------------------------------------------------------------------------------------------
@@ -699,6 +757,25 @@ int pcv_global_avgpool(pcv_plan* plan, int dtype, int N, int HW, int C, const vo
   snprintf(nm, sizeof nm, "gavgpool_%s C=%d HW=%d", dn(dtype), C, HW);
   op->name = nm;
   op->bytes = esize(dtype) * static_cast<double>(N) * C * HW + esize(out_dtype) * static_cast<double>(N) * C;
+  return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
+}
+
+int pcv_adaptive_avgpool(pcv_plan* plan, int dtype, int N, int H, int W, int C, const void* x, int in_pitch, int out_h,
+                         int out_w, void* y, pcv_stream stream) {
+  PCV_DTYPE_OK(dtype);
+  PCV_REQUIRE(x && y, "NULL tensor pointer");
+  PCV_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && N <= 65535, "bad adaptive avgpool dims");
+  PCV_REQUIRE(out_h > 0 && out_w > 0 && out_h <= H && out_w <= W && out_h * out_w <= 65535, "adaptive avgpool output %dx%d must fit the %dx%d map", out_h, out_w, H, W);
+  in_pitch = pitch_or(in_pitch, C);
+  PCV_REQUIRE(C % 8 == 0 && in_pitch % 8 == 0, "adaptive avgpool needs channel count/pitch % 8 == 0");
+  auto op = std::make_unique<AdaptivePoolOp>();
+  op->dtype = dtype; op->N = N; op->H = H; op->W = W; op->C = C; op->OH = out_h; op->OW = out_w; op->in_pitch = in_pitch;
+  op->x = x; op->y = y;
+  char nm[96];
+  snprintf(nm, sizeof nm, "adaptive_avgpool_%s C=%d %dx%d->%dx%d", dn(dtype), C, H, W, out_h, out_w);
+  op->name = nm;
+  // overlapping bins re-read the shared rows / columns (L2 hits); algorithmic bytes = the map once + the bins
+  op->bytes = esize(dtype) * static_cast<double>(N) * C * (static_cast<double>(H) * W + out_h * out_w);
   return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
 }
 

@@ -101,6 +101,15 @@ def global_avgpool(x: torch.Tensor, out_dtype=None) -> torch.Tensor:
     return out
 
 
+def adaptive_avgpool(x: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
+    """nn.AdaptiveAvgPool2d((out_h, out_w)) on an NHWC tensor (pspnet.py:71)."""
+    _need_cuda(x)
+    N, H, W, Cc = x.shape
+    out = torch.empty((N, out_h, out_w, Cc), dtype=x.dtype, device=x.device)
+    _lib.call("pcv_adaptive_avgpool", None, _dt(x), N, H, W, Cc, x.data_ptr(), Cc, out_h, out_w, out.data_ptr(), _stream())
+    return out
+
+
 def se_excite(pooled: torch.Tensor, w1, b1, w2, b2, mid_act=_lib.ACT_RELU, out_act=_lib.ACT_SIGMOID) -> torch.Tensor:
     _need_cuda(pooled, w1, w2)
     N, Cc = pooled.shape

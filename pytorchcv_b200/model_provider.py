@@ -42,6 +42,8 @@ for _name, (_b, _k) in nets.DEEPLABV3_VARIANTS.items():
     _register(_name, nets._deeplab_ctor(_name, _b, _k))
 for _name, (_b, _k) in nets.FCN8SD_VARIANTS.items():
     _register(_name, nets._fcn8sd_ctor(_name, _b, _k))
+for _name, (_b, _k) in nets.PSPNET_VARIANTS.items():
+    _register(_name, nets._pspnet_ctor(_name, _b, _k))
 for _name, _fixed in nets.SERESNET_VARIANTS.items():
     _register(_name, (lambda n, f: lambda **kw: nets.get_seresnet(model_name=n, **f, **kw))(_name, _fixed))
 

@@ -918,3 +918,78 @@ def _fcn8sd_ctor(name, depth, default_classes):
         return get_fcn8sd(backbone=backbone, num_classes=num_classes, aux=aux, model_name=name, **kwargs)
     ctor.__name__ = name
     return ctor
+
+
+# ===== PSPNet on the ResNet(D) backbone (pspnet.py), SURVEY 8(f) rank 3 ================================================
+class Identity(nn.Module):
+    """common/tutti.py:18-29 (no parameters; the plan compiler turns it into a channel slice of the concat buffer)."""
+
+    def forward(self, x):
+        return x
+
+
+class PSPFinalBlock(FCNFinalBlock):
+    """pspnet.py:17-52: the same head as FCNFinalBlock."""
+
+
+class PyramidPoolingBranch(B200Module):
+    """AdaptiveAvgPool2d(k) -> 1x1 ConvBlock -> bilinear to the map size (pspnet.py:55-79)."""
+
+    def __init__(self, in_channels, out_channels, pool_out_size, upscale_out_size):
+        super().__init__()
+        self.upscale_out_size = upscale_out_size
+        self.pool = nn.AdaptiveAvgPool2d(pool_out_size)
+        self.conv = conv1x1_block(in_channels=in_channels, out_channels=out_channels)
+
+
+class PyramidPooling(B200Module):
+    """Identity + four pooled branches (bins 1, 2, 3, 6), concatenated on channels (pspnet.py:82-119)."""
+
+    def __init__(self, in_channels, upscale_out_size):
+        super().__init__()
+        assert in_channels % 4 == 0
+        mid = in_channels // 4
+        self.branches = Concurrent()
+        self.branches.add_module("branch1", Identity())
+        for i, k in enumerate([1, 2, 3, 6]):
+            self.branches.add_module(f"branch{i + 2}", PyramidPoolingBranch(
+                in_channels=in_channels, out_channels=mid, pool_out_size=k, upscale_out_size=upscale_out_size))
+
+
+class PSPNet(B200Module):
+    """pspnet.py:122-205."""
+
+    def __init__(self, backbone, backbone_out_channels=2048, aux=False, fixed_size=True, in_channels=3,
+                 in_size=(480, 480), num_classes=21):
+        super().__init__()
+        assert in_channels > 0
+        assert in_size[0] % 8 == 0 and in_size[1] % 8 == 0
+        self.in_size, self.num_classes, self.aux, self.fixed_size = in_size, num_classes, aux, fixed_size
+        self.backbone = backbone
+        pool_out_size = (in_size[0] // 8, in_size[1] // 8) if fixed_size else None
+        self.pool = PyramidPooling(in_channels=backbone_out_channels, upscale_out_size=pool_out_size)
+        self.final_block = PSPFinalBlock(in_channels=2 * backbone_out_channels, out_channels=num_classes,
+                                         bottleneck_factor=8)
+        if aux:
+            self.aux_block = PSPFinalBlock(in_channels=backbone_out_channels // 2, out_channels=num_classes,
+                                           bottleneck_factor=4)
+        _kaiming_init(self)
+
+
+def get_pspnet(backbone, num_classes, aux=False, model_name=None, pretrained=False, root=None, **kwargs):
+    net = PSPNet(backbone=backbone, num_classes=num_classes, aux=aux, **kwargs)
+    _no_pretrained(pretrained, model_name)
+    return net
+
+
+PSPNET_VARIANTS = {name.replace("fcn8sd", "pspnet"): v for name, v in FCN8SD_VARIANTS.items()}   # pspnet.py:250-560
+
+
+def _pspnet_ctor(name, depth, default_classes):
+    def ctor(pretrained_backbone=False, num_classes=default_classes, aux=True, **kwargs):
+        backbone = get_resnetd(blocks=depth, conv1_stride=False, model_name=f"resnetd{depth}b",
+                               pretrained=pretrained_backbone, ordinary_init=False, bends=(3,)).features
+        del backbone[-1]
+        return get_pspnet(backbone=backbone, num_classes=num_classes, aux=aux, model_name=name, **kwargs)
+    ctor.__name__ = name
+    return ctor

@@ -293,6 +293,16 @@ class Builder:
             "pcv_global_avgpool", plan, x.dtype, x.N, x.H * x.W, x.C, ptr(x), x.pitch, ptr(out), out_dtype, None))
         return out
 
+    def adaptive_pool(self, x: TRef, out_h: int, out_w: int) -> TRef:
+        """nn.AdaptiveAvgPool2d((out_h, out_w)) (pspnet.py:71); (1, 1) is the global pool."""
+        if (out_h, out_w) == (1, 1):
+            return self.gap(x)
+        out = self.new(x.N, out_h, out_w, x.C, dtype=x.dtype)
+        self._use(x, out)
+        self.ops.append(lambda plan, ptr, wptr: _lib.call(
+            "pcv_adaptive_avgpool", plan, x.dtype, x.N, x.H, x.W, x.C, ptr(x), x.pitch, out_h, out_w, ptr(out), None))
+        return out
+
     def se_gate(self, pooled: TRef, w1: torch.Tensor, b1, w2: torch.Tensor, b2, mid_act: int, out_act: int) -> TRef:
         """SEBlock excite (att.py:99-102): gate = out_act(W2 @ mid_act(W1 @ pooled + b1) + b2), all fp32."""
         N, Cc = pooled.N, pooled.C
@@ -451,9 +461,10 @@ def _lower_avgpool(b, m, x, **kw):
 
 @lowers("AdaptiveAvgPool2d")
 def _lower_adaptive(b, m, x, **kw):
-    if m.output_size not in (1, (1, 1)):
-        raise NotImplementedError("only AdaptiveAvgPool2d(1) is supported")
-    return b.gap(x)
+    size = m.output_size if isinstance(m.output_size, (tuple, list)) else (m.output_size, m.output_size)
+    if None in size:
+        raise NotImplementedError("AdaptiveAvgPool2d with a None output size is outside the B200 eval path")
+    return b.adaptive_pool(x, int(size[0]), int(size[1]))
 
 
 def _se_parts(b, m):
@@ -602,11 +613,17 @@ def _lower_concurrent(b, m, x, **kw):
     if m.merge_type != "cat" or m.axis != 1:
         raise NotImplementedError("only Concurrent(cat, axis=1) is supported")
     branches = list(m.children())
-    widths = [_branch_width(br) for br in branches]
+    widths = [_branch_width(br, x.C) for br in branches]
     Ho, Wo = x.H, x.W
     cat = b.new(x.N, Ho, Wo, sum(widths))
     off = 0
     for br, wd in zip(branches, widths):
+        if type(br).__name__ == "Identity":
+            # PyramidPooling's first branch (pspnet.py:109): the input itself becomes a channel slice of the concat
+            # buffer - a same-size align_corners resample is an exact copy (weights 1 / 0) into the pitched slice
+            y = b.bilinear(x, x.H, x.W, out=Builder.view(cat, off, wd))
+            off += wd
+            continue
         y = lower(b, br, x, out=Builder.view(cat, off, wd))
         if y.buf is not cat.buf:
             raise NotImplementedError(f"branch {type(br).__name__} cannot write into a concat slice")
@@ -614,9 +631,11 @@ def _lower_concurrent(b, m, x, **kw):
     return cat
 
 
-def _branch_width(br: nn.Module) -> int:
+def _branch_width(br: nn.Module, in_channels: int | None = None) -> int:
     convs = [mod for mod in br.modules() if isinstance(mod, nn.Conv2d)]
     if not convs:
+        if type(br).__name__ == "Identity" and in_channels is not None:
+            return in_channels
         raise NotImplementedError(f"cannot infer the width of branch {type(br).__name__}")
     return convs[-1].out_channels
 
@@ -629,12 +648,25 @@ def _lower_aspp_avg(b, m, x, out=None, **kw):
     return b.bilinear(y, size[0], size[1], out=out)
 
 
+@lowers("PyramidPoolingBranch")
+def _lower_pyramid_branch(b, m, x, out=None, **kw):
+    """PyramidPoolingBranch.forward (pspnet.py:71-75): adaptive pool -> 1x1 ConvBlock -> bilinear back to the map size."""
+    size = m.upscale_out_size if m.upscale_out_size is not None else (x.H, x.W)
+    y = lower(b, m.conv, lower(b, m.pool, x))
+    return b.bilinear(y, size[0], size[1], out=out)
+
+
+@lowers("PyramidPooling")
+def _lower_pyramid_pooling(b, m, x, **kw):
+    return lower(b, m.branches, x)
+
+
 @lowers("AtrousSpatialPyramidPooling")
 def _lower_aspp(b, m, x, **kw):
     return lower(b, m.dropout, lower(b, m.conv, lower(b, m.branches, x)))
 
 
-@lowers("DeepLabv3FinalBlock", "FCNFinalBlock")
+@lowers("DeepLabv3FinalBlock", "FCNFinalBlock", "PSPFinalBlock")
 def _lower_deeplab_final(b, m, x, out_size=None, **kw):
     """DeepLabv3FinalBlock.forward (deeplabv3.py:49-54) == FCNFinalBlock.forward (fcn8sd.py:47-52); the result is the
     fp32 NCHW tensor the reference returns."""
@@ -654,12 +686,14 @@ def _lower_deeplab(b, m, x, **kw):
     return y
 
 
-@lowers("FCN8sd")
+@lowers("FCN8sd", "PSPNet")
 def _lower_fcn8sd(b, m, x, **kw):
-    """FCN8sd.forward (fcn8sd.py:112-120)."""
+    """FCN8sd.forward (fcn8sd.py:112-120); PSPNet.forward (pspnet.py:196-205) adds the pyramid pooling module."""
     in_size = m.in_size if m.fixed_size else (x.H, x.W)
     feats = lower(b, m.backbone, x)
     x4, x3 = feats[0], feats[1]
+    if hasattr(m, "pool"):
+        x4 = lower(b, m.pool, x4)
     y = lower(b, m.final_block, x4, out_size=in_size)
     if m.aux:
         return y, lower(b, m.aux_block, x3, out_size=in_size)

@@ -45,6 +45,7 @@ NETS = [
     ("seresnet18_bs2", "seresnet18", {}, (2, 3, 224, 224), 0, 1),
     ("seresnet50_bs2", "seresnet50", {}, (2, 3, 224, 224), 0, 1),
     ("fcn8sd_resnetd50b_voc_bs1", "fcn8sd_resnetd50b_voc", {}, (1, 3, 480, 480), 0, 16),
+    ("pspnet_resnetd50b_voc_bs1", "pspnet_resnetd50b_voc", {}, (1, 3, 480, 480), 0, 16),
 ]
 
 # block-level cases: (stem, ctor, input shape)

@@ -74,6 +74,18 @@ def test_global_avgpool(shape, dtype, tol):
     assert _rel(got, want) <= tol
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 4e-3), (torch.float32, 1e-6)])
+@pytest.mark.parametrize("shape,k", [((2, 512, 60, 60), 6), ((1, 264, 15, 17), 3), ((3, 64, 7, 7), 2), ((2, 2048, 9, 9), 1)])
+def test_adaptive_avgpool(shape, k, dtype, tol):
+    """nn.AdaptiveAvgPool2d(k) of PyramidPoolingBranch (pspnet.py:71): torch's floor/ceil bin edges, overlapping bins."""
+    from pytorchcv_b200 import functional as P
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(13))
+    want = F.adaptive_avg_pool2d(x.to(dtype).float(), k)
+    got = _nchw(P.adaptive_avgpool(_nhwc(x, dtype), k, k))
+    assert got.shape == want.shape
+    assert _rel(got, want) <= tol
+
+
 @pytest.mark.parametrize("N,C,mid", [(4, 256, 16), (3, 2048, 128), (1, 64, 4), (70, 512, 32), (256, 1000, 60)])
 def test_se_excite_and_scale(N, C, mid):
     from pytorchcv_b200 import functional as P, _lib
