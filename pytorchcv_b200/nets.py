@@ -30,14 +30,37 @@ def _kaiming_init(net: nn.Module) -> None:
                 nn.init.constant_(mod.bias, 0)
 
 
-def _no_pretrained(pretrained: bool, model_name) -> None:
+def _load_pretrained(net: nn.Module, pretrained: bool, model_name, root=None) -> None:
+    """`pretrained=True`: the local-cache half of the reference's model store
+    (common/model_store.py:140-192, 339-362).  The reference names a checkpoint `{model}-{error}-{sha1[:8]}.pth` under
+    `root` (default ~/.torch/models) and downloads it when it is missing; the B200 path has no network, so it loads a
+    cached file whose content hash matches the 8 hex digits in its own name and raises otherwise.  The state_dict keys are
+    the reference's, so its checkpoints load unchanged."""
     if not pretrained:
         return
     if not model_name:
         raise ValueError("Parameter `model_name` should be properly initialized for loading pretrained model.")
-    raise RuntimeError("pretrained=True needs the reference's model_store download path, which is out of scope for "
-                       "the B200 eval path (no network); build with pretrained=False and load_state_dict() a "
-                       "reference checkpoint instead — the state_dict keys are identical")
+    import glob
+    import hashlib
+    import os
+    import torch
+    root = os.path.expanduser(root if root is not None else os.path.join("~", ".torch", "models"))
+    tried = []
+    for path in sorted(glob.glob(os.path.join(root, f"{model_name}-*-????????.pth"))):
+        h = hashlib.sha1()
+        with open(path, "rb") as f:
+            for chunk in iter(lambda: f.read(1 << 20), b""):
+                h.update(chunk)
+        if h.hexdigest()[:8] != path[-12:-4]:
+            tried.append(f"{os.path.basename(path)} (sha1 mismatch)")
+            continue
+        net.load_state_dict(torch.load(path, map_location="cpu", weights_only=True))
+        return
+    raise RuntimeError(
+        f"pretrained=True: no verified checkpoint '{model_name}-<error>-<sha1[:8]>.pth' under {root}"
+        + (f" (rejected: {', '.join(tried)})" if tried else "")
+        + "; the B200 eval path never downloads (no network) - copy the reference's cached file there, or build with "
+          "pretrained=False and load_state_dict() a reference checkpoint (the keys are identical)")
 
 
 def _stages(features: nn.Sequential, channels, in_channels, make_unit, stride_of=None):
@@ -187,7 +210,7 @@ def get_resnet(blocks, bottleneck=None, conv1_stride=True, width_scale=1.0, mode
     channels, init_channels = _scaled([[w] * n for w, n in zip(widths, layers)], 64, width_scale)
     net = ResNet(channels=channels, init_block_channels=init_channels, bottleneck=bottleneck,
                  conv1_stride=conv1_stride, **kwargs)
-    _no_pretrained(pretrained, model_name)
+    _load_pretrained(net, pretrained, model_name, root)
     return net
 
 
@@ -263,7 +286,7 @@ def get_mobilenetv2(width_scale, remove_exp_conv=False, model_name=None, pretrai
             final_channels = int(final_channels * width_scale)
     net = MobileNetV2(channels=channels, init_block_channels=init_channels, final_block_channels=final_channels,
                       remove_exp_conv=remove_exp_conv, **kwargs)
-    _no_pretrained(pretrained, model_name)
+    _load_pretrained(net, pretrained, model_name, root)
     return net
 
 
@@ -398,7 +421,7 @@ def get_efficientnet(version, in_size, tf_mode=False, bn_eps=1e-5, model_name=No
     net = EfficientNet(channels=channels, init_block_channels=round_channels(32 * width),
                        final_block_channels=final_channels, kernel_sizes=kernels, strides_per_stage=strides,
                        expansion_factors=expansions, dropout_rate=dropout, tf_mode=tf_mode, bn_eps=bn_eps, **kwargs)
-    _no_pretrained(pretrained, model_name)
+    _load_pretrained(net, pretrained, model_name, root)
     return net
 
 
@@ -505,7 +528,7 @@ def get_mobilenetv3(version, width_scale, model_name=None, pretrained=False, roo
             t["final_block_channels"] = round_channels(t["final_block_channels"] * width_scale)
     net = MobileNetV3(init_block_channels=init_channels, classifier_mid_channels=1280, final_use_se=False, **t,
                       **kwargs)
-    _no_pretrained(pretrained, model_name)
+    _load_pretrained(net, pretrained, model_name, root)
     return net
 
 
@@ -555,7 +578,7 @@ def get_mobilenet(width_scale, dws_simplified=False, model_name=None, pretrained
         channels = [[int(c * width_scale) for c in ci] for ci in channels]
     net = MobileNet(channels=channels, first_stage_stride=False, dw_use_bn=not dws_simplified,
                     dw_activation=None if dws_simplified else lambda_relu(), **kwargs)
-    _no_pretrained(pretrained, model_name)
+    _load_pretrained(net, pretrained, model_name, root)
     return net
 
 
@@ -626,28 +649,29 @@ class SEResNeXt(_ResNeXtLike):
     unit_cls = SEResNeXtUnit
 
 
-def _get_resnext_like(cls, family, layer_table, blocks, cardinality, bottleneck_width, model_name, pretrained, kwargs):
+def _get_resnext_like(cls, family, layer_table, blocks, cardinality, bottleneck_width, model_name, pretrained, kwargs,
+                      root=None):
     if blocks not in layer_table:
         raise ValueError("Unsupported {} with number of blocks: {}".format(family, blocks))
     layers = layer_table[blocks]
     channels = [[w] * n for w, n in zip([256, 512, 1024, 2048], layers)]
     net = cls(channels=channels, init_block_channels=64, cardinality=cardinality, bottleneck_width=bottleneck_width,
               **kwargs)
-    _no_pretrained(pretrained, model_name)
+    _load_pretrained(net, pretrained, model_name, root)
     return net
 
 
 def get_seresnext(blocks, cardinality, bottleneck_width, model_name=None, pretrained=False, root=None, **kwargs):
     """Same contract as seresnext.py:143-201."""
     return _get_resnext_like(SEResNeXt, "SE-ResNeXt", {50: [3, 4, 6, 3], 101: [3, 4, 23, 3]}, blocks, cardinality,
-                             bottleneck_width, model_name, pretrained, kwargs)
+                             bottleneck_width, model_name, pretrained, kwargs, root)
 
 
 def get_resnext(blocks, cardinality, bottleneck_width, model_name=None, pretrained=False, root=None, **kwargs):
     """Same contract as resnext.py:193-259."""
     table = {14: [1, 1, 1, 1], 26: [2, 2, 2, 2], 38: [3, 3, 3, 3], 50: [3, 4, 6, 3], 101: [3, 4, 23, 3]}
     return _get_resnext_like(ResNeXt, "ResNeXt", table, blocks, cardinality, bottleneck_width, model_name, pretrained,
-                             kwargs)
+                             kwargs, root)
 
 
 SERESNEXT_VARIANTS = {"seresnext50_32x4d": (50, 32, 4), "seresnext101_32x4d": (101, 32, 4),
@@ -706,7 +730,7 @@ def get_seresnet(blocks, bottleneck=None, conv1_stride=True, model_name=None, pr
         widths = [w * 4 for w in widths]
     net = SEResNet(channels=[[w] * n for w, n in zip(widths, layers)], init_block_channels=64, bottleneck=bottleneck,
                    conv1_stride=conv1_stride, **kwargs)
-    _no_pretrained(pretrained, model_name)
+    _load_pretrained(net, pretrained, model_name, root)
     return net
 
 
@@ -778,7 +802,7 @@ def get_resnetd(blocks, conv1_stride=True, width_scale=1.0, model_name=None, pre
     channels, init_channels = _scaled([[w] * n for w, n in zip(widths, table[blocks])], 64, width_scale)
     net = ResNetD(channels=channels, init_block_channels=init_channels, bottleneck=bottleneck,
                   conv1_stride=conv1_stride, **kwargs)
-    _no_pretrained(pretrained, model_name)
+    _load_pretrained(net, pretrained, model_name, root)
     return net
 
 
@@ -842,7 +866,7 @@ class DeepLabv3(B200Module):
 
 def get_deeplabv3(backbone, num_classes, aux=False, model_name=None, pretrained=False, root=None, **kwargs):
     net = DeepLabv3(backbone=backbone, num_classes=num_classes, aux=aux, **kwargs)
-    _no_pretrained(pretrained, model_name)
+    _load_pretrained(net, pretrained, model_name, root)
     return net
 
 
@@ -898,7 +922,7 @@ class FCN8sd(B200Module):
 
 def get_fcn8sd(backbone, num_classes, aux=False, model_name=None, pretrained=False, root=None, **kwargs):
     net = FCN8sd(backbone=backbone, num_classes=num_classes, aux=aux, **kwargs)
-    _no_pretrained(pretrained, model_name)
+    _load_pretrained(net, pretrained, model_name, root)
     return net
 
 
@@ -978,7 +1002,7 @@ class PSPNet(B200Module):
 
 def get_pspnet(backbone, num_classes, aux=False, model_name=None, pretrained=False, root=None, **kwargs):
     net = PSPNet(backbone=backbone, num_classes=num_classes, aux=aux, **kwargs)
-    _no_pretrained(pretrained, model_name)
+    _load_pretrained(net, pretrained, model_name, root)
     return net
 
 

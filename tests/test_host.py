@@ -165,3 +165,26 @@ def test_product_does_not_import_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f"{f} imports the oracle"
                 assert "/root/reference" not in text, f"{f} reads the reference at run time"
+
+
+def test_pretrained_loads_a_verified_local_checkpoint(tmp_path):
+    """pretrained=True: the reference's cache file naming `{model}-{error}-{sha1[:8]}.pth`
+    (model_store.py:158-165), content hash checked, never a download."""
+    import hashlib
+    src = P.get_model("resnet10", pretrained=False)
+    with torch.no_grad():
+        for prm in src.parameters():
+            prm.add_(0.25)
+    raw = tmp_path / "w.pth"
+    torch.save(src.state_dict(), raw)
+    sha = hashlib.sha1(raw.read_bytes()).hexdigest()
+    raw.rename(tmp_path / f"resnet10-1234-{sha[:8]}.pth")
+    net = P.get_model("resnet10", pretrained=True, root=str(tmp_path))
+    for (ka, a), (kb, bb) in zip(src.state_dict().items(), net.state_dict().items()):
+        assert ka == kb and torch.equal(a, bb)
+    # a file whose content does not match the hash in its name is rejected; a missing file is an error, not a download
+    (tmp_path / "resnet12-0000-deadbeef.pth").write_bytes(b"not a checkpoint")
+    with pytest.raises(RuntimeError, match="sha1 mismatch"):
+        P.get_model("resnet12", pretrained=True, root=str(tmp_path))
+    with pytest.raises(RuntimeError, match="never downloads"):
+        P.get_model("resnet14", pretrained=True, root=str(tmp_path))
