@@ -179,7 +179,7 @@ def main() -> None:
 
     def barrier():
         if world > 1:
-            dist.barrier()
+            dist.barrier(device_ids=[local])
         torch.cuda.synchronize(dev)
 
     # ---------------- value: inputs resident in HBM ----------------
