@@ -148,7 +148,9 @@ PCV_API int pcv_nhwc_to_nchw_f32(pcv_plan* plan, int dtype, int N, int C, int H,
 PCV_API int pcv_stem_s2d_dims(int C, int H, int W, int k, int* rows, int* cols, int* cin_eq, int* taps_eq);
 PCV_API int pcv_stem_s2d_ingest(pcv_plan* plan, int N, int C, int H, int W, int k, const float* x, void* s2d,
                                 pcv_stream stream);
-/* 1 when the stem conv (C-channel HxW image, k x k stride 2 pad k/2, Cout channels) can run with PCV_CONV_POOL3S2. */
+/* 1 when the stem conv (C-channel HxW image, k x k stride 2 pad k/2, Cout channels) can run with PCV_CONV_POOL3S2:
+ * Cout == 64, even conv map with 64 <= W/2 and W/2 + k/2 <= 128 columns (one conv row per 128-row M-block), else 0 and the
+ * caller records pcv_conv2d_bias_act + pcv_maxpool2d. */
 PCV_API int pcv_stem_s2d_pool_ok(int C, int H, int W, int k, int Cout);
 PCV_API int pcv_stem_s2d_weights(int Cout, int C, int k, const float* w, float* w_eq, pcv_stream stream);
 
