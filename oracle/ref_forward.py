@@ -288,6 +288,23 @@ def mobilenetv3_unit(m, x):
     return x + identity if m.residual else x
 
 
+def dws_exp_se_res_unit(m, x):
+    """DwsExpSEResUnit.forward (mnasnet.py:77-88)."""
+    identity = x
+    if m.use_exp_conv:
+        x = conv_block(m.exp_conv, x)
+    x = conv_block(m.dw_conv, x)
+    if m.use_se:
+        x = se_block(m.se, x)
+    x = conv_block(m.pw_conv, x)
+    return x + identity if m.residual else x
+
+
+def mnas_edge_block(m, x):
+    """MnasInitBlock.forward / MnasFinalBlock.forward (mnasnet.py:121-124, 157-160)."""
+    return oracle_forward(m.conv2, oracle_forward(m.conv1, x))
+
+
 def mobilenetv3_final_block(m, x):
     """MobileNetV3FinalBlock.forward (mobilenetv3.py:127-131)."""
     x = conv_block(m.conv, x)
@@ -367,6 +384,8 @@ _BY_NAME = {
     "MobileNetV2": mobilenetv2, "ResNetD": resnetd,
     "EffiInitBlock": effi_init_block, "EffiDwsConvUnit": effi_dws_conv_unit, "EffiInvResUnit": effi_inv_res_unit,
     "EfficientNet": efficientnet,
+    "DwsExpSEResUnit": dws_exp_se_res_unit, "MnasInitBlock": mnas_edge_block, "MnasFinalBlock": mnas_edge_block,
+    "MnasNet": classifier,
     "MobileNetV3Unit": mobilenetv3_unit, "MobileNetV3FinalBlock": mobilenetv3_final_block,
     "MobileNetV3Classifier": mobilenetv3_classifier, "MobileNetV3": mobilenetv3,
     "Concurrent": concurrent, "MultiOutputSequential": multi_output_sequential,

@@ -538,6 +538,107 @@ MOBILENETV3_VARIANTS = {
 }
 
 
+# ===== MnasNet (mnasnet.py), SURVEY 8(f) rank 1 ========================================================================
+class DwsExpSEResUnit(B200Module):
+    """[1x1 expand] -> dw 3x3 | 5x5 -> [SE] -> 1x1 linear (+x) (mnasnet.py:16-88)."""
+
+    def __init__(self, in_channels, out_channels, stride=1, use_kernel3=True, exp_factor=1, se_factor=0, use_skip=True,
+                 activation=lambda_relu()):
+        super().__init__()
+        assert exp_factor >= 1
+        self.residual = (in_channels == out_channels) and (stride == 1) and use_skip
+        self.use_exp_conv = exp_factor > 1
+        self.use_se = se_factor > 0
+        mid = exp_factor * in_channels
+        if self.use_exp_conv:
+            self.exp_conv = conv1x1_block(in_channels=in_channels, out_channels=mid, activation=activation)
+        dw = dwconv3x3_block if use_kernel3 else dwconv5x5_block
+        self.dw_conv = dw(in_channels=mid, out_channels=mid, stride=stride, activation=activation)
+        if self.use_se:
+            self.se = SEBlock(channels=mid, reduction=exp_factor * se_factor, round_mid=False,
+                              mid_activation=activation)
+        self.pw_conv = conv1x1_block(in_channels=mid, out_channels=out_channels, activation=None)
+
+
+class MnasInitBlock(B200Module):
+    """conv3x3/2 -> DwsExpSEResUnit (mnasnet.py:91-124)."""
+
+    def __init__(self, in_channels, out_channels, mid_channels, use_skip):
+        super().__init__()
+        self.conv1 = conv3x3_block(in_channels=in_channels, out_channels=mid_channels, stride=2)
+        self.conv2 = DwsExpSEResUnit(in_channels=mid_channels, out_channels=out_channels, use_skip=use_skip)
+
+
+class MnasFinalBlock(B200Module):
+    """DwsExpSEResUnit(exp 6) -> conv1x1 (mnasnet.py:127-160)."""
+
+    def __init__(self, in_channels, out_channels, mid_channels, use_skip):
+        super().__init__()
+        self.conv1 = DwsExpSEResUnit(in_channels=in_channels, out_channels=mid_channels, exp_factor=6,
+                                     use_skip=use_skip)
+        self.conv2 = conv1x1_block(in_channels=mid_channels, out_channels=out_channels)
+
+
+class MnasNet(_Classifier):
+    """mnasnet.py:163-253."""
+
+    def __init__(self, channels, init_block_channels, final_block_channels, kernels3, exp_factors, se_factors,
+                 init_block_use_skip, final_block_use_skip, in_channels=3, in_size=(224, 224), num_classes=1000):
+        super().__init__()
+        self.in_size, self.num_classes = in_size, num_classes
+        self.features = nn.Sequential()
+        self.features.add_module("init_block", MnasInitBlock(in_channels=in_channels,
+                                                             out_channels=init_block_channels[1],
+                                                             mid_channels=init_block_channels[0],
+                                                             use_skip=init_block_use_skip))
+        last = _stages(self.features, channels, init_block_channels[1],
+                       lambda i, j, cin, cout, s: DwsExpSEResUnit(
+                           in_channels=cin, out_channels=cout, stride=s, use_kernel3=kernels3[i][j] == 1,
+                           exp_factor=exp_factors[i][j], se_factor=se_factors[i][j]),
+                       stride_of=lambda i, j: 2 if j == 0 else 1)
+        self.features.add_module("final_block", MnasFinalBlock(in_channels=last, out_channels=final_block_channels[1],
+                                                               mid_channels=final_block_channels[0],
+                                                               use_skip=final_block_use_skip))
+        self._finish(final_block_channels[1], num_classes)
+
+
+_MNASNET_TABLES = {   # mnasnet.py:284-316
+    "b1": dict(init=(32, 16), final=(320, 1280),
+               channels=[[24, 24, 24], [40, 40, 40], [80, 80, 80, 96, 96], [192, 192, 192, 192]],
+               kernels3=[[1, 1, 1], [0, 0, 0], [0, 0, 0, 1, 1], [0, 0, 0, 0]],
+               exp=[[3, 3, 3], [3, 3, 3], [6, 6, 6, 6, 6], [6, 6, 6, 6]],
+               se=[[0, 0, 0], [0, 0, 0], [0, 0, 0, 0, 0], [0, 0, 0, 0]], skips=(False, False)),
+    "a1": dict(init=(32, 16), final=(320, 1280),
+               channels=[[24, 24], [40, 40, 40], [80, 80, 80, 80, 112, 112], [160, 160, 160]],
+               kernels3=[[1, 1], [0, 0, 0], [1, 1, 1, 1, 1, 1], [0, 0, 0]],
+               exp=[[6, 6], [3, 3, 3], [6, 6, 6, 6, 6, 6], [6, 6, 6]],
+               se=[[0, 0], [4, 4, 4], [0, 0, 0, 0, 4, 4], [4, 4, 4]], skips=(False, True)),
+    "small": dict(init=(8, 8), final=(144, 1280),
+                  channels=[[16], [16, 16], [32, 32, 32, 32, 32, 32, 32], [88, 88, 88]],
+                  kernels3=[[1], [1, 1], [0, 0, 0, 0, 1, 1, 1], [0, 0, 0]],
+                  exp=[[3], [6, 6], [6, 6, 6, 6, 6, 6, 6], [6, 6, 6]],
+                  se=[[0], [0, 0], [4, 4, 4, 4, 4, 4, 4], [4, 4, 4]], skips=(True, True)),
+}
+
+
+def get_mnasnet(version, width_scale, model_name=None, pretrained=False, root=None, **kwargs):
+    """Same contract as mnasnet.py:256-346 (the reference only defines width 1.0 variants)."""
+    if version not in _MNASNET_TABLES:
+        raise ValueError("Unsupported MnasNet version {}".format(version))
+    t = _MNASNET_TABLES[version]
+    channels = [list(c) for c in t["channels"]]
+    if width_scale != 1.0:
+        raise NotImplementedError("MnasNet width scales other than 1.0 are not defined by the reference's registry")
+    net = MnasNet(channels=channels, init_block_channels=t["init"], final_block_channels=t["final"],
+                  kernels3=t["kernels3"], exp_factors=t["exp"], se_factors=t["se"],
+                  init_block_use_skip=t["skips"][0], final_block_use_skip=t["skips"][1], **kwargs)
+    _load_pretrained(net, pretrained, model_name, root)
+    return net
+
+
+MNASNET_VARIANTS = {"mnasnet_b1": "b1", "mnasnet_a1": "a1", "mnasnet_small": "small"}
+
+
 # ===== MobileNet v1: the DwsConvBlock vehicle (mobilenet.py) ==========================================================
 class MobileNet(_Classifier):
     def __init__(self, channels, first_stage_stride, dw_use_bn=True, dw_activation=lambda_relu(), in_channels=3,

@@ -570,6 +570,22 @@ def _lower_mnv3_unit(b, m, x, **kw):
     return lower(b, m.conv2, y, residual=x if m.residual else None, post_act=None)
 
 
+@lowers("DwsExpSEResUnit")
+def _lower_dws_exp_se_res(b, m, x, **kw):
+    """DwsExpSEResUnit.forward (mnasnet.py:77-88): [1x1 expand] -> dw -> [SE] -> 1x1 linear (+x)."""
+    y = lower(b, m.exp_conv, x) if m.use_exp_conv else x
+    y = lower(b, m.dw_conv, y)
+    if m.use_se:
+        y = lower(b, m.se, y)
+    return lower(b, m.pw_conv, y, residual=x if m.residual else None, post_act=None)
+
+
+@lowers("MnasInitBlock", "MnasFinalBlock")
+def _lower_mnas_edge(b, m, x, **kw):
+    """MnasInitBlock.forward / MnasFinalBlock.forward (mnasnet.py:121-124, 157-160): conv1 then conv2."""
+    return lower(b, m.conv2, lower(b, m.conv1, x))
+
+
 @lowers("MobileNetV3FinalBlock")
 def _lower_mnv3_final(b, m, x, **kw):
     """MobileNetV3FinalBlock.forward (mobilenetv3.py:127-131)."""
@@ -705,7 +721,7 @@ def _flat(t: TRef) -> TRef:
     return t
 
 
-@lowers("ResNet", "SEResNeXt", "SEResNet", "ResNeXt", "MobileNet", "EfficientNet")
+@lowers("ResNet", "SEResNeXt", "SEResNet", "ResNeXt", "MobileNet", "EfficientNet", "MnasNet")
 def _lower_classifier(b, m, x, **kw):
     """features -> view(N,-1) -> [Dropout ->] Linear (resnet.py:333-337, seresnext.py:136-140, efficientnet.py:354-358)."""
     return _flat(lower(b, m.output, lower(b, m.features, x)))

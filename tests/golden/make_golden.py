@@ -46,6 +46,8 @@ NETS = [
     ("seresnet50_bs2", "seresnet50", {}, (2, 3, 224, 224), 0, 1),
     ("fcn8sd_resnetd50b_voc_bs1", "fcn8sd_resnetd50b_voc", {}, (1, 3, 480, 480), 0, 16),
     ("pspnet_resnetd50b_voc_bs1", "pspnet_resnetd50b_voc", {}, (1, 3, 480, 480), 0, 16),
+    ("mnasnet_a1_bs2", "mnasnet_a1", {}, (2, 3, 224, 224), 0, 1),
+    ("mnasnet_small_bs2", "mnasnet_small", {}, (2, 3, 224, 224), 0, 1),
 ]
 
 # block-level cases: (stem, ctor, input shape)
