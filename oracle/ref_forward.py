@@ -300,6 +300,15 @@ def dws_exp_se_res_unit(m, x):
     return x + identity if m.residual else x
 
 
+def fbnet_unit(m, x):
+    """FBNetUnit.forward (fbnet.py:77-87) == SPNASUnit.forward (spnasnet.py:72-82)."""
+    identity = x
+    if m.use_exp_conv:
+        x = conv_block(m.exp_conv, x)
+    x = conv_block(m.conv2, conv_block(m.conv1, x))
+    return x + identity if m.residual else x
+
+
 def mnas_edge_block(m, x):
     """MnasInitBlock.forward / MnasFinalBlock.forward (mnasnet.py:121-124, 157-160)."""
     return oracle_forward(m.conv2, oracle_forward(m.conv1, x))
@@ -385,7 +394,8 @@ _BY_NAME = {
     "EffiInitBlock": effi_init_block, "EffiDwsConvUnit": effi_dws_conv_unit, "EffiInvResUnit": effi_inv_res_unit,
     "EfficientNet": efficientnet,
     "DwsExpSEResUnit": dws_exp_se_res_unit, "MnasInitBlock": mnas_edge_block, "MnasFinalBlock": mnas_edge_block,
-    "MnasNet": classifier,
+    "MnasNet": classifier, "FBNetUnit": fbnet_unit, "FBNetInitBlock": mnas_edge_block, "FBNet": classifier,
+    "SPNASUnit": fbnet_unit, "SPNASInitBlock": mnas_edge_block, "SPNASFinalBlock": mnas_edge_block, "SPNASNet": classifier,
     "MobileNetV3Unit": mobilenetv3_unit, "MobileNetV3FinalBlock": mobilenetv3_final_block,
     "MobileNetV3Classifier": mobilenetv3_classifier, "MobileNetV3": mobilenetv3,
     "Concurrent": concurrent, "MultiOutputSequential": multi_output_sequential,

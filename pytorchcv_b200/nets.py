@@ -639,6 +639,144 @@ def get_mnasnet(version, width_scale, model_name=None, pretrained=False, root=No
 MNASNET_VARIANTS = {"mnasnet_b1": "b1", "mnasnet_a1": "a1", "mnasnet_small": "small"}
 
 
+# ===== FBNet (fbnet.py), SURVEY 8(f) rank 1 ==========================================================================
+class FBNetUnit(B200Module):
+    """1x1 expand -> dw 3x3 | 5x5 -> 1x1 linear (+x) (fbnet.py:17-87)."""
+
+    def __init__(self, in_channels, out_channels, stride, use_kernel3, exp_factor, normalization,
+                 activation=lambda_relu()):
+        super().__init__()
+        assert exp_factor >= 1
+        self.residual = (in_channels == out_channels) and (stride == 1)
+        self.use_exp_conv = True
+        mid = exp_factor * in_channels
+        self.exp_conv = conv1x1_block(in_channels=in_channels, out_channels=mid, normalization=normalization,
+                                      activation=activation)
+        dw = dwconv3x3_block if use_kernel3 else dwconv5x5_block
+        self.conv1 = dw(in_channels=mid, out_channels=mid, stride=stride, normalization=normalization,
+                        activation=activation)
+        self.conv2 = conv1x1_block(in_channels=mid, out_channels=out_channels, normalization=normalization,
+                                   activation=None)
+
+
+class FBNetInitBlock(B200Module):
+    """conv3x3/2 -> FBNetUnit(exp 1) (fbnet.py:90-124)."""
+
+    def __init__(self, in_channels, out_channels, normalization):
+        super().__init__()
+        self.conv1 = conv3x3_block(in_channels=in_channels, out_channels=out_channels, stride=2,
+                                   normalization=normalization)
+        self.conv2 = FBNetUnit(in_channels=out_channels, out_channels=out_channels, stride=1, use_kernel3=True,
+                               exp_factor=1, normalization=normalization)
+
+
+class FBNet(_Classifier):
+    """fbnet.py:127-215."""
+
+    def __init__(self, channels, init_block_channels, final_block_channels, kernels3, exp_factors, bn_eps=1e-5,
+                 in_channels=3, in_size=(224, 224), num_classes=1000):
+        super().__init__()
+        self.in_size, self.num_classes = in_size, num_classes
+        norm = lambda_batchnorm2d(eps=bn_eps)
+        self.features = nn.Sequential()
+        self.features.add_module("init_block", FBNetInitBlock(in_channels=in_channels,
+                                                              out_channels=init_block_channels, normalization=norm))
+        last = _stages(self.features, channels, init_block_channels,
+                       lambda i, j, cin, cout, s: FBNetUnit(in_channels=cin, out_channels=cout, stride=s,
+                                                            use_kernel3=kernels3[i][j] == 1,
+                                                            exp_factor=exp_factors[i][j], normalization=norm),
+                       stride_of=lambda i, j: 2 if j == 0 else 1)
+        self.features.add_module("final_block", conv1x1_block(in_channels=last, out_channels=final_block_channels,
+                                                              normalization=norm))
+        self._finish(final_block_channels, num_classes)
+
+
+def get_fbnet(version, bn_eps=1e-5, model_name=None, pretrained=False, root=None, **kwargs):
+    """Same contract as fbnet.py:218-270."""
+    if version != "c":
+        raise ValueError("Unsupported FBNet version {}".format(version))
+    net = FBNet(channels=[[24, 24, 24], [32, 32, 32, 32], [64, 64, 64, 64, 112, 112, 112, 112],
+                          [184, 184, 184, 184, 352]],
+                init_block_channels=16, final_block_channels=1984,
+                kernels3=[[1, 1, 1], [0, 0, 0, 1], [0, 0, 0, 0, 0, 0, 0, 0], [0, 0, 0, 0, 1]],
+                exp_factors=[[6, 1, 1], [6, 3, 6, 6], [6, 3, 6, 6, 6, 6, 6, 3], [6, 6, 6, 6, 6]], bn_eps=bn_eps, **kwargs)
+    _load_pretrained(net, pretrained, model_name, root)
+    return net
+
+
+FBNET_VARIANTS = {"fbnet_cb": dict(version="c", bn_eps=1e-3)}
+
+
+# ===== Single-Path NASNet (spnasnet.py), SURVEY 8(f) rank 1 ============================================================
+class SPNASUnit(B200Module):
+    """[1x1 expand] -> dw 3x3 | 5x5 -> 1x1 linear (+x) (spnasnet.py:16-82)."""
+
+    def __init__(self, in_channels, out_channels, stride, use_kernel3, exp_factor, use_skip=True,
+                 activation=lambda_relu()):
+        super().__init__()
+        assert exp_factor >= 1
+        self.residual = (in_channels == out_channels) and (stride == 1) and use_skip
+        self.use_exp_conv = exp_factor > 1
+        mid = exp_factor * in_channels
+        if self.use_exp_conv:
+            self.exp_conv = conv1x1_block(in_channels=in_channels, out_channels=mid, activation=activation)
+        dw = dwconv3x3_block if use_kernel3 else dwconv5x5_block
+        self.conv1 = dw(in_channels=mid, out_channels=mid, stride=stride, activation=activation)
+        self.conv2 = conv1x1_block(in_channels=mid, out_channels=out_channels, activation=None)
+
+
+class SPNASInitBlock(B200Module):
+    """conv3x3/2 -> SPNASUnit(exp 1, no skip) (spnasnet.py:85-118)."""
+
+    def __init__(self, in_channels, out_channels, mid_channels):
+        super().__init__()
+        self.conv1 = conv3x3_block(in_channels=in_channels, out_channels=mid_channels, stride=2)
+        self.conv2 = SPNASUnit(in_channels=mid_channels, out_channels=out_channels, stride=1, use_kernel3=True,
+                               exp_factor=1, use_skip=False)
+
+
+class SPNASFinalBlock(B200Module):
+    """SPNASUnit(exp 6, no skip) -> conv1x1 (spnasnet.py:121-153)."""
+
+    def __init__(self, in_channels, out_channels, mid_channels):
+        super().__init__()
+        self.conv1 = SPNASUnit(in_channels=in_channels, out_channels=mid_channels, stride=1, use_kernel3=True,
+                               exp_factor=6, use_skip=False)
+        self.conv2 = conv1x1_block(in_channels=mid_channels, out_channels=out_channels)
+
+
+class SPNASNet(_Classifier):
+    """spnasnet.py:156-240: the last stage takes its stride in the middle."""
+
+    def __init__(self, channels, init_block_channels, final_block_channels, kernels3, exp_factors, in_channels=3,
+                 in_size=(224, 224), num_classes=1000):
+        super().__init__()
+        self.in_size, self.num_classes = in_size, num_classes
+        self.features = nn.Sequential()
+        self.features.add_module("init_block", SPNASInitBlock(in_channels=in_channels,
+                                                              out_channels=init_block_channels[1],
+                                                              mid_channels=init_block_channels[0]))
+        last = _stages(self.features, channels, init_block_channels[1],
+                       lambda i, j, cin, cout, s: SPNASUnit(in_channels=cin, out_channels=cout, stride=s,
+                                                            use_kernel3=kernels3[i][j] == 1,
+                                                            exp_factor=exp_factors[i][j]),
+                       stride_of=lambda i, j: 2 if ((j == 0 and i != 3) or (j == len(channels[i]) // 2 and i == 3)) else 1)
+        self.features.add_module("final_block", SPNASFinalBlock(in_channels=last,
+                                                                out_channels=final_block_channels[1],
+                                                                mid_channels=final_block_channels[0]))
+        self._finish(final_block_channels[1], num_classes)
+
+
+def get_spnasnet(model_name=None, pretrained=False, root=None, **kwargs):
+    """Same contract as spnasnet.py:243-290."""
+    net = SPNASNet(channels=[[24, 24, 24], [40, 40, 40, 40], [80, 80, 80, 80], [96, 96, 96, 96, 192, 192, 192, 192]],
+                   init_block_channels=(32, 16), final_block_channels=(320, 1280),
+                   kernels3=[[1, 1, 1], [0, 1, 1, 1], [0, 1, 1, 1], [0, 0, 0, 0, 0, 0, 0, 0]],
+                   exp_factors=[[3, 3, 3], [6, 3, 3, 3], [6, 3, 3, 3], [6, 3, 3, 3, 6, 6, 6, 6]], **kwargs)
+    _load_pretrained(net, pretrained, model_name, root)
+    return net
+
+
 # ===== MobileNet v1: the DwsConvBlock vehicle (mobilenet.py) ==========================================================
 class MobileNet(_Classifier):
     def __init__(self, channels, first_stage_stride, dw_use_bn=True, dw_activation=lambda_relu(), in_channels=3,

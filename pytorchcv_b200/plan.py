@@ -580,7 +580,15 @@ def _lower_dws_exp_se_res(b, m, x, **kw):
     return lower(b, m.pw_conv, y, residual=x if m.residual else None, post_act=None)
 
 
-@lowers("MnasInitBlock", "MnasFinalBlock")
+@lowers("FBNetUnit", "SPNASUnit")
+def _lower_fbnet_unit(b, m, x, **kw):
+    """FBNetUnit.forward (fbnet.py:77-87) == SPNASUnit.forward (spnasnet.py:72-82): [1x1 expand] -> dw -> 1x1 (+x)."""
+    y = lower(b, m.exp_conv, x) if m.use_exp_conv else x
+    y = lower(b, m.conv1, y)
+    return lower(b, m.conv2, y, residual=x if m.residual else None, post_act=None)
+
+
+@lowers("MnasInitBlock", "MnasFinalBlock", "FBNetInitBlock", "SPNASInitBlock", "SPNASFinalBlock")
 def _lower_mnas_edge(b, m, x, **kw):
     """MnasInitBlock.forward / MnasFinalBlock.forward (mnasnet.py:121-124, 157-160): conv1 then conv2."""
     return lower(b, m.conv2, lower(b, m.conv1, x))
@@ -721,7 +729,7 @@ def _flat(t: TRef) -> TRef:
     return t
 
 
-@lowers("ResNet", "SEResNeXt", "SEResNet", "ResNeXt", "MobileNet", "EfficientNet", "MnasNet")
+@lowers("ResNet", "SEResNeXt", "SEResNet", "ResNeXt", "MobileNet", "EfficientNet", "MnasNet", "FBNet", "SPNASNet")
 def _lower_classifier(b, m, x, **kw):
     """features -> view(N,-1) -> [Dropout ->] Linear (resnet.py:333-337, seresnext.py:136-140, efficientnet.py:354-358)."""
     return _flat(lower(b, m.output, lower(b, m.features, x)))

@@ -48,6 +48,8 @@ NETS = [
     ("pspnet_resnetd50b_voc_bs1", "pspnet_resnetd50b_voc", {}, (1, 3, 480, 480), 0, 16),
     ("mnasnet_a1_bs2", "mnasnet_a1", {}, (2, 3, 224, 224), 0, 1),
     ("mnasnet_small_bs2", "mnasnet_small", {}, (2, 3, 224, 224), 0, 1),
+    ("fbnet_cb_bs2", "fbnet_cb", {}, (2, 3, 224, 224), 0, 1),
+    ("spnasnet_bs2", "spnasnet", {}, (2, 3, 224, 224), 0, 1),
 ]
 
 # block-level cases: (stem, ctor, input shape)
