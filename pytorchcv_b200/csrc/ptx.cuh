@@ -6,6 +6,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include "../../include/pcv_b200.h"   // pcv_act codes for fast_act_n
+
 namespace pcv {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -346,25 +348,25 @@ __device__ __forceinline__ float fast_hsigmoid(float x) { return fminf(fmaxf(x +
 __device__ __forceinline__ float fast_hswish(float x) { return x * fast_hsigmoid(x); }
 // One activation over N register values with the switch OUTSIDE the element loop (an inlined per-element switch is what
 // once blew the epilogue up to 100 KB of SASS).  Codes are pcv_act (include/pcv_b200.h): 3 sigmoid, 4 swish, 5 h-swish,
-// 6 h-sigmoid; the clamp family (0..2) is handled by the callers' packed paths.
+// 6 h-sigmoid; the clamp family (0..2) is normally handled by the callers' packed paths.
 template <int N>
 __device__ __forceinline__ void fast_act_n(float (&v)[N], int act) {
-  if (act == 4) {
+  if (act == PCV_ACT_SWISH) {
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = fast_swish(v[i]);
-  } else if (act == 5) {
+  } else if (act == PCV_ACT_HSWISH) {
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = fast_hswish(v[i]);
-  } else if (act == 3) {
+  } else if (act == PCV_ACT_SIGMOID) {
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = fast_sigmoid(v[i]);
-  } else if (act == 6) {
+  } else if (act == PCV_ACT_HSIGMOID) {
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = fast_hsigmoid(v[i]);
-  } else if (act == 1) {
+  } else if (act == PCV_ACT_RELU) {
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = fmaxf(v[i], 0.f);
-  } else if (act == 2) {
+  } else if (act == PCV_ACT_RELU6) {
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = fminf(fmaxf(v[i], 0.f), 6.f);
   }
