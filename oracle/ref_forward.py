@@ -384,7 +384,8 @@ def _leaf(m, x):
 
 _BY_NAME = {
     "ConvBlock": conv_block, "DwsConvBlock": dws_conv_block, "SEBlock": se_block,
-    "ResBlock": res_body, "ResBottleneck": res_body, "ResNeXtBottleneck": res_body,
+    "ResBlock": res_body, "ResBottleneck": res_body, "ResNeXtBottleneck": res_body, "SENetBottleneck": res_body,
+    "SENetUnit": se_resnext_unit, "SENet": efficientnet,
     "ResUnit": res_unit, "ResNeXtUnit": res_unit, "SEResNeXtUnit": se_resnext_unit, "SEResUnit": se_resnext_unit,
     "SEResNet": classifier, "FCN8sd": fcn8sd, "PSPNet": fcn8sd, "PyramidPoolingBranch": pyramid_pooling_branch,
     "PyramidPooling": pyramid_pooling, "Identity": lambda m, x: x,

@@ -50,6 +50,8 @@ for _name, _ver in nets.MNASNET_VARIANTS.items():
         _name, _ver))
 for _name, (_b, _k) in nets.PSPNET_VARIANTS.items():
     _register(_name, nets._pspnet_ctor(_name, _b, _k))
+for _name, _blocks in nets.SENET_VARIANTS.items():
+    _register(_name, (lambda n, b: lambda **kw: nets.get_senet(blocks=b, model_name=n, **kw))(_name, _blocks))
 for _name, _fixed in nets.SERESNET_VARIANTS.items():
     _register(_name, (lambda n, f: lambda **kw: nets.get_seresnet(model_name=n, **f, **kw))(_name, _fixed))
 

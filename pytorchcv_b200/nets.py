@@ -996,6 +996,75 @@ class SEInitBlock(B200Module):
         self.pool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
 
 
+# ----- SENet-16 ... SENet-154 (senet.py:17-124, 167-330), SURVEY 8(f) rank 3 -----------------------------------------
+class SENetBottleneck(B200Module):
+    """1x1 -> grouped 3x3 (half-width in, `cardinality` groups) -> 1x1 (senet.py:17-66)."""
+
+    def __init__(self, in_channels, out_channels, stride, cardinality, bottleneck_width):
+        super().__init__()
+        mid = out_channels // 4
+        d = int(math.floor(mid * (bottleneck_width / 64.0)))
+        group_width = cardinality * d
+        self.conv1 = conv1x1_block(in_channels=in_channels, out_channels=group_width // 2)
+        self.conv2 = conv3x3_block(in_channels=group_width // 2, out_channels=group_width, stride=stride,
+                                   groups=cardinality)
+        self.conv3 = conv1x1_block(in_channels=group_width, out_channels=out_channels, activation=None)
+
+
+class SENetUnit(B200Module):
+    """relu(se(body(x)) + identity); stages 2-4 project the identity with a 3x3 ConvBlock (senet.py:69-124)."""
+
+    def __init__(self, in_channels, out_channels, stride, cardinality, bottleneck_width, identity_conv3x3):
+        super().__init__()
+        self.resize_identity = (in_channels != out_channels) or (stride != 1)
+        self.body = SENetBottleneck(in_channels=in_channels, out_channels=out_channels, stride=stride,
+                                    cardinality=cardinality, bottleneck_width=bottleneck_width)
+        self.se = SEBlock(channels=out_channels)
+        if self.resize_identity:
+            block = conv3x3_block if identity_conv3x3 else conv1x1_block
+            self.identity_conv = block(in_channels=in_channels, out_channels=out_channels, stride=stride,
+                                       activation=None)
+        self.activ = nn.ReLU(inplace=True)
+
+
+class SENet(B200Module):
+    """senet.py:167-245."""
+
+    def __init__(self, channels, init_block_channels, cardinality, bottleneck_width, in_channels=3, in_size=(224, 224),
+                 num_classes=1000):
+        super().__init__()
+        self.in_size, self.num_classes = in_size, num_classes
+        self.features = nn.Sequential()
+        self.features.add_module("init_block", SEInitBlock(in_channels=in_channels, out_channels=init_block_channels))
+        last = _stages(self.features, channels, init_block_channels,
+                       lambda i, j, cin, cout, s: SENetUnit(in_channels=cin, out_channels=cout, stride=s,
+                                                            cardinality=cardinality, bottleneck_width=bottleneck_width,
+                                                            identity_conv3x3=(i != 0)))
+        self.features.add_module("final_pool", nn.AvgPool2d(kernel_size=7, stride=1))
+        self.output = nn.Sequential()
+        self.output.add_module("dropout", nn.Dropout(p=0.2))
+        self.output.add_module("fc", nn.Linear(in_features=last, out_features=num_classes))
+        _kaiming_init(self)
+
+
+_SENET_LAYERS = {16: ([1, 1, 1, 1], 32), 28: ([2, 2, 2, 2], 32), 40: ([3, 3, 3, 3], 32), 52: ([3, 4, 6, 3], 32),
+                 103: ([3, 4, 23, 3], 32), 154: ([3, 8, 36, 3], 64)}
+
+
+def get_senet(blocks, model_name=None, pretrained=False, root=None, **kwargs):
+    """Same contract as senet.py:248-310."""
+    if blocks not in _SENET_LAYERS:
+        raise ValueError("Unsupported SENet with number of blocks: {}".format(blocks))
+    layers, cardinality = _SENET_LAYERS[blocks]
+    net = SENet(channels=[[c] * n for c, n in zip([256, 512, 1024, 2048], layers)], init_block_channels=128,
+                cardinality=cardinality, bottleneck_width=4, **kwargs)
+    _load_pretrained(net, pretrained, model_name, root)
+    return net
+
+
+SENET_VARIANTS = {f"senet{b}": b for b in _SENET_LAYERS}
+
+
 class ResNetD(B200Module):
     """Dilated ResNet: stride only in stages 1-2, dilation 2/4 in stages 3-4 (resnetd.py:59-81)."""
 

@@ -486,7 +486,7 @@ def _lower_se(b, m, x, identity=None, post_act=ACT_NONE, **kw):
     return b.se_scale(x, gate, identity, post_act)
 
 
-@lowers("ResBlock", "ResBottleneck", "ResNeXtBottleneck")
+@lowers("ResBlock", "ResBottleneck", "ResNeXtBottleneck", "SENetBottleneck")
 def _lower_resbody(b, m, x, residual=None, post_act=None, **kw):
     """conv1 -> conv2 [-> conv3] (resnet.py:63-66,136-140; resnext.py:56-59); the last conv takes the fusion."""
     convs = [m.conv1, m.conv2] + ([m.conv3] if hasattr(m, "conv3") else [])
@@ -502,7 +502,7 @@ def _lower_resunit(b, m, x, **kw):
     return lower(b, m.body, x, residual=identity, post_act=act_code(m.activ))
 
 
-@lowers("SEResNeXtUnit", "SEResUnit")
+@lowers("SEResNeXtUnit", "SEResUnit", "SENetUnit")
 def _lower_seresnext_unit(b, m, x, **kw):
     """SEResNeXtUnit.forward (seresnext.py:57-66): relu(se(body(x)) + identity)."""
     identity = lower(b, m.identity_conv, x) if m.resize_identity else x
@@ -729,7 +729,7 @@ def _flat(t: TRef) -> TRef:
     return t
 
 
-@lowers("ResNet", "SEResNeXt", "SEResNet", "ResNeXt", "MobileNet", "EfficientNet", "MnasNet", "FBNet", "SPNASNet")
+@lowers("ResNet", "SEResNeXt", "SEResNet", "ResNeXt", "MobileNet", "EfficientNet", "MnasNet", "FBNet", "SPNASNet", "SENet")
 def _lower_classifier(b, m, x, **kw):
     """features -> view(N,-1) -> [Dropout ->] Linear (resnet.py:333-337, seresnext.py:136-140, efficientnet.py:354-358)."""
     return _flat(lower(b, m.output, lower(b, m.features, x)))

@@ -39,7 +39,7 @@ def test_fp32_tier_matches_oracle_and_golden(stem, name, shape, sub):
     gold = np.load(os.path.join(GOLDEN, stem + ".npz"))
     # SE-ResNeXt with randomised BN statistics is ill-conditioned: the oracle differs from ITSELF by ~1e-3 between
     # fp32 and fp64 (saturating SE gates) — bound the error by max(1e-4, 3x that floor).
-    gated = any(k in name for k in ("seresne", "efficientnet", "mobilenetv3", "mnasnet"))   # SE gates: see above
+    gated = any(k in name for k in ("seresne", "senet", "efficientnet", "mobilenetv3", "mnasnet"))   # SE gates: see above
     tol = 1e-4 if not gated else max(1e-4, 3.0 * _oracle_noise(net, x, want))
     for i, (g, w) in enumerate(zip(got, want)):
         g = g.float().cpu()
