@@ -117,7 +117,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int wo = rem - ho * p.Wo;
         const int w0 = wo * p.stride - p.pad;
         const int h0 = ho * p.stride - p.pad;
-        const int c_base = p.grouped ? n_tile * BN : 0;
+        const int c_base = p.grouped ? n_tile * p.g_in_span : 0;
         int tap = 0, cb = 0, fr = 0, fs = 0;
         for (int kb = 0; kb < p.num_kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -364,7 +364,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 __global__ void igemm_pack_kernel(const float* __restrict__ w, const float* __restrict__ conv_bias,
                                   const float* __restrict__ g, const float* __restrict__ b,
                                   const float* __restrict__ mean, const float* __restrict__ var, float eps,
-                                  int Cout, int Cin, int groups, int taps, int cblocks, int grouped_bn,
+                                  int Cout, int Cin, int groups, int taps, int cblocks, int grouped_bn, int in_span,
                                   __nv_bfloat16* __restrict__ wp, float* __restrict__ bias_out, int bias_len) {
   const int kpad = taps * cblocks * BLOCK_K;
   const size_t total = static_cast<size_t>(Cout) * kpad;
@@ -381,11 +381,13 @@ __global__ void igemm_pack_kernel(const float* __restrict__ w, const float* __re
     if (groups == 1) {
       if (cc < Cin) val = w[(static_cast<size_t>(o) * Cin + cc) * taps + tap];
     } else {
-      // block-diagonal: the A window of this output channel's N tile starts at input channel (o / bn) * bn
-      const int ci_abs = (o / grouped_bn) * grouped_bn + cc;
+      // block-diagonal: the A window of this output channel's N tile starts at input channel (o / bn) * in_span, where
+      // in_span = bn * cin_g / cout_g input channels feed the tile's bn / cout_g groups (== bn when Cin/g == Cout/g;
+      // SENet's half-width grouped 3x3, senet.py:52-56, has in_span = 32)
+      const int ci_abs = (o / grouped_bn) * in_span + cc;
       const int grp = o / cout_g;
       const int ci = ci_abs - grp * cin_g;
-      if (ci >= 0 && ci < cin_g && cc < grouped_bn) val = w[(static_cast<size_t>(o) * cin_g + ci) * taps + tap];
+      if (ci >= 0 && ci < cin_g && cc < in_span) val = w[(static_cast<size_t>(o) * cin_g + ci) * taps + tap];
     }
     wp[idx] = __float2bfloat16(val * scale);
   }
@@ -429,8 +431,11 @@ int igemm_supported(const pcv_conv_desc& d, std::string* why) {
   if (lo < -128 || up_w < -128 || up_h < -128 || up_w > 127 || up_h > 127) return no("im2col corner out of range");
   if (d.groups > 1) {
     const int cg_in = d.Cin / d.groups, cg_out = d.Cout / d.groups;
-    if (cg_in != cg_out) return no("grouped conv needs Cin/g == Cout/g");
-    if (64 % cg_out != 0 || d.Cout % 64 != 0) return no("grouped conv needs 64 % (C/g) == 0 and Cout % 64 == 0");
+    if (64 % cg_out != 0 || d.Cout % 64 != 0) return no("grouped conv needs 64 % (Cout/g) == 0 and Cout % 64 == 0");
+    // a 64-wide output tile covers 64 / cg_out groups = in_span input channels, read as (part of) one 64-channel k-block
+    const int in_span = 64 * cg_in / cg_out;
+    if (cg_in > cg_out || in_span * cg_out != 64 * cg_in || in_span % 8 != 0)
+      return no("grouped conv needs Cin/g <= Cout/g with 64*(Cin/g)/(Cout/g) a multiple of 8");
   }
   return 1;
 }
@@ -450,6 +455,7 @@ int igemm_pack(const pcv_conv_desc& d, const float* w, const float* conv_bias, c
   const size_t total = static_cast<size_t>(d.Cout) * taps * cblocks * BLOCK_K;
   const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 4096));
   igemm_pack_kernel<<<blocks, 256, 0, s>>>(w, conv_bias, g, b, m, v, eps, d.Cout, d.Cin, d.groups, taps, cblocks, 64,
+                                           d.groups > 1 ? 64 * (d.Cin / d.groups) / (d.Cout / d.groups) : 64,
                                            reinterpret_cast<__nv_bfloat16*>(w_packed), bias_out,
                                            round_up(d.Cout, 256));
   g_launches++;
@@ -585,6 +591,7 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   p.act_hi = d.act == PCV_ACT_RELU6 ? 6.f : INFINITY;
   p.has_res = res != nullptr;
   p.grouped = grouped;
+  p.g_in_span = grouped ? 64 * (d.Cin / d.groups) / (d.Cout / d.groups) : 0;
   p.stages = p.nstg = 0;
   p.ksub = 1;
   {

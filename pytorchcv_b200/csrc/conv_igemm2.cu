@@ -139,7 +139,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const int w0 = wo * p.stride - p.pad;
         const int h0 = ho * p.stride - p.pad;
         const int b_row = n_tile * TW + static_cast<int>(rank) * L::HALF_N;
-        const int c_base = p.grouped ? n_tile * TW : 0;
+        const int c_base = p.grouped ? n_tile * p.g_in_span : 0;
         int cb = 0, fr = 0, fs = 0;
         for (int kb = 0; kb < p.num_kblocks; kb += KSUB) {
           const int nsub = min(KSUB, p.num_kblocks - kb);

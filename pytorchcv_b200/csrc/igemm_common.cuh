@@ -26,7 +26,8 @@ struct IgemmParams {
   float act_lo, act_hi;        // ReLU / ReLU6 / none as a clamp; other activations take the slow path
   int a_mode;                 // 0: 2-D tiled [Cin, M]; 1: im2col 4-D
   int out_mode;               // 0: TMA bf16 store; 1: direct bf16; 2: direct fp32
-  int grouped;                // 1: A channel window = n_tile*BLOCK_N (block-diagonal weights)
+  int grouped;                // 1: A channel window = n_tile*g_in_span (block-diagonal weights)
+  int g_in_span;              // grouped: input channels read by one 64-wide output tile = 64 * (Cin/g) / (Cout/g) <= 64
   int dbg;                    // PCV_IGEMM_DBG: bit0 skip operand TMA, bit1 skip MMA issue (throughput experiments)
   int stages, ksub, nstg;     // CTA-pair kernel: ring depth / 64-K sub-blocks per stage / staging slots (per layer)
   int nsubs;                  // CTA-pair kernel: 64-column sub-tiles per tile (tile width = nsubs*64 <= BN), per layer

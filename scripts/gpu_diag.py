@@ -86,6 +86,11 @@ CASES = [
     ("gemm_1x1_hswish_res_256",   2, 14, 14, 128, 256, 1, 1, 0, 1, 1, 5, 1, 0, "bf16"),
     ("conv3x3_s2_swish_stem8",    2, 64, 64,   8,  32, 3, 2, 1, 1, 1, 4, 0, 0, "bf16"),
     ("gemm_1x1_sigmoid_64",       2, 14, 14,  64,  64, 1, 1, 0, 1, 1, 3, 0, 0, "bf16"),
+    # SENet's half-width grouped 3x3 (senet.py:52-56): Cin/g != Cout/g on the block-diagonal tcgen05 route
+    ("g3x3_64_128_g32_senet",     2, 28, 28,  64, 128, 3, 1, 1, 1, 32, 1, 0, 0, "bf16"),
+    ("g3x3_s2_128_256_g32",       3, 28, 28, 128, 256, 3, 2, 1, 1, 32, 1, 0, 0, "bf16"),
+    ("g3x3_256_512_g64_14",       2, 14, 14, 256, 512, 3, 1, 1, 1, 64, 1, 0, 0, "bf16"),
+    ("g1x1_32_64_g32",            2, 14, 14,  32,  64, 1, 1, 0, 1, 32, 0, 0, 0, "bf16"),
 ]
 
 
