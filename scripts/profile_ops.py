@@ -46,6 +46,10 @@ CONVS = {
         ("c1_16_96_112", 256, 112, 16, 96, 1, 1, 1, 1, 0, 2),
         ("c1_144_24_56_res", 256, 56, 144, 24, 1, 1, 1, 1, 1, 0),
     ],
+    "deeplab": [   # DeepLabv3 bs16 480x480: ASPP dilated 3x3 (the dominant kernel), backbone dilated 3x3
+        ("c3_d12_2048_256_60", 16, 60, 2048, 256, 3, 1, 12, 1, 0, 1),
+        ("c3_d2_256_256_60", 16, 60, 256, 256, 3, 1, 2, 1, 0, 1),
+    ],
     "effi": [   # EfficientNet-b0 / MobileNetV3: 5x5 depthwise, swish epilogues (act 4)
         ("dw5_240_28_swish", 256, 28, 240, 240, 5, 1, 1, 240, 0, 4),
         ("dw5s2_144_56_swish", 256, 56, 144, 144, 5, 2, 1, 144, 0, 4),
@@ -107,14 +111,23 @@ def main():
             del x, w, packed, r, out
     if a.set in ("all", "pool") or "pool" in sets:
         for (name, N, H, C) in (("maxpool_64_112", 256, 112, 64), ("maxpool_128_240", 16, 240, 128)):
-            if a.only and a.only not in name:
+            if a.only and not any(o in name for o in a.only.split(",")):
                 continue
             x = torch.randn(N, H, H, C, generator=g).to(dev).to(torch.bfloat16)
             ms = time_op(lambda: P.maxpool2d(x, 3, 2, 1), a.reps, a.warm, buf)
             by = 2.0 * N * C * (H * H + (H // 2) ** 2)
             print(f"{name:22s} {ms:8.4f} ms  {0.0:8.1f} TFLOP/s  {by / ms / 1e6:8.1f} GB/s", flush=True)
+        for (name, N, HW, C) in (("sescale_256_3136", 256, 56, 256),):
+            if a.only and not any(o in name for o in a.only.split(",")):
+                continue
+            x = torch.randn(N, HW, HW, C, generator=g).to(dev).to(torch.bfloat16)
+            idn = torch.randn(N, HW, HW, C, generator=g).to(dev).to(torch.bfloat16)
+            gate = torch.rand(N, C, generator=g).to(dev)
+            ms = time_op(lambda: P.se_scale_add_act(x, gate, idn, _lib.ACT_RELU), a.reps, a.warm, buf)
+            by = 2.0 * N * C * HW * HW * 3
+            print(f"{name:22s} {ms:8.4f} ms  {0.0:8.1f} TFLOP/s  {by / ms / 1e6:8.1f} GB/s", flush=True)
         for (name, N, HW, C) in (("gavg_2048_49", 256, 7, 2048), ("gavg_256_3136", 256, 56, 256)):
-            if a.only and a.only not in name:
+            if a.only and not any(o in name for o in a.only.split(",")):
                 continue
             x = torch.randn(N, HW, HW, C, generator=g).to(dev).to(torch.bfloat16)
             ms = time_op(lambda: P.global_avgpool(x, out_dtype=torch.float32), a.reps, a.warm, buf)
