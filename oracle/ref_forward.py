@@ -309,6 +309,15 @@ def fbnet_unit(m, x):
     return x + identity if m.residual else x
 
 
+def proxyless_unit(m, x):
+    """ProxylessUnit.forward (proxylessnas.py:114-123) with ProxylessBlock.forward (proxylessnas.py:64-70)."""
+    if not m.residual:
+        return x
+    y = conv_block(m.body.bc_conv, x) if m.body.use_bc else x
+    y = conv_block(m.body.pw_conv, conv_block(m.body.dw_conv, y))
+    return x + y if m.shortcut else y
+
+
 def mnas_edge_block(m, x):
     """MnasInitBlock.forward / MnasFinalBlock.forward (mnasnet.py:121-124, 157-160)."""
     return oracle_forward(m.conv2, oracle_forward(m.conv1, x))
@@ -395,7 +404,7 @@ _BY_NAME = {
     "EffiInitBlock": effi_init_block, "EffiDwsConvUnit": effi_dws_conv_unit, "EffiInvResUnit": effi_inv_res_unit,
     "EfficientNet": efficientnet,
     "DwsExpSEResUnit": dws_exp_se_res_unit, "MnasInitBlock": mnas_edge_block, "MnasFinalBlock": mnas_edge_block,
-    "MnasNet": classifier, "FBNetUnit": fbnet_unit, "FBNetInitBlock": mnas_edge_block, "FBNet": classifier,
+    "MnasNet": classifier, "FBNetUnit": fbnet_unit, "FBNetInitBlock": mnas_edge_block, "FBNet": classifier, "ProxylessUnit": proxyless_unit, "ProxylessNAS": classifier,
     "SPNASUnit": fbnet_unit, "SPNASInitBlock": mnas_edge_block, "SPNASFinalBlock": mnas_edge_block, "SPNASNet": classifier,
     "MobileNetV3Unit": mobilenetv3_unit, "MobileNetV3FinalBlock": mobilenetv3_final_block,
     "MobileNetV3Classifier": mobilenetv3_classifier, "MobileNetV3": mobilenetv3,

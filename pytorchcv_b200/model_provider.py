@@ -42,6 +42,8 @@ for _name, (_b, _k) in nets.DEEPLABV3_VARIANTS.items():
     _register(_name, nets._deeplab_ctor(_name, _b, _k))
 for _name, (_b, _k) in nets.FCN8SD_VARIANTS.items():
     _register(_name, nets._fcn8sd_ctor(_name, _b, _k))
+for _name, _ver in nets.PROXYLESSNAS_VARIANTS.items():
+    _register(_name, (lambda n, v: lambda **kw: nets.get_proxylessnas(version=v, model_name=n, **kw))(_name, _ver))
 _register("spnasnet", lambda **kw: nets.get_spnasnet(model_name="spnasnet", **kw))
 for _name, _fixed in nets.FBNET_VARIANTS.items():
     _register(_name, (lambda n, f: lambda **kw: nets.get_fbnet(model_name=n, **f, **kw))(_name, _fixed))

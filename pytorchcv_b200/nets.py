@@ -15,7 +15,7 @@ import math
 
 import torch.nn as nn
 
-from .blocks import (B200Module, SEBlock, conv1x1, conv1x1_block, conv3x3_block, conv7x7_block, dwconv3x3_block,
+from .blocks import (B200Module, ConvBlock, SEBlock, conv1x1, conv1x1_block, conv3x3_block, conv7x7_block, dwconv3x3_block,
                      dwconv5x5_block, dwsconv3x3_block, HSwish, lambda_batchnorm2d, lambda_hsigmoid, lambda_hswish,
                      lambda_relu, lambda_relu6, lambda_swish, round_channels)
 from .plan import run_module
@@ -775,6 +775,100 @@ def get_spnasnet(model_name=None, pretrained=False, root=None, **kwargs):
                    exp_factors=[[3, 3, 3], [6, 3, 3, 3], [6, 3, 3, 3], [6, 3, 3, 3, 6, 6, 6, 6]], **kwargs)
     _load_pretrained(net, pretrained, model_name, root)
     return net
+
+
+# ===== ProxylessNAS (proxylessnas.py), SURVEY 8(f) rank 1 =============================================================
+class ProxylessBlock(B200Module):
+    """[1x1 expand] -> depthwise k x k (k in {3, 5, 7}) -> 1x1 linear (proxylessnas.py:16-70)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, normalization, activation, expansion):
+        super().__init__()
+        self.use_bc = expansion > 1
+        mid = in_channels * expansion
+        if self.use_bc:
+            self.bc_conv = conv1x1_block(in_channels=in_channels, out_channels=mid, normalization=normalization,
+                                         activation=activation)
+        self.dw_conv = ConvBlock(in_channels=mid, out_channels=mid, kernel_size=kernel_size, stride=stride,
+                                 padding=(kernel_size - 1) // 2, groups=mid, normalization=normalization,
+                                 activation=activation)
+        self.pw_conv = conv1x1_block(in_channels=mid, out_channels=out_channels, normalization=normalization,
+                                     activation=None)
+
+
+class ProxylessUnit(B200Module):
+    """identity | body | x + body(x) (proxylessnas.py:73-123)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, normalization, activation, expansion, residual,
+                 shortcut):
+        super().__init__()
+        assert residual or shortcut
+        self.residual, self.shortcut = residual, shortcut
+        if self.residual:
+            self.body = ProxylessBlock(in_channels=in_channels, out_channels=out_channels, kernel_size=kernel_size,
+                                       stride=stride, normalization=normalization, activation=activation,
+                                       expansion=expansion)
+
+
+class ProxylessNAS(_Classifier):
+    """proxylessnas.py:126-230."""
+
+    def __init__(self, channels, init_block_channels, final_block_channels, residuals, shortcuts, kernel_sizes,
+                 expansions, bn_eps=1e-3, in_channels=3, in_size=(224, 224), num_classes=1000):
+        super().__init__()
+        self.in_size, self.num_classes = in_size, num_classes
+        norm, act = lambda_batchnorm2d(eps=bn_eps), lambda_relu6()
+        self.features = nn.Sequential()
+        self.features.add_module("init_block", conv3x3_block(in_channels=in_channels, out_channels=init_block_channels,
+                                                             stride=2, normalization=norm, activation=act))
+        last = _stages(self.features, channels, init_block_channels,
+                       lambda i, j, cin, cout, s: ProxylessUnit(
+                           in_channels=cin, out_channels=cout, kernel_size=kernel_sizes[i][j], stride=s,
+                           normalization=norm, activation=act, expansion=expansions[i][j],
+                           residual=residuals[i][j] == 1, shortcut=shortcuts[i][j] == 1))
+        self.features.add_module("final_block", conv1x1_block(in_channels=last, out_channels=final_block_channels,
+                                                              normalization=norm, activation=act))
+        self._finish(final_block_channels, num_classes)
+
+
+_PROXYLESS_TABLES = {   # proxylessnas.py:261-297
+    "cpu": dict(residuals=[[1], [1, 1, 1, 1], [1, 1, 1, 1], [1, 0, 0, 1, 1, 1, 1, 1], [1, 1, 1, 1, 1]],
+                channels=[[24], [32, 32, 32, 32], [48, 48, 48, 48], [88, 88, 88, 88, 104, 104, 104, 104],
+                          [216, 216, 216, 216, 360]],
+                kernel_sizes=[[3], [3, 3, 3, 3], [3, 3, 3, 5], [3, 3, 3, 3, 5, 3, 3, 3], [5, 5, 5, 3, 5]],
+                expansions=[[1], [6, 3, 3, 3], [6, 3, 3, 3], [6, 3, 3, 3, 6, 3, 3, 3], [6, 3, 3, 3, 6]],
+                init_block_channels=40, final_block_channels=1432),
+    "gpu": dict(residuals=[[1], [1, 0, 0, 0], [1, 0, 0, 1], [1, 0, 0, 1, 1, 0, 1, 1], [1, 1, 1, 1, 1]],
+                channels=[[24], [32, 32, 32, 32], [56, 56, 56, 56], [112, 112, 112, 112, 128, 128, 128, 128],
+                          [256, 256, 256, 256, 432]],
+                kernel_sizes=[[3], [5, 3, 3, 3], [7, 3, 3, 3], [7, 5, 5, 5, 5, 3, 3, 5], [7, 7, 7, 5, 7]],
+                expansions=[[1], [3, 3, 3, 3], [3, 3, 3, 3], [6, 3, 3, 3, 6, 3, 3, 3], [6, 6, 6, 6, 6]],
+                init_block_channels=40, final_block_channels=1728),
+    "mobile": dict(residuals=[[1], [1, 1, 0, 0], [1, 1, 1, 1], [1, 1, 1, 1, 1, 1, 1, 1], [1, 1, 1, 1, 1]],
+                   channels=[[16], [32, 32, 32, 32], [40, 40, 40, 40], [80, 80, 80, 80, 96, 96, 96, 96],
+                             [192, 192, 192, 192, 320]],
+                   kernel_sizes=[[3], [5, 3, 3, 3], [7, 3, 5, 5], [7, 5, 5, 5, 5, 5, 5, 5], [7, 7, 7, 7, 7]],
+                   expansions=[[1], [3, 3, 3, 3], [3, 3, 3, 3], [6, 3, 3, 3, 6, 3, 3, 3], [6, 6, 3, 3, 6]],
+                   init_block_channels=32, final_block_channels=1280),
+    "mobile14": dict(residuals=[[1], [1, 1, 0, 0], [1, 1, 1, 1], [1, 1, 1, 1, 1, 1, 1, 1], [1, 1, 1, 1, 1]],
+                     channels=[[24], [40, 40, 40, 40], [56, 56, 56, 56], [112, 112, 112, 112, 136, 136, 136, 136],
+                               [256, 256, 256, 256, 448]],
+                     kernel_sizes=[[3], [5, 3, 3, 3], [7, 3, 5, 5], [7, 5, 5, 5, 5, 5, 5, 5], [7, 7, 7, 7, 7]],
+                     expansions=[[1], [3, 3, 3, 3], [3, 3, 3, 3], [6, 3, 3, 3, 6, 3, 3, 3], [6, 6, 3, 3, 6]],
+                     init_block_channels=48, final_block_channels=1792),
+}
+
+
+def get_proxylessnas(version, model_name=None, pretrained=False, root=None, **kwargs):
+    """Same contract as proxylessnas.py:233-330."""
+    if version not in _PROXYLESS_TABLES:
+        raise ValueError("Unsupported ProxylessNAS version: {}".format(version))
+    shortcuts = [[0], [0, 1, 1, 1], [0, 1, 1, 1], [0, 1, 1, 1, 0, 1, 1, 1], [0, 1, 1, 1, 0]]
+    net = ProxylessNAS(shortcuts=shortcuts, **_PROXYLESS_TABLES[version], **kwargs)
+    _load_pretrained(net, pretrained, model_name, root)
+    return net
+
+
+PROXYLESSNAS_VARIANTS = {f"proxylessnas_{v}": v for v in _PROXYLESS_TABLES}
 
 
 # ===== MobileNet v1: the DwsConvBlock vehicle (mobilenet.py) ==========================================================

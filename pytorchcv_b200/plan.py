@@ -580,6 +580,17 @@ def _lower_dws_exp_se_res(b, m, x, **kw):
     return lower(b, m.pw_conv, y, residual=x if m.residual else None, post_act=None)
 
 
+@lowers("ProxylessUnit")
+def _lower_proxyless_unit(b, m, x, **kw):
+    """ProxylessUnit.forward (proxylessnas.py:114-123) with ProxylessBlock.forward (:64-70): identity | body | x + body(x)."""
+    if not m.residual:
+        return x
+    blk = m.body
+    y = lower(b, blk.bc_conv, x) if blk.use_bc else x
+    y = lower(b, blk.dw_conv, y)
+    return lower(b, blk.pw_conv, y, residual=x if m.shortcut else None, post_act=None)
+
+
 @lowers("FBNetUnit", "SPNASUnit")
 def _lower_fbnet_unit(b, m, x, **kw):
     """FBNetUnit.forward (fbnet.py:77-87) == SPNASUnit.forward (spnasnet.py:72-82): [1x1 expand] -> dw -> 1x1 (+x)."""
@@ -729,7 +740,7 @@ def _flat(t: TRef) -> TRef:
     return t
 
 
-@lowers("ResNet", "SEResNeXt", "SEResNet", "ResNeXt", "MobileNet", "EfficientNet", "MnasNet", "FBNet", "SPNASNet", "SENet")
+@lowers("ResNet", "SEResNeXt", "SEResNet", "ResNeXt", "MobileNet", "EfficientNet", "MnasNet", "FBNet", "SPNASNet", "SENet", "ProxylessNAS")
 def _lower_classifier(b, m, x, **kw):
     """features -> view(N,-1) -> [Dropout ->] Linear (resnet.py:333-337, seresnext.py:136-140, efficientnet.py:354-358)."""
     return _flat(lower(b, m.output, lower(b, m.features, x)))

@@ -51,6 +51,7 @@ NETS = [
     ("fbnet_cb_bs2", "fbnet_cb", {}, (2, 3, 224, 224), 0, 1),
     ("spnasnet_bs2", "spnasnet", {}, (2, 3, 224, 224), 0, 1),
     ("senet16_bs2", "senet16", {}, (2, 3, 224, 224), 0, 1),
+    ("proxylessnas_mobile_bs2", "proxylessnas_mobile", {}, (2, 3, 224, 224), 0, 1),
 ]
 
 # block-level cases: (stem, ctor, input shape)

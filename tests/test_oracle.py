@@ -35,6 +35,7 @@ NETS = [
     ("fbnet_cb_bs2", "fbnet_cb", (2, 3, 224, 224), 1),
     ("spnasnet_bs2", "spnasnet", (2, 3, 224, 224), 1),
     ("senet16_bs2", "senet16", (2, 3, 224, 224), 1),
+    ("proxylessnas_mobile_bs2", "proxylessnas_mobile", (2, 3, 224, 224), 1),
 ]
 
 BLOCKS = {
@@ -141,7 +142,7 @@ def test_oracle_equals_reference_live(reference_pkg, name, shape):
 @pytest.mark.parametrize("name", ["resnet18", "resnet50", "mobilenetv2_w1", "seresnext50_32x4d",
                                   "deeplabv3_resnetd50b_voc", "mobilenet_w1", "efficientnet_b0", "efficientnet_b3",
                                   "mobilenetv3_large_w1", "mobilenetv3_small_w3d4", "seresnet18", "seresnetbc26b",
-                                  "fcn8sd_resnetd50b_voc", "pspnet_resnetd50b_voc", "mnasnet_b1", "mnasnet_small", "fbnet_cb", "spnasnet", "senet16"])
+                                  "fcn8sd_resnetd50b_voc", "pspnet_resnetd50b_voc", "mnasnet_b1", "mnasnet_small", "fbnet_cb", "spnasnet", "senet16", "proxylessnas_gpu", "proxylessnas_cpu"])
 def test_same_seed_same_random_init_as_reference(reference_pkg, name):
     """torch.manual_seed(0); get_model(name) consumes the RNG in the reference's order -> bit-identical weights."""
     from pytorchcv.model_provider import get_model as ref_get_model
