@@ -14,6 +14,14 @@ REFERENCE = "/root/reference"  # exists only in the build container; never on th
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
     config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
+    # The C-ABI library is a build artefact (git-ignored): a fresh checkout builds it once, like __graft_entry__.build()
+    lib = os.path.join(ROOT, "pytorchcv_b200", "libpcv_b200.so")
+    if not os.path.exists(lib):
+        import shutil
+        import subprocess
+        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "pytorchcv_b200", "csrc"), "-j", "8"], check=False,
+                           capture_output=True)
 
 
 def pytest_collection_modifyitems(config, items):
