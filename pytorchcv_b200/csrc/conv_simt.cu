@@ -38,11 +38,14 @@ __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
-template <typename T>
+// TILE = 64: the throughput shape (4 x 4 register tile per thread).  TILE = 32 (2 x 2 per thread): four times the CTAs
+// for layers whose 64 x 64 grid cannot fill the machine (ResNet-18 at batch 8: 56 CTAs walked K = 4608 on the 7 x 7 maps).
+template <typename T, int TILE>
 __global__ void __launch_bounds__(256)
 conv_simt_kernel(const SimtParams p, const T* __restrict__ x, const float* __restrict__ w,
                  const float* __restrict__ bias, const T* __restrict__ res, void* __restrict__ y) {
-  constexpr int TM = 64, TN = 64, TK = 16;
+  constexpr int TM = TILE, TN = TILE, TK = 16;
+  constexpr int R = TILE / 16;        // register tile edge, also elements per thread of each smem fill
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN];
 
@@ -52,13 +55,13 @@ conv_simt_kernel(const SimtParams p, const T* __restrict__ x, const float* __res
   const int g = blockIdx.z;
 
   // fill roles
-  const int a_pix = tid >> 2;         // 0..63
-  const int a_c = (tid & 3) * 4;      // 0,4,8,12
-  const int b_k = tid >> 4;           // 0..15
-  const int b_n = (tid & 15) * 4;     // 0..60
+  const int a_pix = tid / (16 / R);         // 0..TM-1
+  const int a_c = (tid % (16 / R)) * R;     // first of this thread's R channels of the K chunk
+  const int b_k = tid >> 4;                 // 0..15
+  const int b_n = (tid & 15) * R;           // 0..TN-R
   // compute roles
-  const int ty = tid >> 4;            // pixel quad
-  const int tx = tid & 15;            // channel quad
+  const int ty = tid >> 4;                  // pixel group
+  const int tx = tid & 15;                  // channel group
 
   const int am = m0 + a_pix;
   const bool a_valid = am < p.M;
@@ -71,11 +74,11 @@ conv_simt_kernel(const SimtParams p, const T* __restrict__ x, const float* __res
     a_w0 = (r - ho * p.Wo) * p.stride - p.pad;
   }
 
-  float acc[4][4];
+  float acc[R][R];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < R; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < R; ++j) acc[i][j] = 0.f;
 
   const int taps = p.kh * p.kw;
   for (int tap = 0; tap < taps; ++tap) {
@@ -87,14 +90,14 @@ conv_simt_kernel(const SimtParams p, const T* __restrict__ x, const float* __res
     const float* wp = w + (static_cast<size_t>(g) * taps + tap) * p.cin_g * p.cout_g;
     for (int c0 = 0; c0 < p.cin_g; c0 += TK) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < R; ++i) {
         const int c = c0 + a_c + i;
         As[a_c + i][a_pix] = (pix_ok && c < p.cin_g) ? to_f<T>(xp[c]) : 0.f;
       }
       {
         const int k = c0 + b_k;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < R; ++j) {
           const int n = n0 + b_n + j;
           Bs[b_k][b_n + j] = (k < p.cin_g && n < p.cout_g) ? wp[static_cast<size_t>(k) * p.cout_g + n] : 0.f;
         }
@@ -102,26 +105,28 @@ conv_simt_kernel(const SimtParams p, const T* __restrict__ x, const float* __res
       __syncthreads();
 #pragma unroll
       for (int k = 0; k < TK; ++k) {
-        const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-        const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-        const float av[4] = {a.x, a.y, a.z, a.w};
-        const float bv[4] = {b.x, b.y, b.z, b.w};
+        float av[R], bv[R];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < R; ++i) {
+          av[i] = As[k][ty * R + i];
+          bv[i] = Bs[k][tx * R + i];
+        }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int i = 0; i < R; ++i)
+#pragma unroll
+          for (int j = 0; j < R; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
       }
       __syncthreads();
     }
   }
 
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < R; ++i) {
+    const int m = m0 + ty * R + i;
     if (m >= p.M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+    for (int j = 0; j < R; ++j) {
+      const int n = n0 + tx * R + j;
       if (n >= p.cout_g) continue;
       const int co = g * p.cout_g + n;
       float v = acc[i][j] + bias[co];
@@ -193,12 +198,23 @@ struct SimtOp : Op {
   void* y;
   cudaError_t launch(cudaStream_t s) override {
     g_launches++;
+    const long long ctas64 = static_cast<long long>(ceil_div(p.M, 64)) * ceil_div(p.cout_g, 64) * p.groups;
+    const bool small = ctas64 < 2ll * sm_count() && ceil_div(p.M, 32) <= 2147483647 / 2;   // cannot fill the machine
+    if (small) {
+      dim3 grid(ceil_div(p.M, 32), ceil_div(p.cout_g, 32), p.groups);
+      if (dtype == PCV_F32)
+        conv_simt_kernel<float, 32><<<grid, 256, 0, s>>>(p, (const float*)x, w, bias, (const float*)res, y);
+      else
+        conv_simt_kernel<__nv_bfloat16, 32><<<grid, 256, 0, s>>>(p, (const __nv_bfloat16*)x, w, bias,
+                                                                 (const __nv_bfloat16*)res, y);
+      return cudaGetLastError();
+    }
     dim3 grid(ceil_div(p.M, 64), ceil_div(p.cout_g, 64), p.groups);
     if (dtype == PCV_F32)
-      conv_simt_kernel<float><<<grid, 256, 0, s>>>(p, (const float*)x, w, bias, (const float*)res, y);
+      conv_simt_kernel<float, 64><<<grid, 256, 0, s>>>(p, (const float*)x, w, bias, (const float*)res, y);
     else
-      conv_simt_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p, (const __nv_bfloat16*)x, w, bias,
-                                                           (const __nv_bfloat16*)res, y);
+      conv_simt_kernel<__nv_bfloat16, 64><<<grid, 256, 0, s>>>(p, (const __nv_bfloat16*)x, w, bias,
+                                                               (const __nv_bfloat16*)res, y);
     return cudaGetLastError();
   }
 };
@@ -219,7 +235,7 @@ int simt_make(const pcv_conv_desc& d, int dtype, const void* x, const void* w, c
   p.res_pitch = pitch_or(d.res_pitch, d.Cout);
   p.act = d.act;
   p.out_f32 = (d.flags & PCV_CONV_OUT_F32) ? 1 : 0;
-  PCV_REQUIRE(ceil_div(p.cout_g, 64) <= 65535 && p.groups <= 65535, "grid too large for the CUDA-core conv");
+  PCV_REQUIRE(ceil_div(p.cout_g, 32) <= 65535 && p.groups <= 65535, "grid too large for the CUDA-core conv");
   op->dtype = dtype; op->x = x; op->w = reinterpret_cast<const float*>(w); op->bias = bias; op->res = res; op->y = y;
   char nm[160];
   snprintf(nm, sizeof nm, "conv_simt_%s %dx%d s%d d%d g%d %d->%d @%dx%d%s", dtype == PCV_F32 ? "f32" : "bf16", d.kh,
