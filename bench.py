@@ -121,11 +121,14 @@ def run_reference(a) -> None:
         oracle_forward(net, x)
     dt = (time.perf_counter() - t0) / steps
     v = sample / dt
-    line = {"impl": "reference", "metric": f"{a.model} eval inference images/sec", "value": round(v, 2),
+    # same metric / config strings as the b200 arm (the driver pairs the two lines); dtype says what this arm computes in
+    line = {"impl": "reference", "metric": f"{a.model} bs{batch} {a.dtype} eval inference images/sec", "value": round(v, 2),
             "unit": "images/s", "n_gpus": a.gpus, "steps": steps, "warmup": warm, "ms_per_step": round(dt * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{a.model} eval forward, {H}x{W}, batch {batch} per GPU (fp32 NCHW in, logits out)",
-                       "sample_batch": sample},
+            "config": {"workload": f"{a.model} eval forward, {H}x{W}, batch {batch} per GPU, fp32 NCHW in -> fp32 logits out "
+                                   f"(random-init weights, torch.manual_seed(0))",
+                       "global_batch": batch * a.gpus, "sample_batch": sample,
+                       "parallelism": "reference CPU path on rank 0's host cores (torch fp32, all threads)"},
             "cpu_baseline": {"value": round(v, 2), "unit": "images/s", "cores": cores, "kind": "port",
                              "sample": f"{steps} timed forwards of {sample} images (torch {torch.__version__} CPU, "
                                        f"{torch.get_num_threads()} threads) through oracle/ref_forward.py"},
