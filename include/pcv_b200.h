@@ -11,8 +11,9 @@
  *  - All pointers are DEVICE pointers unless a name ends in _host.  Activations are NHWC ("pixels x channels")
  *    with an explicit channel pitch (elements between consecutive pixels; 0 means "= channels"), so a tensor can
  *    be a channel slice of a wider buffer (torch.cat on dim 1 becomes a write at a channel offset).
- *  - `dtype` selects the arithmetic tier: PCV_BF16 = bf16 storage, fp32 accumulate/epilogue (tcgen05 tensor cores
- *    for dense/grouped conv); PCV_F32 = fp32 storage and true fp32 FMA (the <=1e-4 tier).
+ *  - `dtype` selects the arithmetic tier: PCV_BF16 / PCV_F16 = 16-bit storage, fp32 accumulate/epilogue (tcgen05 tensor
+ *    cores for dense/grouped conv; comments below that say "bf16 tier" apply to both); PCV_F32 = fp32 storage and true
+ *    fp32 FMA (the <=1e-4 tier).
  *  - `plan`: when non-NULL the op is RECORDED into the plan (stream ignored) and runs on every pcv_plan_run();
  *    when NULL it is launched immediately on `stream`.  Kernels never synchronise the host.
  */
@@ -43,7 +44,16 @@ enum pcv_status {
   PCV_ERR_NO_DEVICE = -4     /* no sm_100 device: there is no CPU fallback */
 };
 
-enum pcv_dtype { PCV_BF16 = 0, PCV_F32 = 1 };
+enum pcv_dtype {
+  PCV_BF16 = 0,  /* bf16 storage, fp32 accumulate / epilogue (tcgen05 kind::f16, bf16 operands) */
+  PCV_F32 = 1,   /* fp32 storage, true fp32 FMA: the <= 1e-4 tier */
+  PCV_F16 = 2    /* IEEE fp16 storage, fp32 accumulate / epilogue: the same kernels and MMA rate as PCV_BF16 with 3 more
+                    mantissa bits (MobileNetV2-class networks meet 2e-2 end to end here); |x| > 65504 overflows */
+};
+
+/* element type of the NCHW image handed to the network edge (pcv_*_ingest_ex): the reference's fp32 tensor, or a
+ * narrower copy of it that costs half / a quarter of the host->device bytes */
+enum pcv_image_type { PCV_IMG_F32 = 0, PCV_IMG_BF16 = 1, PCV_IMG_F16 = 2, PCV_IMG_U8 = 3 };
 
 /* activations of pytorchcv/models/common/activ.py:188-222 (create_activation_layer) */
 enum pcv_act {
@@ -134,6 +144,11 @@ PCV_API int pcv_add_act(pcv_plan* plan, int dtype, size_t count, const void* a, 
 /* Reference tensors are NCHW fp32.  Ingest pads channels with zeros up to c_pitch. */
 PCV_API int pcv_nchw_f32_to_nhwc(pcv_plan* plan, int dtype, int N, int C, int H, int W, const float* x, void* y,
                          int c_pitch, pcv_stream stream);
+/* The same edge for an image stored as fp32 / bf16 / fp16 / uint8 NCHW (pcv_image_type): y = float(x) * scale[c] + bias[c]
+ * (scale_host / bias_host: HOST arrays of C floats read when the op is created, NULL = identity; uint8 pipelines fold
+ * their 1/255, mean and std here).  pcv_nchw_f32_to_nhwc is the PCV_IMG_F32, identity case. */
+PCV_API int pcv_nchw_to_nhwc_ex(pcv_plan* plan, int dtype, int img_type, int N, int C, int H, int W, const void* x,
+                        const float* scale_host, const float* bias_host, void* y, int c_pitch, pcv_stream stream);
 PCV_API int pcv_nhwc_to_nchw_f32(pcv_plan* plan, int dtype, int N, int C, int H, int W, const void* x, int c_pitch,
                          float* y, pcv_stream stream);
 /* Space-to-depth stem.  A k x k stride-2 pad-(k/2) convolution on a <=4-channel image (ResInitBlock's 7x7,
@@ -148,6 +163,11 @@ PCV_API int pcv_nhwc_to_nchw_f32(pcv_plan* plan, int dtype, int N, int C, int H,
 PCV_API int pcv_stem_s2d_dims(int C, int H, int W, int k, int* rows, int* cols, int* cin_eq, int* taps_eq);
 PCV_API int pcv_stem_s2d_ingest(pcv_plan* plan, int N, int C, int H, int W, int k, const float* x, void* s2d,
                                 pcv_stream stream);
+/* pcv_stem_s2d_ingest for either 16-bit tier (dtype = PCV_BF16 | PCV_F16) and any pcv_image_type, with the per-channel
+ * affine of pcv_nchw_to_nhwc_ex. */
+PCV_API int pcv_stem_s2d_ingest_ex(pcv_plan* plan, int dtype, int img_type, int N, int C, int H, int W, int k,
+                                   const void* x, const float* scale_host, const float* bias_host, void* s2d,
+                                   pcv_stream stream);
 /* 1 when the stem conv (C-channel HxW image, k x k stride 2 pad k/2, Cout channels) can run with PCV_CONV_POOL3S2:
  * Cout == 64, even conv map with 64 <= W/2 and W/2 + k/2 <= 128 columns (one conv row per 128-row M-block), else 0 and the
  * caller records pcv_conv2d_bias_act + pcv_maxpool2d. */

@@ -15,8 +15,11 @@ import torch.nn.functional as F
 from . import ref_forward as R
 
 
+_STORAGE = [torch.bfloat16]   # the 16-bit element type being emulated (bf16 tier or fp16 tier)
+
+
 def _rb(t: torch.Tensor) -> torch.Tensor:
-    return t.to(torch.bfloat16).float()
+    return t.to(_STORAGE[0]).float()
 
 
 def _conv_block_bf16(m, x):
@@ -43,11 +46,18 @@ _CONV, _SE = R.conv_block, R.se_block
 
 
 @torch.no_grad()
-def oracle_forward_bf16_storage(m, x, **kw):
-    saved = (R.conv_block, R.se_block, R._BY_NAME["ConvBlock"], R._BY_NAME["SEBlock"])
+def oracle_forward_16bit_storage(m, x, storage=torch.bfloat16, **kw):
+    """The oracle with the arithmetic contract of a 16-bit tier: `storage` = torch.bfloat16 (PCV_BF16) or torch.float16
+    (PCV_F16) activations and BN-folded weights, fp32 accumulate / bias / activation, one rounding per block."""
+    saved = (R.conv_block, R.se_block, R._BY_NAME["ConvBlock"], R._BY_NAME["SEBlock"], _STORAGE[0])
     R.conv_block, R.se_block = _conv_block_bf16, _se_block_bf16
     R._BY_NAME["ConvBlock"], R._BY_NAME["SEBlock"] = _conv_block_bf16, _se_block_bf16
+    _STORAGE[0] = storage
     try:
         return R.oracle_forward(m, x, **kw)
     finally:
-        R.conv_block, R.se_block, R._BY_NAME["ConvBlock"], R._BY_NAME["SEBlock"] = saved
+        R.conv_block, R.se_block, R._BY_NAME["ConvBlock"], R._BY_NAME["SEBlock"], _STORAGE[0] = saved
+
+
+def oracle_forward_bf16_storage(m, x, **kw):
+    return oracle_forward_16bit_storage(m, x, storage=torch.bfloat16, **kw)

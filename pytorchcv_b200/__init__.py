@@ -10,8 +10,9 @@ no torch-op or CPU fallback.
 """
 from . import _lib
 from .model_provider import get_model, supported_models
-from .plan import (Accelerated, CompiledModule, accelerate, invalidate, run_module, set_default_precision)
+from .plan import (Accelerated, CompiledModule, accelerate, invalidate, run_module, set_default_graph,
+                   set_default_precision)
 
-__all__ = ["get_model", "supported_models", "accelerate", "invalidate", "run_module", "set_default_precision",
+__all__ = ["get_model", "supported_models", "accelerate", "invalidate", "run_module", "set_default_precision", "set_default_graph",
            "CompiledModule", "Accelerated", "_lib"]
 __version__ = "0.1.0"

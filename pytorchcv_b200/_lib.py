@@ -11,7 +11,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PCV_B200_LIB") or os.path.join(_HERE, "libpcv_b200.so")   # env: A/B a second build
 
-BF16, F32 = 0, 1
+BF16, F32, F16 = 0, 1, 2                      # pcv_dtype
+IMG_F32, IMG_BF16, IMG_F16, IMG_U8 = 0, 1, 2, 3  # pcv_image_type
 ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SIGMOID, ACT_SWISH, ACT_HSWISH, ACT_HSIGMOID = range(7)
 CONV_OUT_F32, CONV_FORCE_SIMT, CONV_A_IM2COL, CONV_IN_OVERLAP, CONV_POOL3S2 = 1, 2, 4, 8, 16
 
@@ -52,10 +53,12 @@ SIGNATURES = {
     "pcv_se_scale_add_act": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P]),
     "pcv_add_act": (_I, [_P, _I, _Z, _P, _P, _I, _P, _P]),
     "pcv_nchw_f32_to_nhwc": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
+    "pcv_nchw_to_nhwc_ex": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "pcv_nhwc_to_nchw_f32": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _P]),
     "pcv_bilinear_upsample_ac": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _P]),
     "pcv_stem_s2d_dims": (_I, [_I, _I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "pcv_stem_s2d_ingest": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "pcv_stem_s2d_ingest_ex": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "pcv_stem_s2d_weights": (_I, [_I, _I, _I, _P, _P, _P]),
     "pcv_stem_s2d_pool_ok": (_I, [_I, _I, _I, _I, _I]),
     "pcv_plan_create": (_I, [C.POINTER(_P)]),

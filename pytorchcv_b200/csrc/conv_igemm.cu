@@ -21,6 +21,7 @@
 #include "igemm_common.cuh"
 
 namespace pcv {
+namespace PCV_TIER {
 
 template <int BN, int STAGES>
 struct SmemLayout {
@@ -150,7 +151,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
     {   // whole warp; tcgen05 instructions under elect.sync
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BN);
+      constexpr uint32_t idesc = make_idesc_e16(BLOCK_M, BN);
       const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA)), b_lo0 = smem_desc_lo(smem_u32(sB));
       int stage = 0;
       uint32_t phase = 0;
@@ -212,7 +213,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const float act_lo = p.act_lo, act_hi = p.act_hi;
     const bool fancy_act = p.act > PCV_ACT_RELU6;
     const bool relu = p.act_lo == 0.f, capped = p.act_hi != INFINITY;   // the clamp family: none / ReLU / ReLU6
-    const uint32_t cap2 = pack_bf16x2(p.act_hi, p.act_hi);
+    const uint32_t cap2 = pack_e16x2(p.act_hi, p.act_hi);
     const uint32_t sStg_u32 = smem_u32(sStg);
     int it = 0;
     int sbuf = 0;           // staging ring position of this tile
@@ -267,14 +268,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (p.has_res) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              v[8 * c + 0] += bf16lo(r4[c].x);
-              v[8 * c + 1] += bf16hi(r4[c].x);
-              v[8 * c + 2] += bf16lo(r4[c].y);
-              v[8 * c + 3] += bf16hi(r4[c].y);
-              v[8 * c + 4] += bf16lo(r4[c].z);
-              v[8 * c + 5] += bf16hi(r4[c].z);
-              v[8 * c + 6] += bf16lo(r4[c].w);
-              v[8 * c + 7] += bf16hi(r4[c].w);
+              v[8 * c + 0] += e16lo(r4[c].x);
+              v[8 * c + 1] += e16hi(r4[c].x);
+              v[8 * c + 2] += e16lo(r4[c].y);
+              v[8 * c + 3] += e16hi(r4[c].y);
+              v[8 * c + 4] += e16lo(r4[c].z);
+              v[8 * c + 5] += e16hi(r4[c].z);
+              v[8 * c + 6] += e16lo(r4[c].w);
+              v[8 * c + 7] += e16hi(r4[c].w);
             }
           }
           uint32_t o[16];
@@ -296,10 +297,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (m < p.M) {
             const int ncol = min(32, p.Cout - (n0 + j * 32));
             if (p.has_res) {
-              const __nv_bfloat16* rp = p.res + static_cast<size_t>(m) * p.res_pitch + n0 + j * 32;
+              const e16* rp = p.res + static_cast<size_t>(m) * p.res_pitch + n0 + j * 32;
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (i < ncol) v[i] += __bfloat162float(rp[i]);
+                if (i < ncol) v[i] += e16_to_float(rp[i]);
             }
             if (fancy_act) {
               fast_act_n(v, p.act);
@@ -313,11 +314,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               for (int i = 0; i < 32; ++i)
                 if (i < ncol) op[i] = v[i];
             } else {
-              __nv_bfloat16* op =
-                  reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(m) * p.out_pitch + n0 + j * 32;
+              e16* op =
+                  reinterpret_cast<e16*>(p.out) + static_cast<size_t>(m) * p.out_pitch + n0 + j * 32;
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (i < ncol) op[i] = __float2bfloat16(v[i]);
+                if (i < ncol) op[i] = float_to_e16(v[i]);
             }
           }
         }
@@ -365,7 +366,7 @@ __global__ void igemm_pack_kernel(const float* __restrict__ w, const float* __re
                                   const float* __restrict__ g, const float* __restrict__ b,
                                   const float* __restrict__ mean, const float* __restrict__ var, float eps,
                                   int Cout, int Cin, int groups, int taps, int cblocks, int grouped_bn, int in_span,
-                                  __nv_bfloat16* __restrict__ wp, float* __restrict__ bias_out, int bias_len) {
+                                  e16* __restrict__ wp, float* __restrict__ bias_out, int bias_len) {
   const int kpad = taps * cblocks * BLOCK_K;
   const size_t total = static_cast<size_t>(Cout) * kpad;
   const int cin_g = Cin / groups;
@@ -389,7 +390,7 @@ __global__ void igemm_pack_kernel(const float* __restrict__ w, const float* __re
       const int ci = ci_abs - grp * cin_g;
       if (ci >= 0 && ci < cin_g && cc < in_span) val = w[(static_cast<size_t>(o) * cin_g + ci) * taps + tap];
     }
-    wp[idx] = __float2bfloat16(val * scale);
+    wp[idx] = float_to_e16(val * scale);
   }
   for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < bias_len; o += gridDim.x * blockDim.x) {
     float v = 0.f;
@@ -456,7 +457,7 @@ int igemm_pack(const pcv_conv_desc& d, const float* w, const float* conv_bias, c
   const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 4096));
   igemm_pack_kernel<<<blocks, 256, 0, s>>>(w, conv_bias, g, b, m, v, eps, d.Cout, d.Cin, d.groups, taps, cblocks, 64,
                                            d.groups > 1 ? 64 * (d.Cin / d.groups) / (d.Cout / d.groups) : 64,
-                                           reinterpret_cast<__nv_bfloat16*>(w_packed), bias_out,
+                                           reinterpret_cast<e16*>(w_packed), bias_out,
                                            round_up(d.Cout, 256));
   g_launches++;
   PCV_CHECK_CUDA(cudaGetLastError());
@@ -474,7 +475,7 @@ static int make_tiled_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(tm, TMAP_E16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -493,7 +494,7 @@ static int make_im2col_4d(CUtensorMap* tm, const void* base, const pcv_conv_desc
   int lower[2] = {-d.pad, -d.pad};                                              // {W, H}
   int upper[2] = {d.pad - (d.kw - 1) * d.dil, d.pad - (d.kh - 1) * d.dil};      // {W, H}
   cuuint32_t estr[4] = {1, (cuuint32_t)d.stride, (cuuint32_t)d.stride, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper,
+  CUresult r = fn(tm, TMAP_E16, 4, const_cast<void*>(base), dims, strides, lower, upper,
                   BLOCK_K, BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -514,13 +515,8 @@ struct IgemmOp : Op {
 template <int BN, int STAGES, int OUT_MODE>
 static cudaError_t launch_variant(const IgemmOp& op, cudaStream_t s) {
   using L = SmemLayout<BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, STAGES, OUT_MODE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};   // per device (see runtime.h)
+  if (cudaError_t e = set_max_smem_once(igemm_kernel<BN, STAGES, OUT_MODE>, L::DYN_BYTES, attr_done)) return e;
   return launch_pdl(igemm_kernel<BN, STAGES, OUT_MODE>, dim3(op.grid), dim3(NUM_THREADS), L::DYN_BYTES, s, op.tmA, op.tmB,
                     op.tmOut, op.tmRes, op.p);
 }
@@ -572,7 +568,7 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   IgemmParams& p = op->p;
   p.bias = bias;
   p.out = y;
-  p.res = reinterpret_cast<const __nv_bfloat16*>(res);
+  p.res = reinterpret_cast<const e16*>(res);
   p.M = d.N * Ho * Wo;
   p.Cout = d.Cout;
   p.out_pitch = out_pitch;
@@ -702,4 +698,5 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   return PCV_OK;
 }
 
+}  // namespace PCV_TIER
 }  // namespace pcv

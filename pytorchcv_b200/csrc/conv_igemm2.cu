@@ -23,6 +23,7 @@
 #include "igemm_common.cuh"
 
 namespace pcv {
+namespace PCV_TIER {
 
 constexpr int NUM_THREADS2 = 384;   // 4 control warps (physical warps 8-11) + 8 epilogue warps
 
@@ -180,7 +181,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else if (warp == 1) {
     // ===================================== MMA issuer (leader CTA only) =====================================
     if (rank == 0) {   // whole warp (see the producer's note); tcgen05 instructions under elect.sync
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, TW);
+      constexpr uint32_t idesc = make_idesc_e16(2 * BLOCK_M, TW);
       const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA)), b_lo0 = smem_desc_lo(smem_u32(sB));
       int stage = 0;
       uint32_t phase = 0;
@@ -269,7 +270,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int row = q * 32 + lane;
     const bool fancy_act = p.act > PCV_ACT_RELU6;
     const bool relu = p.act_lo == 0.f, capped = p.act_hi != INFINITY;   // the clamp family: none / ReLU / ReLU6
-    const uint32_t cap2 = pack_bf16x2(p.act_hi, p.act_hi);
+    const uint32_t cap2 = pack_e16x2(p.act_hi, p.act_hi);
     const uint32_t sStg_u32 = smem_u32(sStg);
     const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
@@ -322,14 +323,14 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           if (p.has_res) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              v[8 * c + 0] += bf16lo(r4[c].x);
-              v[8 * c + 1] += bf16hi(r4[c].x);
-              v[8 * c + 2] += bf16lo(r4[c].y);
-              v[8 * c + 3] += bf16hi(r4[c].y);
-              v[8 * c + 4] += bf16lo(r4[c].z);
-              v[8 * c + 5] += bf16hi(r4[c].z);
-              v[8 * c + 6] += bf16lo(r4[c].w);
-              v[8 * c + 7] += bf16hi(r4[c].w);
+              v[8 * c + 0] += e16lo(r4[c].x);
+              v[8 * c + 1] += e16hi(r4[c].x);
+              v[8 * c + 2] += e16lo(r4[c].y);
+              v[8 * c + 3] += e16hi(r4[c].y);
+              v[8 * c + 4] += e16lo(r4[c].z);
+              v[8 * c + 5] += e16hi(r4[c].z);
+              v[8 * c + 6] += e16lo(r4[c].w);
+              v[8 * c + 7] += e16hi(r4[c].w);
             }
           }
           uint32_t o[16];
@@ -375,12 +376,8 @@ template <int BN, int NS>
 static cudaError_t launch_pair(int grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                                const CUtensorMap& tmRes, const IgemmParams& p, cudaStream_t s) {
   using L = Pair<BN, NS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm2_kernel<BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_LIMIT);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};   // per device (see runtime.h)
+  if (cudaError_t e = set_max_smem_once(igemm2_kernel<BN, NS>, L::SMEM_LIMIT, attr_done)) return e;
   return launch_pdl(igemm2_kernel<BN, NS>, dim3(grid), dim3(NUM_THREADS2), L::bytes(p.stages, p.ksub, p.nstg), s, tmA, tmB, tmOut,
                     tmRes, p);
 }
@@ -430,4 +427,5 @@ cudaError_t launch_igemm2(int bn, int grid, const CUtensorMap& tmA, const CUtens
   }
 }
 
+}  // namespace PCV_TIER
 }  // namespace pcv

@@ -30,10 +30,11 @@
 #include "igemm_common.cuh"
 
 namespace pcv {
+namespace PCV_TIER {
 
 struct Igemm3Params {
   const float* bias;
-  __nv_bfloat16* out;
+  e16* out;
   int out_pitch;
   int N, H, W, Cout;
   int R, PW, NMB;            // output rows per tile, padded width W+2, 128-row M-blocks per tile
@@ -163,7 +164,7 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     // UTCHMMA was wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY "waterfall" of ~13 dependent instructions, which
     // capped the issue rate at one MMA per ~120 cycles whatever its N.)
     if (rank == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BN);
+      constexpr uint32_t idesc = make_idesc_e16(2 * BLOCK_M, BN);
       const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA)), b_lo0 = smem_desc_lo(smem_u32(sB));
       const uint32_t b_step = p.b_block_bytes >> 4;
       mbar_wait(b_full, 0);
@@ -224,7 +225,7 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int half = (warp - 4) >> 2;
     const int row = q4 * 32 + lane;
     const bool relu = p.act_lo == 0.f, capped = p.act_hi != INFINITY;   // clamp family only (igemm3_try_make)
-    const uint32_t cap2 = pack_bf16x2(p.act_hi, p.act_hi);
+    const uint32_t cap2 = pack_e16x2(p.act_hi, p.act_hi);
     const uint32_t tmem_empty_leader0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     const uint32_t tmem_empty_leader1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
     const bool storer = STAGED && warp == 4 && lane == 0;   // owns every bulk store group of this CTA
@@ -247,7 +248,7 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const int r = q / p.PW;
         const int c = q - r * p.PW;
         const bool ok = tile_ok && c < p.W && r < p.R && (h0 + r) < p.H;
-        __nv_bfloat16* dst = p.out + (static_cast<size_t>(img * p.H + h0 + r) * p.W + c) * p.out_pitch + g * BN;
+        e16* dst = p.out + (static_cast<size_t>(img * p.H + h0 + r) * p.W + c) * p.out_pitch + g * BN;
 #pragma unroll 1
         for (int j = half; j < BN / 32; j += 2) {
           uint32_t acc[32];
@@ -327,12 +328,8 @@ struct Igemm3Op : Op {
 
 template <int BN, bool STAGED>
 static cudaError_t launch_i3(const Igemm3Op& op, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm3_kernel<BN, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};   // per device (see runtime.h)
+  if (cudaError_t e = set_max_smem_once(igemm3_kernel<BN, STAGED>, 232448, attr_done)) return e;
   return launch_pdl(igemm3_kernel<BN, STAGED>, dim3(op.grid), dim3(I3_THREADS), op.smem_bytes, s, op.tmA, op.tmB,
                     op.tmOut, op.p);
 }
@@ -404,7 +401,7 @@ int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const 
   auto op = std::make_unique<Igemm3Op>();
   Igemm3Params& p = op->p;
   p.bias = bias;
-  p.out = reinterpret_cast<__nv_bfloat16*>(y);
+  p.out = reinterpret_cast<e16*>(y);
   p.out_pitch = out_pitch;
   p.N = d.N; p.H = d.H; p.W = d.W; p.Cout = d.Cout;
   p.R = bestR; p.PW = PW; p.NMB = bestNMB; p.cblocks = cblocks; p.G = G;
@@ -434,7 +431,7 @@ int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const 
     cuuint64_t strides[3] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)d.W * in_pitch * 2, (cuuint64_t)d.H * d.W * in_pitch * 2};
     cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)PW, (cuuint32_t)(bestR + 2), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(&op->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+    CUresult r = fn(&op->tmA, TMAP_E16, 4, const_cast<void*>(x), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled (halo A) failed (%d)", (int)r);
@@ -445,7 +442,7 @@ int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const 
     cuuint64_t strides[1] = {kpad * 2};
     cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)(BN / 2)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(&op->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+    CUresult r = fn(&op->tmB, TMAP_E16, 2, const_cast<void*>(w), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled (halo B) failed (%d)", (int)r);
@@ -456,7 +453,7 @@ int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const 
     cuuint64_t strides[3] = {(cuuint64_t)out_pitch * 2, (cuuint64_t)d.W * out_pitch * 2, (cuuint64_t)d.H * d.W * out_pitch * 2};
     cuuint32_t box[4] = {(cuuint32_t)BN, (cuuint32_t)d.W, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(&op->tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, dims, strides, box, estr,
+    CUresult r = fn(&op->tmOut, TMAP_E16, 4, y, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled (halo out) failed (%d)", (int)r);
@@ -472,4 +469,5 @@ int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const 
   return PCV_OK;
 }
 
+}  // namespace PCV_TIER
 }  // namespace pcv

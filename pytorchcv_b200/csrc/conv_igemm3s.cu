@@ -29,10 +29,11 @@
 #include "igemm_common.cuh"
 
 namespace pcv {
+namespace PCV_TIER {
 
 struct StemParams {
   const float* bias;
-  __nv_bfloat16* out;
+  e16* out;
   int out_pitch;
   int N, Ho, Wo, Cout;
   int R, PW, NMB, T;         // output rows per tile, s2d row width (Wo + T - 1), 128-row M-blocks per tile, taps per axis
@@ -170,7 +171,7 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ===================================== MMA issuer (leader CTA only) =====================================
     if (rank == 0) {   // whole warp, warp-uniform values; tcgen05 instructions under elect.sync
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BN);
+      constexpr uint32_t idesc = make_idesc_e16(2 * BLOCK_M, BN);
       const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA)), b_lo0 = smem_desc_lo(smem_u32(sB));
       mbar_wait(b_full, 0);
       tc_fence_after();
@@ -279,24 +280,24 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (relu_only) {
 #pragma unroll
               for (int i = 0; i < 16; ++i)
-                o[i] = pack_relu_bf16x2(__uint_as_float(a[2 * i]) + bias_r[2 * i], __uint_as_float(a[2 * i + 1]) + bias_r[2 * i + 1]);
+                o[i] = pack_relu_e16x2(__uint_as_float(a[2 * i]) + bias_r[2 * i], __uint_as_float(a[2 * i + 1]) + bias_r[2 * i + 1]);
             } else {
 #pragma unroll
               for (int i = 0; i < 16; ++i)
-                o[i] = pack_bf16x2(fminf(fmaxf(__uint_as_float(a[2 * i]) + bias_r[2 * i], act_lo), act_hi),
+                o[i] = pack_e16x2(fminf(fmaxf(__uint_as_float(a[2 * i]) + bias_r[2 * i], act_lo), act_hi),
                                    fminf(fmaxf(__uint_as_float(a[2 * i + 1]) + bias_r[2 * i + 1], act_lo), act_hi));
             }
             if ((r & 1) == 0) {                    // row 2pr: start pooled row pr with the row above (if inside the image)
               const bool top = r == 0 && h0 == 0;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = top ? o[i] : hmax2_bf16(prev[i], o[i]);
+              for (int i = 0; i < 16; ++i) v[i] = top ? o[i] : hmax2_e16(prev[i], o[i]);
             } else {                               // row 2pr+1 completes it
               if (col_ok) {
                 const uint32_t dstp = v_dst + (r >> 1) * v_rowb;
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                  sts128(dstp + (((j * 4 + i) ^ v_sw) << 4), hmax2_bf16(v[4 * i], o[4 * i]), hmax2_bf16(v[4 * i + 1], o[4 * i + 1]),
-                         hmax2_bf16(v[4 * i + 2], o[4 * i + 2]), hmax2_bf16(v[4 * i + 3], o[4 * i + 3]));
+                  sts128(dstp + (((j * 4 + i) ^ v_sw) << 4), hmax2_e16(v[4 * i], o[4 * i]), hmax2_e16(v[4 * i + 1], o[4 * i + 1]),
+                         hmax2_e16(v[4 * i + 2], o[4 * i + 2]), hmax2_e16(v[4 * i + 3], o[4 * i + 3]));
               }
             }
 #pragma unroll
@@ -326,8 +327,8 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint4 a = lds128(rowp + c0 * ROWB + ((cg ^ (c0 & 7u)) << 4));
           const uint4 b = lds128(rowp + c1 * ROWB + ((cg ^ (c1 & 7u)) << 4));
           const uint4 c = lds128(rowp + c2 * ROWB + ((cg ^ (c2 & 7u)) << 4));
-          sts128(pool_u32 + pr * p_rowb + px * ROWB + ((cg ^ (px & 7u)) << 4), hmax3_bf16(a.x, b.x, c.x),
-                 hmax3_bf16(a.y, b.y, c.y), hmax3_bf16(a.z, b.z, c.z), hmax3_bf16(a.w, b.w, c.w));
+          sts128(pool_u32 + pr * p_rowb + px * ROWB + ((cg ^ (px & 7u)) << 4), hmax3_e16(a.x, b.x, c.x),
+                 hmax3_e16(a.y, b.y, c.y), hmax3_e16(a.z, b.z, c.z), hmax3_e16(a.w, b.w, c.w));
         }
       }
       fence_proxy_async_smem();
@@ -409,11 +410,11 @@ stem_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (relu_only) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              o[i] = pack_relu_bf16x2(__uint_as_float(a[2 * i]) + bias_r[2 * i], __uint_as_float(a[2 * i + 1]) + bias_r[2 * i + 1]);
+              o[i] = pack_relu_e16x2(__uint_as_float(a[2 * i]) + bias_r[2 * i], __uint_as_float(a[2 * i + 1]) + bias_r[2 * i + 1]);
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              o[i] = pack_bf16x2(fminf(fmaxf(__uint_as_float(a[2 * i]) + bias_r[2 * i], act_lo), act_hi),
+              o[i] = pack_e16x2(fminf(fmaxf(__uint_as_float(a[2 * i]) + bias_r[2 * i], act_lo), act_hi),
                                  fminf(fmaxf(__uint_as_float(a[2 * i + 1]) + bias_r[2 * i + 1], act_lo), act_hi));
           }
           if (st_off[k] >= 0 && tile_ok && h0 + st_r[k] < p.Ho) {
@@ -465,12 +466,8 @@ struct StemOp : Op {
 
 template <int BN, int T, bool POOL>
 static cudaError_t launch_stem(const StemOp& op, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(stem_halo_kernel<BN, T, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};   // per device (see runtime.h)
+  if (cudaError_t e = set_max_smem_once(stem_halo_kernel<BN, T, POOL>, 232448, attr_done)) return e;
   return launch_pdl(stem_halo_kernel<BN, T, POOL>, dim3(op.grid), dim3(ST_THREADS), op.smem_bytes, s, op.tmA, op.tmB, op.tmOut,
                     op.p);
 }
@@ -566,7 +563,7 @@ int stem_halo_try_make(const pcv_conv_desc& d, const void* x, const void* w, con
   auto op = std::make_unique<StemOp>();
   StemParams& p = op->p;
   p.bias = bias;
-  p.out = reinterpret_cast<__nv_bfloat16*>(y);
+  p.out = reinterpret_cast<e16*>(y);
   p.out_pitch = out_pitch;
   p.N = d.N; p.Ho = Ho; p.Wo = Wo; p.Cout = d.Cout;
   const int PWK = pool ? ST_POOL_PW : PW;   // pixels per staged A row (the kernel's row pitch)
@@ -598,7 +595,7 @@ int stem_halo_try_make(const pcv_conv_desc& d, const void* x, const void* w, con
     cuuint64_t strides[3] = {ST_ROW, (cuuint64_t)PW * ST_ROW, (cuuint64_t)rows * PW * ST_ROW};
     cuuint32_t box[4] = {16, (cuuint32_t)PWK, (cuuint32_t)(bestR + T - 1), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(&op->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+    CUresult r = fn(&op->tmA, TMAP_E16, 4, const_cast<void*>(x), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled (stem A) failed (%d)", (int)r);
@@ -609,7 +606,7 @@ int stem_halo_try_make(const pcv_conv_desc& d, const void* x, const void* w, con
     cuuint64_t strides[1] = {kpad * 2};
     cuuint32_t box[2] = {16, (cuuint32_t)(BN / 2)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(&op->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+    CUresult r = fn(&op->tmB, TMAP_E16, 2, const_cast<void*>(w), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled (stem B) failed (%d)", (int)r);
@@ -620,7 +617,7 @@ int stem_halo_try_make(const pcv_conv_desc& d, const void* x, const void* w, con
     cuuint64_t strides[3] = {(cuuint64_t)out_pitch * 2, (cuuint64_t)Wy * out_pitch * 2, (cuuint64_t)Hy * Wy * out_pitch * 2};
     cuuint32_t box[4] = {(cuuint32_t)BN, (cuuint32_t)Wy, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(&op->tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, dims, strides, box, estr,
+    CUresult r = fn(&op->tmOut, TMAP_E16, 4, y, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, BN == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled (stem out) failed (%d)", (int)r);
@@ -638,4 +635,5 @@ int stem_halo_try_make(const pcv_conv_desc& d, const void* x, const void* w, con
   return PCV_OK;
 }
 
+}  // namespace PCV_TIER
 }  // namespace pcv

@@ -37,6 +37,16 @@ template <>
 __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <>
+__device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
+template <>
+__device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
 
 // TILE = 64: the throughput shape (4 x 4 register tile per thread).  TILE = 32 (2 x 2 per thread): four times the CTAs
 // for layers whose 64 x 64 grid cannot fill the machine (ResNet-18 at batch 8: 56 CTAs walked K = 4608 on the 7 x 7 maps).
@@ -136,7 +146,7 @@ conv_simt_kernel(const SimtParams p, const T* __restrict__ x, const float* __res
       if (p.out_f32 || sizeof(T) == 4) {
         reinterpret_cast<float*>(y)[o] = v;
       } else {
-        reinterpret_cast<__nv_bfloat16*>(y)[o] = __float2bfloat16(v);
+        reinterpret_cast<T*>(y)[o] = from_f<T>(v);
       }
     }
   }
@@ -147,7 +157,7 @@ conv_simt_kernel(const SimtParams p, const T* __restrict__ x, const float* __res
 __global__ void simt_pack_kernel(const float* __restrict__ w, const float* __restrict__ conv_bias,
                                  const float* __restrict__ g, const float* __restrict__ b,
                                  const float* __restrict__ mean, const float* __restrict__ var, float eps, int Cout,
-                                 int cin_g, int cout_g, int taps, int round_bf16, float* __restrict__ wp,
+                                 int cin_g, int cout_g, int taps, int round16, float* __restrict__ wp,
                                  float* __restrict__ bias_out) {
   const size_t total = static_cast<size_t>(Cout) * cin_g * taps;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -161,7 +171,8 @@ __global__ void simt_pack_kernel(const float* __restrict__ w, const float* __res
     const int o = grp * cout_g + n;
     const float scale = g ? g[o] / sqrtf(var[o] + eps) : 1.f;
     float v = w[(static_cast<size_t>(o) * cin_g + c) * taps + tap] * scale;
-    if (round_bf16) v = __bfloat162float(__float2bfloat16(v));
+    if (round16 == 1) v = __bfloat162float(__float2bfloat16(v));
+    else if (round16 == 2) v = __half2float(__float2half_rn(v));
     wp[idx] = v;
   }
   for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < Cout; o += gridDim.x * blockDim.x) {
@@ -182,7 +193,7 @@ int simt_pack(const pcv_conv_desc& d, int dtype, const float* w, const float* co
   const size_t total = static_cast<size_t>(d.Cout) * (d.Cin / d.groups) * d.kh * d.kw;
   const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 4096));
   simt_pack_kernel<<<blocks, 256, 0, s>>>(w, conv_bias, g, b, m, v, eps, d.Cout, d.Cin / d.groups, d.Cout / d.groups,
-                                          d.kh * d.kw, dtype == PCV_BF16, reinterpret_cast<float*>(w_packed), bias_out);
+                                          d.kh * d.kw, dtype == PCV_BF16 ? 1 : (dtype == PCV_F16 ? 2 : 0), reinterpret_cast<float*>(w_packed), bias_out);
   g_launches++;
   PCV_CHECK_CUDA(cudaGetLastError());
   return PCV_OK;
@@ -204,7 +215,10 @@ struct SimtOp : Op {
       dim3 grid(ceil_div(p.M, 32), ceil_div(p.cout_g, 32), p.groups);
       if (dtype == PCV_F32)
         conv_simt_kernel<float, 32><<<grid, 256, 0, s>>>(p, (const float*)x, w, bias, (const float*)res, y);
-      else
+      else if (dtype == PCV_F16)
+        conv_simt_kernel<__half, 32><<<grid, 256, 0, s>>>(p, (const __half*)x, w, bias,
+                                                                 (const __half*)res, y);
+    else
         conv_simt_kernel<__nv_bfloat16, 32><<<grid, 256, 0, s>>>(p, (const __nv_bfloat16*)x, w, bias,
                                                                  (const __nv_bfloat16*)res, y);
       return cudaGetLastError();
@@ -212,6 +226,9 @@ struct SimtOp : Op {
     dim3 grid(ceil_div(p.M, 64), ceil_div(p.cout_g, 64), p.groups);
     if (dtype == PCV_F32)
       conv_simt_kernel<float, 64><<<grid, 256, 0, s>>>(p, (const float*)x, w, bias, (const float*)res, y);
+    else if (dtype == PCV_F16)
+      conv_simt_kernel<__half, 64><<<grid, 256, 0, s>>>(p, (const __half*)x, w, bias,
+                                                               (const __half*)res, y);
     else
       conv_simt_kernel<__nv_bfloat16, 64><<<grid, 256, 0, s>>>(p, (const __nv_bfloat16*)x, w, bias,
                                                                (const __nv_bfloat16*)res, y);
@@ -238,7 +255,7 @@ int simt_make(const pcv_conv_desc& d, int dtype, const void* x, const void* w, c
   PCV_REQUIRE(ceil_div(p.cout_g, 32) <= 65535 && p.groups <= 65535, "grid too large for the CUDA-core conv");
   op->dtype = dtype; op->x = x; op->w = reinterpret_cast<const float*>(w); op->bias = bias; op->res = res; op->y = y;
   char nm[160];
-  snprintf(nm, sizeof nm, "conv_simt_%s %dx%d s%d d%d g%d %d->%d @%dx%d%s", dtype == PCV_F32 ? "f32" : "bf16", d.kh,
+  snprintf(nm, sizeof nm, "conv_simt_%s %dx%d s%d d%d g%d %d->%d @%dx%d%s", dtype_name(dtype), d.kh,
            d.kw, d.stride, d.dil, d.groups, d.Cin, d.Cout, d.H, d.W, res ? " +res" : "");
   op->name = nm;
   const double e = esize(dtype);

@@ -49,6 +49,20 @@ struct Vec8<__nv_bfloat16> {
   }
 };
 template <>
+struct Vec8<__half> {
+  static __device__ __forceinline__ void load(const __half* p, float (&f)[8]) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    f[0] = f16lo(v.x); f[1] = f16hi(v.x); f[2] = f16lo(v.y); f[3] = f16hi(v.y);
+    f[4] = f16lo(v.z); f[5] = f16hi(v.z); f[6] = f16lo(v.w); f[7] = f16hi(v.w);
+  }
+  static __device__ __forceinline__ void store(__half* p, const float (&f)[8]) {
+    uint4 v;
+    v.x = pack_f16x2(f[0], f[1]); v.y = pack_f16x2(f[2], f[3]);
+    v.z = pack_f16x2(f[4], f[5]); v.w = pack_f16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = v;
+  }
+};
+template <>
 struct Vec8<float> {
   static __device__ __forceinline__ void load(const float* p, float (&f)[8]) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(p));
@@ -187,13 +201,14 @@ dwconv_generic_kernel(const DwParams p, const T* __restrict__ x, const float* __
 __global__ void dw_pack_kernel(const float* __restrict__ w, const float* __restrict__ conv_bias,
                                const float* __restrict__ g, const float* __restrict__ b,
                                const float* __restrict__ mean, const float* __restrict__ var, float eps, int C,
-                               int taps, int round_bf16, float* __restrict__ wp, float* __restrict__ bias_out) {
+                               int taps, int round16, float* __restrict__ wp, float* __restrict__ bias_out) {
   const int total = C * taps;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int c = idx % C, tap = idx / C;
     const float scale = g ? g[c] / sqrtf(var[c] + eps) : 1.f;
     float v = w[c * taps + tap] * scale;
-    if (round_bf16) v = __bfloat162float(__float2bfloat16(v));
+    if (round16 == 1) v = __bfloat162float(__float2bfloat16(v));   // weights carry the tier's storage precision
+    else if (round16 == 2) v = __half2float(__float2half_rn(v));
     wp[idx] = v;
   }
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
@@ -212,7 +227,7 @@ int dw_pack(const pcv_conv_desc& d, int dtype, const float* w, const float* conv
             const float* m, const float* v, float eps, void* w_packed, float* bias_out, cudaStream_t s) {
   const int total = d.Cout * d.kh * d.kw;
   dw_pack_kernel<<<ceil_div(total, 256), 256, 0, s>>>(w, conv_bias, g, b, m, v, eps, d.Cout, d.kh * d.kw,
-                                                      dtype == PCV_BF16, reinterpret_cast<float*>(w_packed), bias_out);
+                                                      dtype == PCV_BF16 ? 1 : (dtype == PCV_F16 ? 2 : 0), reinterpret_cast<float*>(w_packed), bias_out);
   g_launches++;
   PCV_CHECK_CUDA(cudaGetLastError());
   return PCV_OK;
@@ -254,7 +269,7 @@ struct DwOp : Op {
   }
   cudaError_t launch(cudaStream_t s) override {
     g_launches++;
-    return dtype == PCV_F32 ? run<float>(s) : run<__nv_bfloat16>(s);
+    return dtype == PCV_F32 ? run<float>(s) : (dtype == PCV_F16 ? run<__half>(s) : run<__nv_bfloat16>(s));
   }
 };
 
@@ -267,15 +282,15 @@ int dw_make(const pcv_conv_desc& d, int dtype, const void* x, const void* w, con
   const double M = static_cast<double>(d.N) * Ho_ * Wo_;
   const double flops = 2.0 * M * d.Cout * d.kh * d.kw;
   const double bytes = e * d.N * d.Cin * d.H * d.W + e * M * d.Cout * (res ? 2.0 : 1.0) + 4.0 * d.Cout * d.kh * d.kw + 4.0 * d.Cout;
-  if (dtype == PCV_BF16 && d.dil == 1) {
+  if (is16(dtype) && d.dil == 1) {
     // TMA halo-staged kernel (window_tma.cu) for the 3x3 stride-1/2 layers of the MobileNet family
     Op* wop = nullptr;
-    const int rc = win_make(0, d.N, d.H, d.W, d.Cout, d.kh, d.stride, d.pad, d.act, x, pitch_or(d.in_pitch, d.Cin),
+    const int rc = (dtype == PCV_F16 ? hf::win_make : bf::win_make)(0, d.N, d.H, d.W, d.Cout, d.kh, d.stride, d.pad, d.act, x, pitch_or(d.in_pitch, d.Cin),
                             reinterpret_cast<const float*>(w), bias, res, pitch_or(d.res_pitch, d.Cout), y,
                             pitch_or(d.out_pitch, d.Cout), &wop);
     if (rc == PCV_OK) {
-      snprintf(nm, sizeof nm, "dwconv_tma_bf16 %dx%d s%d d%d C=%d @%dx%d%s", d.kh, d.kw, d.stride, d.dil, d.Cout, d.H,
-               d.W, res ? " +res" : "");
+      snprintf(nm, sizeof nm, "dwconv_tma_%s %dx%d s%d d%d C=%d @%dx%d%s", dtype_name(dtype), d.kh, d.kw, d.stride, d.dil,
+               d.Cout, d.H, d.W, res ? " +res" : "");
       wop->name = nm; wop->flops = flops; wop->bytes = bytes;
       *out = wop;
       return PCV_OK;
@@ -297,7 +312,7 @@ int dw_make(const pcv_conv_desc& d, int dtype, const void* x, const void* w, con
   p.act = d.act;
   p.strips = 0;
   op->dtype = dtype; op->x = x; op->w = reinterpret_cast<const float*>(w); op->bias = bias; op->res = res; op->y = y;
-  snprintf(nm, sizeof nm, "dwconv_%s %dx%d s%d d%d C=%d @%dx%d%s", dtype == PCV_F32 ? "f32" : "bf16", d.kh, d.kw,
+  snprintf(nm, sizeof nm, "dwconv_%s %dx%d s%d d%d C=%d @%dx%d%s", dtype_name(dtype), d.kh, d.kw,
            d.stride, d.dil, d.Cout, d.H, d.W, res ? " +res" : "");
   op->name = nm;
   op->flops = flops;

@@ -4,6 +4,7 @@
 #include "runtime.h"
 
 namespace pcv {
+namespace PCV_TIER {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
@@ -14,7 +15,7 @@ constexpr int EPI_THREADS = 128;
 struct IgemmParams {
   const float* bias;          // [round_up(Cout,128)] folded BN bias
   void* out;                  // direct-store modes only
-  const __nv_bfloat16* res;   // direct-store modes only
+  const e16* res;   // direct-store modes only
   int M, Cout;
   int out_pitch, res_pitch;
   int HoWo, Wo;
@@ -45,8 +46,7 @@ int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const 
 int stem_halo_try_make(const pcv_conv_desc& d, const void* x, const void* w, const float* bias, const void* res,
                        void* y, Op** out);
 
-int stem_pool_ok(int C, int H, int W, int k, int Cout);
-
 void igemm2_pick_smem(int bn, int num_kblocks, bool has_res, int taps, int* stages, int* ksub, int* nstg);
 
+}  // namespace PCV_TIER
 }  // namespace pcv

@@ -2,7 +2,6 @@
 // All NHWC with 8-channel (16-byte bf16) vectors per lane; consecutive lanes own consecutive channel vectors.
 #include "ptx.cuh"
 #include "runtime.h"
-#include "igemm_common.cuh"
 
 namespace pcv {
 
@@ -35,6 +34,22 @@ struct V8<__nv_bfloat16> {
   }
   static __device__ __forceinline__ float ld1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
   static __device__ __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+};
+template <>
+struct V8<__half> {
+  static __device__ __forceinline__ void load(const __half* p, float (&f)[8]) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    f[0] = f16lo(v.x); f[1] = f16hi(v.x); f[2] = f16lo(v.y); f[3] = f16hi(v.y);
+    f[4] = f16lo(v.z); f[5] = f16hi(v.z); f[6] = f16lo(v.w); f[7] = f16hi(v.w);
+  }
+  static __device__ __forceinline__ void store(__half* p, const float (&f)[8]) {
+    uint4 v;
+    v.x = pack_f16x2(f[0], f[1]); v.y = pack_f16x2(f[2], f[3]);
+    v.z = pack_f16x2(f[4], f[5]); v.w = pack_f16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = v;
+  }
+  static __device__ __forceinline__ float ld1(const __half* p) { return __half2float(*p); }
+  static __device__ __forceinline__ void st1(__half* p, float v) { *p = __float2half_rn(v); }
 };
 template <>
 struct V8<float> {
@@ -100,6 +115,9 @@ struct MaxPoolOp : Op {
     if (dtype == PCV_F32)
       maxpool_kernel<float><<<grid, 256, 0, s>>>(N, H, W, C, Ho, Wo, k, stride, pad, (const float*)x, in_pitch,
                                                  (float*)y, out_pitch);
+    else if (dtype == PCV_F16)
+      maxpool_kernel<__half><<<grid, 256, 0, s>>>(N, H, W, C, Ho, Wo, k, stride, pad, (const __half*)x,
+                                                         in_pitch, (__half*)y, out_pitch);
     else
       maxpool_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(N, H, W, C, Ho, Wo, k, stride, pad, (const __nv_bfloat16*)x,
                                                          in_pitch, (__nv_bfloat16*)y, out_pitch);
@@ -172,6 +190,7 @@ struct GapOp : Op {
     while (slab > 64 && (slab > C || static_cast<long long>(N) * ceil_div(C, slab) < 4ll * sm_count())) slab >>= 1;
     dim3 grid(ceil_div(C, slab), N);
     if (dtype == PCV_F32) gap_kernel<float><<<grid, 256, 0, s>>>(HW, C, slab, (const float*)x, in_pitch, out, out_f32);
+    else if (dtype == PCV_F16) gap_kernel<__half><<<grid, 256, 0, s>>>(HW, C, slab, (const __half*)x, in_pitch, out, out_f32);
     else gap_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(HW, C, slab, (const __nv_bfloat16*)x, in_pitch, out, out_f32);
     return cudaGetLastError();
   }
@@ -229,6 +248,8 @@ struct AdaptivePoolOp : Op {
     dim3 grid(OH * OW, ceil_div(C, 256), N);
     if (dtype == PCV_F32)
       adaptive_avgpool_kernel<float><<<grid, 256, 0, s>>>(H, W, C, OH, OW, (const float*)x, in_pitch, (float*)y);
+    else if (dtype == PCV_F16)
+      adaptive_avgpool_kernel<__half><<<grid, 256, 0, s>>>(H, W, C, OH, OW, (const __half*)x, in_pitch, (__half*)y);
     else
       adaptive_avgpool_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(H, W, C, OH, OW, (const __nv_bfloat16*)x, in_pitch, (__nv_bfloat16*)y);
     return cudaGetLastError();
@@ -380,11 +401,9 @@ struct SeExciteOp : Op {
     const bool aligned = ((reinterpret_cast<uintptr_t>(pooled) | reinterpret_cast<uintptr_t>(w1) |
                            reinterpret_cast<uintptr_t>(w2) | reinterpret_cast<uintptr_t>(mid)) & 15) == 0;
     if (C % 4 == 0 && Cmid % 4 == 0 && smem1 <= 200 * 1024 && aligned && N <= 65535 * IMGS) {
-      static size_t attr = 48 * 1024;
-      if (smem1 > attr) {
-        cudaError_t e = cudaFuncSetAttribute(se_fc1_kernel<IMGS, JPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        attr = 200 * 1024;
+      if (smem1 > 48 * 1024) {
+        static std::atomic<uint64_t> attr_done{0};   // per device (see runtime.h)
+        if (cudaError_t e = set_max_smem_once(se_fc1_kernel<IMGS, JPW>, 200 * 1024, attr_done)) return e;
       }
       se_fc1_kernel<IMGS, JPW><<<dim3(ceil_div(N, IMGS), ceil_div(Cmid, 8 * JPW)), 256, smem1, s>>>(N, C, Cmid, pooled, w1, b1, mid_act, mid);
       se_fc2_kernel<IMGS><<<dim3(ceil_div(N, IMGS), ceil_div(C, 256)), 256, smem2, s>>>(N, C, Cmid, mid, w2, b2, out_act, gate);
@@ -437,6 +456,9 @@ struct SeScaleOp : Op {
     const int grid = grid_for(vecs);
     if (dtype == PCV_F32)
       se_scale_kernel<float><<<grid, 256, 0, s>>>(HW, C, vecs, (const float*)x, gate, (const float*)idn, act, (float*)y);
+    else if (dtype == PCV_F16)
+      se_scale_kernel<__half><<<grid, 256, 0, s>>>(HW, C, vecs, (const __half*)x, gate,
+                                                          (const __half*)idn, act, (__half*)y);
     else
       se_scale_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(HW, C, vecs, (const __nv_bfloat16*)x, gate,
                                                           (const __nv_bfloat16*)idn, act, (__nv_bfloat16*)y);
@@ -467,6 +489,8 @@ struct AddActOp : Op {
     g_launches++;
     const int grid = grid_for(vecs);
     if (dtype == PCV_F32) add_act_kernel<float><<<grid, 256, 0, s>>>(vecs, (const float*)a, (const float*)b, act, (float*)y);
+    else if (dtype == PCV_F16) add_act_kernel<__half><<<grid, 256, 0, s>>>(vecs, (const __half*)a, (const __half*)b, act,
+                                                             (__half*)y);
     else add_act_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(vecs, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, act,
                                                              (__nv_bfloat16*)y);
     return cudaGetLastError();
@@ -476,10 +500,73 @@ struct AddActOp : Op {
 // ---------------------------------------------------------------------------------------------------------------
 // layout edges: NCHW fp32 <-> NHWC T
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T>
+// Image element types the network edge accepts (include/pcv_b200.h pcv_image_type): the reference's fp32 NCHW tensor, or
+// a 16-bit / 8-bit copy of it (half / a quarter of the host->device bytes).  value = float(x) * scale[c] + bias[c].
+template <typename TI>
+struct Img;
+template <>
+struct Img<float> {
+  static __device__ __forceinline__ float ld1(const float* p) { return *p; }
+  static __device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+  static __device__ __forceinline__ float4 ld4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+};
+template <>
+struct Img<__nv_bfloat16> {
+  static __device__ __forceinline__ float ld1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ float2 ld2(const __nv_bfloat16* p) {
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(p);
+    return make_float2(bf16lo(v), bf16hi(v));
+  }
+  static __device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+    const uint2 v = __ldcs(reinterpret_cast<const uint2*>(p));
+    return make_float4(bf16lo(v.x), bf16hi(v.x), bf16lo(v.y), bf16hi(v.y));
+  }
+};
+template <>
+struct Img<__half> {
+  static __device__ __forceinline__ float ld1(const __half* p) { return __half2float(*p); }
+  static __device__ __forceinline__ float2 ld2(const __half* p) {
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(p);
+    return make_float2(f16lo(v), f16hi(v));
+  }
+  static __device__ __forceinline__ float4 ld4(const __half* p) {
+    const uint2 v = __ldcs(reinterpret_cast<const uint2*>(p));
+    return make_float4(f16lo(v.x), f16hi(v.x), f16lo(v.y), f16hi(v.y));
+  }
+};
+template <>
+struct Img<uint8_t> {
+  static __device__ __forceinline__ float ld1(const uint8_t* p) { return static_cast<float>(*p); }
+  static __device__ __forceinline__ float2 ld2(const uint8_t* p) {
+    const uint16_t v = *reinterpret_cast<const uint16_t*>(p);
+    return make_float2(static_cast<float>(v & 0xFF), static_cast<float>(v >> 8));
+  }
+  static __device__ __forceinline__ float4 ld4(const uint8_t* p) {
+    const uint32_t v = __ldcs(reinterpret_cast<const uint32_t*>(p));
+    return make_float4(static_cast<float>(v & 0xFF), static_cast<float>((v >> 8) & 0xFF),
+                       static_cast<float>((v >> 16) & 0xFF), static_cast<float>(v >> 24));
+  }
+};
+struct ImgAffine {   // per-channel value = x * scale + bias for the first 4 channels (identity beyond)
+  float scale[4], bias[4];
+};
+static inline size_t img_esize(int img_type) { return img_type == PCV_IMG_F32 ? 4 : (img_type == PCV_IMG_U8 ? 1 : 2); }
+static inline const char* img_name(int img_type) {
+  return img_type == PCV_IMG_F32 ? "f32" : (img_type == PCV_IMG_U8 ? "u8" : (img_type == PCV_IMG_F16 ? "f16" : "bf16"));
+}
+static inline ImgAffine make_affine(int C, const float* scale_host, const float* bias_host) {
+  ImgAffine af;
+  for (int c = 0; c < 4; ++c) {
+    af.scale[c] = (scale_host && c < C) ? scale_host[c] : 1.f;
+    af.bias[c] = (bias_host && c < C) ? bias_host[c] : 0.f;
+  }
+  return af;
+}
+
+
+template <typename TI, typename T>
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_kernel(int N, int C, int HW, int c_pitch, const float* __restrict__ x, T* __restrict__ y) {
-  // thread = (pixel, 8-channel vector); pixel-fastest so the NCHW plane reads are coalesced
+nchw_to_nhwc_kernel(int N, int C, int HW, int c_pitch, const TI* __restrict__ x, T* __restrict__ y, ImgAffine af) {
   const int cvecs = c_pitch >> 3;
   const long long total = static_cast<long long>(N) * cvecs * HW;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -492,7 +579,9 @@ nchw_to_nhwc_kernel(int N, int C, int HW, int c_pitch, const float* __restrict__
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = cv * 8 + e;
-      v[e] = c < C ? x[(static_cast<size_t>(n) * C + c) * HW + p] : 0.f;
+      float t = c < C ? Img<TI>::ld1(x + (static_cast<size_t>(n) * C + c) * HW + p) : 0.f;
+      if (c < 4 && c < C) t = fmaf(t, af.scale[c], af.bias[c]);
+      v[e] = t;
     }
     V8<T>::store(y + (static_cast<size_t>(n) * HW + p) * c_pitch + cv * 8, v);
   }
@@ -513,18 +602,30 @@ nhwc_to_nchw_kernel(int N, int C, int HW, int c_pitch, const T* __restrict__ x, 
 }
 
 struct LayoutOp : Op {
-  int dtype, N, C, HW, c_pitch, to_nhwc;
+  int dtype, N, C, HW, c_pitch, to_nhwc, img_type = PCV_IMG_F32;
+  ImgAffine af;
   const void* x;
   void* y;
+  template <typename TI>
+  void ingest(int grid, cudaStream_t s) {
+    if (dtype == PCV_F32) nchw_to_nhwc_kernel<TI, float><<<grid, 256, 0, s>>>(N, C, HW, c_pitch, (const TI*)x, (float*)y, af);
+    else if (dtype == PCV_F16) nchw_to_nhwc_kernel<TI, __half><<<grid, 256, 0, s>>>(N, C, HW, c_pitch, (const TI*)x, (__half*)y, af);
+    else nchw_to_nhwc_kernel<TI, __nv_bfloat16><<<grid, 256, 0, s>>>(N, C, HW, c_pitch, (const TI*)x, (__nv_bfloat16*)y, af);
+  }
   cudaError_t launch(cudaStream_t s) override {
     g_launches++;
     if (to_nhwc) {
       const int grid = grid_for(static_cast<long long>(N) * (c_pitch >> 3) * HW);
-      if (dtype == PCV_F32) nchw_to_nhwc_kernel<float><<<grid, 256, 0, s>>>(N, C, HW, c_pitch, (const float*)x, (float*)y);
-      else nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(N, C, HW, c_pitch, (const float*)x, (__nv_bfloat16*)y);
+      switch (img_type) {
+        case PCV_IMG_BF16: ingest<__nv_bfloat16>(grid, s); break;
+        case PCV_IMG_F16: ingest<__half>(grid, s); break;
+        case PCV_IMG_U8: ingest<uint8_t>(grid, s); break;
+        default: ingest<float>(grid, s); break;
+      }
     } else {
       const int grid = grid_for(static_cast<long long>(N) * C * HW);
       if (dtype == PCV_F32) nhwc_to_nchw_kernel<float><<<grid, 256, 0, s>>>(N, C, HW, c_pitch, (const float*)x, (float*)y);
+      else if (dtype == PCV_F16) nhwc_to_nchw_kernel<__half><<<grid, 256, 0, s>>>(N, C, HW, c_pitch, (const __half*)x, (float*)y);
       else nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(N, C, HW, c_pitch, (const __nv_bfloat16*)x, (float*)y);
     }
     return cudaGetLastError();
@@ -676,13 +777,18 @@ struct BilinearOp : Op {
       const size_t smem = static_cast<size_t>(C) * (Win + 2) * sizeof(float);
       if (dtype == PCV_F32)
         bilinear_nchw_rows_kernel<float><<<dim3(Hout, N), 256, smem, s>>>(Hin, Win, C, (const float*)x, in_pitch, Hout, Wout, (float*)y, sh, sw);
-      else
+      else if (dtype == PCV_F16)
+        bilinear_nchw_rows_kernel<__half><<<dim3(Hout, N), 256, smem, s>>>(Hin, Win, C, (const __half*)x, in_pitch, Hout, Wout, (float*)y, sh, sw);
+    else
         bilinear_nchw_rows_kernel<__nv_bfloat16><<<dim3(Hout, N), 256, smem, s>>>(Hin, Win, C, (const __nv_bfloat16*)x, in_pitch, Hout, Wout, (float*)y, sh, sw);
     } else if (nchw) {
       const int grid = grid_for(static_cast<long long>(N) * C * Hout * Wout);
       if (dtype == PCV_F32)
         bilinear_nchw_kernel<float><<<grid, 256, 0, s>>>(N, Hin, Win, C, (const float*)x, in_pitch, Hout, Wout, (float*)y, sh, sw);
-      else
+      else if (dtype == PCV_F16)
+        bilinear_nchw_kernel<__half><<<grid, 256, 0, s>>>(N, Hin, Win, C, (const __half*)x, in_pitch, Hout,
+                                                                 Wout, (float*)y, sh, sw);
+    else
         bilinear_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(N, Hin, Win, C, (const __nv_bfloat16*)x, in_pitch, Hout,
                                                                  Wout, (float*)y, sh, sw);
     } else {
@@ -690,7 +796,10 @@ struct BilinearOp : Op {
       if (dtype == PCV_F32)
         bilinear_nhwc_kernel<float><<<grid, 256, 0, s>>>(N, Hin, Win, C, (const float*)x, in_pitch, Hout, Wout, (float*)y,
                                                          out_pitch, sh, sw);
-      else
+      else if (dtype == PCV_F16)
+        bilinear_nhwc_kernel<__half><<<grid, 256, 0, s>>>(N, Hin, Win, C, (const __half*)x, in_pitch, Hout,
+                                                                 Wout, (__half*)y, out_pitch, sh, sw);
+    else
         bilinear_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(N, Hin, Win, C, (const __nv_bfloat16*)x, in_pitch, Hout,
                                                                  Wout, (__nv_bfloat16*)y, out_pitch, sh, sw);
     }
@@ -702,8 +811,8 @@ struct BilinearOp : Op {
 
 using namespace pcv;
 
-static const char* dn(int dtype) { return dtype == PCV_F32 ? "f32" : "bf16"; }
-#define PCV_DTYPE_OK(dt) PCV_REQUIRE((dt) == PCV_BF16 || (dt) == PCV_F32, "unknown dtype %d", (dt))
+static const char* dn(int dtype) { return dtype_name(dtype); }
+#define PCV_DTYPE_OK(dt) PCV_REQUIRE((dt) == PCV_BF16 || (dt) == PCV_F32 || (dt) == PCV_F16, "unknown dtype %d", (dt))
 
 extern "C" {
 
@@ -715,13 +824,13 @@ int pcv_maxpool2d(pcv_plan* plan, int dtype, int N, int H, int W, int C, int k, 
   in_pitch = pitch_or(in_pitch, C);
   out_pitch = pitch_or(out_pitch, C);
   PCV_REQUIRE(C % 8 == 0 && in_pitch % 8 == 0 && out_pitch % 8 == 0, "maxpool needs channel counts/pitches % 8 == 0");
-  if (dtype == PCV_BF16) {
+  if (is16(dtype)) {
     Op* wop = nullptr;
-    const int rc = win_make(1, N, H, W, C, k, stride, pad, PCV_ACT_NONE, x, in_pitch, nullptr, nullptr, nullptr, 0, y,
+    const int rc = (dtype == PCV_F16 ? hf::win_make : bf::win_make)(1, N, H, W, C, k, stride, pad, PCV_ACT_NONE, x, in_pitch, nullptr, nullptr, nullptr, 0, y,
                             out_pitch, &wop);
     if (rc == PCV_OK) {
       char nm[96];
-      snprintf(nm, sizeof nm, "maxpool_tma_bf16 %dx%d s%d C=%d @%dx%d", k, k, stride, C, H, W);
+      snprintf(nm, sizeof nm, "maxpool_tma_%s %dx%d s%d C=%d @%dx%d", dn(dtype), k, k, stride, C, H, W);
       wop->name = nm;
       const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
       wop->bytes = 2.0 * static_cast<double>(N) * C * (static_cast<double>(H) * W + static_cast<double>(Ho) * Wo);
@@ -823,19 +932,26 @@ int pcv_add_act(pcv_plan* plan, int dtype, size_t count, const void* a, const vo
   return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
 }
 
-int pcv_nchw_f32_to_nhwc(pcv_plan* plan, int dtype, int N, int C, int H, int W, const float* x, void* y, int c_pitch,
-                         pcv_stream stream) {
+int pcv_nchw_to_nhwc_ex(pcv_plan* plan, int dtype, int img_type, int N, int C, int H, int W, const void* x,
+                        const float* scale_host, const float* bias_host, void* y, int c_pitch, pcv_stream stream) {
   PCV_DTYPE_OK(dtype);
+  PCV_REQUIRE(img_type >= PCV_IMG_F32 && img_type <= PCV_IMG_U8, "unknown image type %d", img_type);
   PCV_REQUIRE(x && y, "NULL tensor pointer");
   c_pitch = pitch_or(c_pitch, round_up(C, 8));
   PCV_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && c_pitch >= C && c_pitch % 8 == 0, "bad ingest dims");
   auto op = std::make_unique<LayoutOp>();
   op->dtype = dtype; op->N = N; op->C = C; op->HW = H * W; op->c_pitch = c_pitch; op->to_nhwc = 1; op->x = x; op->y = y;
+  op->img_type = img_type; op->af = make_affine(C, scale_host, bias_host);
   char nm[96];
-  snprintf(nm, sizeof nm, "ingest_nchw_f32_to_nhwc_%s C=%d->%d @%dx%d", dn(dtype), C, c_pitch, H, W);
+  snprintf(nm, sizeof nm, "ingest_nchw_%s_to_nhwc_%s C=%d->%d @%dx%d", img_name(img_type), dn(dtype), C, c_pitch, H, W);
   op->name = nm;
-  op->bytes = static_cast<double>(N) * H * W * (4.0 * C + esize(dtype) * c_pitch);
+  op->bytes = static_cast<double>(N) * H * W * (static_cast<double>(img_esize(img_type)) * C + esize(dtype) * c_pitch);
   return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
+}
+
+int pcv_nchw_f32_to_nhwc(pcv_plan* plan, int dtype, int N, int C, int H, int W, const float* x, void* y, int c_pitch,
+                         pcv_stream stream) {
+  return pcv_nchw_to_nhwc_ex(plan, dtype, PCV_IMG_F32, N, C, H, W, x, nullptr, nullptr, y, c_pitch, stream);
 }
 
 int pcv_nhwc_to_nchw_f32(pcv_plan* plan, int dtype, int N, int C, int H, int W, const void* x, int c_pitch, float* y,
@@ -893,9 +1009,17 @@ static inline S2dGeom s2d_geom(int H, int W, int k) {
   return g;
 }
 
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) { return pack_bf16x2(lo, hi); }
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) { return pack_f16x2(lo, hi); }
+
+template <typename TI, typename T>
 __global__ void __launch_bounds__(256)
-s2d_ingest_kernel(int N, int C, int H, int W, int pad_lo, int rows, int cols, const float* __restrict__ x,
-                  __nv_bfloat16* __restrict__ y) {
+s2d_ingest_kernel(int N, int C, int H, int W, int pad_lo, int rows, int cols, const TI* __restrict__ x,
+                  T* __restrict__ y, ImgAffine af) {
   const int Hb = H >> 1, Wb = W >> 1;
   const long long total = static_cast<long long>(N) * Hb * Wb;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -907,10 +1031,13 @@ s2d_ingest_kernel(int N, int C, int H, int W, int pad_lo, int rows, int cols, co
     float v[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) v[e] = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const float* px = x + ((static_cast<size_t>(n) * C + c) * H + 2 * hb) * W + 2 * wb;
-      const float2 top = *reinterpret_cast<const float2*>(px);
-      const float2 bot = *reinterpret_cast<const float2*>(px + W);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c >= C) break;
+      const TI* px = x + ((static_cast<size_t>(n) * C + c) * H + 2 * hb) * W + 2 * wb;
+      float2 top = Img<TI>::ld2(px), bot = Img<TI>::ld2(px + W);
+      top.x = fmaf(top.x, af.scale[c], af.bias[c]); top.y = fmaf(top.y, af.scale[c], af.bias[c]);
+      bot.x = fmaf(bot.x, af.scale[c], af.bias[c]); bot.y = fmaf(bot.y, af.scale[c], af.bias[c]);
       // channel = (dy*2+dx)*C + c ; C <= 4 so the index is < 16 (static indexing keeps v[] in registers)
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
@@ -921,20 +1048,21 @@ s2d_ingest_kernel(int N, int C, int H, int W, int pad_lo, int rows, int cols, co
       }
     }
     uint4 lo, hi;
-    lo.x = pack_bf16x2(v[0], v[1]); lo.y = pack_bf16x2(v[2], v[3]); lo.z = pack_bf16x2(v[4], v[5]); lo.w = pack_bf16x2(v[6], v[7]);
-    hi.x = pack_bf16x2(v[8], v[9]); hi.y = pack_bf16x2(v[10], v[11]); hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
+    lo.x = pack2<T>(v[0], v[1]); lo.y = pack2<T>(v[2], v[3]); lo.z = pack2<T>(v[4], v[5]); lo.w = pack2<T>(v[6], v[7]);
+    hi.x = pack2<T>(v[8], v[9]); hi.y = pack2<T>(v[10], v[11]); hi.z = pack2<T>(v[12], v[13]); hi.w = pack2<T>(v[14], v[15]);
     uint4* dst = reinterpret_cast<uint4*>(y + ((static_cast<size_t>(n) * rows + hb + pad_lo) * cols + wb + pad_lo) * 16);
     dst[0] = lo;
     dst[1] = hi;
   }
 }
 
-// Two s2d pixels (four image columns) per thread: 16-byte loads (a warp reads 512 contiguous bytes of each image row),
-// 64 contiguous output bytes per thread, 32-bit index arithmetic.  C == 3 or 4, W % 4 == 0, x 16-byte aligned.
-template <int C>
+// Two s2d pixels (four image columns) per thread: one 16-byte (fp32) / 8-byte (16-bit) / 4-byte (u8) load per image row
+// and channel - a warp reads 128 contiguous pixels of each row - 64 contiguous output bytes per thread, 32-bit index
+// arithmetic.  C == 3 or 4, W % 4 == 0, x aligned to 4 pixels.
+template <int C, typename TI, typename T>
 __global__ void __launch_bounds__(256)
-s2d_ingest2_kernel(int N, int H, int W, int pad_lo, int rows, int cols, const float* __restrict__ x,
-                   __nv_bfloat16* __restrict__ y) {
+s2d_ingest2_kernel(int N, int H, int W, int pad_lo, int rows, int cols, const TI* __restrict__ x, T* __restrict__ y,
+                   ImgAffine af) {
   const int Hb = H >> 1, Wq = W >> 2;
   const int total = N * Hb * Wq;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -945,9 +1073,12 @@ s2d_ingest2_kernel(int N, int H, int W, int pad_lo, int rows, int cols, const fl
     float4 top[C], bot[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const float* px = x + ((static_cast<size_t>(n) * C + c) * H + 2 * hb) * W + 4 * wq;
-      top[c] = __ldcs(reinterpret_cast<const float4*>(px));       // the image is read exactly once
-      bot[c] = __ldcs(reinterpret_cast<const float4*>(px + W));
+      const TI* px = x + ((static_cast<size_t>(n) * C + c) * H + 2 * hb) * W + 4 * wq;
+      top[c] = Img<TI>::ld4(px);       // the image is read exactly once
+      bot[c] = Img<TI>::ld4(px + W);
+      const float sc = af.scale[c], bi = af.bias[c];
+      top[c].x = fmaf(top[c].x, sc, bi); top[c].y = fmaf(top[c].y, sc, bi); top[c].z = fmaf(top[c].z, sc, bi); top[c].w = fmaf(top[c].w, sc, bi);
+      bot[c].x = fmaf(bot[c].x, sc, bi); bot[c].y = fmaf(bot[c].y, sc, bi); bot[c].z = fmaf(bot[c].z, sc, bi); bot[c].w = fmaf(bot[c].w, sc, bi);
     }
     // s2d channel = (dy*2+dx)*C + c, zero padded to 16
     float a[16], b[16];
@@ -959,10 +1090,10 @@ s2d_ingest2_kernel(int N, int H, int W, int pad_lo, int rows, int cols, const fl
       b[0 * C + c] = top[c].z; b[1 * C + c] = top[c].w; b[2 * C + c] = bot[c].z; b[3 * C + c] = bot[c].w;
     }
     uint4* dst = reinterpret_cast<uint4*>(y + ((static_cast<size_t>(n) * rows + hb + pad_lo) * cols + 2 * wq + pad_lo) * 16);
-    dst[0] = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
-    dst[1] = make_uint4(pack_bf16x2(a[8], a[9]), pack_bf16x2(a[10], a[11]), pack_bf16x2(a[12], a[13]), pack_bf16x2(a[14], a[15]));
-    dst[2] = make_uint4(pack_bf16x2(b[0], b[1]), pack_bf16x2(b[2], b[3]), pack_bf16x2(b[4], b[5]), pack_bf16x2(b[6], b[7]));
-    dst[3] = make_uint4(pack_bf16x2(b[8], b[9]), pack_bf16x2(b[10], b[11]), pack_bf16x2(b[12], b[13]), pack_bf16x2(b[14], b[15]));
+    dst[0] = make_uint4(pack2<T>(a[0], a[1]), pack2<T>(a[2], a[3]), pack2<T>(a[4], a[5]), pack2<T>(a[6], a[7]));
+    dst[1] = make_uint4(pack2<T>(a[8], a[9]), pack2<T>(a[10], a[11]), pack2<T>(a[12], a[13]), pack2<T>(a[14], a[15]));
+    dst[2] = make_uint4(pack2<T>(b[0], b[1]), pack2<T>(b[2], b[3]), pack2<T>(b[4], b[5]), pack2<T>(b[6], b[7]));
+    dst[3] = make_uint4(pack2<T>(b[8], b[9]), pack2<T>(b[10], b[11]), pack2<T>(b[12], b[13]), pack2<T>(b[14], b[15]));
   }
 }
 
@@ -986,22 +1117,36 @@ __global__ void s2d_weight_kernel(int Cout, int C, int k, int kb, int delta, con
 }
 
 struct S2dIngestOp : Op {
-  int N, C, H, W;
+  int N, C, H, W, dtype, img_type;
   S2dGeom g;
-  const float* x;
-  __nv_bfloat16* y;
-  cudaError_t launch(cudaStream_t s) override {
-    g_launches++;
+  ImgAffine af;
+  const void* x;
+  void* y;
+  template <typename TI, typename T>
+  cudaError_t run(cudaStream_t s) {
     const long long quads = static_cast<long long>(N) * (H / 2) * (W / 4);
-    if ((C == 3 || C == 4) && W % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && quads < (1ll << 30)) {
+    const TI* xi = reinterpret_cast<const TI*>(x);
+    T* yo = reinterpret_cast<T*>(y);
+    if ((C == 3 || C == 4) && W % 4 == 0 && reinterpret_cast<uintptr_t>(x) % (4 * sizeof(TI)) == 0 && quads < (1ll << 30)) {
       const int grid = grid_for(quads);
-      if (C == 3) s2d_ingest2_kernel<3><<<grid, 256, 0, s>>>(N, H, W, g.pad_lo, g.rows, g.cols, x, y);
-      else s2d_ingest2_kernel<4><<<grid, 256, 0, s>>>(N, H, W, g.pad_lo, g.rows, g.cols, x, y);
+      if (C == 3) s2d_ingest2_kernel<3, TI, T><<<grid, 256, 0, s>>>(N, H, W, g.pad_lo, g.rows, g.cols, xi, yo, af);
+      else s2d_ingest2_kernel<4, TI, T><<<grid, 256, 0, s>>>(N, H, W, g.pad_lo, g.rows, g.cols, xi, yo, af);
       return cudaGetLastError();
     }
     const int grid = grid_for(static_cast<long long>(N) * (H / 2) * (W / 2));
-    s2d_ingest_kernel<<<grid, 256, 0, s>>>(N, C, H, W, g.pad_lo, g.rows, g.cols, x, y);
+    s2d_ingest_kernel<TI, T><<<grid, 256, 0, s>>>(N, C, H, W, g.pad_lo, g.rows, g.cols, xi, yo, af);
     return cudaGetLastError();
+  }
+  template <typename TI>
+  cudaError_t run_in(cudaStream_t s) { return dtype == PCV_F16 ? run<TI, __half>(s) : run<TI, __nv_bfloat16>(s); }
+  cudaError_t launch(cudaStream_t s) override {
+    g_launches++;
+    switch (img_type) {
+      case PCV_IMG_BF16: return run_in<__nv_bfloat16>(s);
+      case PCV_IMG_F16: return run_in<__half>(s);
+      case PCV_IMG_U8: return run_in<uint8_t>(s);
+      default: return run_in<float>(s);
+    }
   }
 };
 
@@ -1020,22 +1165,30 @@ int pcv_stem_s2d_dims(int C, int H, int W, int k, int* rows, int* cols, int* cin
   return PCV_OK;
 }
 
-int pcv_stem_s2d_ingest(pcv_plan* plan, int N, int C, int H, int W, int k, const float* x, void* s2d,
-                        pcv_stream stream) {
+int pcv_stem_s2d_ingest_ex(pcv_plan* plan, int dtype, int img_type, int N, int C, int H, int W, int k, const void* x,
+                           const float* scale_host, const float* bias_host, void* s2d, pcv_stream stream) {
   if (int rc = pcv_stem_s2d_dims(C, H, W, k, nullptr, nullptr, nullptr, nullptr)) return rc;
+  PCV_REQUIRE(dtype == PCV_BF16 || dtype == PCV_F16, "the space-to-depth stem exists in the 16-bit tiers only");
+  PCV_REQUIRE(img_type >= PCV_IMG_F32 && img_type <= PCV_IMG_U8, "unknown image type %d", img_type);
   PCV_REQUIRE(x && s2d && N > 0, "NULL tensor pointer");
-  PCV_REQUIRE(reinterpret_cast<uintptr_t>(x) % 8 == 0 && reinterpret_cast<uintptr_t>(s2d) % 16 == 0, "misaligned stem tensors");
+  PCV_REQUIRE(reinterpret_cast<uintptr_t>(x) % (2 * img_esize(img_type)) == 0 && reinterpret_cast<uintptr_t>(s2d) % 16 == 0,
+              "misaligned stem tensors");
   auto op = std::make_unique<S2dIngestOp>();
-  op->N = N; op->C = C; op->H = H; op->W = W; op->g = s2d_geom(H, W, k); op->x = x;
-  op->y = reinterpret_cast<__nv_bfloat16*>(s2d);
+  op->N = N; op->C = C; op->H = H; op->W = W; op->g = s2d_geom(H, W, k); op->x = x; op->y = s2d;
+  op->dtype = dtype; op->img_type = img_type; op->af = make_affine(C, scale_host, bias_host);
   char nm[96];
-  snprintf(nm, sizeof nm, "ingest_s2d_bf16 C=%d k=%d @%dx%d", C, k, H, W);
+  snprintf(nm, sizeof nm, "ingest_s2d_%s_to_%s C=%d k=%d @%dx%d", img_name(img_type), dn(dtype), C, k, H, W);
   op->name = nm;
-  op->bytes = static_cast<double>(N) * (4.0 * C * H * W + 32.0 * (H / 2) * (W / 2));
+  op->bytes = static_cast<double>(N) * (static_cast<double>(img_esize(img_type)) * C * H * W + 32.0 * (H / 2) * (W / 2));
   return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
 }
 
-int pcv_stem_s2d_pool_ok(int C, int H, int W, int k, int Cout) { return pcv::stem_pool_ok(C, H, W, k, Cout); }
+int pcv_stem_s2d_ingest(pcv_plan* plan, int N, int C, int H, int W, int k, const float* x, void* s2d,
+                        pcv_stream stream) {
+  return pcv_stem_s2d_ingest_ex(plan, PCV_BF16, PCV_IMG_F32, N, C, H, W, k, x, nullptr, nullptr, s2d, stream);
+}
+
+int pcv_stem_s2d_pool_ok(int C, int H, int W, int k, int Cout) { return pcv::bf::stem_pool_ok(C, H, W, k, Cout); }
 
 int pcv_stem_s2d_weights(int Cout, int C, int k, const float* w, float* w_eq, pcv_stream stream) {
   PCV_REQUIRE(w && w_eq && Cout > 0 && C >= 1 && C <= 4 && (k == 3 || k == 5 || k == 7), "bad stem weight arguments");

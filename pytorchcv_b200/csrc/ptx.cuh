@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "../../include/pcv_b200.h"   // pcv_act codes for fast_act_n
@@ -271,10 +272,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 
-// Instruction descriptor for kind::f16 with bf16 A/B (K-major both), fp32 accumulate, M x N tile.
+// Instruction descriptor for kind::f16 (K-major A and B, fp32 accumulate, M x N tile).  Bits [7,10) / [10,13) are the
+// A / B element formats: 1 = bf16, 0 = f16 - the same instruction and rate serve both 16-bit storage tiers.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -286,6 +291,31 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
   uint32_t d;
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
+}
+// fp16-storage tier twins (same roles, IEEE half: 10-bit mantissa, max 65504 - overflow rounds to inf like torch's .half())
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ float f16lo(uint32_t v) {
+  return __half2float(__ushort_as_half(static_cast<unsigned short>(v & 0xFFFFu)));
+}
+__device__ __forceinline__ float f16hi(uint32_t v) {
+  return __half2float(__ushort_as_half(static_cast<unsigned short>(v >> 16)));
+}
+__device__ __forceinline__ uint32_t hmax2_f16(uint32_t a, uint32_t b) {
+  const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t hmin2_f16(uint32_t a, uint32_t b) {
+  const __half2 r = __hmin2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
 }
 // packed fp32x2 add (Blackwell FADD2); each lane rounds like a scalar add
 __device__ __forceinline__ float2 add2(const float2 a, const float2 b) {
@@ -311,25 +341,6 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
-}
-__device__ __forceinline__ uint32_t hmax3_bf16(uint32_t a, uint32_t b, uint32_t c) {   // one VHMNMX
-  return hmax2_bf16(hmax2_bf16(a, b), c);
-}
-// The clamp-family activations (none / ReLU / ReLU6: lo in {-inf, 0}, hi in {+inf, 6}) on 16 packed pairs: the lower
-// bound rides on the conversion (F2FP.RELU), the upper bound is a packed bf16 min AFTER rounding (6.0 is exact in bf16
-// and rounding is monotonic, so min-then-round == round-then-min).  16 or 32 instructions instead of 64 FMNMX + 16 F2FP.
-__device__ __forceinline__ void clamp_pack32(const float (&v)[32], uint32_t (&o)[16], bool relu, bool capped, uint32_t cap2) {
-  if (relu) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) o[i] = pack_relu_bf16x2(v[2 * i], v[2 * i + 1]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-  }
-  if (capped) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) o[i] = hmin2_bf16(o[i], cap2);
-  }
 }
 // bf16-tier versions of the smooth activations (activ.py:16-47): one MUFU.TANH instead of ex2 + a full-precision
 // division.  sigmoid(x) = 0.5 + 0.5 tanh(x/2); tanh.approx.f32 has ~2^-11 relative error, below the bf16 the result is
@@ -450,3 +461,67 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar, uint16_t mask) {
 }
 
 }  // namespace pcv
+
+// ----------------------------------------------------------------------------------------------
+// 16-bit storage tier of this translation unit.  The tensor-core / TMA-window kernels are compiled twice, once per tier
+// (Makefile: -DPCV_TIER=bf -DPCV_HALF=0 and -DPCV_TIER=hf -DPCV_HALF=1), into namespaces pcv::bf and pcv::hf; inside them
+// `e16` is the element type and the e16 helpers below resolve to the bf16 or the f16 instruction.
+// ----------------------------------------------------------------------------------------------
+#ifdef PCV_TIER
+namespace pcv {
+namespace PCV_TIER {
+#if PCV_HALF
+using e16 = __half;
+using e16x2 = __half2;
+constexpr CUtensorMapDataType TMAP_E16 = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+constexpr uint32_t E16_NEG_INF2 = 0xFC00FC00u;
+constexpr int TIER_DTYPE = PCV_F16;
+#define PCV_TIER_NAME "f16"
+__host__ __device__ constexpr uint32_t make_idesc_e16(int M, int N) { return make_idesc_f16(M, N); }
+__device__ __forceinline__ uint32_t pack_e16x2(float lo, float hi) { return pack_f16x2(lo, hi); }
+__device__ __forceinline__ uint32_t pack_relu_e16x2(float lo, float hi) { return pack_relu_f16x2(lo, hi); }
+__device__ __forceinline__ float e16lo(uint32_t v) { return f16lo(v); }
+__device__ __forceinline__ float e16hi(uint32_t v) { return f16hi(v); }
+__device__ __forceinline__ uint32_t hmax2_e16(uint32_t a, uint32_t b) { return hmax2_f16(a, b); }
+__device__ __forceinline__ uint32_t hmin2_e16(uint32_t a, uint32_t b) { return hmin2_f16(a, b); }
+__device__ __forceinline__ float e16_to_float(e16 v) { return __half2float(v); }
+__device__ __forceinline__ e16 float_to_e16(float v) { return __float2half_rn(v); }
+#else
+using e16 = __nv_bfloat16;
+using e16x2 = __nv_bfloat162;
+constexpr CUtensorMapDataType TMAP_E16 = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+constexpr uint32_t E16_NEG_INF2 = 0xFF80FF80u;
+constexpr int TIER_DTYPE = PCV_BF16;
+#define PCV_TIER_NAME "bf16"
+__host__ __device__ constexpr uint32_t make_idesc_e16(int M, int N) { return make_idesc_bf16(M, N); }
+__device__ __forceinline__ uint32_t pack_e16x2(float lo, float hi) { return pack_bf16x2(lo, hi); }
+__device__ __forceinline__ uint32_t pack_relu_e16x2(float lo, float hi) { return pack_relu_bf16x2(lo, hi); }
+__device__ __forceinline__ float e16lo(uint32_t v) { return bf16lo(v); }
+__device__ __forceinline__ float e16hi(uint32_t v) { return bf16hi(v); }
+__device__ __forceinline__ uint32_t hmax2_e16(uint32_t a, uint32_t b) { return hmax2_bf16(a, b); }
+__device__ __forceinline__ uint32_t hmin2_e16(uint32_t a, uint32_t b) { return hmin2_bf16(a, b); }
+__device__ __forceinline__ float e16_to_float(e16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ e16 float_to_e16(float v) { return __float2bfloat16(v); }
+#endif
+__device__ __forceinline__ uint32_t hmax3_e16(uint32_t a, uint32_t b, uint32_t c) {   // one VHMNMX
+  return hmax2_e16(hmax2_e16(a, b), c);
+}
+// The clamp-family activations (none / ReLU / ReLU6: lo in {-inf, 0}, hi in {+inf, 6}) on 16 packed pairs: the lower
+// bound rides on the conversion (F2FP.RELU), the upper bound is a packed e16 min AFTER rounding (6.0 is exact in e16
+// and rounding is monotonic, so min-then-round == round-then-min).  16 or 32 instructions instead of 64 FMNMX + 16 F2FP.
+__device__ __forceinline__ void clamp_pack32(const float (&v)[32], uint32_t (&o)[16], bool relu, bool capped, uint32_t cap2) {
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = pack_relu_e16x2(v[2 * i], v[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = pack_e16x2(v[2 * i], v[2 * i + 1]);
+  }
+  if (capped) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = hmin2_e16(o[i], cap2);
+  }
+}
+}  // namespace PCV_TIER
+}  // namespace pcv
+#endif  // PCV_TIER

@@ -33,11 +33,14 @@ bool pdl_enabled() {
 }
 
 int sm_count() {
-  static int n = 0;
+  static std::atomic<int> cache[64];   // per device ordinal; 0 = not queried yet
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  std::atomic<int>& slot = cache[dev & 63];
+  int n = slot.load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    slot.store(n, std::memory_order_relaxed);
   }
   return n;
 }
@@ -75,15 +78,17 @@ int submit(pcv_plan* plan, Op* op, cudaStream_t stream) {
 // implicit GEMM, anything else -> CUDA-core direct conv.  fp32: depthwise -> dwconv, else CUDA-core direct conv.
 int conv_route(const pcv_conv_desc& d, int dtype, std::string* why) {
   const bool depthwise = d.groups > 1 && d.groups == d.Cin && d.Cin == d.Cout;
-  if (depthwise && pitch_or(d.in_pitch, d.Cin) % 8 == 0 && pitch_or(d.out_pitch, d.Cout) % 8 == 0 && d.Cin % 8 == 0)
+  // the depthwise kernels take square windows and store in the tier's own type; anything else falls to the generic kernel
+  if (depthwise && d.kh == d.kw && !(d.flags & PCV_CONV_OUT_F32) && pitch_or(d.in_pitch, d.Cin) % 8 == 0 &&
+      pitch_or(d.out_pitch, d.Cout) % 8 == 0 && d.Cin % 8 == 0)
     return ROUTE_DW;
-  if (dtype == PCV_BF16 && !(d.flags & PCV_CONV_FORCE_SIMT) && igemm_supported(d, why)) return ROUTE_IGEMM;
+  if (is16(dtype) && !(d.flags & PCV_CONV_FORCE_SIMT) && bf::igemm_supported(d, why)) return ROUTE_IGEMM;
   return ROUTE_SIMT;  // (validate_conv rejects overlapped / row-pitched views that reach this route)
 }
 
 static int validate_conv(const pcv_conv_desc* d, int dtype) {
   PCV_REQUIRE(d != nullptr, "conv desc is NULL");
-  PCV_REQUIRE(dtype == PCV_BF16 || dtype == PCV_F32, "unknown dtype %d", dtype);
+  PCV_REQUIRE(dtype == PCV_BF16 || dtype == PCV_F32 || dtype == PCV_F16, "unknown dtype %d", dtype);
   PCV_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "non-positive conv dims");
   PCV_REQUIRE(d->kh > 0 && d->kw > 0 && d->stride > 0 && d->dil > 0 && d->pad >= 0, "bad kernel/stride/pad/dilation");
   PCV_REQUIRE(d->groups > 0 && d->Cin % d->groups == 0 && d->Cout % d->groups == 0,
@@ -92,13 +97,13 @@ static int validate_conv(const pcv_conv_desc* d, int dtype) {
   PCV_REQUIRE((pitch_or(d->in_pitch, d->Cin) >= d->Cin || (d->flags & PCV_CONV_IN_OVERLAP)) &&
                   pitch_or(d->out_pitch, d->Cout) >= d->Cout,
               "channel pitch smaller than channel count");
-  PCV_REQUIRE(!(d->flags & PCV_CONV_IN_OVERLAP) || (dtype == PCV_BF16 && d->groups == 1),
+  PCV_REQUIRE(!(d->flags & PCV_CONV_IN_OVERLAP) || (is16(dtype) && d->groups == 1),
               "overlapping input views are only supported by the bf16 tensor-core path");
   PCV_REQUIRE(d->in_row_pitch == 0 || d->in_row_pitch >= (d->W - 1) * pitch_or(d->in_pitch, d->Cin) + d->Cin ||
                   (d->flags & PCV_CONV_IN_OVERLAP),
               "in_row_pitch smaller than a row");
-  PCV_REQUIRE(!(d->flags & PCV_CONV_OUT_F32) || dtype == PCV_BF16, "OUT_F32 only applies to the bf16 tier");
-  PCV_REQUIRE(!(d->flags & PCV_CONV_POOL3S2) || ((d->flags & PCV_CONV_IN_OVERLAP) && dtype == PCV_BF16),
+  PCV_REQUIRE(!(d->flags & PCV_CONV_OUT_F32) || is16(dtype), "OUT_F32 only applies to the 16-bit tiers");
+  PCV_REQUIRE(!(d->flags & PCV_CONV_POOL3S2) || ((d->flags & PCV_CONV_IN_OVERLAP) && is16(dtype)),
               "POOL3S2 only applies to the bf16 space-to-depth stem");
   if ((d->flags & PCV_CONV_IN_OVERLAP) || d->in_row_pitch != 0) {
     std::string why;
@@ -135,7 +140,7 @@ int pcv_conv_packed_bytes(const pcv_conv_desc* d, int dtype, size_t* w_bytes, si
   PCV_REQUIRE(w_bytes && bias_bytes, "NULL output pointer");
   switch (conv_route(*d, dtype, nullptr)) {
     case ROUTE_DW: return dw_packed_bytes(*d, dtype, w_bytes, bias_bytes);
-    case ROUTE_IGEMM: return igemm_packed_bytes(*d, w_bytes, bias_bytes);
+    case ROUTE_IGEMM: return bf::igemm_packed_bytes(*d, w_bytes, bias_bytes);
     default: return simt_packed_bytes(*d, dtype, w_bytes, bias_bytes);
   }
 }
@@ -150,7 +155,9 @@ int pcv_pack_conv_weights(const pcv_conv_desc* d, int dtype, const float* w, con
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (conv_route(*d, dtype, nullptr)) {
     case ROUTE_DW: return dw_pack(*d, dtype, w, conv_bias, bn_gamma, bn_beta, bn_mean, bn_var, eps, w_packed, bias_out, s);
-    case ROUTE_IGEMM: return igemm_pack(*d, w, conv_bias, bn_gamma, bn_beta, bn_mean, bn_var, eps, w_packed, bias_out, s);
+    case ROUTE_IGEMM:
+      return (dtype == PCV_F16 ? hf::igemm_pack : bf::igemm_pack)(*d, w, conv_bias, bn_gamma, bn_beta, bn_mean, bn_var, eps,
+                                                                  w_packed, bias_out, s);
     default: return simt_pack(*d, dtype, w, conv_bias, bn_gamma, bn_beta, bn_mean, bn_var, eps, w_packed, bias_out, s);
   }
 }
@@ -163,7 +170,7 @@ int pcv_conv2d_bias_act(pcv_plan* plan, const pcv_conv_desc* d, int dtype, const
   int rc;
   switch (conv_route(*d, dtype, nullptr)) {
     case ROUTE_DW: rc = dw_make(*d, dtype, x, w_packed, bias, residual, y, &op); break;
-    case ROUTE_IGEMM: rc = igemm_make(*d, x, w_packed, bias, residual, y, &op); break;
+    case ROUTE_IGEMM: rc = (dtype == PCV_F16 ? hf::igemm_make : bf::igemm_make)(*d, x, w_packed, bias, residual, y, &op); break;
     default: rc = simt_make(*d, dtype, x, w_packed, bias, residual, y, &op); break;
   }
   if (rc) return rc;

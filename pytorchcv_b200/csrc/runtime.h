@@ -62,7 +62,24 @@ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 inline int conv_out(int H, int k, int stride, int pad, int dil) { return (H + 2 * pad - dil * (k - 1) - 1) / stride + 1; }
 inline int pitch_or(int pitch, int c) { return pitch > 0 ? pitch : c; }
 inline size_t esize(int dtype) { return dtype == PCV_F32 ? 4 : 2; }
-int sm_count();
+inline const char* dtype_name(int dtype) { return dtype == PCV_F32 ? "f32" : (dtype == PCV_F16 ? "f16" : "bf16"); }
+int sm_count();   // SMs of the CURRENT device (cached per device)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE function attribute: `done` holds one bit per device
+// ordinal for one kernel instantiation, so a process that drives several GPUs sets it on each of them.
+inline cudaError_t set_max_smem_once(const void* func, int bytes, std::atomic<uint64_t>& done) {
+  int dev = 0;
+  if (cudaError_t e = cudaGetDevice(&dev)) return e;
+  const uint64_t bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  if (cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) return e;
+  done.fetch_or(bit, std::memory_order_release);
+  return cudaSuccess;
+}
+template <typename... KArgs>
+inline cudaError_t set_max_smem_once(void (*kernel)(KArgs...), int bytes, std::atomic<uint64_t>& done) {
+  return set_max_smem_once(reinterpret_cast<const void*>(kernel), bytes, done);
+}
 
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
 // The hot kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization so that the next kernel's
@@ -96,13 +113,29 @@ EncodeTiledFn encode_tiled_fn();
 EncodeIm2colFn encode_im2col_fn();
 
 // ---- launchers implemented in the .cu files --------------------------------------------------------------------
-// conv_igemm.cu : tcgen05 implicit GEMM (dense + block-diagonal grouped), bf16
-int igemm_supported(const pcv_conv_desc& d, std::string* why);
-int igemm_packed_bytes(const pcv_conv_desc& d, size_t* w_bytes, size_t* b_bytes);
-int igemm_pack(const pcv_conv_desc& d, const float* w, const float* conv_bias, const float* g, const float* b,
-               const float* m, const float* v, float eps, void* w_packed, float* bias_out, cudaStream_t s);
-int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float* bias, const void* res, void* y,
-               Op** out);
+// The tensor-core and TMA-window kernels exist once per 16-bit storage tier (ptx.cuh, "16-bit storage tier"): the same
+// sources compiled into pcv::bf (bf16) and pcv::hf (IEEE fp16).
+#define PCV_DECLARE_TIER_API(NS)                                                                                         \
+  namespace NS {                                                                                                         \
+  /* conv_igemm.cu : tcgen05 implicit GEMM (dense + block-diagonal grouped) */                                           \
+  int igemm_supported(const pcv_conv_desc& d, std::string* why);                                                         \
+  int igemm_packed_bytes(const pcv_conv_desc& d, size_t* w_bytes, size_t* b_bytes);                                      \
+  int igemm_pack(const pcv_conv_desc& d, const float* w, const float* conv_bias, const float* g, const float* b,        \
+                 const float* m, const float* v, float eps, void* w_packed, float* bias_out, cudaStream_t s);            \
+  int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float* bias, const void* res, void* y,     \
+                 Op** out);                                                                                              \
+  /* window_tma.cu : TMA halo-staged 3x3 / 5x5 window ops (op_kind 0 = depthwise conv, 1 = max pool).  Returns */        \
+  /* PCV_ERR_UNSUPPORTED (without touching the error message) for shapes the caller serves with its generic kernel. */   \
+  int win_make(int op_kind, int N, int H, int W, int C, int k, int stride, int pad, int act, const void* x,              \
+               int in_pitch, const float* w, const float* bias, const void* res, int res_pitch, void* y, int out_pitch,  \
+               Op** out);                                                                                                \
+  /* conv_igemm3s.cu : can the s2d stem take the fused max pool (pcv_stem_s2d_pool_ok) */                                \
+  int stem_pool_ok(int C, int H, int W, int k, int Cout);                                                                \
+  }
+PCV_DECLARE_TIER_API(bf)
+PCV_DECLARE_TIER_API(hf)
+#undef PCV_DECLARE_TIER_API
+inline bool is16(int dtype) { return dtype == PCV_BF16 || dtype == PCV_F16; }
 // conv_simt.cu : CUDA-core direct convolution (fp32 tier; generic bf16 fallback / cross-check)
 int simt_packed_bytes(const pcv_conv_desc& d, int dtype, size_t* w_bytes, size_t* b_bytes);
 int simt_pack(const pcv_conv_desc& d, int dtype, const float* w, const float* conv_bias, const float* g,
@@ -116,11 +149,6 @@ int dw_pack(const pcv_conv_desc& d, int dtype, const float* w, const float* conv
             const float* m, const float* v, float eps, void* w_packed, float* bias_out, cudaStream_t s);
 int dw_make(const pcv_conv_desc& d, int dtype, const void* x, const void* w, const float* bias, const void* res,
             void* y, Op** out);
-
-// window_tma.cu : TMA halo-staged 3x3 window ops, bf16 (op_kind 0 = depthwise conv, 1 = max pool).  Returns
-// PCV_ERR_UNSUPPORTED (without touching the error message) for shapes the caller must serve with its generic kernel.
-int win_make(int op_kind, int N, int H, int W, int C, int k, int stride, int pad, int act, const void* x, int in_pitch,
-             const float* w, const float* bias, const void* res, int res_pitch, void* y, int out_pitch, Op** out);
 
 enum ConvRoute { ROUTE_IGEMM = 0, ROUTE_DW = 1, ROUTE_SIMT = 2 };
 int conv_route(const pcv_conv_desc& d, int dtype, std::string* why);

@@ -23,6 +23,7 @@
 #include "runtime.h"
 
 namespace pcv {
+namespace PCV_TIER {
 
 struct WinParams {
   int N, H, W, C, Ho, Wo;
@@ -56,13 +57,13 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
 }
 
 __device__ __forceinline__ uint32_t hclamp2_u32(uint32_t v, uint32_t lo, uint32_t hi) {
-  const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(&v);
-  const __nv_bfloat162 r = __hmin2(__hmax2(x, *reinterpret_cast<const __nv_bfloat162*>(&lo)),
-                                   *reinterpret_cast<const __nv_bfloat162*>(&hi));
+  const e16x2 x = *reinterpret_cast<const e16x2*>(&v);
+  const e16x2 r = __hmin2(__hmax2(x, *reinterpret_cast<const e16x2*>(&lo)),
+                                   *reinterpret_cast<const e16x2*>(&hi));
   return *reinterpret_cast<const uint32_t*>(&r);
 }
 __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
-  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  const e16x2 r = __hmax2(*reinterpret_cast<const e16x2*>(&a), *reinterpret_cast<const e16x2*>(&b));
   return *reinterpret_cast<const uint32_t*>(&r);
 }
 
@@ -101,7 +102,7 @@ template <int OP, int KS, int S, int TH, int COLS, bool RES>
 __global__ void __launch_bounds__(KS == 5 ? 384 : 256, KS == 5 ? 1 : 2)   // 5x5: 25 taps x 4 channels of fp32 weights live in
                                                                          // registers (~165): one 384-thread CTA per SM
 win_kernel(const __grid_constant__ CUtensorMap tmIn, const WinParams p, const float* __restrict__ w,
-           const float* __restrict__ bias, const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ y) {
+           const float* __restrict__ bias, const e16* __restrict__ res, e16* __restrict__ y) {
   constexpr int IH = (TH - 1) * S + KS;
   constexpr int NACC = (KS + S - 1) / S;
   constexpr int NIN = (COLS - 1) * S + KS;      // input columns touched by one thread
@@ -162,7 +163,7 @@ win_kernel(const __grid_constant__ CUtensorMap tmIn, const WinParams p, const fl
     }
   };
   if (p.cblocks == 1) load_weights(v * 4);                   // one channel block: weights are loop-invariant
-  const uint32_t act_lo2 = pack_bf16x2(p.act_lo, p.act_lo), act_hi2 = pack_bf16x2(p.act_hi, p.act_hi);
+  const uint32_t act_lo2 = pack_e16x2(p.act_lo, p.act_lo), act_hi2 = pack_e16x2(p.act_hi, p.act_hi);
 
   int stage = 0;
   uint32_t phase = 0;
@@ -203,8 +204,8 @@ win_kernel(const __grid_constant__ CUtensorMap tmIn, const WinParams p, const fl
       if (OP == 0) {
 #pragma unroll
         for (int j = 0; j < NIN; ++j) {
-          xv[j][0] = make_float2(bf16lo(raw[j].x), bf16hi(raw[j].x));
-          xv[j][1] = make_float2(bf16lo(raw[j].y), bf16hi(raw[j].y));
+          xv[j][0] = make_float2(e16lo(raw[j].x), e16hi(raw[j].x));
+          xv[j][1] = make_float2(e16lo(raw[j].y), e16hi(raw[j].y));
         }
       }
       const bool row_ok = (hi0 + ir) >= 0 && (hi0 + ir) < H;
@@ -226,7 +227,7 @@ win_kernel(const __grid_constant__ CUtensorMap tmIn, const WinParams p, const fl
               ffma2(acc[a][cc][1], xv[cc * S + fs][1], wr[fr * KS + fs][1]);
             }
           } else {
-            if (fr == 0) mx[a][cc] = make_uint2(0xFF80FF80u, 0xFF80FF80u);   // -inf, -inf
+            if (fr == 0) mx[a][cc] = make_uint2(E16_NEG_INF2, E16_NEG_INF2);   // -inf, -inf
             if (row_ok) {
 #pragma unroll
               for (int fs = 0; fs < KS; ++fs) {
@@ -252,7 +253,7 @@ win_kernel(const __grid_constant__ CUtensorMap tmIn, const WinParams p, const fl
                 if (RES) {
                   uint2 rr = make_uint2(0u, 0u);
                   if (live) rr = __ldg(reinterpret_cast<const uint2*>(res + (ro + ho * r_row + cc * res_pitch)));
-                  r0.x += bf16lo(rr.x); r0.y += bf16hi(rr.x); r1.x += bf16lo(rr.y); r1.y += bf16hi(rr.y);
+                  r0.x += e16lo(rr.x); r0.y += e16hi(rr.x); r1.x += e16lo(rr.y); r1.y += e16hi(rr.y);
                 }
                 if (p.act > PCV_ACT_RELU6) {   // swish / h-swish / (h-)sigmoid (EfficientNet, MobileNetV3): warp-uniform
                   float f[4] = {r0.x, r0.y, r1.x, r1.y};
@@ -262,8 +263,8 @@ win_kernel(const __grid_constant__ CUtensorMap tmIn, const WinParams p, const fl
                 }
                 // clamp AFTER rounding to bf16: the bounds (0, 6, +-inf) are bf16-exact and rounding is monotone,
                 // so this equals round(clamp(x)) at half the instruction count (packed bf16x2 min / max)
-                o.x = hclamp2_u32(pack_bf16x2(r0.x, r0.y), act_lo2, act_hi2);
-                o.y = hclamp2_u32(pack_bf16x2(r1.x, r1.y), act_lo2, act_hi2);
+                o.x = hclamp2_u32(pack_e16x2(r0.x, r0.y), act_lo2, act_hi2);
+                o.y = hclamp2_u32(pack_e16x2(r1.x, r1.y), act_lo2, act_hi2);
               } else {
                 o = mx[a][cc];
               }
@@ -356,7 +357,7 @@ static int make_win_map(CUtensorMap* tm, const void* x, int N, int H, int W, int
   cuuint64_t strides[3] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)W * in_pitch * 2, (cuuint64_t)H * W * in_pitch * 2};
   cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)IW, (cuuint32_t)IH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+  CUresult r = fn(tm, TMAP_E16, 4, const_cast<void*>(x), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -371,18 +372,13 @@ struct WinOp : Op {
   WinCfg cfg;
   int op_kind, S, K = 3;
   const float *w, *bias;
-  const __nv_bfloat16* res;
-  __nv_bfloat16* y;
+  const e16* res;
+  e16* y;
 
   template <int OP, int K_, int S_, int TH, int COLS, bool RES>
   cudaError_t go(cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(win_kernel<OP, K_, S_, TH, COLS, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (K_ == 5 ? 224 : 112) * 1024);
-      if (e != cudaSuccess) return e;
-      attr_set = true;
-    }
+    static std::atomic<uint64_t> attr_done{0};   // per device (see runtime.h)
+    if (cudaError_t e = set_max_smem_once(win_kernel<OP, K_, S_, TH, COLS, RES>, (K_ == 5 ? 224 : 112) * 1024, attr_done)) return e;
     const long long cap = static_cast<long long>(sm_count()) * cfg.ctas_per_sm;
     const int grid = static_cast<int>(std::min<long long>(p.num_tiles, cap));
     return launch_pdl(win_kernel<OP, K_, S_, TH, COLS, RES>, dim3(grid), dim3(cfg.threads), cfg.smem_bytes, s, tm, p, w, bias, res, y);
@@ -430,10 +426,11 @@ int win_make(int op_kind, int N, int H, int W, int C, int k, int stride, int pad
   const int IH = (op->cfg.TH - 1) * stride + k;
   if (int rc = make_win_map(&op->tm, x, N, H, W, C, in_pitch, p.CB, p.IW, IH)) return rc;
   op->op_kind = op_kind; op->S = stride; op->K = k; op->w = w; op->bias = bias;
-  op->res = reinterpret_cast<const __nv_bfloat16*>(res);
-  op->y = reinterpret_cast<__nv_bfloat16*>(y);
+  op->res = reinterpret_cast<const e16*>(res);
+  op->y = reinterpret_cast<e16*>(y);
   *out = op.release();
   return PCV_OK;
 }
 
+}  // namespace PCV_TIER
 }  // namespace pcv

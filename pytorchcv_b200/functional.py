@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import BF16, F32, ConvDesc
+from ._lib import BF16, F16, F32, ConvDesc
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -18,11 +18,17 @@ def _dt(t: torch.Tensor) -> int:
         return BF16
     if t.dtype == torch.float32:
         return F32
+    if t.dtype == torch.float16:
+        return F16
     raise TypeError(f"unsupported tensor dtype {t.dtype}")
 
 
 def _tdt(code: int):
-    return torch.float32 if code == F32 else torch.bfloat16
+    return torch.float32 if code == F32 else (torch.float16 if code == F16 else torch.bfloat16)
+
+
+def _code(dtype) -> int:
+    return F32 if dtype == torch.float32 else (F16 if dtype == torch.float16 else BF16)
 
 
 def _stream() -> int:
@@ -97,7 +103,7 @@ def global_avgpool(x: torch.Tensor, out_dtype=None) -> torch.Tensor:
     odt = x.dtype if out_dtype is None else out_dtype
     out = torch.empty((N, Cc), dtype=odt, device=x.device)
     _lib.call("pcv_global_avgpool", None, _dt(x), N, H * W, Cc, x.data_ptr(), Cc, out.data_ptr(),
-              F32 if odt == torch.float32 else BF16, _stream())
+              _code(odt), _stream())
     return out
 
 
@@ -146,7 +152,7 @@ def nchw_to_nhwc(x: torch.Tensor, dtype=torch.bfloat16, c_pitch: int = 0) -> tor
     N, Cc, H, W = x.shape
     pitch = c_pitch or (Cc + 7) // 8 * 8
     out = torch.empty((N, H, W, pitch), dtype=dtype, device=x.device)
-    _lib.call("pcv_nchw_f32_to_nhwc", None, F32 if dtype == torch.float32 else BF16, N, Cc, H, W, x.data_ptr(),
+    _lib.call("pcv_nchw_f32_to_nhwc", None, _code(dtype), N, Cc, H, W, x.data_ptr(),
               out.data_ptr(), pitch, _stream())
     return out
 

@@ -35,10 +35,13 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
     return rank, world, local
 
 
-def gather_logits(local: torch.Tensor, sizes: list[int] | None = None, group=None) -> torch.Tensor:
-    """All-gather per-rank logits [n_r, C] into [sum n_r, C] on every rank (rank order == image order).
+def gather_logits(local, sizes: list[int] | None = None, group=None):
+    """All-gather per-rank outputs [n_r, ...] into [sum n_r, ...] on every rank (rank order == image order).
 
-    Equal shards use one all_gather_into_tensor (a single NCCL all-gather); ragged shards pad to the largest."""
+    Equal shards use one all_gather_into_tensor (a single NCCL all-gather); ragged shards pad to the largest.
+    Tuples / lists (DeepLabv3 / FCN / PSPNet with aux=True, ResNetD with multi_output) are gathered element-wise."""
+    if isinstance(local, (tuple, list)):
+        return type(local)(gather_logits(t, sizes, group) for t in local)
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return local
     world = dist.get_world_size(group)

@@ -20,7 +20,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SIGMOID, ACT_SWISH, ACT_HSWISH, ACT_HSIGMOID, BF16, F32, ConvDesc
+from ._lib import (ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SIGMOID, ACT_SWISH, ACT_HSWISH, ACT_HSIGMOID, BF16, F16, F32,
+                   ConvDesc)
 
 _ALIGN = 1024  # arena / weight blob alignment (TMA needs 16 B; 1 KiB keeps every tensor sector- and line-aligned)
 
@@ -33,12 +34,24 @@ def _rup(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
 
+_DTYPE_NAMES = {"bf16": BF16, "bfloat16": BF16, "fp16": F16, "f16": F16, "half": F16, "float16": F16,
+                "fp32": F32, "f32": F32, "float32": F32,
+                torch.bfloat16: BF16, torch.float16: F16, torch.float32: F32}
+
+
 def dtype_code(dtype) -> int:
-    if dtype in (BF16, "bf16", torch.bfloat16):
-        return BF16
-    if dtype in (F32, "fp32", "f32", torch.float32):
-        return F32
-    raise ValueError(f"unsupported dtype {dtype!r}: the path has a bf16 tier and an fp32 tier")
+    """Tier code (pcv_dtype) of "bf16" | "fp16" | "fp32", a torch dtype, or a code."""
+    if isinstance(dtype, int) and not isinstance(dtype, bool) and dtype in (BF16, F32, F16):
+        return dtype
+    try:
+        return _DTYPE_NAMES[dtype]
+    except (KeyError, TypeError):
+        raise ValueError(f"unsupported dtype {dtype!r}: the path has two 16-bit storage tiers (bf16, fp16) and an "
+                         "fp32 tier") from None
+
+
+def _is16(dtype: int) -> bool:
+    return dtype in (BF16, F16)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -66,6 +79,8 @@ class TRef:
     ch_off: int = 0
     layout: str = "nhwc"   # "nhwc" | "nchw" (fp32 network outputs written by the bilinear kernel)
     flat: bool = False     # return as [N, C] (the reference's x.view(N, -1))
+    tail: Any = None       # network-edge op run per call AFTER the plan, writing a fresh caller-owned tensor:
+                           # tail(ptr, out_ptr, stream); such a tensor has no arena storage and cannot feed another op
 
     @property
     def byte_off(self) -> int:
@@ -153,6 +168,8 @@ class Builder:
         idx = len(self.ops)
         for t in trefs:
             if t is not None:
+                if t.tail is not None:
+                    raise NotImplementedError("an fp32 NCHW network output cannot feed another op of the plan")
                 if self.stem is not None and self.input_tref is not None and t.buf is self.input_tref.buf:
                     raise _NoS2dStem()
                 if self.stem is not None and t.buf is self.stem.get("fused_conv_buf"):
@@ -162,7 +179,7 @@ class Builder:
 
     def _s2d_stem(self, x: TRef, conv, k: int, stride: int, pad: int, dil: int) -> bool:
         """k x k stride-2 conv on the <=4-channel network input -> space-to-depth stem (include/pcv_b200.h)."""
-        return (self.allow_s2d_stem and self.dtype == BF16 and x is self.input_tref and self.stem is None
+        return (self.allow_s2d_stem and _is16(self.dtype) and x is self.input_tref and self.stem is None
                 and x.buf.last < 0 and conv.groups == 1 and conv.in_channels == self.image_channels <= 4
                 and k in (3, 5, 7) and conv.kernel_size[0] == conv.kernel_size[1] and stride == 2 and pad == k // 2
                 and dil == 1 and x.H % 2 == 0 and x.W % 2 == 0)
@@ -241,7 +258,7 @@ class Builder:
         d = ConvDesc(N=x.N, H=x.H, W=x.W, Cin=x.C, Cout=cout, kh=kh, kw=kw, stride=k_stride, pad=k_pad, dil=k_dil,
                      groups=groups, act=act, in_pitch=x.pitch, out_pitch=out.pitch,
                      res_pitch=residual.pitch if residual is not None else 0,
-                     flags=flags | (_lib.CONV_OUT_F32 if (out_f32 and self.dtype == BF16) else 0))
+                     flags=flags | (_lib.CONV_OUT_F32 if (out_f32 and _is16(self.dtype)) else 0))
         wb, bb = C.c_size_t(), C.c_size_t()
         _lib.call("pcv_conv_packed_bytes", C.byref(d), self.dtype, C.byref(wb), C.byref(bb))
         w_off, b_off = self._wblob(wb.value), self._wblob(bb.value)
@@ -342,10 +359,23 @@ class Builder:
             "pcv_add_act", plan, a.dtype, a.N * a.H * a.W * a.C, ptr(a), ptr(b), act, ptr(out), None))
         return out
 
+    def _edge_out(self, x: TRef, H: int, W: int, name: str, launch) -> TRef:
+        """An fp32 NCHW tensor the reference returns (freshly allocated, caller-owned): produced per call by
+        `launch(plan=None, ptr, out_ptr, stream)` after the plan, straight into a new torch tensor - no arena storage."""
+        self._use(x)
+        x.buf.pinned = True   # read after the whole plan has run
+        out = TRef(x.N, H, W, x.C, x.C, F32, Buf(nbytes=0, first=len(self.ops)), 0, "nchw")
+        out.tail = {"launch": launch, "name": name,
+                    "bytes": float(x.N * x.C * (_esize(x.dtype) * x.H * x.W + 4 * H * W))}
+        return out
+
     def bilinear(self, x: TRef, Hout: int, Wout: int, out: TRef | None = None, nchw_f32: bool = False) -> TRef:
         if nchw_f32:
-            out = self.new(x.N, Hout, Wout, x.C, dtype=F32, layout="nchw")
-        elif out is None:
+            return self._edge_out(x, Hout, Wout, f"bilinear C={x.C} {x.H}x{x.W}->{Hout}x{Wout} nchw_f32 (edge)",
+                                  lambda ptr, optr, stream: _lib.call(
+                "pcv_bilinear_upsample_ac", None, x.dtype, x.N, x.H, x.W, x.C, ptr(x), x.pitch, Hout, Wout, optr,
+                x.C, 1, stream))
+        if out is None:
             out = self.new(x.N, Hout, Wout, x.C, dtype=x.dtype)
         self._use(x, out)
         self.ops.append(lambda plan, ptr, wptr: _lib.call(
@@ -354,11 +384,8 @@ class Builder:
         return out
 
     def egress(self, x: TRef) -> TRef:
-        out = self.new(x.N, x.H, x.W, x.C, dtype=F32, layout="nchw")
-        self._use(x, out)
-        self.ops.append(lambda plan, ptr, wptr: _lib.call(
-            "pcv_nhwc_to_nchw_f32", plan, x.dtype, x.N, x.C, x.H, x.W, ptr(x), x.pitch, ptr(out), None))
-        return out
+        return self._edge_out(x, x.H, x.W, f"nhwc_to_nchw_f32 C={x.C} {x.H}x{x.W} (edge)", lambda ptr, optr, stream: _lib.call(
+            "pcv_nhwc_to_nchw_f32", None, x.dtype, x.N, x.C, x.H, x.W, ptr(x), x.pitch, optr, stream))
 
 
 class _ConvShim:
@@ -795,7 +822,15 @@ class CompiledModule:
     """A module tree compiled for one input shape / tier / device."""
 
     def __init__(self, module: nn.Module, in_shape: tuple[int, int, int, int], dtype="bf16",
-                 device: torch.device | str | None = None, graph: bool = False, lower_kwargs: dict | None = None):
+                 device: torch.device | str | None = None, graph: bool = False, lower_kwargs: dict | None = None,
+                 alias_outputs: bool = False, input_affine: tuple | None = None):
+        """`input_affine=(scale, bias)` (per-channel sequences) applies x * scale[c] + bias[c] inside the ingest kernel: a
+        uint8 pipeline passes (1 / (255 * std), -mean / std) and hands the raw uint8 NCHW batch to forward().
+
+        `alias_outputs=True` returns the SAME tensors on every call (views of plan-owned memory, overwritten by the
+        next forward): a zero-copy opt-in for pipelines that consume a result before the next call.  The default follows
+        the reference's contract (resnet.py:333-337): every call returns freshly allocated, caller-owned
+        tensors."""
         lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("pytorchcv_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -805,6 +840,13 @@ class CompiledModule:
         self.dtype = dtype_code(dtype)
         self.in_shape = tuple(int(v) for v in in_shape)
         self.use_graph = graph
+        self.alias_outputs = bool(alias_outputs)
+        self._affine = None
+        if input_affine is not None:
+            sc, bi = ([float(v) for v in t] for t in input_affine)
+            if len(sc) != in_shape[1] or len(bi) != in_shape[1] or in_shape[1] > 4:
+                raise ValueError("input_affine needs one scale and one bias per image channel (<= 4 channels)")
+            self._affine = ((C.c_float * len(sc))(*sc), (C.c_float * len(bi))(*bi))
         self.signature = weights_signature(module)
         N, Cin, H, W = self.in_shape
 
@@ -830,7 +872,9 @@ class CompiledModule:
                 flat = t.flat
                 t = b.egress(t)
                 t.flat = flat
-            t.buf.pinned = True
+            if t.tail is None:
+                t.buf.pinned = True
+                t.buf.first = -1   # stable from one forward to the next (never part of another tensor's slot)
             outs.append(t)
         self._outs = outs
 
@@ -855,12 +899,14 @@ class CompiledModule:
             for emit in b.ops:
                 emit(self._plan, ptr, wptr)
             torch.cuda.synchronize(self.device)
+            self._ptr = ptr
         self._in_ptr = ptr(self._in)
         self.arena_bytes = arena_bytes
         self.weight_bytes = b.weight_bytes
         self.num_ops = lib.pcv_plan_num_ops(self._plan)
-        self.num_launches = lib.pcv_plan_num_launches(self._plan) + 1  # + ingest
-        self._out_tensors = [self._tensor_of(t) for t in outs]
+        self.num_launches = lib.pcv_plan_num_launches(self._plan) + 1 + sum(t.tail is not None for t in outs)  # + ingest + edge ops
+        self._arena_views = [self._tensor_of(t) if t.tail is None else None for t in outs]
+        self._static_outs = None   # alias_outputs: edge tensors allocated once
         self._graph_stream = torch.cuda.Stream(device=self.device) if graph else None
 
     # -- weights ------------------------------------------------------------------------------------------------
@@ -931,44 +977,83 @@ class CompiledModule:
             raise ValueError(f"compiled for input {self.in_shape}, got {tuple(x.shape)}")
         if x.device != self.device:
             raise ValueError(f"compiled for {self.device}, input is on {x.device}: there is no CPU fallback")
-        if x.dtype != torch.float32 or not x.is_contiguous():
-            x = x.float().contiguous()
-        N, Cin, H, W = self.in_shape
-        cur = torch.cuda.current_stream(self.device)
-        if self.use_graph:
-            gs = self._graph_stream
-            gs.wait_stream(cur)
-            self._ingest(x, gs.cuda_stream)
-            _lib.call("pcv_plan_graph_launch", self._plan, gs.cuda_stream)
-            cur.wait_stream(gs)
-            x.record_stream(gs)
-        else:
-            self._ingest(x, cur.cuda_stream)
-            _lib.call("pcv_plan_run", self._plan, cur.cuda_stream)
-        return _unflatten(self._structure, list(self._out_tensors))
+        if x.dtype not in _IMG_TYPES:
+            x = x.float()
+        if not x.is_contiguous():
+            x = x.contiguous()
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            if self.use_graph:
+                gs = self._graph_stream
+                gs.wait_stream(cur)
+                self._ingest(x, gs.cuda_stream)
+                _lib.call("pcv_plan_graph_launch", self._plan, gs.cuda_stream)
+                cur.wait_stream(gs)
+                x.record_stream(gs)
+            else:
+                self._ingest(x, cur.cuda_stream)
+                _lib.call("pcv_plan_run", self._plan, cur.cuda_stream)
+            return _unflatten(self._structure, self._outputs(cur))
+
+    def _outputs(self, cur) -> list:
+        """The tensors of this call (on stream `cur`, after the plan): edge ops write straight into fresh tensors, logits
+        are copied out of the arena (<= 1 MB).  With alias_outputs the same plan-owned tensors are returned every time."""
+        if self.alias_outputs and self._static_outs is None:
+            self._static_outs = [v if t.tail is None else self._shape(torch.empty(
+                (t.N, t.C, t.H, t.W), dtype=torch.float32, device=self.device), t)
+                for t, v in zip(self._outs, self._arena_views)]
+        res = []
+        for i, (t, view) in enumerate(zip(self._outs, self._arena_views)):
+            if t.tail is None:
+                res.append(view if self.alias_outputs else view.clone())
+                continue
+            o = (self._static_outs[i] if self.alias_outputs
+                 else self._shape(torch.empty((t.N, t.C, t.H, t.W), dtype=torch.float32, device=self.device), t))
+            t.tail["launch"](self._ptr, o.data_ptr(), cur.cuda_stream)
+            res.append(o)
+        return res
+
+    @staticmethod
+    def _shape(o: torch.Tensor, t: TRef) -> torch.Tensor:
+        return o.view(t.N, -1) if t.flat else o
 
     def _ingest(self, x: torch.Tensor, stream: int) -> None:
-        """The network edge: NCHW fp32 image -> NHWC (channel-padded) or, for a strided stem, space-to-depth."""
+        """The network edge: NCHW image (fp32 as in the reference, or a bf16 / fp16 / uint8 copy of it) -> NHWC
+        (channel-padded) or, for a strided stem, space-to-depth."""
         N, Cin, H, W = self.in_shape
+        sc, bi = self._affine if self._affine is not None else (None, None)
         if self._stem_k:
-            _lib.call("pcv_stem_s2d_ingest", None, N, Cin, H, W, self._stem_k, x.data_ptr(), self._in_ptr, stream)
+            _lib.call("pcv_stem_s2d_ingest_ex", None, self.dtype, _IMG_TYPES[x.dtype], N, Cin, H, W, self._stem_k,
+                      x.data_ptr(), sc, bi, self._in_ptr, stream)
         else:
-            _lib.call("pcv_nchw_f32_to_nhwc", None, self.dtype, N, Cin, H, W, x.data_ptr(), self._in_ptr,
-                      self._in.pitch, stream)
+            _lib.call("pcv_nchw_to_nhwc_ex", None, self.dtype, _IMG_TYPES[x.dtype], N, Cin, H, W, x.data_ptr(), sc, bi,
+                      self._in_ptr, self._in.pitch, stream)
 
     def profile(self) -> list[tuple[str, float, float, float]]:
-        """[(op name, ms, algorithmic FLOPs, algorithmic bytes)] for one eager pass (synchronises)."""
+        """[(op name, ms, algorithmic FLOPs, algorithmic bytes)] for one eager pass (synchronises); the per-call edge ops
+        (fp32 NCHW outputs written after the plan) are timed the same way and appended."""
         lib = _lib.load()
         n = self.num_ops
         ms = (C.c_float * n)()
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.call("pcv_plan_profile", self._plan, stream, ms, n)
         rows = []
-        for i in range(n):
-            fl, by = C.c_double(), C.c_double()
-            _lib.call("pcv_plan_op_cost", self._plan, i, C.byref(fl), C.byref(by))
-            rows.append((lib.pcv_plan_op_name(self._plan, i).decode(), float(ms[i]),
-                         self._flops_override.get(i, fl.value), by.value))
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream(self.device)
+            _lib.call("pcv_plan_profile", self._plan, cur.cuda_stream, ms, n)
+            for i in range(n):
+                fl, by = C.c_double(), C.c_double()
+                _lib.call("pcv_plan_op_cost", self._plan, i, C.byref(fl), C.byref(by))
+                rows.append((lib.pcv_plan_op_name(self._plan, i).decode(), float(ms[i]),
+                             self._flops_override.get(i, fl.value), by.value))
+            for t in self._outs:
+                if t.tail is None:
+                    continue
+                o = torch.empty((t.N, t.C, t.H, t.W), dtype=torch.float32, device=self.device)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(cur)
+                t.tail["launch"](self._ptr, o.data_ptr(), cur.cuda_stream)
+                e1.record(cur)
+                e1.synchronize()
+                rows.append((t.tail["name"], e0.elapsed_time(e1), 0.0, t.tail["bytes"]))
         return rows
 
     def __del__(self):
@@ -979,6 +1064,10 @@ class CompiledModule:
             except Exception:
                 pass
             self._plan = None
+
+
+_IMG_TYPES = {torch.float32: _lib.IMG_F32, torch.bfloat16: _lib.IMG_BF16, torch.float16: _lib.IMG_F16,
+              torch.uint8: _lib.IMG_U8}
 
 
 def _flatten(obj):
@@ -1004,7 +1093,7 @@ def _unflatten(spec, flat):
 # ---------------------------------------------------------------------------------------------------------------
 # per-module cache used by the mirror modules' forward() and by accelerate()
 # ---------------------------------------------------------------------------------------------------------------
-_DEFAULT = {"dtype": "bf16", "graph": False}
+_DEFAULT = {"dtype": "bf16", "graph": True}   # mirror modules: compile on first call, CUDA-graph replay after
 # compiled plans per module instance; kept OUT of module.__dict__ so deepcopy / pickle / state_dict never see them
 _CACHES: "weakref.WeakKeyDictionary[nn.Module, dict]" = weakref.WeakKeyDictionary()
 
@@ -1019,7 +1108,18 @@ def set_default_precision(dtype: str) -> None:
     _DEFAULT["dtype"] = dtype
 
 
-def run_module(module: nn.Module, x: torch.Tensor, dtype=None, graph=None, check_weights: bool = True, **lower_kwargs):
+def _affine_key(a):
+    return None if a is None else (tuple(float(v) for v in a[0]), tuple(float(v) for v in a[1]))
+
+
+def set_default_graph(enabled: bool) -> None:
+    """Whether modules that were not explicitly accelerate()d replay their plan from a CUDA graph (default) or launch it
+    kernel by kernel."""
+    _DEFAULT["graph"] = bool(enabled)
+
+
+def run_module(module: nn.Module, x: torch.Tensor, dtype=None, graph=None, check_weights: bool = True,
+               alias_outputs: bool = False, input_affine: tuple | None = None, **lower_kwargs):
     """forward() of every mirror block/net: compile on first use (per input shape & tier), then run the plan."""
     if not isinstance(x, torch.Tensor) or x.dim() != 4:
         raise ValueError("expected an NCHW tensor")
@@ -1029,13 +1129,14 @@ def run_module(module: nn.Module, x: torch.Tensor, dtype=None, graph=None, check
     dtype = _DEFAULT["dtype"] if dtype is None else dtype
     graph = _DEFAULT["graph"] if graph is None else graph
     cache = plan_cache(module)
-    key = (tuple(x.shape), dtype_code(dtype), x.device.index, bool(graph), tuple(sorted(lower_kwargs.items())))
+    key = (tuple(x.shape), dtype_code(dtype), x.device.index, bool(graph), bool(alias_outputs),
+           _affine_key(input_affine), tuple(sorted(lower_kwargs.items())))
     cm = cache.get(key)
     if cm is not None and check_weights and cm.signature != weights_signature(module):
         cm = None  # parameters were replaced or modified in place (load_state_dict, .to(), optimizer step)
     if cm is None:
         cm = CompiledModule(module, tuple(x.shape), dtype=dtype, device=x.device, graph=graph,
-                            lower_kwargs=lower_kwargs)
+                            lower_kwargs=lower_kwargs, alias_outputs=alias_outputs, input_affine=input_affine)
         cache[key] = cm
     return cm(x)
 
@@ -1049,21 +1150,26 @@ def invalidate(module: nn.Module) -> None:
 class Accelerated(nn.Module):
     """Drop-in wrapper returned by accelerate(): same call signature as the wrapped reference module."""
 
-    def __init__(self, net: nn.Module, dtype="bf16", graph: bool = False, check_weights: bool = True):
+    def __init__(self, net: nn.Module, dtype="bf16", graph: bool = False, check_weights: bool = True,
+                 alias_outputs: bool = False, input_affine: tuple | None = None):
         super().__init__()
         self.net = net
-        self._dtype, self._graph, self._check = dtype, graph, check_weights
+        self._dtype, self._graph, self._check, self._alias = dtype, graph, check_weights, alias_outputs
+        self._affine = input_affine
 
     def forward(self, x):
-        return run_module(self.net, x, dtype=self._dtype, graph=self._graph, check_weights=self._check)
+        return run_module(self.net, x, dtype=self._dtype, graph=self._graph, check_weights=self._check,
+                          alias_outputs=self._alias, input_affine=self._affine)
 
     def compiled(self, x: torch.Tensor) -> CompiledModule:
         self.forward(x)
-        key = (tuple(x.shape), dtype_code(self._dtype), x.device.index, bool(self._graph), ())
+        key = (tuple(x.shape), dtype_code(self._dtype), x.device.index, bool(self._graph), bool(self._alias),
+               _affine_key(self._affine), ())
         return plan_cache(self.net)[key]
 
 
-def accelerate(net: nn.Module, dtype="bf16", graph: bool = False, check_weights: bool = True) -> Accelerated:
+def accelerate(net: nn.Module, dtype="bf16", graph: bool = False, check_weights: bool = True,
+               alias_outputs: bool = False, input_affine: tuple | None = None) -> Accelerated:
     """Compile an eval-mode pytorchcv network (reference or mirror modules) for the B200 path.
 
     Opt-in per model instance (the reference's own _test()s call .backward() on eval nets, so a
@@ -1071,4 +1177,5 @@ def accelerate(net: nn.Module, dtype="bf16", graph: bool = False, check_weights:
     if net.training:
         raise RuntimeError("pytorchcv_b200 is an eval-mode path: call net.eval() first")
     dtype_code(dtype)
-    return Accelerated(net, dtype=dtype, graph=graph, check_weights=check_weights)
+    return Accelerated(net, dtype=dtype, graph=graph, check_weights=check_weights, alias_outputs=alias_outputs,
+                       input_affine=input_affine)

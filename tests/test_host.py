@@ -113,11 +113,13 @@ def test_lowering_and_arena(name, shape, n_ops, tier):
     x.buf.first, x.buf.pinned = -1, True
     out = PL.lower(b, net, x)
     _, trefs = PL._flatten(out)
-    assert len(b.ops) == n_ops
+    # plan ops + the per-call edge ops (fp32 NCHW outputs written after the plan into fresh, caller-owned tensors)
+    assert len(b.ops) + sum(t.tail is not None for t in trefs) == n_ops
     for t in trefs:
         t.buf.pinned = True
     if name.startswith("deeplab"):
         assert [(t.N, t.C, t.H, t.W, t.layout) for t in trefs] == [(N, 21, 480, 480, "nchw")] * 2
+        assert all(t.tail is not None and t.buf.nbytes == 0 for t in trefs)   # no arena storage: nothing to alias
     else:
         assert [(t.N, t.C, t.flat) for t in trefs] == [(N, 1000, True)]
     top = PL._assign_offsets(b.bufs)
