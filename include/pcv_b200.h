@@ -179,6 +179,23 @@ PCV_API int pcv_stem_s2d_weights(int Cout, int C, int k, const float* w, float* 
 PCV_API int pcv_bilinear_upsample_ac(pcv_plan* plan, int dtype, int N, int Hin, int Win, int C, const void* x, int in_pitch,
                              int Hout, int Wout, void* y, int out_pitch, int out_nchw_f32, pcv_stream stream);
 
+/* ---- multi-GPU exchange ---------------------------------------------------------------------------- */
+/* Batch-sharded inference has exactly one exchange per step: an all-gather of every rank's [N/G, classes] logits.  The
+ * reference has no multi-GPU code; this replaces the host-launched ncclAllGather a data-parallel wrapper would issue with
+ * ONE device-initiated kernel over NVLink peer memory (push to every peer, flag, wait for every peer, drain), so a step
+ * has no host-side collective and no second stream.  Each rank owns an exchange buffer of pcv_peer_buffer_bytes() bytes
+ * (cudaMalloc, zeroed; exported as a 64-byte CUDA IPC handle) that every peer process maps with pcv_peer_buffer_open.
+ * Every rank must call pcv_peer_allgather the same number of times, in the same order, for a given set of buffers. */
+PCV_API int pcv_peer_buffer_bytes(int world, size_t bytes_per_rank, size_t* total);
+PCV_API int pcv_peer_buffer_alloc(size_t bytes, void** ptr, void* ipc_handle_out_64B_host);
+PCV_API int pcv_peer_buffer_open(const void* ipc_handle_64B_host, void** ptr);
+PCV_API int pcv_peer_buffer_close(void* ptr);
+PCV_API int pcv_peer_buffer_free(void* ptr);
+/* out[r * bytes_per_rank ...] = rank r's `local` for every r (rank order == image order).  peer_bufs_host: HOST array of
+ * `world` device pointers - entry r is rank r's exchange buffer as mapped in this process (entry `rank` = the own buffer). */
+PCV_API int pcv_peer_allgather(pcv_plan* plan, const void* local, size_t bytes_per_rank, int rank, int world,
+                               void* const* peer_bufs_host, void* out, pcv_stream stream);
+
 /* ---- plans ---------------------------------------------------------------------------------------------------- */
 PCV_API int pcv_plan_create(pcv_plan** plan);
 PCV_API int pcv_plan_destroy(pcv_plan* plan);

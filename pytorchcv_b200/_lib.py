@@ -61,6 +61,12 @@ SIGNATURES = {
     "pcv_stem_s2d_ingest_ex": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "pcv_stem_s2d_weights": (_I, [_I, _I, _I, _P, _P, _P]),
     "pcv_stem_s2d_pool_ok": (_I, [_I, _I, _I, _I, _I]),
+    "pcv_peer_buffer_bytes": (_I, [_I, _Z, C.POINTER(_Z)]),
+    "pcv_peer_buffer_alloc": (_I, [_Z, C.POINTER(_P), _P]),
+    "pcv_peer_buffer_open": (_I, [_P, C.POINTER(_P)]),
+    "pcv_peer_buffer_close": (_I, [_P]),
+    "pcv_peer_buffer_free": (_I, [_P]),
+    "pcv_peer_allgather": (_I, [_P, _P, _Z, _I, _I, C.POINTER(_P), _P, _P]),
     "pcv_plan_create": (_I, [C.POINTER(_P)]),
     "pcv_plan_destroy": (_I, [_P]),
     "pcv_plan_num_ops": (_I, [_P]),

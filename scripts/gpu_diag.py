@@ -91,6 +91,27 @@ CASES = [
     ("g3x3_s2_128_256_g32",       3, 28, 28, 128, 256, 3, 2, 1, 1, 32, 1, 0, 0, "bf16"),
     ("g3x3_256_512_g64_14",       2, 14, 14, 256, 512, 3, 1, 1, 1, 64, 1, 0, 0, "bf16"),
     ("g1x1_32_64_g32",            2, 14, 14,  32,  64, 1, 1, 0, 1, 32, 0, 0, 0, "bf16"),
+    # fp16 storage tier (PCV_F16): one case per kernel family - the same sources compiled with the f16 element type
+    ("f16_gemm_1x1_res_relu",     2, 16, 16, 128, 128, 1, 1, 0, 1, 1, 1, 1, 0, "fp16"),
+    ("f16_gemm_1x1_bn32_twin",    4, 56, 56,  32,  32, 1, 1, 0, 1, 1, 2, 0, 0, "fp16"),
+    ("f16_gemm_1x1_odd_144_32",   2, 28, 28, 144,  32, 1, 1, 0, 1, 1, 0, 1, 0, "fp16"),
+    ("f16_pair_64_256_res",       8, 56, 56,  64, 256, 1, 1, 0, 1, 1, 1, 1, 0, "fp16"),
+    ("f16_pair_cout144",          4, 56, 56,  24, 144, 1, 1, 0, 1, 1, 2, 0, 0, "fp16"),
+    ("f16_conv3x3_s2",            2, 28, 28,  64, 128, 3, 2, 1, 1, 1, 1, 0, 0, "fp16"),
+    ("f16_conv3x3_d12",           1, 60, 60, 128,  64, 3, 1, 12, 12, 1, 1, 0, 0, "fp16"),
+    ("f16_halo3x3_64_64_56",      4, 56, 56,  64,  64, 3, 1, 1, 1, 1, 1, 0, 0, "fp16"),
+    ("f16_halo3x3_128_128_28",    5, 28, 28, 128, 128, 3, 1, 1, 1, 1, 1, 0, 0, "fp16"),
+    ("f16_halo_grouped_g32_c128", 2, 56, 56, 128, 128, 3, 1, 1, 1, 32, 1, 0, 0, "fp16"),
+    ("f16_grouped_g32_c256_s2",   2, 28, 28, 256, 256, 3, 2, 1, 1, 32, 1, 0, 0, "fp16"),
+    ("f16_fc_2048_1000_f32out",   8,  1,  1, 2048, 1000, 1, 1, 0, 1, 1, 0, 0, 1, "fp16"),
+    ("f16_head_256_21_direct",    2, 30, 30, 256,  21, 1, 1, 0, 1, 1, 0, 0, 0, "fp16"),
+    ("f16_simt_3x3",              2, 14, 14,  64,  64, 3, 1, 1, 1, 1, 1, 1, 2, "fp16"),
+    ("f16_dw3x3_s1",              2, 28, 28, 144, 144, 3, 1, 1, 1, 144, 2, 0, 0, "fp16"),
+    ("f16_dw3x3_s2_ragged",       3, 19, 23,  40,  40, 3, 2, 1, 1, 40, 0, 0, 0, "fp16"),
+    ("f16_dw3x3_s1_ragged_res",   2, 20, 18,  48,  48, 3, 1, 1, 1, 48, 1, 1, 0, "fp16"),
+    ("f16_dw5x5_s1_swish",        2, 28, 28, 240, 240, 5, 1, 2, 1, 240, 4, 0, 0, "fp16"),
+    ("f16_dw3x3_d2_generic",      2, 28, 28,  32,  32, 3, 1, 2, 2, 32, 1, 0, 0, "fp16"),
+    ("f16_gemm_1x1_hswish_res",   2, 14, 14, 128, 256, 1, 1, 0, 1, 1, 5, 1, 0, "fp16"),
 ]
 
 
@@ -100,8 +121,8 @@ def run_case(idx: int) -> dict:
     from pytorchcv_b200 import functional as P, _lib
 
     name, N, H, W, Cin, Cout, k, stride, pad, dil, groups, act, has_res, flags, dt = CASES[idx]
-    tdt = torch.bfloat16 if dt == "bf16" else torch.float32
-    code = _lib.BF16 if dt == "bf16" else _lib.F32
+    tdt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[dt]
+    code = {"bf16": _lib.BF16, "fp16": _lib.F16, "fp32": _lib.F32}[dt]
     g = torch.Generator().manual_seed(1000 + idx)
     x = torch.randn(N, Cin, H, W, generator=g)
     w = torch.randn(Cout, Cin // groups, k, k, generator=g) * (2.0 / (Cin // groups * k * k)) ** 0.5
@@ -114,7 +135,7 @@ def run_case(idx: int) -> dict:
     res = torch.randn(N, Cout, Ho, Wo, generator=g) if has_res else None
 
     # reference: same operand rounding as the tier (bf16 activations / BN-folded bf16 weights), fp32 math
-    rnd = (lambda t: t.to(torch.bfloat16).float()) if dt == "bf16" else (lambda t: t)
+    rnd = (lambda t: t.to(tdt).float()) if dt != "fp32" else (lambda t: t)
     scale = gamma / torch.sqrt(var + 1e-5)
     wf = rnd(w * scale.view(-1, 1, 1, 1)) if groups != Cin or dt == "fp32" or True else w
     bf = beta - mean * scale
@@ -137,7 +158,9 @@ def run_case(idx: int) -> dict:
     err = (got - ref).abs()
     denom = ref.abs().max().item() + 1e-12
     rel = err.max().item() / denom
-    tol = 1.2e-2 if dt == "bf16" and not (flags & 1) else (2e-3 if dt == "bf16" else 1e-4)
+    # one rounding of the result to the tier's storage type (bf16: 2^-9, fp16: 2^-12 relative) on top of fp32 accumulation;
+    # fp32 outputs of a 16-bit tier (flags & 1) only see the accumulation-order noise
+    tol = {"bf16": 1.2e-2, "fp16": 2e-3, "fp32": 1e-4}[dt] if not (flags & 1) or dt == "fp32" else 2e-3
     out = {"case": name, "rel": rel, "ok": bool(rel <= tol and torch.isfinite(got).all()), "ms": round(dt_ms, 2)}
     if not out["ok"]:
         bad = err > tol * denom

@@ -29,6 +29,11 @@ CASES = [  # name, k, Cout, act, N, H, W
     ("pool_stem7_64_w160", 7, 64, "relu", 5, 256, 160),
     ("pool_stem3_64_224", 3, 64, "relu6", 2, 224, 224),
     ("pool_stem5_64_192", 5, 64, "relu", 2, 192, 192),
+    # fp16 storage tier (the f16 build of the same kernel; name prefix selects the tier)
+    ("f16_stem7_64_224", 7, 64, "relu", 2, 224, 224),
+    ("f16_stem3_32_relu6_224", 3, 32, "relu6", 2, 224, 224),
+    ("f16_pool_stem7_64_224", 7, 64, "relu", 3, 224, 224),
+    ("f16_pool_stem3_64_160", 3, 64, "relu", 2, 160, 96),
 ]
 
 
@@ -41,7 +46,9 @@ def run(idx):
     name, k, cout, act, N, H, W = CASES[idx]
     blk = blocks.ConvBlock(in_channels=3, out_channels=cout, kernel_size=k, stride=2, padding=k // 2,
                            activation=(lambda: torch.nn.ReLU6(inplace=True)) if act == "relu6" else (lambda: torch.nn.ReLU(inplace=True)))
-    pool = name.startswith("pool_")
+    half = name.startswith("f16_")
+    tdt, tol = (torch.float16, 2e-3) if half else (torch.bfloat16, 1.2e-2)
+    pool = "pool_" in name
     if pool:
         blk = torch.nn.Sequential(blk, torch.nn.MaxPool2d(kernel_size=3, stride=2, padding=1))
     blk = seeded_init(blk.eval(), seed=3, randomize_bn=True)
@@ -49,7 +56,7 @@ def run(idx):
     cb = blk[0] if pool else blk
     bn = cb.bn
     scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
-    rnd = lambda t: t.to(torch.bfloat16).float()
+    rnd = lambda t: t.to(tdt).float()
     wf = rnd(cb.conv.weight * scale.view(-1, 1, 1, 1))
     bf = bn.bias - bn.running_mean * scale
     with torch.no_grad():
@@ -57,15 +64,15 @@ def run(idx):
         ref = ref.clamp(0, 6) if act == "relu6" else torch.relu(ref)
         if pool:
             ref = F.max_pool2d(ref, 3, 2, 1)
-    fast = P.accelerate(blk.cuda(), dtype="bf16", graph=False)
+    fast = P.accelerate(blk.cuda(), dtype="fp16" if half else "bf16", graph=False)
     y = fast(x.cuda()).float().cpu()
     torch.cuda.synchronize()
     cm = fast.compiled(x.cuda())
     names = [r[0] for r in cm.profile()]
     rel = float((y - ref).abs().max() / ref.abs().max())
-    out = {"case": name, "rel": rel, "ok": bool(rel <= 1.2e-2 and torch.isfinite(y).all()), "ops": names}
+    out = {"case": name, "rel": rel, "ok": bool(rel <= tol and torch.isfinite(y).all()), "ops": names}
     if not out["ok"]:
-        err = (y - ref).abs() > 1.2e-2 * ref.abs().max()
+        err = (y - ref).abs() > tol * ref.abs().max()
         out["bad_frac"] = float(err.float().mean())
         out["bad_by_channel"] = [round(v, 2) for v in err.float().mean(dim=(0, 2, 3))[:16].tolist()]
         out["bad_by_row"] = [round(v, 2) for v in err.float().mean(dim=(0, 1, 3))[:16].tolist()]

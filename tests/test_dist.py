@@ -26,7 +26,13 @@ def _worker(rank, world, port, global_batch, q):
     full = torch.arange(global_batch * 5, dtype=torch.float32).view(global_batch, 5)
     runner = parallel.ShardedInference(lambda t: t * 2.0, r, w)       # stand-in replica: logits = 2 * x
     out = runner(full[runner.local_slice(global_batch)], global_batch=global_batch)
-    q.put((rank, torch.equal(out, full * 2.0), tuple(out.shape)))
+    ok = torch.equal(out, full * 2.0)
+    # tuple outputs (DeepLabv3 / FCN / PSPNet with aux=True): gathered element-wise, structure preserved
+    seg = parallel.ShardedInference(lambda t: (t + 1.0, [t - 1.0]), r, w, exchange="nccl")
+    main, (aux,) = seg(full[runner.local_slice(global_batch)], global_batch=global_batch)
+    ok = ok and torch.equal(main, full + 1.0) and torch.equal(aux, full - 1.0)
+    ok = ok and runner.exchange_used.startswith("nccl")          # CPU tensors never take the peer-memory kernel
+    q.put((rank, ok, tuple(out.shape)))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 import pytorchcv_b200 as P
-from oracle import oracle_forward, oracle_forward_bf16_storage, seeded_init, seeded_input
+from oracle import oracle_forward, oracle_forward_16bit_storage, oracle_forward_bf16_storage, seeded_init, seeded_input
 from conftest import GOLDEN
 from test_oracle import BLOCKS, NETS
 
@@ -63,8 +63,8 @@ def test_fp32_tier_seresnext_default_bn_meets_1e4():
 
 
 BF16_E2E = {  # nets whose end-to-end bf16 error is within the north star's 2e-2 (SURVEY 7.3 explains the others)
-    "resnet18": 2e-2, "resnet50": 2e-2, "mobilenet_w1": 2e-2, "deeplabv3_resnetd50b_voc": 2.5e-2,
-    "fcn8sd_resnetd50b_voc": 2.5e-2, "pspnet_resnetd50b_voc": 2.5e-2,
+    "resnet18": 2e-2, "resnet50": 2e-2, "mobilenet_w1": 2e-2, "deeplabv3_resnetd50b_voc": 2e-2,
+    "fcn8sd_resnetd50b_voc": 2e-2, "pspnet_resnetd50b_voc": 2e-2,
 }
 
 
@@ -95,9 +95,138 @@ def test_bf16_tier(stem, name, shape, sub):
         floor_torch = max(_rel(t.float(), w) for t, w in zip(theirs, want))
         floor_emu = max(_rel(e, w) for e, w in zip(emu, want))
         floor = max(floor_torch, floor_emu)
-        assert max(rels) <= 1.5 * floor + 1e-2, (name, rels, floor_torch, floor_emu)
+        assert max(rels) <= 1.5 * floor + 2e-3, (name, rels, floor_torch, floor_emu)
         vs_emu = max(_rel(g.float().cpu(), e) for g, e in zip(got, emu))
-        assert vs_emu <= 1.5 * floor_emu + 1e-2, (name, vs_emu, floor_emu)
+        assert vs_emu <= 1.5 * floor_emu + 2e-3, (name, vs_emu, floor_emu)
+
+
+# fp16 storage tier (PCV_F16): same kernels and MMA rate as bf16, 3 more mantissa bits.  With the reference's own init
+# statistics (the weights bench.py times) every network below meets the north star's 2e-2 + identical top-1 end to end;
+# SE-ResNeXt-50 does not in ANY 16-bit format (4.8e-2 in the fp16 emulation: saturating SE gates).
+FP16_DEFAULT_BN = {"resnet50": 2e-3, "mobilenetv2_w1": 2e-2, "mobilenet_w1": 2e-2, "efficientnet_b0": 2e-2,
+                   "mobilenetv3_large_w1": 2e-2, "deeplabv3_resnetd50b_voc": 5e-3}
+FP16_SHAPES = {n[1]: n[2] for n in NETS}
+
+
+@pytest.mark.parametrize("name", sorted(FP16_DEFAULT_BN))
+def test_fp16_tier_default_bn_meets_2e2_and_top1(name):
+    net = seeded_init(P.get_model(name, pretrained=False).eval(), seed=0, randomize_bn=False)
+    x = seeded_input(FP16_SHAPES[name], seed=1234)
+    want = _tuple(oracle_forward(net, x))
+    got = _tuple(P.accelerate(copy.deepcopy(net).cuda(), dtype="fp16")(x.cuda()))
+    for g, w in zip(got, want):
+        g = g.float().cpu()
+        assert torch.isfinite(g).all()
+        assert _rel(g, w) <= FP16_DEFAULT_BN[name], (name, _rel(g, w))
+    if want[0].dim() == 2:
+        assert torch.equal(got[0].float().cpu().argmax(1), want[0].argmax(1))
+    else:
+        assert (got[0].float().cpu().argmax(1) == want[0].argmax(1)).float().mean().item() >= 0.995
+
+
+@pytest.mark.parametrize("name", ["resnet50", "mobilenetv2_w1", "efficientnet_b0", "seresnext50_32x4d"])
+def test_fp16_tier_random_bn_within_storage_floor(name):
+    """Randomised BN statistics: the error must stay within 1.5x of what the fp16 storage contract itself costs
+    (oracle/bf16_storage.py with storage=float16) and track that emulation closely."""
+    net = seeded_init(P.get_model(name, pretrained=False).eval(), seed=0, randomize_bn=True)
+    x = seeded_input(FP16_SHAPES[name], seed=1234)
+    want = oracle_forward(net, x)
+    emu = oracle_forward_16bit_storage(net, x, storage=torch.float16)
+    got = P.accelerate(copy.deepcopy(net).cuda(), dtype="fp16")(x.cuda()).float().cpu()
+    floor = _rel(emu, want)
+    assert torch.isfinite(got).all()
+    assert _rel(got, want) <= 1.5 * floor + 1e-3, (name, _rel(got, want), floor)
+    assert _rel(got, emu) <= 1.5 * floor + 1e-3, (name, _rel(got, emu), floor)
+    if name in ("resnet50", "efficientnet_b0"):
+        assert _rel(got, want) <= 2e-2 and torch.equal(got.argmax(1), want.argmax(1))
+
+
+# ---- parity at the BENCHMARKED shapes (BASELINE.json configs; bench.py's weights: torch.manual_seed(0) default init) ----
+# The bs256 / bs16 / bs8 plans pick different tile splits than the bs2 nets above; a fixed subsample of images spread
+# over the batch (first / last tile, CTA-range boundaries) is compared with the oracle evaluated on those images alone
+# (eval-mode images are independent).
+BENCH_CASES = [  # name, batch, H, tier, tolerance, images compared
+    ("resnet50", 256, 224, "bf16", 2e-2, (0, 1, 37, 100, 127, 128, 200, 255)),
+    ("mobilenetv2_w1", 256, 224, "fp16", 2e-2, (0, 1, 37, 100, 127, 128, 200, 255)),
+    ("mobilenetv2_w1", 256, 224, "fp32", 1e-4, (0, 127, 255)),
+    ("seresnext50_32x4d", 256, 224, "fp32", 1e-4, (0, 127, 255)),
+    ("resnet18", 8, 224, "fp32", 1e-4, tuple(range(8))),
+    ("deeplabv3_resnetd50b_voc", 16, 480, "bf16", 2e-2, (0, 15)),
+]
+
+
+@pytest.mark.parametrize("name,batch,hw,tier,tol,picks", BENCH_CASES, ids=[f"{c[0]}-bs{c[1]}-{c[3]}" for c in BENCH_CASES])
+def test_parity_at_benchmarked_shape(name, batch, hw, tier, tol, picks):
+    torch.manual_seed(0)
+    kw = {"in_size": (hw, hw)} if name.startswith("deeplab") else {}
+    net = P.get_model(name, pretrained=False, **kw).eval()          # exactly bench.py's build_net()
+    x = torch.randn(batch, 3, hw, hw, generator=torch.Generator().manual_seed(1234))
+    idx = torch.tensor(picks)
+    want = _tuple(oracle_forward(net, x[idx]))
+    got = _tuple(P.accelerate(copy.deepcopy(net).cuda(), dtype=tier, graph=True)(x.cuda()))
+    for g, w in zip(got, want):
+        g = g.float().cpu()[idx]
+        assert g.shape == w.shape
+        assert _rel(g, w) <= tol, (name, tier, _rel(g, w))
+    if want[0].dim() == 2:
+        assert torch.equal(got[0].float().cpu()[idx].argmax(1), want[0].argmax(1))
+    else:
+        assert (got[0].float().cpu()[idx].argmax(1) == want[0].argmax(1)).float().mean().item() >= 0.97
+
+
+def test_outputs_are_caller_owned():
+    """forward returns freshly allocated tensors - a result must survive the next forward (eager and graph
+    replay, logits and fp32 NCHW segmentation maps); alias_outputs=True is the documented zero-copy opt-in."""
+    net = seeded_init(P.get_model("resnet18", pretrained=False).eval(), seed=0).cuda()
+    xa, xb = seeded_input((2, 3, 224, 224), seed=1).cuda(), seeded_input((2, 3, 224, 224), seed=2).cuda()
+    for graph in (False, True):
+        fast = P.accelerate(net, dtype="bf16", graph=graph)
+        ya = fast(xa)
+        keep = ya.clone()
+        yb = fast(xb)
+        torch.cuda.synchronize()
+        assert ya.data_ptr() != yb.data_ptr()
+        assert torch.equal(ya, keep) and not torch.equal(ya, yb)
+        outs = torch.cat([fast(t) for t in (xa, xb, xa)])           # the loader idiom the advisor flagged
+        assert torch.equal(outs[:2], keep) and torch.equal(outs[4:], keep)
+    seg = P.accelerate(seeded_init(P.get_model("deeplabv3_resnetd50b_voc", pretrained=False, in_size=(96, 96)).eval(),
+                                   seed=0).cuda(), dtype="bf16")
+    sa, sb = seeded_input((1, 3, 96, 96), seed=3).cuda(), seeded_input((1, 3, 96, 96), seed=4).cuda()
+    y0, a0 = seg(sa)
+    k0, k1 = y0.clone(), a0.clone()
+    y1, _ = seg(sb)
+    torch.cuda.synchronize()
+    assert torch.equal(y0, k0) and torch.equal(a0, k1) and not torch.equal(y0, y1)
+    shared = P.accelerate(net, dtype="bf16", alias_outputs=True)
+    z0 = shared(xa)
+    z1 = shared(xb)
+    assert z0.data_ptr() == z1.data_ptr()
+
+
+def test_image_types_at_the_network_edge():
+    """The ingest kernels take the reference's fp32 NCHW batch or a bf16 / fp16 / uint8 copy of it (half / a quarter of
+    the host->device bytes); uint8 pipelines fold 1/255, mean and std into the per-channel affine."""
+    net = seeded_init(P.get_model("resnet18", pretrained=False).eval(), seed=0).cuda()
+    g = torch.Generator().manual_seed(7)
+    u8 = torch.randint(0, 256, (2, 3, 224, 224), generator=g, dtype=torch.uint8)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    xf = ((u8.float() / 255.0) - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    ref = P.accelerate(net, dtype="bf16")(xf.cuda())
+    aff = ([1.0 / (255.0 * s) for s in std], [-m / s for m, s in zip(mean, std)])
+    got = P.accelerate(net, dtype="bf16", input_affine=aff)(u8.cuda())
+    assert _rel(got.cpu(), ref.cpu()) <= 1e-2                      # same values up to one bf16 rounding of the pixels
+    for dt in (torch.bfloat16, torch.float16):
+        y = P.accelerate(net, dtype="bf16")(xf.to(dt).cuda())
+        assert _rel(y.cpu(), ref.cpu()) <= 1e-2
+    exact = P.accelerate(net, dtype="bf16")(xf.to(torch.bfloat16).float().cuda())
+    assert torch.equal(exact, P.accelerate(net, dtype="bf16")(xf.to(torch.bfloat16).cuda()))
+    from pytorchcv_b200 import blocks as B                           # generic NHWC ingest (no strided stem), both tiers
+    blk = seeded_init(B.conv3x3_block(in_channels=8, out_channels=16).eval(), seed=1).cuda()
+    v8 = torch.randint(0, 256, (2, 8, 12, 10), generator=g, dtype=torch.uint8)
+    for tier in ("bf16", "fp16", "fp32"):
+        a = P.accelerate(blk, dtype=tier)(v8.cuda())
+        b = P.accelerate(blk, dtype=tier)(v8.float().cuda())
+        assert torch.equal(a, b)                                     # 0..255 are exact in every tier's storage type
 
 
 @pytest.mark.parametrize("stem", sorted(BLOCKS))
@@ -122,10 +251,10 @@ def test_mirror_blocks_forward(stem, tier, tol):
 def test_recompiles_when_weights_change_and_caches_per_shape():
     net = seeded_init(P.get_model("resnet18", pretrained=False).eval(), seed=0).cuda()
     x = seeded_input((2, 3, 224, 224)).cuda()
-    y0 = net(x).clone()
+    y0 = net(x)
     from pytorchcv_b200.plan import plan_cache
     assert len(plan_cache(net)) == 1
-    y1 = net(x).clone()
+    y1 = net(x)
     assert torch.equal(y0, y1)                       # deterministic replay
     net(seeded_input((1, 3, 224, 224)).cuda())
     assert len(plan_cache(net)) == 2                 # one plan per input shape
@@ -141,10 +270,10 @@ def test_recompiles_when_weights_change_and_caches_per_shape():
 def test_cuda_graph_replay_matches_eager():
     net = seeded_init(P.get_model("resnet50", pretrained=False).eval(), seed=0).cuda()
     x = seeded_input((4, 3, 224, 224)).cuda()
-    eager = P.accelerate(net, dtype="bf16", graph=False)(x).clone()
+    eager = P.accelerate(net, dtype="bf16", graph=False)(x)
     graphed = P.accelerate(copy.deepcopy(net), dtype="bf16", graph=True)
-    a = graphed(x).clone()
-    b = graphed(x).clone()
+    a = graphed(x)
+    b = graphed(x)
     torch.cuda.synchronize()
     assert torch.equal(a, eager) and torch.equal(b, eager)
 
