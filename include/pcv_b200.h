@@ -71,6 +71,10 @@ enum pcv_conv_flags {
   PCV_CONV_FORCE_SIMT = 2,   /* bf16 tier only: use the CUDA-core kernel (cross-check for the tcgen05 path) */
   PCV_CONV_A_IM2COL = 4,     /* bf16 tier only: use the im2col TMA descriptor even for 1x1 stride-1 */
   PCV_CONV_IN_OVERLAP = 8,   /* x is an overlapping-window VIEW: in_pitch < Cin is allowed (space-to-depth stem) */
+  PCV_CONV_F32_SPLIT = 32,   /* fp32 tier only: evaluate the dense / grouped conv on the tensor cores as a 3-way bf16 split of
+                                the fp32 activations and weights (24 significant bits per operand, exact products, fp32
+                                accumulation: fp32-FMA accuracy at tcgen05 rate).  Needs pcv_conv_workspace_bytes() of
+                                scratch handed to pcv_conv2d_bias_act_ws; weights must be packed with the same flag */
   PCV_CONV_POOL3S2 = 16      /* space-to-depth stem only: fuse the following MaxPool2d(3, stride 2, pad 1) (ResInitBlock,
                                 resnet.py:255-263); y is the POOLED map [N, Ho/2, Wo/2, Cout].  Ask pcv_stem_s2d_pool_ok first */
 };
@@ -112,6 +116,12 @@ PCV_API int pcv_pack_conv_weights(const pcv_conv_desc* d, int dtype, const float
  * mobilenetv2.py:62-71) fused into one kernel.  residual may be NULL. */
 PCV_API int pcv_conv2d_bias_act(pcv_plan* plan, const pcv_conv_desc* d, int dtype, const void* x, const void* w_packed,
                         const float* bias, const void* residual, void* y, pcv_stream stream);
+
+/* The same op for descriptors that need scratch memory (PCV_CONV_F32_SPLIT: the split copy of x).  `workspace`: device
+ * buffer of pcv_conv_workspace_bytes() bytes (0 = none needed), 16-byte aligned, private to this op while it runs. */
+PCV_API int pcv_conv_workspace_bytes(const pcv_conv_desc* d, int dtype, size_t* bytes);
+PCV_API int pcv_conv2d_bias_act_ws(pcv_plan* plan, const pcv_conv_desc* d, int dtype, const void* x, const void* w_packed,
+                           const float* bias, const void* residual, void* y, void* workspace, pcv_stream stream);
 
 /* nn.MaxPool2d(k, stride, pad), -inf padding, floor mode (resnet.py:255-258, senet.py:154-157). */
 PCV_API int pcv_maxpool2d(pcv_plan* plan, int dtype, int N, int H, int W, int C, int k, int stride, int pad, const void* x,

@@ -407,7 +407,7 @@ __global__ void igemm_pack_kernel(const float* __restrict__ w, const float* __re
   }
 }
 
-static int pick_bn(const pcv_conv_desc& d, int tiles_m) {
+int pick_bn(const pcv_conv_desc& d, int tiles_m) {
   if (d.groups > 1) return 64;
   if (d.Cout <= 32) return 32;
   if (d.Cout <= 64) return 64;
@@ -467,7 +467,7 @@ int igemm_pack(const pcv_conv_desc& d, const float* w, const float* conv_bias, c
 // ------------------------------------------------------------------------------------------------------------
 // tensor maps
 // ------------------------------------------------------------------------------------------------------------
-static int make_tiled_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+int make_tiled_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
                          uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -485,7 +485,7 @@ static int make_tiled_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint
   return PCV_OK;
 }
 
-static int make_im2col_4d(CUtensorMap* tm, const void* base, const pcv_conv_desc& d, int in_pitch) {
+int make_im2col_4d(CUtensorMap* tm, const void* base, const pcv_conv_desc& d, int in_pitch) {
   EncodeIm2colFn fn = encode_im2col_fn();
   if (!fn) return fail(PCV_ERR_CUDA, "cuTensorMapEncodeIm2col entry point not available");
   cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.N};

@@ -46,6 +46,12 @@ int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const 
 int stem_halo_try_make(const pcv_conv_desc& d, const void* x, const void* w, const float* bias, const void* res,
                        void* y, Op** out);
 
+// conv_igemm.cu helpers shared with conv_f32x3.cu
+int pick_bn(const pcv_conv_desc& d, int tiles_m);
+int make_tiled_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                  uint32_t box_inner, uint32_t box_rows, CUtensorMapSwizzle swz);
+int make_im2col_4d(CUtensorMap* tm, const void* base, const pcv_conv_desc& d, int in_pitch);
+
 void igemm2_pick_smem(int bn, int num_kblocks, bool has_res, int taps, int* stages, int* ksub, int* nstg);
 
 }  // namespace PCV_TIER

@@ -175,7 +175,7 @@ gap_kernel(int HW, int C, int slab, const T* __restrict__ x, int in_pitch, void*
       const float mean = s / static_cast<float>(HW);
       const size_t o = static_cast<size_t>(n) * C + c0 + ch;
       if (out_f32) reinterpret_cast<float*>(out)[o] = mean;
-      else reinterpret_cast<__nv_bfloat16*>(out)[o] = __float2bfloat16(mean);
+      else V8<T>::st1(reinterpret_cast<T*>(out) + o, mean);   // the tier's own storage type
     }
   }
 }

@@ -10,9 +10,12 @@
 //   2. signal : system-scope fence, then flags[rank] := e in every peer's control block (st.release.sys);
 //   3. wait   : spin (ld.acquire.sys) until the LOCAL flags of all ranks are >= e: every shard of step e has landed here;
 //   4. drain  : copy slab e&1 (rank order == image order) into the caller's output tensor; epoch := e.
-// No host synchronisation, no second stream, no launch per peer.  Slab parity makes the push of step e+1 safe: a peer can
+// The kernel runs as a small grid (64 CTAs): step 2 is done by the last CTA to finish its part of the push and the epoch
+// is closed by the last CTA to finish draining (two counters in the control block).  No host synchronisation, no second stream, no launch per peer.  Slab parity makes the push of step e+1 safe: a peer can
 // only be one step ahead (it needs this rank's step-e flag to finish step e), and slab (e+1)&1 was drained here in step
 // e-1, before this rank signalled step e.
+#include <algorithm>
+
 #include "ptx.cuh"
 #include "runtime.h"
 
@@ -41,23 +44,38 @@ __device__ __forceinline__ uint4 ld_cg(const uint4* p) {   // L2 only: remote GP
   return v;
 }
 
-__global__ void __launch_bounds__(1024, 1)
+// Grid of PEER_CTAS CTAs.  Intra-grid ordering uses two counters in the control block ("last CTA to arrive acts"): no CTA
+// ever waits for another CTA of its own grid, so the kernel needs no co-residency guarantee.
+constexpr int PEER_CTAS = 64;
+constexpr int PEER_THREADS = 512;
+
+__global__ void __launch_bounds__(PEER_THREADS)
 peer_allgather_kernel(const PeerArgs a, const uint4* __restrict__ local, uint4* __restrict__ out) {
   unsigned char* mine = a.bufs[a.rank];
-  uint32_t* ctrl = reinterpret_cast<uint32_t*>(mine);          // [0] epoch, [16 + r] flag of rank r
-  const uint32_t e = ctrl[0] + 1;
+  uint32_t* ctrl = reinterpret_cast<uint32_t*>(mine);   // [0] epoch, [1] pushed-CTA count, [2] drained-CTA count, [16 + r] flag of rank r
+  const uint32_t e = *reinterpret_cast<volatile uint32_t*>(ctrl) + 1;   // stable: only rewritten after EVERY CTA has drained
   const size_t vecs = a.bytes >> 4;
   const size_t slab_off = PEER_CTRL_BYTES + static_cast<size_t>(e & 1) * a.world * a.bytes;
-  // 1. push
-  for (int p = 0; p < a.world; ++p) {
-    uint4* dst = reinterpret_cast<uint4*>(a.bufs[p] + slab_off + static_cast<size_t>(a.rank) * a.bytes);
-    for (size_t i = threadIdx.x; i < vecs; i += blockDim.x) dst[i] = local[i];
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthr = static_cast<size_t>(gridDim.x) * blockDim.x;
+  __shared__ int is_last;
+  // 1. push: this rank's shard into slot `rank` of slab e&1 of every rank's buffer (the local vector is read once)
+  for (size_t i = tid; i < vecs; i += nthr) {
+    const uint4 v = local[i];
+    for (int p = 0; p < a.world; ++p)
+      reinterpret_cast<uint4*>(a.bufs[p] + slab_off + static_cast<size_t>(a.rank) * a.bytes)[i] = v;
   }
-  // 2. signal
+  // 2. signal: the CTA that completes the push tells every peer that this rank's shard of step e has been written
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x < a.world) st_release_sys(reinterpret_cast<uint32_t*>(a.bufs[threadIdx.x]) + 16 + a.rank, e);
-  // 3. wait (a peer that never arrives is a protocol / launch error: trap after ~4 s instead of hanging the GPU)
+  if (threadIdx.x == 0) is_last = (atomicAdd(ctrl + 1, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) {
+    __threadfence_system();
+    if (threadIdx.x < a.world) st_release_sys(reinterpret_cast<uint32_t*>(a.bufs[threadIdx.x]) + 16 + a.rank, e);
+  }
+  // 3. wait until every rank's shard of step e has landed HERE (a peer that never arrives is a protocol / launch error:
+  //    trap after a few seconds instead of hanging the GPU)
   if (threadIdx.x < a.world) {
     const uint32_t* flag = ctrl + 16 + threadIdx.x;
     const long long t0 = clock64();
@@ -66,12 +84,17 @@ peer_allgather_kernel(const PeerArgs a, const uint4* __restrict__ local, uint4* 
     }
   }
   __syncthreads();
-  // 4. drain
+  // 4. drain slab e&1 (rank order == image order) into the caller's tensor
   const uint4* slab = reinterpret_cast<const uint4*>(mine + slab_off);
   const size_t total = vecs * a.world;
-  for (size_t i = threadIdx.x; i < total; i += blockDim.x) out[i] = ld_cg(slab + i);
+  for (size_t i = tid; i < total; i += nthr) out[i] = ld_cg(slab + i);
   __syncthreads();
-  if (threadIdx.x == 0) ctrl[0] = e;
+  if (threadIdx.x == 0 && atomicAdd(ctrl + 2, 1u) == gridDim.x - 1) {   // last CTA out: close the step
+    ctrl[1] = 0;
+    ctrl[2] = 0;
+    __threadfence();
+    *reinterpret_cast<volatile uint32_t*>(ctrl) = e;
+  }
 }
 
 struct PeerGatherOp : Op {
@@ -80,7 +103,8 @@ struct PeerGatherOp : Op {
   void* out;
   cudaError_t launch(cudaStream_t s) override {
     g_launches++;
-    peer_allgather_kernel<<<1, 1024, 0, s>>>(a, reinterpret_cast<const uint4*>(local), reinterpret_cast<uint4*>(out));
+    const int ctas = static_cast<int>(std::min<size_t>(PEER_CTAS, std::max<size_t>(1, (a.bytes >> 4) / PEER_THREADS)));
+    peer_allgather_kernel<<<ctas, PEER_THREADS, 0, s>>>(a, reinterpret_cast<const uint4*>(local), reinterpret_cast<uint4*>(out));
     return cudaGetLastError();
   }
 };

@@ -83,6 +83,7 @@ int conv_route(const pcv_conv_desc& d, int dtype, std::string* why) {
       pitch_or(d.out_pitch, d.Cout) % 8 == 0 && d.Cin % 8 == 0)
     return ROUTE_DW;
   if (is16(dtype) && !(d.flags & PCV_CONV_FORCE_SIMT) && bf::igemm_supported(d, why)) return ROUTE_IGEMM;
+  if (dtype == PCV_F32 && (d.flags & PCV_CONV_F32_SPLIT) && bf::igemm_split_supported(d, why)) return ROUTE_SPLIT;
   return ROUTE_SIMT;  // (validate_conv rejects overlapped / row-pitched views that reach this route)
 }
 
@@ -103,6 +104,7 @@ static int validate_conv(const pcv_conv_desc* d, int dtype) {
                   (d->flags & PCV_CONV_IN_OVERLAP),
               "in_row_pitch smaller than a row");
   PCV_REQUIRE(!(d->flags & PCV_CONV_OUT_F32) || is16(dtype), "OUT_F32 only applies to the 16-bit tiers");
+  PCV_REQUIRE(!(d->flags & PCV_CONV_F32_SPLIT) || dtype == PCV_F32, "F32_SPLIT only applies to the fp32 tier");
   PCV_REQUIRE(!(d->flags & PCV_CONV_POOL3S2) || ((d->flags & PCV_CONV_IN_OVERLAP) && is16(dtype)),
               "POOL3S2 only applies to the bf16 space-to-depth stem");
   if ((d->flags & PCV_CONV_IN_OVERLAP) || d->in_row_pitch != 0) {
@@ -141,6 +143,7 @@ int pcv_conv_packed_bytes(const pcv_conv_desc* d, int dtype, size_t* w_bytes, si
   switch (conv_route(*d, dtype, nullptr)) {
     case ROUTE_DW: return dw_packed_bytes(*d, dtype, w_bytes, bias_bytes);
     case ROUTE_IGEMM: return bf::igemm_packed_bytes(*d, w_bytes, bias_bytes);
+    case ROUTE_SPLIT: return bf::igemm_split_packed_bytes(*d, w_bytes, bias_bytes, nullptr);
     default: return simt_packed_bytes(*d, dtype, w_bytes, bias_bytes);
   }
 }
@@ -155,6 +158,7 @@ int pcv_pack_conv_weights(const pcv_conv_desc* d, int dtype, const float* w, con
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (conv_route(*d, dtype, nullptr)) {
     case ROUTE_DW: return dw_pack(*d, dtype, w, conv_bias, bn_gamma, bn_beta, bn_mean, bn_var, eps, w_packed, bias_out, s);
+    case ROUTE_SPLIT: return bf::igemm_split_pack(*d, w, conv_bias, bn_gamma, bn_beta, bn_mean, bn_var, eps, w_packed, bias_out, s);
     case ROUTE_IGEMM:
       return (dtype == PCV_F16 ? hf::igemm_pack : bf::igemm_pack)(*d, w, conv_bias, bn_gamma, bn_beta, bn_mean, bn_var, eps,
                                                                   w_packed, bias_out, s);
@@ -162,8 +166,16 @@ int pcv_pack_conv_weights(const pcv_conv_desc* d, int dtype, const float* w, con
   }
 }
 
-int pcv_conv2d_bias_act(pcv_plan* plan, const pcv_conv_desc* d, int dtype, const void* x, const void* w_packed,
-                        const float* bias, const void* residual, void* y, pcv_stream stream) {
+int pcv_conv_workspace_bytes(const pcv_conv_desc* d, int dtype, size_t* bytes) {
+  if (int rc = validate_conv(d, dtype)) return rc;
+  PCV_REQUIRE(bytes != nullptr, "NULL output pointer");
+  *bytes = 0;
+  if (conv_route(*d, dtype, nullptr) == ROUTE_SPLIT) return bf::igemm_split_packed_bytes(*d, nullptr, nullptr, bytes);
+  return PCV_OK;
+}
+
+int pcv_conv2d_bias_act_ws(pcv_plan* plan, const pcv_conv_desc* d, int dtype, const void* x, const void* w_packed,
+                           const float* bias, const void* residual, void* y, void* workspace, pcv_stream stream) {
   if (int rc = validate_conv(d, dtype)) return rc;
   PCV_REQUIRE(x && w_packed && bias && y, "NULL tensor pointer");
   Op* op = nullptr;
@@ -171,10 +183,16 @@ int pcv_conv2d_bias_act(pcv_plan* plan, const pcv_conv_desc* d, int dtype, const
   switch (conv_route(*d, dtype, nullptr)) {
     case ROUTE_DW: rc = dw_make(*d, dtype, x, w_packed, bias, residual, y, &op); break;
     case ROUTE_IGEMM: rc = (dtype == PCV_F16 ? hf::igemm_make : bf::igemm_make)(*d, x, w_packed, bias, residual, y, &op); break;
+    case ROUTE_SPLIT: rc = bf::igemm_split_make(*d, x, w_packed, bias, residual, y, workspace, &op); break;
     default: rc = simt_make(*d, dtype, x, w_packed, bias, residual, y, &op); break;
   }
   if (rc) return rc;
   return submit(plan, op, static_cast<cudaStream_t>(stream));
+}
+
+int pcv_conv2d_bias_act(pcv_plan* plan, const pcv_conv_desc* d, int dtype, const void* x, const void* w_packed,
+                        const float* bias, const void* residual, void* y, pcv_stream stream) {
+  return pcv_conv2d_bias_act_ws(plan, d, dtype, x, w_packed, bias, residual, y, nullptr, stream);
 }
 
 int pcv_plan_create(pcv_plan** plan) {

@@ -135,6 +135,15 @@ EncodeIm2colFn encode_im2col_fn();
 PCV_DECLARE_TIER_API(bf)
 PCV_DECLARE_TIER_API(hf)
 #undef PCV_DECLARE_TIER_API
+namespace bf {
+// conv_igemm.cu : the fp32 tier on the tensor cores (PCV_CONV_F32_SPLIT): 3-way bf16 split of fp32 operands
+int igemm_split_supported(const pcv_conv_desc& d, std::string* why);
+int igemm_split_packed_bytes(const pcv_conv_desc& d, size_t* w_bytes, size_t* b_bytes, size_t* ws_bytes);
+int igemm_split_pack(const pcv_conv_desc& d, const float* w, const float* conv_bias, const float* g, const float* b,
+                     const float* m, const float* v, float eps, void* w_packed, float* bias_out, cudaStream_t s);
+int igemm_split_make(const pcv_conv_desc& d, const void* x, const void* w, const float* bias, const void* res, void* y,
+                     void* workspace, Op** out);
+}  // namespace bf
 inline bool is16(int dtype) { return dtype == PCV_BF16 || dtype == PCV_F16; }
 // conv_simt.cu : CUDA-core direct convolution (fp32 tier; generic bf16 fallback / cross-check)
 int simt_packed_bytes(const pcv_conv_desc& d, int dtype, size_t* w_bytes, size_t* b_bytes);
@@ -150,7 +159,7 @@ int dw_pack(const pcv_conv_desc& d, int dtype, const float* w, const float* conv
 int dw_make(const pcv_conv_desc& d, int dtype, const void* x, const void* w, const float* bias, const void* res,
             void* y, Op** out);
 
-enum ConvRoute { ROUTE_IGEMM = 0, ROUTE_DW = 1, ROUTE_SIMT = 2 };
+enum ConvRoute { ROUTE_IGEMM = 0, ROUTE_DW = 1, ROUTE_SIMT = 2, ROUTE_SPLIT = 3 };
 int conv_route(const pcv_conv_desc& d, int dtype, std::string* why);
 
 }  // namespace pcv

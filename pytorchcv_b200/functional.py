@@ -82,8 +82,14 @@ def conv2d(x: torch.Tensor, packed: PackedConv, residual: torch.Tensor | None = 
     odt = torch.float32 if (d.flags & _lib.CONV_OUT_F32) else _tdt(packed.dtype)
     if out is None:
         out = torch.zeros((d.N, Ho, Wo, d.out_pitch or d.Cout), dtype=odt, device=x.device)
-    _lib.call("pcv_conv2d_bias_act", None, C.byref(d), packed.dtype, x.data_ptr(), packed.w.data_ptr(),
-              packed.bias.data_ptr(), residual.data_ptr() if residual is not None else None, out.data_ptr(), _stream())
+    ws = C.c_size_t()
+    _lib.call("pcv_conv_workspace_bytes", C.byref(d), packed.dtype, C.byref(ws))
+    scratch = torch.empty(ws.value + 16, dtype=torch.uint8, device=x.device) if ws.value else None
+    _lib.call("pcv_conv2d_bias_act_ws", None, C.byref(d), packed.dtype, x.data_ptr(), packed.w.data_ptr(),
+              packed.bias.data_ptr(), residual.data_ptr() if residual is not None else None, out.data_ptr(),
+              scratch.data_ptr() if scratch is not None else None, _stream())
+    if scratch is not None:
+        scratch.record_stream(torch.cuda.current_stream())
     return out
 
 

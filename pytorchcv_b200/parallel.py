@@ -65,7 +65,7 @@ class PeerExchange:
     exchange"): every rank owns an exchange buffer exported through CUDA IPC; torch.distributed only carries the 64-byte
     handles once at set-up.  Raises if any rank cannot map every peer (callers fall back to NCCL on ALL ranks)."""
 
-    MAX_BYTES = 8 << 20   # per rank: a single-CTA kernel; large segmentation maps go through NCCL
+    MAX_BYTES = 16 << 20   # per rank: a 64-CTA kernel sized for logits; large segmentation maps go through NCCL
 
     def __init__(self, rank: int, world: int, bytes_per_rank: int, device: torch.device, group=None):
         import ctypes as C
@@ -155,7 +155,8 @@ class ShardedInference:
         """The peer exchange for this output, set up on first use; None when the output / group is outside its domain."""
         if self._peer is not None:
             return self._peer
-        if self.exchange_used == "nccl" or self.exchange == "nccl":
+        if self.exchange == "nccl" or (self.exchange_used or "").startswith("nccl"):
+            self.exchange_used = "nccl: one all_gather_into_tensor per output"
             return None
         eligible = isinstance(y, torch.Tensor) and y.is_cuda and y.dim() == 2
         if eligible:

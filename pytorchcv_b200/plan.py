@@ -12,6 +12,7 @@ patterns raise (NotImplementedError / ValueError) at compile time.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from dataclasses import dataclass, field
 from typing import Any, Callable
@@ -23,6 +24,8 @@ from . import _lib
 from ._lib import (ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SIGMOID, ACT_SWISH, ACT_HSWISH, ACT_HSIGMOID, BF16, F16, F32,
                    ConvDesc)
 
+# fp32 tier: dense / grouped convs on the tensor cores as a 3-way bf16 split (PCV_F32_SPLIT=0: the CUDA-core kernel instead)
+_F32_SPLIT = os.environ.get("PCV_F32_SPLIT", "1") != "0"
 _ALIGN = 1024  # arena / weight blob alignment (TMA needs 16 B; 1 KiB keeps every tensor sector- and line-aligned)
 
 
@@ -255,20 +258,31 @@ class Builder:
             raise ValueError("conv output view has the wrong shape")
         if residual is not None and (residual.N, residual.H, residual.W, residual.C) != (x.N, Ho, Wo, cout):
             raise ValueError("residual shape does not match the conv output")
+        if self.dtype == F32 and _F32_SPLIT and groups != cin:
+            # the fp32 tier's dense / grouped convs run on the tensor cores as a 3-way bf16 split (include/pcv_b200.h
+            # PCV_CONV_F32_SPLIT); the library ignores the flag (CUDA-core kernel) for shapes the tcgen05 route cannot take
+            flags |= _lib.CONV_F32_SPLIT
         d = ConvDesc(N=x.N, H=x.H, W=x.W, Cin=x.C, Cout=cout, kh=kh, kw=kw, stride=k_stride, pad=k_pad, dil=k_dil,
                      groups=groups, act=act, in_pitch=x.pitch, out_pitch=out.pitch,
                      res_pitch=residual.pitch if residual is not None else 0,
                      flags=flags | (_lib.CONV_OUT_F32 if (out_f32 and _is16(self.dtype)) else 0))
-        wb, bb = C.c_size_t(), C.c_size_t()
+        wb, bb, ws = C.c_size_t(), C.c_size_t(), C.c_size_t()
         _lib.call("pcv_conv_packed_bytes", C.byref(d), self.dtype, C.byref(wb), C.byref(bb))
+        _lib.call("pcv_conv_workspace_bytes", C.byref(d), self.dtype, C.byref(ws))
         w_off, b_off = self._wblob(wb.value), self._wblob(bb.value)
         self.weight_jobs.append(("conv", (d, conv, bn, pad_cin, w_off, b_off)))
-        self._use(x, residual, out)
+        idx = self._use(x, residual, out)
+        scratch = None
+        if ws.value:   # private to this op: lives exactly as long as op `idx`
+            sbuf = Buf(nbytes=ws.value, first=idx, last=idx)
+            self.bufs.append(sbuf)
+            scratch = TRef(1, 1, 1, ws.value // 2, ws.value // 2, BF16, sbuf)
         dtype = self.dtype
 
         def emit(plan, ptr, wptr):
-            _lib.call("pcv_conv2d_bias_act", plan, C.byref(d), dtype, ptr(x), wptr(w_off), wptr(b_off),
-                      ptr(residual) if residual is not None else None, ptr(out), None)
+            _lib.call("pcv_conv2d_bias_act_ws", plan, C.byref(d), dtype, ptr(x), wptr(w_off), wptr(b_off),
+                      ptr(residual) if residual is not None else None, ptr(out),
+                      ptr(scratch) if scratch is not None else None, None)
         self.ops.append(emit)
         return out
 

@@ -112,6 +112,19 @@ CASES = [
     ("f16_dw5x5_s1_swish",        2, 28, 28, 240, 240, 5, 1, 2, 1, 240, 4, 0, 0, "fp16"),
     ("f16_dw3x3_d2_generic",      2, 28, 28,  32,  32, 3, 1, 2, 2, 32, 1, 0, 0, "fp16"),
     ("f16_gemm_1x1_hswish_res",   2, 14, 14, 128, 256, 1, 1, 0, 1, 1, 5, 1, 0, "fp16"),
+    # fp32 tier on the tensor cores (flags 32 = PCV_CONV_F32_SPLIT): 3-way bf16 split, fp32-FMA accuracy (tolerance 1e-5)
+    ("f32x3_3x3_64_64_res",       2, 14, 14,  64,  64, 3, 1, 1, 1, 1, 1, 1, 32, "fp32"),
+    ("f32x3_1x1_s2_64_128",       2, 28, 28,  64, 128, 1, 2, 0, 1, 1, 0, 0, 32, "fp32"),
+    ("f32x3_3x3_s2_128_256",      3, 28, 28, 128, 256, 3, 2, 1, 1, 1, 1, 0, 32, "fp32"),
+    ("f32x3_7x7_s2_c8",           2, 64, 64,   8,  64, 7, 2, 3, 1, 1, 1, 0, 32, "fp32"),
+    ("f32x3_1x1_16_96_relu6",     2, 28, 28,  16,  96, 1, 1, 0, 1, 1, 2, 0, 32, "fp32"),
+    ("f32x3_1x1_144_24_res",      2, 28, 28, 144,  24, 1, 1, 0, 1, 1, 0, 1, 32, "fp32"),
+    ("f32x3_3x3_512_512_7",       8,  7,  7, 512, 512, 3, 1, 1, 1, 1, 1, 1, 32, "fp32"),
+    ("f32x3_grouped_g32_c128",    2, 14, 14, 128, 128, 3, 1, 1, 1, 32, 1, 0, 32, "fp32"),
+    ("f32x3_grouped_g32_c256_s2", 2, 28, 28, 256, 256, 3, 2, 1, 1, 32, 1, 0, 32, "fp32"),
+    ("f32x3_1x1_swish_40_240",    2, 14, 14,  40, 240, 1, 1, 0, 1, 1, 4, 0, 32, "fp32"),
+    ("f32x3_3x3_d2_64_64",        2, 30, 30,  64,  64, 3, 1, 2, 2, 1, 1, 0, 32, "fp32"),
+    ("f32x3_fc_512_1000",         8,  1,  1, 512, 1000, 1, 1, 0, 1, 1, 0, 0, 32, "fp32"),
 ]
 
 
@@ -161,6 +174,8 @@ def run_case(idx: int) -> dict:
     # one rounding of the result to the tier's storage type (bf16: 2^-9, fp16: 2^-12 relative) on top of fp32 accumulation;
     # fp32 outputs of a 16-bit tier (flags & 1) only see the accumulation-order noise
     tol = {"bf16": 1.2e-2, "fp16": 2e-3, "fp32": 1e-4}[dt] if not (flags & 1) or dt == "fp32" else 2e-3
+    if flags & 32:
+        tol = 1e-5   # the split must be as good as an fp32 FMA chain, not merely within the tier's 1e-4
     out = {"case": name, "rel": rel, "ok": bool(rel <= tol and torch.isfinite(got).all()), "ms": round(dt_ms, 2)}
     if not out["ok"]:
         bad = err > tol * denom

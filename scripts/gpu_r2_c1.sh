@@ -2,7 +2,7 @@
 # round 2, call 1: full GPU test suite + the default bench line (all BASELINE configs) + a short reference-arm check
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/r02_c1_smi.txt 2>&1
-timeout 1500 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_multi.py 2>&1 | tail -60 > gpurun_out/r02_c1_pytest.log
+timeout 1500 python -m pytest tests -m gpu -q --deselect tests/test_gpu_multi.py 2>&1 | tail -60 > gpurun_out/r02_c1_pytest.log
 echo "pytest rc=$?" >> gpurun_out/r02_c1_pytest.log
 tail -5 gpurun_out/r02_c1_pytest.log
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_c1_bench.json 2> gpurun_out/r02_c1_bench.err

@@ -62,7 +62,7 @@ def test_maxpool_3x3_s2_p1(shape, dtype):
     assert torch.equal(got, want)  # max of representable values: exact
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 4e-3), (torch.float16, 5e-4), (torch.float32, 1e-6)])
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 4e-3), (torch.float16, 1e-3), (torch.float32, 1e-6)])
 @pytest.mark.parametrize("shape", [(4, 2048, 7, 7), (2, 256, 56, 56), (1, 72, 5, 3)])
 def test_global_avgpool(shape, dtype, tol):
     from pytorchcv_b200 import functional as P
@@ -74,7 +74,7 @@ def test_global_avgpool(shape, dtype, tol):
     assert _rel(got, want) <= tol
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 4e-3), (torch.float16, 5e-4), (torch.float32, 1e-6)])
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 4e-3), (torch.float16, 1e-3), (torch.float32, 1e-6)])
 @pytest.mark.parametrize("shape,k", [((2, 512, 60, 60), 6), ((1, 264, 15, 17), 3), ((3, 64, 7, 7), 2), ((2, 2048, 9, 9), 1)])
 def test_adaptive_avgpool(shape, k, dtype, tol):
     """nn.AdaptiveAvgPool2d(k) of PyramidPoolingBranch (pspnet.py:71): torch's floor/ceil bin edges, overlapping bins."""
