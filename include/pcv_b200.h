@@ -123,6 +123,18 @@ PCV_API int pcv_conv_workspace_bytes(const pcv_conv_desc* d, int dtype, size_t* 
 PCV_API int pcv_conv2d_bias_act_ws(pcv_plan* plan, const pcv_conv_desc* d, int dtype, const void* x, const void* w_packed,
                            const float* bias, const void* residual, void* y, void* workspace, pcv_stream stream);
 
+/* Cross-layer fusion of a bottleneck's tail (ResBottleneck.forward resnet.py:136-140 + ResUnit.forward :221-229):
+ *     y = act3( conv3_1x1( relu(conv2_3x3(x)) ) + residual )
+ * in one kernel - the 64-channel intermediate stays on the SM (TMEM -> registers -> shared memory -> tensor core).
+ * d2: the 3x3 ConvBlock (dense, stride 1, pad 1, Cin % 64 == 0, Cout == 64, ReLU); d3: the 1x1 ConvBlock (64 -> Cout,
+ * Cout % 128 == 0, act = the unit's ReLU/ReLU6, residual required); both packed with pcv_pack_conv_weights as usual.
+ * pcv_bottleneck_tail_fusable returns 1 when the pair is in the kernel's domain (16-bit tiers, W + 2 <= 64, even H),
+ * else 0 and the caller records the two convolutions separately. */
+PCV_API int pcv_bottleneck_tail_fusable(const pcv_conv_desc* d2, const pcv_conv_desc* d3, int dtype);
+PCV_API int pcv_bottleneck_tail(pcv_plan* plan, const pcv_conv_desc* d2, const pcv_conv_desc* d3, int dtype, const void* x,
+                        const void* w2_packed, const float* bias2, const void* w3_packed, const float* bias3,
+                        const void* residual, void* y, pcv_stream stream);
+
 /* nn.MaxPool2d(k, stride, pad), -inf padding, floor mode (resnet.py:255-258, senet.py:154-157). */
 PCV_API int pcv_maxpool2d(pcv_plan* plan, int dtype, int N, int H, int W, int C, int k, int stride, int pad, const void* x,
                   int in_pitch, void* y, int out_pitch, pcv_stream stream);

@@ -48,6 +48,8 @@ SIGNATURES = {
     "pcv_conv2d_bias_act": (_I, [_P, C.POINTER(ConvDesc), _I, _P, _P, _P, _P, _P, _P]),
     "pcv_conv_workspace_bytes": (_I, [C.POINTER(ConvDesc), _I, C.POINTER(_Z)]),
     "pcv_conv2d_bias_act_ws": (_I, [_P, C.POINTER(ConvDesc), _I, _P, _P, _P, _P, _P, _P, _P]),
+    "pcv_bottleneck_tail_fusable": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvDesc), _I]),
+    "pcv_bottleneck_tail": (_I, [_P, C.POINTER(ConvDesc), C.POINTER(ConvDesc), _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pcv_maxpool2d": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P]),
     "pcv_global_avgpool": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _I, _P]),
     "pcv_adaptive_avgpool": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P]),

@@ -195,6 +195,25 @@ int pcv_conv2d_bias_act(pcv_plan* plan, const pcv_conv_desc* d, int dtype, const
   return pcv_conv2d_bias_act_ws(plan, d, dtype, x, w_packed, bias, residual, y, nullptr, stream);
 }
 
+int pcv_bottleneck_tail_fusable(const pcv_conv_desc* d2, const pcv_conv_desc* d3, int dtype) {
+  if (!d2 || !d3 || !is16(dtype)) return 0;
+  if (validate_conv(d2, dtype) != PCV_OK || validate_conv(d3, dtype) != PCV_OK) return 0;
+  return bf::fused_tail_ok(*d2, *d3);
+}
+
+int pcv_bottleneck_tail(pcv_plan* plan, const pcv_conv_desc* d2, const pcv_conv_desc* d3, int dtype, const void* x,
+                        const void* w2_packed, const float* bias2, const void* w3_packed, const float* bias3,
+                        const void* residual, void* y, pcv_stream stream) {
+  if (int rc = validate_conv(d2, dtype)) return rc;
+  if (int rc = validate_conv(d3, dtype)) return rc;
+  PCV_REQUIRE(is16(dtype), "the fused bottleneck tail exists in the 16-bit tiers only");
+  Op* op = nullptr;
+  const int rc = (dtype == PCV_F16 ? hf::fused_tail_make : bf::fused_tail_make)(*d2, *d3, x, w2_packed, bias2, w3_packed, bias3,
+                                                                                residual, y, &op);
+  if (rc) return rc;
+  return submit(plan, op, static_cast<cudaStream_t>(stream));
+}
+
 int pcv_plan_create(pcv_plan** plan) {
   PCV_REQUIRE(plan != nullptr, "NULL plan out-pointer");
   *plan = new pcv_plan();

@@ -129,6 +129,10 @@ EncodeIm2colFn encode_im2col_fn();
   int win_make(int op_kind, int N, int H, int W, int C, int k, int stride, int pad, int act, const void* x,              \
                int in_pitch, const float* w, const float* bias, const void* res, int res_pitch, void* y, int out_pitch,  \
                Op** out);                                                                                                \
+  /* conv_igemm3x.cu : bottleneck tail  relu(conv3_1x1(relu(conv2_3x3(x))) + identity)  in one kernel */               \
+  int fused_tail_ok(const pcv_conv_desc& d2, const pcv_conv_desc& d3);                                                   \
+  int fused_tail_make(const pcv_conv_desc& d2, const pcv_conv_desc& d3, const void* x, const void* w2,                  \
+                      const float* bias2, const void* w3, const float* bias3, const void* res, void* y, Op** out);      \
   /* conv_igemm3s.cu : can the s2d stem take the fused max pool (pcv_stem_s2d_pool_ok) */                                \
   int stem_pool_ok(int C, int H, int W, int k, int Cout);                                                                \
   }

@@ -26,6 +26,16 @@ from ._lib import (ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SIGMOID, ACT_SWISH, ACT_HS
 
 # fp32 tier: dense / grouped convs on the tensor cores as a 3-way bf16 split (PCV_F32_SPLIT=0: the CUDA-core kernel instead)
 _F32_SPLIT = os.environ.get("PCV_F32_SPLIT", "1") != "0"
+# cross-layer fusion of bottleneck tails (pcv_bottleneck_tail): correct, but measured no faster than the two kernels it
+# replaces (shared-memory-port bound, csrc/conv_igemm3x.cu) - off unless asked for
+_FUSE_TAIL = [os.environ.get("PCV_FUSE_TAIL", "0") == "1"]
+
+
+def set_fuse_tail(enabled: bool) -> None:
+    """Record ResBottleneck tails (3x3 -> 1x1 + add + ReLU) as one fused kernel where the shapes allow it."""
+    _FUSE_TAIL[0] = bool(enabled)
+
+
 _ALIGN = 1024  # arena / weight blob alignment (TMA needs 16 B; 1 KiB keeps every tensor sector- and line-aligned)
 
 
@@ -286,6 +296,53 @@ class Builder:
         self.ops.append(emit)
         return out
 
+    def bottleneck_tail(self, x: TRef, cb2: nn.Module, cb3: nn.Module, residual: TRef, post_act: int) -> TRef | None:
+        """conv2 (3x3 ConvBlock) -> conv3 (1x1 ConvBlock) + residual + the unit's activation as ONE fused kernel
+        (include/pcv_b200.h pcv_bottleneck_tail), or None when the pair is outside that kernel's domain."""
+        if not _FUSE_TAIL[0] or not _is16(self.dtype) or residual is None or post_act not in (ACT_RELU, ACT_RELU6):
+            return None
+        for cb in (cb2, cb3):
+            if (type(cb).__name__ != "ConvBlock" or getattr(cb, "use_pad", False) or not cb.normalize
+                    or cb.conv.padding_mode != "zeros" or isinstance(cb.conv.padding, str) or cb.conv.bias is not None):
+                return None
+        if not cb2.activate or act_code(cb2.activ) != ACT_RELU or cb3.activate:
+            return None
+        c2, c3 = cb2.conv, cb3.conv
+        if c2.in_channels != x.C or c3.in_channels != c2.out_channels:
+            return None
+        try:
+            geo = [(c.kernel_size, _one(c.stride), _one(c.padding), _one(c.dilation), c.groups) for c in (c2, c3)]
+        except NotImplementedError:
+            return None
+        (k2, s2, p2, dl2, g2), (k3, s3, p3, dl3, g3) = geo
+        d2 = ConvDesc(N=x.N, H=x.H, W=x.W, Cin=x.C, Cout=c2.out_channels, kh=k2[0], kw=k2[1], stride=s2, pad=p2, dil=dl2,
+                      groups=g2, act=ACT_RELU, in_pitch=x.pitch, out_pitch=c2.out_channels, res_pitch=0, flags=0)
+        d3 = ConvDesc(N=x.N, H=x.H, W=x.W, Cin=c3.in_channels, Cout=c3.out_channels, kh=k3[0], kw=k3[1], stride=s3, pad=p3,
+                      dil=dl3, groups=g3, act=post_act, in_pitch=c3.in_channels, out_pitch=c3.out_channels,
+                      res_pitch=residual.pitch, flags=0)
+        if (residual.N, residual.H, residual.W, residual.C) != (x.N, x.H, x.W, c3.out_channels):
+            return None
+        if not _lib.load().pcv_bottleneck_tail_fusable(C.byref(d2), C.byref(d3), self.dtype):
+            return None
+        _check_bn(cb2.bn)
+        _check_bn(cb3.bn)
+        out = self.new(x.N, x.H, x.W, c3.out_channels)
+        offs = []
+        for d, cb in ((d2, cb2), (d3, cb3)):
+            wb, bb = C.c_size_t(), C.c_size_t()
+            _lib.call("pcv_conv_packed_bytes", C.byref(d), self.dtype, C.byref(wb), C.byref(bb))
+            w_off, b_off = self._wblob(wb.value), self._wblob(bb.value)
+            self.weight_jobs.append(("conv", (d, cb.conv, cb.bn, 0, w_off, b_off)))
+            offs += [w_off, b_off]
+        self._use(x, residual, out)
+        dtype = self.dtype
+
+        def emit(plan, ptr, wptr):
+            _lib.call("pcv_bottleneck_tail", plan, C.byref(d2), C.byref(d3), dtype, ptr(x), wptr(offs[0]), wptr(offs[1]),
+                      wptr(offs[2]), wptr(offs[3]), ptr(residual), ptr(out), None)
+        self.ops.append(emit)
+        return out
+
     def linear(self, x: TRef, fc: nn.Linear, out_f32: bool = True) -> TRef:
         """nn.Linear on pooled features == 1x1 conv on a 1x1 map (resnet.py:320-322,335-336)."""
         if (x.H, x.W) != (1, 1):
@@ -531,6 +588,12 @@ def _lower_se(b, m, x, identity=None, post_act=ACT_NONE, **kw):
 def _lower_resbody(b, m, x, residual=None, post_act=None, **kw):
     """conv1 -> conv2 [-> conv3] (resnet.py:63-66,136-140; resnext.py:56-59); the last conv takes the fusion."""
     convs = [m.conv1, m.conv2] + ([m.conv3] if hasattr(m, "conv3") else [])
+    if len(convs) == 3 and residual is not None and post_act is not None:
+        y1 = lower(b, convs[0], x)
+        fused = b.bottleneck_tail(y1, convs[1], convs[2], residual, post_act)   # 3x3 -> 1x1 + add + act in one kernel
+        if fused is not None:
+            return fused
+        return lower(b, convs[2], lower(b, convs[1], y1), residual=residual, post_act=post_act)
     for c in convs[:-1]:
         x = lower(b, c, x)
     return lower(b, convs[-1], x, residual=residual, post_act=post_act)

@@ -212,6 +212,50 @@ def test_parity_at_benchmarked_shape(name, batch, hw, tier, tol, picks):
         assert (got[0].float().cpu()[idx].argmax(1) == want[0].argmax(1)).float().mean().item() >= 0.97
 
 
+@pytest.mark.parametrize("tier,tol", [("bf16", 1.5e-2), ("fp16", 2e-3)])
+@pytest.mark.parametrize("cin,cout,shape", [(256, 256, (3, 56, 56)), (64, 256, (2, 56, 56)), (256, 256, (1, 30, 30)),
+                                             (128, 512, (2, 24, 40))])
+def test_fused_bottleneck_tail(cin, cout, shape, tier, tol):
+    """ResUnit (resnet.py:221-229) whose 3x3 -> 1x1 + add + ReLU tail runs as ONE kernel (pcv_bottleneck_tail): identity
+    and projection shortcuts, an odd number of 2-row tiles (N=1, H=30: phantom tile of the CTA pair), ragged widths.  The
+    oracle is fed this tier's operand rounding at the fused op's boundaries only loosely - the bound is the tier's."""
+    from pytorchcv_b200 import nets as M
+    n, h, w = shape
+    mid_ok = cout // 4 == 64
+    unit = seeded_init(M.ResUnit(cin, cout, stride=1, bottleneck=True, conv1_stride=True).eval(), seed=11, randomize_bn=True)
+    x = seeded_input((n, cin, h, w), seed=21)
+    want = oracle_forward(unit, x)
+    from pytorchcv_b200 import plan as PL
+    PL.set_fuse_tail(True)
+    try:
+        fast = P.accelerate(copy.deepcopy(unit).cuda(), dtype=tier, graph=False)
+        got = fast(x.cuda()).float().cpu()
+        names = [r[0] for r in fast.compiled(x.cuda()).profile()]
+    finally:
+        PL.set_fuse_tail(False)
+    assert any(nm.startswith("conv_tc3x fused") for nm in names) == mid_ok, names
+    assert got.shape == want.shape and torch.isfinite(got).all()
+    assert _rel(got, want) <= tol, (_rel(got, want), names)
+
+
+def test_fused_bottleneck_tail_whole_net():
+    """ResNet-50 with its three stage-1 tails fused: same logits as the unfused plan to the tier's rounding, same top-1."""
+    from pytorchcv_b200 import plan as PL
+    net = seeded_init(P.get_model("resnet50", pretrained=False).eval(), seed=0, randomize_bn=True)
+    x = seeded_input((4, 3, 224, 224), seed=1234)
+    want = oracle_forward(net, x)
+    plain = P.accelerate(copy.deepcopy(net).cuda(), dtype="bf16")(x.cuda()).cpu()
+    PL.set_fuse_tail(True)
+    try:
+        fast = P.accelerate(copy.deepcopy(net).cuda(), dtype="bf16")
+        fused = fast(x.cuda()).cpu()
+        assert fast.compiled(x.cuda()).num_ops == 53      # 56 - 3 fused tails
+    finally:
+        PL.set_fuse_tail(False)
+    assert _rel(fused, want) <= 2e-2 and torch.equal(fused.argmax(1), want.argmax(1))
+    assert _rel(fused, plain) <= 1e-2
+
+
 def test_outputs_are_caller_owned():
     """forward returns freshly allocated tensors - a result must survive the next forward (eager and graph
     replay, logits and fp32 NCHW segmentation maps); alias_outputs=True is the documented zero-copy opt-in."""

@@ -113,7 +113,7 @@ def test_lowering_and_arena(name, shape, n_ops, tier):
     x.buf.first, x.buf.pinned = -1, True
     out = PL.lower(b, net, x)
     _, trefs = PL._flatten(out)
-    # plan ops + the per-call edge ops (fp32 NCHW outputs written after the plan into fresh, caller-owned tensors)
+    # plan ops + the per-call edge ops (fp32 NCHW outputs written after the plan into fresh, caller-owned tensors);
     assert len(b.ops) + sum(t.tail is not None for t in trefs) == n_ops
     for t in trefs:
         t.buf.pinned = True
