@@ -623,14 +623,26 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   p.nsubs = 1;
   int b_box_rows = op->bn;
   if (op->pair) {
-    // tile width = nsubs * 64 <= BN: the candidate that pads ceil(Cout/64) the least (ties -> the widest)
+    // tile width = nsubs * 64 <= BN.  Candidates are scored by (waves of pair tiles over the machine) x (tile cost ~ width
+    // + a fixed per-tile overhead): a layer whose tiles barely spill into another wave (stage 4 of ResNet-50: 49 M-pairs x
+    // 2 N-tiles = 98 tiles on 74 CTA pairs, a second wave that is one third full) runs as 3 narrower N-tiles (147 tiles,
+    // two FULL waves of 3/4-cost tiles); ties go to the candidate that pads ceil(Cout/64) the least, then to the widest.
     const int units = ceil_div(d.Cout, 64), maxns = op->bn / 64;
+    const int pairs_avail = std::max(1, sm_count() / 2), pair_m = (p.tiles_m + 1) / 2;
     int best = maxns, bestpad = 1 << 30;
-    for (int ns = maxns; ns >= std::max(1, maxns / 2); --ns) {
+    double bestcost = 1e30;
+    for (int ns = maxns; ns >= (op->bn == 256 ? 2 : maxns); --ns) {   // instantiated widths: 256 / 192 / 128, 128, 64
       const int pad = ceil_div(units, ns) * ns;
-      if (pad < bestpad) {
+      const long long tiles = static_cast<long long>(pair_m) * ceil_div(units, ns);
+      // (measured: 3x3 512->512 @7x7 0.065 -> 0.059 ms; short-K 1x1 layers are overhead-bound and gain nothing, so the
+      // wave term only applies to k x k layers)
+      const double waves = taps > 1 ? static_cast<double>((tiles + pairs_avail - 1) / pairs_avail)
+                                    : static_cast<double>(tiles) / pairs_avail;
+      const double cost = waves * (ns + 0.35);
+      if (cost < bestcost * 0.97 || (cost <= bestcost * 1.03 && pad < bestpad)) {
         best = ns;
         bestpad = pad;
+        bestcost = std::min(cost, bestcost);
       }
     }
     static const bool narrow = [] {
