@@ -155,6 +155,13 @@ PCV_API int pcv_adaptive_avgpool(pcv_plan* plan, int dtype, int N, int H, int W,
  * scale:  y = act(x * gate[n, c] + identity)   (seresnext.py:62-65; identity may be NULL, act may be NONE). */
 PCV_API int pcv_se_excite(pcv_plan* plan, int N, int C, int Cmid, const float* pooled, const float* w1, const float* b1,
                   const float* w2, const float* b2, int mid_act, int out_act, float* gate, pcv_stream stream);
+/* The excite with an input of a different width: gate = out_act(W2 * mid_act(W1 * pooled + b1) + b2) with pooled [N, Cin],
+ * W1 [Cmid, Cin], W2 [C, Cmid]; `gate` holds N*(C+Cmid) floats.  Used when the squeeze is moved UPSTREAM of the unit's last
+ * 1x1 ConvBlock by linearity (seresnext.py:60-62: mean_HW(conv3(y)) == W3' * mean_HW(y) + b3'): the caller pools conv3's
+ * input (half the bytes in SE-ResNeXt) and folds W3', b3' into W1, b1 on the host. */
+PCV_API int pcv_se_excite_ex(pcv_plan* plan, int N, int Cin, int Cmid, int C, const float* pooled, const float* w1,
+                     const float* b1, const float* w2, const float* b2, int mid_act, int out_act, float* gate,
+                     pcv_stream stream);
 PCV_API int pcv_se_scale_add_act(pcv_plan* plan, int dtype, int N, int HW, int C, const void* x, const float* gate,
                          const void* identity, int act, void* y, pcv_stream stream);
 

@@ -54,6 +54,7 @@ SIGNATURES = {
     "pcv_global_avgpool": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _I, _P]),
     "pcv_adaptive_avgpool": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P]),
     "pcv_se_excite": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
+    "pcv_se_excite_ex": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "pcv_se_scale_add_act": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P]),
     "pcv_add_act": (_I, [_P, _I, _Z, _P, _P, _I, _P, _P]),
     "pcv_nchw_f32_to_nhwc": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P]),

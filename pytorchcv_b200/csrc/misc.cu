@@ -391,25 +391,27 @@ se_fc2_kernel(int N, int C, int Cmid, const float* __restrict__ mid, const float
 
 struct SeExciteOp : Op {
   int N, C, Cmid, mid_act, out_act;
+  int Cin = 0;   // width of `pooled` / rows of w1 (== C for a plain SEBlock; the conv3-folded form pools conv3's INPUT)
   const float *pooled, *w1, *b1, *w2, *b2;
   float* gate;
   float* mid;  // scratch lives at gate + N*C (caller sizes gate as N*(C+Cmid))
   cudaError_t launch(cudaStream_t s) override {
     constexpr int IMGS = 4, JPW = 2;
     g_launches += 2;
-    const size_t smem1 = static_cast<size_t>(IMGS) * C * sizeof(float), smem2 = static_cast<size_t>(IMGS) * Cmid * sizeof(float);
+    const int Ci = Cin > 0 ? Cin : C;
+    const size_t smem1 = static_cast<size_t>(IMGS) * Ci * sizeof(float), smem2 = static_cast<size_t>(IMGS) * Cmid * sizeof(float);
     const bool aligned = ((reinterpret_cast<uintptr_t>(pooled) | reinterpret_cast<uintptr_t>(w1) |
                            reinterpret_cast<uintptr_t>(w2) | reinterpret_cast<uintptr_t>(mid)) & 15) == 0;
-    if (C % 4 == 0 && Cmid % 4 == 0 && smem1 <= 200 * 1024 && aligned && N <= 65535 * IMGS) {
+    if (C % 4 == 0 && Ci % 4 == 0 && Cmid % 4 == 0 && smem1 <= 200 * 1024 && aligned && N <= 65535 * IMGS) {
       if (smem1 > 48 * 1024) {
         static std::atomic<uint64_t> attr_done{0};   // per device (see runtime.h)
         if (cudaError_t e = set_max_smem_once(se_fc1_kernel<IMGS, JPW>, 200 * 1024, attr_done)) return e;
       }
-      se_fc1_kernel<IMGS, JPW><<<dim3(ceil_div(N, IMGS), ceil_div(Cmid, 8 * JPW)), 256, smem1, s>>>(N, C, Cmid, pooled, w1, b1, mid_act, mid);
+      se_fc1_kernel<IMGS, JPW><<<dim3(ceil_div(N, IMGS), ceil_div(Cmid, 8 * JPW)), 256, smem1, s>>>(N, Ci, Cmid, pooled, w1, b1, mid_act, mid);
       se_fc2_kernel<IMGS><<<dim3(ceil_div(N, IMGS), ceil_div(C, 256)), 256, smem2, s>>>(N, C, Cmid, mid, w2, b2, out_act, gate);
       return cudaGetLastError();
     }
-    fc_f32_kernel<<<dim3(ceil_div(Cmid, 8), ceil_div(N, 8)), 256, 0, s>>>(N, C, Cmid, pooled, w1, b1, mid_act, mid);
+    fc_f32_kernel<<<dim3(ceil_div(Cmid, 8), ceil_div(N, 8)), 256, 0, s>>>(N, Ci, Cmid, pooled, w1, b1, mid_act, mid);
     fc_f32_kernel<<<dim3(ceil_div(C, 8), ceil_div(N, 8)), 256, 0, s>>>(N, Cmid, C, mid, w2, b2, out_act, gate);
     return cudaGetLastError();
   }
@@ -888,21 +890,27 @@ int pcv_adaptive_avgpool(pcv_plan* plan, int dtype, int N, int H, int W, int C, 
   return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
 }
 
-int pcv_se_excite(pcv_plan* plan, int N, int C, int Cmid, const float* pooled, const float* w1, const float* b1,
-                  const float* w2, const float* b2, int mid_act, int out_act, float* gate, pcv_stream stream) {
+int pcv_se_excite_ex(pcv_plan* plan, int N, int Cin, int Cmid, int C, const float* pooled, const float* w1, const float* b1,
+                     const float* w2, const float* b2, int mid_act, int out_act, float* gate, pcv_stream stream) {
   PCV_REQUIRE(pooled && w1 && w2 && gate, "NULL tensor pointer");
-  PCV_REQUIRE(N > 0 && C > 0 && Cmid > 0, "bad SE dims");
+  PCV_REQUIRE(N > 0 && C > 0 && Cmid > 0 && Cin > 0, "bad SE dims");
   auto op = std::make_unique<SeExciteOp>();
-  op->N = N; op->C = C; op->Cmid = Cmid; op->mid_act = mid_act; op->out_act = out_act;
+  op->N = N; op->C = C; op->Cin = Cin; op->Cmid = Cmid; op->mid_act = mid_act; op->out_act = out_act;
   op->pooled = pooled; op->w1 = w1; op->b1 = b1; op->w2 = w2; op->b2 = b2; op->gate = gate;
   op->mid = gate + static_cast<size_t>(N) * C;
   op->launches = 2;
   char nm[96];
-  snprintf(nm, sizeof nm, "se_excite C=%d mid=%d", C, Cmid);
+  if (Cin == C) snprintf(nm, sizeof nm, "se_excite C=%d mid=%d", C, Cmid);
+  else snprintf(nm, sizeof nm, "se_excite in=%d mid=%d C=%d (conv3 folded into fc1)", Cin, Cmid, C);
   op->name = nm;
-  op->flops = 4.0 * N * C * Cmid;
-  op->bytes = 8.0 * C * Cmid + 8.0 * N * C;
+  op->flops = 2.0 * N * Cmid * (Cin + C);
+  op->bytes = 4.0 * Cmid * (Cin + C) + 4.0 * N * (Cin + C);
   return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
+}
+
+int pcv_se_excite(pcv_plan* plan, int N, int C, int Cmid, const float* pooled, const float* w1, const float* b1,
+                  const float* w2, const float* b2, int mid_act, int out_act, float* gate, pcv_stream stream) {
+  return pcv_se_excite_ex(plan, N, C, Cmid, C, pooled, w1, b1, w2, b2, mid_act, out_act, gate, stream);
 }
 
 int pcv_se_scale_add_act(pcv_plan* plan, int dtype, int N, int HW, int C, const void* x, const float* gate,

@@ -36,6 +36,8 @@ def set_fuse_tail(enabled: bool) -> None:
     _FUSE_TAIL[0] = bool(enabled)
 
 
+# SE units: squeeze moved upstream of the unit's last 1x1 conv by linearity (PCV_SE_FOLD=0: pool the conv's output instead)
+_SE_FOLD = os.environ.get("PCV_SE_FOLD", "1") != "0"
 _ALIGN = 1024  # arena / weight blob alignment (TMA needs 16 B; 1 KiB keeps every tensor sector- and line-aligned)
 
 
@@ -392,8 +394,9 @@ class Builder:
         return out
 
     def se_gate(self, pooled: TRef, w1: torch.Tensor, b1, w2: torch.Tensor, b2, mid_act: int, out_act: int) -> TRef:
-        """SEBlock excite (att.py:99-102): gate = out_act(W2 @ mid_act(W1 @ pooled + b1) + b2), all fp32."""
-        N, Cc = pooled.N, pooled.C
+        """SEBlock excite (att.py:99-102): gate = out_act(W2 @ mid_act(W1 @ pooled + b1) + b2), all fp32.  `pooled` may be
+        narrower than the gate (w1 [mid, pooled.C], w2 [C, mid]) when the unit's last 1x1 conv was folded into W1."""
+        N, Cin, Cc = pooled.N, pooled.C, w2.shape[0]
         cmid = w1.shape[0]
         gate = self.new(N, 1, 1, Cc, dtype=F32, extra_bytes=N * cmid * 4)
         offs = []
@@ -404,7 +407,7 @@ class Builder:
         self._use(pooled, gate)
 
         def emit(plan, ptr, wptr):
-            _lib.call("pcv_se_excite", plan, N, Cc, cmid, ptr(pooled), wptr(offs[0]),
+            _lib.call("pcv_se_excite_ex", plan, N, Cin, cmid, Cc, ptr(pooled), wptr(offs[0]),
                       wptr(offs[1]) if offs[1] is not None else None, wptr(offs[2]),
                       wptr(offs[3]) if offs[3] is not None else None, mid_act, out_act, ptr(gate), None)
         self.ops.append(emit)
@@ -606,12 +609,54 @@ def _lower_resunit(b, m, x, **kw):
     return lower(b, m.body, x, residual=identity, post_act=act_code(m.activ))
 
 
+def _fold_conv3_into_se(conv3, se):
+    """mean_HW(conv3(y)) == W3' mean_HW(y) + b3' for a 1x1 stride-1 ConvBlock without activation (BN folded into W3', b3'):
+    returns (W1 W3', W1 b3' + b1) so that the SE squeeze can pool conv3's INPUT (fewer channels), or None."""
+    c = getattr(conv3, "conv", None)
+    if (type(conv3).__name__ != "ConvBlock" or conv3.activate or getattr(conv3, "use_pad", False) or c is None
+            or c.kernel_size != (1, 1) or _one(c.stride) != 1 or _one(c.padding) != 0 or c.groups != 1
+            or not _SE_FOLD or c.in_channels >= c.out_channels):
+        return None
+    with torch.no_grad():
+        w3 = c.weight.detach().double().view(c.out_channels, c.in_channels)
+        b3 = c.bias.detach().double() if c.bias is not None else torch.zeros(c.out_channels, dtype=torch.float64,
+                                                                              device=w3.device)
+        if conv3.normalize:
+            bn = conv3.bn
+            _check_bn(bn)
+            g = bn.weight.detach().double() if bn.weight is not None else torch.ones_like(bn.running_var.double())
+            be = bn.bias.detach().double() if bn.bias is not None else torch.zeros_like(g)
+            sc = g / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+            w3, b3 = w3 * sc[:, None], (b3 - bn.running_mean.detach().double()) * sc + be
+        if se.use_conv:
+            w1 = se.conv1.weight.detach().double().view(se.conv1.out_channels, -1)
+            b1 = se.conv1.bias
+        else:
+            w1, b1 = se.fc1.weight.detach().double(), se.fc1.bias
+        b1 = b1.detach().double() if b1 is not None else torch.zeros(w1.shape[0], dtype=torch.float64, device=w1.device)
+        return (w1 @ w3).float().contiguous(), (w1 @ b3 + b1).float().contiguous()
+
+
 @lowers("SEResNeXtUnit", "SEResUnit", "SENetUnit")
 def _lower_seresnext_unit(b, m, x, **kw):
-    """SEResNeXtUnit.forward (seresnext.py:57-66): relu(se(body(x)) + identity)."""
+    """SEResNeXtUnit.forward (seresnext.py:57-66): relu(se(body(x)) + identity).
+
+    When the body ends in a linear 1x1 ConvBlock (ResNeXtBottleneck / ResBottleneck / SENetBottleneck conv3) the SE squeeze
+    is taken on that conv's INPUT: global mean commutes with the 1x1 conv + BN, whose weights fold into the first SE FC on
+    the host.  The squeeze pass then reads the bottleneck width instead of the unit width (half the bytes in SE-ResNeXt,
+    a quarter in SE-ResNet) and sees unrounded values of conv3's output."""
     identity = lower(b, m.identity_conv, x) if m.resize_identity else x
-    y = lower(b, m.body, x)
-    return lower(b, m.se, y, identity=identity, post_act=act_code(m.activ))
+    body, se = m.body, m.se
+    folded = _fold_conv3_into_se(body.conv3, se) if hasattr(body, "conv3") else None
+    if folded is None:
+        y = lower(b, body, x)
+        return lower(b, se, y, identity=identity, post_act=act_code(m.activ))
+    y2 = lower(b, body.conv2, lower(b, body.conv1, x))
+    pooled = b.gap(y2, out_dtype=F32)
+    y3 = lower(b, body.conv3, y2)
+    _, _, w2, b2, mid_act, out_act = _se_parts(b, se)
+    gate = b.se_gate(pooled, folded[0], folded[1], w2, b2, mid_act, out_act)
+    return b.se_scale(y3, gate, identity, act_code(m.activ))
 
 
 @lowers("ResInitBlock")
