@@ -638,7 +638,10 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
       // wave term only applies to k x k layers)
       const double waves = taps > 1 ? static_cast<double>((tiles + pairs_avail - 1) / pairs_avail)
                                     : static_cast<double>(tiles) / pairs_avail;
-      const double cost = waves * (ns + 0.35);
+      // per-tile cost ~ cycles of one K = 16 MMA step at this width (measured, shared-memory bound: N = 256 170 clk,
+      // N = 192 130, N = 128 110 - narrower tiles do less work per operand byte) + a fixed share for the tile's hand-over
+      const double mma_clk = ns >= 4 ? 170.0 : (ns == 3 ? 130.0 : 110.0);
+      const double cost = waves * (mma_clk + 15.0);
       if (cost < bestcost * 0.97 || (cost <= bestcost * 1.03 && pad < bestpad)) {
         best = ns;
         bestpad = pad;
