@@ -135,6 +135,12 @@ PCV_API int pcv_bottleneck_tail(pcv_plan* plan, const pcv_conv_desc* d2, const p
                         const void* w2_packed, const float* bias2, const void* w3_packed, const float* bias3,
                         const void* residual, void* y, pcv_stream stream);
 
+/* nn.ZeroPad2d((left, right, top, bottom)): the explicit asymmetric padding of a ConvBlock built with a 4-tuple `padding`
+ * (conv.py:245-249,279-280) and of EfficientNet's tf_mode forwards (F.pad(x, calc_tf_padding(...)), efficientnet.py:27-55).
+ * y is [N, H + top + bottom, W + left + right, C]; the convolution that follows runs with pad = 0. */
+PCV_API int pcv_zero_pad2d(pcv_plan* plan, int dtype, int N, int H, int W, int C, const void* x, int in_pitch, int pad_left,
+                   int pad_right, int pad_top, int pad_bottom, void* y, int out_pitch, pcv_stream stream);
+
 /* nn.MaxPool2d(k, stride, pad), -inf padding, floor mode (resnet.py:255-258, senet.py:154-157). */
 PCV_API int pcv_maxpool2d(pcv_plan* plan, int dtype, int N, int H, int W, int C, int k, int stride, int pad, const void* x,
                   int in_pitch, void* y, int out_pitch, pcv_stream stream);

@@ -603,6 +603,46 @@ nhwc_to_nchw_kernel(int N, int C, int HW, int c_pitch, const T* __restrict__ x, 
   }
 }
 
+// nn.ZeroPad2d((left, right, top, bottom)) on NHWC (conv.py:245-249: ConvBlock with a 4-tuple padding; EfficientNet tf_mode's
+// F.pad(calc_tf_padding(...)), efficientnet.py:27-55,108-109,189-190,236-237): one pass, 8 channels per thread
+template <typename T>
+__global__ void __launch_bounds__(256)
+zero_pad_kernel(int N, int H, int W, int C, int in_pitch, int pl, int pt, int Ho, int Wo, int out_pitch,
+                const T* __restrict__ x, T* __restrict__ y) {
+  const int cv = C >> 3;
+  const long long total = static_cast<long long>(N) * Ho * Wo * cv;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = idx;
+    const int c8 = static_cast<int>(r % cv) << 3; r /= cv;
+    const int wo = static_cast<int>(r % Wo); r /= Wo;
+    const int ho = static_cast<int>(r % Ho);
+    const int n = static_cast<int>(r / Ho);
+    const int h = ho - pt, w = wo - pl;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (h >= 0 && h < H && w >= 0 && w < W) V8<T>::load(x + ((static_cast<size_t>(n) * H + h) * W + w) * in_pitch + c8, v);
+    V8<T>::store(y + ((static_cast<size_t>(n) * Ho + ho) * Wo + wo) * out_pitch + c8, v);
+  }
+}
+
+struct ZeroPadOp : Op {
+  int dtype, N, H, W, C, in_pitch, pl, pt, Ho, Wo, out_pitch;
+  const void* x;
+  void* y;
+  cudaError_t launch(cudaStream_t s) override {
+    g_launches++;
+    const int grid = grid_for(static_cast<long long>(N) * Ho * Wo * (C >> 3));
+    if (dtype == PCV_F32)
+      zero_pad_kernel<float><<<grid, 256, 0, s>>>(N, H, W, C, in_pitch, pl, pt, Ho, Wo, out_pitch, (const float*)x, (float*)y);
+    else if (dtype == PCV_F16)
+      zero_pad_kernel<__half><<<grid, 256, 0, s>>>(N, H, W, C, in_pitch, pl, pt, Ho, Wo, out_pitch, (const __half*)x, (__half*)y);
+    else
+      zero_pad_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(N, H, W, C, in_pitch, pl, pt, Ho, Wo, out_pitch, (const __nv_bfloat16*)x,
+                                                          (__nv_bfloat16*)y);
+    return cudaGetLastError();
+  }
+};
+
 struct LayoutOp : Op {
   int dtype, N, C, HW, c_pitch, to_nhwc, img_type = PCV_IMG_F32;
   ImgAffine af;
@@ -960,6 +1000,25 @@ int pcv_nchw_to_nhwc_ex(pcv_plan* plan, int dtype, int img_type, int N, int C, i
 int pcv_nchw_f32_to_nhwc(pcv_plan* plan, int dtype, int N, int C, int H, int W, const float* x, void* y, int c_pitch,
                          pcv_stream stream) {
   return pcv_nchw_to_nhwc_ex(plan, dtype, PCV_IMG_F32, N, C, H, W, x, nullptr, nullptr, y, c_pitch, stream);
+}
+
+int pcv_zero_pad2d(pcv_plan* plan, int dtype, int N, int H, int W, int C, const void* x, int in_pitch, int pad_left,
+                   int pad_right, int pad_top, int pad_bottom, void* y, int out_pitch, pcv_stream stream) {
+  PCV_DTYPE_OK(dtype);
+  PCV_REQUIRE(x && y, "NULL tensor pointer");
+  in_pitch = pitch_or(in_pitch, C);
+  out_pitch = pitch_or(out_pitch, C);
+  PCV_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && pad_left >= 0 && pad_right >= 0 && pad_top >= 0 && pad_bottom >= 0,
+              "bad zero-pad dims");
+  PCV_REQUIRE(C % 8 == 0 && in_pitch % 8 == 0 && out_pitch % 8 == 0, "zero pad needs channels / pitches that are multiples of 8");
+  auto op = std::make_unique<ZeroPadOp>();
+  op->dtype = dtype; op->N = N; op->H = H; op->W = W; op->C = C; op->in_pitch = in_pitch; op->pl = pad_left; op->pt = pad_top;
+  op->Ho = H + pad_top + pad_bottom; op->Wo = W + pad_left + pad_right; op->out_pitch = out_pitch; op->x = x; op->y = y;
+  char nm[96];
+  snprintf(nm, sizeof nm, "zero_pad_%s C=%d %dx%d +(l%d r%d t%d b%d)", dn(dtype), C, H, W, pad_left, pad_right, pad_top, pad_bottom);
+  op->name = nm;
+  op->bytes = static_cast<double>(esize(dtype)) * N * C * (static_cast<double>(H) * W + static_cast<double>(op->Ho) * op->Wo);
+  return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
 }
 
 int pcv_nhwc_to_nchw_f32(pcv_plan* plan, int dtype, int N, int C, int H, int W, const void* x, int c_pitch, float* y,

@@ -32,9 +32,10 @@ for _name, (_b, _c, _w) in nets.RESNEXT_VARIANTS.items():
 for _name, _b in nets.RESNETD_VARIANTS.items():
     _register(_name, (lambda n, b: lambda **kw: nets.get_resnetd(
         blocks=b, conv1_stride=False, model_name=n, **kw))(_name, _b))
-for _name, (_v, _sz) in nets.EFFICIENTNET_VARIANTS.items():
-    _register(_name, (lambda n, v, sz: lambda in_size=None, **kw: nets.get_efficientnet(
-        version=v, in_size=in_size if in_size is not None else (sz, sz), model_name=n, **kw))(_name, _v, _sz))
+for _name, (_v, _sz, _tf, _eps) in nets.EFFICIENTNET_VARIANTS.items():
+    _register(_name, (lambda n, v, sz, tf, eps: lambda in_size=None, **kw: nets.get_efficientnet(
+        version=v, in_size=in_size if in_size is not None else (sz, sz), tf_mode=tf, bn_eps=eps, model_name=n, **kw))(
+        _name, _v, _sz, _tf, _eps))
 for _name, (_ver, _ws) in nets.MOBILENETV3_VARIANTS.items():
     _register(_name, (lambda n, v, w: lambda **kw: nets.get_mobilenetv3(version=v, width_scale=w, model_name=n, **kw))(
         _name, _ver, _ws))

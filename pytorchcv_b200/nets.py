@@ -301,21 +301,14 @@ MOBILENETV2_VARIANTS = {
 
 
 # ===== EfficientNet (efficientnet.py), SURVEY 8(f) rank 1 ===========================================================
-def _no_tf_mode(tf_mode: bool) -> None:
-    if tf_mode:
-        raise NotImplementedError("EfficientNet tf_mode=True pads asymmetrically per input size (efficientnet.py:27-55); "
-                                  "only the symmetric-padding variants (efficientnet_b0..b8) are on the B200 eval path")
-
-
 class EffiDwsConvUnit(B200Module):
     """dw3x3 -> SE(reduction 4, swish bottleneck) -> 1x1 linear (+x) (efficientnet.py:58-115)."""
 
     def __init__(self, in_channels, out_channels, stride, normalization, activation, tf_mode):
         super().__init__()
-        _no_tf_mode(tf_mode)
         self.tf_mode = tf_mode
         self.residual = (in_channels == out_channels) and (stride == 1)
-        self.dw_conv = dwconv3x3_block(in_channels=in_channels, out_channels=in_channels, padding=1,
+        self.dw_conv = dwconv3x3_block(in_channels=in_channels, out_channels=in_channels, padding=(0 if tf_mode else 1),
                                        normalization=normalization, activation=activation)
         self.se = SEBlock(channels=in_channels, reduction=4, mid_activation=activation)
         self.pw_conv = conv1x1_block(in_channels=in_channels, out_channels=out_channels, normalization=normalization,
@@ -328,7 +321,6 @@ class EffiInvResUnit(B200Module):
     def __init__(self, in_channels, out_channels, kernel_size, stride, exp_factor, se_factor, normalization, activation,
                  tf_mode):
         super().__init__()
-        _no_tf_mode(tf_mode)
         self.kernel_size, self.stride, self.tf_mode = kernel_size, stride, tf_mode
         self.residual = (in_channels == out_channels) and (stride == 1)
         self.use_se = se_factor > 0
@@ -336,7 +328,7 @@ class EffiInvResUnit(B200Module):
         dw = dwconv3x3_block if kernel_size == 3 else (dwconv5x5_block if kernel_size == 5 else None)
         self.conv1 = conv1x1_block(in_channels=in_channels, out_channels=mid, normalization=normalization,
                                    activation=activation)
-        self.conv2 = dw(in_channels=mid, out_channels=mid, stride=stride, padding=kernel_size // 2,
+        self.conv2 = dw(in_channels=mid, out_channels=mid, stride=stride, padding=(0 if tf_mode else kernel_size // 2),
                         normalization=normalization, activation=activation)
         if self.use_se:
             self.se = SEBlock(channels=mid, reduction=exp_factor * se_factor, mid_activation=activation)
@@ -349,9 +341,8 @@ class EffiInitBlock(B200Module):
 
     def __init__(self, in_channels, out_channels, normalization, activation, tf_mode):
         super().__init__()
-        _no_tf_mode(tf_mode)
         self.tf_mode = tf_mode
-        self.conv = conv3x3_block(in_channels=in_channels, out_channels=out_channels, stride=2, padding=1,
+        self.conv = conv3x3_block(in_channels=in_channels, out_channels=out_channels, stride=2, padding=(0 if tf_mode else 1),
                                   normalization=normalization, activation=activation)
 
 
@@ -425,7 +416,12 @@ def get_efficientnet(version, in_size, tf_mode=False, bn_eps=1e-5, model_name=No
     return net
 
 
-EFFICIENTNET_VARIANTS = {f"efficientnet_{v}": (v, sz) for v, (sz, _, _, _) in _EFFICIENTNET_SCALING.items()}
+# name -> (version, input size, tf_mode, bn_eps): b0..b8 (efficientnet.py:492-735), the TF-like b0b..b7b / b0c..b8c with
+# asymmetric "SAME" padding and bn_eps = 1e-3 (efficientnet.py:738-1090)
+EFFICIENTNET_VARIANTS = {f"efficientnet_{v}": (v, sz, False, 1e-5) for v, (sz, _, _, _) in _EFFICIENTNET_SCALING.items()}
+EFFICIENTNET_VARIANTS.update({f"efficientnet_{v}b": (v, sz, True, 1e-3) for v, (sz, _, _, _) in _EFFICIENTNET_SCALING.items()
+                              if v != "b8"})
+EFFICIENTNET_VARIANTS.update({f"efficientnet_{v}c": (v, sz, True, 1e-3) for v, (sz, _, _, _) in _EFFICIENTNET_SCALING.items()})
 
 
 # ===== MobileNetV3 (mobilenetv3.py), SURVEY 8(f) rank 1 ==============================================================

@@ -239,12 +239,23 @@ class Builder:
 
     # -- ops ----------------------------------------------------------------------------------------------------
     def conv(self, x: TRef, conv: nn.Conv2d, bn: nn.Module | None = None, act: int = ACT_NONE,
-             residual: TRef | None = None, out: TRef | None = None, out_f32: bool = False, flags: int = 0) -> TRef:
-        """One fused ConvBlock: conv + folded BN + optional residual + activation."""
+             residual: TRef | None = None, out: TRef | None = None, out_f32: bool = False, flags: int = 0,
+             pad_lrtb: tuple | None = None) -> TRef:
+        """One fused ConvBlock: conv + folded BN + optional residual + activation.  `pad_lrtb` = (left, right, top, bottom)
+        replaces the conv's own padding (ZeroPad2d / tf_mode): symmetric amounts ride on the kernel's padding, asymmetric
+        ones are materialised by one zero-pad pass."""
         if conv.padding_mode != "zeros" or isinstance(conv.padding, str):
             raise NotImplementedError("only zero padding with integer sizes is supported")
         kh, kw = conv.kernel_size
         k_stride, k_pad, k_dil = _one(conv.stride), _one(conv.padding), _one(conv.dilation)
+        if pad_lrtb is not None:
+            if k_pad != 0:
+                raise NotImplementedError("explicit padding in front of a convolution that pads itself")
+            pl, pr, pt, pb = (int(v) for v in pad_lrtb)
+            if pl == pr == pt == pb:
+                k_pad = pl
+            else:
+                x = self.pad(x, pl, pr, pt, pb)
         cin, cout, groups = conv.in_channels, conv.out_channels, conv.groups
         if residual is None and out is None and not out_f32 and self._s2d_stem(x, conv, kh, k_stride, k_pad, k_dil):
             if bn is not None:
@@ -343,6 +354,17 @@ class Builder:
             _lib.call("pcv_bottleneck_tail", plan, C.byref(d2), C.byref(d3), dtype, ptr(x), wptr(offs[0]), wptr(offs[1]),
                       wptr(offs[2]), wptr(offs[3]), ptr(residual), ptr(out), None)
         self.ops.append(emit)
+        return out
+
+    def pad(self, x: TRef, left: int, right: int, top: int, bottom: int) -> TRef:
+        """nn.ZeroPad2d((left, right, top, bottom)) / F.pad on the map (conv.py:279-280, efficientnet.py:108-109)."""
+        if left == right == top == bottom == 0:
+            return x
+        out = self.new(x.N, x.H + top + bottom, x.W + left + right, x.C, dtype=x.dtype)
+        self._use(x, out)
+        self.ops.append(lambda plan, ptr, wptr: _lib.call(
+            "pcv_zero_pad2d", plan, x.dtype, x.N, x.H, x.W, x.C, ptr(x), x.pitch, left, right, top, bottom, ptr(out),
+            out.pitch, None))
         return out
 
     def linear(self, x: TRef, fc: nn.Linear, out_f32: bool = True) -> TRef:
@@ -522,18 +544,21 @@ def _lower_linear(b, m, x, **kw):
 
 
 @lowers("ConvBlock")
-def _lower_convblock(b, m, x, residual=None, post_act=None, out=None, **kw):
-    """ConvBlock.forward (conv.py:278-286); `residual`/`post_act` carry the enclosing unit's add + activation."""
+def _lower_convblock(b, m, x, residual=None, post_act=None, out=None, pad_lrtb=None, **kw):
+    """ConvBlock.forward (conv.py:278-286); `residual`/`post_act` carry the enclosing unit's add + activation.  A block built
+    with a 4-tuple padding applies nn.ZeroPad2d first (conv.py:245-249,279-280); `pad_lrtb` is the caller's F.pad (tf_mode)."""
     if getattr(m, "use_pad", False):
-        raise NotImplementedError("ConvBlock with asymmetric ZeroPad2d padding is outside the B200 eval path")
+        if pad_lrtb is not None:
+            raise NotImplementedError("ZeroPad2d ConvBlock behind an explicit F.pad")
+        pad_lrtb = tuple(int(v) for v in m.pad.padding)
     bn = m.bn if m.normalize else None
     act = act_code(m.activ) if m.activate else ACT_NONE
     if residual is None and post_act is None:
-        return b.conv(x, m.conv, bn, act, out=out)
+        return b.conv(x, m.conv, bn, act, out=out, pad_lrtb=pad_lrtb)
     post = ACT_NONE if post_act is None else post_act
     if act == ACT_NONE:
-        return b.conv(x, m.conv, bn, post, residual=residual, out=out)     # fused: act(conv + residual)
-    y = b.conv(x, m.conv, bn, act)                                         # block has its own activation
+        return b.conv(x, m.conv, bn, post, residual=residual, out=out, pad_lrtb=pad_lrtb)   # fused: act(conv + residual)
+    y = b.conv(x, m.conv, bn, act, pad_lrtb=pad_lrtb)                      # block has its own activation
     return b.add_act(y, residual, post) if residual is not None else y
 
 
@@ -679,31 +704,36 @@ def _lower_linear_bottleneck(b, m, x, **kw):
     return lower(b, m.conv3, y, residual=x if m.residual else None, post_act=None)
 
 
-def _no_tf_mode(m):
-    if getattr(m, "tf_mode", False):
-        raise NotImplementedError("EfficientNet tf_mode (asymmetric, input-size dependent padding) is outside the B200 eval path")
+def _tf_pad(m, x: TRef, kernel_size: int, stride: int = 1, dilation: int = 1):
+    """calc_tf_padding (efficientnet.py:27-55) for a tf_mode unit, None otherwise.  The reference hands the tuple
+    (pad_h//2, pad_h - pad_h//2, pad_w//2, pad_w - pad_w//2) to F.pad, whose order is (left, right, top, bottom): the
+    HEIGHT amounts land on the width axis and vice versa - reproduced as is (identical for square maps)."""
+    if not getattr(m, "tf_mode", False):
+        return None
+    oh, ow = -(-x.H // stride), -(-x.W // stride)
+    ph = max((oh - 1) * stride + (kernel_size - 1) * dilation + 1 - x.H, 0)
+    pw = max((ow - 1) * stride + (kernel_size - 1) * dilation + 1 - x.W, 0)
+    return (ph // 2, ph - ph // 2, pw // 2, pw - pw // 2)
 
 
 @lowers("EffiInitBlock")
 def _lower_effi_init(b, m, x, **kw):
     """EffiInitBlock.forward (efficientnet.py:235-239)."""
-    _no_tf_mode(m)
-    return lower(b, m.conv, x)
+    return lower(b, m.conv, x, pad_lrtb=_tf_pad(m, x, 3, 2))
 
 
 @lowers("EffiDwsConvUnit")
 def _lower_effi_dws(b, m, x, **kw):
     """EffiDwsConvUnit.forward (efficientnet.py:105-115): dw3x3 -> SE -> 1x1 linear (+x); the add rides on the 1x1."""
-    _no_tf_mode(m)
-    y = lower(b, m.se, lower(b, m.dw_conv, x))
+    y = lower(b, m.se, lower(b, m.dw_conv, x, pad_lrtb=_tf_pad(m, x, 3)))
     return lower(b, m.pw_conv, y, residual=x if m.residual else None, post_act=None)
 
 
 @lowers("EffiInvResUnit")
 def _lower_effi_invres(b, m, x, **kw):
     """EffiInvResUnit.forward (efficientnet.py:185-197): 1x1 expand -> dw kxk -> [SE] -> 1x1 linear (+x)."""
-    _no_tf_mode(m)
-    y = lower(b, m.conv2, lower(b, m.conv1, x))
+    y1 = lower(b, m.conv1, x)
+    y = lower(b, m.conv2, y1, pad_lrtb=_tf_pad(m, y1, m.kernel_size, m.stride))
     if m.use_se:
         y = lower(b, m.se, y)
     return lower(b, m.conv3, y, residual=x if m.residual else None, post_act=None)

@@ -153,8 +153,13 @@ def test_unsupported_patterns_raise_at_compile_time():
         PL.lower(b, B.conv1x1_block(in_channels=16, out_channels=16), x)            # still in training mode
     with pytest.raises(NotImplementedError, match="cannot be folded"):
         PL.lower(b, B.ConvBlock(16, 16, 1, normalization=lambda num_features: nn.InstanceNorm2d(num_features)).eval(), x)
-    with pytest.raises(NotImplementedError, match="ZeroPad2d"):
-        PL.lower(b, B.ConvBlock(16, 16, 3, padding=(1, 0, 1, 0)).eval(), x)
+    # a 4-tuple padding (nn.ZeroPad2d in front of the conv, conv.py:245-249) lowers to one zero-pad pass + the conv
+    n0 = len(b.ops)
+    y = PL.lower(b, B.ConvBlock(16, 16, 3, padding=(1, 0, 1, 0)).eval(), x)
+    assert len(b.ops) == n0 + 2 and (y.H, y.W) == (7, 7)
+    n0 = len(b.ops)
+    y = PL.lower(b, B.ConvBlock(16, 16, 3, padding=(1, 1, 1, 1)).eval(), x)   # symmetric amounts ride on the kernel's padding
+    assert len(b.ops) == n0 + 1 and (y.H, y.W) == (8, 8)
     with pytest.raises(RuntimeError, match="eval-mode"):
         P.accelerate(P.get_model("resnet18"))
 

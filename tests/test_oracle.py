@@ -36,6 +36,7 @@ NETS = [
     ("spnasnet_bs2", "spnasnet", (2, 3, 224, 224), 1),
     ("senet16_bs2", "senet16", (2, 3, 224, 224), 1),
     ("proxylessnas_mobile_bs2", "proxylessnas_mobile", (2, 3, 224, 224), 1),
+    ("efficientnet_b0b_bs2", "efficientnet_b0b", (2, 3, 224, 224), 1),           # tf_mode: asymmetric "SAME" padding
 ]
 
 BLOCKS = {
@@ -66,6 +67,11 @@ BLOCKS = {
                                                          activation=B.lambda_hswish(), use_se=True), (2, 40, 14, 14)),
     "mnv3_unit_k5_s2_se": (lambda: M.MobileNetV3Unit(24, 40, exp_channels=96, stride=2, use_kernel3=False,
                                                      activation=B.lambda_hswish(), use_se=True), (1, 24, 17, 15)),
+    # asymmetric padding: ConvBlock with a 4-tuple padding (nn.ZeroPad2d, conv.py:245-249) and a tf_mode unit (F.pad)
+    "convblock_3x3_s2_pad4": (lambda: B.ConvBlock(16, 24, kernel_size=3, stride=2, padding=(0, 1, 2, 1)), (2, 16, 14, 15)),
+    "effi_invres_k5_s2_tf": (lambda: M.EffiInvResUnit(24, 40, kernel_size=5, stride=2, exp_factor=6, se_factor=4,
+                                                      normalization=B.lambda_batchnorm2d(eps=1e-3),
+                                                      activation=B.lambda_swish(), tf_mode=True), (1, 24, 16, 16)),
 }
 
 
