@@ -26,7 +26,14 @@ namespace pcv {
 namespace PCV_TIER {
 
 constexpr int F3_PARTS = 3;
-constexpr int F3_THREADS = 256;      // warp 0 producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4-7 epilogue
+// warp 0 producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, then the epilogue warps: 4 for BN <= 64 (one per TMEM lane
+// quarter), 8 for BN = 128 (lane quarter x 64-column half, so the running sums stay at 64 registers per thread)
+template <int BN>
+struct F3Cfg {
+  static constexpr int EPI_WARPS = BN > 64 ? 8 : 4;
+  static constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);
+  static constexpr int THREADS = 128 + EPI_WARPS * 32;
+};
 constexpr int F3_CHUNK_KB = 4;       // k-blocks (16 MMAs) per TMEM accumulation chain: ~3e-7 of truncation error, i.e. the
                                      // level of an fp32 FMA chain (ResNet-18 end to end: 3e-6 with 4, 1.4e-5 with 16, 4.6e-5 unchunked)
 
@@ -49,7 +56,7 @@ struct F3Params {
 
 template <int BN>
 struct F3Smem {
-  static constexpr int STAGES = BN == 32 ? 10 : 8;
+  static constexpr int STAGES = BN == 32 ? 10 : (BN == 64 ? 8 : 6);
   static constexpr int B_STAGE = BN * BLOCK_K * 2;
   static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_B + STAGES * B_STAGE;
@@ -66,7 +73,7 @@ __device__ __forceinline__ float f3_act(float x, int act, float lo, float hi) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(F3_THREADS, 1)
+__global__ void __launch_bounds__(F3Cfg<BN>::THREADS, 1)
 f32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const F3Params p) {
   using L = F3Smem<BN>;
   constexpr int STAGES = L::STAGES;
@@ -98,7 +105,7 @@ f32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], F3Cfg<BN>::EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -202,26 +209,28 @@ f32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp >= 4) {
     // ===================================== epilogue: chunk sums in registers (RN fp32), then bias / residual / act ====
+    constexpr int CW = F3Cfg<BN>::COLS_PER_WARP, EPI_THREADS = F3Cfg<BN>::EPI_WARPS * 32;
     const int q4 = warp & 3;
+    const int c_off = ((warp - 4) >> 2) * CW;   // this warp's columns of the tile: [c_off, c_off + CW)
     const int row = q4 * 32 + lane;
     int it = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
       const int tile = u / p.S, s = u - tile * p.S;
       const int m_tile = tile / p.tiles_n, n_tile = tile - m_tile * p.tiles_n;
       const int m = m_tile * BLOCK_M + row;
-      const int n0 = n_tile * BN;
+      const int n0 = n_tile * BN + c_off;
       const int kb0 = s * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.num_kblocks);
-      float run[BN];
+      float run[CW];
 #pragma unroll
-      for (int i = 0; i < BN; ++i) run[i] = 0.f;
+      for (int i = 0; i < CW; ++i) run[i] = 0.f;
       for (int c0 = kb0; c0 < kb1; c0 += p.chunk_kb, ++it) {
         const int buf = it & 1;
         mbar_wait(&tmem_full[buf], (it >> 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int j = 0; j < BN / 32; ++j) {
+        for (int j = 0; j < CW / 32; ++j) {
           uint32_t acc[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * BN + j * 32, acc);
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * BN + c_off + j * 32, acc);
           tmem_ld_wait_regs(acc);
 #pragma unroll
           for (int i = 0; i < 32; ++i) run[j * 32 + i] += __uint_as_float(acc[i]);
@@ -232,38 +241,38 @@ f32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       if (p.S > 1) {
         // split-K: publish this split's partial tile; the last split to arrive sums all of them in fixed order
-        float* mine = p.partial + (static_cast<size_t>(u) * BLOCK_M + row) * BN;
+        float* mine = p.partial + (static_cast<size_t>(u) * BLOCK_M + row) * BN + c_off;
 #pragma unroll
-        for (int i = 0; i < BN; i += 4) *reinterpret_cast<float4*>(mine + i) = make_float4(run[i], run[i + 1], run[i + 2], run[i + 3]);
+        for (int i = 0; i < CW; i += 4) *reinterpret_cast<float4*>(mine + i) = make_float4(run[i], run[i + 1], run[i + 2], run[i + 3]);
         __threadfence();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, EPI_THREADS);
         if (threadIdx.x == 128) {
           const unsigned int prev = atomicAdd(p.counter + tile, 1u);
           *last_flag = (prev == static_cast<unsigned int>(p.S - 1));
           if (prev == static_cast<unsigned int>(p.S - 1)) p.counter[tile] = 0;
           __threadfence();
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, EPI_THREADS);
         const bool last = *last_flag != 0;
-        named_bar_sync(1, 128);   // everyone has read the flag before the next unit may rewrite it
+        named_bar_sync(1, EPI_THREADS);   // everyone has read the flag before the next unit may rewrite it
         if (!last) continue;
 #pragma unroll
-        for (int i = 0; i < BN; ++i) run[i] = 0.f;
+        for (int i = 0; i < CW; ++i) run[i] = 0.f;
         for (int ss = 0; ss < p.S; ++ss) {
-          const float* src = p.partial + ((static_cast<size_t>(tile) * p.S + ss) * BLOCK_M + row) * BN;
+          const float* src = p.partial + ((static_cast<size_t>(tile) * p.S + ss) * BLOCK_M + row) * BN + c_off;
 #pragma unroll
-          for (int i = 0; i < BN; i += 4) {
+          for (int i = 0; i < CW; i += 4) {
             const float4 v = __ldcg(reinterpret_cast<const float4*>(src + i));
             run[i] += v.x; run[i + 1] += v.y; run[i + 2] += v.z; run[i + 3] += v.w;
           }
         }
       }
       if (m < p.M) {
-        const int ncol = min(BN, p.Cout - n0);
+        const int ncol = min(CW, p.Cout - n0);
         float* op = p.out + static_cast<size_t>(m) * p.out_pitch + n0;
         const float* rp = p.has_res ? p.res + static_cast<size_t>(m) * p.res_pitch + n0 : nullptr;
 #pragma unroll
-        for (int i = 0; i < BN; ++i) {
+        for (int i = 0; i < CW; ++i) {
           if (i < ncol) {
             float v = run[i] + __ldg(p.bias + n0 + i);
             if (rp) v += rp[i];
@@ -377,9 +386,16 @@ static F3Geom f3_geom(const pcv_conv_desc& d) {
   g.M = d.N * g.Ho * g.Wo;
   g.num_kblocks = g.gtaps * g.per_tap;
   const int tiles_m = ceil_div(g.M, BLOCK_M);
-  g.bn = (d.groups > 1 || d.Cout > 32) ? 64 : 32;
+  // tile width 64 (32 for narrow layers); small-M layers get their parallelism from split-K below.  A 128-wide variant
+  // (8 epilogue warps, 6 stages) exists and was measured SLOWER (ResNet-18 bs8: 2.05 vs 1.52 ms/step): the kernel is bound
+  // by k-block round trips per SM, and fewer, larger units with a shallower ring lose more than the halved A traffic wins.
+  // PCV_F3_BN=128 selects it for experiments.
   const int sms = sm_count();
-  if (d.groups == 1 && tiles_m * ceil_div(d.Cout, 64) * 2 <= sms) g.bn = 32;   // few rows: more CTAs on the weight stream
+  g.bn = (d.groups > 1 || d.Cout > 32) ? 64 : 32;
+  if (const char* e = getenv("PCV_F3_BN")) {
+    const int v = atoi(e);
+    if (d.groups == 1 && (v == 32 || v == 64 || (v == 128 && d.Cout >= 128))) g.bn = v;
+  }
   g.tiles = tiles_m * ceil_div(d.Cout, g.bn);
   // split-K when the tiles alone cannot fill the machine; at least 2 chunks of work per split
   int S = 1;
@@ -489,7 +505,7 @@ struct F3Op : Op {
   cudaError_t run(cudaStream_t s) {
     static std::atomic<uint64_t> attr_done{0};
     if (cudaError_t e = set_max_smem_once(f32x3_kernel<BN>, F3Smem<BN>::BYTES, attr_done)) return e;
-    return launch_pdl(f32x3_kernel<BN>, dim3(grid), dim3(F3_THREADS), F3Smem<BN>::BYTES, s, tmA, tmB, p);
+    return launch_pdl(f32x3_kernel<BN>, dim3(grid), dim3(F3Cfg<BN>::THREADS), F3Smem<BN>::BYTES, s, tmA, tmB, p);
   }
   cudaError_t launch(cudaStream_t s) override {
     g_launches += 2;
@@ -505,7 +521,7 @@ struct F3Op : Op {
           pixels, d.Cin, in_pitch, x, xs, p.counter, g.tiles);
     }
     if (cudaError_t e = cudaGetLastError()) return e;
-    return g.bn == 32 ? run<32>(s) : run<64>(s);
+    return g.bn == 32 ? run<32>(s) : (g.bn == 64 ? run<64>(s) : run<128>(s));
   }
 };
 
