@@ -20,6 +20,12 @@
 //     the epilogue warps sum in registers with round-to-nearest fp32 adds (two-level accumulation);
 //   * small-M layers (ResNet-18 stage 4 at batch 8: 4 M-tiles) are split along K over several CTAs; partial tiles go to the
 //     workspace and the LAST CTA to finish a tile sums them in fixed order s = 0..S-1 (deterministic) and runs the epilogue.
+//
+// Where the time goes (ResNet-18 bs8, 1.42 ms/step; PCV_F3_DBG decomposition, profiles/README.md): per op ~25 us are fixed
+// (two launches, TMEM / barrier prologue, split-K hand-over) and each k-block costs ~0.35 us of which 0.25 us remain with NO
+// loads and NO MMAs issued - the producer / MMA-warp barrier hand-over per stage (a tcgen05.commit per 4 small MMAs), not
+// bandwidth or math; busy-polling the barriers instead of try_wait changes nothing.  Grouping several k-blocks per stage
+// (the KSUB of conv_igemm2.cu) and emitting the split activation from the producing conv's epilogue are the next steps.
 #include "igemm_common.cuh"
 
 namespace pcv {
@@ -52,6 +58,7 @@ struct F3Params {
   int kq[3], per_tap, cstride;
   int S, kb_per_split;   // split-K factor and k-blocks per split
   int chunk_kb;          // k-blocks per TMEM accumulation chain (F3_CHUNK_KB; PCV_F3_CHUNK overrides for experiments)
+  int dbg;               // PCV_F3_DBG throughput experiments (WRONG results): 1 skip the A loads, 2 skip the B loads, 4 skip MMA issue
 };
 
 template <int BN>
@@ -75,6 +82,7 @@ __device__ __forceinline__ float f3_act(float x, int act, float lo, float hi) {
 template <int BN>
 __global__ void __launch_bounds__(F3Cfg<BN>::THREADS, 1)
 f32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const F3Params p) {
+
   using L = F3Smem<BN>;
   constexpr int STAGES = L::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -146,15 +154,17 @@ f32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full[stage], A_STAGE_BYTES + L::B_STAGE);
+          mbar_arrive_expect_tx(&full[stage], ((p.dbg & 1) ? 0 : A_STAGE_BYTES) + ((p.dbg & 2) ? 0 : L::B_STAGE));
           uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
-          if (p.a_mode == 1) {
-            tma_load_im2col_4d(&tmA, &full[stage], a_dst, c_base + cb * p.cstride, w0, h0, img,
-                               static_cast<uint16_t>(fs * p.dil), static_cast<uint16_t>(fr * p.dil));
-          } else {
-            tma_load_2d(&tmA, &full[stage], a_dst, c_base + cb * p.cstride, m0);
+          if (!(p.dbg & 1)) {
+            if (p.a_mode == 1) {
+              tma_load_im2col_4d(&tmA, &full[stage], a_dst, c_base + cb * p.cstride, w0, h0, img,
+                                 static_cast<uint16_t>(fs * p.dil), static_cast<uint16_t>(fr * p.dil));
+            } else {
+              tma_load_2d(&tmA, &full[stage], a_dst, c_base + cb * p.cstride, m0);
+            }
           }
-          tma_load_2d(&tmB, &full[stage], sB + stage * L::B_STAGE, kb * BLOCK_K, n_tile * BN);
+          if (!(p.dbg & 2)) tma_load_2d(&tmB, &full[stage], sB + stage * L::B_STAGE, kb * BLOCK_K, n_tile * BN);
         }
         if (++cb == p.kq[q]) {
           cb = 0;
@@ -194,9 +204,11 @@ f32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint32_t a_lo = a_lo0 + stage * (A_STAGE_BYTES >> 4);
           const uint32_t b_lo = b_lo0 + stage * (L::B_STAGE >> 4);
           if (elect_one()) {
+            if (!(p.dbg & 4)) {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / 16; ++k)
-              umma_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb != c0 || k != 0) ? 1u : 0u);
+              for (int k = 0; k < BLOCK_K / 16; ++k)
+                umma_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb != c0 || k != 0) ? 1u : 0u);
+            }
             umma_commit(&empty[stage]);
           }
           if (++stage == STAGES) {
@@ -572,6 +584,8 @@ int igemm_split_make(const pcv_conv_desc& d, const void* x, const void* w, const
   p.kb_per_split = g.kb_per_split;
   p.chunk_kb = F3_CHUNK_KB;
   if (const char* e = getenv("PCV_F3_CHUNK")) p.chunk_kb = std::max(1, atoi(e));
+  p.dbg = 0;
+  if (const char* e = getenv("PCV_F3_DBG")) p.dbg = atoi(e);
   const bool pointwise = g.im2col || (d.kh * d.kw == 1 && d.stride == 1 && d.pad == 0);
   p.a_mode = pointwise ? 0 : 1;
   // the activation the GEMM reads: the workspace, [rows, 3 * gC] bf16
