@@ -1,0 +1,16 @@
+#!/bin/bash
+PCV_F3_DBG=16 timeout 300 python - <<'PY'
+import torch, sys
+sys.path.insert(0, '.')
+import pytorchcv_b200 as P
+from bench import build_net
+net = build_net("resnet18", 224, 224).cuda()
+fast = P.accelerate(net, dtype="fp32", graph=False)
+x = torch.randn(8, 3, 224, 224, device="cuda")
+for _ in range(3):
+    fast(x)
+torch.cuda.synchronize()
+print("=== timed pass", flush=True)
+fast(x)
+torch.cuda.synchronize()
+PY
