@@ -59,7 +59,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.lines, self.proc, self.start = index, [], None, 0
+
+    def mark(self):
+        """The timed region starts now: samples taken before (NVML start-up, warm-up steps) are not summarised.  The
+        sampler is started BEFORE the warm-up so that nvidia-smi's own initialisation never overlaps a timed step."""
+        self.start = len(self.lines)
 
     def __enter__(self):
         try:
@@ -87,7 +92,7 @@ class ClockSampler:
 
     def summary(self) -> dict:
         sm, smax, pw, reasons = [], 0, 0.0, set()
-        for ln in self.lines:
+        for ln in self.lines[self.start:]:
             f = [s.strip() for s in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -268,8 +273,10 @@ def measure(a, model, N, H, W, dtype, K, Wm, rank, world, local, dev, pk, full: 
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps):
+    def timed(fn, steps, clk=None):
         barrier()
+        if clk is not None:
+            clk.mark()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
@@ -284,16 +291,17 @@ def measure(a, model, N, H, W, dtype, K, Wm, rank, world, local, dev, pk, full: 
     # ---------------- value: inputs resident in HBM ----------------
     y = runner(x)
     cm = fast.compiled(x)
-    for _ in range(Wm):
-        runner(x)
-    barrier()
-    l0 = _lib.launch_count()
     keep = {}
 
     def step(i):
         keep["y"] = runner(x)
     with ClockSampler(local) as clk:
-        ms_step = timed(step, K)
+        time.sleep(0.3)            # nvidia-smi / NVML start-up happens here, not inside the timed region
+        for _ in range(Wm):
+            runner(x)
+        barrier()
+        l0 = _lib.launch_count()
+        ms_step = timed(step, K, clk)
     launches = _lib.launch_count() - l0
     y = keep["y"]
     value = N * world / (ms_step * 1e-3)
@@ -312,7 +320,8 @@ def measure(a, model, N, H, W, dtype, K, Wm, rank, world, local, dev, pk, full: 
     if full:
         n_sus = max(K, int(a.sustain_s * 1e3 / ms_step) + 1)
         with ClockSampler(local) as clk2:
-            ms_sus = timed(step, n_sus)
+            time.sleep(0.3)
+            ms_sus = timed(step, n_sus, clk2)
         res["sustained"] = {"value": round(N * world / (ms_sus * 1e-3), 1), "ms_per_step": round(ms_sus, 4), "steps": n_sus,
                             "seconds": round(ms_sus * n_sus / 1e3, 2), "clocks": clk2.summary()}
 
@@ -527,7 +536,7 @@ def main() -> None:
                 continue
             b, h, w, dt = CONFIGS[m]
             try:
-                o = measure(a, m, b, h, w, dt, min(K, 30), Wm, rank, world, local, dev, pk, full=False)
+                o = measure(a, m, b, h, w, dt, 50, Wm, rank, world, local, dev, pk, full=False)   # 50 timed steps each
                 others.append({"config": workload_string(m, h, w, b), "model": m, "batch": b, "dtype": dt, "value": o["value"],
                                "unit": "images/s", "ms_per_step": o["ms_per_step"], "e2e": o["e2e"]["value"],
                                "e2e_f32": o["e2e_f32"]["value"], "roofline_step": o.get("roofline_step", {}).get("frac"),
