@@ -61,6 +61,14 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index, self.lines, self.proc, self.start = index, [], None, 0
 
+    def ready(self, timeout: float = 5.0):
+        """Block until nvidia-smi has printed its first sample: its start-up (NVML attach, ~0.1-1 s, during which the driver
+        can stall kernel launches for tens of ms) is then over."""
+        t0 = time.time()
+        while self.proc is not None and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.02)
+        time.sleep(0.1)
+
     def mark(self):
         """The timed region starts now: samples taken before (NVML start-up, warm-up steps) are not summarised.  The
         sampler is started BEFORE the warm-up so that nvidia-smi's own initialisation never overlaps a timed step."""
@@ -296,7 +304,7 @@ def measure(a, model, N, H, W, dtype, K, Wm, rank, world, local, dev, pk, full: 
     def step(i):
         keep["y"] = runner(x)
     with ClockSampler(local) as clk:
-        time.sleep(0.3)            # nvidia-smi / NVML start-up happens here, not inside the timed region
+        clk.ready()                # nvidia-smi / NVML start-up happens here, not inside the timed region
         for _ in range(Wm):
             runner(x)
         barrier()
@@ -320,7 +328,7 @@ def measure(a, model, N, H, W, dtype, K, Wm, rank, world, local, dev, pk, full: 
     if full:
         n_sus = max(K, int(a.sustain_s * 1e3 / ms_step) + 1)
         with ClockSampler(local) as clk2:
-            time.sleep(0.3)
+            clk2.ready()
             ms_sus = timed(step, n_sus, clk2)
         res["sustained"] = {"value": round(N * world / (ms_sus * 1e-3), 1), "ms_per_step": round(ms_sus, 4), "steps": n_sus,
                             "seconds": round(ms_sus * n_sus / 1e3, 2), "clocks": clk2.summary()}
