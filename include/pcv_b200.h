@@ -135,6 +135,17 @@ PCV_API int pcv_bottleneck_tail(pcv_plan* plan, const pcv_conv_desc* d2, const p
                         const void* w2_packed, const float* bias2, const void* w3_packed, const float* bias3,
                         const void* residual, void* y, pcv_stream stream);
 
+/* DwsConvBlock.forward (conv.py:605-608) and the depthwise -> linear-pointwise tail of LinearBottleneck (mobilenetv2.py:52-71)
+ * in ONE kernel: y = act_pw(W_pw * act_dw(dw3x3(x)) [+ residual]); the depthwise tensor - the widest of the block - stays in
+ * shared memory as the A operand of the pointwise GEMM.  dw: the depthwise ConvBlock (3x3, stride 1 or 2, pad 1, act in
+ * {none, ReLU, ReLU6}), packed with pcv_pack_conv_weights as usual; pw: the 1x1 ConvBlock (Cout <= 256, same activation
+ * family, optional residual), likewise.  pcv_dw_pw_fusable returns 1 inside the kernel's domain (16-bit tiers, output map at
+ * least 14 wide and 8 high), else 0 and the caller records the two convolutions separately. */
+PCV_API int pcv_dw_pw_fusable(const pcv_conv_desc* dw, const pcv_conv_desc* pw, int dtype);
+PCV_API int pcv_dw_pw_fused(pcv_plan* plan, const pcv_conv_desc* dw, const pcv_conv_desc* pw, int dtype, const void* x,
+                    const void* w_dw_packed, const float* bias_dw, const void* w_pw_packed, const float* bias_pw,
+                    const void* residual, void* y, pcv_stream stream);
+
 /* nn.ZeroPad2d((left, right, top, bottom)): the explicit asymmetric padding of a ConvBlock built with a 4-tuple `padding`
  * (conv.py:245-249,279-280) and of EfficientNet's tf_mode forwards (F.pad(x, calc_tf_padding(...)), efficientnet.py:27-55).
  * y is [N, H + top + bottom, W + left + right, C]; the convolution that follows runs with pad = 0. */

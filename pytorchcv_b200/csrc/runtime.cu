@@ -214,6 +214,25 @@ int pcv_bottleneck_tail(pcv_plan* plan, const pcv_conv_desc* d2, const pcv_conv_
   return submit(plan, op, static_cast<cudaStream_t>(stream));
 }
 
+int pcv_dw_pw_fusable(const pcv_conv_desc* dw, const pcv_conv_desc* pw, int dtype) {
+  if (!dw || !pw || !is16(dtype)) return 0;
+  if (validate_conv(dw, dtype) != PCV_OK || validate_conv(pw, dtype) != PCV_OK) return 0;
+  return bf::dwpw_ok(*dw, *pw);
+}
+
+int pcv_dw_pw_fused(pcv_plan* plan, const pcv_conv_desc* dw, const pcv_conv_desc* pw, int dtype, const void* x,
+                    const void* w_dw_packed, const float* bias_dw, const void* w_pw_packed, const float* bias_pw,
+                    const void* residual, void* y, pcv_stream stream) {
+  if (int rc = validate_conv(dw, dtype)) return rc;
+  if (int rc = validate_conv(pw, dtype)) return rc;
+  PCV_REQUIRE(is16(dtype), "the fused depthwise -> pointwise kernel exists in the 16-bit tiers only");
+  Op* op = nullptr;
+  const int rc = (dtype == PCV_F16 ? hf::dwpw_make : bf::dwpw_make)(*dw, *pw, x, reinterpret_cast<const float*>(w_dw_packed),
+                                                                    bias_dw, w_pw_packed, bias_pw, residual, y, &op);
+  if (rc) return rc;
+  return submit(plan, op, static_cast<cudaStream_t>(stream));
+}
+
 int pcv_plan_create(pcv_plan** plan) {
   PCV_REQUIRE(plan != nullptr, "NULL plan out-pointer");
   *plan = new pcv_plan();

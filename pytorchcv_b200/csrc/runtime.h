@@ -133,6 +133,10 @@ EncodeIm2colFn encode_im2col_fn();
   int fused_tail_ok(const pcv_conv_desc& d2, const pcv_conv_desc& d3);                                                   \
   int fused_tail_make(const pcv_conv_desc& d2, const pcv_conv_desc& d3, const void* x, const void* w2,                  \
                       const float* bias2, const void* w3, const float* bias3, const void* res, void* y, Op** out);      \
+  /* conv_dwpw.cu : depthwise 3x3 -> pointwise 1x1 in one kernel (the depthwise tensor stays in shared memory) */       \
+  int dwpw_ok(const pcv_conv_desc& dw, const pcv_conv_desc& pw);                                                         \
+  int dwpw_make(const pcv_conv_desc& dw, const pcv_conv_desc& pw, const void* x, const float* w_dw, const float* b_dw,  \
+                const void* w_pw, const float* b_pw, const void* res, void* y, Op** out);                                \
   /* conv_igemm3s.cu : can the s2d stem take the fused max pool (pcv_stem_s2d_pool_ok) */                                \
   int stem_pool_ok(int C, int H, int W, int k, int Cout);                                                                \
   }

@@ -38,6 +38,23 @@ def set_fuse_tail(enabled: bool) -> None:
 
 # SE units: squeeze moved upstream of the unit's last 1x1 conv by linearity (PCV_SE_FOLD=0: pool the conv's output instead)
 _SE_FOLD = os.environ.get("PCV_SE_FOLD", "1") != "0"
+# depthwise -> pointwise pairs as one fused kernel (pcv_dw_pw_fused); PCV_FUSE_DWPW=0 records the two convolutions
+_FUSE_DWPW = [os.environ.get("PCV_FUSE_DWPW", "1") != "0"]
+
+
+def set_fuse_dwpw(enabled: bool) -> None:
+    _FUSE_DWPW[0] = bool(enabled)
+
+
+def _dw_then_pw(b, dwb, pwb, x, residual=None, post_act=None, **kw):
+    """dw ConvBlock -> pw ConvBlock [+ residual, post_act]: the fused kernel where it applies, else the two convolutions."""
+    if not kw:
+        fused = b.dw_pw(x, dwb, pwb, residual, post_act)
+        if fused is not None:
+            return fused
+    return lower(b, pwb, lower(b, dwb, x), residual=residual, post_act=post_act, **kw)
+
+
 _ALIGN = 1024  # arena / weight blob alignment (TMA needs 16 B; 1 KiB keeps every tensor sector- and line-aligned)
 
 
@@ -367,6 +384,65 @@ class Builder:
             out.pitch, None))
         return out
 
+    def dw_pw(self, x: TRef, dwb: nn.Module, pwb: nn.Module, residual: TRef | None, post_act: int | None) -> TRef | None:
+        """Depthwise ConvBlock -> pointwise ConvBlock (+ residual, + the unit's activation) as ONE fused kernel
+        (include/pcv_b200.h pcv_dw_pw_fused), or None when the pair is outside that kernel's domain."""
+        if not _FUSE_DWPW[0] or not _is16(self.dtype):
+            return None
+        for cb in (dwb, pwb):
+            if (type(cb).__name__ != "ConvBlock" or getattr(cb, "use_pad", False) or not cb.normalize
+                    or cb.conv.padding_mode != "zeros" or isinstance(cb.conv.padding, str)):
+                return None
+        cd, cp = dwb.conv, pwb.conv
+        if cd.in_channels != x.C or cd.groups != cd.in_channels or cd.out_channels != cd.in_channels:
+            return None
+        if cp.in_channels != cd.out_channels or cp.groups != 1 or cd.bias is not None or cp.bias is not None:
+            return None
+        try:
+            geo = [(c.kernel_size, _one(c.stride), _one(c.padding), _one(c.dilation)) for c in (cd, cp)]
+            act_dw = act_code(dwb.activ) if dwb.activate else ACT_NONE
+            act_pw = act_code(pwb.activ) if pwb.activate else ACT_NONE
+        except NotImplementedError:
+            return None
+        if residual is not None:
+            if act_pw != ACT_NONE:
+                return None                      # the block's own activation would sit between the conv and the add
+            act_pw = ACT_NONE if post_act is None else post_act
+        elif post_act not in (None, ACT_NONE):
+            return None
+        (kd, sd, pd, dd), (kp, sp, pp, dp) = geo
+        Ho = (x.H + 2 * pd - dd * (kd[0] - 1) - 1) // sd + 1
+        Wo = (x.W + 2 * pd - dd * (kd[1] - 1) - 1) // sd + 1
+        if Ho <= 0 or Wo <= 0:
+            return None
+        if residual is not None and (residual.N, residual.H, residual.W, residual.C) != (x.N, Ho, Wo, cp.out_channels):
+            return None
+        d_dw = ConvDesc(N=x.N, H=x.H, W=x.W, Cin=x.C, Cout=x.C, kh=kd[0], kw=kd[1], stride=sd, pad=pd, dil=dd, groups=x.C,
+                        act=act_dw, in_pitch=x.pitch, out_pitch=x.C, res_pitch=0, flags=0)
+        d_pw = ConvDesc(N=x.N, H=Ho, W=Wo, Cin=x.C, Cout=cp.out_channels, kh=kp[0], kw=kp[1], stride=sp, pad=pp, dil=dp,
+                        groups=1, act=act_pw, in_pitch=x.C, out_pitch=cp.out_channels,
+                        res_pitch=residual.pitch if residual is not None else 0, flags=0)
+        if not _lib.load().pcv_dw_pw_fusable(C.byref(d_dw), C.byref(d_pw), self.dtype):
+            return None
+        _check_bn(dwb.bn)
+        _check_bn(pwb.bn)
+        out = self.new(x.N, Ho, Wo, cp.out_channels)
+        offs = []
+        for d, cb in ((d_dw, dwb), (d_pw, pwb)):
+            wb, bb = C.c_size_t(), C.c_size_t()
+            _lib.call("pcv_conv_packed_bytes", C.byref(d), self.dtype, C.byref(wb), C.byref(bb))
+            w_off, b_off = self._wblob(wb.value), self._wblob(bb.value)
+            self.weight_jobs.append(("conv", (d, cb.conv, cb.bn, 0, w_off, b_off)))
+            offs += [w_off, b_off]
+        self._use(x, residual, out)
+        dtype = self.dtype
+
+        def emit(plan, ptr, wptr):
+            _lib.call("pcv_dw_pw_fused", plan, C.byref(d_dw), C.byref(d_pw), dtype, ptr(x), wptr(offs[0]), wptr(offs[1]),
+                      wptr(offs[2]), wptr(offs[3]), ptr(residual) if residual is not None else None, ptr(out), None)
+        self.ops.append(emit)
+        return out
+
     def linear(self, x: TRef, fc: nn.Linear, out_f32: bool = True) -> TRef:
         """nn.Linear on pooled features == 1x1 conv on a 1x1 map (resnet.py:320-322,335-336)."""
         if (x.H, x.W) != (1, 1):
@@ -565,7 +641,7 @@ def _lower_convblock(b, m, x, residual=None, post_act=None, out=None, pad_lrtb=N
 @lowers("DwsConvBlock")
 def _lower_dws(b, m, x, **kw):
     """DwsConvBlock.forward (conv.py:605-608): depthwise ConvBlock then pointwise ConvBlock."""
-    return lower(b, m.pw_conv, lower(b, m.dw_conv, x), **kw)
+    return _dw_then_pw(b, m.dw_conv, m.pw_conv, x, **kw)
 
 
 @lowers("MaxPool2d")
@@ -700,8 +776,7 @@ def _lower_seinit(b, m, x, **kw):
 def _lower_linear_bottleneck(b, m, x, **kw):
     """LinearBottleneck.forward (mobilenetv2.py:62-71): [1x1 expand] -> dw3x3 -> 1x1 linear (+x), no final act."""
     y = lower(b, m.conv1, x) if m.use_exp_conv else x
-    y = lower(b, m.conv2, y)
-    return lower(b, m.conv3, y, residual=x if m.residual else None, post_act=None)
+    return _dw_then_pw(b, m.conv2, m.conv3, y, residual=x if m.residual else None, post_act=None)
 
 
 def _tf_pad(m, x: TRef, kernel_size: int, stride: int = 1, dilation: int = 1):
@@ -766,16 +841,14 @@ def _lower_proxyless_unit(b, m, x, **kw):
         return x
     blk = m.body
     y = lower(b, blk.bc_conv, x) if blk.use_bc else x
-    y = lower(b, blk.dw_conv, y)
-    return lower(b, blk.pw_conv, y, residual=x if m.shortcut else None, post_act=None)
+    return _dw_then_pw(b, blk.dw_conv, blk.pw_conv, y, residual=x if m.shortcut else None, post_act=None)
 
 
 @lowers("FBNetUnit", "SPNASUnit")
 def _lower_fbnet_unit(b, m, x, **kw):
     """FBNetUnit.forward (fbnet.py:77-87) == SPNASUnit.forward (spnasnet.py:72-82): [1x1 expand] -> dw -> 1x1 (+x)."""
     y = lower(b, m.exp_conv, x) if m.use_exp_conv else x
-    y = lower(b, m.conv1, y)
-    return lower(b, m.conv2, y, residual=x if m.residual else None, post_act=None)
+    return _dw_then_pw(b, m.conv1, m.conv2, y, residual=x if m.residual else None, post_act=None)
 
 
 @lowers("MnasInitBlock", "MnasFinalBlock", "FBNetInitBlock", "SPNASInitBlock", "SPNASFinalBlock")

@@ -239,6 +239,72 @@ def test_fused_bottleneck_tail(cin, cout, shape, tier, tol):
     assert _rel(got, want) <= tol, (_rel(got, want), names)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("tier,tol", [("bf16", 1.5e-2), ("fp16", 2e-3)])
+@pytest.mark.parametrize("kind,cin,cout,stride,shape", [
+    ("lb", 24, 24, 1, (3, 56, 56)),      # MobileNetV2 stage-2 unit with residual: C=144 (64+64+16 channel blocks), Cout=24
+    ("lb", 16, 24, 2, (2, 112, 112)),    # stride 2, C=96
+    ("lb", 32, 64, 2, (2, 28, 28)),      # stride 2 down to 14x14: the smallest tile the kernel takes
+    ("lb", 64, 64, 1, (1, 14, 14)),      # C=384, one ragged 8x16 tile column
+    ("lb", 32, 32, 1, (2, 19, 37)),      # ragged both ways
+    ("lb0", 64, 16, 1, (2, 56, 56)),     # no expansion conv (the shape of MobileNetV2's first unit), Cout=16
+    ("dws", 64, 128, 1, (2, 56, 56)),    # MobileNet-v1 DwsConvBlock: ReLU after both
+    ("dws", 128, 128, 2, (2, 56, 56)),
+    ("dws", 128, 256, 1, (2, 28, 28)),   # Cout = 256: the widest accumulator (2 x 256 TMEM columns)
+    ("dws", 48, 72, 1, (1, 30, 23)),     # C not a multiple of 64, Cout not a multiple of 16
+])
+def test_fused_dw_pw(kind, cin, cout, stride, shape, tier, tol):
+    """depthwise 3x3 -> pointwise 1x1 (+ residual) as ONE kernel (pcv_dw_pw_fused) against the oracle and against the
+    two-convolution plan: mobilenetv2.py LinearBottleneck (conv2 -> conv3 [+ x]) and common/conv.py DwsConvBlock."""
+    from pytorchcv_b200 import nets as M, blocks as BK, plan as PL
+    n, h, w = shape
+    if kind == "dws":
+        unit = BK.dwsconv3x3_block(in_channels=cin, out_channels=cout, stride=stride)
+    else:
+        unit = M.LinearBottleneck(cin, cout, stride, expansion=(kind == "lb"), remove_exp_conv=True,
+                                  activation=BK.lambda_relu6())
+    unit = seeded_init(unit.eval(), seed=5, randomize_bn=True)
+    x = seeded_input((n, cin, h, w), seed=6)
+    want = oracle_forward(unit, x)
+    fast = P.accelerate(copy.deepcopy(unit).cuda(), dtype=tier, graph=False)
+    got = fast(x.cuda()).float().cpu()
+    names = [r[0] for r in fast.compiled(x.cuda()).profile()]
+    assert any(nm.startswith("conv_dwpw fused") for nm in names), names
+    PL.set_fuse_dwpw(False)
+    try:
+        plain = P.accelerate(copy.deepcopy(unit).cuda(), dtype=tier, graph=False)(x.cuda()).float().cpu()
+    finally:
+        PL.set_fuse_dwpw(True)
+    assert got.shape == want.shape and torch.isfinite(got).all()
+    assert _rel(got, want) <= tol, (_rel(got, want), names)
+    # same operand rounding as the two-kernel plan (the depthwise result is stored in the tier's 16-bit type either
+    # way): only fp32 summation order differs
+    assert _rel(got, plain) <= tol / 4, (_rel(got, plain), names)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["mobilenetv2_w1", "mobilenet_w1", "fbnet_cb", "proxylessnas_gpu"])
+def test_fused_dw_pw_whole_net(name):
+    """Whole networks with their dw -> pw pairs fused: logits within the fp16 tier bound of the oracle and of the unfused
+    plan, same top-1; the plan shrinks by one op per fused pair."""
+    from pytorchcv_b200 import plan as PL
+    net = seeded_init(P.get_model(name, pretrained=False).eval(), seed=0)
+    x = seeded_input((4, 3, 224, 224), seed=1234)
+    want = oracle_forward(net, x)
+    fast = P.accelerate(copy.deepcopy(net).cuda(), dtype="fp16")
+    fused = fast(x.cuda()).cpu()
+    n_fused = sum(r[0].startswith("conv_dwpw fused") for r in fast.compiled(x.cuda()).profile())
+    PL.set_fuse_dwpw(False)
+    try:
+        base = P.accelerate(copy.deepcopy(net).cuda(), dtype="fp16")
+        plain = base(x.cuda()).cpu()
+        assert n_fused > 0 and fast.compiled(x.cuda()).num_ops == base.compiled(x.cuda()).num_ops - n_fused
+    finally:
+        PL.set_fuse_dwpw(True)
+    assert _rel(fused, want) <= 2e-2 and torch.equal(fused.argmax(1), want.argmax(1)), _rel(fused, want)
+    assert _rel(fused, plain) <= 1e-2, _rel(fused, plain)
+
+
 def test_fused_bottleneck_tail_whole_net():
     """ResNet-50 with its three stage-1 tails fused: same logits as the unfused plan to the tier's rounding, same top-1."""
     from pytorchcv_b200 import plan as PL

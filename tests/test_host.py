@@ -114,7 +114,10 @@ def test_lowering_and_arena(name, shape, n_ops, tier):
     out = PL.lower(b, net, x)
     _, trefs = PL._flatten(out)
     # plan ops + the per-call edge ops (fp32 NCHW outputs written after the plan into fresh, caller-owned tensors);
-    assert len(b.ops) + sum(t.tail is not None for t in trefs) == n_ops
+    # on the 16-bit tiers 12 of MobileNetV2's 17 dw->pw pairs (>= 14x14 outputs, >= 2/3 full channel blocks) are one fused
+    # op each
+    n_fused = 12 if (name == "mobilenetv2_w1" and tier == BF16) else 0
+    assert len(b.ops) + sum(t.tail is not None for t in trefs) == n_ops - n_fused
     for t in trefs:
         t.buf.pinned = True
     if name.startswith("deeplab"):
