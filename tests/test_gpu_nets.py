@@ -288,7 +288,9 @@ def test_fused_dw_pw_whole_net(name):
     """Whole networks with their dw -> pw pairs fused: logits within the fp16 tier bound of the oracle and of the unfused
     plan, same top-1; the plan shrinks by one op per fused pair."""
     from pytorchcv_b200 import plan as PL
-    net = seeded_init(P.get_model(name, pretrained=False).eval(), seed=0)
+    # the fp16 tier's contract (DESIGN 4): the reference's own init statistics - with the tests' randomised BN statistics
+    # FBNet's activations reach 1e6, beyond IEEE half
+    net = seeded_init(P.get_model(name, pretrained=False).eval(), seed=0, randomize_bn=False)
     x = seeded_input((4, 3, 224, 224), seed=1234)
     want = oracle_forward(net, x)
     fast = P.accelerate(copy.deepcopy(net).cuda(), dtype="fp16")
