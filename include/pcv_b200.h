@@ -63,7 +63,9 @@ enum pcv_act {
   PCV_ACT_SIGMOID = 3,  /* nn.Sigmoid  activ.py:123-132 */
   PCV_ACT_SWISH = 4,    /* Swish       activ.py:16-21   */
   PCV_ACT_HSWISH = 5,   /* HSwish      activ.py:33-47   */
-  PCV_ACT_HSIGMOID = 6  /* HSigmoid    activ.py:24-30   */
+  PCV_ACT_HSIGMOID = 6, /* HSigmoid    activ.py:24-30   */
+  PCV_ACT_LEAKY_RELU = 7 /* nn.LeakyReLU activ.py:101-120: x >= 0 ? x : act_param * x (dense / grouped convs; the
+                            per-channel nn.PReLU of activ.py:84-98 is pcv_channel_affine_act's `slope`) */
 };
 
 enum pcv_conv_flags {
@@ -92,6 +94,7 @@ typedef struct pcv_conv_desc {
   int32_t res_pitch;      /* channel pitch of residual (0 -> Cout) */
   int32_t flags;          /* pcv_conv_flags */
   int32_t in_row_pitch;   /* elements between consecutive input rows (0 -> W * in_pitch); image pitch = H * that */
+  float act_param;        /* PCV_ACT_LEAKY_RELU: the negative slope (nn.LeakyReLU.negative_slope); ignored otherwise */
 } pcv_conv_desc;
 
 /* ---- library ---------------------------------------------------------------------------------------------- */
@@ -185,6 +188,16 @@ PCV_API int pcv_se_scale_add_act(pcv_plan* plan, int dtype, int N, int HW, int C
 /* y = act(a + b), elementwise over N*HW*C (residual adds that could not be fused into a conv epilogue). */
 PCV_API int pcv_add_act(pcv_plan* plan, int dtype, size_t count, const void* a, const void* b, int act, void* y,
                 pcv_stream stream);
+
+/* y[p, c] = act(x[p, c] * scale[c] + shift[c]) over `pixels` NHWC pixels of C channels (C % 8 == 0), then, when `slope` is
+ * given, negative results are multiplied by slope[c].  scale / shift / slope: fp32 [C] device vectors, each may be NULL.
+ * Serves the stand-alone pieces of the reference that cannot ride on a producing conv's epilogue: the BN -> ReLU
+ * pre-activation of PreConvBlock / PreResActivation (conv.py:717-731, preresnet.py:203-221; scale / shift = the folded
+ * BatchNorm, act = ReLU), nn.PReLU (activ.py:84-98; slope = its weight, broadcast on the host when num_parameters == 1)
+ * and LeakyReLU behind kernels without that epilogue (slope filled with negative_slope). */
+PCV_API int pcv_channel_affine_act(pcv_plan* plan, int dtype, size_t pixels, int C, const void* x, int in_pitch,
+                                   const float* scale, const float* shift, const float* slope, int act, void* y,
+                                   int out_pitch, pcv_stream stream);
 
 /* ---- network edges ------------------------------------------------------------------------------------------- */
 /* Reference tensors are NCHW fp32.  Ingest pads channels with zeros up to c_pitch. */

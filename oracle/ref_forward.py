@@ -47,6 +47,10 @@ def _activation(m: nn.Module, x: torch.Tensor) -> torch.Tensor:
         return x * (x + 3.0).clamp(0.0, 6.0) / 6.0                 # activ.py:46-47
     if name == "HSigmoid":
         return (x + 3.0).clamp(0.0, 6.0) / 6.0                     # activ.py:29-30
+    if isinstance(m, nn.PReLU):
+        return F.prelu(x, m.weight)                                # activ.py:84-98
+    if isinstance(m, nn.LeakyReLU):
+        return F.leaky_relu(x, m.negative_slope)                   # activ.py:101-120
     if isinstance(m, nn.Identity):
         return x
     raise OracleUnsupported(f"activation {name}")
@@ -372,6 +376,50 @@ def fcn8sd(m, x):
     return x
 
 
+# ---- pre-activation family, DarkNet-53 -------------------------------------------------------
+def pre_conv_block(m, x):
+    """PreConvBlock.forward (common/conv.py:717-731): BN -> activation -> conv; optionally also the pre-activated map."""
+    if m.normalize:
+        x = _batchnorm(m.bn, x)
+    if m.activate:
+        x = _activation(m.activ, x)
+    y = _conv2d(m.conv, x)
+    return (y, x) if m.return_preact else y
+
+
+def pre_res_body(m, x):
+    """PreResBlock.forward (preresnet.py:56-59) / PreResBottleneck.forward (preresnet.py:98-102)."""
+    x, x_pre_activ = pre_conv_block(m.conv1, x)
+    x = pre_conv_block(m.conv2, x)
+    if hasattr(m, "conv3"):
+        x = pre_conv_block(m.conv3, x)
+    return x, x_pre_activ
+
+
+def pre_res_unit(m, x):
+    """PreResUnit.forward (preresnet.py:157-163)."""
+    identity = x
+    x, x_pre_activ = pre_res_body(m.body, x)
+    if m.resize_identity:
+        identity = _conv2d(m.identity_conv, x_pre_activ)
+    return x + identity
+
+
+def pre_res_init_block(m, x):
+    """PreResInitBlock.forward (preresnet.py:195-200)."""
+    return _leaf(m.pool, _activation(m.activ, _batchnorm(m.bn, _conv2d(m.conv, x))))
+
+
+def pre_res_activation(m, x):
+    """PreResActivation.forward (preresnet.py:218-221)."""
+    return _activation(m.activ, _batchnorm(m.bn, x))
+
+
+def dark_unit(m, x):
+    """DarkUnit.forward (darknet53.py:45-49)."""
+    return conv_block(m.conv2, conv_block(m.conv1, x)) + x
+
+
 # ---- dispatch --------------------------------------------------------------------------------------------------------
 def _leaf(m, x):
     if isinstance(m, nn.Conv2d):
@@ -408,6 +456,9 @@ _BY_NAME = {
     "SPNASUnit": fbnet_unit, "SPNASInitBlock": mnas_edge_block, "SPNASFinalBlock": mnas_edge_block, "SPNASNet": classifier,
     "MobileNetV3Unit": mobilenetv3_unit, "MobileNetV3FinalBlock": mobilenetv3_final_block,
     "MobileNetV3Classifier": mobilenetv3_classifier, "MobileNetV3": mobilenetv3,
+    "PreConvBlock": pre_conv_block, "PreResBlock": pre_res_body, "PreResBottleneck": pre_res_body, "PreResUnit": pre_res_unit,
+    "PreResInitBlock": pre_res_init_block, "PreResActivation": pre_res_activation, "PreResNet": classifier,
+    "DarkUnit": dark_unit, "DarkNet53": classifier,
     "Concurrent": concurrent, "MultiOutputSequential": multi_output_sequential,
     "ASPPAvgBranch": aspp_avg_branch, "AtrousSpatialPyramidPooling": aspp, "DeepLabv3": deeplabv3,
 }

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("PCV_B200_LIB") or os.path.join(_HERE, "libpcv_b200.so
 
 BF16, F32, F16 = 0, 1, 2                      # pcv_dtype
 IMG_F32, IMG_BF16, IMG_F16, IMG_U8 = 0, 1, 2, 3  # pcv_image_type
-ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SIGMOID, ACT_SWISH, ACT_HSWISH, ACT_HSIGMOID = range(7)
+ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SIGMOID, ACT_SWISH, ACT_HSWISH, ACT_HSIGMOID, ACT_LEAKY_RELU = range(8)
 CONV_OUT_F32, CONV_FORCE_SIMT, CONV_A_IM2COL, CONV_IN_OVERLAP, CONV_POOL3S2, CONV_F32_SPLIT = 1, 2, 4, 8, 16, 32
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = 0, -1, -2, -3, -4
@@ -30,7 +30,7 @@ class PcvError(RuntimeError):
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "N", "H", "W", "Cin", "Cout", "kh", "kw", "stride", "pad", "dil", "groups", "act",
-        "in_pitch", "out_pitch", "res_pitch", "flags", "in_row_pitch")]
+        "in_pitch", "out_pitch", "res_pitch", "flags", "in_row_pitch")] + [("act_param", C.c_float)]
 
 
 _P = C.c_void_p
@@ -60,6 +60,7 @@ SIGNATURES = {
     "pcv_se_excite_ex": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "pcv_se_scale_add_act": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P]),
     "pcv_add_act": (_I, [_P, _I, _Z, _P, _P, _I, _P, _P]),
+    "pcv_channel_affine_act": (_I, [_P, _I, _Z, _I, _P, _I, _P, _P, _P, _I, _P, _I, _P]),
     "pcv_nchw_f32_to_nhwc": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "pcv_nchw_to_nhwc_ex": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "pcv_nhwc_to_nchw_f32": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _P]),

@@ -55,7 +55,7 @@ struct F3Params {
   int HoWo, Wo, stride, pad, dil, kw;
   int num_kblocks, tiles_m, tiles_n;
   int act, has_res;
-  float act_lo, act_hi;
+  float act_lo, act_hi, act_a;
   int a_mode, grouped, g_in_span;
   int kq[3], per_tap, cstride;
   int S, kb_per_split;   // split-K factor and k-blocks per split
@@ -75,8 +75,9 @@ struct F3Smem {
   static constexpr int BYTES = OFF_BAR + NUM_BARS * 8 + 32 + 1024;
 };
 
-__device__ __forceinline__ float f3_act(float x, int act, float lo, float hi) {
+__device__ __forceinline__ float f3_act(float x, int act, float lo, float hi, float a) {
   if (act <= PCV_ACT_RELU6) return fminf(fmaxf(x, lo), hi);
+  if (act == PCV_ACT_LEAKY_RELU) return x >= 0.f ? x : x * a;
   if (act == PCV_ACT_SIGMOID) return 1.f / (1.f + expf(-x));
   if (act == PCV_ACT_SWISH) return x / (1.f + expf(-x));
   if (act == PCV_ACT_HSWISH) return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) / 6.f;
@@ -333,8 +334,8 @@ f32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 const float4 r4 = *reinterpret_cast<const float4*>(rp + i);
                 v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
               }
-              v.x = f3_act(v.x, p.act, p.act_lo, p.act_hi); v.y = f3_act(v.y, p.act, p.act_lo, p.act_hi);
-              v.z = f3_act(v.z, p.act, p.act_lo, p.act_hi); v.w = f3_act(v.w, p.act, p.act_lo, p.act_hi);
+              v.x = f3_act(v.x, p.act, p.act_lo, p.act_hi, p.act_a); v.y = f3_act(v.y, p.act, p.act_lo, p.act_hi, p.act_a);
+              v.z = f3_act(v.z, p.act, p.act_lo, p.act_hi, p.act_a); v.w = f3_act(v.w, p.act, p.act_lo, p.act_hi, p.act_a);
               *reinterpret_cast<float4*>(op + i) = v;
             }
           }
@@ -344,7 +345,7 @@ f32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (i < ncol) {
               float v = run[i] + __ldg(p.bias + n0 + i);
               if (rp) v += rp[i];
-              op[i] = f3_act(v, p.act, p.act_lo, p.act_hi);
+              op[i] = f3_act(v, p.act, p.act_lo, p.act_hi, p.act_a);
             }
           }
         }
@@ -634,6 +635,7 @@ int igemm_split_make(const pcv_conv_desc& d, const void* x, const void* w, const
   p.act = d.act;
   p.act_lo = (d.act == PCV_ACT_RELU || d.act == PCV_ACT_RELU6) ? 0.f : -INFINITY;
   p.act_hi = d.act == PCV_ACT_RELU6 ? 6.f : INFINITY;
+  p.act_a = d.act_param;
   p.has_res = res != nullptr;
   p.grouped = d.groups > 1;
   p.g_in_span = p.grouped ? 64 * (d.Cin / d.groups) / (d.Cout / d.groups) : 0;

@@ -280,7 +280,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           uint32_t o[16];
           if (fancy_act) {
-            fast_act_n(v, p.act);
+            fast_act_n(v, p.act, p.act_a);
             clamp_pack32(v, o, false, false, 0u);
           } else {
             clamp_pack32(v, o, relu, capped, cap2);
@@ -303,7 +303,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (i < ncol) v[i] += e16_to_float(rp[i]);
             }
             if (fancy_act) {
-              fast_act_n(v, p.act);
+              fast_act_n(v, p.act, p.act_a);
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = fminf(fmaxf(v[i], act_lo), act_hi);
@@ -585,6 +585,7 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   p.act = d.act;
   p.act_lo = (d.act == PCV_ACT_RELU || d.act == PCV_ACT_RELU6) ? 0.f : -INFINITY;
   p.act_hi = d.act == PCV_ACT_RELU6 ? 6.f : INFINITY;
+  p.act_a = d.act_param;
   p.has_res = res != nullptr;
   p.grouped = grouped;
   p.g_in_span = grouped ? 64 * (d.Cin / d.groups) / (d.Cout / d.groups) : 0;

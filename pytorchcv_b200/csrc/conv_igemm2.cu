@@ -335,7 +335,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           }
           uint32_t o[16];
           if (fancy_act) {
-            fast_act_n(v, p.act);
+            fast_act_n(v, p.act, p.act_a);
             clamp_pack32(v, o, false, false, 0u);
           } else {
             clamp_pack32(v, o, relu, capped, cap2);

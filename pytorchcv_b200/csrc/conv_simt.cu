@@ -17,10 +17,12 @@ struct SimtParams {
   int kh, kw, stride, pad, dil;
   int in_pitch, out_pitch, res_pitch;
   int act, out_f32;
+  float act_a;   // PCV_ACT_LEAKY_RELU: negative slope
 };
 
-__device__ __forceinline__ float simt_act(float v, int act) {
+__device__ __forceinline__ float simt_act(float v, int act, float a) {
   switch (act) {
+    case PCV_ACT_LEAKY_RELU: return v >= 0.f ? v : v * a;
     case PCV_ACT_RELU: return fmaxf(v, 0.f);
     case PCV_ACT_RELU6: return fminf(fmaxf(v, 0.f), 6.f);
     case PCV_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
@@ -141,7 +143,7 @@ conv_simt_kernel(const SimtParams p, const T* __restrict__ x, const float* __res
       const int co = g * p.cout_g + n;
       float v = acc[i][j] + bias[co];
       if (res) v += to_f<T>(res[static_cast<size_t>(m) * p.res_pitch + co]);
-      v = simt_act(v, p.act);
+      v = simt_act(v, p.act, p.act_a);
       const size_t o = static_cast<size_t>(m) * p.out_pitch + co;
       if (p.out_f32 || sizeof(T) == 4) {
         reinterpret_cast<float*>(y)[o] = v;
@@ -251,6 +253,7 @@ int simt_make(const pcv_conv_desc& d, int dtype, const void* x, const void* w, c
   p.out_pitch = pitch_or(d.out_pitch, d.Cout);
   p.res_pitch = pitch_or(d.res_pitch, d.Cout);
   p.act = d.act;
+  p.act_a = d.act_param;
   p.out_f32 = (d.flags & PCV_CONV_OUT_F32) ? 1 : 0;
   PCV_REQUIRE(ceil_div(p.cout_g, 32) <= 65535 && p.groups <= 65535, "grid too large for the CUDA-core conv");
   op->dtype = dtype; op->x = x; op->w = reinterpret_cast<const float*>(w); op->bias = bias; op->res = res; op->y = y;

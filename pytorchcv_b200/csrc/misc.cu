@@ -849,6 +849,65 @@ struct BilinearOp : Op {
   }
 };
 
+// y = act(x * scale[c] + shift[c]), negative side times slope[c]: the stand-alone BN -> ReLU pre-activation of PreConvBlock /
+// PreResActivation (conv.py:717-731, preresnet.py:203-221), nn.PReLU and LeakyReLU (activ.py:84-120).  One pass at the copy
+// roofline: a thread owns 8 channels of a pixel (one 16-byte load / store in the 16-bit tiers), the per-channel vectors
+// come through the read-only path (C * 12 bytes, L1-resident).
+template <typename T>
+__global__ void __launch_bounds__(256)
+channel_affine_act_kernel(long long pixels, int C, int in_pitch, int out_pitch, const T* __restrict__ x,
+                          const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ slope, int act, T* __restrict__ y) {
+  const int cv = C >> 3;
+  const long long total = pixels * cv;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(idx % cv) << 3;
+    const long long p = idx / cv;
+    float v[8];
+    V8<T>::load(x + p * in_pitch + c8, v);
+    if (scale) {
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c8)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c8 + 4));
+      v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+    }
+    if (shift) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + c8)), b1 = __ldg(reinterpret_cast<const float4*>(shift + c8 + 4));
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    if (act != PCV_ACT_NONE) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = misc_act(v[e], act);
+    }
+    if (slope) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(slope + c8)), a1 = __ldg(reinterpret_cast<const float4*>(slope + c8 + 4));
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = v[e] >= 0.f ? v[e] : v[e] * a[e];
+    }
+    V8<T>::store(y + p * out_pitch + c8, v);
+  }
+}
+
+struct ChannelAffineOp : Op {
+  int dtype, C, in_pitch, out_pitch, act;
+  long long pixels;
+  const void* x;
+  const float *scale, *shift, *slope;
+  void* y;
+  template <typename T>
+  void run(int grid, cudaStream_t s) {
+    channel_affine_act_kernel<T><<<grid, 256, 0, s>>>(pixels, C, in_pitch, out_pitch, (const T*)x, scale, shift, slope, act, (T*)y);
+  }
+  cudaError_t launch(cudaStream_t s) override {
+    g_launches++;
+    const int grid = grid_for(pixels * (C >> 3));
+    if (dtype == PCV_F32) run<float>(grid, s);
+    else if (dtype == PCV_F16) run<__half>(grid, s);
+    else run<__nv_bfloat16>(grid, s);
+    return cudaGetLastError();
+  }
+};
+
 }  // namespace pcv
 
 using namespace pcv;
@@ -977,6 +1036,31 @@ int pcv_add_act(pcv_plan* plan, int dtype, size_t count, const void* a, const vo
   op->dtype = dtype; op->act = act; op->vecs = static_cast<long long>(count / 8); op->a = a; op->b = b; op->y = y;
   op->name = std::string("add_act_") + dn(dtype);
   op->bytes = 3.0 * esize(dtype) * static_cast<double>(count);
+  return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
+}
+
+int pcv_channel_affine_act(pcv_plan* plan, int dtype, size_t pixels, int C, const void* x, int in_pitch, const float* scale,
+                           const float* shift, const float* slope, int act, void* y, int out_pitch, pcv_stream stream) {
+  PCV_DTYPE_OK(dtype);
+  PCV_REQUIRE(x && y, "NULL tensor pointer");
+  in_pitch = pitch_or(in_pitch, C);
+  out_pitch = pitch_or(out_pitch, C);
+  PCV_REQUIRE(pixels > 0 && C > 0 && C % 8 == 0 && in_pitch >= C && out_pitch >= C, "channel_affine_act needs C %% 8 == 0");
+  const int vec = dtype == PCV_F32 ? 4 : 8;   // 16-byte vector accesses
+  PCV_REQUIRE(in_pitch % vec == 0 && out_pitch % vec == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
+                  reinterpret_cast<uintptr_t>(y) % 16 == 0,
+              "channel_affine_act needs 16-byte aligned pixel rows");
+  for (const float* v : {scale, shift, slope})
+    PCV_REQUIRE(reinterpret_cast<uintptr_t>(v) % 16 == 0, "channel_affine_act needs 16-byte aligned channel vectors");
+  PCV_REQUIRE(act >= PCV_ACT_NONE && act <= PCV_ACT_HSIGMOID, "unknown activation %d", act);
+  auto op = std::make_unique<ChannelAffineOp>();
+  op->dtype = dtype; op->C = C; op->in_pitch = in_pitch; op->out_pitch = out_pitch; op->act = act;
+  op->pixels = static_cast<long long>(pixels); op->x = x; op->scale = scale; op->shift = shift; op->slope = slope; op->y = y;
+  char nm[112];
+  snprintf(nm, sizeof nm, "channel_affine_act_%s C=%d px=%lld%s%s act=%d", dn(dtype), C, op->pixels, scale ? " bn" : "",
+           slope ? " slope" : "", act);
+  op->name = nm;
+  op->bytes = 2.0 * esize(dtype) * static_cast<double>(pixels) * C;
   return submit(plan, op.release(), static_cast<cudaStream_t>(stream));
 }
 

@@ -361,7 +361,7 @@ __device__ __forceinline__ float fast_hswish(float x) { return x * fast_hsigmoid
 // once blew the epilogue up to 100 KB of SASS).  Codes are pcv_act (include/pcv_b200.h): 3 sigmoid, 4 swish, 5 h-swish,
 // 6 h-sigmoid; the clamp family (0..2) is normally handled by the callers' packed paths.
 template <int N>
-__device__ __forceinline__ void fast_act_n(float (&v)[N], int act) {
+__device__ __forceinline__ void fast_act_n(float (&v)[N], int act, float leaky_slope = 0.f) {
   if (act == PCV_ACT_SWISH) {
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = fast_swish(v[i]);
@@ -380,6 +380,9 @@ __device__ __forceinline__ void fast_act_n(float (&v)[N], int act) {
   } else if (act == PCV_ACT_RELU6) {
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = fminf(fmaxf(v[i], 0.f), 6.f);
+  } else if (act == PCV_ACT_LEAKY_RELU) {   // nn.LeakyReLU (activ.py:101-120)
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = v[i] >= 0.f ? v[i] : v[i] * leaky_slope;
   }
 }
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }

@@ -94,7 +94,12 @@ static int validate_conv(const pcv_conv_desc* d, int dtype) {
   PCV_REQUIRE(d->kh > 0 && d->kw > 0 && d->stride > 0 && d->dil > 0 && d->pad >= 0, "bad kernel/stride/pad/dilation");
   PCV_REQUIRE(d->groups > 0 && d->Cin % d->groups == 0 && d->Cout % d->groups == 0,
               "channels (%d -> %d) not divisible by groups=%d", d->Cin, d->Cout, d->groups);
-  PCV_REQUIRE(d->act >= PCV_ACT_NONE && d->act <= PCV_ACT_HSIGMOID, "unknown activation %d", d->act);
+  PCV_REQUIRE(d->act >= PCV_ACT_NONE && d->act <= PCV_ACT_LEAKY_RELU, "unknown activation %d", d->act);
+  if (d->act == PCV_ACT_LEAKY_RELU) {
+    std::string why;
+    PCV_REQUIRE(conv_route(*d, dtype, &why) != ROUTE_DW,
+                "the LeakyReLU epilogue serves dense / grouped convs; a depthwise conv takes pcv_channel_affine_act behind it");
+  }
   PCV_REQUIRE((pitch_or(d->in_pitch, d->Cin) >= d->Cin || (d->flags & PCV_CONV_IN_OVERLAP)) &&
                   pitch_or(d->out_pitch, d->Cout) >= d->Cout,
               "channel pitch smaller than channel count");

@@ -21,8 +21,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import (ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SIGMOID, ACT_SWISH, ACT_HSWISH, ACT_HSIGMOID, BF16, F16, F32,
-                   ConvDesc)
+from ._lib import (ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SIGMOID, ACT_SWISH, ACT_HSWISH, ACT_HSIGMOID, ACT_LEAKY_RELU, BF16,
+                   F16, F32, ConvDesc)
 
 # fp32 tier: dense / grouped convs on the tensor cores as a 3-way bf16 split (PCV_F32_SPLIT=0: the CUDA-core kernel instead)
 _F32_SPLIT = os.environ.get("PCV_F32_SPLIT", "1") != "0"
@@ -138,7 +138,33 @@ def act_code(m: nn.Module | None) -> int:
         return ACT_HSWISH
     if name == "HSigmoid" or isinstance(m, nn.Hardsigmoid):
         return ACT_HSIGMOID
+    if isinstance(m, nn.LeakyReLU):
+        return ACT_LEAKY_RELU            # slope: act_param(m); fused into dense / grouped conv epilogues
     raise NotImplementedError(f"activation {name} is outside the B200 eval path (SURVEY 8a8)")
+
+
+def act_param(m: nn.Module | None) -> float:
+    """The scalar an activation code carries: nn.LeakyReLU's negative slope (activ.py:101-120)."""
+    return float(m.negative_slope) if isinstance(m, nn.LeakyReLU) else 0.0
+
+
+def _standalone_act(m: nn.Module | None, conv: nn.Conv2d | None = None) -> bool:
+    """Activations that do not ride on the conv's epilogue and run as one pcv_channel_affine_act pass behind it: nn.PReLU
+    (per-channel slopes, activ.py:84-98) and a LeakyReLU behind a depthwise conv."""
+    if isinstance(m, nn.PReLU):
+        return True
+    return isinstance(m, nn.LeakyReLU) and conv is not None and conv.groups > 1 and conv.groups == conv.in_channels
+
+
+def _bn_scale_shift(bn: nn.BatchNorm2d):
+    """Eval BatchNorm as y = x * scale + shift (norm.py:34-50), computed in float64 on the host."""
+    _check_bn(bn)
+    with torch.no_grad():
+        var, mean = bn.running_var.detach().double(), bn.running_mean.detach().double()
+        g = bn.weight.detach().double() if bn.weight is not None else torch.ones_like(var)
+        be = bn.bias.detach().double() if bn.bias is not None else torch.zeros_like(var)
+        sc = g / torch.sqrt(var + bn.eps)
+        return sc.float().contiguous(), (be - mean * sc).float().contiguous()
 
 
 def _check_bn(bn: nn.Module) -> None:
@@ -257,7 +283,7 @@ class Builder:
     # -- ops ----------------------------------------------------------------------------------------------------
     def conv(self, x: TRef, conv: nn.Conv2d, bn: nn.Module | None = None, act: int = ACT_NONE,
              residual: TRef | None = None, out: TRef | None = None, out_f32: bool = False, flags: int = 0,
-             pad_lrtb: tuple | None = None) -> TRef:
+             pad_lrtb: tuple | None = None, act_a: float = 0.0) -> TRef:
         """One fused ConvBlock: conv + folded BN + optional residual + activation.  `pad_lrtb` = (left, right, top, bottom)
         replaces the conv's own padding (ZeroPad2d / tf_mode): symmetric amounts ride on the kernel's padding, asymmetric
         ones are materialised by one zero-pad pass."""
@@ -274,7 +300,8 @@ class Builder:
             else:
                 x = self.pad(x, pl, pr, pt, pb)
         cin, cout, groups = conv.in_channels, conv.out_channels, conv.groups
-        if residual is None and out is None and not out_f32 and self._s2d_stem(x, conv, kh, k_stride, k_pad, k_dil):
+        if (residual is None and out is None and not out_f32 and act != ACT_LEAKY_RELU
+                and self._s2d_stem(x, conv, kh, k_stride, k_pad, k_dil)):
             if bn is not None:
                 _check_bn(bn)
             return self._conv_s2d(x, conv, bn, act, kh)
@@ -305,7 +332,7 @@ class Builder:
         d = ConvDesc(N=x.N, H=x.H, W=x.W, Cin=x.C, Cout=cout, kh=kh, kw=kw, stride=k_stride, pad=k_pad, dil=k_dil,
                      groups=groups, act=act, in_pitch=x.pitch, out_pitch=out.pitch,
                      res_pitch=residual.pitch if residual is not None else 0,
-                     flags=flags | (_lib.CONV_OUT_F32 if (out_f32 and _is16(self.dtype)) else 0))
+                     flags=flags | (_lib.CONV_OUT_F32 if (out_f32 and _is16(self.dtype)) else 0), act_param=act_a)
         wb, bb, ws = C.c_size_t(), C.c_size_t(), C.c_size_t()
         _lib.call("pcv_conv_packed_bytes", C.byref(d), self.dtype, C.byref(wb), C.byref(bb))
         _lib.call("pcv_conv_workspace_bytes", C.byref(d), self.dtype, C.byref(ws))
@@ -531,6 +558,40 @@ class Builder:
             "pcv_add_act", plan, a.dtype, a.N * a.H * a.W * a.C, ptr(a), ptr(b), act, ptr(out), None))
         return out
 
+    def affine_act(self, x: TRef, scale: torch.Tensor | None, shift: torch.Tensor | None, act: int = ACT_NONE,
+                   slope: torch.Tensor | None = None) -> TRef:
+        """y = act(x * scale[c] + shift[c]), negative side times slope[c] (include/pcv_b200.h pcv_channel_affine_act): the
+        BN -> ReLU pre-activation of PreConvBlock / PreResActivation, nn.PReLU, LeakyReLU behind a depthwise conv."""
+        if x.C % 8 != 0:
+            raise NotImplementedError(f"a stand-alone normalisation / activation pass needs C % 8 == 0, got {x.C}")
+        out = self.new(x.N, x.H, x.W, x.C, dtype=x.dtype)
+        offs = []
+        for t in (scale, shift, slope):
+            if t is None:
+                offs.append(None)
+                continue
+            if t.numel() != x.C:
+                raise ValueError(f"per-channel vector of {t.numel()} values for {x.C} channels")
+            offs.append(self._wblob(x.C * 4))
+            self.weight_jobs.append(("raw", (t, offs[-1])))
+        self._use(x, out)
+
+        def emit(plan, ptr, wptr):
+            _lib.call("pcv_channel_affine_act", plan, x.dtype, x.N * x.H * x.W, x.C, ptr(x), x.pitch,
+                      *(wptr(o) if o is not None else None for o in offs[:3]), act, ptr(out), out.pitch, None)
+        self.ops.append(emit)
+        return out
+
+    def activation(self, x: TRef, m: nn.Module) -> TRef:
+        """A stand-alone activation module on a map (PReLU / LeakyReLU / any pcv_act code) as one pass."""
+        if isinstance(m, nn.PReLU):
+            w = m.weight.detach().float()
+            return self.affine_act(x, None, None, ACT_NONE, (w.expand(x.C) if w.numel() == 1 else w).contiguous())
+        if isinstance(m, nn.LeakyReLU):
+            return self.affine_act(x, None, None, ACT_NONE,
+                                   torch.full((x.C,), float(m.negative_slope), dtype=torch.float32, device=self.device))
+        return self.affine_act(x, None, None, act_code(m))
+
     def _edge_out(self, x: TRef, H: int, W: int, name: str, launch) -> TRef:
         """An fp32 NCHW tensor the reference returns (freshly allocated, caller-owned): produced per call by
         `launch(plan=None, ptr, out_ptr, stream)` after the plan, straight into a new torch tensor - no arena storage."""
@@ -628,13 +689,20 @@ def _lower_convblock(b, m, x, residual=None, post_act=None, out=None, pad_lrtb=N
             raise NotImplementedError("ZeroPad2d ConvBlock behind an explicit F.pad")
         pad_lrtb = tuple(int(v) for v in m.pad.padding)
     bn = m.bn if m.normalize else None
-    act = act_code(m.activ) if m.activate else ACT_NONE
-    if residual is None and post_act is None:
-        return b.conv(x, m.conv, bn, act, out=out, pad_lrtb=pad_lrtb)
     post = ACT_NONE if post_act is None else post_act
+    if m.activate and _standalone_act(m.activ, m.conv):
+        # nn.PReLU (per-channel slopes) / LeakyReLU behind a depthwise conv: one pass behind the conv
+        if out is not None:
+            raise NotImplementedError("a ConvBlock with a stand-alone activation cannot write into a concat slice")
+        y = b.activation(b.conv(x, m.conv, bn, ACT_NONE, pad_lrtb=pad_lrtb), m.activ)
+        return b.add_act(y, residual, post) if residual is not None else y
+    act = act_code(m.activ) if m.activate else ACT_NONE
+    act_a = act_param(m.activ) if m.activate else 0.0
+    if residual is None and post_act is None:
+        return b.conv(x, m.conv, bn, act, out=out, pad_lrtb=pad_lrtb, act_a=act_a)
     if act == ACT_NONE:
         return b.conv(x, m.conv, bn, post, residual=residual, out=out, pad_lrtb=pad_lrtb)   # fused: act(conv + residual)
-    y = b.conv(x, m.conv, bn, act, pad_lrtb=pad_lrtb)                      # block has its own activation
+    y = b.conv(x, m.conv, bn, act, pad_lrtb=pad_lrtb, act_a=act_a)         # block has its own activation
     return b.add_act(y, residual, post) if residual is not None else y
 
 
@@ -777,6 +845,88 @@ def _lower_linear_bottleneck(b, m, x, **kw):
     """LinearBottleneck.forward (mobilenetv2.py:62-71): [1x1 expand] -> dw3x3 -> 1x1 linear (+x), no final act."""
     y = lower(b, m.conv1, x) if m.use_exp_conv else x
     return _dw_then_pw(b, m.conv2, m.conv3, y, residual=x if m.residual else None, post_act=None)
+
+
+# ---- pre-activation family (conv.py:652-732, preresnet.py) ------------------------------------------------------------
+def _pre_act(b, m, x):
+    """The BN -> activation half of a PreConvBlock (conv.py:717-721) as one stand-alone pass over `x`."""
+    scale = shift = None
+    if m.normalize:
+        scale, shift = _bn_scale_shift(m.bn)
+    if m.activate and _standalone_act(m.activ):
+        return b.activation(b.affine_act(x, scale, shift) if scale is not None else x, m.activ)
+    if m.activate and isinstance(m.activ, nn.LeakyReLU):
+        slope = torch.full((x.C,), float(m.activ.negative_slope), dtype=torch.float32)
+        return b.affine_act(x, scale, shift, ACT_NONE, slope)
+    act = act_code(m.activ) if m.activate else ACT_NONE
+    if scale is None and act == ACT_NONE:
+        return x
+    return b.affine_act(x, scale, shift, act)
+
+
+@lowers("PreConvBlock")
+def _lower_preconv(b, m, x, **kw):
+    """PreConvBlock.forward (conv.py:717-731): BN -> ReLU -> conv; with return_preact the activated map is the second result
+    (PreResUnit feeds it to its identity convolution, preresnet.py:157-163)."""
+    pre = _pre_act(b, m, x)
+    y = b.conv(pre, m.conv, None, ACT_NONE)
+    return (y, pre) if m.return_preact else y
+
+
+def _pre_chain(b, blocks, x, residual=None):
+    """PreConvBlocks in series: block i+1's BN -> activation is a per-output-channel affine + activation of block i's conv, so
+    it rides on that conv's epilogue (folded weights / bias); only the first block's pre-activation needs its own pass.
+    `residual`: a tensor, or a function of the first block's pre-activated input (PreResUnit's projection shortcut).
+    Returns (result of the last conv [+ residual], first block's pre-activated input)."""
+    pre = _pre_act(b, blocks[0], x)
+    if callable(residual):
+        residual = residual(pre)
+    y = pre
+    for i, blk in enumerate(blocks):
+        nxt = blocks[i + 1] if i + 1 < len(blocks) else None
+        if nxt is None:
+            y = b.conv(y, blk.conv, None, ACT_NONE, residual=residual)
+        elif _standalone_act(nxt.activ if nxt.activate else None):
+            y = _pre_act(b, nxt, b.conv(y, blk.conv, None, ACT_NONE))
+        else:
+            y = b.conv(y, blk.conv, nxt.bn if nxt.normalize else None, act_code(nxt.activ) if nxt.activate else ACT_NONE,
+                       act_a=act_param(nxt.activ) if nxt.activate else 0.0)
+    return y, pre
+
+
+@lowers("PreResBlock", "PreResBottleneck")
+def _lower_preres_body(b, m, x, residual=None, **kw):
+    """PreResBlock.forward / PreResBottleneck.forward (preresnet.py:56-59, 98-102): conv1 (returns its pre-activation) ->
+    conv2 [-> conv3]; result (x, x_pre_activ) like the reference."""
+    blocks = [m.conv1, m.conv2] + ([m.conv3] if hasattr(m, "conv3") else [])
+    return _pre_chain(b, blocks, x, residual=residual)
+
+
+@lowers("PreResUnit")
+def _lower_preres_unit(b, m, x, **kw):
+    """PreResUnit.forward (preresnet.py:157-163): body(x) + (identity_conv(pre-activated x) | x), no activation after the add.
+    The add rides on the last conv's epilogue; the projection reads the pre-activated map the body's first block produced."""
+    shortcut = (lambda pre: lower(b, m.identity_conv, pre)) if m.resize_identity else x
+    return lower(b, m.body, x, residual=shortcut)[0]
+
+
+@lowers("PreResInitBlock")
+def _lower_preres_init(b, m, x, **kw):
+    """PreResInitBlock.forward (preresnet.py:195-200): bare conv7x7 -> BN -> ReLU -> max pool == ResInitBlock's arithmetic."""
+    return lower(b, m.pool, b.conv(x, m.conv, m.bn, act_code(m.activ)))
+
+
+@lowers("PreResActivation")
+def _lower_preres_activation(b, m, x, **kw):
+    """PreResActivation.forward (preresnet.py:218-221): the network's last BN -> ReLU."""
+    scale, shift = _bn_scale_shift(m.bn)
+    return b.affine_act(x, scale, shift, act_code(m.activ))
+
+
+@lowers("DarkUnit")
+def _lower_dark_unit(b, m, x, **kw):
+    """DarkUnit.forward (darknet53.py:45-49): conv1x1 -> conv3x3 (each with its LeakyReLU) + x, nothing after the add."""
+    return lower(b, m.conv2, lower(b, m.conv1, x), residual=x, post_act=ACT_NONE)
 
 
 def _tf_pad(m, x: TRef, kernel_size: int, stride: int = 1, dilation: int = 1):
@@ -992,7 +1142,8 @@ def _flat(t: TRef) -> TRef:
     return t
 
 
-@lowers("ResNet", "SEResNeXt", "SEResNet", "ResNeXt", "MobileNet", "EfficientNet", "MnasNet", "FBNet", "SPNASNet", "SENet", "ProxylessNAS")
+@lowers("ResNet", "SEResNeXt", "SEResNet", "ResNeXt", "MobileNet", "EfficientNet", "MnasNet", "FBNet", "SPNASNet", "SENet", "ProxylessNAS",
+        "PreResNet", "DarkNet53")
 def _lower_classifier(b, m, x, **kw):
     """features -> view(N,-1) -> [Dropout ->] Linear (resnet.py:333-337, seresnext.py:136-140, efficientnet.py:354-358)."""
     return _flat(lower(b, m.output, lower(b, m.features, x)))

@@ -22,7 +22,9 @@ from pytorchcv.models.common.att import SEBlock  # noqa: E402
 from pytorchcv.models.resnet import ResUnit  # noqa: E402
 from pytorchcv.models.mobilenetv2 import LinearBottleneck  # noqa: E402
 from pytorchcv.models.seresnext import SEResNeXtUnit  # noqa: E402
-from pytorchcv.models.common.activ import lambda_relu6, lambda_swish, lambda_hswish  # noqa: E402
+from pytorchcv.models.common.activ import lambda_relu6, lambda_swish, lambda_hswish, lambda_prelu, lambda_leakyrelu  # noqa: E402
+from pytorchcv.models.common.conv import PreConvBlock, dwconv3x3_block  # noqa: E402
+from pytorchcv.models.preresnet import PreResUnit  # noqa: E402
 from pytorchcv.models.mobilenetv3 import MobileNetV3Unit  # noqa: E402
 from pytorchcv.models.common.norm import lambda_batchnorm2d  # noqa: E402
 from pytorchcv.models.efficientnet import EffiDwsConvUnit, EffiInvResUnit  # noqa: E402
@@ -53,7 +55,12 @@ NETS = [
     ("senet16_bs2", "senet16", {}, (2, 3, 224, 224), 0, 1),
     ("proxylessnas_mobile_bs2", "proxylessnas_mobile", {}, (2, 3, 224, 224), 0, 1),
     ("efficientnet_b0b_bs2", "efficientnet_b0b", {}, (2, 3, 224, 224), 0, 1),    # tf_mode: asymmetric "SAME" padding
+    ("preresnet18_bs2", "preresnet18", {}, (2, 3, 224, 224), 0, 1),              # PreConvBlock family
+    ("preresnet50_bs2", "preresnet50", {}, (2, 3, 224, 224), 0, 1),
+    ("darknet53_bs2", "darknet53", {}, (2, 3, 224, 224), 0, 1),                  # LeakyReLU epilogues
 ]
+
+NO_MIRROR = {"preresnet18", "preresnet50", "darknet53"}
 
 # block-level cases: (stem, ctor, input shape)
 BLOCKS = [
@@ -84,6 +91,16 @@ BLOCKS = [
                                                     tf_mode=True), (1, 24, 16, 16)),
     ("mnv3_unit_k5_s2_se", lambda: MobileNetV3Unit(24, 40, exp_channels=96, stride=2, use_kernel3=False,
                                                    activation=lambda_hswish(), use_se=True), (1, 24, 17, 15)),
+    ("convblock_3x3_prelu", lambda: conv3x3_block(in_channels=16, out_channels=24, activation=lambda_prelu(24)), (2, 16, 13, 13)),
+    ("convblock_1x1_prelu1", lambda: ConvBlock(32, 64, kernel_size=1, activation=lambda_prelu(1)), (2, 32, 9, 9)),
+    ("convblock_3x3_leaky", lambda: conv3x3_block(in_channels=16, out_channels=32, stride=2,
+                                                  activation=lambda_leakyrelu(negative_slope=0.1)), (2, 16, 15, 15)),
+    ("dwconv3x3_leaky", lambda: dwconv3x3_block(in_channels=24, out_channels=24,
+                                                activation=lambda_leakyrelu(negative_slope=0.2)), (1, 24, 11, 11)),
+    ("preconv_3x3_preact", lambda: PreConvBlock(16, 32, kernel_size=3, stride=1, padding=1, return_preact=True), (2, 16, 12, 12)),
+    ("preconv_1x1_s2_bias", lambda: PreConvBlock(24, 16, kernel_size=1, stride=2, padding=0, bias=True), (2, 24, 10, 10)),
+    ("preresunit_bottleneck_s2", lambda: PreResUnit(64, 128, stride=2, bottleneck=True, conv1_stride=True), (2, 64, 14, 14)),
+    ("preresunit_basic", lambda: PreResUnit(32, 32, stride=1, bottleneck=False, conv1_stride=False), (2, 32, 8, 8)),
 ]
 
 
@@ -113,6 +130,10 @@ def main():
             arrs[f"out{i}_sha1"] = np.frombuffer(sha(a).encode(), dtype=np.uint8)
             arrs[f"out{i}"] = a[..., ::sub, ::sub] if (a.ndim == 4 and sub > 1) else a
         arrs["n_params"] = np.array(sum(p.numel() for p in net.parameters()))
+        if name in NO_MIRROR:   # lowered from the reference's own modules: no mirror class whose state_dict to pin
+            np.savez_compressed(os.path.join(OUT, stem + ".npz"), **arrs)
+            print(stem, [tuple(t.shape) for t in ys], int(arrs["n_params"]))
+            continue
         keys[name] = {"n": len(net.state_dict()),
                       "sha1": hashlib.sha1("\n".join(f"{k}:{tuple(v.shape)}" for k, v in net.state_dict().items())
                                            .encode()).hexdigest()}
@@ -127,8 +148,9 @@ def main():
         blk = seeded_init(ctor().eval(), seed=7, randomize_bn=True)
         x = seeded_input(shape, seed=99)
         y = blk(x)
-        np.savez_compressed(os.path.join(OUT, "block_" + stem + ".npz"), out0=y.numpy())
-        print("block", stem, tuple(y.shape))
+        ys = y if isinstance(y, (tuple, list)) else (y,)
+        np.savez_compressed(os.path.join(OUT, "block_" + stem + ".npz"), **{f"out{i}": t.numpy() for i, t in enumerate(ys)})
+        print("block", stem, [tuple(t.shape) for t in ys])
 
 
 if __name__ == "__main__":

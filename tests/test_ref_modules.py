@@ -1,0 +1,165 @@
+"""Families lowered straight from the REFERENCE'S OWN modules (no mirror classes): the pre-activation PreConvBlock family
+(common/conv.py:652-732, preresnet.py), LeakyReLU / PReLU activations (common/activ.py:84-120, darknet53.py).
+
+`accelerate()` pattern-matches on the reference's class names, so the unmodified `pytorchcv` package is the module source:
+/root/reference in the build container, `baseline/_ref` (the reference-arm install, which travels with the repo) on the GPU
+box.  CPU tests pin the oracle restatements against golden vectors produced by the reference (tests/golden/make_golden.py)
+and dry-run the lowerings; the GPU tests compare the CUDA path with the oracle and the golden vectors through the C ABI.
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+import pytorchcv_b200 as P
+from oracle import oracle_forward, seeded_init, seeded_input
+from conftest import GOLDEN, REFERENCE, ROOT
+
+
+def _ref():
+    """The unmodified reference package, or skip."""
+    for path in (REFERENCE, os.path.join(ROOT, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(path, "pytorchcv")):
+            if path not in sys.path:
+                sys.path.insert(0, path)
+            import pytorchcv  # noqa: F401
+            return pytorchcv
+    pytest.skip("the reference package is neither at /root/reference nor installed under baseline/_ref")
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30))
+
+
+def _tuple(y):
+    return tuple(y) if isinstance(y, (tuple, list)) else (y,)
+
+
+def _block(stem):
+    _ref()
+    from pytorchcv.models.common.conv import ConvBlock, PreConvBlock, conv3x3_block, dwconv3x3_block
+    from pytorchcv.models.common.activ import lambda_prelu, lambda_leakyrelu
+    from pytorchcv.models.preresnet import PreResUnit
+    table = {
+        "convblock_3x3_prelu": (lambda: conv3x3_block(in_channels=16, out_channels=24, activation=lambda_prelu(24)), (2, 16, 13, 13)),
+        "convblock_1x1_prelu1": (lambda: ConvBlock(32, 64, kernel_size=1, activation=lambda_prelu(1)), (2, 32, 9, 9)),
+        "convblock_3x3_leaky": (lambda: conv3x3_block(in_channels=16, out_channels=32, stride=2,
+                                                      activation=lambda_leakyrelu(negative_slope=0.1)), (2, 16, 15, 15)),
+        "dwconv3x3_leaky": (lambda: dwconv3x3_block(in_channels=24, out_channels=24,
+                                                    activation=lambda_leakyrelu(negative_slope=0.2)), (1, 24, 11, 11)),
+        "preconv_3x3_preact": (lambda: PreConvBlock(16, 32, kernel_size=3, stride=1, padding=1, return_preact=True), (2, 16, 12, 12)),
+        "preconv_1x1_s2_bias": (lambda: PreConvBlock(24, 16, kernel_size=1, stride=2, padding=0, bias=True), (2, 24, 10, 10)),
+        "preresunit_bottleneck_s2": (lambda: PreResUnit(64, 128, stride=2, bottleneck=True, conv1_stride=True), (2, 64, 14, 14)),
+        "preresunit_basic": (lambda: PreResUnit(32, 32, stride=1, bottleneck=False, conv1_stride=False), (2, 32, 8, 8)),
+    }
+    ctor, shape = table[stem]
+    return seeded_init(ctor().eval(), seed=7, randomize_bn=True), seeded_input(shape, seed=99)
+
+
+BLOCKS = ["convblock_3x3_prelu", "convblock_1x1_prelu1", "convblock_3x3_leaky", "dwconv3x3_leaky", "preconv_3x3_preact",
+          "preconv_1x1_s2_bias", "preresunit_bottleneck_s2", "preresunit_basic"]
+NETS = [("preresnet18_bs2", "preresnet18"), ("preresnet50_bs2", "preresnet50"), ("darknet53_bs2", "darknet53")]
+
+
+def _net(name, randomize_bn=True):
+    _ref()
+    from pytorchcv.model_provider import get_model as ref_get_model
+    return seeded_init(ref_get_model(name, pretrained=False).eval(), seed=0, randomize_bn=randomize_bn)
+
+
+# ---- CPU: the oracle restatements against the reference's golden vectors, the lowerings as dry runs --------------------
+@pytest.mark.parametrize("stem", BLOCKS)
+def test_oracle_matches_golden_blocks(stem):
+    blk, x = _block(stem)
+    got = _tuple(oracle_forward(blk, x))
+    gold = np.load(os.path.join(GOLDEN, "block_" + stem + ".npz"))
+    assert len(got) == len(gold.files)
+    for i, g in enumerate(got):
+        assert _rel(g, torch.from_numpy(gold[f"out{i}"])) <= 1e-5, (stem, i)
+
+
+@pytest.mark.parametrize("stem,name", NETS)
+def test_oracle_matches_golden_nets(stem, name):
+    net = _net(name)
+    got = oracle_forward(net, seeded_input((2, 3, 224, 224), seed=1234))
+    gold = np.load(os.path.join(GOLDEN, stem + ".npz"))
+    assert _rel(got, torch.from_numpy(gold["out0"])) <= 1e-4
+    assert int(gold["n_params"]) == sum(p.numel() for p in net.parameters())
+
+
+@pytest.mark.parametrize("name,n_ops", [("preresnet18", 32), ("preresnet50", 73), ("darknet53", 77)])
+def test_reference_modules_lower(name, n_ops):
+    """Dry run of the lowering on the reference's module tree (no GPU): the op count shows what was fused.
+    preresnet18: stem conv(+BN+ReLU) with the fused pool, per unit one pre-activation pass + 2 convs (+ projection), the
+    final BN -> ReLU pass, pool, fc; darknet53: 52 convs with LeakyReLU epilogues + 23 residual adds + pool + fc."""
+    from pytorchcv_b200 import plan as PL
+    from pytorchcv_b200._lib import BF16
+    net = _net(name)
+    b = PL.Builder(BF16, torch.device("cpu"))
+    out = PL.lower(b, net, b.new(2, 224, 224, 8))
+    assert (out.N, out.C, out.flat) == (2, 1000, True)
+    assert len(b.ops) == n_ops, len(b.ops)
+
+
+def test_unknown_activation_still_raises():
+    from pytorchcv_b200 import plan as PL
+    with pytest.raises(NotImplementedError):
+        PL.act_code(nn.Softplus())
+
+
+# ---- GPU: the CUDA path against the oracle and the golden vectors --------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("tier,tol", [("fp32", 1e-4), ("bf16", 2e-2), ("fp16", 4e-3)])
+@pytest.mark.parametrize("stem", BLOCKS)
+def test_blocks_gpu(stem, tier, tol):
+    blk, x = _block(stem)
+    want = _tuple(oracle_forward(blk, x))
+    got = _tuple(P.accelerate(copy.deepcopy(blk).cuda(), dtype=tier, graph=False)(x.cuda()))
+    gold = np.load(os.path.join(GOLDEN, "block_" + stem + ".npz"))
+    assert len(got) == len(want)
+    for i, (g, w) in enumerate(zip(got, want)):
+        g = g.float().cpu()
+        assert g.shape == w.shape and torch.isfinite(g).all()
+        assert _rel(g, w) <= tol, (stem, tier, i, _rel(g, w))
+        assert _rel(g, torch.from_numpy(gold[f"out{i}"])) <= tol, (stem, tier, i)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stem,name", NETS)
+def test_nets_fp32_tier_gpu(stem, name):
+    """fp32 tier with randomised BN statistics: <= 1e-4 of the oracle and of the reference's golden vector, same top-1."""
+    net = _net(name)
+    x = seeded_input((2, 3, 224, 224), seed=1234)
+    want = oracle_forward(net, x)
+    got = P.accelerate(copy.deepcopy(net).cuda(), dtype="fp32")(x.cuda()).cpu()
+    gold = torch.from_numpy(np.load(os.path.join(GOLDEN, stem + ".npz"))["out0"])
+    assert _rel(got, want) <= 1e-4, _rel(got, want)
+    assert _rel(got, gold) <= 1e-4
+    assert torch.equal(got.argmax(1), want.argmax(1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tier", ["bf16", "fp16"])
+@pytest.mark.parametrize("name", ["preresnet18", "preresnet50", "darknet53"])
+def test_nets_16bit_tiers_gpu(name, tier):
+    """16-bit tiers with the reference's init statistics (the fp16 tier's contract): <= 2e-2, same top-1."""
+    if (name, tier) == ("darknet53", "fp16"):
+        pytest.skip("DarkNet-53 at this init reaches |x| = 1.5e5 (23 un-normalised residual adds): beyond IEEE half, bf16 tier only")
+    net = _net(name, randomize_bn=False)
+    x = seeded_input((4, 3, 224, 224), seed=1234)
+    want = oracle_forward(net, x)
+    fast = P.accelerate(copy.deepcopy(net).cuda(), dtype=tier)
+    got = fast(x.cuda()).cpu()
+    assert torch.isfinite(got).all()
+    assert _rel(got, want) <= 2e-2, (name, tier, _rel(got, want))
+    assert torch.equal(got.argmax(1), want.argmax(1))
+    names = [r[0] for r in fast.compiled(x.cuda()).profile()]
+    if name == "darknet53":   # LeakyReLU rides on the conv epilogues: no stand-alone activation pass in the plan
+        assert not any(n.startswith("channel_affine_act") for n in names), names
+    else:                     # one pre-activation pass per unit + the network's last BN -> ReLU, the rest folded into convs
+        n_units = sum(type(m).__name__ == "PreResUnit" for m in net.modules())
+        assert sum(n.startswith("channel_affine_act") for n in names) == n_units + 1, names
