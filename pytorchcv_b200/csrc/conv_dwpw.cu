@@ -12,6 +12,10 @@
 // warps add bias (+ the unit's identity), clamp and store.  Depthwise compute of block c+1 overlaps the MMA of block c
 // (two A buffers) and the epilogue of tile t overlaps tile t+1 (two TMEM accumulators).
 //
+// A TAIL channel block with <= 32 (<= 16) valid channels runs as a 32- (16-) channel block: the stencil warps re-map their
+// lanes onto fewer channels and more columns (dp_stencil<S, 2 / 1>) and the MMA issues 2 (1) K = 16 steps, so C = 96 / 144 pay
+// for 96 / 144 channels of stencil work instead of 128 / 192 (MobileNetV2 bs256: 146.7 k -> 148.9 k img/s) and C = 32 fuses.
+//
 // Saved per block: one write + one read of the depthwise tensor (MobileNetV2 bs256: 2.4 GB of the step's 7.3 GB) and one
 // kernel launch.  Domain: 3x3 depthwise, stride 1 or 2, pad 1, clamp-family activations, Cout <= 256, maps >= 14 wide.
 #include "igemm_common.cuh"
@@ -76,6 +80,68 @@ __device__ __forceinline__ void dp_sts32(uint32_t addr, uint32_t a) {
 }
 __device__ __forceinline__ uint32_t dp_hclamp2(uint32_t v, uint32_t lo, uint32_t hi) {
   return hmin2_e16(hmax2_e16(v, lo), hi);
+}
+
+// The depthwise stencil of one (tile, 64-channel block) for the NQ adjacent output columns row0 .. row0 + NQ - 1 of the
+// tile that this thread owns, channels 2 cp and 2 cp + 1 of the block: walks down the IH input rows with the next row's loads in
+// flight, 3 S + 3 ... (NQ - 1) S + 3 input columns per row, NQ x NACC independent FFMA2 chains, and writes the activated 16-bit
+// results into rows (ho * 16 + row0 + q) of the A operand (16-byte chunks XOR-swizzled by row & 7, independent of ho).
+template <int S, int NQ>
+__device__ __forceinline__ void dp_stencil(const uint32_t stage_u32, const uint32_t abase, const int row0, const int cp,
+                                           const float2 (&wr)[9], const float2 b2, const bool dw_relu, const uint32_t dw_hi2) {
+  constexpr int IH = (DP_TH - 1) * S + 3, IW = (DP_TW - 1) * S + 3;
+  constexpr int NACC = (3 + S - 1) / S;
+  constexpr int NJ = (NQ - 1) * S + 3;
+  const uint32_t sbase = stage_u32 + (row0 * S * 64 + cp * 2) * 2;
+  uint32_t a_off[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const uint32_t r = static_cast<uint32_t>(row0 + q);
+    a_off[q] = r * 128 + (((static_cast<uint32_t>(cp) >> 2) ^ (r & 7u)) << 4) + (static_cast<uint32_t>(cp) & 3u) * 4;
+  }
+  float2 acc[NACC][NQ];
+  uint32_t raw[2][NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) raw[0][j] = dp_lds32(sbase + j * 128);
+#pragma unroll
+  for (int ir = 0; ir < IH; ++ir) {
+    if (ir + 1 < IH) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) raw[(ir + 1) & 1][j] = dp_lds32(sbase + ((ir + 1) * IW + j) * 128);
+    }
+    float2 xv[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) xv[j] = make_float2(e16lo(raw[ir & 1][j]), e16hi(raw[ir & 1][j]));
+#pragma unroll
+    for (int fr = 0; fr < 3; ++fr) {
+      if ((ir - fr) < 0 || (ir - fr) % S != 0 || (ir - fr) / S >= DP_TH) continue;   // compile-time after unrolling
+      const int ho = (ir - fr) / S;
+      const int a = ho % NACC;
+      if (fr == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) acc[a][q] = b2;
+      }
+#pragma unroll
+      for (int fs = 0; fs < 3; ++fs) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) dp_ffma2(acc[a][q], xv[q * S + fs], wr[fr * 3 + fs]);
+      }
+      if (fr == 2) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const uint32_t o = dw_relu ? pack_relu_e16x2(acc[a][q].x, acc[a][q].y) : pack_e16x2(acc[a][q].x, acc[a][q].y);
+          dp_sts32(abase + ho * (DP_TW * 128) + a_off[q], hmin2_e16(o, dw_hi2));
+        }
+      }
+    }
+  }
+}
+
+// K = 16 MMA steps a channel block needs: a TAIL block with <= 32 (<= 16) valid channels is computed and multiplied as a
+// 32- (16-) channel block - the stencil warps re-map their lanes onto fewer channels and more columns (dp_stencil<S, 2 / 1>).
+__host__ __device__ __forceinline__ int dp_ksteps(int C, int cb) {
+  const int cvalid = C - cb * BLOCK_K;
+  return cvalid > 32 ? 4 : (cvalid > 16 ? 2 : 1);
 }
 
 template <int S>
@@ -193,10 +259,12 @@ dwpw_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CU
         tc_fence_after();
         const uint32_t a_lo = a_lo0 + ab * (BLOCK_M * 128 >> 4);
         const uint32_t b_lo = smem_desc_lo(smem_u32(p.b_res ? sB + cb * p.b_bytes : sStage + st * p.stage_bytes + p.halo_bytes));
+        const int ks = dp_ksteps(p.C, cb);
         if (elect_one()) {
           if (!(p.dbg & 8))
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) umma_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, p.idesc, (cb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            if (k < ks) umma_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, p.idesc, (cb | k) != 0 ? 1u : 0u);
           umma_commit(&a_empty[ab]);
           if (!p.b_res) umma_commit(&empty[st]);
         }
@@ -215,21 +283,17 @@ dwpw_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CU
     // shared-memory access of a warp is one contiguous 128-byte line.
     const int team = (warp - 8) >> 2;
     const int quad = (warp - 8) & 3;     // output columns 4 quad .. 4 quad + 3 of the tile
-    const int cp = lane;                 // channels 2 cp, 2 cp + 1 of the 64-channel block
-    constexpr int NQ = 4, NJ = (NQ - 1) * S + 3;
     const uint32_t dw_hi2 = pack_e16x2(p.dw_hi, p.dw_hi);
     const bool dw_relu = p.dw_lo == 0.f;
-    const uint32_t in_off = (quad * NQ * S * 64 + cp * 2) * 2;
-    uint32_t a_off[NQ];                  // byte offset of (row 4 quad + q, this thread's channel pair) inside an A buffer
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const uint32_t r = static_cast<uint32_t>(quad * NQ + q);
-      a_off[q] = r * 128 + (((static_cast<uint32_t>(cp) >> 2) ^ (r & 7u)) << 4) + (static_cast<uint32_t>(cp) & 3u) * 4;
-    }
     const int total_g = my_tiles * p.ncb;
     float2 wr[9], b2;
     for (int g = team; g < total_g; g += 2) {
       const int st = g % p.stages, ab = g & ((1 << p.na_shift) - 1), cb = g % p.ncb;
+      // lane -> (channel pair, column group): a full block gives a thread 2 channels of the warp's 4 columns; a tail block with
+      // <= 32 (<= 16) valid channels gives it 2 (1) of those columns, so that no lane works on padding channels
+      const int ks = dp_ksteps(p.C, cb);
+      const int cp = ks == 4 ? lane : (ks == 2 ? (lane & 15) : (lane & 7));     // channels 2 cp, 2 cp + 1 of the block
+      const int row0 = quad * 4 + (ks == 4 ? 0 : (ks == 2 ? (lane >> 4) * 2 : (lane >> 3)));
       // this block's depthwise weights: 9 taps x 2 channels (zero beyond C: the TMA zero-fills those channels too)
       if (g == team || p.ncb > 1) {
         const float2* wsm = reinterpret_cast<const float2*>(sW + cb * DP_WROW) + cp;
@@ -244,46 +308,12 @@ dwpw_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CU
       if (tl) tq1 = clock64();
       mbar_wait(&a_empty[ab], ((g >> p.na_shift) & 1) ^ 1);
       if (tl) tq2 = clock64();
-      const uint32_t sbase = smem_u32(sStage + st * p.stage_bytes) + in_off;
+      const uint32_t stage_u32 = smem_u32(sStage + st * p.stage_bytes);
       const uint32_t abase = smem_u32(sA) + ab * (BLOCK_M * 128);
-      float2 acc[NACC][NQ];
-      uint32_t raw[2][NJ];
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) raw[0][j] = dp_lds32(sbase + j * 128);
-      if (!(p.dbg & 1))
-#pragma unroll
-      for (int ir = 0; ir < IH; ++ir) {
-        if (ir + 1 < IH) {
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) raw[(ir + 1) & 1][j] = dp_lds32(sbase + ((ir + 1) * IW + j) * 128);
-        }
-        float2 xv[NJ];
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) xv[j] = make_float2(e16lo(raw[ir & 1][j]), e16hi(raw[ir & 1][j]));
-#pragma unroll
-        for (int fr = 0; fr < 3; ++fr) {
-          if ((ir - fr) < 0 || (ir - fr) % S != 0 || (ir - fr) / S >= DP_TH) continue;   // compile-time after unrolling
-          const int ho = (ir - fr) / S;
-          const int a = ho % NACC;
-          if (fr == 0) {
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) acc[a][q] = b2;
-          }
-#pragma unroll
-          for (int fs = 0; fs < 3; ++fs) {
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) dp_ffma2(acc[a][q], xv[q * S + fs], wr[fr * 3 + fs]);
-          }
-          if (fr == 2) {
-            // activated 16-bit results -> rows (ho * 16 + 4 quad + q) of the A operand (16-byte chunks XOR-swizzled by
-            // row & 7, which does not depend on ho)
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-              const uint32_t o = dw_relu ? pack_relu_e16x2(acc[a][q].x, acc[a][q].y) : pack_e16x2(acc[a][q].x, acc[a][q].y);
-              dp_sts32(abase + ho * (DP_TW * 128) + a_off[q], hmin2_e16(o, dw_hi2));
-            }
-          }
-        }
+      if (!(p.dbg & 1)) {
+        if (ks == 4) dp_stencil<S, 4>(stage_u32, abase, row0, cp, wr, b2, dw_relu, dw_hi2);
+        else if (ks == 2) dp_stencil<S, 2>(stage_u32, abase, row0, cp, wr, b2, dw_relu, dw_hi2);
+        else dp_stencil<S, 1>(stage_u32, abase, row0, cp, wr, b2, dw_relu, dw_hi2);
       }
       if (tl) tq3 = clock64();
       fence_proxy_async_smem();   // the A block is read by tcgen05.mma (async proxy)
@@ -424,8 +454,9 @@ static bool dwpw_geom(const pcv_conv_desc& dw, const pcv_conv_desc& pw, DwPwGeom
   g->nmma = round_up(pw.Cout, 16);
   g->halo_bytes = round_up(g->IH * g->IW * 128, 1024);
   g->b_bytes = round_up(g->nmma * 128, 1024);
-  // a 64-channel block that is mostly padding wastes the stencil's arithmetic (C = 32: half of it)
-  if (g->ncb * BLOCK_K * 2 > dw.Cin * 3) return false;
+  // a channel block that is mostly padding wastes the stencil's arithmetic; tail blocks run as 32- / 16-channel blocks
+  // (dp_ksteps), so what counts is the padding that is left after that (C = 24: 32 channels of work for 24)
+  if (((g->ncb - 1) * BLOCK_K + dp_ksteps(dw.Cin, g->ncb - 1) * 16) * 2 > dw.Cin * 3) return false;
   for (g->na_shift = 2; g->na_shift >= 1; --g->na_shift) {
     const int fixed = 1024 + (BLOCK_M * 128 << g->na_shift) + g->ncb * DP_WROW * 4 + 512;
     // the pointwise weights either stay resident (a stage is a bare halo, released by the stencil warps alone) or ride

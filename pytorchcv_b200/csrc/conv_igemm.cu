@@ -637,6 +637,7 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
       const long long tiles = static_cast<long long>(pair_m) * ceil_div(units, ns);
       // (measured: 3x3 512->512 @7x7 0.065 -> 0.059 ms; short-K 1x1 layers are overhead-bound and gain nothing, so the
       // wave term only applies to k x k layers)
+      // (the same term on the long-K 1x1 reductions of stage 4, 2048->512 @7x7 as 3 x 192-wide tiles: 40.3 -> 40.0 us, nothing)
       const double waves = taps > 1 ? static_cast<double>((tiles + pairs_avail - 1) / pairs_avail)
                                     : static_cast<double>(tiles) / pairs_avail;
       // per-tile cost ~ cycles of one K = 16 MMA step at this width (measured, shared-memory bound: N = 256 170 clk,
