@@ -149,6 +149,21 @@ PCV_API int pcv_dw_pw_fused(pcv_plan* plan, const pcv_conv_desc* dw, const pcv_c
                     const void* w_dw_packed, const float* bias_dw, const void* w_pw_packed, const float* bias_pw,
                     const void* residual, void* y, pcv_stream stream);
 
+/* The whole inverted-residual block - LinearBottleneck.forward (mobilenetv2.py:62-71): conv1 (1x1 expansion ConvBlock) -> conv2
+ * (depthwise 3x3 ConvBlock) -> conv3 (linear 1x1 ConvBlock) [+ x]; the same triple in FBNetUnit / SPNASUnit / ProxylessBlock
+ * (fbnet.py:77-87, spnasnet.py:72-82, proxylessnas.py:64-70) - in ONE kernel:
+ *   y = act_pw(W_pw * act_dw(dw3x3(act_ex(W_ex * x))) [+ residual]).
+ * Neither the expanded tensor nor the depthwise tensor exists in HBM: the expansion runs on the tensor cores over the input halo
+ * of each output tile, its result is staged in shared memory for the depthwise stencil, whose result is the A operand of the
+ * projection.  ex: the 1x1 stride-1 expansion (Cin <= 64, act in {none, ReLU, ReLU6}); dw / pw as for pcv_dw_pw_fused (Cout <=
+ * 128 at stride 1, <= 64 at stride 2); all three packed with pcv_pack_conv_weights as usual.  pcv_exp_dw_pw_fusable returns 1
+ * inside the kernel's domain, else 0 and the caller records the expansion and pcv_dw_pw_fused (or three convolutions). */
+PCV_API int pcv_exp_dw_pw_fusable(const pcv_conv_desc* ex, const pcv_conv_desc* dw, const pcv_conv_desc* pw, int dtype);
+PCV_API int pcv_exp_dw_pw_fused(pcv_plan* plan, const pcv_conv_desc* ex, const pcv_conv_desc* dw, const pcv_conv_desc* pw,
+                                int dtype, const void* x, const void* w_ex_packed, const float* bias_ex,
+                                const void* w_dw_packed, const float* bias_dw, const void* w_pw_packed, const float* bias_pw,
+                                const void* residual, void* y, pcv_stream stream);
+
 /* nn.ZeroPad2d((left, right, top, bottom)): the explicit asymmetric padding of a ConvBlock built with a 4-tuple `padding`
  * (conv.py:245-249,279-280) and of EfficientNet's tf_mode forwards (F.pad(x, calc_tf_padding(...)), efficientnet.py:27-55).
  * y is [N, H + top + bottom, W + left + right, C]; the convolution that follows runs with pad = 0. */

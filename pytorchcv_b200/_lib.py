@@ -52,6 +52,9 @@ SIGNATURES = {
     "pcv_bottleneck_tail": (_I, [_P, C.POINTER(ConvDesc), C.POINTER(ConvDesc), _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pcv_dw_pw_fusable": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvDesc), _I]),
     "pcv_dw_pw_fused": (_I, [_P, C.POINTER(ConvDesc), C.POINTER(ConvDesc), _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pcv_exp_dw_pw_fusable": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvDesc), C.POINTER(ConvDesc), _I]),
+    "pcv_exp_dw_pw_fused": (_I, [_P, C.POINTER(ConvDesc), C.POINTER(ConvDesc), C.POINTER(ConvDesc), _I, _P, _P, _P, _P, _P, _P,
+                                _P, _P, _P, _P]),
     "pcv_zero_pad2d": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "pcv_maxpool2d": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P]),
     "pcv_global_avgpool": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _I, _P]),

@@ -238,6 +238,33 @@ int pcv_dw_pw_fused(pcv_plan* plan, const pcv_conv_desc* dw, const pcv_conv_desc
   return submit(plan, op, static_cast<cudaStream_t>(stream));
 }
 
+int pcv_exp_dw_pw_fusable(const pcv_conv_desc* ex, const pcv_conv_desc* dw, const pcv_conv_desc* pw, int dtype) {
+  if (!ex || !dw || !pw || !is16(dtype)) return 0;
+  if (validate_conv(ex, dtype) != PCV_OK || validate_conv(dw, dtype) != PCV_OK || validate_conv(pw, dtype) != PCV_OK) return 0;
+  std::string why;
+  // the kernel reads the expansion / projection weights in the tcgen05 route's packed layout, the depthwise ones in dwconv's
+  if (conv_route(*ex, dtype, &why) != ROUTE_IGEMM || conv_route(*pw, dtype, &why) != ROUTE_IGEMM ||
+      conv_route(*dw, dtype, &why) != ROUTE_DW)
+    return 0;
+  return bf::xdwpw_ok(*ex, *dw, *pw);
+}
+
+int pcv_exp_dw_pw_fused(pcv_plan* plan, const pcv_conv_desc* ex, const pcv_conv_desc* dw, const pcv_conv_desc* pw, int dtype,
+                        const void* x, const void* w_ex_packed, const float* bias_ex, const void* w_dw_packed,
+                        const float* bias_dw, const void* w_pw_packed, const float* bias_pw, const void* residual, void* y,
+                        pcv_stream stream) {
+  if (int rc = validate_conv(ex, dtype)) return rc;
+  if (int rc = validate_conv(dw, dtype)) return rc;
+  if (int rc = validate_conv(pw, dtype)) return rc;
+  PCV_REQUIRE(is16(dtype), "the fused expansion -> depthwise -> pointwise kernel exists in the 16-bit tiers only");
+  Op* op = nullptr;
+  const int rc = (dtype == PCV_F16 ? hf::xdwpw_make : bf::xdwpw_make)(
+      *ex, *dw, *pw, x, w_ex_packed, bias_ex, reinterpret_cast<const float*>(w_dw_packed), bias_dw, w_pw_packed, bias_pw,
+      residual, y, &op);
+  if (rc) return rc;
+  return submit(plan, op, static_cast<cudaStream_t>(stream));
+}
+
 int pcv_plan_create(pcv_plan** plan) {
   PCV_REQUIRE(plan != nullptr, "NULL plan out-pointer");
   *plan = new pcv_plan();

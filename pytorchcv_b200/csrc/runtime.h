@@ -137,6 +137,11 @@ EncodeIm2colFn encode_im2col_fn();
   int dwpw_ok(const pcv_conv_desc& dw, const pcv_conv_desc& pw);                                                         \
   int dwpw_make(const pcv_conv_desc& dw, const pcv_conv_desc& pw, const void* x, const float* w_dw, const float* b_dw,  \
                 const void* w_pw, const float* b_pw, const void* res, void* y, Op** out);                                \
+  /* conv_xdwpw.cu : 1x1 expansion -> depthwise 3x3 -> pointwise 1x1 in one kernel (neither wide tensor touches HBM) */           \
+  int xdwpw_ok(const pcv_conv_desc& ex, const pcv_conv_desc& dw, const pcv_conv_desc& pw);                                       \
+  int xdwpw_make(const pcv_conv_desc& ex, const pcv_conv_desc& dw, const pcv_conv_desc& pw, const void* x, const void* w_ex,    \
+                 const float* b_ex, const float* w_dw, const float* b_dw, const void* w_pw, const float* b_pw,                   \
+                 const void* res, void* y, Op** out);                                                                            \
   /* conv_igemm3s.cu : can the s2d stem take the fused max pool (pcv_stem_s2d_pool_ok) */                                \
   int stem_pool_ok(int C, int H, int W, int k, int Cout);                                                                \
   }

@@ -46,6 +46,31 @@ def set_fuse_dwpw(enabled: bool) -> None:
     _FUSE_DWPW[0] = bool(enabled)
 
 
+# 1x1 expansion -> depthwise -> pointwise triples as one fused kernel (pcv_exp_dw_pw_fused); PCV_FUSE_XDWPW=0 records the
+# expansion and the dw -> pw pair
+_FUSE_XDWPW = [os.environ.get("PCV_FUSE_XDWPW", "1") != "0"]
+# Measured (MobileNetV2 bs256, fp16): the triple kernel is bound by its CUDA-core work (stencil + conversion of the expanded halo),
+# not by HBM, so it pays where the expanded tensor is largest relative to that work - stride 2, whose two-kernel plan moves 4
+# expanded pixels per output pixel (16->96->24 @112: 375 -> 327 us).  Stride-1 triples are at parity with expansion +
+# pcv_dw_pw_fused and are recorded only on request (PCV_XDWPW_S1=1 / set_fuse_xdwpw(True, stride1=True)).
+_XDWPW_S1 = [os.environ.get("PCV_XDWPW_S1", "0") == "1"]
+
+
+def set_fuse_xdwpw(enabled: bool, stride1: bool | None = None) -> None:
+    _FUSE_XDWPW[0] = bool(enabled)
+    if stride1 is not None:
+        _XDWPW_S1[0] = bool(stride1)
+
+
+def _exp_dw_pw(b, expb, dwb, pwb, x, residual=None, post_act=None):
+    """expansion ConvBlock -> dw ConvBlock -> pw ConvBlock [+ residual]: one kernel where the triple is in its domain, else the
+    expansion followed by the dw -> pw pair."""
+    fused = b.exp_dw_pw(x, expb, dwb, pwb, residual, post_act)
+    if fused is not None:
+        return fused
+    return _dw_then_pw(b, dwb, pwb, lower(b, expb, x), residual=residual, post_act=post_act)
+
+
 def _dw_then_pw(b, dwb, pwb, x, residual=None, post_act=None, **kw):
     """dw ConvBlock -> pw ConvBlock [+ residual, post_act]: the fused kernel where it applies, else the two convolutions."""
     if not kw:
@@ -470,6 +495,71 @@ class Builder:
         self.ops.append(emit)
         return out
 
+    def exp_dw_pw(self, x: TRef, expb: nn.Module, dwb: nn.Module, pwb: nn.Module, residual: TRef | None,
+                  post_act: int | None) -> TRef | None:
+        """1x1 expansion ConvBlock -> depthwise ConvBlock -> pointwise ConvBlock (+ residual) as ONE fused kernel
+        (include/pcv_b200.h pcv_exp_dw_pw_fused), or None when the triple is outside that kernel's domain."""
+        if not _FUSE_XDWPW[0] or not _FUSE_DWPW[0] or not _is16(self.dtype):
+            return None
+        for cb in (expb, dwb, pwb):
+            if (type(cb).__name__ != "ConvBlock" or getattr(cb, "use_pad", False) or not cb.normalize
+                    or cb.conv.padding_mode != "zeros" or isinstance(cb.conv.padding, str) or cb.conv.bias is not None):
+                return None
+        ce, cd, cp = expb.conv, dwb.conv, pwb.conv
+        if ce.in_channels != x.C or ce.groups != 1 or cd.in_channels != ce.out_channels:
+            return None
+        if cd.groups != cd.in_channels or cd.out_channels != cd.in_channels or cp.in_channels != cd.out_channels or cp.groups != 1:
+            return None
+        try:
+            geo = [(c.kernel_size, _one(c.stride), _one(c.padding), _one(c.dilation)) for c in (ce, cd, cp)]
+            acts = [act_code(cb.activ) if cb.activate else ACT_NONE for cb in (expb, dwb, pwb)]
+        except NotImplementedError:
+            return None
+        act_pw = acts[2]
+        if residual is not None:
+            if act_pw != ACT_NONE:
+                return None
+            act_pw = ACT_NONE if post_act is None else post_act
+        elif post_act not in (None, ACT_NONE):
+            return None
+        (ke, se, pe, de), (kd, sd, pd, dd), (kp, sp, pp, dp) = geo
+        if sd == 1 and not _XDWPW_S1[0]:
+            return None
+        Ho = (x.H + 2 * pd - dd * (kd[0] - 1) - 1) // sd + 1
+        Wo = (x.W + 2 * pd - dd * (kd[1] - 1) - 1) // sd + 1
+        if Ho <= 0 or Wo <= 0:
+            return None
+        if residual is not None and (residual.N, residual.H, residual.W, residual.C) != (x.N, Ho, Wo, cp.out_channels):
+            return None
+        cm = ce.out_channels
+        d_ex = ConvDesc(N=x.N, H=x.H, W=x.W, Cin=x.C, Cout=cm, kh=ke[0], kw=ke[1], stride=se, pad=pe, dil=de, groups=1,
+                        act=acts[0], in_pitch=x.pitch, out_pitch=cm, res_pitch=0, flags=0)
+        d_dw = ConvDesc(N=x.N, H=x.H, W=x.W, Cin=cm, Cout=cm, kh=kd[0], kw=kd[1], stride=sd, pad=pd, dil=dd, groups=cm,
+                        act=acts[1], in_pitch=cm, out_pitch=cm, res_pitch=0, flags=0)
+        d_pw = ConvDesc(N=x.N, H=Ho, W=Wo, Cin=cm, Cout=cp.out_channels, kh=kp[0], kw=kp[1], stride=sp, pad=pp, dil=dp,
+                        groups=1, act=act_pw, in_pitch=cm, out_pitch=cp.out_channels,
+                        res_pitch=residual.pitch if residual is not None else 0, flags=0)
+        if not _lib.load().pcv_exp_dw_pw_fusable(C.byref(d_ex), C.byref(d_dw), C.byref(d_pw), self.dtype):
+            return None
+        for cb in (expb, dwb, pwb):
+            _check_bn(cb.bn)
+        out = self.new(x.N, Ho, Wo, cp.out_channels)
+        offs = []
+        for d, cb in ((d_ex, expb), (d_dw, dwb), (d_pw, pwb)):
+            wb, bb = C.c_size_t(), C.c_size_t()
+            _lib.call("pcv_conv_packed_bytes", C.byref(d), self.dtype, C.byref(wb), C.byref(bb))
+            w_off, b_off = self._wblob(wb.value), self._wblob(bb.value)
+            self.weight_jobs.append(("conv", (d, cb.conv, cb.bn, 0, w_off, b_off)))
+            offs += [w_off, b_off]
+        self._use(x, residual, out)
+        dtype = self.dtype
+
+        def emit(plan, ptr, wptr):
+            _lib.call("pcv_exp_dw_pw_fused", plan, C.byref(d_ex), C.byref(d_dw), C.byref(d_pw), dtype, ptr(x),
+                      *(wptr(o) for o in offs), ptr(residual) if residual is not None else None, ptr(out), None)
+        self.ops.append(emit)
+        return out
+
     def linear(self, x: TRef, fc: nn.Linear, out_f32: bool = True) -> TRef:
         """nn.Linear on pooled features == 1x1 conv on a 1x1 map (resnet.py:320-322,335-336)."""
         if (x.H, x.W) != (1, 1):
@@ -843,8 +933,9 @@ def _lower_seinit(b, m, x, **kw):
 @lowers("LinearBottleneck")
 def _lower_linear_bottleneck(b, m, x, **kw):
     """LinearBottleneck.forward (mobilenetv2.py:62-71): [1x1 expand] -> dw3x3 -> 1x1 linear (+x), no final act."""
-    y = lower(b, m.conv1, x) if m.use_exp_conv else x
-    return _dw_then_pw(b, m.conv2, m.conv3, y, residual=x if m.residual else None, post_act=None)
+    if m.use_exp_conv:
+        return _exp_dw_pw(b, m.conv1, m.conv2, m.conv3, x, residual=x if m.residual else None, post_act=None)
+    return _dw_then_pw(b, m.conv2, m.conv3, x, residual=x if m.residual else None, post_act=None)
 
 
 # ---- pre-activation family (conv.py:652-732, preresnet.py) ------------------------------------------------------------
@@ -990,15 +1081,17 @@ def _lower_proxyless_unit(b, m, x, **kw):
     if not m.residual:
         return x
     blk = m.body
-    y = lower(b, blk.bc_conv, x) if blk.use_bc else x
-    return _dw_then_pw(b, blk.dw_conv, blk.pw_conv, y, residual=x if m.shortcut else None, post_act=None)
+    if blk.use_bc:
+        return _exp_dw_pw(b, blk.bc_conv, blk.dw_conv, blk.pw_conv, x, residual=x if m.shortcut else None, post_act=None)
+    return _dw_then_pw(b, blk.dw_conv, blk.pw_conv, x, residual=x if m.shortcut else None, post_act=None)
 
 
 @lowers("FBNetUnit", "SPNASUnit")
 def _lower_fbnet_unit(b, m, x, **kw):
     """FBNetUnit.forward (fbnet.py:77-87) == SPNASUnit.forward (spnasnet.py:72-82): [1x1 expand] -> dw -> 1x1 (+x)."""
-    y = lower(b, m.exp_conv, x) if m.use_exp_conv else x
-    return _dw_then_pw(b, m.conv1, m.conv2, y, residual=x if m.residual else None, post_act=None)
+    if m.use_exp_conv:
+        return _exp_dw_pw(b, m.exp_conv, m.conv1, m.conv2, x, residual=x if m.residual else None, post_act=None)
+    return _dw_then_pw(b, m.conv1, m.conv2, x, residual=x if m.residual else None, post_act=None)
 
 
 @lowers("MnasInitBlock", "MnasFinalBlock", "FBNetInitBlock", "SPNASInitBlock", "SPNASFinalBlock")

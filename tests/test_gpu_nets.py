@@ -247,6 +247,9 @@ def test_fused_bottleneck_tail(cin, cout, shape, tier, tol):
     ("lb", 32, 64, 2, (2, 28, 28)),      # stride 2 down to 14x14: the smallest tile the kernel takes
     ("lb", 64, 64, 1, (1, 14, 14)),      # C=384, one ragged 8x16 tile column
     ("lb", 32, 32, 1, (2, 19, 37)),      # ragged both ways
+    ("lb", 24, 32, 2, (2, 56, 56)),      # stride 2 with C=144: tail block of 16 channels, 3 expansion M-blocks
+    ("lb", 16, 16, 1, (5, 33, 50)),      # one K step of expansion, odd tile counts over 5 images
+    ("lb", 48, 48, 1, (2, 28, 28)),      # Cin = 48 (3 K steps), C=288: tail block of 32 channels
     ("lb0", 64, 16, 1, (2, 56, 56)),     # no expansion conv (the shape of MobileNetV2's first unit), Cout=16
     ("dws", 64, 128, 1, (2, 56, 56)),    # MobileNet-v1 DwsConvBlock: ReLU after both
     ("dws", 128, 128, 2, (2, 56, 56)),
@@ -254,8 +257,9 @@ def test_fused_bottleneck_tail(cin, cout, shape, tier, tol):
     ("dws", 48, 72, 1, (1, 30, 23)),     # C not a multiple of 64, Cout not a multiple of 16
 ])
 def test_fused_dw_pw(kind, cin, cout, stride, shape, tier, tol):
-    """depthwise 3x3 -> pointwise 1x1 (+ residual) as ONE kernel (pcv_dw_pw_fused) against the oracle and against the
-    two-convolution plan: mobilenetv2.py LinearBottleneck (conv2 -> conv3 [+ x]) and common/conv.py DwsConvBlock."""
+    """depthwise 3x3 -> pointwise 1x1 (+ residual) as ONE kernel (pcv_dw_pw_fused) and, where the unit has an expansion conv,
+    expansion -> depthwise -> pointwise as ONE kernel (pcv_exp_dw_pw_fused), against the oracle and against the plan of
+    separate convolutions: mobilenetv2.py LinearBottleneck (conv1 -> conv2 -> conv3 [+ x]) and common/conv.py DwsConvBlock."""
     from pytorchcv_b200 import nets as M, blocks as BK, plan as PL
     n, h, w = shape
     if kind == "dws":
@@ -266,20 +270,32 @@ def test_fused_dw_pw(kind, cin, cout, stride, shape, tier, tol):
     unit = seeded_init(unit.eval(), seed=5, randomize_bn=True)
     x = seeded_input((n, cin, h, w), seed=6)
     want = oracle_forward(unit, x)
-    fast = P.accelerate(copy.deepcopy(unit).cuda(), dtype=tier, graph=False)
-    got = fast(x.cuda()).float().cpu()
-    names = [r[0] for r in fast.compiled(x.cuda()).profile()]
+
+    def run(pair, triple):
+        PL.set_fuse_dwpw(pair)
+        PL.set_fuse_xdwpw(triple, stride1=True)   # the default policy records stride-2 triples only (plan.py)
+        try:
+            fast = P.accelerate(copy.deepcopy(unit).cuda(), dtype=tier, graph=False)
+            y = fast(x.cuda()).float().cpu()
+            return y, [r[0] for r in fast.compiled(x.cuda()).profile()]
+        finally:
+            PL.set_fuse_dwpw(True)
+            PL.set_fuse_xdwpw(True, stride1=False)
+
+    plain, _ = run(False, False)
+    got, names = run(True, False)
     assert any(nm.startswith("conv_dwpw fused") for nm in names), names
-    PL.set_fuse_dwpw(False)
-    try:
-        plain = P.accelerate(copy.deepcopy(unit).cuda(), dtype=tier, graph=False)(x.cuda()).float().cpu()
-    finally:
-        PL.set_fuse_dwpw(True)
     assert got.shape == want.shape and torch.isfinite(got).all()
     assert _rel(got, want) <= tol, (_rel(got, want), names)
-    # same operand rounding as the two-kernel plan (the depthwise result is stored in the tier's 16-bit type either
-    # way): only fp32 summation order differs
+    # same operand rounding as the plan of separate convolutions (the depthwise result is stored in the tier's 16-bit type
+    # either way): only fp32 summation order differs
     assert _rel(got, plain) <= tol / 4, (_rel(got, plain), names)
+    if kind == "lb":
+        got3, names3 = run(True, True)
+        assert names3[0].startswith("conv_xdwpw fused") and not any(nm.startswith("conv_tc") for nm in names3), names3
+        assert got3.shape == want.shape and torch.isfinite(got3).all()
+        assert _rel(got3, want) <= tol, (_rel(got3, want), names3)
+        assert _rel(got3, plain) <= tol / 4, (_rel(got3, plain), names3)
 
 
 @pytest.mark.gpu
@@ -296,7 +312,9 @@ def test_fused_dw_pw_whole_net(name):
     want = oracle_forward(net, x)
     fast = P.accelerate(copy.deepcopy(net).cuda(), dtype=tier)
     fused = fast(x.cuda()).cpu()
-    n_fused = sum(r[0].startswith("conv_dwpw fused") for r in fast.compiled(x.cuda()).profile())
+    names = [r[0] for r in fast.compiled(x.cuda()).profile()]
+    # a fused pair replaces two ops, a fused expansion -> dw -> pw triple three
+    n_fused = sum(nm.startswith("conv_dwpw fused") + 2 * nm.startswith("conv_xdwpw fused") for nm in names)
     PL.set_fuse_dwpw(False)
     try:
         base = P.accelerate(copy.deepcopy(net).cuda(), dtype=tier)
