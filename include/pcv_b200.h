@@ -64,8 +64,9 @@ enum pcv_act {
   PCV_ACT_SWISH = 4,    /* Swish       activ.py:16-21   */
   PCV_ACT_HSWISH = 5,   /* HSwish      activ.py:33-47   */
   PCV_ACT_HSIGMOID = 6, /* HSigmoid    activ.py:24-30   */
-  PCV_ACT_LEAKY_RELU = 7 /* nn.LeakyReLU activ.py:101-120: x >= 0 ? x : act_param * x (dense / grouped convs; the
-                            per-channel nn.PReLU of activ.py:84-98 is pcv_channel_affine_act's `slope`) */
+  PCV_ACT_LEAKY_RELU = 7, /* nn.LeakyReLU activ.py:101-120: x >= 0 ? x : act_param * x (dense / grouped convs; the
+                             per-channel nn.PReLU of activ.py:84-98 is pcv_channel_affine_act's `slope`) */
+  PCV_ACT_CLAMP01 = 8     /* GhostHSigmoid ghostnet.py:18-24: clamp(x, 0, 1) - SE gates (pcv_se_excite*) only */
 };
 
 enum pcv_conv_flags {

@@ -47,6 +47,8 @@ def _activation(m: nn.Module, x: torch.Tensor) -> torch.Tensor:
         return x * (x + 3.0).clamp(0.0, 6.0) / 6.0                 # activ.py:46-47
     if name == "HSigmoid":
         return (x + 3.0).clamp(0.0, 6.0) / 6.0                     # activ.py:29-30
+    if name == "GhostHSigmoid":
+        return x.clamp(0.0, 1.0)                                   # ghostnet.py:23-24
     if isinstance(m, nn.PReLU):
         return F.prelu(x, m.weight)                                # activ.py:84-98
     if isinstance(m, nn.LeakyReLU):
@@ -415,6 +417,36 @@ def pre_res_activation(m, x):
     return _activation(m.activ, _batchnorm(m.bn, x))
 
 
+def ghost_conv_block(m, x):
+    """GhostConvBlock.forward (ghostnet.py:57-60)."""
+    x = conv_block(m.main_conv, x)
+    y = conv_block(m.cheap_conv, x)
+    return torch.cat((x, y), dim=1)
+
+
+def ghost_exp_block(m, x):
+    """GhostExpBlock.forward (ghostnet.py:114-121)."""
+    x = ghost_conv_block(m.exp_conv, x)
+    if m.use_dw_conv:
+        x = conv_block(m.dw_conv, x)
+    if m.use_se:
+        x = se_block(m.se, x)
+    return ghost_conv_block(m.pw_conv, x)
+
+
+def ghost_unit(m, x):
+    """GhostUnit.forward (ghostnet.py:167-174)."""
+    identity = dws_conv_block(m.identity_conv, x) if m.resize_identity else x
+    return ghost_exp_block(m.body, x) + identity
+
+
+def ghostnet(m, x):
+    """GhostNet.forward (ghostnet.py:298-302) with GhostClassifier.forward (ghostnet.py:203-206)."""
+    x = oracle_forward(m.features, x)
+    x = _conv2d(m.output.conv2, conv_block(m.output.conv1, x))
+    return x.view(x.size(0), -1)
+
+
 def dark_unit(m, x):
     """DarkUnit.forward (darknet53.py:45-49)."""
     return conv_block(m.conv2, conv_block(m.conv1, x)) + x
@@ -459,6 +491,7 @@ _BY_NAME = {
     "PreConvBlock": pre_conv_block, "PreResBlock": pre_res_body, "PreResBottleneck": pre_res_body, "PreResUnit": pre_res_unit,
     "PreResInitBlock": pre_res_init_block, "PreResActivation": pre_res_activation, "PreResNet": classifier,
     "DarkUnit": dark_unit, "DarkNet53": classifier,
+    "GhostConvBlock": ghost_conv_block, "GhostExpBlock": ghost_exp_block, "GhostUnit": ghost_unit, "GhostNet": ghostnet,
     "Concurrent": concurrent, "MultiOutputSequential": multi_output_sequential,
     "ASPPAvgBranch": aspp_avg_branch, "AtrousSpatialPyramidPooling": aspp, "DeepLabv3": deeplabv3,
 }

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("PCV_B200_LIB") or os.path.join(_HERE, "libpcv_b200.so
 
 BF16, F32, F16 = 0, 1, 2                      # pcv_dtype
 IMG_F32, IMG_BF16, IMG_F16, IMG_U8 = 0, 1, 2, 3  # pcv_image_type
-ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SIGMOID, ACT_SWISH, ACT_HSWISH, ACT_HSIGMOID, ACT_LEAKY_RELU = range(8)
+ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SIGMOID, ACT_SWISH, ACT_HSWISH, ACT_HSIGMOID, ACT_LEAKY_RELU, ACT_CLAMP01 = range(9)
 CONV_OUT_F32, CONV_FORCE_SIMT, CONV_A_IM2COL, CONV_IN_OVERLAP, CONV_POOL3S2, CONV_F32_SPLIT = 1, 2, 4, 8, 16, 32
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = 0, -1, -2, -3, -4

@@ -13,6 +13,7 @@ __device__ __forceinline__ float misc_act(float v, int act) {
     case PCV_ACT_SWISH: return v / (1.f + expf(-v));
     case PCV_ACT_HSWISH: return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) / 6.f;
     case PCV_ACT_HSIGMOID: return fminf(fmaxf(v + 3.f, 0.f), 6.f) / 6.f;
+    case PCV_ACT_CLAMP01: return fminf(fmaxf(v, 0.f), 1.f);
     default: return v;
   }
 }

@@ -21,8 +21,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import (ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SIGMOID, ACT_SWISH, ACT_HSWISH, ACT_HSIGMOID, ACT_LEAKY_RELU, BF16,
-                   F16, F32, ConvDesc)
+from ._lib import (ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SIGMOID, ACT_SWISH, ACT_HSWISH, ACT_HSIGMOID, ACT_LEAKY_RELU, ACT_CLAMP01,
+                   BF16, F16, F32, ConvDesc)
 
 # fp32 tier: dense / grouped convs on the tensor cores as a 3-way bf16 split (PCV_F32_SPLIT=0: the CUDA-core kernel instead)
 _F32_SPLIT = os.environ.get("PCV_F32_SPLIT", "1") != "0"
@@ -138,6 +138,14 @@ class TRef:
     flat: bool = False     # return as [N, C] (the reference's x.view(N, -1))
     tail: Any = None       # network-edge op run per call AFTER the plan, writing a fresh caller-owned tensor:
                            # tail(ptr, out_ptr, stream); such a tensor has no arena storage and cannot feed another op
+    cmap: Any = None       # "virtual channel padding": storage index of each REAL channel when the C storage channels hold
+                           # fewer real ones (a torch.cat of parts whose widths are not multiples of 8, ghostnet.py:57-60: every
+                           # part is padded to 8 so that all slices stay 16-byte aligned).  Padding channels hold exact zeros;
+                           # consumers scatter their weights' input channels accordingly (zero weights on the padding).
+
+    @property
+    def creal(self) -> int:
+        return self.C if self.cmap is None else len(self.cmap)
 
     @property
     def byte_off(self) -> int:
@@ -163,6 +171,8 @@ def act_code(m: nn.Module | None) -> int:
         return ACT_HSWISH
     if name == "HSigmoid" or isinstance(m, nn.Hardsigmoid):
         return ACT_HSIGMOID
+    if name == "GhostHSigmoid":
+        return ACT_CLAMP01               # clamp(x, 0, 1) (ghostnet.py:18-24): SE gates only
     if isinstance(m, nn.LeakyReLU):
         return ACT_LEAKY_RELU            # slope: act_param(m); fused into dense / grouped conv epilogues
     raise NotImplementedError(f"activation {name} is outside the B200 eval path (SURVEY 8a8)")
@@ -308,7 +318,7 @@ class Builder:
     # -- ops ----------------------------------------------------------------------------------------------------
     def conv(self, x: TRef, conv: nn.Conv2d, bn: nn.Module | None = None, act: int = ACT_NONE,
              residual: TRef | None = None, out: TRef | None = None, out_f32: bool = False, flags: int = 0,
-             pad_lrtb: tuple | None = None, act_a: float = 0.0) -> TRef:
+             pad_lrtb: tuple | None = None, act_a: float = 0.0, out_cmap: list | None = None) -> TRef:
         """One fused ConvBlock: conv + folded BN + optional residual + activation.  `pad_lrtb` = (left, right, top, bottom)
         replaces the conv's own padding (ZeroPad2d / tf_mode): symmetric amounts ride on the kernel's padding, asymmetric
         ones are materialised by one zero-pad pass."""
@@ -325,6 +335,9 @@ class Builder:
             else:
                 x = self.pad(x, pl, pr, pt, pb)
         cin, cout, groups = conv.in_channels, conv.out_channels, conv.groups
+        # virtual channel padding (TRef.cmap): the input's / output's real channels sit at given storage positions
+        if x.cmap is not None or out_cmap is not None or (out is not None and out.C != cout):
+            return self._conv_mapped(x, conv, bn, act, act_a, residual, out, out_cmap, k_stride, k_pad, k_dil, flags)
         if (residual is None and out is None and not out_f32 and act != ACT_LEAKY_RELU
                 and self._s2d_stem(x, conv, kh, k_stride, k_pad, k_dil)):
             if bn is not None:
@@ -378,10 +391,80 @@ class Builder:
         self.ops.append(emit)
         return out
 
+    def _conv_mapped(self, x: TRef, conv, bn, act: int, act_a: float, residual: TRef | None, out: TRef | None,
+                     out_cmap: list | None, k_stride: int, k_pad: int, k_dil: int, flags: int) -> TRef:
+        """A dense or depthwise conv whose input and / or output carries virtual channel padding (TRef.cmap).  The weights are
+        scattered into the storage channel space - zero rows for padding outputs (with bias 0 and an identity BatchNorm, so
+        they stay exact zeros through any activation with act(0) = 0), zero columns for padding inputs."""
+        kh, kw = conv.kernel_size
+        cin, cout, groups = conv.in_channels, conv.out_channels, conv.groups
+        depthwise = groups > 1 and groups == cin and cin == cout
+        if groups != 1 and not depthwise:
+            raise NotImplementedError("grouped convolution on a tensor with virtual channel padding")
+        if x.creal != cin:
+            raise ValueError(f"conv expects {cin} input channels, tensor has {x.creal}")
+        if act in (ACT_SIGMOID, ACT_HSIGMOID):
+            raise NotImplementedError("act(0) != 0 on a tensor with virtual channel padding")
+        in_idx = list(x.cmap) if x.cmap is not None else list(range(cin))
+        if depthwise:
+            out_idx, cs_out = in_idx, x.C
+            if out_cmap is not None and list(out_cmap) != in_idx:
+                raise NotImplementedError("a depthwise conv keeps its input's channel layout")
+            if out is not None and out.C != cs_out:
+                raise ValueError("depthwise output view has the wrong width")
+        else:
+            out_idx = list(out_cmap) if out_cmap is not None else list(range(cout))
+            cs_out = out.C if out is not None else _rup(max(out_idx) + 1, 8)
+        if len(out_idx) != cout or max(out_idx) >= cs_out:
+            raise ValueError("output channel map does not match the convolution")
+        if bn is not None:
+            _check_bn(bn)
+        Ho = (x.H + 2 * k_pad - k_dil * (kh - 1) - 1) // k_stride + 1
+        Wo = (x.W + 2 * k_pad - k_dil * (kw - 1) - 1) // k_stride + 1
+        if Ho <= 0 or Wo <= 0:
+            raise ValueError(f"convolution output is empty for input {x.H}x{x.W}")
+        if out is None:
+            out = self.new(x.N, Ho, Wo, cs_out)
+        if (out.N, out.H, out.W, out.dtype) != (x.N, Ho, Wo, self.dtype):
+            raise ValueError("conv output view has the wrong shape")
+        identity_map = out_idx == list(range(cout)) and cs_out == cout
+        out.cmap = None if identity_map else out_idx
+        if residual is not None:
+            if (residual.N, residual.H, residual.W, residual.C) != (x.N, Ho, Wo, cs_out) or \
+                    (list(residual.cmap) if residual.cmap is not None else list(range(cs_out))) != \
+                    (out_idx if not identity_map else list(range(cs_out))):
+                raise ValueError("residual layout does not match the conv output")
+        if self.dtype == F32 and _F32_SPLIT and not depthwise:
+            flags |= _lib.CONV_F32_SPLIT
+        d = ConvDesc(N=x.N, H=x.H, W=x.W, Cin=x.C, Cout=cs_out, kh=kh, kw=kw, stride=k_stride, pad=k_pad, dil=k_dil,
+                     groups=x.C if depthwise else 1, act=act, in_pitch=x.pitch, out_pitch=out.pitch,
+                     res_pitch=residual.pitch if residual is not None else 0, flags=flags, act_param=act_a)
+        wb, bb, ws = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        _lib.call("pcv_conv_packed_bytes", C.byref(d), self.dtype, C.byref(wb), C.byref(bb))
+        _lib.call("pcv_conv_workspace_bytes", C.byref(d), self.dtype, C.byref(ws))
+        w_off, b_off = self._wblob(wb.value), self._wblob(bb.value)
+        self.weight_jobs.append(("conv_mapped", (d, conv, bn, in_idx, x.C, out_idx, cs_out, depthwise, w_off, b_off)))
+        idx = self._use(x, residual, out)
+        scratch = None
+        if ws.value:
+            sbuf = Buf(nbytes=ws.value, first=idx, last=idx)
+            self.bufs.append(sbuf)
+            scratch = TRef(1, 1, 1, ws.value // 2, ws.value // 2, BF16, sbuf)
+        dtype = self.dtype
+
+        def emit(plan, ptr, wptr):
+            _lib.call("pcv_conv2d_bias_act_ws", plan, C.byref(d), dtype, ptr(x), wptr(w_off), wptr(b_off),
+                      ptr(residual) if residual is not None else None, ptr(out),
+                      ptr(scratch) if scratch is not None else None, None)
+        self.ops.append(emit)
+        return out
+
     def bottleneck_tail(self, x: TRef, cb2: nn.Module, cb3: nn.Module, residual: TRef, post_act: int) -> TRef | None:
         """conv2 (3x3 ConvBlock) -> conv3 (1x1 ConvBlock) + residual + the unit's activation as ONE fused kernel
         (include/pcv_b200.h pcv_bottleneck_tail), or None when the pair is outside that kernel's domain."""
         if not _FUSE_TAIL[0] or not _is16(self.dtype) or residual is None or post_act not in (ACT_RELU, ACT_RELU6):
+            return None
+        if x.cmap is not None or residual.cmap is not None:
             return None
         for cb in (cb2, cb3):
             if (type(cb).__name__ != "ConvBlock" or getattr(cb, "use_pad", False) or not cb.normalize
@@ -430,6 +513,7 @@ class Builder:
         if left == right == top == bottom == 0:
             return x
         out = self.new(x.N, x.H + top + bottom, x.W + left + right, x.C, dtype=x.dtype)
+        out.cmap = x.cmap
         self._use(x, out)
         self.ops.append(lambda plan, ptr, wptr: _lib.call(
             "pcv_zero_pad2d", plan, x.dtype, x.N, x.H, x.W, x.C, ptr(x), x.pitch, left, right, top, bottom, ptr(out),
@@ -439,7 +523,7 @@ class Builder:
     def dw_pw(self, x: TRef, dwb: nn.Module, pwb: nn.Module, residual: TRef | None, post_act: int | None) -> TRef | None:
         """Depthwise ConvBlock -> pointwise ConvBlock (+ residual, + the unit's activation) as ONE fused kernel
         (include/pcv_b200.h pcv_dw_pw_fused), or None when the pair is outside that kernel's domain."""
-        if not _FUSE_DWPW[0] or not _is16(self.dtype):
+        if not _FUSE_DWPW[0] or not _is16(self.dtype) or x.cmap is not None or (residual is not None and residual.cmap is not None):
             return None
         for cb in (dwb, pwb):
             if (type(cb).__name__ != "ConvBlock" or getattr(cb, "use_pad", False) or not cb.normalize
@@ -499,7 +583,8 @@ class Builder:
                   post_act: int | None) -> TRef | None:
         """1x1 expansion ConvBlock -> depthwise ConvBlock -> pointwise ConvBlock (+ residual) as ONE fused kernel
         (include/pcv_b200.h pcv_exp_dw_pw_fused), or None when the triple is outside that kernel's domain."""
-        if not _FUSE_XDWPW[0] or not _FUSE_DWPW[0] or not _is16(self.dtype):
+        if not _FUSE_XDWPW[0] or not _FUSE_DWPW[0] or not _is16(self.dtype) or x.cmap is not None or (
+                residual is not None and residual.cmap is not None):
             return None
         for cb in (expb, dwb, pwb):
             if (type(cb).__name__ != "ConvBlock" or getattr(cb, "use_pad", False) or not cb.normalize
@@ -584,6 +669,7 @@ class Builder:
             x.buf.nbytes = 0
             return pooled
         out = self.new(x.N, Ho, Wo, x.C, dtype=x.dtype)
+        out.cmap = x.cmap
         self._use(x, out)
         self.ops.append(lambda plan, ptr, wptr: _lib.call(
             "pcv_maxpool2d", plan, x.dtype, x.N, x.H, x.W, x.C, k, stride, pad, ptr(x), x.pitch, ptr(out), out.pitch,
@@ -593,6 +679,7 @@ class Builder:
     def gap(self, x: TRef, out_dtype: int | None = None) -> TRef:
         out_dtype = x.dtype if out_dtype is None else out_dtype
         out = self.new(x.N, 1, 1, x.C, dtype=out_dtype)
+        out.cmap = x.cmap
         self._use(x, out)
         self.ops.append(lambda plan, ptr, wptr: _lib.call(
             "pcv_global_avgpool", plan, x.dtype, x.N, x.H * x.W, x.C, ptr(x), x.pitch, ptr(out), out_dtype, None))
@@ -603,6 +690,7 @@ class Builder:
         if (out_h, out_w) == (1, 1):
             return self.gap(x)
         out = self.new(x.N, out_h, out_w, x.C, dtype=x.dtype)
+        out.cmap = x.cmap
         self._use(x, out)
         self.ops.append(lambda plan, ptr, wptr: _lib.call(
             "pcv_adaptive_avgpool", plan, x.dtype, x.N, x.H, x.W, x.C, ptr(x), x.pitch, out_h, out_w, ptr(out), None))
@@ -611,9 +699,25 @@ class Builder:
     def se_gate(self, pooled: TRef, w1: torch.Tensor, b1, w2: torch.Tensor, b2, mid_act: int, out_act: int) -> TRef:
         """SEBlock excite (att.py:99-102): gate = out_act(W2 @ mid_act(W1 @ pooled + b1) + b2), all fp32.  `pooled` may be
         narrower than the gate (w1 [mid, pooled.C], w2 [C, mid]) when the unit's last 1x1 conv was folded into W1."""
-        N, Cin, Cc = pooled.N, pooled.C, w2.shape[0]
         cmid = w1.shape[0]
+        if pooled.cmap is not None:
+            # virtual channel padding: W1's columns / W2's rows (and b2) move to the storage positions, zeros elsewhere - the
+            # padding channels' gates multiply exact zeros
+            idx = torch.tensor(pooled.cmap, dtype=torch.long, device=w1.device)
+            if w1.shape[1] != len(pooled.cmap) or w2.shape[0] != len(pooled.cmap):
+                raise NotImplementedError("SE block on a padded tensor must gate the tensor it pools")
+            w1s = torch.zeros(cmid, pooled.C, dtype=w1.dtype, device=w1.device)
+            w1s[:, idx] = w1.detach()
+            w2s = torch.zeros(pooled.C, cmid, dtype=w2.dtype, device=w2.device)
+            w2s[idx] = w2.detach()
+            if b2 is not None:
+                b2s = torch.zeros(pooled.C, dtype=b2.dtype, device=b2.device)
+                b2s[idx] = b2.detach()
+                b2 = b2s
+            w1, w2 = w1s, w2s
+        N, Cin, Cc = pooled.N, pooled.C, w2.shape[0]
         gate = self.new(N, 1, 1, Cc, dtype=F32, extra_bytes=N * cmid * 4)
+        gate.cmap = pooled.cmap
         offs = []
         for t in (w1, b1, w2, b2):
             offs.append(None if t is None else self._wblob(t.numel() * 4))
@@ -632,7 +736,10 @@ class Builder:
         for t in (x, identity):
             if t is not None and t.pitch != t.C:
                 raise NotImplementedError("SE scale needs dense tensors")
+        if identity is not None and identity.cmap != x.cmap:
+            raise ValueError("SE identity has a different channel layout")
         out = self.new(x.N, x.H, x.W, x.C, dtype=x.dtype)
+        out.cmap = x.cmap
         self._use(x, gate, identity, out)
         self.ops.append(lambda plan, ptr, wptr: _lib.call(
             "pcv_se_scale_add_act", plan, x.dtype, x.N, x.H * x.W, x.C, ptr(x), ptr(gate),
@@ -642,7 +749,10 @@ class Builder:
     def add_act(self, a: TRef, b: TRef, act: int) -> TRef:
         if (a.N, a.H, a.W, a.C) != (b.N, b.H, b.W, b.C) or a.pitch != a.C or b.pitch != b.C:
             raise ValueError("add needs two dense tensors of the same shape")
+        if a.cmap != b.cmap:
+            raise ValueError("add of two tensors with different channel layouts")
         out = self.new(a.N, a.H, a.W, a.C, dtype=a.dtype)
+        out.cmap = a.cmap
         self._use(a, b, out)
         self.ops.append(lambda plan, ptr, wptr: _lib.call(
             "pcv_add_act", plan, a.dtype, a.N * a.H * a.W * a.C, ptr(a), ptr(b), act, ptr(out), None))
@@ -655,13 +765,20 @@ class Builder:
         if x.C % 8 != 0:
             raise NotImplementedError(f"a stand-alone normalisation / activation pass needs C % 8 == 0, got {x.C}")
         out = self.new(x.N, x.H, x.W, x.C, dtype=x.dtype)
+        out.cmap = x.cmap
+        if x.cmap is not None and act in (ACT_SIGMOID, ACT_HSIGMOID):
+            raise NotImplementedError("act(0) != 0 on a tensor with virtual channel padding")
         offs = []
-        for t in (scale, shift, slope):
+        for k, t in enumerate((scale, shift, slope)):
             if t is None:
                 offs.append(None)
                 continue
-            if t.numel() != x.C:
-                raise ValueError(f"per-channel vector of {t.numel()} values for {x.C} channels")
+            if t.numel() != x.creal:
+                raise ValueError(f"per-channel vector of {t.numel()} values for {x.creal} channels")
+            if x.cmap is not None:   # scatter to the storage positions: scale 1 / shift 0 / slope 1 on the padding (zeros stay zeros)
+                full = torch.full((x.C,), 0.0 if k == 1 else 1.0, dtype=torch.float32, device=t.device)
+                full[torch.tensor(x.cmap, dtype=torch.long, device=t.device)] = t.detach().float()
+                t = full
             offs.append(self._wblob(x.C * 4))
             self.weight_jobs.append(("raw", (t, offs[-1])))
         self._use(x, out)
@@ -676,10 +793,10 @@ class Builder:
         """A stand-alone activation module on a map (PReLU / LeakyReLU / any pcv_act code) as one pass."""
         if isinstance(m, nn.PReLU):
             w = m.weight.detach().float()
-            return self.affine_act(x, None, None, ACT_NONE, (w.expand(x.C) if w.numel() == 1 else w).contiguous())
+            return self.affine_act(x, None, None, ACT_NONE, (w.expand(x.creal) if w.numel() == 1 else w).contiguous())
         if isinstance(m, nn.LeakyReLU):
             return self.affine_act(x, None, None, ACT_NONE,
-                                   torch.full((x.C,), float(m.negative_slope), dtype=torch.float32, device=self.device))
+                                   torch.full((x.creal,), float(m.negative_slope), dtype=torch.float32, device=self.device))
         return self.affine_act(x, None, None, act_code(m))
 
     def _edge_out(self, x: TRef, H: int, W: int, name: str, launch) -> TRef:
@@ -693,6 +810,8 @@ class Builder:
         return out
 
     def bilinear(self, x: TRef, Hout: int, Wout: int, out: TRef | None = None, nchw_f32: bool = False) -> TRef:
+        if x.cmap is not None:
+            x = self.compact(x)
         if nchw_f32:
             return self._edge_out(x, Hout, Wout, f"bilinear C={x.C} {x.H}x{x.W}->{Hout}x{Wout} nchw_f32 (edge)",
                                   lambda ptr, optr, stream: _lib.call(
@@ -706,9 +825,23 @@ class Builder:
             out.pitch, 1 if nchw_f32 else 0, None))
         return out
 
+    def compact(self, x: TRef) -> TRef:
+        """Gather the real channels of a tensor with virtual channel padding into a dense tensor: a 1x1 convolution whose
+        weight is the identity on the real channels (exact in every tier: products by 1.0, sums with zeros)."""
+        if x.cmap is None:
+            return x
+        n = x.creal
+        shim = _ConvShim(torch.eye(n, dtype=torch.float32, device=self.device).view(n, n, 1, 1), None)
+        return self.conv(x, shim, None, ACT_NONE)
+
     def egress(self, x: TRef) -> TRef:
-        return self._edge_out(x, x.H, x.W, f"nhwc_to_nchw_f32 C={x.C} {x.H}x{x.W} (edge)", lambda ptr, optr, stream: _lib.call(
-            "pcv_nhwc_to_nchw_f32", None, x.dtype, x.N, x.C, x.H, x.W, ptr(x), x.pitch, optr, stream))
+        if x.cmap is not None and list(x.cmap) != list(range(x.creal)):
+            x = self.compact(x)
+        creal = x.creal   # a prefix map (padding at the end only) is just a narrower tensor at the same pitch
+        out = self._edge_out(x, x.H, x.W, f"nhwc_to_nchw_f32 C={creal} {x.H}x{x.W} (edge)", lambda ptr, optr, stream: _lib.call(
+            "pcv_nhwc_to_nchw_f32", None, x.dtype, x.N, creal, x.H, x.W, ptr(x), x.pitch, optr, stream))
+        out.C = out.pitch = creal
+        return out
 
 
 class _ConvShim:
@@ -771,7 +904,7 @@ def _lower_linear(b, m, x, **kw):
 
 
 @lowers("ConvBlock")
-def _lower_convblock(b, m, x, residual=None, post_act=None, out=None, pad_lrtb=None, **kw):
+def _lower_convblock(b, m, x, residual=None, post_act=None, out=None, pad_lrtb=None, out_cmap=None, **kw):
     """ConvBlock.forward (conv.py:278-286); `residual`/`post_act` carry the enclosing unit's add + activation.  A block built
     with a 4-tuple padding applies nn.ZeroPad2d first (conv.py:245-249,279-280); `pad_lrtb` is the caller's F.pad (tf_mode)."""
     if getattr(m, "use_pad", False):
@@ -784,15 +917,15 @@ def _lower_convblock(b, m, x, residual=None, post_act=None, out=None, pad_lrtb=N
         # nn.PReLU (per-channel slopes) / LeakyReLU behind a depthwise conv: one pass behind the conv
         if out is not None:
             raise NotImplementedError("a ConvBlock with a stand-alone activation cannot write into a concat slice")
-        y = b.activation(b.conv(x, m.conv, bn, ACT_NONE, pad_lrtb=pad_lrtb), m.activ)
+        y = b.activation(b.conv(x, m.conv, bn, ACT_NONE, pad_lrtb=pad_lrtb, out_cmap=out_cmap), m.activ)
         return b.add_act(y, residual, post) if residual is not None else y
     act = act_code(m.activ) if m.activate else ACT_NONE
     act_a = act_param(m.activ) if m.activate else 0.0
     if residual is None and post_act is None:
-        return b.conv(x, m.conv, bn, act, out=out, pad_lrtb=pad_lrtb, act_a=act_a)
+        return b.conv(x, m.conv, bn, act, out=out, pad_lrtb=pad_lrtb, act_a=act_a, out_cmap=out_cmap)
     if act == ACT_NONE:
-        return b.conv(x, m.conv, bn, post, residual=residual, out=out, pad_lrtb=pad_lrtb)   # fused: act(conv + residual)
-    y = b.conv(x, m.conv, bn, act, pad_lrtb=pad_lrtb, act_a=act_a)         # block has its own activation
+        return b.conv(x, m.conv, bn, post, residual=residual, out=out, pad_lrtb=pad_lrtb, out_cmap=out_cmap)   # fused: act(conv + residual)
+    y = b.conv(x, m.conv, bn, act, pad_lrtb=pad_lrtb, act_a=act_a, out_cmap=out_cmap)   # block has its own activation
     return b.add_act(y, residual, post) if residual is not None else y
 
 
@@ -1012,6 +1145,67 @@ def _lower_preres_activation(b, m, x, **kw):
     """PreResActivation.forward (preresnet.py:218-221): the network's last BN -> ReLU."""
     scale, shift = _bn_scale_shift(m.bn)
     return b.affine_act(x, scale, shift, act_code(m.activ))
+
+
+# ---- GhostNet (ghostnet.py): torch.cat of a 1x1 conv and a cheap depthwise conv of it ---------------------------------------
+@lowers("GhostConvBlock")
+def _lower_ghost_conv(b, m, x, out_cmap=None, **kw):
+    """GhostConvBlock.forward (ghostnet.py:57-60): x = main_conv(x); cat(x, cheap_conv(x)).  Both halves are written straight
+    into channel slices of one buffer; a half whose width is not a multiple of 8 is padded to 8 with zero channels (TRef.cmap)
+    so that the cheap depthwise conv and every consumer see 16-byte aligned slices."""
+    if kw.get("residual") is not None or kw.get("post_act") is not None or out_cmap is not None:
+        raise NotImplementedError("GhostConvBlock takes no fused residual")
+    main_c, cheap_c = m.main_conv.conv.out_channels, m.cheap_conv.conv.out_channels
+    if main_c != cheap_c:
+        raise NotImplementedError("GhostConvBlock with an odd width")
+    ms = _rup(main_c, 8)
+    conv0 = m.main_conv.conv
+    Ho = (x.H + 2 * _one(conv0.padding) - _one(conv0.dilation) * (conv0.kernel_size[0] - 1) - 1) // _one(conv0.stride) + 1
+    Wo = (x.W + 2 * _one(conv0.padding) - _one(conv0.dilation) * (conv0.kernel_size[1] - 1) - 1) // _one(conv0.stride) + 1
+    cat = b.new(x.N, Ho, Wo, 2 * ms)
+    xm = lower(b, m.main_conv, x, out=Builder.view(cat, 0, ms))
+    y = lower(b, m.cheap_conv, xm, out=Builder.view(cat, ms, ms))
+    if y.buf is not cat.buf or xm.buf is not cat.buf:
+        raise NotImplementedError("GhostConvBlock halves must write into the concat buffer")
+    cat.cmap = None if ms == main_c else list(range(main_c)) + [ms + i for i in range(cheap_c)]
+    return cat
+
+
+@lowers("GhostExpBlock")
+def _lower_ghost_exp(b, m, x, **kw):
+    """GhostExpBlock.forward (ghostnet.py:114-121): exp_conv -> [depthwise stride-2 conv] -> [SE] -> pw_conv."""
+    y = lower(b, m.exp_conv, x)
+    if m.use_dw_conv:
+        y = lower(b, m.dw_conv, y)
+    if m.use_se:
+        y = lower(b, m.se, y)
+    return lower(b, m.pw_conv, y)
+
+
+@lowers("GhostUnit")
+def _lower_ghost_unit(b, m, x, **kw):
+    """GhostUnit.forward (ghostnet.py:167-174): body(x) + (identity_conv(x) | x), nothing after the add.  The projection
+    shortcut's pointwise conv writes its channels in the body's (padded) concat layout so that the add is elementwise."""
+    y = lower(b, m.body, x)
+    if m.resize_identity:
+        idc = m.identity_conv
+        identity = lower(b, idc.pw_conv, lower(b, idc.dw_conv, x), out=b.new(y.N, y.H, y.W, y.C),
+                         out_cmap=y.cmap if y.cmap is not None else list(range(y.C)))
+    else:
+        identity = x
+    return b.add_act(y, identity, ACT_NONE)
+
+
+@lowers("GhostClassifier")
+def _lower_ghost_classifier(b, m, x, **kw):
+    """GhostClassifier.forward (ghostnet.py:203-206): 1x1 ConvBlock then a bare 1x1 conv with bias on the 1x1 map (fp32 logits)."""
+    return b.conv(lower(b, m.conv1, x), m.conv2, None, ACT_NONE, out_f32=True)
+
+
+@lowers("GhostNet")
+def _lower_ghostnet(b, m, x, **kw):
+    """GhostNet.forward (ghostnet.py:298-302): features -> classifier convs -> view."""
+    return _flat(lower(b, m.output, lower(b, m.features, x)))
 
 
 @lowers("DarkUnit")
@@ -1395,6 +1589,9 @@ class CompiledModule:
                 rel = wptr(off) - self.weights.data_ptr()
                 self.weights[rel:rel + src.numel() * 4].copy_(src.view(-1).view(torch.uint8))
                 continue
+            if kind == "conv_mapped":
+                self._pack_mapped(payload, keep, stream, wptr)
+                continue
             if kind == "conv_s2d":
                 d, conv, bn, k, w_off, b_off = payload
                 w0 = self._dev_f32(conv.weight)
@@ -1424,6 +1621,46 @@ class CompiledModule:
                       eps, wptr(w_off), wptr(b_off), stream)
         torch.cuda.synchronize(self.device)
         del keep
+
+    def _pack_mapped(self, payload, keep, stream, wptr) -> None:
+        """Weights of a conv with virtual channel padding (Builder._conv_mapped): scatter into the storage channel space."""
+        d, conv, bn, in_idx, cs_in, out_idx, cs_out, depthwise, w_off, b_off = payload
+        dev = self.device
+        w0 = self._dev_f32(conv.weight)
+        oi = torch.tensor(out_idx, dtype=torch.long, device=dev)
+        ii = torch.tensor(in_idx, dtype=torch.long, device=dev)
+        kh, kw = w0.shape[2], w0.shape[3]
+        if depthwise:
+            w = torch.zeros((cs_out, 1, kh, kw), dtype=torch.float32, device=dev)
+            w[oi] = w0
+        else:
+            w = torch.zeros((cs_out, cs_in, kh, kw), dtype=torch.float32, device=dev)
+            w[oi[:, None], ii[None, :]] = w0
+        cb = None
+        if conv.bias is not None:
+            cb = torch.zeros(cs_out, dtype=torch.float32, device=dev)
+            cb[oi] = self._dev_f32(conv.bias)
+        g = be = mu = var = None
+        eps = 0.0
+        if bn is not None:
+            # padding channels: identity BatchNorm on a zero weight row and a zero bias -> exact zeros
+            g = torch.ones(cs_out, dtype=torch.float32, device=dev)
+            be = torch.zeros(cs_out, dtype=torch.float32, device=dev)
+            mu = torch.zeros(cs_out, dtype=torch.float32, device=dev)
+            var = torch.ones(cs_out, dtype=torch.float32, device=dev)
+            if bn.weight is not None:
+                g[oi] = self._dev_f32(bn.weight)
+            if bn.bias is not None:
+                be[oi] = self._dev_f32(bn.bias)
+            mu[oi] = self._dev_f32(bn.running_mean)
+            var[oi] = self._dev_f32(bn.running_var)
+            eps = float(bn.eps)
+        keep += [w0, w, cb, g, be, mu, var]
+        _lib.call("pcv_pack_conv_weights", C.byref(d), self.dtype, w.data_ptr(),
+                  cb.data_ptr() if cb is not None else None,
+                  g.data_ptr() if g is not None else None, be.data_ptr() if be is not None else None,
+                  mu.data_ptr() if mu is not None else None, var.data_ptr() if var is not None else None,
+                  eps, wptr(w_off), wptr(b_off), stream)
 
     # -- outputs ------------------------------------------------------------------------------------------------
     def _tensor_of(self, t: TRef) -> torch.Tensor:

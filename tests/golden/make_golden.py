@@ -25,6 +25,7 @@ from pytorchcv.models.seresnext import SEResNeXtUnit  # noqa: E402
 from pytorchcv.models.common.activ import lambda_relu6, lambda_swish, lambda_hswish, lambda_prelu, lambda_leakyrelu  # noqa: E402
 from pytorchcv.models.common.conv import PreConvBlock, dwconv3x3_block  # noqa: E402
 from pytorchcv.models.preresnet import PreResUnit  # noqa: E402
+from pytorchcv.models.ghostnet import GhostConvBlock, GhostUnit  # noqa: E402
 from pytorchcv.models.mobilenetv3 import MobileNetV3Unit  # noqa: E402
 from pytorchcv.models.common.norm import lambda_batchnorm2d  # noqa: E402
 from pytorchcv.models.efficientnet import EffiDwsConvUnit, EffiInvResUnit  # noqa: E402
@@ -58,9 +59,10 @@ NETS = [
     ("preresnet18_bs2", "preresnet18", {}, (2, 3, 224, 224), 0, 1),              # PreConvBlock family
     ("preresnet50_bs2", "preresnet50", {}, (2, 3, 224, 224), 0, 1),
     ("darknet53_bs2", "darknet53", {}, (2, 3, 224, 224), 0, 1),                  # LeakyReLU epilogues
+    ("ghostnet_bs2", "ghostnet", {}, (2, 3, 224, 224), 0, 1),                    # torch.cat of odd-width halves
 ]
 
-NO_MIRROR = {"preresnet18", "preresnet50", "darknet53"}
+NO_MIRROR = {"preresnet18", "preresnet50", "darknet53", "ghostnet"}
 
 # block-level cases: (stem, ctor, input shape)
 BLOCKS = [
@@ -101,6 +103,11 @@ BLOCKS = [
     ("preconv_1x1_s2_bias", lambda: PreConvBlock(24, 16, kernel_size=1, stride=2, padding=0, bias=True), (2, 24, 10, 10)),
     ("preresunit_bottleneck_s2", lambda: PreResUnit(64, 128, stride=2, bottleneck=True, conv1_stride=True), (2, 64, 14, 14)),
     ("preresunit_basic", lambda: PreResUnit(32, 32, stride=1, bottleneck=False, conv1_stride=False), (2, 32, 8, 8)),
+    ("ghostconv_24_72", lambda: GhostConvBlock(24, 72), (2, 24, 14, 14)),                     # halves of 36: padded to 40
+    ("ghostunit_16_24_s2", lambda: GhostUnit(16, 24, stride=2, use_kernel3=True, exp_factor=3.0, use_se=False), (2, 16, 28, 28)),
+    ("ghostunit_24_24", lambda: GhostUnit(24, 24, stride=1, use_kernel3=True, exp_factor=3.0, use_se=False), (2, 24, 14, 14)),
+    ("ghostunit_24_40_s2_k5_se", lambda: GhostUnit(24, 40, stride=2, use_kernel3=False, exp_factor=3.0, use_se=True), (2, 24, 28, 28)),
+    ("ghostunit_80_80_se", lambda: GhostUnit(80, 80, stride=1, use_kernel3=True, exp_factor=2.3, use_se=True), (1, 80, 14, 14)),
 ]
 
 

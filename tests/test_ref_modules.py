@@ -44,7 +44,13 @@ def _block(stem):
     from pytorchcv.models.common.conv import ConvBlock, PreConvBlock, conv3x3_block, dwconv3x3_block
     from pytorchcv.models.common.activ import lambda_prelu, lambda_leakyrelu
     from pytorchcv.models.preresnet import PreResUnit
+    from pytorchcv.models.ghostnet import GhostConvBlock, GhostUnit
     table = {
+        "ghostconv_24_72": (lambda: GhostConvBlock(24, 72), (2, 24, 14, 14)),
+        "ghostunit_16_24_s2": (lambda: GhostUnit(16, 24, stride=2, use_kernel3=True, exp_factor=3.0, use_se=False), (2, 16, 28, 28)),
+        "ghostunit_24_24": (lambda: GhostUnit(24, 24, stride=1, use_kernel3=True, exp_factor=3.0, use_se=False), (2, 24, 14, 14)),
+        "ghostunit_24_40_s2_k5_se": (lambda: GhostUnit(24, 40, stride=2, use_kernel3=False, exp_factor=3.0, use_se=True), (2, 24, 28, 28)),
+        "ghostunit_80_80_se": (lambda: GhostUnit(80, 80, stride=1, use_kernel3=True, exp_factor=2.3, use_se=True), (1, 80, 14, 14)),
         "convblock_3x3_prelu": (lambda: conv3x3_block(in_channels=16, out_channels=24, activation=lambda_prelu(24)), (2, 16, 13, 13)),
         "convblock_1x1_prelu1": (lambda: ConvBlock(32, 64, kernel_size=1, activation=lambda_prelu(1)), (2, 32, 9, 9)),
         "convblock_3x3_leaky": (lambda: conv3x3_block(in_channels=16, out_channels=32, stride=2,
@@ -61,8 +67,10 @@ def _block(stem):
 
 
 BLOCKS = ["convblock_3x3_prelu", "convblock_1x1_prelu1", "convblock_3x3_leaky", "dwconv3x3_leaky", "preconv_3x3_preact",
-          "preconv_1x1_s2_bias", "preresunit_bottleneck_s2", "preresunit_basic"]
-NETS = [("preresnet18_bs2", "preresnet18"), ("preresnet50_bs2", "preresnet50"), ("darknet53_bs2", "darknet53")]
+          "preconv_1x1_s2_bias", "preresunit_bottleneck_s2", "preresunit_basic", "ghostconv_24_72", "ghostunit_16_24_s2",
+          "ghostunit_24_24", "ghostunit_24_40_s2_k5_se", "ghostunit_80_80_se"]
+NETS = [("preresnet18_bs2", "preresnet18"), ("preresnet50_bs2", "preresnet50"), ("darknet53_bs2", "darknet53"),
+        ("ghostnet_bs2", "ghostnet")]
 
 
 def _net(name, randomize_bn=True):
@@ -91,7 +99,7 @@ def test_oracle_matches_golden_nets(stem, name):
     assert int(gold["n_params"]) == sum(p.numel() for p in net.parameters())
 
 
-@pytest.mark.parametrize("name,n_ops", [("preresnet18", 32), ("preresnet50", 73), ("darknet53", 77)])
+@pytest.mark.parametrize("name,n_ops", [("preresnet18", 32), ("preresnet50", 73), ("darknet53", 77), ("ghostnet", 120)])
 def test_reference_modules_lower(name, n_ops):
     """Dry run of the lowering on the reference's module tree (no GPU): the op count shows what was fused.
     preresnet18: stem conv(+BN+ReLU) with the fused pool, per unit one pre-activation pass + 2 convs (+ projection), the
@@ -144,7 +152,7 @@ def test_nets_fp32_tier_gpu(stem, name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("tier", ["bf16", "fp16"])
-@pytest.mark.parametrize("name", ["preresnet18", "preresnet50", "darknet53"])
+@pytest.mark.parametrize("name", ["preresnet18", "preresnet50", "darknet53", "ghostnet"])
 def test_nets_16bit_tiers_gpu(name, tier):
     """16-bit tiers with the reference's init statistics (the fp16 tier's contract): <= 2e-2, same top-1."""
     if (name, tier) == ("darknet53", "fp16"):
@@ -158,7 +166,7 @@ def test_nets_16bit_tiers_gpu(name, tier):
     assert _rel(got, want) <= 2e-2, (name, tier, _rel(got, want))
     assert torch.equal(got.argmax(1), want.argmax(1))
     names = [r[0] for r in fast.compiled(x.cuda()).profile()]
-    if name == "darknet53":   # LeakyReLU rides on the conv epilogues: no stand-alone activation pass in the plan
+    if name in ("darknet53", "ghostnet"):   # LeakyReLU rides on the conv epilogues: no stand-alone activation pass in the plan
         assert not any(n.startswith("channel_affine_act") for n in names), names
     else:                     # one pre-activation pass per unit + the network's last BN -> ReLU, the rest folded into convs
         n_units = sum(type(m).__name__ == "PreResUnit" for m in net.modules())
