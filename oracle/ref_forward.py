@@ -447,6 +447,34 @@ def ghostnet(m, x):
     return x.view(x.size(0), -1)
 
 
+def mix_conv_block(m, x):
+    """MixConvBlock.forward (mixnet.py:151-157) with MixConv.forward (mixnet.py:76-80)."""
+    xx = torch.split(x, m.conv.splitted_in_channels, dim=m.conv.axis)
+    x = torch.cat(tuple(_conv2d(conv_i, x_i) for x_i, conv_i in zip(xx, m.conv.children())), dim=m.conv.axis)
+    if m.normalize:
+        x = _batchnorm(m.bn, x)
+    if m.activate:
+        x = _activation(m.activ, x)
+    return x
+
+
+def mix_unit(m, x):
+    """MixUnit.forward (mixnet.py:282-293)."""
+    identity = x
+    if m.use_exp_conv:
+        x = oracle_forward(m.exp_conv, x)
+    x = oracle_forward(m.conv1, x)
+    if m.use_se:
+        x = se_block(m.se, x)
+    x = oracle_forward(m.conv2, x)
+    return x + identity if m.residual else x
+
+
+def mix_init_block(m, x):
+    """MixInitBlock.forward (mixnet.py:326-329)."""
+    return mix_unit(m.conv2, conv_block(m.conv1, x))
+
+
 def dark_unit(m, x):
     """DarkUnit.forward (darknet53.py:45-49)."""
     return conv_block(m.conv2, conv_block(m.conv1, x)) + x
@@ -491,6 +519,7 @@ _BY_NAME = {
     "PreConvBlock": pre_conv_block, "PreResBlock": pre_res_body, "PreResBottleneck": pre_res_body, "PreResUnit": pre_res_unit,
     "PreResInitBlock": pre_res_init_block, "PreResActivation": pre_res_activation, "PreResNet": classifier,
     "DarkUnit": dark_unit, "DarkNet53": classifier,
+    "MixConvBlock": mix_conv_block, "MixUnit": mix_unit, "MixInitBlock": mix_init_block, "MixNet": classifier,
     "GhostConvBlock": ghost_conv_block, "GhostExpBlock": ghost_exp_block, "GhostUnit": ghost_unit, "GhostNet": ghostnet,
     "Concurrent": concurrent, "MultiOutputSequential": multi_output_sequential,
     "ASPPAvgBranch": aspp_avg_branch, "AtrousSpatialPyramidPooling": aspp, "DeepLabv3": deeplabv3,

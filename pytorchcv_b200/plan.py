@@ -825,14 +825,22 @@ class Builder:
             out.pitch, 1 if nchw_f32 else 0, None))
         return out
 
-    def compact(self, x: TRef) -> TRef:
-        """Gather the real channels of a tensor with virtual channel padding into a dense tensor: a 1x1 convolution whose
-        weight is the identity on the real channels (exact in every tier: products by 1.0, sums with zeros)."""
-        if x.cmap is None:
-            return x
+    def relayout(self, x: TRef, cmap: list | None, storage: int | None = None) -> TRef:
+        """Move the real channels of `x` to the storage positions `cmap` (None: dense) of a `storage`-channel tensor: a 1x1
+        convolution whose weight is the identity on the real channels (exact in every tier: products by 1.0, sums with
+        zeros).  The one extra pass a torch.split / torch.cat costs when producer and consumer disagree on the padding."""
         n = x.creal
+        want = list(cmap) if cmap is not None else list(range(n))
+        have = list(x.cmap) if x.cmap is not None else list(range(n))
+        storage = _rup(max(want) + 1, 8) if storage is None else storage
+        if want == have and storage == x.C:
+            return x
         shim = _ConvShim(torch.eye(n, dtype=torch.float32, device=self.device).view(n, n, 1, 1), None)
-        return self.conv(x, shim, None, ACT_NONE)
+        return self.conv(x, shim, None, ACT_NONE, out=self.new(x.N, x.H, x.W, storage), out_cmap=want)
+
+    def compact(self, x: TRef) -> TRef:
+        """Gather the real channels of a tensor with virtual channel padding into a dense tensor."""
+        return x if x.cmap is None else self.relayout(x, None)
 
     def egress(self, x: TRef) -> TRef:
         if x.cmap is not None and list(x.cmap) != list(range(x.creal)):
@@ -1208,6 +1216,90 @@ def _lower_ghostnet(b, m, x, **kw):
     return _flat(lower(b, m.output, lower(b, m.features, x)))
 
 
+# ---- MixNet (mixnet.py): torch.split -> one conv per part (mixed kernel sizes) -> torch.cat -> ONE BatchNorm -----------------
+def _seg_layout(sizes):
+    """Channel layout of a concat of parts: part i starts at the sum of the 8-rounded widths before it.  Returns (cmap | None,
+    storage width, part offsets)."""
+    offs, off = [], 0
+    for n in sizes:
+        offs.append(off)
+        off += _rup(n, 8)
+    cmap = [o + i for o, n in zip(offs, sizes) for i in range(n)]
+    return (None if cmap == list(range(sum(sizes))) and off == sum(sizes) else cmap), off, offs
+
+
+def _bn_slice(bn: nn.BatchNorm2d, lo: int, hi: int) -> nn.BatchNorm2d:
+    """Channels [lo, hi) of an eval BatchNorm2d as a BatchNorm2d of their own (MixConvBlock normalises the concat, mixnet.py:151-157;
+    a changed parameter recompiles the plan, so a copy is as good as a view)."""
+    _check_bn(bn)
+    part = nn.BatchNorm2d(hi - lo, eps=bn.eps, affine=bn.weight is not None).to(bn.running_mean.device).eval()
+    with torch.no_grad():
+        part.running_mean.copy_(bn.running_mean[lo:hi])
+        part.running_var.copy_(bn.running_var[lo:hi])
+        if bn.weight is not None:
+            part.weight.copy_(bn.weight[lo:hi])
+            part.bias.copy_(bn.bias[lo:hi])
+    return part
+
+
+@lowers("MixConvBlock")
+def _lower_mixconv_block(b, m, x, **kw):
+    """MixConvBlock.forward (mixnet.py:151-157) with MixConv.forward (mixnet.py:76-80): split the input channels, one conv per
+    part (1x1 parts, or depthwise parts with kernels 3, 5, 7, ...), concatenate, normalise, activate.  Every part reads and writes
+    a channel slice of one buffer (parts padded to 8 channels, TRef.cmap); the shared BatchNorm is folded part by part."""
+    if kw.get("residual") is not None or kw.get("post_act") is not None or kw.get("out") is not None:
+        raise NotImplementedError("MixConvBlock takes no fused residual / concat slice")
+    mc = m.conv
+    if mc.axis != 1:
+        raise NotImplementedError("MixConv splits along the channel axis")
+    convs = list(mc.children())
+    sizes_in = list(mc.splitted_in_channels)
+    sizes_out = [c.out_channels for c in convs]
+    in_map, in_storage, in_offs = _seg_layout(sizes_in)
+    x = b.relayout(x, in_map, in_storage)
+    out_map, out_storage, out_offs = _seg_layout(sizes_out)
+    c0 = convs[0]
+    Ho = (x.H + 2 * _one(c0.padding) - _one(c0.dilation) * (c0.kernel_size[0] - 1) - 1) // _one(c0.stride) + 1
+    Wo = (x.W + 2 * _one(c0.padding) - _one(c0.dilation) * (c0.kernel_size[1] - 1) - 1) // _one(c0.stride) + 1
+    cat = b.new(x.N, Ho, Wo, out_storage)
+    act = act_code(m.activ) if m.activate else ACT_NONE
+    if m.activate and _standalone_act(m.activ):
+        raise NotImplementedError("MixConvBlock with a stand-alone activation")
+    lo = 0
+    for conv, n_in, n_out, oi, oo in zip(convs, sizes_in, sizes_out, in_offs, out_offs):
+        xi = Builder.view(x, oi, _rup(n_in, 8))
+        xi.cmap = None if n_in % 8 == 0 else list(range(n_in))
+        bn = _bn_slice(m.bn, lo, lo + n_out) if m.normalize else None
+        y = b.conv(xi, conv, bn, act, out=Builder.view(cat, oo, _rup(n_out, 8)),
+                   act_a=act_param(m.activ) if m.activate else 0.0)
+        if y.buf is not cat.buf:
+            raise NotImplementedError("MixConv parts must write into the concat buffer")
+        lo += n_out
+    cat.cmap = out_map
+    return cat
+
+
+@lowers("MixUnit")
+def _lower_mix_unit(b, m, x, **kw):
+    """MixUnit.forward (mixnet.py:282-293): [expansion] -> (mixed) depthwise -> [SE] -> (mixed) 1x1 linear (+x)."""
+    y = lower(b, m.exp_conv, x) if m.use_exp_conv else x
+    y = lower(b, m.conv1, y)
+    if m.use_se:
+        y = lower(b, m.se, y)
+    if not m.residual:
+        return lower(b, m.conv2, y)
+    if type(m.conv2).__name__ == "ConvBlock" and x.cmap is None:
+        return lower(b, m.conv2, y, residual=x, post_act=None)       # the add rides on the 1x1 conv's epilogue
+    y = lower(b, m.conv2, y)
+    return b.add_act(b.relayout(y, x.cmap, x.C), x, ACT_NONE)
+
+
+@lowers("MixInitBlock")
+def _lower_mix_init(b, m, x, **kw):
+    """MixInitBlock.forward (mixnet.py:326-329)."""
+    return lower(b, m.conv2, lower(b, m.conv1, x))
+
+
 @lowers("DarkUnit")
 def _lower_dark_unit(b, m, x, **kw):
     """DarkUnit.forward (darknet53.py:45-49): conv1x1 -> conv3x3 (each with its LeakyReLU) + x, nothing after the add."""
@@ -1430,7 +1522,7 @@ def _flat(t: TRef) -> TRef:
 
 
 @lowers("ResNet", "SEResNeXt", "SEResNet", "ResNeXt", "MobileNet", "EfficientNet", "MnasNet", "FBNet", "SPNASNet", "SENet", "ProxylessNAS",
-        "PreResNet", "DarkNet53")
+        "PreResNet", "DarkNet53", "MixNet")
 def _lower_classifier(b, m, x, **kw):
     """features -> view(N,-1) -> [Dropout ->] Linear (resnet.py:333-337, seresnext.py:136-140, efficientnet.py:354-358)."""
     return _flat(lower(b, m.output, lower(b, m.features, x)))

@@ -26,6 +26,7 @@ from pytorchcv.models.common.activ import lambda_relu6, lambda_swish, lambda_hsw
 from pytorchcv.models.common.conv import PreConvBlock, dwconv3x3_block  # noqa: E402
 from pytorchcv.models.preresnet import PreResUnit  # noqa: E402
 from pytorchcv.models.ghostnet import GhostConvBlock, GhostUnit  # noqa: E402
+from pytorchcv.models.mixnet import MixConvBlock, MixUnit, mixconv1x1_block  # noqa: E402
 from pytorchcv.models.mobilenetv3 import MobileNetV3Unit  # noqa: E402
 from pytorchcv.models.common.norm import lambda_batchnorm2d  # noqa: E402
 from pytorchcv.models.efficientnet import EffiDwsConvUnit, EffiInvResUnit  # noqa: E402
@@ -60,9 +61,10 @@ NETS = [
     ("preresnet50_bs2", "preresnet50", {}, (2, 3, 224, 224), 0, 1),
     ("darknet53_bs2", "darknet53", {}, (2, 3, 224, 224), 0, 1),                  # LeakyReLU epilogues
     ("ghostnet_bs2", "ghostnet", {}, (2, 3, 224, 224), 0, 1),                    # torch.cat of odd-width halves
+    ("mixnet_s_bs2", "mixnet_s", {}, (2, 3, 224, 224), 0, 1),                    # torch.split / mixed depthwise kernels 3..11
 ]
 
-NO_MIRROR = {"preresnet18", "preresnet50", "darknet53", "ghostnet"}
+NO_MIRROR = {"preresnet18", "preresnet50", "darknet53", "ghostnet", "mixnet_s"}
 
 # block-level cases: (stem, ctor, input shape)
 BLOCKS = [
@@ -108,6 +110,13 @@ BLOCKS = [
     ("ghostunit_24_24", lambda: GhostUnit(24, 24, stride=1, use_kernel3=True, exp_factor=3.0, use_se=False), (2, 24, 14, 14)),
     ("ghostunit_24_40_s2_k5_se", lambda: GhostUnit(24, 40, stride=2, use_kernel3=False, exp_factor=3.0, use_se=True), (2, 24, 28, 28)),
     ("ghostunit_80_80_se", lambda: GhostUnit(80, 80, stride=1, use_kernel3=True, exp_factor=2.3, use_se=True), (1, 80, 14, 14)),
+    ("mixconv_dw_240_k4_s2", lambda: MixConvBlock(240, 240, kernel_size=[3, 5, 7, 9], stride=2, padding=[1, 2, 3, 4], groups=240,
+                                                  activation=lambda_swish()), (1, 240, 28, 28)),      # 4 parts of 60: padded to 64
+    ("mixconv1x1_40_120_k2", lambda: mixconv1x1_block(in_channels=40, out_channels=120, kernel_count=2), (2, 40, 14, 14)),
+    ("mixunit_40_40_se", lambda: MixUnit(40, 40, stride=1, exp_kernel_count=2, conv1_kernel_count=2, conv2_kernel_count=2,
+                                         exp_factor=6, se_factor=2, activation=lambda_swish()), (2, 40, 14, 14)),
+    ("mixunit_24_40_s2_k3", lambda: MixUnit(24, 40, stride=2, exp_kernel_count=1, conv1_kernel_count=3, conv2_kernel_count=1,
+                                            exp_factor=6, se_factor=2, activation=lambda_swish()), (1, 24, 28, 28)),
 ]
 
 

@@ -45,7 +45,16 @@ def _block(stem):
     from pytorchcv.models.common.activ import lambda_prelu, lambda_leakyrelu
     from pytorchcv.models.preresnet import PreResUnit
     from pytorchcv.models.ghostnet import GhostConvBlock, GhostUnit
+    from pytorchcv.models.mixnet import MixConvBlock, MixUnit, mixconv1x1_block
+    from pytorchcv.models.common.activ import lambda_swish
     table = {
+        "mixconv_dw_240_k4_s2": (lambda: MixConvBlock(240, 240, kernel_size=[3, 5, 7, 9], stride=2, padding=[1, 2, 3, 4], groups=240,
+                                                      activation=lambda_swish()), (1, 240, 28, 28)),
+        "mixconv1x1_40_120_k2": (lambda: mixconv1x1_block(in_channels=40, out_channels=120, kernel_count=2), (2, 40, 14, 14)),
+        "mixunit_40_40_se": (lambda: MixUnit(40, 40, stride=1, exp_kernel_count=2, conv1_kernel_count=2, conv2_kernel_count=2,
+                                             exp_factor=6, se_factor=2, activation=lambda_swish()), (2, 40, 14, 14)),
+        "mixunit_24_40_s2_k3": (lambda: MixUnit(24, 40, stride=2, exp_kernel_count=1, conv1_kernel_count=3, conv2_kernel_count=1,
+                                                exp_factor=6, se_factor=2, activation=lambda_swish()), (1, 24, 28, 28)),
         "ghostconv_24_72": (lambda: GhostConvBlock(24, 72), (2, 24, 14, 14)),
         "ghostunit_16_24_s2": (lambda: GhostUnit(16, 24, stride=2, use_kernel3=True, exp_factor=3.0, use_se=False), (2, 16, 28, 28)),
         "ghostunit_24_24": (lambda: GhostUnit(24, 24, stride=1, use_kernel3=True, exp_factor=3.0, use_se=False), (2, 24, 14, 14)),
@@ -68,9 +77,10 @@ def _block(stem):
 
 BLOCKS = ["convblock_3x3_prelu", "convblock_1x1_prelu1", "convblock_3x3_leaky", "dwconv3x3_leaky", "preconv_3x3_preact",
           "preconv_1x1_s2_bias", "preresunit_bottleneck_s2", "preresunit_basic", "ghostconv_24_72", "ghostunit_16_24_s2",
-          "ghostunit_24_24", "ghostunit_24_40_s2_k5_se", "ghostunit_80_80_se"]
+          "ghostunit_24_24", "ghostunit_24_40_s2_k5_se", "ghostunit_80_80_se", "mixconv_dw_240_k4_s2", "mixconv1x1_40_120_k2",
+          "mixunit_40_40_se", "mixunit_24_40_s2_k3"]
 NETS = [("preresnet18_bs2", "preresnet18"), ("preresnet50_bs2", "preresnet50"), ("darknet53_bs2", "darknet53"),
-        ("ghostnet_bs2", "ghostnet")]
+        ("ghostnet_bs2", "ghostnet"), ("mixnet_s_bs2", "mixnet_s")]
 
 
 def _net(name, randomize_bn=True):
@@ -99,7 +109,8 @@ def test_oracle_matches_golden_nets(stem, name):
     assert int(gold["n_params"]) == sum(p.numel() for p in net.parameters())
 
 
-@pytest.mark.parametrize("name,n_ops", [("preresnet18", 32), ("preresnet50", 73), ("darknet53", 77), ("ghostnet", 120)])
+@pytest.mark.parametrize("name,n_ops", [("preresnet18", 32), ("preresnet50", 73), ("darknet53", 77), ("ghostnet", 120), ("mixnet_s", 164),
+                                        ("mixnet_m", 215)])
 def test_reference_modules_lower(name, n_ops):
     """Dry run of the lowering on the reference's module tree (no GPU): the op count shows what was fused.
     preresnet18: stem conv(+BN+ReLU) with the fused pool, per unit one pre-activation pass + 2 convs (+ projection), the
@@ -152,7 +163,7 @@ def test_nets_fp32_tier_gpu(stem, name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("tier", ["bf16", "fp16"])
-@pytest.mark.parametrize("name", ["preresnet18", "preresnet50", "darknet53", "ghostnet"])
+@pytest.mark.parametrize("name", ["preresnet18", "preresnet50", "darknet53", "ghostnet", "mixnet_s"])
 def test_nets_16bit_tiers_gpu(name, tier):
     """16-bit tiers with the reference's init statistics (the fp16 tier's contract): <= 2e-2, same top-1."""
     if (name, tier) == ("darknet53", "fp16"):
@@ -166,7 +177,7 @@ def test_nets_16bit_tiers_gpu(name, tier):
     assert _rel(got, want) <= 2e-2, (name, tier, _rel(got, want))
     assert torch.equal(got.argmax(1), want.argmax(1))
     names = [r[0] for r in fast.compiled(x.cuda()).profile()]
-    if name in ("darknet53", "ghostnet"):   # LeakyReLU rides on the conv epilogues: no stand-alone activation pass in the plan
+    if name in ("darknet53", "ghostnet", "mixnet_s"):   # LeakyReLU rides on the conv epilogues: no stand-alone activation pass in the plan
         assert not any(n.startswith("channel_affine_act") for n in names), names
     else:                     # one pre-activation pass per unit + the network's last BN -> ReLU, the rest folded into convs
         n_units = sum(type(m).__name__ == "PreResUnit" for m in net.modules())
