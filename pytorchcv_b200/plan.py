@@ -1200,7 +1200,7 @@ def _lower_ghost_unit(b, m, x, **kw):
         identity = lower(b, idc.pw_conv, lower(b, idc.dw_conv, x), out=b.new(y.N, y.H, y.W, y.C),
                          out_cmap=y.cmap if y.cmap is not None else list(range(y.C)))
     else:
-        identity = x
+        identity = b.relayout(x, y.cmap, y.C)   # a no-op inside the network: the previous unit left the same layout
     return b.add_act(y, identity, ACT_NONE)
 
 
