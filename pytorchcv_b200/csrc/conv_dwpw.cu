@@ -18,6 +18,7 @@
 //
 // Saved per block: one write + one read of the depthwise tensor (MobileNetV2 bs256: 2.4 GB of the step's 7.3 GB) and one
 // kernel launch.  Domain: 3x3 depthwise, stride 1 or 2, pad 1, clamp-family activations, Cout <= 256, maps >= 14 wide.
+#define PCV_MBAR_SUSPEND_NS 20000u   // idle role warps sleep in mbarrier.try_wait instead of re-polling (ptx.cuh)
 #include "igemm_common.cuh"
 
 namespace pcv {
@@ -287,8 +288,11 @@ dwpw_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CU
     const bool dw_relu = p.dw_lo == 0.f;
     const int total_g = my_tiles * p.ncb;
     float2 wr[9], b2;
+    // ring position / phase and channel block advance incrementally (g += 2): a division per block and warp was 8 % of the
+    // stencil warps' instructions (ncu source page, profiles/README.md)
+    int st = team % p.stages, st_phase = (team / p.stages) & 1, cb = team % p.ncb;
     for (int g = team; g < total_g; g += 2) {
-      const int st = g % p.stages, ab = g & ((1 << p.na_shift) - 1), cb = g % p.ncb;
+      const int ab = g & ((1 << p.na_shift) - 1);
       // lane -> (channel pair, column group): a full block gives a thread 2 channels of the warp's 4 columns; a tail block with
       // <= 32 (<= 16) valid channels gives it 2 (1) of those columns, so that no lane works on padding channels
       const int ks = dp_ksteps(p.C, cb);
@@ -304,7 +308,7 @@ dwpw_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CU
       const bool tl = (p.dbg & 16) && blockIdx.x == 0 && quad == 0 && lane == 0 && g >= 24 && g < 32;
       long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0;
       if (tl) tq0 = clock64();
-      mbar_wait(&full[st], (g / p.stages) & 1);
+      mbar_wait(&full[st], st_phase);
       if (tl) tq1 = clock64();
       mbar_wait(&a_empty[ab], ((g >> p.na_shift) & 1) ^ 1);
       if (tl) tq2 = clock64();
@@ -326,6 +330,11 @@ dwpw_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CU
         long long* L = tlog + (g - 24) * 6;
         L[0] = tq0; L[1] = tq1; L[2] = tq2; L[3] = tq3; L[4] = clock64();
       }
+      st += 2;
+      if (st >= p.stages) { st -= p.stages; st_phase ^= 1; }
+      cb += 2;
+      if (cb >= p.ncb) cb -= p.ncb;
+      if (cb >= p.ncb) cb -= p.ncb;
     }
   } else if (warp >= 4) {
     // ===================================== epilogue: bias (+ identity), clamp, 16-bit, direct stores ====================

@@ -33,6 +33,7 @@
 //
 // Domain: 1x1 stride-1 expansion with Cin <= 64 and a clamp-family activation, 3x3 depthwise (stride 1 or 2, pad 1), 1x1
 // projection with Cout <= 128 (stride 1) / 64 (stride 2), maps >= 14 wide at the output.
+#define PCV_MBAR_SUSPEND_NS 20000u   // idle role warps sleep in mbarrier.try_wait instead of re-polling (ptx.cuh)
 #include "igemm_common.cuh"
 
 namespace pcv {
@@ -322,10 +323,14 @@ xdwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     const uint32_t stage_u32 = smem_u32(sStage + team * p.halo_bytes);
     const int total_g = my_tiles * p.ncb;
     float2 wr[9], b2;
+    // channel block and tile coordinates advance incrementally (g += 2; a tile step is a mixed-radix add of gridDim.x): the
+    // divisions they replace were ~15 % of these warps' instructions per block
+    const int dtx = static_cast<int>(gridDim.x) % p.tiles_x, dq = static_cast<int>(gridDim.x) / p.tiles_x;
+    const int dty = dq % p.tiles_y, dn = dq / p.tiles_y;
+    int cb = team % p.ncb, n, ty, tx;
+    tile_coords(blockIdx.x + (team / p.ncb) * gridDim.x, n, ty, tx);
     for (int g = team; g < total_g; g += 2) {
-      const int ab = g & ((1 << p.na_shift) - 1), cb = g % p.ncb, it = g / p.ncb;
-      int n, ty, tx;
-      tile_coords(blockIdx.x + it * gridDim.x, n, ty, tx);
+      const int ab = g & ((1 << p.na_shift) - 1);
       const int gy0 = ty * TH * S - 1, gx0 = tx * XD_TW * S - 1;
       // ---- expansion epilogue: TMEM -> stage buffer (every warp of the team is past its previous stencil: named barrier)
       mbar_wait(&e_full[team], (g >> 1) & 1);
@@ -394,6 +399,16 @@ xdwpw_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
       fence_proxy_async_smem();   // the A block is read by tcgen05.mma (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[ab]);
+      cb += 2;
+      while (cb >= p.ncb) {   // next tile(s) of this CTA
+        cb -= p.ncb;
+        tx += dtx;
+        int carry = 0;
+        if (tx >= p.tiles_x) { tx -= p.tiles_x; carry = 1; }
+        ty += dty + carry;
+        if (ty >= p.tiles_y) { ty -= p.tiles_y; n += 1; }
+        n += dn;
+      }
     }
   } else if (warp >= 4) {
     // ===================================== projection epilogue: bias (+ identity), clamp, 16-bit, direct stores =========

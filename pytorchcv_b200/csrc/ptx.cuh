@@ -50,16 +50,29 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// Optional suspend-time hint of mbarrier.try_wait (a translation unit defines PCV_MBAR_SUSPEND_NS before including this file):
+// without one a waiting warp re-polls every few tens of ns - in the CUDA-core-bound fused dw -> pw kernels the poll loops of
+// the idle role warps were 32 % of all issued instructions (ncu source page) and compete with the stencil warps for issue
+// slots; with it the warp sleeps in hardware until the phase completes (or the hint expires).  The latency-bound GEMM
+// kernels keep the plain form (ResNet-18 fp32 bs8: -0.5 % with the hint).
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred P;\n\t"
+#ifdef PCV_MBAR_SUSPEND_NS
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+#endif
       "selp.u32 %0, 1, 0, P;\n\t"
       "}\n"
       : "=r"(ok)
+#ifdef PCV_MBAR_SUSPEND_NS
+      : "r"(smem_u32(bar)), "r"(parity), "r"(PCV_MBAR_SUSPEND_NS)
+#else
       : "r"(smem_u32(bar)), "r"(parity)
+#endif
       : "memory");
   return ok != 0;
 }
