@@ -6,7 +6,7 @@ for rep in $(seq 1 ${REPS:-2}); do
 for m in $MODELS; do
   for which in prev new; do
     if [ $which = prev ]; then export PCV_B200_LIB=$PWD/pytorchcv_b200/libpcv_b200_prev.so; else unset PCV_B200_LIB; fi
-    timeout 300 python bench.py --model $m --no-cpu-baseline --steps 30 --ops-out gpurun_out/ab_ops_${m}_$which.json > gpurun_out/ab_${m}_$which.json 2> gpurun_out/ab_${m}_$which.err
+    timeout 300 python bench.py --model $m --no-cpu-baseline --no-configs --steps 30 --ops-out gpurun_out/ab_ops_${m}_$which.json > gpurun_out/ab_${m}_$which.json 2> gpurun_out/ab_${m}_$which.err
     python - <<PY
 import json
 try:
