@@ -475,6 +475,16 @@ def mix_init_block(m, x):
     return mix_unit(m.conv2, conv_block(m.conv1, x))
 
 
+def effi_edge_res_unit(m, x):
+    """EffiEdgeResUnit.forward (efficientnetedge.py:77-86)."""
+    identity = x
+    x = conv_block(m.conv1, x)
+    if m.use_se:
+        x = se_block(m.se, x)
+    x = conv_block(m.conv2, x)
+    return x + identity if m.residual else x
+
+
 def dark_unit(m, x):
     """DarkUnit.forward (darknet53.py:45-49)."""
     return conv_block(m.conv2, conv_block(m.conv1, x)) + x
@@ -519,6 +529,7 @@ _BY_NAME = {
     "PreConvBlock": pre_conv_block, "PreResBlock": pre_res_body, "PreResBottleneck": pre_res_body, "PreResUnit": pre_res_unit,
     "PreResInitBlock": pre_res_init_block, "PreResActivation": pre_res_activation, "PreResNet": classifier,
     "DarkUnit": dark_unit, "DarkNet53": classifier,
+    "EffiEdgeResUnit": effi_edge_res_unit, "EfficientNetEdge": efficientnet,
     "MixConvBlock": mix_conv_block, "MixUnit": mix_unit, "MixInitBlock": mix_init_block, "MixNet": classifier,
     "GhostConvBlock": ghost_conv_block, "GhostExpBlock": ghost_exp_block, "GhostUnit": ghost_unit, "GhostNet": ghostnet,
     "Concurrent": concurrent, "MultiOutputSequential": multi_output_sequential,

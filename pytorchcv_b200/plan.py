@@ -1341,6 +1341,15 @@ def _lower_effi_invres(b, m, x, **kw):
     return lower(b, m.conv3, y, residual=x if m.residual else None, post_act=None)
 
 
+@lowers("EffiEdgeResUnit")
+def _lower_effi_edge_unit(b, m, x, **kw):
+    """EffiEdgeResUnit.forward (efficientnetedge.py:77-86): conv3x3 expansion -> [SE] -> 1x1 linear (+x); the add rides on the 1x1."""
+    y = lower(b, m.conv1, x)
+    if m.use_se:
+        y = lower(b, m.se, y)
+    return lower(b, m.conv2, y, residual=x if m.residual else None, post_act=None)
+
+
 @lowers("MobileNetV3Unit")
 def _lower_mnv3_unit(b, m, x, **kw):
     """MobileNetV3Unit.forward (mobilenetv3.py:82-93): [1x1 expand] -> dw -> [SE] -> 1x1 linear (+x)."""
@@ -1522,7 +1531,7 @@ def _flat(t: TRef) -> TRef:
 
 
 @lowers("ResNet", "SEResNeXt", "SEResNet", "ResNeXt", "MobileNet", "EfficientNet", "MnasNet", "FBNet", "SPNASNet", "SENet", "ProxylessNAS",
-        "PreResNet", "DarkNet53", "MixNet")
+        "PreResNet", "DarkNet53", "MixNet", "EfficientNetEdge")
 def _lower_classifier(b, m, x, **kw):
     """features -> view(N,-1) -> [Dropout ->] Linear (resnet.py:333-337, seresnext.py:136-140, efficientnet.py:354-358)."""
     return _flat(lower(b, m.output, lower(b, m.features, x)))

@@ -62,9 +62,10 @@ NETS = [
     ("darknet53_bs2", "darknet53", {}, (2, 3, 224, 224), 0, 1),                  # LeakyReLU epilogues
     ("ghostnet_bs2", "ghostnet", {}, (2, 3, 224, 224), 0, 1),                    # torch.cat of odd-width halves
     ("mixnet_s_bs2", "mixnet_s", {}, (2, 3, 224, 224), 0, 1),                    # torch.split / mixed depthwise kernels 3..11
+    ("efficientnet_edge_small_b_bs2", "efficientnet_edge_small_b", {}, (2, 3, 224, 224), 0, 1),   # EffiEdgeResUnit, tf_mode
 ]
 
-NO_MIRROR = {"preresnet18", "preresnet50", "darknet53", "ghostnet", "mixnet_s"}
+NO_MIRROR = {"preresnet18", "preresnet50", "darknet53", "ghostnet", "mixnet_s", "efficientnet_edge_small_b"}
 
 # block-level cases: (stem, ctor, input shape)
 BLOCKS = [

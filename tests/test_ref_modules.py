@@ -80,7 +80,8 @@ BLOCKS = ["convblock_3x3_prelu", "convblock_1x1_prelu1", "convblock_3x3_leaky", 
           "ghostunit_24_24", "ghostunit_24_40_s2_k5_se", "ghostunit_80_80_se", "mixconv_dw_240_k4_s2", "mixconv1x1_40_120_k2",
           "mixunit_40_40_se", "mixunit_24_40_s2_k3"]
 NETS = [("preresnet18_bs2", "preresnet18"), ("preresnet50_bs2", "preresnet50"), ("darknet53_bs2", "darknet53"),
-        ("ghostnet_bs2", "ghostnet"), ("mixnet_s_bs2", "mixnet_s")]
+        ("ghostnet_bs2", "ghostnet"), ("mixnet_s_bs2", "mixnet_s"),
+        ("efficientnet_edge_small_b_bs2", "efficientnet_edge_small_b")]
 
 
 def _net(name, randomize_bn=True):
@@ -110,7 +111,7 @@ def test_oracle_matches_golden_nets(stem, name):
 
 
 @pytest.mark.parametrize("name,n_ops", [("preresnet18", 32), ("preresnet50", 73), ("darknet53", 77), ("ghostnet", 120), ("mixnet_s", 164),
-                                        ("mixnet_m", 215)])
+                                        ("mixnet_m", 215), ("efficientnet_edge_small_b", 54)])
 def test_reference_modules_lower(name, n_ops):
     """Dry run of the lowering on the reference's module tree (no GPU): the op count shows what was fused.
     preresnet18: stem conv(+BN+ReLU) with the fused pool, per unit one pre-activation pass + 2 convs (+ projection), the
@@ -163,7 +164,7 @@ def test_nets_fp32_tier_gpu(stem, name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("tier", ["bf16", "fp16"])
-@pytest.mark.parametrize("name", ["preresnet18", "preresnet50", "darknet53"])
+@pytest.mark.parametrize("name", ["preresnet18", "preresnet50", "darknet53", "efficientnet_edge_small_b"])
 def test_nets_16bit_tiers_gpu(name, tier):
     """16-bit tiers with the reference's init statistics (the fp16 tier's contract): <= 2e-2, same top-1."""
     if (name, tier) == ("darknet53", "fp16"):
@@ -177,7 +178,7 @@ def test_nets_16bit_tiers_gpu(name, tier):
     assert _rel(got, want) <= 2e-2, (name, tier, _rel(got, want))
     assert torch.equal(got.argmax(1), want.argmax(1))
     names = [r[0] for r in fast.compiled(x.cuda()).profile()]
-    if name == "darknet53":   # LeakyReLU rides on the conv epilogues: no stand-alone activation pass in the plan
+    if name in ("darknet53", "efficientnet_edge_small_b"):   # every activation rides on a conv epilogue: no stand-alone pass
         assert not any(n.startswith("channel_affine_act") for n in names), names
     else:                     # one pre-activation pass per unit + the network's last BN -> ReLU, the rest folded into convs
         n_units = sum(type(m).__name__ == "PreResUnit" for m in net.modules())
