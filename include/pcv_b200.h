@@ -74,6 +74,10 @@ enum pcv_conv_flags {
   PCV_CONV_FORCE_SIMT = 2,   /* bf16 tier only: use the CUDA-core kernel (cross-check for the tcgen05 path) */
   PCV_CONV_A_IM2COL = 4,     /* bf16 tier only: use the im2col TMA descriptor even for 1x1 stride-1 */
   PCV_CONV_IN_OVERLAP = 8,   /* x is an overlapping-window VIEW: in_pitch < Cin is allowed (space-to-depth stem) */
+  PCV_CONV_SE_GATE = 64,     /* 16-bit tiers, pair tcgen05 kernel (ask pcv_conv_se_gate_ok): `workspace` of pcv_conv2d_bias_act_ws is a
+                                const float* gate[N][Cout]; y = act((conv + bias) * gate[n, c] + residual) - the SE scale + identity
+                                + activation of SEResNeXtUnit / SEResUnit (seresnext.py:57-66) in the epilogue of the unit's last
+                                1x1 conv, possible because the squeeze is taken on that conv's INPUT (mean commutes with a 1x1 conv) */
   PCV_CONV_F32_SPLIT = 32,   /* fp32 tier only: evaluate the dense / grouped conv on the tensor cores as a 3-way bf16 split of
                                 the fp32 activations and weights (24 significant bits per operand, exact products, fp32
                                 accumulation: fp32-FMA accuracy at tcgen05 rate).  Needs pcv_conv_workspace_bytes() of
@@ -121,6 +125,9 @@ PCV_API int pcv_pack_conv_weights(const pcv_conv_desc* d, int dtype, const float
 PCV_API int pcv_conv2d_bias_act(pcv_plan* plan, const pcv_conv_desc* d, int dtype, const void* x, const void* w_packed,
                         const float* bias, const void* residual, void* y, pcv_stream stream);
 
+/* 1 when `d` (with PCV_CONV_SE_GATE set) is served by the kernel that has the gated epilogue, else 0: the caller then records the
+ * convolution and pcv_se_scale_add_act separately. */
+PCV_API int pcv_conv_se_gate_ok(const pcv_conv_desc* d, int dtype);
 /* The same op for descriptors that need scratch memory (PCV_CONV_F32_SPLIT: the split copy of x).  `workspace`: device
  * buffer of pcv_conv_workspace_bytes() bytes (0 = none needed), 16-byte aligned, private to this op while it runs. */
 PCV_API int pcv_conv_workspace_bytes(const pcv_conv_desc* d, int dtype, size_t* bytes);

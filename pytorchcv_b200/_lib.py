@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("PCV_B200_LIB") or os.path.join(_HERE, "libpcv_b200.so
 BF16, F32, F16 = 0, 1, 2                      # pcv_dtype
 IMG_F32, IMG_BF16, IMG_F16, IMG_U8 = 0, 1, 2, 3  # pcv_image_type
 ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SIGMOID, ACT_SWISH, ACT_HSWISH, ACT_HSIGMOID, ACT_LEAKY_RELU, ACT_CLAMP01 = range(9)
-CONV_OUT_F32, CONV_FORCE_SIMT, CONV_A_IM2COL, CONV_IN_OVERLAP, CONV_POOL3S2, CONV_F32_SPLIT = 1, 2, 4, 8, 16, 32
+CONV_OUT_F32, CONV_FORCE_SIMT, CONV_A_IM2COL, CONV_IN_OVERLAP, CONV_POOL3S2, CONV_F32_SPLIT, CONV_SE_GATE = 1, 2, 4, 8, 16, 32, 64
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 
@@ -46,6 +46,7 @@ SIGNATURES = {
     "pcv_conv_packed_bytes": (_I, [C.POINTER(ConvDesc), _I, C.POINTER(_Z), C.POINTER(_Z)]),
     "pcv_pack_conv_weights": (_I, [C.POINTER(ConvDesc), _I, _P, _P, _P, _P, _P, _P, C.c_float, _P, _P, _P]),
     "pcv_conv2d_bias_act": (_I, [_P, C.POINTER(ConvDesc), _I, _P, _P, _P, _P, _P, _P]),
+    "pcv_conv_se_gate_ok": (_I, [C.POINTER(ConvDesc), _I]),
     "pcv_conv_workspace_bytes": (_I, [C.POINTER(ConvDesc), _I, C.POINTER(_Z)]),
     "pcv_conv2d_bias_act_ws": (_I, [_P, C.POINTER(ConvDesc), _I, _P, _P, _P, _P, _P, _P, _P]),
     "pcv_bottleneck_tail_fusable": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvDesc), _I]),

@@ -540,17 +540,33 @@ cudaError_t IgemmOp::launch(cudaStream_t s) {
   }
 }
 
+// Is `d` served by the CTA-pair kernel (the one with the PCV_CONV_SE_GATE epilogue)?  Mirrors igemm_make's choice for aligned
+// operands: a dense 1x1 / k x k layer outside the halo and stem kernels, bf16/fp16 output through TMA stores.
+int igemm_gate_ok(const pcv_conv_desc& d) {
+  std::string why;
+  if (!igemm_supported(d, &why) || d.groups != 1 || (d.flags & (PCV_CONV_OUT_F32 | PCV_CONV_IN_OVERLAP | PCV_CONV_POOL3S2))) return 0;
+  if (d.kh != 1 || d.kw != 1 || d.stride != 1 || d.pad != 0) return 0;   // the unit's last 1x1 conv
+  const long long M = static_cast<long long>(d.N) * d.H * d.W;
+  if (pitch_or(d.out_pitch, d.Cout) % 8 || pitch_or(d.res_pitch, d.Cout) % 8 || d.Cout % 8 || d.Cout < 64) return 0;
+  const char* e = getenv("PCV_IGEMM_2CTA");
+  return !(e && e[0] == '0') && ceil_div(static_cast<int>(M), BLOCK_M) >= 2;
+}
+
 int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float* bias, const void* res, void* y,
-               Op** out) {
+               Op** out, const float* gate) {
   std::string why;
   if (!igemm_supported(d, &why)) return fail(PCV_ERR_UNSUPPORTED, "tcgen05 conv: %s", why.c_str());
-  {
+  if (gate == nullptr || !(d.flags & PCV_CONV_SE_GATE)) {
+    PCV_REQUIRE(gate == nullptr && !(d.flags & PCV_CONV_SE_GATE), "PCV_CONV_SE_GATE needs the gate in `workspace` (and only then)");
+  } else {
+    PCV_REQUIRE(igemm_gate_ok(d), "PCV_CONV_SE_GATE: this layer is not served by the gated-epilogue kernel (ask pcv_conv_se_gate_ok)");
+    PCV_REQUIRE(reinterpret_cast<uintptr_t>(gate) % 16 == 0, "the SE gate must be 16-byte aligned");
+  }
+  if (gate == nullptr) {
     const int rcs = stem_halo_try_make(d, x, w, bias, res, y, out);   // s2d stem with a 32-byte-row halo tile
     if (rcs != PCV_ERR_UNSUPPORTED) return rcs;
     if (d.flags & PCV_CONV_POOL3S2)
       return fail(PCV_ERR_UNSUPPORTED, "PCV_CONV_POOL3S2: this stem cannot take the fused max pool (ask pcv_stem_s2d_pool_ok)");
-  }
-  {
     const int rc3 = igemm3_try_make(d, x, w, bias, res, y, out);   // 3x3 stride-1 layers with a smem halo tile
     if (rc3 != PCV_ERR_UNSUPPORTED) return rc3;
   }
@@ -586,6 +602,8 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   p.act_lo = (d.act == PCV_ACT_RELU || d.act == PCV_ACT_RELU6) ? 0.f : -INFINITY;
   p.act_hi = d.act == PCV_ACT_RELU6 ? 6.f : INFINITY;
   p.act_a = d.act_param;
+  p.gate = gate;
+  p.n_img = d.N;
   p.has_res = res != nullptr;
   p.grouped = grouped;
   p.g_in_span = grouped ? 64 * (d.Cin / d.groups) / (d.Cout / d.groups) : 0;
@@ -616,6 +634,7 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
     return e ? atoi(e) : 64;
   }();
   op->pair = pair_enabled && p.out_mode == 0 && d.Cout >= pair_min_cout && d.Cout % 8 == 0 && p.tiles_m >= 2;
+  PCV_REQUIRE(gate == nullptr || op->pair, "PCV_CONV_SE_GATE: operands not aligned for the CTA-pair kernel");
   if (op->pair) {
     op->bn = grouped ? 64 : (d.Cout > 128 ? 256 : (d.Cout > 64 ? 128 : 64));
     igemm2_pick_smem(op->bn, p.num_kblocks, res != nullptr, taps, &p.stages, &p.ksub, &p.nstg);
@@ -703,14 +722,15 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
     else snprintf(cfg, sizeof cfg, " st%dx%d/%d", p.stages, p.ksub, p.nstg);
   }
   snprintf(nm, sizeof nm, "conv_tc%s %dx%d s%d d%d g%d %d->%d @%dx%d bn=%d%s%s%s", op->pair ? "2" : "", d.kh, d.kw,
-           d.stride, d.dil, d.groups, d.Cin, d.Cout, d.H, d.W, op->bn, cfg, res ? " +res" : "",
-           p.out_mode ? " direct" : "");
+           d.stride, d.dil, d.groups, d.Cin, d.Cout, d.H, d.W, op->bn, cfg, gate ? " *gate" : "", res ? " +res" : "");
+  if (p.out_mode) strncat(nm, " direct", sizeof nm - strlen(nm) - 1);
   op->name = nm;
   const double e = 2.0;
   const double pin = (taps == 1 && d.stride > 1) ? (double)Ho * Wo : (double)d.H * d.W;
   op->flops = 2.0 * p.M * d.Cout * (d.Cin / d.groups) * taps;
   op->bytes = e * d.N * d.Cin * pin + ((d.flags & PCV_CONV_OUT_F32) ? 4.0 : e) * p.M * d.Cout +
-              (res ? e * p.M * d.Cout : 0.0) + e * d.Cout * (d.Cin / d.groups) * taps + 4.0 * d.Cout;
+              (res ? e * p.M * d.Cout : 0.0) + e * d.Cout * (d.Cin / d.groups) * taps + 4.0 * d.Cout +
+              (gate ? 4.0 * d.N * d.Cout : 0.0);
   *out = op.release();
   return PCV_OK;
 }

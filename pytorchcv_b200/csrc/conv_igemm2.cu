@@ -311,6 +311,17 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
             for (int c = 0; c < 4; ++c) r4[c] = lds128(stg_u32 + ((row_off + c * 16) ^ sw));
           }
+          // SE scale in the epilogue (PCV_CONV_SE_GATE): the row's image picks the gate vector (the rows of a warp mostly share
+          // it: broadcast loads), fetched under the TMEM load like the bias
+          float4 g4[8];
+          if (p.gate != nullptr) {
+            const int m = (2 * pm + static_cast<int>(rank)) * BLOCK_M + row;
+            const int img = min(m / p.HoWo, p.n_img - 1);
+            const float4* gp = reinterpret_cast<const float4*>(p.gate + static_cast<size_t>(img) * p.Cout + n0 + col);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              g4[i] = (n0 + col + 4 * i < p.Cout) ? __ldg(gp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           tmem_ld_wait_regs(acc);
           float v[32];
 #pragma unroll
@@ -319,6 +330,12 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             v[4 * i + 1] = __uint_as_float(acc[4 * i + 1]) + b4[i].y;
             v[4 * i + 2] = __uint_as_float(acc[4 * i + 2]) + b4[i].z;
             v[4 * i + 3] = __uint_as_float(acc[4 * i + 3]) + b4[i].w;
+          }
+          if (p.gate != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[4 * i + 0] *= g4[i].x; v[4 * i + 1] *= g4[i].y; v[4 * i + 2] *= g4[i].z; v[4 * i + 3] *= g4[i].w;
+            }
           }
           if (p.has_res) {
 #pragma unroll

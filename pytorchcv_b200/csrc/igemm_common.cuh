@@ -26,6 +26,8 @@ struct IgemmParams {
   int act, has_res;
   float act_lo, act_hi;        // ReLU / ReLU6 / none as a clamp; other activations take the slow path
   float act_a;                 // PCV_ACT_LEAKY_RELU: negative slope
+  const float* gate;           // PCV_CONV_SE_GATE (pair kernel): fp32 [images][Cout], multiplies (acc + bias) before the residual
+  int n_img;                   // images (rows of `gate`)
   int a_mode;                 // 0: 2-D tiled [Cin, M]; 1: im2col 4-D
   int out_mode;               // 0: TMA bf16 store; 1: direct bf16; 2: direct fp32
   int grouped;                // 1: A channel window = n_tile*g_in_span (block-diagonal weights)

@@ -110,6 +110,11 @@ static int validate_conv(const pcv_conv_desc* d, int dtype) {
               "in_row_pitch smaller than a row");
   PCV_REQUIRE(!(d->flags & PCV_CONV_OUT_F32) || is16(dtype), "OUT_F32 only applies to the 16-bit tiers");
   PCV_REQUIRE(!(d->flags & PCV_CONV_F32_SPLIT) || dtype == PCV_F32, "F32_SPLIT only applies to the fp32 tier");
+  if (d->flags & PCV_CONV_SE_GATE) {
+    std::string why;
+    PCV_REQUIRE(is16(dtype) && conv_route(*d, dtype, &why) == ROUTE_IGEMM && bf::igemm_gate_ok(*d),
+                "PCV_CONV_SE_GATE: layer outside the gated-epilogue kernel's domain (ask pcv_conv_se_gate_ok)");
+  }
   PCV_REQUIRE(!(d->flags & PCV_CONV_POOL3S2) || ((d->flags & PCV_CONV_IN_OVERLAP) && is16(dtype)),
               "POOL3S2 only applies to the bf16 space-to-depth stem");
   if ((d->flags & PCV_CONV_IN_OVERLAP) || d->in_row_pitch != 0) {
@@ -179,6 +184,11 @@ int pcv_conv_workspace_bytes(const pcv_conv_desc* d, int dtype, size_t* bytes) {
   return PCV_OK;
 }
 
+int pcv_conv_se_gate_ok(const pcv_conv_desc* d, int dtype) {
+  if (!d || !is16(dtype) || !(d->flags & PCV_CONV_SE_GATE)) return 0;
+  return validate_conv(d, dtype) == PCV_OK ? 1 : 0;
+}
+
 int pcv_conv2d_bias_act_ws(pcv_plan* plan, const pcv_conv_desc* d, int dtype, const void* x, const void* w_packed,
                            const float* bias, const void* residual, void* y, void* workspace, pcv_stream stream) {
   if (int rc = validate_conv(d, dtype)) return rc;
@@ -187,7 +197,10 @@ int pcv_conv2d_bias_act_ws(pcv_plan* plan, const pcv_conv_desc* d, int dtype, co
   int rc;
   switch (conv_route(*d, dtype, nullptr)) {
     case ROUTE_DW: rc = dw_make(*d, dtype, x, w_packed, bias, residual, y, &op); break;
-    case ROUTE_IGEMM: rc = (dtype == PCV_F16 ? hf::igemm_make : bf::igemm_make)(*d, x, w_packed, bias, residual, y, &op); break;
+    case ROUTE_IGEMM:
+      rc = (dtype == PCV_F16 ? hf::igemm_make : bf::igemm_make)(*d, x, w_packed, bias, residual, y, &op,
+                                                                (d->flags & PCV_CONV_SE_GATE) ? static_cast<const float*>(workspace) : nullptr);
+      break;
     case ROUTE_SPLIT: rc = bf::igemm_split_make(*d, x, w_packed, bias, residual, y, workspace, &op); break;
     default: rc = simt_make(*d, dtype, x, w_packed, bias, residual, y, &op); break;
   }

@@ -123,7 +123,8 @@ EncodeIm2colFn encode_im2col_fn();
   int igemm_pack(const pcv_conv_desc& d, const float* w, const float* conv_bias, const float* g, const float* b,        \
                  const float* m, const float* v, float eps, void* w_packed, float* bias_out, cudaStream_t s);            \
   int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float* bias, const void* res, void* y,     \
-                 Op** out);                                                                                              \
+                 Op** out, const float* gate = nullptr);                                                                 \
+  int igemm_gate_ok(const pcv_conv_desc& d);                                                                             \
   /* window_tma.cu : TMA halo-staged 3x3 / 5x5 window ops (op_kind 0 = depthwise conv, 1 = max pool).  Returns */        \
   /* PCV_ERR_UNSUPPORTED (without touching the error message) for shapes the caller serves with its generic kernel. */   \
   int win_make(int op_kind, int N, int H, int W, int C, int k, int stride, int pad, int act, const void* x,              \

@@ -318,7 +318,8 @@ class Builder:
     # -- ops ----------------------------------------------------------------------------------------------------
     def conv(self, x: TRef, conv: nn.Conv2d, bn: nn.Module | None = None, act: int = ACT_NONE,
              residual: TRef | None = None, out: TRef | None = None, out_f32: bool = False, flags: int = 0,
-             pad_lrtb: tuple | None = None, act_a: float = 0.0, out_cmap: list | None = None) -> TRef:
+             pad_lrtb: tuple | None = None, act_a: float = 0.0, out_cmap: list | None = None,
+             gate: TRef | None = None) -> TRef | None:
         """One fused ConvBlock: conv + folded BN + optional residual + activation.  `pad_lrtb` = (left, right, top, bottom)
         replaces the conv's own padding (ZeroPad2d / tf_mode): symmetric amounts ride on the kernel's padding, asymmetric
         ones are materialised by one zero-pad pass."""
@@ -335,6 +336,8 @@ class Builder:
             else:
                 x = self.pad(x, pl, pr, pt, pb)
         cin, cout, groups = conv.in_channels, conv.out_channels, conv.groups
+        if gate is not None and (x.cmap is not None or out_cmap is not None or out is not None or not _is16(self.dtype)):
+            return None
         # virtual channel padding (TRef.cmap): the input's / output's real channels sit at given storage positions
         if x.cmap is not None or out_cmap is not None or (out is not None and out.C != cout):
             return self._conv_mapped(x, conv, bn, act, act_a, residual, out, out_cmap, k_stride, k_pad, k_dil, flags)
@@ -367,17 +370,26 @@ class Builder:
             # the fp32 tier's dense / grouped convs run on the tensor cores as a 3-way bf16 split (include/pcv_b200.h
             # PCV_CONV_F32_SPLIT); the library ignores the flag (CUDA-core kernel) for shapes the tcgen05 route cannot take
             flags |= _lib.CONV_F32_SPLIT
+        if gate is not None:
+            # SE scale + identity + activation in this conv's epilogue (include/pcv_b200.h PCV_CONV_SE_GATE); None when the layer
+            # is outside that kernel's domain - the caller then records the conv and the SE scale pass separately
+            flags |= _lib.CONV_SE_GATE
         d = ConvDesc(N=x.N, H=x.H, W=x.W, Cin=x.C, Cout=cout, kh=kh, kw=kw, stride=k_stride, pad=k_pad, dil=k_dil,
                      groups=groups, act=act, in_pitch=x.pitch, out_pitch=out.pitch,
                      res_pitch=residual.pitch if residual is not None else 0,
                      flags=flags | (_lib.CONV_OUT_F32 if (out_f32 and _is16(self.dtype)) else 0), act_param=act_a)
+        if gate is not None:
+            if (gate.C != cout or gate.N != x.N or gate.dtype != F32 or gate.cmap is not None
+                    or not _lib.load().pcv_conv_se_gate_ok(C.byref(d), self.dtype)):
+                self.bufs.remove(out.buf)   # nothing was recorded: drop the output buffer allocated above
+                return None
         wb, bb, ws = C.c_size_t(), C.c_size_t(), C.c_size_t()
         _lib.call("pcv_conv_packed_bytes", C.byref(d), self.dtype, C.byref(wb), C.byref(bb))
         _lib.call("pcv_conv_workspace_bytes", C.byref(d), self.dtype, C.byref(ws))
         w_off, b_off = self._wblob(wb.value), self._wblob(bb.value)
         self.weight_jobs.append(("conv", (d, conv, bn, pad_cin, w_off, b_off)))
-        idx = self._use(x, residual, out)
-        scratch = None
+        idx = self._use(x, residual, out, gate)
+        scratch = gate   # PCV_CONV_SE_GATE: the `workspace` argument carries the gate
         if ws.value:   # private to this op: lives exactly as long as op `idx`
             sbuf = Buf(nbytes=ws.value, first=idx, last=idx)
             self.bufs.append(sbuf)
@@ -1009,6 +1021,15 @@ def _lower_resunit(b, m, x, **kw):
     return lower(b, m.body, x, residual=identity, post_act=act_code(m.activ))
 
 
+# SE scale + identity + activation in the epilogue of the unit's last 1x1 conv (PCV_CONV_SE_GATE); PCV_SE_GATE_FUSE=0 keeps the
+# separate pcv_se_scale_add_act pass
+_SE_GATE_FUSE = [os.environ.get("PCV_SE_GATE_FUSE", "1") != "0"]
+
+
+def set_se_gate_fuse(enabled: bool) -> None:
+    _SE_GATE_FUSE[0] = bool(enabled)
+
+
 def _fold_conv3_into_se(conv3, se):
     """mean_HW(conv3(y)) == W3' mean_HW(y) + b3' for a 1x1 stride-1 ConvBlock without activation (BN folded into W3', b3'):
     returns (W1 W3', W1 b3' + b1) so that the SE squeeze can pool conv3's INPUT (fewer channels), or None."""
@@ -1053,9 +1074,16 @@ def _lower_seresnext_unit(b, m, x, **kw):
         return lower(b, se, y, identity=identity, post_act=act_code(m.activ))
     y2 = lower(b, body.conv2, lower(b, body.conv1, x))
     pooled = b.gap(y2, out_dtype=F32)
-    y3 = lower(b, body.conv3, y2)
     _, _, w2, b2, mid_act, out_act = _se_parts(b, se)
     gate = b.se_gate(pooled, folded[0], folded[1], w2, b2, mid_act, out_act)
+    # the gate exists BEFORE conv3 runs (it was squeezed from conv3's input), so the SE scale, the identity add and the unit's
+    # activation ride on conv3's epilogue: conv3's output and the scale pass's read of it never touch HBM
+    if _SE_GATE_FUSE[0]:
+        c3 = body.conv3
+        fused = b.conv(y2, c3.conv, c3.bn if c3.normalize else None, act_code(m.activ), residual=identity, gate=gate)
+        if fused is not None:
+            return fused
+    y3 = lower(b, body.conv3, y2)
     return b.se_scale(y3, gate, identity, act_code(m.activ))
 
 

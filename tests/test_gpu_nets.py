@@ -466,3 +466,38 @@ def test_batch_and_resolution_edges():
         B.conv3x3_block(in_channels=16, out_channels=8, padding=0).eval().cuda()(torch.zeros(1, 16, 2, 2).cuda())
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         blk(torch.zeros(1, 16, 8, 8))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tier,tol", [("bf16", 2e-2), ("fp16", 4e-3)])
+@pytest.mark.parametrize("kind,cin,cout,stride,shape", [
+    ("seresnext", 256, 256, 1, (3, 28, 28)),    # identity shortcut; 784 pixels per image: M tiles straddle image boundaries
+    ("seresnext", 256, 512, 2, (2, 28, 28)),    # projection shortcut, stride 2
+    ("seres", 64, 256, 1, (5, 19, 23)),         # SE-ResNet bottleneck, ragged map: 437 pixels per image
+])
+def test_se_gate_in_conv3_epilogue(kind, cin, cout, stride, shape, tier, tol):
+    """SEResNeXtUnit / SEResUnit (seresnext.py:57-66, seresnet.py:63-72) with the SE scale + identity + ReLU in the epilogue of
+    the unit's last 1x1 conv (PCV_CONV_SE_GATE) against the oracle and against the plan with the separate scale pass."""
+    from pytorchcv_b200 import nets as M, plan as PL
+    n, h, w = shape
+    if kind == "seresnext":
+        unit = M.SEResNeXtUnit(cin, cout, stride=stride, cardinality=32, bottleneck_width=4)
+    else:
+        unit = M.SEResUnit(cin, cout, stride=stride, bottleneck=True, conv1_stride=False)
+    unit = seeded_init(unit.eval(), seed=11, randomize_bn=True)
+    x = seeded_input((n, cin, h, w), seed=12)
+    want = oracle_forward(unit, x)
+    fast = P.accelerate(copy.deepcopy(unit).cuda(), dtype=tier, graph=False)
+    got = fast(x.cuda()).float().cpu()
+    names = [r[0] for r in fast.compiled(x.cuda()).profile()]
+    assert any("*gate" in nm for nm in names) and not any(nm.startswith("se_scale") for nm in names), names
+    PL.set_se_gate_fuse(False)
+    try:
+        base = P.accelerate(copy.deepcopy(unit).cuda(), dtype=tier, graph=False)
+        plain = base(x.cuda()).float().cpu()
+        assert any(nm.startswith("se_scale") for nm in [r[0] for r in base.compiled(x.cuda()).profile()])
+    finally:
+        PL.set_se_gate_fuse(True)
+    assert got.shape == want.shape and torch.isfinite(got).all()
+    assert _rel(got, want) <= tol, (_rel(got, want), names)
+    assert _rel(got, plain) <= tol, (_rel(got, plain), names)
