@@ -673,7 +673,7 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
       const char* e = getenv("PCV_IGEMM2_NARROW");
       return !(e && e[0] == '0');
     }();
-    p.nsubs = (narrow && !grouped) ? best : maxns;
+    p.nsubs = (narrow && !grouped && gate == nullptr) ? best : maxns;   // (the gated epilogue exists for full-width tiles)
     p.tiles_n = ceil_div(d.Cout, p.nsubs * 64);
     b_box_rows = p.nsubs * 32;   // each CTA of the pair loads half of the tile's weight rows
   }
