@@ -48,6 +48,9 @@ struct Igemm3Params {
   int WP8, stg_bytes;        // STAGED: pixels per staged image row (W rounded up to 8), bytes of one staging buffer
   float act_lo, act_hi;
   int dbg;                   // PCV_IGEMM3_DBG throughput experiments: 1 skip MMA issue, 2 skip epilogue math+stores, 4 skip A loads
+  int sub16;                 // grouped layers with <= 16 channels per group: the 64 x 64 block-diagonal weight block is four
+                             // 16 x 16 diagonal blocks, multiplied as four N = 16 MMAs (one K = 16 step each) instead of four
+                             // N = 64 MMAs over mostly-zero weights; a CTA's share of sub-block j is rows 16 j + 8 rank .. + 8
 };
 
 __device__ __forceinline__ void tma2_load_4d(const CUtensorMap* m, uint32_t mbar_cluster_addr, void* dst, int c0,
@@ -127,8 +130,14 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       if (rank == 0 && elect_one()) mbar_arrive_expect_tx(b_full, 2 * nb_blocks * p.b_block_bytes);
       for (int b = 0; b < nb_blocks; ++b) {
         const int g = b / (9 * p.cblocks), kb = b - g * 9 * p.cblocks;
-        if (elect_one())
+        if (p.sub16) {   // four 8-row boxes: this CTA's half of each 16 x 16 diagonal sub-block
+          for (int j = 0; j < 4; ++j)
+            if (elect_one())
+              tma2_load_2d(&tmB, bfull_leader, sB + b * p.b_block_bytes + j * 1024, kb * BLOCK_K,
+                           g * BN + 16 * j + 8 * static_cast<int>(rank));
+        } else if (elect_one()) {
           tma2_load_2d(&tmB, bfull_leader, sB + b * p.b_block_bytes, kb * BLOCK_K, g * BN + static_cast<int>(rank) * (BN / 2));
+        }
       }
       pdl_wait();   // weights above do not depend on the previous kernel; the activations below do
       int slot = 0;
@@ -193,7 +202,25 @@ igemm3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           for (int mb = 0; mb < ((p.dbg & 1) ? 0 : p.NMB); ++mb) {
             const uint32_t a_mb = a_buf + mb * (BLOCK_M * 128 >> 4);
             const uint32_t d_mb = d_tmem + mb * BN;
-            if (elect_one()) {
+            if (p.sub16) {
+              // four 16 x 16 diagonal sub-blocks: MMA j multiplies K step j of the pixels by rows 16 j .. 16 j + 15 of the
+              // weights into accumulator columns 16 j .. 16 j + 15
+              constexpr uint32_t idesc16 = make_idesc_e16(2 * BLOCK_M, 16);
+              if (elect_one()) {
+#pragma unroll
+                for (int fr = 0; fr < 3; ++fr) {
+                  const uint32_t a_row = a_mb + fr * row_step;
+#pragma unroll
+                  for (int fs = 0; fs < 3; ++fs) {
+                    const uint32_t a_lo = a_row + fs * (128 >> 4);
+                    const uint32_t b_lo = b_cb + (fr * 3 + fs) * tap_step;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                      umma2_bf16_lohi(d_mb + 16 * j, a_lo + 2 * j, b_lo + j * (1024 >> 4) + 2 * j, idesc16, (fr | fs) != 0 ? 1u : 0u);
+                  }
+                }
+              }
+            } else if (elect_one()) {
 #pragma unroll
               for (int fr = 0; fr < 3; ++fr) {
                 const uint32_t a_row = a_mb + fr * row_step;
@@ -411,6 +438,12 @@ int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const 
   p.a_buf_bytes = best_buf;
   p.a_tx_bytes = (bestR + 2) * PW * 128;
   p.b_block_bytes = b_block;
+  {
+    // PCV_IGEMM3_SUB16=0: the plain N = 64 block-diagonal MMAs
+    const char* e = getenv("PCV_IGEMM3_SUB16");
+    const int cg = grouped ? d.Cin / d.groups : 0;
+    p.sub16 = (grouped && cg <= 16 && 16 % cg == 0 && !(e && e[0] == '0')) ? 1 : 0;
+  }
   p.WP8 = WP8;
   p.stg_bytes = best_stg;
   p.act_lo = (d.act == PCV_ACT_RELU || d.act == PCV_ACT_RELU6) ? 0.f : -INFINITY;
@@ -440,7 +473,7 @@ int igemm3_try_make(const pcv_conv_desc& d, const void* x, const void* w, const 
     const uint64_t kpad = 9ull * cblocks * BLOCK_K;   // grouped: [Cout, 9 * 64] block-diagonal rows
     cuuint64_t dims[2] = {kpad, (cuuint64_t)d.Cout};
     cuuint64_t strides[1] = {kpad * 2};
-    cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)(BN / 2)};
+    cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)(p.sub16 ? 8 : BN / 2)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(&op->tmB, TMAP_E16, 2, const_cast<void*>(w), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
