@@ -172,6 +172,19 @@ PCV_API int pcv_exp_dw_pw_fused(pcv_plan* plan, const pcv_conv_desc* ex, const p
                                 const void* w_dw_packed, const float* bias_dw, const void* w_pw_packed, const float* bias_pw,
                                 const void* residual, void* y, pcv_stream stream);
 
+/* The end of a ResUnit with a projection shortcut - ResUnit.forward (resnet.py:225-233) when resize_identity:
+ *   identity = identity_conv(x)        (1x1 ConvBlock, stride s, no activation)
+ *   x = body(x); x = x + identity; x = activ(x)        with body ending in ResBottleneck.conv3 (linear 1x1 ConvBlock)
+ * as ONE GEMM over K-concatenated operands:  y = act([W3 | Wid] * [y2 ; x[::s]] + (b3 + bid)).  The identity tensor is never
+ * written: the kernel's TMA producer reads the k-blocks beyond d->Cin from the second activation `x2` through d2's (strided)
+ * 1x1 window.  d: the stride-1 1x1 conv over `x` (its act is the unit's activation), d2: the 1x1 shortcut conv over `x2`
+ * (stride 1 or 2, act none, same N / Cout / output grid).  w_cat_packed: for every output channel the row of d's packed
+ * weights followed by the row of d2's (both from pcv_pack_conv_weights, i.e. each padded to a multiple of 64 input channels);
+ * bias_sum = bias + bias2.  16-bit tiers; pcv_conv1x1_dual_ok returns 1 inside the kernel's domain (Cout > 128, dense). */
+PCV_API int pcv_conv1x1_dual_ok(const pcv_conv_desc* d, const pcv_conv_desc* d2, int dtype);
+PCV_API int pcv_conv1x1_dual(pcv_plan* plan, const pcv_conv_desc* d, const pcv_conv_desc* d2, int dtype, const void* x,
+                             const void* x2, const void* w_cat_packed, const float* bias_sum, void* y, pcv_stream stream);
+
 /* nn.ZeroPad2d((left, right, top, bottom)): the explicit asymmetric padding of a ConvBlock built with a 4-tuple `padding`
  * (conv.py:245-249,279-280) and of EfficientNet's tf_mode forwards (F.pad(x, calc_tf_padding(...)), efficientnet.py:27-55).
  * y is [N, H + top + bottom, W + left + right, C]; the convolution that follows runs with pad = 0. */

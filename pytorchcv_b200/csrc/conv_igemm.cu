@@ -552,17 +552,42 @@ int igemm_gate_ok(const pcv_conv_desc& d) {
   return !(e && e[0] == '0') && ceil_div(static_cast<int>(M), BLOCK_M) >= 2;
 }
 
+// Dual-source 1x1 conv (pcv_conv1x1_dual): y = act(W1 x1 + W2 x2[::s] + b) as ONE GEMM over the K-concatenated operands - a
+// bottleneck's last 1x1 conv with the unit's projection shortcut folded in.  `d` is the stride-1 conv over x1, `d2` the
+// (possibly strided) 1x1 conv over x2; both land on the same output grid.  Served by the CTA-pair kernel's 256-wide tile.
+int igemm_dual_ok(const pcv_conv_desc& d, const pcv_conv_desc& d2) {
+  std::string why;
+  if (!igemm_supported(d, &why) || !igemm_supported(d2, &why)) return 0;
+  auto plain1x1 = [](const pcv_conv_desc& c) {
+    return c.kh == 1 && c.kw == 1 && c.pad == 0 && c.groups == 1 && c.dil == 1 && c.in_row_pitch == 0 && c.Cin % 8 == 0 &&
+           pitch_or(c.in_pitch, c.Cin) % 8 == 0;
+  };
+  if (!plain1x1(d) || !plain1x1(d2) || d.stride != 1 || d2.stride < 1 || d2.stride > 2) return 0;
+  if ((d.flags | d2.flags) != 0 || d2.act != PCV_ACT_NONE) return 0;
+  if (d.N != d2.N || d.Cout != d2.Cout || conv_out(d2.H, 1, d2.stride, 0, 1) != d.H || conv_out(d2.W, 1, d2.stride, 0, 1) != d.W)
+    return 0;
+  if (d.Cout <= 128 || d.Cout % 8 || pitch_or(d.out_pitch, d.Cout) % 8) return 0;   // the 256-wide pair tile
+  const char* e = getenv("PCV_IGEMM_2CTA");
+  const long long M = static_cast<long long>(d.N) * d.H * d.W;
+  return !(e && e[0] == '0') && ceil_div(static_cast<int>(M), BLOCK_M) >= 2;
+}
+
 int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float* bias, const void* res, void* y,
-               Op** out, const float* gate) {
+               Op** out, const float* gate, const IgemmDual* dual) {
   std::string why;
   if (!igemm_supported(d, &why)) return fail(PCV_ERR_UNSUPPORTED, "tcgen05 conv: %s", why.c_str());
+  if (dual) {
+    PCV_REQUIRE(igemm_dual_ok(d, *dual->d2) && res == nullptr && gate == nullptr,
+                "pcv_conv1x1_dual: layer pair outside the dual-source kernel's domain (ask pcv_conv1x1_dual_ok)");
+    PCV_REQUIRE(dual->x2 && reinterpret_cast<uintptr_t>(dual->x2) % 16 == 0, "second source must be 16-byte aligned");
+  }
   if (gate == nullptr || !(d.flags & PCV_CONV_SE_GATE)) {
     PCV_REQUIRE(gate == nullptr && !(d.flags & PCV_CONV_SE_GATE), "PCV_CONV_SE_GATE needs the gate in `workspace` (and only then)");
   } else {
     PCV_REQUIRE(igemm_gate_ok(d), "PCV_CONV_SE_GATE: this layer is not served by the gated-epilogue kernel (ask pcv_conv_se_gate_ok)");
     PCV_REQUIRE(reinterpret_cast<uintptr_t>(gate) % 16 == 0, "the SE gate must be 16-byte aligned");
   }
-  if (gate == nullptr) {
+  if (gate == nullptr && dual == nullptr) {
     const int rcs = stem_halo_try_make(d, x, w, bias, res, y, out);   // s2d stem with a 32-byte-row halo tile
     if (rcs != PCV_ERR_UNSUPPORTED) return rcs;
     if (d.flags & PCV_CONV_POOL3S2)
@@ -597,6 +622,13 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   p.kw = d.kw;
   p.cblocks = grouped ? 1 : ceil_div(d.Cin, BLOCK_K);
   p.num_kblocks = taps * p.cblocks;
+  p.kb_split = p.a_mode2 = p.stride2 = 0;
+  if (dual) {
+    p.kb_split = p.cblocks;
+    p.num_kblocks += ceil_div(dual->d2->Cin, BLOCK_K);
+    p.stride2 = dual->d2->stride;
+    p.a_mode2 = dual->d2->stride > 1 ? 1 : 0;
+  }
   p.tiles_m = ceil_div(p.M, BLOCK_M);
   p.act = d.act;
   p.act_lo = (d.act == PCV_ACT_RELU || d.act == PCV_ACT_RELU6) ? 0.f : -INFINITY;
@@ -634,7 +666,7 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
     return e ? atoi(e) : 64;
   }();
   op->pair = pair_enabled && p.out_mode == 0 && d.Cout >= pair_min_cout && d.Cout % 8 == 0 && p.tiles_m >= 2;
-  PCV_REQUIRE(gate == nullptr || op->pair, "PCV_CONV_SE_GATE: operands not aligned for the CTA-pair kernel");
+  PCV_REQUIRE((gate == nullptr && dual == nullptr) || op->pair, "gated / dual-source conv: operands not aligned for the CTA-pair kernel");
   if (op->pair) {
     op->bn = grouped ? 64 : (d.Cout > 128 ? 256 : (d.Cout > 64 ? 128 : 64));
     igemm2_pick_smem(op->bn, p.num_kblocks, res != nullptr, taps, &p.stages, &p.ksub, &p.nstg);
@@ -673,7 +705,8 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
       const char* e = getenv("PCV_IGEMM2_NARROW");
       return !(e && e[0] == '0');
     }();
-    p.nsubs = (narrow && !grouped && gate == nullptr) ? best : maxns;   // (the gated epilogue exists for full-width tiles)
+    // (the gated epilogue and the dual-source producer exist for full-width tiles)
+    p.nsubs = (narrow && !grouped && gate == nullptr && dual == nullptr) ? best : maxns;
     p.tiles_n = ceil_div(d.Cout, p.nsubs * 64);
     b_box_rows = p.nsubs * 32;   // each CTA of the pair loads half of the tile's weight rows
   }
@@ -685,7 +718,7 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
     rc = make_tiled_2d(&op->tmA, x, d.Cin, p.M, (uint64_t)in_pitch * 2, BLOCK_K, BLOCK_M, CU_TENSOR_MAP_SWIZZLE_128B);
   }
   if (rc) return rc;
-  const uint64_t kpad = (uint64_t)taps * p.cblocks * BLOCK_K;
+  const uint64_t kpad = (uint64_t)p.num_kblocks * BLOCK_K;   // (dual-source: both weight blocks, K-concatenated per output row)
   rc = make_tiled_2d(&op->tmB, w, kpad, d.Cout, kpad * 2, BLOCK_K, b_box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   const int sub_cols = op->bn >= 64 ? 64 : op->bn;
@@ -695,6 +728,12 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
     if (rc) return rc;
     if (res) {
       rc = make_tiled_2d(&op->tmRes, res, d.Cout, p.M, (uint64_t)res_pitch * 2, sub_cols, BLOCK_M, oswz);
+      if (rc) return rc;
+    } else if (dual) {   // the second activation rides in the residual slot
+      const pcv_conv_desc& d2 = *dual->d2;
+      const int pitch2 = pitch_or(d2.in_pitch, d2.Cin);
+      if (p.a_mode2 == 1) rc = make_im2col_4d(&op->tmRes, dual->x2, d2, pitch2);
+      else rc = make_tiled_2d(&op->tmRes, dual->x2, d2.Cin, p.M, (uint64_t)pitch2 * 2, BLOCK_K, BLOCK_M, CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     } else {
       op->tmRes = op->tmOut;
@@ -721,8 +760,10 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
     if (p.nsubs * 64 != op->bn) snprintf(cfg, sizeof cfg, " tw=%d st%dx%d/%d", p.nsubs * 64, p.stages, p.ksub, p.nstg);
     else snprintf(cfg, sizeof cfg, " st%dx%d/%d", p.stages, p.ksub, p.nstg);
   }
-  snprintf(nm, sizeof nm, "conv_tc%s %dx%d s%d d%d g%d %d->%d @%dx%d bn=%d%s%s%s", op->pair ? "2" : "", d.kh, d.kw,
-           d.stride, d.dil, d.groups, d.Cin, d.Cout, d.H, d.W, op->bn, cfg, gate ? " *gate" : "", res ? " +res" : "");
+  char dl[48] = "";
+  if (dual) snprintf(dl, sizeof dl, " +1x1 s%d %d@%dx%d", dual->d2->stride, dual->d2->Cin, dual->d2->H, dual->d2->W);
+  snprintf(nm, sizeof nm, "conv_tc%s %dx%d s%d d%d g%d %d->%d @%dx%d bn=%d%s%s%s%s", op->pair ? "2" : "", d.kh, d.kw,
+           d.stride, d.dil, d.groups, d.Cin, d.Cout, d.H, d.W, op->bn, cfg, gate ? " *gate" : "", res ? " +res" : "", dl);
   if (p.out_mode) strncat(nm, " direct", sizeof nm - strlen(nm) - 1);
   op->name = nm;
   const double e = 2.0;
@@ -731,6 +772,10 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   op->bytes = e * d.N * d.Cin * pin + ((d.flags & PCV_CONV_OUT_F32) ? 4.0 : e) * p.M * d.Cout +
               (res ? e * p.M * d.Cout : 0.0) + e * d.Cout * (d.Cin / d.groups) * taps + 4.0 * d.Cout +
               (gate ? 4.0 * d.N * d.Cout : 0.0);
+  if (dual) {
+    op->flops += 2.0 * p.M * d.Cout * dual->d2->Cin;
+    op->bytes += e * p.M * dual->d2->Cin + e * d.Cout * dual->d2->Cin;
+  }
   *out = op.release();
   return PCV_OK;
 }

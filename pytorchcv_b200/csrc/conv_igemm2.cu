@@ -48,7 +48,7 @@ struct Pair {
   }
 };
 
-template <int BN, int NS, bool GATE>
+template <int BN, int NS, bool GATE, bool DUAL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
@@ -88,7 +88,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
-    if (p.has_res) tma_prefetch_desc(&tmRes);
+    if (p.has_res || DUAL) tma_prefetch_desc(&tmRes);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -152,6 +152,22 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           uint8_t* a_dst = sA + stage * KSUB * A_STAGE_BYTES;
           uint8_t* b_dst = sB + stage * KSUB * L::B_STAGE_BYTES;
           for (int j = 0; j < nsub; ++j) {
+            if (DUAL && kb + j >= p.kb_split) {
+              // second source (pcv_conv1x1_dual): the unit's input under the projection shortcut's (strided) 1x1 conv - its
+              // tensor map sits in the residual slot, its weights follow the first source's along K
+              if (elect_one()) {
+                const int c2 = (kb + j - p.kb_split) * BLOCK_K;
+                if (p.a_mode2 == 1) {
+                  tma2_load_im2col_4d(&tmRes, full_leader, a_dst, c2, wo * p.stride2, ho * p.stride2, img, 0, 0);
+                } else {
+                  tma2_load_2d(&tmRes, full_leader, a_dst, c2, m0);
+                }
+                tma2_load_2d(&tmB, full_leader, b_dst, (kb + j) * BLOCK_K, b_row);
+              }
+              a_dst += A_STAGE_BYTES;
+              b_dst += L::B_STAGE_BYTES;
+              continue;
+            }
             if (elect_one()) {
               if (p.a_mode == 1) {
                 tma2_load_im2col_4d(&tmA, full_leader, a_dst, c_base + cb * BLOCK_K, w0, h0, img,
@@ -391,14 +407,14 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   }
 }
 
-template <int BN, int NS, bool GATE>
+template <int BN, int NS, bool GATE, bool DUAL = false>
 static cudaError_t launch_pair_g(int grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                                  const CUtensorMap& tmRes, const IgemmParams& p, cudaStream_t s) {
   using L = Pair<BN, NS>;
   static std::atomic<uint64_t> attr_done{0};   // per device (see runtime.h)
-  if (cudaError_t e = set_max_smem_once(igemm2_kernel<BN, NS, GATE>, L::SMEM_LIMIT, attr_done)) return e;
-  return launch_pdl(igemm2_kernel<BN, NS, GATE>, dim3(grid), dim3(NUM_THREADS2), L::bytes(p.stages, p.ksub, p.nstg), s, tmA, tmB,
-                    tmOut, tmRes, p);
+  if (cudaError_t e = set_max_smem_once(igemm2_kernel<BN, NS, GATE, DUAL>, L::SMEM_LIMIT, attr_done)) return e;
+  return launch_pdl(igemm2_kernel<BN, NS, GATE, DUAL>, dim3(grid), dim3(NUM_THREADS2), L::bytes(p.stages, p.ksub, p.nstg), s, tmA,
+                    tmB, tmOut, tmRes, p);
 }
 // the gated epilogue (PCV_CONV_SE_GATE) is its own instantiation of the full-width tiles that SE units' last 1x1 convs use
 template <int BN, int NS>
@@ -406,9 +422,11 @@ static cudaError_t launch_pair(int grid, const CUtensorMap& tmA, const CUtensorM
                                const CUtensorMap& tmRes, const IgemmParams& p, cudaStream_t s) {
   if constexpr (NS * 64 == BN) {
     if (p.gate != nullptr) return launch_pair_g<BN, NS, true>(grid, tmA, tmB, tmOut, tmRes, p, s);
-  } else {
-    if (p.gate != nullptr) return cudaErrorInvalidValue;   // igemm_make keeps gated layers on full-width tiles
+    if constexpr (BN == 256) {   // the dual-source producer is instantiated for the tile the bottleneck tails use
+      if (p.kb_split > 0) return launch_pair_g<BN, NS, false, true>(grid, tmA, tmB, tmOut, tmRes, p, s);
+    }
   }
+  if (p.gate != nullptr || p.kb_split > 0) return cudaErrorInvalidValue;   // igemm_make keeps such layers on full-width 256 tiles
   return launch_pair_g<BN, NS, false>(grid, tmA, tmB, tmOut, tmRes, p, s);
 }
 

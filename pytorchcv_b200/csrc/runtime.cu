@@ -199,7 +199,7 @@ int pcv_conv2d_bias_act_ws(pcv_plan* plan, const pcv_conv_desc* d, int dtype, co
     case ROUTE_DW: rc = dw_make(*d, dtype, x, w_packed, bias, residual, y, &op); break;
     case ROUTE_IGEMM:
       rc = (dtype == PCV_F16 ? hf::igemm_make : bf::igemm_make)(*d, x, w_packed, bias, residual, y, &op,
-                                                                (d->flags & PCV_CONV_SE_GATE) ? static_cast<const float*>(workspace) : nullptr);
+                                                                (d->flags & PCV_CONV_SE_GATE) ? static_cast<const float*>(workspace) : nullptr, nullptr);
       break;
     case ROUTE_SPLIT: rc = bf::igemm_split_make(*d, x, w_packed, bias, residual, y, workspace, &op); break;
     default: rc = simt_make(*d, dtype, x, w_packed, bias, residual, y, &op); break;
@@ -274,6 +274,28 @@ int pcv_exp_dw_pw_fused(pcv_plan* plan, const pcv_conv_desc* ex, const pcv_conv_
   const int rc = (dtype == PCV_F16 ? hf::xdwpw_make : bf::xdwpw_make)(
       *ex, *dw, *pw, x, w_ex_packed, bias_ex, reinterpret_cast<const float*>(w_dw_packed), bias_dw, w_pw_packed, bias_pw,
       residual, y, &op);
+  if (rc) return rc;
+  return submit(plan, op, static_cast<cudaStream_t>(stream));
+}
+
+int pcv_conv1x1_dual_ok(const pcv_conv_desc* d, const pcv_conv_desc* d2, int dtype) {
+  if (!d || !d2 || !is16(dtype)) return 0;
+  if (validate_conv(d, dtype) != PCV_OK || validate_conv(d2, dtype) != PCV_OK) return 0;
+  std::string why;
+  if (conv_route(*d, dtype, &why) != ROUTE_IGEMM || conv_route(*d2, dtype, &why) != ROUTE_IGEMM) return 0;
+  return bf::igemm_dual_ok(*d, *d2);
+}
+
+int pcv_conv1x1_dual(pcv_plan* plan, const pcv_conv_desc* d, const pcv_conv_desc* d2, int dtype, const void* x, const void* x2,
+                     const void* w_cat_packed, const float* bias_sum, void* y, pcv_stream stream) {
+  if (int rc = validate_conv(d, dtype)) return rc;
+  if (int rc = validate_conv(d2, dtype)) return rc;
+  PCV_REQUIRE(is16(dtype), "the dual-source 1x1 conv exists in the 16-bit tiers only");
+  PCV_REQUIRE(x && x2 && w_cat_packed && bias_sum && y, "NULL tensor pointer");
+  PCV_REQUIRE(pcv_conv1x1_dual_ok(d, d2, dtype), "layer pair outside the dual-source kernel's domain (ask pcv_conv1x1_dual_ok)");
+  Op* op = nullptr;
+  const IgemmDual dual{d2, x2};
+  const int rc = (dtype == PCV_F16 ? hf::igemm_make : bf::igemm_make)(*d, x, w_cat_packed, bias_sum, nullptr, y, &op, nullptr, &dual);
   if (rc) return rc;
   return submit(plan, op, static_cast<cudaStream_t>(stream));
 }

@@ -115,6 +115,10 @@ EncodeIm2colFn encode_im2col_fn();
 // ---- launchers implemented in the .cu files --------------------------------------------------------------------
 // The tensor-core and TMA-window kernels exist once per 16-bit storage tier (ptx.cuh, "16-bit storage tier"): the same
 // sources compiled into pcv::bf (bf16) and pcv::hf (IEEE fp16).
+struct IgemmDual {   // second source of a dual-source 1x1 conv (pcv_conv1x1_dual): y = act(W1 x1 + W2 x2[::s] + b)
+  const pcv_conv_desc* d2;
+  const void* x2;
+};
 #define PCV_DECLARE_TIER_API(NS)                                                                                         \
   namespace NS {                                                                                                         \
   /* conv_igemm.cu : tcgen05 implicit GEMM (dense + block-diagonal grouped) */                                           \
@@ -123,8 +127,9 @@ EncodeIm2colFn encode_im2col_fn();
   int igemm_pack(const pcv_conv_desc& d, const float* w, const float* conv_bias, const float* g, const float* b,        \
                  const float* m, const float* v, float eps, void* w_packed, float* bias_out, cudaStream_t s);            \
   int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float* bias, const void* res, void* y,     \
-                 Op** out, const float* gate = nullptr);                                                                 \
+                 Op** out, const float* gate = nullptr, const IgemmDual* dual = nullptr);                                \
   int igemm_gate_ok(const pcv_conv_desc& d);                                                                             \
+  int igemm_dual_ok(const pcv_conv_desc& d, const pcv_conv_desc& d2);                                                    \
   /* window_tma.cu : TMA halo-staged 3x3 / 5x5 window ops (op_kind 0 = depthwise conv, 1 = max pool).  Returns */        \
   /* PCV_ERR_UNSUPPORTED (without touching the error message) for shapes the caller serves with its generic kernel. */   \
   int win_make(int op_kind, int N, int H, int W, int C, int k, int stride, int pad, int act, const void* x,              \

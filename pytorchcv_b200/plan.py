@@ -403,6 +403,51 @@ class Builder:
         self.ops.append(emit)
         return out
 
+    def conv_dual(self, x: TRef, cb: nn.Module, x2: TRef, cb2: nn.Module, act: int) -> TRef | None:
+        """act(cb(x) + cb2(x2)) for two linear 1x1 ConvBlocks as ONE GEMM over K-concatenated operands (include/pcv_b200.h
+        pcv_conv1x1_dual): a bottleneck's conv3 with the unit's projection shortcut folded in - the identity tensor is never
+        written.  None when the pair is outside that kernel's domain."""
+        if not _DUAL_IDENTITY[0] or not _is16(self.dtype) or x.cmap is not None or x2.cmap is not None:
+            return None
+        for m in (cb, cb2):
+            c = getattr(m, "conv", None)
+            if (type(m).__name__ != "ConvBlock" or m.activate or getattr(m, "use_pad", False) or c is None
+                    or c.kernel_size != (1, 1) or c.groups != 1 or c.padding_mode != "zeros" or isinstance(c.padding, str)):
+                return None
+        c1, c2 = cb.conv, cb2.conv
+        try:
+            s1, p1, s2, p2 = _one(c1.stride), _one(c1.padding), _one(c2.stride), _one(c2.padding)
+        except NotImplementedError:
+            return None
+        if (s1, p1, p2) != (1, 0, 0) or c1.in_channels != x.C or c2.in_channels != x2.C or c1.out_channels != c2.out_channels:
+            return None
+        cout = c1.out_channels
+        d = ConvDesc(N=x.N, H=x.H, W=x.W, Cin=x.C, Cout=cout, kh=1, kw=1, stride=1, pad=0, dil=1, groups=1, act=act,
+                     in_pitch=x.pitch, out_pitch=cout, res_pitch=0, flags=0)
+        d2 = ConvDesc(N=x2.N, H=x2.H, W=x2.W, Cin=x2.C, Cout=cout, kh=1, kw=1, stride=s2, pad=0, dil=1, groups=1,
+                      act=ACT_NONE, in_pitch=x2.pitch, out_pitch=cout, res_pitch=0, flags=0)
+        if not _lib.load().pcv_conv1x1_dual_ok(C.byref(d), C.byref(d2), self.dtype):
+            return None
+        for m in (cb, cb2):
+            if m.normalize:
+                _check_bn(m.bn)
+        out = self.new(x.N, x.H, x.W, cout)
+        sizes = []
+        for dd in (d, d2):
+            wb, bb = C.c_size_t(), C.c_size_t()
+            _lib.call("pcv_conv_packed_bytes", C.byref(dd), self.dtype, C.byref(wb), C.byref(bb))
+            sizes.append((wb.value, bb.value))
+        w_off, b_off = self._wblob(sizes[0][0] + sizes[1][0]), self._wblob(sizes[0][1])
+        self.weight_jobs.append(("conv_dual", (d, cb, d2, cb2, sizes, w_off, b_off)))
+        self._use(x, x2, out)
+        dtype = self.dtype
+
+        def emit(plan, ptr, wptr):
+            _lib.call("pcv_conv1x1_dual", plan, C.byref(d), C.byref(d2), dtype, ptr(x), ptr(x2), wptr(w_off), wptr(b_off),
+                      ptr(out), None)
+        self.ops.append(emit)
+        return out
+
     def _conv_mapped(self, x: TRef, conv, bn, act: int, act_a: float, residual: TRef | None, out: TRef | None,
                      out_cmap: list | None, k_stride: int, k_pad: int, k_dil: int, flags: int) -> TRef:
         """A dense or depthwise conv whose input and / or output carries virtual channel padding (TRef.cmap).  The weights are
@@ -1014,11 +1059,31 @@ def _lower_resbody(b, m, x, residual=None, post_act=None, **kw):
     return lower(b, convs[-1], x, residual=residual, post_act=post_act)
 
 
+# A unit's projection shortcut folded into its last 1x1 conv (pcv_conv1x1_dual); PCV_DUAL_IDENTITY=0 keeps the separate
+# identity_conv kernel and the residual add in conv3's epilogue
+_DUAL_IDENTITY = [os.environ.get("PCV_DUAL_IDENTITY", "1") != "0"]
+
+
+def set_dual_identity(enabled: bool) -> None:
+    _DUAL_IDENTITY[0] = bool(enabled)
+
+
 @lowers("ResUnit", "ResNeXtUnit")
 def _lower_resunit(b, m, x, **kw):
-    """ResUnit.forward (resnet.py:221-229): act(body(x) + (identity_conv(x) | x))."""
+    """ResUnit.forward (resnet.py:221-229): act(body(x) + (identity_conv(x) | x)).
+
+    With a projection shortcut behind a bottleneck body, conv3 and identity_conv are both linear 1x1 ConvBlocks landing on the
+    same grid: act(W3 y2 + b3 + Wid x[::s] + bid) is one GEMM over [y2 ; x[::s]] (Builder.conv_dual)."""
+    body = m.body
+    if (m.resize_identity and _DUAL_IDENTITY[0] and _is16(b.dtype) and hasattr(body, "conv3")
+            and type(body).__name__ in ("ResBottleneck", "ResNeXtBottleneck") and not _FUSE_TAIL[0]):
+        y2 = lower(b, body.conv2, lower(b, body.conv1, x))
+        fused = b.conv_dual(y2, body.conv3, x, m.identity_conv, act_code(m.activ))
+        if fused is not None:
+            return fused
+        return lower(b, body.conv3, y2, residual=lower(b, m.identity_conv, x), post_act=act_code(m.activ))
     identity = lower(b, m.identity_conv, x) if m.resize_identity else x
-    return lower(b, m.body, x, residual=identity, post_act=act_code(m.activ))
+    return lower(b, body, x, residual=identity, post_act=act_code(m.activ))
 
 
 # SE scale + identity + activation in the epilogue of the unit's last 1x1 conv (PCV_CONV_SE_GATE); PCV_SE_GATE_FUSE=0 keeps the
@@ -1721,6 +1786,9 @@ class CompiledModule:
             if kind == "conv_mapped":
                 self._pack_mapped(payload, keep, stream, wptr)
                 continue
+            if kind == "conv_dual":
+                self._pack_dual(payload, keep, stream, wptr)
+                continue
             if kind == "conv_s2d":
                 d, conv, bn, k, w_off, b_off = payload
                 w0 = self._dev_f32(conv.weight)
@@ -1750,6 +1818,38 @@ class CompiledModule:
                       eps, wptr(w_off), wptr(b_off), stream)
         torch.cuda.synchronize(self.device)
         del keep
+
+    def _pack_one(self, d, conv, bn, w_ptr: int, b_ptr: int, keep, stream) -> None:
+        """pcv_pack_conv_weights of one ConvBlock's conv (+ BatchNorm, folded by the library) at explicit device addresses."""
+        w, cb = self._dev_f32(conv.weight), self._dev_f32(conv.bias)
+        g = be = mu = var = None
+        eps = 0.0
+        if bn is not None:
+            g = self._dev_f32(bn.weight) if bn.weight is not None else torch.ones_like(self._dev_f32(bn.running_var))
+            be = self._dev_f32(bn.bias) if bn.bias is not None else torch.zeros_like(g)
+            mu, var, eps = self._dev_f32(bn.running_mean), self._dev_f32(bn.running_var), float(bn.eps)
+        keep += [w, cb, g, be, mu, var]
+        _lib.call("pcv_pack_conv_weights", C.byref(d), self.dtype, w.data_ptr(), cb.data_ptr() if cb is not None else None,
+                  g.data_ptr() if g is not None else None, be.data_ptr() if be is not None else None,
+                  mu.data_ptr() if mu is not None else None, var.data_ptr() if var is not None else None, eps, w_ptr, b_ptr,
+                  stream)
+
+    def _pack_dual(self, payload, keep, stream, wptr) -> None:
+        """Weights of Builder.conv_dual: both 1x1 convs packed as usual, then joined row by row along K; biases summed."""
+        d, cb, d2, cb2, sizes, w_off, b_off = payload
+        parts = []
+        for dd, m, (wn, bn_) in ((d, cb, sizes[0]), (d2, cb2, sizes[1])):
+            wt = torch.empty(wn, dtype=torch.uint8, device=self.device)
+            bt = torch.empty(bn_ // 4, dtype=torch.float32, device=self.device)
+            self._pack_one(dd, m.conv, m.bn if m.normalize else None, wt.data_ptr(), bt.data_ptr(), keep, stream)
+            parts.append((wt.view(d.Cout, -1), bt))
+        joined = torch.cat([parts[0][0], parts[1][0]], dim=1).contiguous().view(-1)
+        bias = (parts[0][1] + parts[1][1]).view(torch.uint8).view(-1)
+        keep += [joined, bias]
+        rel = wptr(w_off) - self.weights.data_ptr()
+        self.weights[rel:rel + joined.numel()].copy_(joined)
+        rel = wptr(b_off) - self.weights.data_ptr()
+        self.weights[rel:rel + bias.numel()].copy_(bias)
 
     def _pack_mapped(self, payload, keep, stream, wptr) -> None:
         """Weights of a conv with virtual channel padding (Builder._conv_mapped): scatter into the storage channel space."""

@@ -501,3 +501,41 @@ def test_se_gate_in_conv3_epilogue(kind, cin, cout, stride, shape, tier, tol):
     assert got.shape == want.shape and torch.isfinite(got).all()
     assert _rel(got, want) <= tol, (_rel(got, want), names)
     assert _rel(got, plain) <= tol, (_rel(got, plain), names)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tier,tol", [("bf16", 2e-2), ("fp16", 4e-3)])
+@pytest.mark.parametrize("kind,cin,cout,stride,shape", [
+    ("res", 64, 256, 1, (4, 56, 56)),       # ResNet-50 stage 1: stride-1 shortcut read as a plain 2-D tile
+    ("res", 256, 512, 2, (3, 56, 56)),      # stage 2: strided shortcut through the im2col window; tiles straddle images
+    ("res", 1024, 2048, 2, (5, 14, 14)),    # stage 4: 49 pixels per image, the second M tile is partial
+    ("res", 256, 512, 2, (2, 27, 31)),      # odd map: 14 x 16 outputs, the shortcut's last row / column never read
+    ("res", 72, 288, 2, (3, 20, 20)),       # channel counts off the 64-wide k-block: zero-filled tails on both sources
+    ("resnext", 256, 512, 2, (2, 28, 28)),  # ResNeXtUnit: grouped conv2 in front of the dual conv3
+])
+def test_projection_shortcut_in_conv3(kind, cin, cout, stride, shape, tier, tol):
+    """ResUnit / ResNeXtUnit (resnet.py:221-229, resnext.py:117-125) with a projection shortcut: conv3 and identity_conv as one
+    K-concatenated GEMM (pcv_conv1x1_dual) against the oracle and against the plan with the separate identity conv."""
+    from pytorchcv_b200 import nets as M, plan as PL
+    n, h, w = shape
+    if kind == "res":
+        unit = M.ResUnit(cin, cout, stride=stride, bottleneck=True, conv1_stride=False)
+    else:
+        unit = M.ResNeXtUnit(cin, cout, stride=stride, cardinality=32, bottleneck_width=4)
+    unit = seeded_init(unit.eval(), seed=21, randomize_bn=True)
+    x = seeded_input((n, cin, h, w), seed=22)
+    want = oracle_forward(unit, x)
+    fast = P.accelerate(copy.deepcopy(unit).cuda(), dtype=tier, graph=False)
+    got = fast(x.cuda()).float().cpu()
+    names = [r[0] for r in fast.compiled(x.cuda()).profile()]
+    assert sum("+1x1 s" in nm for nm in names) == 1 and not any("+res" in nm for nm in names), names
+    PL.set_dual_identity(False)
+    try:
+        base = P.accelerate(copy.deepcopy(unit).cuda(), dtype=tier, graph=False)
+        plain = base(x.cuda()).float().cpu()
+        assert any("+res" in nm for nm in [r[0] for r in base.compiled(x.cuda()).profile()])
+    finally:
+        PL.set_dual_identity(True)
+    assert got.shape == want.shape and torch.isfinite(got).all()
+    assert _rel(got, want) <= tol, (_rel(got, want), names)
+    assert _rel(got, plain) <= tol, (_rel(got, plain), names)
