@@ -670,6 +670,13 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   if (op->pair) {
     op->bn = grouped ? 64 : (d.Cout > 128 ? 256 : (d.Cout > 64 ? 128 : 64));
     igemm2_pick_smem(op->bn, p.num_kblocks, res != nullptr, taps, &p.stages, &p.ksub, &p.nstg);
+    if (dual) {
+      // measured on ResNet-50's four projection units (profiles/README.md, "dual-source ring sweep"): 2 k-blocks keep the
+      // picker's 2x2/6; 6 k-blocks: 5x1/4 110 -> 96 us; 12 and 24 k-blocks: 3x2/2 82 -> 77 us and 81 -> 74 us
+      if (p.num_kblocks >= 9) p.stages = 3, p.ksub = 2, p.nstg = 2;
+      else if (p.num_kblocks >= 3) p.stages = 5, p.ksub = 1, p.nstg = 4;
+      if (const char* e = getenv("PCV_IGEMM2_DUAL_CFG")) sscanf(e, "%d,%d,%d", &p.stages, &p.ksub, &p.nstg);
+    }
   }
   p.tiles_n = ceil_div(d.Cout, op->bn);
   p.nsubs = 1;
