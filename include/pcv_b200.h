@@ -172,7 +172,7 @@ PCV_API int pcv_exp_dw_pw_fused(pcv_plan* plan, const pcv_conv_desc* ex, const p
                                 const void* w_dw_packed, const float* bias_dw, const void* w_pw_packed, const float* bias_pw,
                                 const void* residual, void* y, pcv_stream stream);
 
-/* The end of a ResUnit with a projection shortcut - ResUnit.forward (resnet.py:225-233) when resize_identity:
+/* The end of a ResUnit with a projection shortcut - ResUnit.forward (resnet.py:221-229) when resize_identity:
  *   identity = identity_conv(x)        (1x1 ConvBlock, stride s, no activation)
  *   x = body(x); x = x + identity; x = activ(x)        with body ending in ResBottleneck.conv3 (linear 1x1 ConvBlock)
  * as ONE GEMM over K-concatenated operands:  y = act([W3 | Wid] * [y2 ; x[::s]] + (b3 + bid)).  The identity tensor is never

@@ -112,7 +112,7 @@ def res_body(m, x):
 
 
 def res_unit(m, x):
-    """ResUnit.forward (resnet.py:221-229) and ResNeXtUnit.forward (resnext.py:102-110)."""
+    """ResUnit.forward (resnet.py:221-229) and ResNeXtUnit.forward (resnext.py:108-116)."""
     identity = conv_block(m.identity_conv, x) if m.resize_identity else x
     x = res_body(m.body, x)
     x = x + identity

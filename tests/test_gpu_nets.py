@@ -514,7 +514,7 @@ def test_se_gate_in_conv3_epilogue(kind, cin, cout, stride, shape, tier, tol):
     ("resnext", 256, 512, 2, (2, 28, 28)),  # ResNeXtUnit: grouped conv2 in front of the dual conv3
 ])
 def test_projection_shortcut_in_conv3(kind, cin, cout, stride, shape, tier, tol):
-    """ResUnit / ResNeXtUnit (resnet.py:221-229, resnext.py:117-125) with a projection shortcut: conv3 and identity_conv as one
+    """ResUnit / ResNeXtUnit (resnet.py:221-229, resnext.py:108-116) with a projection shortcut: conv3 and identity_conv as one
     K-concatenated GEMM (pcv_conv1x1_dual) against the oracle and against the plan with the separate identity conv."""
     from pytorchcv_b200 import nets as M, plan as PL
     n, h, w = shape
