@@ -66,6 +66,34 @@ def test_packed_sizes_follow_route():
     assert wb.value == 256 * 9 * 4                                          # depthwise: fp32 [tap][C]
 
 
+def test_dual_source_conv_domain():
+    """pcv_conv1x1_dual_ok (host logic only): ResNet-50's four projection units are inside the dual-source kernel's domain in
+    both 16-bit tiers; narrow outputs, the fp32 tier, mismatched grids and an activated shortcut conv are not."""
+    from pytorchcv_b200._lib import F16
+    lib = _lib.load()
+
+    def pair(cin, mid, cout, stride, hw, n=256, **kw2):
+        ho = (hw - 1) // stride + 1
+        d = _lib.ConvDesc(N=n, H=ho, W=ho, Cin=mid, Cout=cout, kh=1, kw=1, stride=1, pad=0, dil=1, groups=1, act=_lib.ACT_RELU)
+        f2 = dict(N=n, H=hw, W=hw, Cin=cin, Cout=cout, kh=1, kw=1, stride=stride, pad=0, dil=1, groups=1, act=_lib.ACT_NONE)
+        f2.update(kw2)
+        return d, _lib.ConvDesc(**f2)
+
+    for cin, mid, cout, stride, hw in [(64, 64, 256, 1, 56), (256, 128, 512, 2, 56), (512, 256, 1024, 2, 28), (1024, 512, 2048, 2, 14)]:
+        d, d2 = pair(cin, mid, cout, stride, hw)
+        for tier in (BF16, F16):
+            assert lib.pcv_conv1x1_dual_ok(ctypes.byref(d), ctypes.byref(d2), tier) == 1, (cin, cout, tier)
+        assert lib.pcv_conv1x1_dual_ok(ctypes.byref(d), ctypes.byref(d2), F32) == 0
+    for bad in (pair(64, 32, 128, 1, 56),                       # Cout <= 128: not the 256-wide pair tile
+                pair(256, 128, 512, 2, 56, act=_lib.ACT_RELU),  # the shortcut conv must be linear
+                pair(256, 128, 512, 2, 56, N=128),              # different batch
+                pair(256, 128, 512, 2, 56, H=54, W=54),         # grids do not meet
+                pair(256, 128, 512, 2, 56, Cout=256),           # widths do not meet
+                pair(1024, 512, 2048, 2, 14, n=2)):             # a single 128-row tile: outside the CTA-pair kernel
+        assert lib.pcv_conv1x1_dual_ok(ctypes.byref(bad[0]), ctypes.byref(bad[1]), BF16) == 0
+    assert lib.pcv_conv1x1_dual_ok(None, None, BF16) == 0
+
+
 def test_get_model_contract():
     assert isinstance(P.get_model("ResNet18"), nn.Module)                   # case-insensitive (model_provider.py:1378)
     with pytest.raises(ValueError, match="Unsupported model"):
