@@ -184,6 +184,14 @@ PCV_API int pcv_exp_dw_pw_fused(pcv_plan* plan, const pcv_conv_desc* ex, const p
 PCV_API int pcv_conv1x1_dual_ok(const pcv_conv_desc* d, const pcv_conv_desc* d2, int dtype);
 PCV_API int pcv_conv1x1_dual(pcv_plan* plan, const pcv_conv_desc* d, const pcv_conv_desc* d2, int dtype, const void* x,
                              const void* x2, const void* w_cat_packed, const float* bias_sum, void* y, pcv_stream stream);
+/* The same for an SE unit with a projection shortcut - SEResNeXtUnit.forward (seresnext.py:57-66), SEResUnit (seresnet.py:63-72):
+ *   y = act((W3 * y2 + bias) * gate[n, c] + (Wid * x[::s] + bias2))
+ * d carries PCV_CONV_SE_GATE; the gate (fp32 [N][Cout], as for pcv_conv2d_bias_act_ws) multiplies conv3's half of the sum only,
+ * so the kernel keeps the two halves in two TMEM accumulators (128-wide tiles) and the biases stay separate.  Same weight layout
+ * and domain query (pcv_conv1x1_dual_ok with the flag set on d). */
+PCV_API int pcv_conv1x1_dual_se(pcv_plan* plan, const pcv_conv_desc* d, const pcv_conv_desc* d2, int dtype, const void* x,
+                                const void* x2, const void* w_cat_packed, const float* bias, const float* bias2,
+                                const float* gate, void* y, pcv_stream stream);
 
 /* nn.ZeroPad2d((left, right, top, bottom)): the explicit asymmetric padding of a ConvBlock built with a 4-tuple `padding`
  * (conv.py:245-249,279-280) and of EfficientNet's tf_mode forwards (F.pad(x, calc_tf_padding(...)), efficientnet.py:27-55).

@@ -55,6 +55,7 @@ SIGNATURES = {
     "pcv_dw_pw_fused": (_I, [_P, C.POINTER(ConvDesc), C.POINTER(ConvDesc), _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pcv_conv1x1_dual_ok": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvDesc), _I]),
     "pcv_conv1x1_dual": (_I, [_P, C.POINTER(ConvDesc), C.POINTER(ConvDesc), _I, _P, _P, _P, _P, _P, _P]),
+    "pcv_conv1x1_dual_se": (_I, [_P, C.POINTER(ConvDesc), C.POINTER(ConvDesc), _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pcv_exp_dw_pw_fusable": (_I, [C.POINTER(ConvDesc), C.POINTER(ConvDesc), C.POINTER(ConvDesc), _I]),
     "pcv_exp_dw_pw_fused": (_I, [_P, C.POINTER(ConvDesc), C.POINTER(ConvDesc), C.POINTER(ConvDesc), _I, _P, _P, _P, _P, _P, _P,
                                 _P, _P, _P, _P]),

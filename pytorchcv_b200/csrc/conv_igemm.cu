@@ -563,7 +563,8 @@ int igemm_dual_ok(const pcv_conv_desc& d, const pcv_conv_desc& d2) {
            pitch_or(c.in_pitch, c.Cin) % 8 == 0;
   };
   if (!plain1x1(d) || !plain1x1(d2) || d.stride != 1 || d2.stride < 1 || d2.stride > 2) return 0;
-  if ((d.flags | d2.flags) != 0 || d2.act != PCV_ACT_NONE) return 0;
+  // (PCV_CONV_SE_GATE on d: the gated variant - the shortcut's half of the sum lives in a second accumulator, outside the gate)
+  if ((d.flags & ~PCV_CONV_SE_GATE) != 0 || d2.flags != 0 || d2.act != PCV_ACT_NONE) return 0;
   if (d.N != d2.N || d.Cout != d2.Cout || conv_out(d2.H, 1, d2.stride, 0, 1) != d.H || conv_out(d2.W, 1, d2.stride, 0, 1) != d.W)
     return 0;
   if (d.Cout <= 128 || d.Cout % 8 || pitch_or(d.out_pitch, d.Cout) % 8) return 0;   // the 256-wide pair tile
@@ -577,8 +578,9 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   std::string why;
   if (!igemm_supported(d, &why)) return fail(PCV_ERR_UNSUPPORTED, "tcgen05 conv: %s", why.c_str());
   if (dual) {
-    PCV_REQUIRE(igemm_dual_ok(d, *dual->d2) && res == nullptr && gate == nullptr,
+    PCV_REQUIRE(igemm_dual_ok(d, *dual->d2) && res == nullptr,
                 "pcv_conv1x1_dual: layer pair outside the dual-source kernel's domain (ask pcv_conv1x1_dual_ok)");
+    PCV_REQUIRE((gate != nullptr) == (dual->bias2 != nullptr), "the gated dual-source conv takes the shortcut's bias separately");
     PCV_REQUIRE(dual->x2 && reinterpret_cast<uintptr_t>(dual->x2) % 16 == 0, "second source must be 16-byte aligned");
   }
   if (gate == nullptr || !(d.flags & PCV_CONV_SE_GATE)) {
@@ -623,6 +625,7 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
   p.cblocks = grouped ? 1 : ceil_div(d.Cin, BLOCK_K);
   p.num_kblocks = taps * p.cblocks;
   p.kb_split = p.a_mode2 = p.stride2 = 0;
+  p.bias2 = dual ? dual->bias2 : nullptr;
   if (dual) {
     p.kb_split = p.cblocks;
     p.num_kblocks += ceil_div(dual->d2->Cin, BLOCK_K);
@@ -714,6 +717,7 @@ int igemm_make(const pcv_conv_desc& d, const void* x, const void* w, const float
     }();
     // (the gated epilogue and the dual-source producer exist for full-width tiles)
     p.nsubs = (narrow && !grouped && gate == nullptr && dual == nullptr) ? best : maxns;
+    if (gate != nullptr && dual != nullptr) p.nsubs = 2;   // two 128-column accumulators per TMEM buffer (conv_igemm2.cu)
     p.tiles_n = ceil_div(d.Cout, p.nsubs * 64);
     b_box_rows = p.nsubs * 32;   // each CTA of the pair loads half of the tile's weight rows
   }

@@ -216,9 +216,17 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           uint32_t a_lo = a_lo0 + stage * KSUB * (A_STAGE_BYTES >> 4);
           uint32_t b_lo = b_lo0 + stage * KSUB * (L::B_STAGE_BYTES >> 4);
           for (int j = 0; j < nsub; ++j) {
+            uint32_t d_acc = d_tmem, acc0 = accum;
+            if constexpr (GATE && DUAL) {
+              // gated unit with a projection shortcut: the SE gate multiplies conv3's half of the sum only, so the shortcut's
+              // k-blocks accumulate into a SECOND accumulator (columns TW .. 2 TW of the buffer) that the epilogue adds un-gated
+              static_assert(2 * TW <= BN, "two accumulators per TMEM buffer");
+              if (kb + j >= p.kb_split) d_acc = d_tmem + TW;
+              if (kb + j == p.kb_split) acc0 = 0;
+            }
             if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < BLOCK_K / 16; ++k) umma2_bf16_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, k ? 1u : accum);
+              for (int k = 0; k < BLOCK_K / 16; ++k) umma2_bf16_lohi(d_acc, a_lo + 2 * k, b_lo + 2 * k, idesc, k ? 1u : acc0);
             }
             accum = 1;
             a_lo += A_STAGE_BYTES >> 4;
@@ -355,6 +363,21 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               v[4 * i + 0] *= g4[i].x; v[4 * i + 1] *= g4[i].y; v[4 * i + 2] *= g4[i].z; v[4 * i + 3] *= g4[i].w;
             }
           }
+          if constexpr (GATE && DUAL) {
+            // + the projection shortcut from the second accumulator (and its own folded bias), outside the gate
+            uint32_t acc2[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + TW + col, acc2);
+            const float4* bias24 = reinterpret_cast<const float4*>(p.bias2 + n0 + col);
+            tmem_ld_wait_regs(acc2);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b2 = (n0 + col + 4 * i < p.Cout) ? __ldg(bias24 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+              v[4 * i + 0] += __uint_as_float(acc2[4 * i + 0]) + b2.x;
+              v[4 * i + 1] += __uint_as_float(acc2[4 * i + 1]) + b2.y;
+              v[4 * i + 2] += __uint_as_float(acc2[4 * i + 2]) + b2.z;
+              v[4 * i + 3] += __uint_as_float(acc2[4 * i + 3]) + b2.w;
+            }
+          }
           if (p.has_res) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -420,10 +443,13 @@ static cudaError_t launch_pair_g(int grid, const CUtensorMap& tmA, const CUtenso
 template <int BN, int NS>
 static cudaError_t launch_pair(int grid, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                                const CUtensorMap& tmRes, const IgemmParams& p, cudaStream_t s) {
+  if constexpr (BN == 256 && NS == 2) {   // gated dual-source conv: two 128-column accumulators per TMEM buffer
+    if (p.gate != nullptr && p.kb_split > 0) return launch_pair_g<BN, NS, true, true>(grid, tmA, tmB, tmOut, tmRes, p, s);
+  }
   if constexpr (NS * 64 == BN) {
-    if (p.gate != nullptr) return launch_pair_g<BN, NS, true>(grid, tmA, tmB, tmOut, tmRes, p, s);
+    if (p.kb_split == 0 && p.gate != nullptr) return launch_pair_g<BN, NS, true>(grid, tmA, tmB, tmOut, tmRes, p, s);
     if constexpr (BN == 256) {   // the dual-source producer is instantiated for the tile the bottleneck tails use
-      if (p.kb_split > 0) return launch_pair_g<BN, NS, false, true>(grid, tmA, tmB, tmOut, tmRes, p, s);
+      if (p.kb_split > 0 && p.gate == nullptr) return launch_pair_g<BN, NS, false, true>(grid, tmA, tmB, tmOut, tmRes, p, s);
     }
   }
   if (p.gate != nullptr || p.kb_split > 0) return cudaErrorInvalidValue;   // igemm_make keeps such layers on full-width 256 tiles

@@ -28,6 +28,7 @@ struct IgemmParams {
   float act_a;                 // PCV_ACT_LEAKY_RELU: negative slope
   const float* gate;           // PCV_CONV_SE_GATE (pair kernel): fp32 [images][Cout], multiplies (acc + bias) before the residual
   int n_img;                   // images (rows of `gate`)
+  const float* bias2;          // gated dual-source conv: the shortcut conv's own folded bias (added outside the gate)
   int kb_split;                // dual-source 1x1 (pcv_conv1x1_dual): k-blocks >= kb_split read the SECOND activation (the tensor
   int a_mode2, stride2;        // map in the residual slot; its 1x1 conv may be strided), weights are K-concatenated
   int a_mode;                 // 0: 2-D tiled [Cin, M]; 1: im2col 4-D

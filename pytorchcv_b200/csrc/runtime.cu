@@ -294,8 +294,26 @@ int pcv_conv1x1_dual(pcv_plan* plan, const pcv_conv_desc* d, const pcv_conv_desc
   PCV_REQUIRE(x && x2 && w_cat_packed && bias_sum && y, "NULL tensor pointer");
   PCV_REQUIRE(pcv_conv1x1_dual_ok(d, d2, dtype), "layer pair outside the dual-source kernel's domain (ask pcv_conv1x1_dual_ok)");
   Op* op = nullptr;
-  const IgemmDual dual{d2, x2};
+  PCV_REQUIRE(!(d->flags & PCV_CONV_SE_GATE), "gated unit: use pcv_conv1x1_dual_se");
+  const IgemmDual dual{d2, x2, nullptr};
   const int rc = (dtype == PCV_F16 ? hf::igemm_make : bf::igemm_make)(*d, x, w_cat_packed, bias_sum, nullptr, y, &op, nullptr, &dual);
+  if (rc) return rc;
+  return submit(plan, op, static_cast<cudaStream_t>(stream));
+}
+
+int pcv_conv1x1_dual_se(pcv_plan* plan, const pcv_conv_desc* d, const pcv_conv_desc* d2, int dtype, const void* x, const void* x2,
+                        const void* w_cat_packed, const float* bias, const float* bias2, const float* gate, void* y,
+                        pcv_stream stream) {
+  if (int rc = validate_conv(d, dtype)) return rc;
+  if (int rc = validate_conv(d2, dtype)) return rc;
+  PCV_REQUIRE(is16(dtype), "the dual-source 1x1 conv exists in the 16-bit tiers only");
+  PCV_REQUIRE(x && x2 && w_cat_packed && bias && bias2 && gate && y, "NULL tensor pointer");
+  PCV_REQUIRE((d->flags & PCV_CONV_SE_GATE) && pcv_conv1x1_dual_ok(d, d2, dtype),
+              "layer pair outside the gated dual-source kernel's domain (PCV_CONV_SE_GATE on d, ask pcv_conv1x1_dual_ok)");
+  PCV_REQUIRE(reinterpret_cast<uintptr_t>(gate) % 16 == 0, "the SE gate must be 16-byte aligned");
+  Op* op = nullptr;
+  const IgemmDual dual{d2, x2, bias2};
+  const int rc = (dtype == PCV_F16 ? hf::igemm_make : bf::igemm_make)(*d, x, w_cat_packed, bias, nullptr, y, &op, gate, &dual);
   if (rc) return rc;
   return submit(plan, op, static_cast<cudaStream_t>(stream));
 }

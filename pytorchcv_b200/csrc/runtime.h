@@ -118,6 +118,7 @@ EncodeIm2colFn encode_im2col_fn();
 struct IgemmDual {   // second source of a dual-source 1x1 conv (pcv_conv1x1_dual): y = act(W1 x1 + W2 x2[::s] + b)
   const pcv_conv_desc* d2;
   const void* x2;
+  const float* bias2;   // gated variant only (PCV_CONV_SE_GATE on the first desc): the shortcut's bias, added outside the gate
 };
 #define PCV_DECLARE_TIER_API(NS)                                                                                         \
   namespace NS {                                                                                                         \

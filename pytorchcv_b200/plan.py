@@ -403,11 +403,15 @@ class Builder:
         self.ops.append(emit)
         return out
 
-    def conv_dual(self, x: TRef, cb: nn.Module, x2: TRef, cb2: nn.Module, act: int) -> TRef | None:
+    def conv_dual(self, x: TRef, cb: nn.Module, x2: TRef, cb2: nn.Module, act: int, gate: TRef | None = None) -> TRef | None:
         """act(cb(x) + cb2(x2)) for two linear 1x1 ConvBlocks as ONE GEMM over K-concatenated operands (include/pcv_b200.h
         pcv_conv1x1_dual): a bottleneck's conv3 with the unit's projection shortcut folded in - the identity tensor is never
-        written.  None when the pair is outside that kernel's domain."""
+        written.  With `gate` (an SE unit): act(cb(x) * gate + cb2(x2)) (pcv_conv1x1_dual_se).  None when the pair is outside
+        that kernel's domain."""
         if not _DUAL_IDENTITY[0] or not _is16(self.dtype) or x.cmap is not None or x2.cmap is not None:
+            return None
+        if gate is not None and (x.H * x.W < _DUAL_GATE_MIN_HW[0] or gate.dtype != F32 or gate.cmap is not None
+                                 or gate.N != x.N or gate.C != cb.conv.out_channels):
             return None
         for m in (cb, cb2):
             c = getattr(m, "conv", None)
@@ -423,7 +427,7 @@ class Builder:
             return None
         cout = c1.out_channels
         d = ConvDesc(N=x.N, H=x.H, W=x.W, Cin=x.C, Cout=cout, kh=1, kw=1, stride=1, pad=0, dil=1, groups=1, act=act,
-                     in_pitch=x.pitch, out_pitch=cout, res_pitch=0, flags=0)
+                     in_pitch=x.pitch, out_pitch=cout, res_pitch=0, flags=_lib.CONV_SE_GATE if gate is not None else 0)
         d2 = ConvDesc(N=x2.N, H=x2.H, W=x2.W, Cin=x2.C, Cout=cout, kh=1, kw=1, stride=s2, pad=0, dil=1, groups=1,
                       act=ACT_NONE, in_pitch=x2.pitch, out_pitch=cout, res_pitch=0, flags=0)
         if not _lib.load().pcv_conv1x1_dual_ok(C.byref(d), C.byref(d2), self.dtype):
@@ -438,13 +442,18 @@ class Builder:
             _lib.call("pcv_conv_packed_bytes", C.byref(dd), self.dtype, C.byref(wb), C.byref(bb))
             sizes.append((wb.value, bb.value))
         w_off, b_off = self._wblob(sizes[0][0] + sizes[1][0]), self._wblob(sizes[0][1])
-        self.weight_jobs.append(("conv_dual", (d, cb, d2, cb2, sizes, w_off, b_off)))
-        self._use(x, x2, out)
+        b2_off = self._wblob(sizes[1][1]) if gate is not None else None   # gated: the shortcut's bias stays outside the gate
+        self.weight_jobs.append(("conv_dual", (d, cb, d2, cb2, sizes, w_off, b_off, b2_off)))
+        self._use(x, x2, out, gate)
         dtype = self.dtype
 
         def emit(plan, ptr, wptr):
-            _lib.call("pcv_conv1x1_dual", plan, C.byref(d), C.byref(d2), dtype, ptr(x), ptr(x2), wptr(w_off), wptr(b_off),
-                      ptr(out), None)
+            if gate is not None:
+                _lib.call("pcv_conv1x1_dual_se", plan, C.byref(d), C.byref(d2), dtype, ptr(x), ptr(x2), wptr(w_off),
+                          wptr(b_off), wptr(b2_off), ptr(gate), ptr(out), None)
+            else:
+                _lib.call("pcv_conv1x1_dual", plan, C.byref(d), C.byref(d2), dtype, ptr(x), ptr(x2), wptr(w_off),
+                          wptr(b_off), ptr(out), None)
         self.ops.append(emit)
         return out
 
@@ -1068,6 +1077,16 @@ def set_dual_identity(enabled: bool) -> None:
     _DUAL_IDENTITY[0] = bool(enabled)
 
 
+# the gated variant (SE units) runs 128-wide tiles with two accumulators: it pays on the bandwidth-bound early stages only
+# (SE-ResNeXt-50 bs256, identity conv + gated conv3 -> one op: @56x56 334 -> 234 us, @28x28 200 -> 193, @14x14 136 -> 140,
+# @7x7 123 -> 127), so the default takes it for output maps of >= 28 x 28
+_DUAL_GATE_MIN_HW = [int(os.environ.get("PCV_DUAL_GATE_MIN_HW", "784"))]
+
+
+def set_dual_gate_min_hw(pixels: int) -> None:
+    _DUAL_GATE_MIN_HW[0] = int(pixels)
+
+
 @lowers("ResUnit", "ResNeXtUnit")
 def _lower_resunit(b, m, x, **kw):
     """ResUnit.forward (resnet.py:221-229): act(body(x) + (identity_conv(x) | x)).
@@ -1131,18 +1150,27 @@ def _lower_seresnext_unit(b, m, x, **kw):
     is taken on that conv's INPUT: global mean commutes with the 1x1 conv + BN, whose weights fold into the first SE FC on
     the host.  The squeeze pass then reads the bottleneck width instead of the unit width (half the bytes in SE-ResNeXt,
     a quarter in SE-ResNet) and sees unrounded values of conv3's output."""
-    identity = lower(b, m.identity_conv, x) if m.resize_identity else x
     body, se = m.body, m.se
     folded = _fold_conv3_into_se(body.conv3, se) if hasattr(body, "conv3") else None
     if folded is None:
+        identity = lower(b, m.identity_conv, x) if m.resize_identity else x
         y = lower(b, body, x)
         return lower(b, se, y, identity=identity, post_act=act_code(m.activ))
+    # a projection shortcut that can ride on conv3 as the second half of its K dimension (Builder.conv_dual) is never computed
+    # on its own; otherwise it keeps its place in front of the body
+    dual = m.resize_identity and _SE_GATE_FUSE[0] and _DUAL_IDENTITY[0] and _is16(b.dtype)
+    identity = None if dual else (lower(b, m.identity_conv, x) if m.resize_identity else x)
     y2 = lower(b, body.conv2, lower(b, body.conv1, x))
     pooled = b.gap(y2, out_dtype=F32)
     _, _, w2, b2, mid_act, out_act = _se_parts(b, se)
     gate = b.se_gate(pooled, folded[0], folded[1], w2, b2, mid_act, out_act)
     # the gate exists BEFORE conv3 runs (it was squeezed from conv3's input), so the SE scale, the identity add and the unit's
     # activation ride on conv3's epilogue: conv3's output and the scale pass's read of it never touch HBM
+    if dual:
+        fused = b.conv_dual(y2, body.conv3, x, m.identity_conv, act_code(m.activ), gate=gate)
+        if fused is not None:
+            return fused
+        identity = lower(b, m.identity_conv, x)
     if _SE_GATE_FUSE[0]:
         c3 = body.conv3
         fused = b.conv(y2, c3.conv, c3.bn if c3.normalize else None, act_code(m.activ), residual=identity, gate=gate)
@@ -1836,7 +1864,7 @@ class CompiledModule:
 
     def _pack_dual(self, payload, keep, stream, wptr) -> None:
         """Weights of Builder.conv_dual: both 1x1 convs packed as usual, then joined row by row along K; biases summed."""
-        d, cb, d2, cb2, sizes, w_off, b_off = payload
+        d, cb, d2, cb2, sizes, w_off, b_off, b2_off = payload
         parts = []
         for dd, m, (wn, bn_) in ((d, cb, sizes[0]), (d2, cb2, sizes[1])):
             wt = torch.empty(wn, dtype=torch.uint8, device=self.device)
@@ -1844,12 +1872,15 @@ class CompiledModule:
             self._pack_one(dd, m.conv, m.bn if m.normalize else None, wt.data_ptr(), bt.data_ptr(), keep, stream)
             parts.append((wt.view(d.Cout, -1), bt))
         joined = torch.cat([parts[0][0], parts[1][0]], dim=1).contiguous().view(-1)
-        bias = (parts[0][1] + parts[1][1]).view(torch.uint8).view(-1)
-        keep += [joined, bias]
-        rel = wptr(w_off) - self.weights.data_ptr()
-        self.weights[rel:rel + joined.numel()].copy_(joined)
-        rel = wptr(b_off) - self.weights.data_ptr()
-        self.weights[rel:rel + bias.numel()].copy_(bias)
+        blobs = [(w_off, joined)]
+        if b2_off is None:
+            blobs.append((b_off, (parts[0][1] + parts[1][1]).view(torch.uint8).view(-1)))
+        else:
+            blobs += [(b_off, parts[0][1].view(torch.uint8).view(-1)), (b2_off, parts[1][1].view(torch.uint8).view(-1))]
+        for off, t in blobs:
+            keep.append(t)
+            rel = wptr(off) - self.weights.data_ptr()
+            self.weights[rel:rel + t.numel()].copy_(t)
 
     def _pack_mapped(self, payload, keep, stream, wptr) -> None:
         """Weights of a conv with virtual channel padding (Builder._conv_mapped): scatter into the storage channel space."""

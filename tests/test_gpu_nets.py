@@ -474,8 +474,11 @@ def test_batch_and_resolution_edges():
 @pytest.mark.parametrize("tier,tol", [("bf16", 2e-2), ("fp16", 4e-3)])
 @pytest.mark.parametrize("kind,cin,cout,stride,shape", [
     ("seresnext", 256, 256, 1, (3, 28, 28)),    # identity shortcut; 784 pixels per image: M tiles straddle image boundaries
-    ("seresnext", 256, 512, 2, (2, 28, 28)),    # projection shortcut, stride 2
-    ("seres", 64, 256, 1, (5, 19, 23)),         # SE-ResNet bottleneck, ragged map: 437 pixels per image
+    ("seresnext", 256, 512, 2, (2, 28, 28)),    # projection shortcut, stride 2: second accumulator (pcv_conv1x1_dual_se)
+    ("seres", 64, 256, 1, (5, 19, 23)),         # SE-ResNet bottleneck, ragged map: 437 pixels per image; stride-1 projection
+    ("seresnext", 64, 256, 1, (4, 56, 56)),     # SE-ResNeXt-50 stage 1: K = 128 + 64
+    ("seresnext", 1024, 2048, 2, (5, 14, 14)),  # stage 4: 49 pixels per image, 16 + 16 k-blocks, partial second M tile
+    ("seresnext", 136, 264, 2, (3, 20, 20)),    # widths off the 64 / 128 grids: clipped last N tile, zero-filled k-block tails
 ])
 def test_se_gate_in_conv3_epilogue(kind, cin, cout, stride, shape, tier, tol):
     """SEResNeXtUnit / SEResUnit (seresnext.py:57-66, seresnet.py:63-72) with the SE scale + identity + ReLU in the epilogue of
@@ -489,10 +492,16 @@ def test_se_gate_in_conv3_epilogue(kind, cin, cout, stride, shape, tier, tol):
     unit = seeded_init(unit.eval(), seed=11, randomize_bn=True)
     x = seeded_input((n, cin, h, w), seed=12)
     want = oracle_forward(unit, x)
-    fast = P.accelerate(copy.deepcopy(unit).cuda(), dtype=tier, graph=False)
-    got = fast(x.cuda()).float().cpu()
+    PL.set_dual_gate_min_hw(0)   # the default keeps the shortcut fusion for maps of >= 28 x 28: test it on every shape
+    try:
+        fast = P.accelerate(copy.deepcopy(unit).cuda(), dtype=tier, graph=False)
+        got = fast(x.cuda()).float().cpu()
+    finally:
+        PL.set_dual_gate_min_hw(784)
     names = [r[0] for r in fast.compiled(x.cuda()).profile()]
     assert any("*gate" in nm for nm in names) and not any(nm.startswith("se_scale") for nm in names), names
+    if cin != cout or stride != 1:   # the projection shortcut is the second half of the gated conv's K dimension
+        assert sum("*gate" in nm and "+1x1 s" in nm for nm in names) == 1 and not any("+res" in nm for nm in names), names
     PL.set_se_gate_fuse(False)
     try:
         base = P.accelerate(copy.deepcopy(unit).cuda(), dtype=tier, graph=False)

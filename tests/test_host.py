@@ -84,6 +84,8 @@ def test_dual_source_conv_domain():
         for tier in (BF16, F16):
             assert lib.pcv_conv1x1_dual_ok(ctypes.byref(d), ctypes.byref(d2), tier) == 1, (cin, cout, tier)
         assert lib.pcv_conv1x1_dual_ok(ctypes.byref(d), ctypes.byref(d2), F32) == 0
+        d.flags = _lib.CONV_SE_GATE   # the gated variant (SE units) shares the domain
+        assert lib.pcv_conv1x1_dual_ok(ctypes.byref(d), ctypes.byref(d2), BF16) == 1
     for bad in (pair(64, 32, 128, 1, 56),                       # Cout <= 128: not the 256-wide pair tile
                 pair(256, 128, 512, 2, 56, act=_lib.ACT_RELU),  # the shortcut conv must be linear
                 pair(256, 128, 512, 2, 56, N=128),              # different batch
@@ -146,7 +148,9 @@ def test_lowering_and_arena(name, shape, n_ops, tier):
     # stride-2 ones among them are ONE fused expansion -> dw -> pw op (-1 more each)
     n_fused = 16 if (name == "mobilenetv2_w1" and tier == BF16) else 0
     if name == "seresnext50_32x4d" and tier == BF16:
-        n_fused = 16   # the SE scale + identity + ReLU of all 16 units rides on conv3's epilogue (PCV_CONV_SE_GATE)
+        # the SE scale + identity + ReLU of all 16 units rides on conv3's epilogue (PCV_CONV_SE_GATE); the 4 projection shortcuts
+        # are the second half of that conv's K dimension (pcv_conv1x1_dual_se)
+        n_fused = 16 + 2   # (the gated variant is taken for output maps of >= 28 x 28: stages 1 and 2)
     if name in ("resnet50", "deeplabv3_resnetd50b_voc") and tier == BF16:
         n_fused = 4    # the 4 projection shortcuts are K-concatenated into their units' conv3 (pcv_conv1x1_dual)
     assert len(b.ops) + sum(t.tail is not None for t in trefs) == n_ops - n_fused
