@@ -175,3 +175,46 @@ def test_reference_modules_lower_without_mirror(reference_pkg):
     # 53 convs + maxpool + global pool + fc, minus the projection shortcuts of stages 1-3 folded into their units' conv3
     # (pcv_conv1x1_dual; stage 4 at batch 2 is a single 128-row tile, outside the CTA-pair kernel's domain)
     assert len(b.ops) == 53
+
+
+def _fold_1x1(cb):
+    """A linear 1x1 ConvBlock (conv + eval-mode BatchNorm, conv.py:278-286) as (W', b') in float64."""
+    c, bn = cb.conv, cb.bn
+    w = c.weight.detach().double().view(c.out_channels, c.in_channels)
+    b = c.bias.detach().double() if c.bias is not None else torch.zeros(c.out_channels, dtype=torch.float64)
+    sc = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+    return w * sc[:, None], (b - bn.running_mean.detach().double()) * sc + bn.bias.detach().double()
+
+
+@pytest.mark.parametrize("kind,cin,cout,stride", [("res", 64, 256, 1), ("res", 256, 512, 2), ("resnext", 72, 264, 2),
+                                                  ("seresnext", 64, 256, 1), ("seresnext", 136, 264, 2)])
+def test_projection_shortcut_is_the_second_half_of_conv3s_k_dimension(kind, cin, cout, stride):
+    """The identity the dual-source conv (pcv_conv1x1_dual / _se) computes, checked against the oracle in float64:
+    act(conv3(y2) + identity_conv(x)) == act([W3 | Wid] . [y2 ; x[::s]] + b3 + bid)  (ResUnit, resnet.py:221-229) and, with the
+    SE gate g squeezed from conv3's output, act((W3 y2 + b3) g + Wid x[::s] + bid)  (SEResNeXtUnit, seresnext.py:57-66)."""
+    if kind == "res":
+        unit = M.ResUnit(cin, cout, stride=stride, bottleneck=True, conv1_stride=False)
+    elif kind == "resnext":
+        unit = M.ResNeXtUnit(cin, cout, stride=stride, cardinality=32, bottleneck_width=4)
+    else:
+        unit = M.SEResNeXtUnit(cin, cout, stride=stride, cardinality=32, bottleneck_width=4)
+    unit = seeded_init(unit.eval(), seed=31, randomize_bn=True).double()
+    x = seeded_input((3, cin, 13, 11), seed=32).double()
+    with torch.no_grad():
+        want = oracle_forward(unit, x)
+        y2 = oracle_forward(unit.body.conv2, oracle_forward(unit.body.conv1, x))
+        (w3, b3), (wid, bid) = _fold_1x1(unit.body.conv3), _fold_1x1(unit.identity_conv)
+        xs = x[:, :, ::stride, ::stride]
+        assert xs.shape[2:] == y2.shape[2:]
+        if kind == "seresnext":
+            main = torch.einsum("oc,nchw->nohw", w3, y2) + b3[None, :, None, None]
+            # SEBlock.forward returns x * w (att.py:99-105): recover w, one value per (image, channel)
+            gate = (oracle_forward(unit.se, main) * main).sum((2, 3)) / (main * main).sum((2, 3))
+            got = main * gate[:, :, None, None] + torch.einsum("oc,nchw->nohw", wid, xs) + bid[None, :, None, None]
+        else:
+            a = torch.cat([y2, xs], dim=1)                       # [y2 ; x[::s]] along K
+            w = torch.cat([w3, wid], dim=1)                      # [W3 | Wid]
+            got = torch.einsum("ok,nkhw->nohw", w, a) + (b3 + bid)[None, :, None, None]
+        got = torch.relu(got)
+    assert got.shape == want.shape
+    assert float((got - want).abs().max() / want.abs().max()) <= 1e-10
